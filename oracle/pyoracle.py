@@ -1,0 +1,254 @@
+"""TEST INFRASTRUCTURE — ctypes binding of oracle/libtribs_oracle.so (the plain-C CPU
+restatement) plus a tiny driver that steps it exactly like the reference's time loop
+(reference: src/tSimulator/tSimul.cpp:248-293, 386-406, 506-520).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline leg import this module.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB = os.path.join(HERE, "libtribs_oracle.so")
+HDR = os.path.join(HERE, "tribs_oracle.h")
+
+
+def _xlist(macro: str) -> list[str]:
+    src = open(HDR).read()
+    m = re.search(r"#define\s+" + macro + r"\(X\)\s*\\?\n?((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
+STATIC_F64 = _xlist("ORC_STATIC_F64")
+STATIC_I32 = _xlist("ORC_STATIC_I32")
+EDGE_F64 = _xlist("ORC_EDGE_F64")
+EDGE_I32 = _xlist("ORC_EDGE_I32")
+STATE_F64 = _xlist("ORC_STATE_F64")
+GLOBALS = _xlist("ORC_GLOBALS")
+RESULTS = _xlist("ORC_RESULTS")
+
+PD = C.POINTER(C.c_double)
+PI = C.POINTER(C.c_int32)
+
+
+class Basin(C.Structure):
+    _fields_ = [
+        ("n", C.c_int32), ("n_edges", C.c_int32),
+        ("sf", PD * len(STATIC_F64)), ("si", PI * len(STATIC_I32)),
+        ("nbr_rowptr", PI),
+        ("ef", PD * len(EDGE_F64)), ("ei", PI * len(EDGE_I32)),
+        ("BasArea", C.c_double), ("BasArea_flow", C.c_double), ("IntStormMAX", C.c_double),
+        ("surfaceSoilDepth", C.c_double), ("rootZoneDepth", C.c_double),
+        ("EToption", C.c_int32), ("Ioption", C.c_int32), ("SnOpt", C.c_int32), ("RdstrOption", C.c_int32),
+        ("velcoef", C.c_double), ("velratio", C.c_double), ("flowexp", C.c_double),
+        ("baseflow", C.c_double), ("kincoef", C.c_double), ("dtReff", C.c_double), ("hillvel0", C.c_double),
+        ("outlet_node", C.c_int32), ("outlet_contr_area", C.c_double),
+        ("tstep", C.c_double), ("gwstep", C.c_double), ("etistep", C.c_double), ("output_interval", C.c_double),
+    ]
+
+
+class State(C.Structure):
+    _fields_ = [("f", PD * len(STATE_F64)), ("glob", C.c_double * len(GLOBALS))]
+
+
+class Stack(C.Structure):
+    _fields_ = [("n", C.c_int32), ("cap", C.c_int32), ("tind", PI), ("q", PD)]
+
+
+class Results(C.Structure):
+    _fields_ = [("limit", C.c_int32), ("a", PD * len(RESULTS)), ("stacks", C.POINTER(Stack))]
+
+
+def build(force: bool = False) -> str:
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "tribs_oracle.c")):
+        subprocess.check_call(["make", "-C", HERE, "port"], stdout=subprocess.DEVNULL)
+    return LIB
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        build()
+        L = C.CDLL(LIB)
+        L.orc_unsat.argtypes = [C.POINTER(Basin), C.POINTER(State), C.c_double, C.c_double]
+        L.orc_reset_gw.argtypes = [C.POINTER(Basin), C.POINTER(State)]
+        L.orc_sat.argtypes = [C.POINTER(Basin), C.POINTER(State), C.c_double, C.c_double]
+        L.orc_route.argtypes = [C.POINTER(Basin), C.POINTER(State), C.POINTER(Results), C.c_double]
+        L.orc_reset.argtypes = [C.POINTER(Basin), C.POINTER(State)]
+        L.orc_retrieve_qeff.argtypes = [C.POINTER(Basin), C.POINTER(Results), C.c_double, PD]
+        L.orc_state_counts.argtypes = [C.POINTER(C.c_longlong), C.c_int]
+        for nm, nargs in (("lambertw", 1),):
+            getattr(L, "orc_kat_" + nm).restype = C.c_double
+            getattr(L, "orc_kat_" + nm).argtypes = [C.c_double] * nargs
+        for nm, nargs in (("total_moist", 1), ("upper_moist", 2), ("lower_moist", 2), ("newton1", 2),
+                          ("recharge", 2), ("unsat_lat", 3), ("sat_lat", 4), ("z1z2", 3)):
+            fn = getattr(L, "orc_kat_" + nm)
+            fn.restype = C.c_double
+            fn.argtypes = [PD] + [C.c_double] * nargs
+        L.orc_kat_newton2.restype = C.c_double
+        L.orc_kat_newton2.argtypes = [PD, C.c_double, C.c_double, C.c_double, C.c_int]
+        L.orc_sizes.restype = C.c_int
+        L.orc_sizes.argtypes = [C.c_int]
+        assert [L.orc_sizes(k) for k in range(7)] == [len(x) for x in (
+            STATIC_F64, STATIC_I32, EDGE_F64, EDGE_I32, STATE_F64, GLOBALS, RESULTS)]
+        assert L.orc_sizes(99) == C.sizeof(Basin)
+        _lib = L
+    return _lib
+
+
+# basin.trb name -> oracle name where they differ
+_BASIN_ALIAS = {
+    "nbr_len": "spoke_len", "nbr_vedglen": "spoke_vedglen", "nbr_len_in": "spoke_compl_len",
+    "nbr_vedglen_in": "spoke_compl_vedglen", "nbr_col": "spoke_nbr", "nbr_listpos": "spoke_edge_listpos",
+}
+
+
+def _pd(a):
+    return a.ctypes.data_as(PD)
+
+
+def _pi(a):
+    return a.ctypes.data_as(PI)
+
+
+class OracleModel:
+    """Steps the C oracle over a flattened basin (dict as read from basin.trb)."""
+
+    def __init__(self, basin: dict, rain_schedule=None):
+        self.L = lib()
+        b = basin
+        self.n = n = int(b["n_active"][0])
+        self.keep = {}
+        B = Basin()
+        B.n = n
+        rp = np.ascontiguousarray(b["spoke_rowptr"], np.int32)
+        B.n_edges = int(rp[-1])
+        self.keep["rowptr"] = rp
+        B.nbr_rowptr = _pi(rp)
+        for k, nm in enumerate(STATIC_F64):
+            a = np.ascontiguousarray(b[nm], np.float64); self.keep["sf" + nm] = a; B.sf[k] = _pd(a)
+        for k, nm in enumerate(STATIC_I32):
+            a = np.ascontiguousarray(b[nm], np.int32); self.keep["si" + nm] = a; B.si[k] = _pi(a)
+        for k, nm in enumerate(EDGE_F64):
+            a = np.ascontiguousarray(b[_BASIN_ALIAS[nm]], np.float64); self.keep["ef" + nm] = a; B.ef[k] = _pd(a)
+        for k, nm in enumerate(EDGE_I32):
+            a = np.ascontiguousarray(b[_BASIN_ALIAS[nm]], np.int32); self.keep["ei" + nm] = a; B.ei[k] = _pi(a)
+        sc = lambda k: float(b[k][0])
+        B.BasArea = sc("BasArea"); B.BasArea_flow = sc("BasArea_flow"); B.IntStormMAX = sc("IntStormMAX")
+        B.surfaceSoilDepth = sc("surfaceSoilDepth"); B.rootZoneDepth = sc("rootZoneDepth")
+        B.EToption = int(b["EToption"][0]); B.Ioption = int(b["Ioption"][0])
+        B.SnOpt = int(b["SnOpt"][0]); B.RdstrOption = int(b["RdstrOption"][0])
+        B.velcoef = sc("velcoef"); B.velratio = sc("velratio"); B.flowexp = sc("flowexp")
+        B.baseflow = sc("baseflow"); B.kincoef = sc("kincoef"); B.dtReff = sc("dtReff"); B.hillvel0 = sc("hillvel")
+        B.outlet_node = int(b["outlet_stream_node"][0]); B.outlet_contr_area = sc("outlet_contr_area")
+        B.tstep = sc("tstep"); B.gwstep = sc("gwstep"); B.etistep = sc("etistep")
+        B.output_interval = sc("output_interval")
+        self.B = B
+        self.gw_on = int(b["GW_model_label"][0]) != 0
+        self.endtime = sc("endtime")
+
+        S = State()
+        self.state = {}
+        for k, nm in enumerate(STATE_F64):
+            src = "init_" + nm
+            if nm == "TTime":
+                a = np.array(b["ttime"], np.float64)
+            elif src in b:
+                a = np.array(b[src], np.float64)
+            else:
+                a = np.zeros(n)
+            self.state[nm] = a
+            S.f[k] = _pd(a)
+        self.S = S
+        self.glob = np.ctypeslib.as_array(S.glob)
+
+        R = Results()
+        R.limit = int(b["res_limit"][0])
+        self.res = {}
+        for k, nm in enumerate(RESULTS):
+            a = np.zeros(R.limit)
+            if nm == "rmin":
+                a[:] = 9999.99
+            self.res[nm] = a
+            R.a[k] = _pd(a)
+        self.stacks = (Stack * (n + 1))()
+        R.stacks = C.cast(self.stacks, C.POINTER(Stack))
+        self.R = R
+        self.time = 0.0
+        self.step_no = 0
+        self.rain_schedule = rain_schedule
+
+    # -- phases -------------------------------------------------------------------
+    def advance(self):
+        self.time += self.B.tstep
+        self.step_no += 1
+        if self.rain_schedule is not None:
+            self.state["Rain"][:] = self.rain_schedule(self.time)
+
+    def unsat(self):
+        self.L.orc_unsat(C.byref(self.B), C.byref(self.S), self.B.tstep, self.time)
+
+    def gw_due(self) -> bool:
+        return self.gw_on and math.fmod(self.time, self.B.gwstep) == 0.0
+
+    def sat(self):
+        self.L.orc_reset_gw(C.byref(self.B), C.byref(self.S))
+        self.L.orc_sat(C.byref(self.B), C.byref(self.S), self.B.gwstep, self.time)
+
+    def route(self):
+        self.L.orc_route(C.byref(self.B), C.byref(self.S), C.byref(self.R), self.time)
+
+    def retrieve_qeff(self):
+        out = np.zeros(self.n + 1)
+        self.L.orc_retrieve_qeff(C.byref(self.B), C.byref(self.R), self.time, _pd(out))
+        return out
+
+    def state_counts(self, reset=False):
+        out = (C.c_longlong * 16)()
+        self.L.orc_state_counts(out, int(reset))
+        return list(out)
+
+    def reset(self):
+        self.L.orc_reset(C.byref(self.B), C.byref(self.S))
+
+    def step(self):
+        self.advance()
+        self.unsat()
+        if self.gw_due():
+            self.sat()
+        self.route()
+        self.retrieve_qeff()
+        self.reset()
+
+    def stack_of(self, i):
+        st = self.stacks[i]
+        return ([st.tind[k] for k in range(st.n)], [st.q[k] for k in range(st.n)])
+
+
+def stochastic_storm_schedule(pmean: float, stdur: float, istdur: float):
+    """Rain rate seen by the cells under STOCHASTICMODE 1 (mean values, no sampling).
+    One storm of PMEAN for STDUR hours; the rate is then set to 0 during the interstorm
+    (tSimul.cpp:398-399) and, because tStorm::GenerateStorm leaves `p` untouched in mode 1
+    (tStorm.cpp:228-242), every later "storm" rains 0 — the reference's actual behaviour.
+    (reference: src/tSimulator/tSimul.cpp:386-406, tRunTimer::UpdateStorm tRunTimer.cpp:559)"""
+    state = {"storm_time": stdur + istdur, "rate": pmean}
+
+    def rain(t):
+        if t <= state["storm_time"] - istdur:
+            return state["rate"]
+        if t <= state["storm_time"]:
+            state["rate"] = 0.0
+            return 0.0
+        state["storm_time"] += stdur + istdur
+        return state["rate"]
+
+    return rain

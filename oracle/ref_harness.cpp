@@ -1,0 +1,617 @@
+// TEST INFRASTRUCTURE — NOT PRODUCT CODE.
+//
+// Reference harness: links the *unmodified* reference sources where they lie under
+// /root/reference (see oracle/Makefile; nothing is copied into this repo), wires the same
+// objects the reference's serialSimulation() wires (reference: src/main.cpp:64-155), and
+// runs the reference's own time loop (reference: src/tSimulator/tSimul.cpp:248-293) one
+// call at a time so that raw FP64 state can be dumped between phases. Text outputs of the
+// reference carry only 4-7 significant digits, so this is the only way to pin 1e-6
+// relative parity.
+//
+// Outputs (all under --out DIR, container format "TRBDUMP1", see tribs_b200/trb.py):
+//   basin.trb  flattened mesh / parameters / initial state in sweep (list) order
+//   steps.trb  per-step, per-phase snapshots of the hot-path tCNode fields + global sums
+//   kat.trb    known-answer vectors of the reference's scalar helper functions
+//   timing: one JSON line on stdout ("ref_timing")
+//
+// Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference leg
+// may execute the binary built from this file.
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <cmath>
+#include <cstdint>
+#include <string>
+#include <vector>
+#include <list>
+#include <unordered_map>
+#include <iostream>
+#include <fstream>
+#include <sstream>
+#include <chrono>
+#include <memory>
+#include <algorithm>
+#include <iomanip>
+
+// The harness needs to read a handful of private accumulators (Stok, TotRain, psrf ...).
+// Access specifiers do not change the object layout g++ produces, and the reference
+// translation units are compiled untouched.
+#define private public
+#define protected public
+#include "src/Headers/globalIO.h"
+#include "Headers/Inclusions.h"
+#include "src/Mathutil/predicates.h"
+#include "src/tFlowNet/tKinemat.h"
+#include "tFlowNet/tReservoir.h"
+#include "src/tRasTin/tRainfall.h"
+#include "src/tRasTin/tShelter.h"
+#include "src/tSimulator/tSimul.h"
+#include "src/Headers/TemplDefinitions.h"
+#include "src/tHydro/tSnowPack.h"
+#include "src/tFlowNet/tFlowResults.h"
+#undef private
+#undef protected
+
+using namespace std;
+
+Predicates predicate;
+tOstream Cout(cout);
+tOstream Cerr(cerr);
+
+// ---------------------------------------------------------------------------------
+// TRBDUMP1 writer
+// ---------------------------------------------------------------------------------
+struct TrbWriter {
+    FILE *f = nullptr;
+    explicit TrbWriter(const string &path) {
+        f = fopen(path.c_str(), "wb");
+        if (!f) { fprintf(stderr, "cannot open %s\n", path.c_str()); exit(3); }
+        fwrite("TRBDUMP1", 1, 8, f);
+    }
+    ~TrbWriter() { if (f) fclose(f); }
+    void rec(const string &name, int dtype, int64_t n, const void *p, size_t esz) {
+        char nm[48]; memset(nm, 0, sizeof nm);
+        strncpy(nm, name.c_str(), 47);
+        fwrite(nm, 1, 48, f);
+        int32_t dt = dtype; fwrite(&dt, 4, 1, f);
+        int32_t pad = 0;    fwrite(&pad, 4, 1, f);
+        fwrite(&n, 8, 1, f);
+        if (n) fwrite(p, esz, (size_t)n, f);
+    }
+    void f64(const string &name, const vector<double> &v) { rec(name, 0, (int64_t)v.size(), v.data(), 8); }
+    void i32(const string &name, const vector<int32_t> &v) { rec(name, 1, (int64_t)v.size(), v.data(), 4); }
+    void f64s(const string &name, double v) { rec(name, 0, 1, &v, 8); }
+    void i32s(const string &name, int32_t v) { rec(name, 1, 1, &v, 4); }
+};
+
+// ---------------------------------------------------------------------------------
+struct Harness {
+    tMesh<tCNode> *mesh;
+    tKinemat *flow;
+    tHydroModel *hydro;
+    tRunTimer *timer;
+    vector<tCNode*> cells;                    // active cells in list (sweep) order
+    unordered_map<tNode*, int> pos;           // node -> index in cells
+
+    void index() {
+        tMeshListIter<tCNode> it(mesh->getNodeList());
+        tCNode *cn;
+        for (cn = it.FirstP(); it.IsActive(); cn = it.NextP()) {
+            pos[(tNode*)cn] = (int)cells.size();
+            cells.push_back(cn);
+        }
+    }
+    int idx(tNode *n) const {
+        auto k = pos.find(n);
+        return k == pos.end() ? -1 : k->second;
+    }
+
+    template <class F> vector<double> col(F fn) {
+        vector<double> v(cells.size());
+        for (size_t i = 0; i < cells.size(); i++) v[i] = fn(cells[i]);
+        return v;
+    }
+    template <class F> vector<int32_t> icol(F fn) {
+        vector<int32_t> v(cells.size());
+        for (size_t i = 0; i < cells.size(); i++) v[i] = fn(cells[i]);
+        return v;
+    }
+
+    // -------------------------------------------------------------- static basin
+    void dump_basin(const string &path, tInputFile &inf) {
+        TrbWriter w(path);
+        int N = (int)cells.size();
+        w.i32s("n_active", N);
+        w.i32s("n_nodes_total", mesh->getNodeList()->getSize());
+        w.i32("id", icol([](tCNode *c) { return c->getID(); }));
+        w.i32("boundary", icol([](tCNode *c) { return c->getBoundaryFlag(); }));
+        w.f64("x", col([](tCNode *c) { return c->getX(); }));
+        w.f64("y", col([](tCNode *c) { return c->getY(); }));
+        w.f64("z", col([](tCNode *c) { return c->getZ(); }));
+        w.f64("varea", col([](tCNode *c) { return c->getVArea(); }));
+        w.f64("bedrock", col([](tCNode *c) { return c->getBedrockDepth(); }));
+        w.f64("flow_slope", col([](tCNode *c) { return c->getFlowEdg()->getSlope(); }));
+        w.f64("flow_len", col([](tCNode *c) { return c->getFlowEdg()->getLength(); }));
+        w.f64("flow_vedglen", col([](tCNode *c) { return c->getFlowEdg()->getVEdgLen(); }));
+        w.i32("flow_dest", icol([this](tCNode *c) { return idx(c->getFlowEdg()->getDestinationPtrNC()); }));
+        w.i32("flow_edge_id", icol([](tCNode *c) { return c->getFlowEdg()->getID(); }));
+        w.i32("stream_node", icol([this](tCNode *c) { return c->getStreamNode() ? idx((tNode*)c->getStreamNode()) : -1; }));
+        w.f64("hillpath", col([](tCNode *c) { return c->getHillPath(); }));
+        w.f64("streampath", col([](tCNode *c) { return c->getStreamPath(); }));
+        w.f64("ttime", col([](tCNode *c) { return c->getTTime(); }));
+        w.f64("contr_area", col([](tCNode *c) { return c->getContrArea(); }));
+        w.i32("reach", icol([](tCNode *c) { return c->getReach(); }));
+        w.i32("soil_id", icol([](tCNode *c) { return c->getSoilID(); }));
+        w.i32("land_use", icol([](tCNode *c) { return c->getLandUse(); }));
+        w.f64("aspect", col([](tCNode *c) { return c->getAspect(); }));
+        // soil
+        w.f64("Ks", col([](tCNode *c) { return c->getKs(); }));
+        w.f64("ThetaS", col([](tCNode *c) { return c->getThetaS(); }));
+        w.f64("ThetaR", col([](tCNode *c) { return c->getThetaR(); }));
+        w.f64("PoreSize", col([](tCNode *c) { return c->getPoreSize(); }));
+        w.f64("AirEBubPres", col([](tCNode *c) { return c->getAirEBubPres(); }));
+        w.f64("DecayF", col([](tCNode *c) { return c->getDecayF(); }));
+        w.f64("SatAnRatio", col([](tCNode *c) { return c->getSatAnRatio(); }));
+        w.f64("UnsatAnRatio", col([](tCNode *c) { return c->getUnsatAnRatio(); }));
+        w.f64("Porosity", col([](tCNode *c) { return c->getPorosity(); }));
+        w.f64("VolHeatCond", col([](tCNode *c) { return c->getVolHeatCond(); }));
+        w.f64("SoilHeatCap", col([](tCNode *c) { return c->getSoilHeatCap(); }));
+        w.f64("soil_cutoff", col([](tCNode *c) { return c->getSoilCutoff(); }));
+        w.f64("root_cutoff", col([](tCNode *c) { return c->getRootCutoff(); }));
+        // land
+        w.f64("CanStorParam", col([](tCNode *c) { return c->getCanStorParam(); }));
+        w.f64("IntercepCoeff", col([](tCNode *c) { return c->getIntercepCoeff(); }));
+        w.f64("ThroughFall", col([](tCNode *c) { return c->getThroughFall(); }));
+        w.f64("CanFieldCap", col([](tCNode *c) { return c->getCanFieldCap(); }));
+        w.f64("DrainCoeff", col([](tCNode *c) { return c->getDrainCoeff(); }));
+        w.f64("DrainExpPar", col([](tCNode *c) { return c->getDrainExpPar(); }));
+        w.f64("LandUseAlb", col([](tCNode *c) { return c->getLandUseAlb(); }));
+        w.f64("VegHeight", col([](tCNode *c) { return c->getVegHeight(); }));
+        w.f64("OptTransmCoeff", col([](tCNode *c) { return c->getOptTransmCoeff(); }));
+        w.f64("StomRes", col([](tCNode *c) { return c->getStomRes(); }));
+        w.f64("VegFraction", col([](tCNode *c) { return c->getVegFraction(); }));
+        w.f64("LeafAI", col([](tCNode *c) { return c->getLeafAI(); }));
+
+        // Voronoi spokes in CCW order starting at getEdg() -> CSR over active cells.
+        vector<int32_t> rowptr(N + 1, 0), nbr, eid, cid;
+        vector<double> elen, evl, clen, cvl;
+        // edge-list position of every active directed edge (list order = flux loop order,
+        // reference: tHydroModel.cpp:2675)
+        unordered_map<tEdge*, int> epos;
+        {
+            tMeshListIter<tEdge> eit(mesh->getEdgeList());
+            tEdge *ce; int k = 0;
+            for (ce = eit.FirstP(); eit.IsActive(); ce = eit.NextP()) epos[ce] = k++;
+            w.i32s("n_active_edges", k);
+        }
+        vector<int32_t> elistpos;
+        for (int i = 0; i < N; i++) {
+            tEdge *first = cells[i]->getEdg();
+            tEdge *e = first;
+            int guard = 0;
+            do {
+                nbr.push_back(idx(e->getDestinationPtrNC()));
+                eid.push_back(e->getID());
+                elen.push_back(e->getLength());
+                evl.push_back(e->getVEdgLen());
+                auto ep = epos.find(e);
+                elistpos.push_back(ep == epos.end() ? -1 : ep->second);
+                tEdge *c = e->FindComplement();
+                cid.push_back(c ? c->getID() : -1);
+                clen.push_back(c ? c->getLength() : 0.0);
+                cvl.push_back(c ? c->getVEdgLen() : 0.0);
+                e = e->getCCWEdg();
+            } while (e != first && ++guard < 1000);
+            rowptr[i + 1] = (int32_t)nbr.size();
+        }
+        w.i32("spoke_rowptr", rowptr);
+        w.i32("spoke_nbr", nbr);
+        w.i32("spoke_edge_id", eid);
+        w.i32("spoke_edge_listpos", elistpos);
+        w.f64("spoke_len", elen);
+        w.f64("spoke_vedglen", evl);
+        w.i32("spoke_compl_id", cid);
+        w.f64("spoke_compl_len", clen);
+        w.f64("spoke_compl_vedglen", cvl);
+
+        // active directed edge list (orig, dest) in list order
+        {
+            tMeshListIter<tEdge> eit(mesh->getEdgeList());
+            tEdge *ce;
+            vector<int32_t> eo, ed, eids;
+            for (ce = eit.FirstP(); eit.IsActive(); ce = eit.NextP()) {
+                eo.push_back(idx(ce->getOriginPtrNC()));
+                ed.push_back(idx(ce->getDestinationPtrNC()));
+                eids.push_back(ce->getID());
+            }
+            w.i32("edge_org", eo);
+            w.i32("edge_dest", ed);
+            w.i32("edge_id", eids);
+        }
+
+        // flow-net / routing scalars
+        w.f64s("hillvel", flow->hillvel);
+        w.f64s("streamvel", flow->streamvel);
+        w.f64s("velratio", flow->velratio);
+        w.f64s("velcoef", flow->velcoef);
+        w.f64s("flowexp", flow->flowexp);
+        w.f64s("baseflow", flow->baseflow);
+        w.f64s("kincoef", flow->kincoef);
+        w.f64s("dtReff", flow->dtReff);
+        w.f64s("BasArea_flow", flow->BasArea);
+        w.f64s("maxttime", flow->maxttime);
+        w.i32s("outlet_stream_node", idx((tNode*)flow->OutletNode));
+        w.f64s("outlet_contr_area", flow->OutletNode->getContrArea());
+        w.i32s("res_limit", flow->res->limit);
+        // reach lists
+        {
+            vector<int32_t> heads, outs, nn;
+            tPtrListIter<tCNode> hi(flow->NodesLstH), oi(flow->NodesLstO);
+            tCNode *c;
+            for (c = hi.FirstP(); !hi.AtEnd(); c = hi.NextP()) heads.push_back(idx((tNode*)c));
+            for (c = oi.FirstP(); !oi.AtEnd(); c = oi.NextP()) outs.push_back(idx((tNode*)c));
+            tListNode<int> *p = flow->NNodes.getFirst();
+            for (int k = 0; k < flow->NNodes.getSize(); k++, p = p->getNextNC()) nn.push_back(p->getDataNC());
+            w.i32("reach_head", heads);
+            w.i32("reach_outlet", outs);
+            w.i32("reach_nnodes", nn);
+        }
+        // hydro model scalars / options
+        w.f64s("BasArea", hydro->BasArea);
+        w.f64s("IntStormMAX", hydro->IntStormMAX);
+        w.f64s("surfaceSoilDepth", hydro->surfaceSoilDepth);
+        w.f64s("rootZoneDepth", hydro->rootZoneDepth);
+        w.i32s("EToption", hydro->EToption);
+        w.i32s("Ioption", hydro->Ioption);
+        w.i32s("SnOpt", hydro->SnOpt);
+        w.i32s("RunOnoption", hydro->RunOnoption);
+        w.i32s("RdstrOption", hydro->RdstrOption);
+        w.i32s("GW_model_label", (int)hydro->simCtrl->GW_model_label);
+        // timer
+        w.f64s("tstep", timer->getTimeStep());
+        w.f64s("gwstep", timer->getGWTimeStep());
+        w.f64s("metstep", timer->getMetStep());
+        w.f64s("etistep", timer->getEtIStep());
+        w.f64s("endtime", timer->getEndTime());
+        w.f64s("output_interval", timer->getOutputInterval());
+        dump_state(w, "init_", true);
+    }
+
+    // -------------------------------------------------------------- dynamic state
+    void dump_state(TrbWriter &w, const string &pre, bool with_old) {
+        w.f64(pre + "NwtNew", col([](tCNode *c) { return c->getNwtNew(); }));
+        w.f64(pre + "MuNew", col([](tCNode *c) { return c->getMuNew(); }));
+        w.f64(pre + "MiNew", col([](tCNode *c) { return c->getMiNew(); }));
+        w.f64(pre + "NtNew", col([](tCNode *c) { return c->getNtNew(); }));
+        w.f64(pre + "NfNew", col([](tCNode *c) { return c->getNfNew(); }));
+        w.f64(pre + "RuNew", col([](tCNode *c) { return c->getRuNew(); }));
+        w.f64(pre + "RiNew", col([](tCNode *c) { return c->getRiNew(); }));
+        if (with_old) {
+            w.f64(pre + "NwtOld", col([](tCNode *c) { return c->getNwtOld(); }));
+            w.f64(pre + "MuOld", col([](tCNode *c) { return c->getMuOld(); }));
+            w.f64(pre + "MiOld", col([](tCNode *c) { return c->getMiOld(); }));
+            w.f64(pre + "NtOld", col([](tCNode *c) { return c->getNtOld(); }));
+            w.f64(pre + "NfOld", col([](tCNode *c) { return c->getNfOld(); }));
+            w.f64(pre + "RuOld", col([](tCNode *c) { return c->getRuOld(); }));
+            w.f64(pre + "RiOld", col([](tCNode *c) { return c->getRiOld(); }));
+        }
+        w.f64(pre + "Qpin", col([](tCNode *c) { return c->getQpin(); }));
+        w.f64(pre + "Qpout", col([](tCNode *c) { return c->getQpout(); }));
+        w.f64(pre + "intstorm", col([](tCNode *c) { return c->getIntStormVar(); }));
+        w.f64(pre + "gwchange", col([](tCNode *c) { return c->gwchange; }));
+        w.f64(pre + "srf", col([](tCNode *c) { return c->getSrf(); }));
+        w.f64(pre + "hsrf", col([](tCNode *c) { return c->getHsrf(); }));
+        w.f64(pre + "sbsrf", col([](tCNode *c) { return c->getSbsrf(); }));
+        w.f64(pre + "psrf", col([](tCNode *c) { return c->getPsrf(); }));
+        w.f64(pre + "satsrf", col([](tCNode *c) { return c->getSatsrf(); }));
+        w.f64(pre + "esrf", col([](tCNode *c) { return c->getEsrf(); }));
+        w.f64(pre + "srf_hr", col([](tCNode *c) { return c->getSrf_Hr(); }));
+        w.f64(pre + "cumsrf", col([](tCNode *c) { return c->getCumSrf(); }));
+        w.f64(pre + "Rain", col([](tCNode *c) { return c->getRain(); }));
+        w.f64(pre + "SoilMoisture", col([](tCNode *c) { return c->getSoilMoisture(); }));
+        w.f64(pre + "SoilMoistureSC", col([](tCNode *c) { return c->getSoilMoistureSC(); }));
+        w.f64(pre + "SoilMoistureUNSC", col([](tCNode *c) { return c->getSoilMoistureUNSC(); }));
+        w.f64(pre + "RootMoisture", col([](tCNode *c) { return c->getRootMoisture(); }));
+        w.f64(pre + "RootMoistureSC", col([](tCNode *c) { return c->getRootMoistureSC(); }));
+        w.f64(pre + "AvSoilMoisture", col([](tCNode *c) { return c->getAvSoilMoisture(); }));
+        w.f64(pre + "Recharge", col([](tCNode *c) { return c->getRecharge(); }));
+        w.f64(pre + "UnSatFlowIn", col([](tCNode *c) { return c->getUnSatFlowIn(); }));
+        w.f64(pre + "UnSatFlowOut", col([](tCNode *c) { return c->getUnSatFlowOut(); }));
+        w.f64(pre + "Transmissivity", col([](tCNode *c) { return c->getTransmiss(); }));
+        w.f64(pre + "hsrfOccur", col([](tCNode *c) { return c->hsrfOccur; }));
+        w.f64(pre + "sbsrfOccur", col([](tCNode *c) { return c->sbsrfOccur; }));
+        w.f64(pre + "psrfOccur", col([](tCNode *c) { return c->psrfOccur; }));
+        w.f64(pre + "satsrfOccur", col([](tCNode *c) { return c->satsrfOccur; }));
+        w.f64(pre + "satOccur", col([](tCNode *c) { return (double)c->satOccur; }));
+        w.f64(pre + "RechDisch", col([](tCNode *c) { return c->RechDisch; }));
+        w.f64(pre + "FlowVelocity", col([](tCNode *c) { return c->getFlowVelocity(); }));
+        w.f64(pre + "TTime", col([](tCNode *c) { return c->getTTime(); }));
+        w.f64(pre + "Qstrm", col([](tCNode *c) { return c->getQstrm(); }));
+        w.f64(pre + "Hlevel", col([](tCNode *c) { return c->getHlevel(); }));
+        w.f64(pre + "NetPrecipitation", col([](tCNode *c) { return c->getNetPrecipitation(); }));
+        w.f64(pre + "EvapSoil", col([](tCNode *c) { return c->getEvapSoil(); }));
+        w.f64(pre + "EvapDryCanopy", col([](tCNode *c) { return c->getEvapDryCanopy(); }));
+        w.f64(pre + "EvapoTrans", col([](tCNode *c) { return c->getEvapoTrans(); }));
+        w.f64(pre + "UnSaturatedStorage", col([](tCNode *c) { return c->getUnSaturatedStorage(); }));
+        w.f64(pre + "SaturatedStorage", col([](tCNode *c) { return c->getSaturatedStorage(); }));
+        // basin accumulators of tHydroModel
+        vector<double> g = {hydro->Stok, hydro->TotRain, hydro->TotGWchange, hydro->TotMoist,
+                            hydro->psrf, timer->getCurrentTime(), flow->Qout,
+                            hydro->fSoi100, hydro->fTop100, hydro->fClm100, hydro->fGW100,
+                            hydro->dM100, hydro->dMRt, hydro->mTh100, hydro->mThRt};
+        w.f64(pre + "globals", g);
+    }
+
+    void dump_routing(TrbWriter &w, const string &pre) {
+        // (TimeInd, Qeff) stacks of the stream cells (reference: tKinemat.cpp:1023-1067)
+        vector<int32_t> off(1, 0), node, tind;
+        vector<double> q;
+        for (size_t i = 0; i < cells.size(); i++) {
+            tCNode *c = cells[i];
+            if (c->getBoundaryFlag() != kStream) continue;
+            tList<int> *ti = c->getTimeIndList();
+            tList<double> *qe = c->getQeffList();
+            if (!ti || !qe) continue;
+            node.push_back((int)i);
+            tListNode<int> *a = ti->getFirst();
+            tListNode<double> *b = qe->getFirst();
+            for (int k = 0; k < ti->getSize(); k++, a = a->getNextNC(), b = b->getNextNC()) {
+                tind.push_back(a->getDataNC());
+                q.push_back(b->getDataNC());
+            }
+            off.push_back((int32_t)tind.size());
+        }
+        w.i32(pre + "qeff_node", node);
+        w.i32(pre + "qeff_off", off);
+        w.i32(pre + "qeff_tind", tind);
+        w.f64(pre + "qeff_val", q);
+        tFlowResults *r = flow->res;
+        int lim = r->limit;
+        auto arr = [&](const char *nm, double *p) {
+            w.rec(pre + nm, 0, lim, p, 8);
+        };
+        arr("mhydro", r->mhydro);
+        arr("HsrfRout", r->HsrfRout);
+        arr("SbsrfRout", r->SbsrfRout);
+        arr("PsrfRout", r->PsrfRout);
+        arr("SatsrfRout", r->SatsrfRout);
+        arr("crr", r->crr);
+        arr("rmax", r->max);
+        arr("rmin", r->min);
+        arr("frac", r->frac);
+        arr("msm", r->msm);
+        arr("msmRt", r->msmRt);
+        arr("msmU", r->msmU);
+        arr("mgw", r->mgw);
+        arr("sat", r->sat);
+        arr("qunsat", r->qunsat);
+    }
+
+    // -------------------------------------------------------------- known answers
+    void dump_kat(const string &path) {
+        TrbWriter w(path);
+        tCNode *cn = cells[0];
+        hydro->SetupNodeUSZ(cn);
+        hydro->DtoBedrock = cn->getBedrockDepth();
+        vector<double> prm = {hydro->Ksat, hydro->Ths, hydro->Thr, hydro->PoreInd, hydro->Psib,
+                              hydro->F, hydro->Ar, hydro->UAr, hydro->Eps, hydro->DtoBedrock};
+        w.f64("kat_soil", prm);
+        // LambertW (reference: tHydroModel.cpp:3831-3915)
+        {
+            vector<double> zi, zo;
+            for (int k = 0; k <= 400; k++) {
+                double z = -0.3678 + 0.3678 * k / 400.0 * 0.999999;
+                zi.push_back(z);
+            }
+            for (int k = 1; k <= 60; k++) zi.push_back(-pow(10.0, -0.25 * k));
+            for (int k = 1; k <= 40; k++) zi.push_back(0.05 * k);
+            zi.push_back(1.0); zi.push_back(2.5); zi.push_back(10.0); zi.push_back(0.0);
+            for (double z : zi) zo.push_back(hydro->LambertW(z));
+            w.f64("lambertw_in", zi);
+            w.f64("lambertw_out", zo);
+        }
+        // get_Total_Moist / get_Upper_Moist / get_Lower_Moist
+        {
+            vector<double> a, o;
+            for (int k = 0; k <= 300; k++) {
+                double nwt = 50.0 * k;
+                a.push_back(nwt);
+                double save = hydro->NwtNew;
+                o.push_back(hydro->get_Total_Moist(nwt));
+                hydro->NwtNew = save;
+            }
+            w.f64("total_moist_in", a);
+            w.f64("total_moist_out", o);
+            vector<double> nf, nw, up, lo;
+            for (int i = 1; i <= 40; i++)
+                for (int j = 1; j <= 12; j++) {
+                    double nwt = 250.0 + 1200.0 * j;
+                    double f = nwt * i / 41.0;
+                    nf.push_back(f); nw.push_back(nwt);
+                    up.push_back(hydro->get_Upper_Moist(f, nwt));
+                    lo.push_back(hydro->get_Lower_Moist(f, nwt));
+                }
+            w.f64("ul_moist_nf", nf);
+            w.f64("ul_moist_nwt", nw);
+            w.f64("upper_moist_out", up);
+            w.f64("lower_moist_out", lo);
+        }
+        // Newton #1 (water-table solve, reference: tHydroModel.cpp:3937-4020)
+        {
+            vector<double> dm, nw, o;
+            for (int i = 0; i <= 30; i++)
+                for (int j = 0; j <= 10; j++) {
+                    double nwt = (j == 0) ? 0.0 : 300.0 + 1400.0 * j;
+                    double d = 5.0 + 40.0 * i * (1 + j);
+                    dm.push_back(d); nw.push_back(nwt);
+                    double save = hydro->NwtNew;
+                    o.push_back(hydro->Newton(d, nwt));
+                    hydro->NwtNew = save;
+                }
+            w.f64("newton1_dm", dm);
+            w.f64("newton1_nwt", nw);
+            w.f64("newton1_out", o);
+        }
+        // Newton #2 (front relocation, reference: tHydroModel.cpp:4037-4082)
+        {
+            vector<double> dm, nw, nf, fl, o;
+            for (int flag = 0; flag <= 1; flag++)
+                for (int i = 1; i <= 12; i++)
+                    for (int j = 1; j <= 8; j++) {
+                        double nwt = 1500.0 + 1000.0 * j;
+                        double f = (nwt - 250.0) * i / 14.0;
+                        double d = 0.2 * i + 0.05 * j;
+                        dm.push_back(d); nw.push_back(nwt); nf.push_back(f); fl.push_back(flag);
+                        o.push_back(hydro->Newton(d, nwt, f, flag));
+                    }
+            w.f64("newton2_dm", dm);
+            w.f64("newton2_nwt", nw);
+            w.f64("newton2_nf", nf);
+            w.f64("newton2_flag", fl);
+            w.f64("newton2_out", o);
+        }
+        // get_RechargeRate, lateral flows, Z1Z2
+        {
+            vector<double> a, b, o, us, ss, zz;
+            for (int i = 1; i <= 30; i++)
+                for (int j = 1; j <= 10; j++) {
+                    double nf = 20.0 * i;
+                    double dmv = hydro->Thr * nf + (hydro->Ths - hydro->Thr) * nf * j / 11.0;
+                    a.push_back(dmv); b.push_back(nf);
+                    double ru = hydro->get_RechargeRate(dmv, nf);
+                    o.push_back(ru);
+                    us.push_back(hydro->get_UnSat_LateralFlow(nf, ru, 30000.0));
+                    ss.push_back(hydro->get_Sat_LateralFlow(nf * j / 11.0 * (j % 3 ? 1 : 0), nf, ru, 30000.0));
+                    zz.push_back(hydro->get_Z1Z2_Moist(nf, nf + 100.0 * j, 3000.0, 0));
+                }
+            w.f64("recharge_dm", a);
+            w.f64("recharge_nf", b);
+            w.f64("recharge_out", o);
+            w.f64("unsat_lat_out", us);
+            w.f64("sat_lat_out", ss);
+            w.f64("z1z2_out", zz);
+        }
+    }
+};
+
+static double now_s() {
+    using namespace std::chrono;
+    return duration<double>(steady_clock::now().time_since_epoch()).count();
+}
+
+int main(int argc, char **argv) {
+    // harness flags are stripped before the reference's own CLI parser sees argv
+    string outdir = ".";
+    int snap_from = 1, snap_to = 0, snap_every = 1;
+    string phases = "ugre";
+    bool do_kat = false, do_basin = true;
+    vector<char*> rargs;
+    for (int i = 0; i < argc; i++) {
+        string a = argv[i];
+        if (a == "--out" && i + 1 < argc) outdir = argv[++i];
+        else if (a == "--snap-from" && i + 1 < argc) snap_from = atoi(argv[++i]);
+        else if (a == "--snap-to" && i + 1 < argc) snap_to = atoi(argv[++i]);
+        else if (a == "--snap-every" && i + 1 < argc) snap_every = atoi(argv[++i]);
+        else if (a == "--phases" && i + 1 < argc) phases = argv[++i];
+        else if (a == "--kat") do_kat = true;
+        else if (a == "--no-basin") do_basin = false;
+        else rargs.push_back(argv[i]);
+    }
+    int rargc = (int)rargs.size();
+    char **rargv = rargs.data();
+
+    double t_setup0 = now_s();
+    SimulationControl SimCtrl(rargc, rargv);
+    tInputFile InputFile(SimCtrl.infile);
+    tPreProcess PreProcessor(&SimCtrl, InputFile);
+    tRunTimer Timer(InputFile);
+    tMesh<tCNode> BasinMesh(&SimCtrl, InputFile);
+    tKinemat Flow(&SimCtrl, &BasinMesh, InputFile, &Timer);
+    tResample RsmplMaster(&SimCtrl, &BasinMesh);
+    tShelter Shelter(&SimCtrl, &BasinMesh, InputFile);
+    tCOutput<tCNode> Output(&SimCtrl, &BasinMesh, InputFile, &RsmplMaster, &Timer);
+    tWaterBalance Balance(&SimCtrl, &BasinMesh, InputFile);
+    tHydroModel Moisture(&SimCtrl, &BasinMesh, InputFile, &RsmplMaster, &Balance, &Timer);
+    tRainfall Rainfall(&SimCtrl, &BasinMesh, InputFile, &RsmplMaster);
+    tEvapoTrans EvapoTrans(&SimCtrl, &BasinMesh, InputFile, &Timer, &RsmplMaster, &Moisture, &Rainfall);
+    tIntercept Intercept(&SimCtrl, &BasinMesh, InputFile, &Timer, &RsmplMaster, &Moisture);
+    tSnowPack SnowPack(&SimCtrl, &BasinMesh, InputFile, &Timer, &RsmplMaster, &Moisture, &Rainfall);
+    tRestart<tCNode> Restart(&Timer, &BasinMesh, &Flow, &Balance, &Moisture, &Rainfall,
+                             &EvapoTrans, &Intercept, &SnowPack);
+    Simulator Sim(&SimCtrl, &Rainfall, &Timer, &Output, &Restart);
+    Sim.initialize_simulation(&EvapoTrans, &SnowPack, InputFile);
+    double t_setup1 = now_s();
+
+    Harness H;
+    H.mesh = &BasinMesh; H.flow = &Flow; H.hydro = &Moisture; H.timer = &Timer;
+    H.index();
+    if (do_basin) H.dump_basin(outdir + "/basin.trb", InputFile);
+    if (do_kat) H.dump_kat(outdir + "/kat.trb");
+
+    std::unique_ptr<TrbWriter> sw;
+    if (snap_to >= snap_from) sw.reset(new TrbWriter(outdir + "/steps.trb"));
+
+    // The reference's simulation_loop body (tSimul.cpp:248-293), one call at a time.
+    int step = 0;
+    double t_loop = 0.0, t_unsat = 0.0, t_sat = 0.0, t_route = 0.0, t_rest = 0.0;
+    vector<int32_t> snap_steps;
+    while (!Timer.IsFinished()) {
+        step++;
+        bool snap = sw && step >= snap_from && step <= snap_to && ((step - snap_from) % snap_every == 0);
+        char pre[64];
+        double t0 = now_s();
+        Timer.Advance(Timer.getTimeStep());
+        Sim.UpdatePrecipitationInput(Rainfall.getoptStorm());
+        Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
+        double t1 = now_s();
+        // SubSurfaceHydroProcesses, split so the state between the two zones is observable
+        Moisture.UnSaturatedZone(Timer.getTimeStep());
+        double t2 = now_s();
+        if (snap && phases.find('u') != string::npos) {
+            snprintf(pre, sizeof pre, "s%d_u_", step); H.dump_state(*sw, pre, false);
+        }
+        double t2b = now_s();
+        Sim.GW_label = fmod(Timer.getCurrentTime(), Timer.getGWTimeStep());
+        bool gw = false;
+        if (SimCtrl.GW_model_label && !Sim.GW_label) {
+            Moisture.ResetGW();
+            Moisture.SaturatedZone(Timer.getGWTimeStep());
+            gw = true;
+        }
+        double t3 = now_s();
+        if (snap && gw && phases.find('g') != string::npos) {
+            snprintf(pre, sizeof pre, "s%d_g_", step); H.dump_state(*sw, pre, true);
+        }
+        double t3b = now_s();
+        Flow.SurfaceFlow();
+        double t4 = now_s();
+        if (snap && phases.find('r') != string::npos) {
+            snprintf(pre, sizeof pre, "s%d_r_", step); H.dump_state(*sw, pre, false);
+            H.dump_routing(*sw, pre);
+        }
+        double t4b = now_s();
+        Sim.OutputSimulatedVars(&Flow);
+        Sim.UpdateWaterBalance(&Balance);
+        Moisture.Reset();
+        double t5 = now_s();
+        if (snap && phases.find('e') != string::npos) {
+            snprintf(pre, sizeof pre, "s%d_e_", step); H.dump_state(*sw, pre, true);
+        }
+        if (snap) snap_steps.push_back(step);
+        t_rest += (t1 - t0) + (t5 - t4b);
+        t_unsat += t2 - t1; t_sat += t3 - t2b; t_route += t4 - t3b;
+        t_loop += (t1 - t0) + (t2 - t1) + (t3 - t2b) + (t4 - t3b) + (t5 - t4b);
+    }
+    if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
+    Sim.end_simulation(&Flow);
+
+    long ncell = (long)H.cells.size();
+    printf("\nref_timing {\"cells\": %ld, \"steps\": %d, \"setup_s\": %.6f, \"loop_s\": %.6f, "
+           "\"unsat_s\": %.6f, \"sat_s\": %.6f, \"route_s\": %.6f, \"other_s\": %.6f, "
+           "\"cell_steps_per_s\": %.6e}\n",
+           ncell, step, t_setup1 - t_setup0, t_loop, t_unsat, t_sat, t_route, t_rest,
+           t_loop > 0 ? (double)ncell * step / t_loop : 0.0);
+    fflush(stdout);
+    return 0;
+}
