@@ -1,0 +1,190 @@
+/* tribs_gpu.h — C ABI of the B200 water-balance path (libtribs_gpu.so).
+ *
+ * This is the boundary a host model binds to. It replaces, for the per-timestep Voronoi-cell
+ * water balance only, the bodies of these reference member functions (the host keeps their
+ * signatures and forwards to the calls below; see INTEGRATION.md for the binding):
+ *
+ *   tHydroModel::UnSaturatedZone(double dt)      src/tHydro/tHydroModel.cpp:720   -> TRIBS_PHASE_UNSAT
+ *   tHydroModel::ResetGW()                       src/tHydro/tHydroModel.cpp:2470  -> TRIBS_PHASE_SAT (first half)
+ *   tHydroModel::SaturatedZone(double dtGW)      src/tHydro/tHydroModel.cpp:2998  -> TRIBS_PHASE_SAT
+ *   tKinemat::RunHydrologicRouting()             src/tFlowNet/tKinemat.cpp:920    -> TRIBS_PHASE_ROUTE
+ *   tFlowNet::SurfaceFlow()                      src/tFlowNet/tFlowNet.cpp:735    -> TRIBS_PHASE_ROUTE
+ *   tHydroModel::Reset()                         src/tHydro/tHydroModel.cpp:2441  -> TRIBS_PHASE_RESET
+ *   tRainfall::NewRain(double) / per-cell rain   src/tRasTin/tRainfall.cpp:281    -> tribs_step_t.rain*
+ *
+ * Conventions: plain pointers and sizes, no C++ or torch types. All per-cell arrays are in the
+ * reference's sweep order (position in the active part of tMesh::nodeList, == tNode::getID()
+ * after tFlowNet's sort). Indices are int32, values FP64. Every entry point returns 0 on
+ * success, non-zero on failure with the message available from tribs_gpu_last_error(); the C++
+ * shim turns that into the reference's `cout << msg; exit(n)` convention.
+ * Single host thread per handle; one handle per GPU (one partition per GPU).
+ */
+#ifndef TRIBS_GPU_H
+#define TRIBS_GPU_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRIBS_GPU_ABI_VERSION 1
+
+typedef struct tribs_ctx *tribs_handle_t;
+
+/* ------------------------------------------------------------------ dynamic per-cell fields
+ * Names are the tCNode members (src/tCNode/tCNode.h:683-920). Old/New pairs are listed once:
+ * the "New" id is the current value; "Old" is the value at the start of the step. */
+#define TRIBS_FIELDS(X) \
+  X(NwtNew) X(MuNew) X(MiNew) X(NtNew) X(NfNew) X(RuNew) X(RiNew) \
+  X(NwtOld) X(MuOld) X(MiOld) X(NtOld) X(NfOld) X(RuOld) X(RiOld) \
+  X(Qpin) X(Qpout) X(intstorm) X(gwchange) \
+  X(srf) X(hsrf) X(sbsrf) X(psrf) X(satsrf) X(esrf) X(srf_hr) X(cumsrf) \
+  X(Rain) X(NetPrecipitation) X(EvapSoil) X(EvapDryCanopy) \
+  X(SoilMoisture) X(SoilMoistureSC) X(SoilMoistureUNSC) X(RootMoisture) X(RootMoistureSC) \
+  X(AvSoilMoisture) X(Recharge) X(UnSatFlowIn) X(UnSatFlowOut) X(Transmissivity) \
+  X(hsrfOccur) X(sbsrfOccur) X(psrfOccur) X(satsrfOccur) X(satOccur) X(RechDisch) \
+  X(FlowVelocity) X(TTime) X(Qstrm) X(LiqWE) X(IceWE) X(LiqRouted)
+
+#define TRIBS_FIELD_ENUM(name) TRIBS_F_##name,
+typedef enum { TRIBS_FIELDS(TRIBS_FIELD_ENUM) TRIBS_N_FIELDS } tribs_field_t;
+#define TRIBS_MASK(field) (1ull << (field))
+#define TRIBS_MASK_ALL ((TRIBS_N_FIELDS >= 64) ? ~0ull : ((1ull << TRIBS_N_FIELDS) - 1ull))
+
+/* ------------------------------------------------------------------ mesh (tMesh/tFlowNet outputs) */
+typedef struct {
+  int32_t n_cells;              /* active cells (boundary 0 or 3), sweep order */
+  int32_t n_edges;              /* directed Voronoi spokes in the CSR below */
+  const int32_t *boundary;      /* [n] kNonBoundary=0 | kStream=3 (Definitions.h:42-45) */
+  const double *z;              /* [n] m */
+  const double *varea;          /* [n] m^2 */
+  const double *flow_slope;     /* [n] slope of tCNode::getFlowEdg() */
+  const double *flow_vedglen;   /* [n] Voronoi width of the flow edge, m */
+  const int32_t *flow_dest;     /* [n] sweep index of the downslope cell, -1 = outlet node */
+  const int32_t *stream_node;   /* [n] sweep index of tCNode::getStreamNode(), -1 = outlet node */
+  const double *hillpath;       /* [n] m */
+  const double *streampath;     /* [n] m */
+  const double *contr_area;     /* [n] m^2 (used for stream cells) */
+  const double *ttime;          /* [n] initial tCNode::traveltime, h */
+  const int32_t *reach;         /* [n] tCNode::getReach(); may be NULL when not partitioned */
+  /* Voronoi neighbour graph: row i lists the spokes of cell i counter-clockwise starting at
+   * tNode::getEdg(). Each spoke is the directed edge i -> nbr_col[k]. */
+  const int32_t *nbr_rowptr;    /* [n+1] */
+  const int32_t *nbr_col;       /* [E] sweep index of the destination, -1 = not an active cell */
+  const double *nbr_len;        /* [E] tEdge::getLength() of i->j */
+  const double *nbr_vedglen;    /* [E] tEdge::getVEdgLen() of i->j */
+  const double *nbr_len_in;     /* [E] getLength() of the complementary edge j->i */
+  const double *nbr_vedglen_in; /* [E] getVEdgLen() of j->i (differs after FixVoronoiEdgeWidth) */
+  const int32_t *nbr_listpos;   /* [E] position of i->j in the active edge list (flux loop order) */
+} tribs_mesh_t;
+
+/* ------------------------------------------------------------------ parameters */
+typedef struct {
+  /* per-cell soil (tCNode::getKs() ...; src/tHydro/tHydroModel.cpp:669-679) */
+  const double *Ks, *ThetaS, *ThetaR, *PoreSize, *AirEBubPres, *DecayF, *SatAnRatio, *UnsatAnRatio;
+  const double *bedrock;        /* [n] tCNode::getBedrockDepth(), mm */
+  double BasArea;               /* tHydroModel::BasArea */
+  double BasArea_flow;          /* tFlowNet::BasArea */
+  double IntStormMAX;           /* h */
+  double surfaceSoilDepth, rootZoneDepth; /* mm */
+  int32_t EToption, Ioption, SnOpt, RdstrOption;
+  /* hillslope routing (tFlowNet / tKinemat members) */
+  double velcoef, velratio, flowexp, baseflow, kincoef, dtReff, outlet_contr_area;
+  /* timer (hours) */
+  double tstep, gwstep, etistep, output_interval;
+  int32_t res_limit;            /* tFlowResults::limit: bins per hydrograph array */
+  int32_t reserved;
+} tribs_params_t;
+
+/* host staging of dynamic fields; NULL entries are skipped */
+typedef struct {
+  double *f[TRIBS_N_FIELDS];
+} tribs_state_t;
+
+/* ------------------------------------------------------------------ multi-GPU partition (optional) */
+typedef struct {
+  int32_t rank, nranks;
+  const void *nccl_unique_id;   /* 128-byte ncclUniqueId shared by all ranks, NULL for nranks==1 */
+  const int32_t *cell_owner;    /* [n_cells_global] owning rank of every cell of the global basin */
+} tribs_part_t;
+
+/* ------------------------------------------------------------------ stepping */
+enum {
+  TRIBS_PHASE_UNSAT = 1,   /* UnSaturatedZone(dt) */
+  TRIBS_PHASE_SAT   = 2,   /* ResetGW(); SaturatedZone(dt_gw) */
+  TRIBS_PHASE_ROUTE = 4,   /* RunHydrologicRouting(); tFlowNet::SurfaceFlow() accumulations */
+  TRIBS_PHASE_RESET = 8    /* tHydroModel::Reset() */
+};
+
+enum { TRIBS_RAIN_KEEP = 0, TRIBS_RAIN_UNIFORM = 1, TRIBS_RAIN_PER_CELL = 2 };
+
+typedef struct {
+  double current_time;      /* tRunTimer::getCurrentTime() after Advance(), hours */
+  double dt;                /* tRunTimer::getTimeStep(), hours */
+  double dt_gw;             /* tRunTimer::getGWTimeStep(), hours */
+  int32_t elapsed_steps;    /* tRunTimer::getElapsedSteps(currentTime) */
+  int32_t hourly_reset;     /* !(fmod(currentTime - tstep, etistep)), tHydroModel.cpp:700-702 */
+  int32_t rain_mode;        /* TRIBS_RAIN_* : tRainfall::NewRain for this step */
+  int32_t reserved;
+  double rain_uniform;      /* mm/h, rain_mode == UNIFORM */
+  const double *rain;       /* host [n] mm/h, rain_mode == PER_CELL */
+  const double *qstrm;      /* host [n] tCNode::Qstrm (stream cells) or NULL: only read if flowexp>0 */
+  double qstrm_outlet;      /* OutletNode->getQstrm() */
+} tribs_step_t;
+
+/* basin accumulators returned by tribs_gpu_get_globals (tHydroModel private sums) */
+enum { TRIBS_G_Stok, TRIBS_G_TotRain, TRIBS_G_TotGWchange, TRIBS_G_TotMoist, TRIBS_G_psrf_last,
+       TRIBS_G_hillvel_last, TRIBS_N_GLOBALS };
+
+/* tFlowResults arrays kept on the device (src/tFlowNet/tFlowResults.h:74-96) */
+enum { TRIBS_R_mhydro, TRIBS_R_HsrfRout, TRIBS_R_SbsrfRout, TRIBS_R_PsrfRout, TRIBS_R_SatsrfRout,
+       TRIBS_R_crr, TRIBS_R_rmax, TRIBS_R_rmin, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt,
+       TRIBS_R_msmU, TRIBS_R_mgw, TRIBS_R_sat, TRIBS_R_qunsat, TRIBS_N_RESULTS };
+
+/* Build the device mirror: SoA FP64 state, CSR neighbour graph, sweep schedule. Copies
+ * everything it needs; the host arrays may be freed afterwards. `part` may be NULL. */
+int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *prm, const tribs_state_t *init,
+                   const tribs_part_t *part, tribs_handle_t *out);
+
+/* Run the phases in `phase_mask` (TRIBS_PHASE_* ORed, executed in the reference's order
+ * UNSAT, SAT, ROUTE, RESET) for the step described by `s`. Asynchronous on the handle's
+ * compute stream; tribs_gpu_sync / the getters synchronise. */
+int tribs_gpu_step(tribs_handle_t h, uint32_t phase_mask, const tribs_step_t *s);
+
+/* Copy the fields selected by `field_mask` (TRIBS_MASK(...)) back into host SoA staging in
+ * sweep order; the host shim scatters them into tCNode. Blocks until the data is on the host. */
+int tribs_gpu_sync(tribs_handle_t h, uint64_t field_mask, tribs_state_t *host);
+
+/* Overwrite device fields from host staging (restart / external modification of tCNode). */
+int tribs_gpu_push(tribs_handle_t h, uint64_t field_mask, const tribs_state_t *host);
+
+/* Lateral inflow the channel router sees this step: what tKinemat::RetrieveQeff
+ * (tKinemat.cpp:1504) returns for every stream cell, in sweep order of the stream cells, and
+ * for the outlet node in the last slot. `out` has tribs_gpu_n_stream()+1 entries. Consumes
+ * the bin at the end of a dtReff interval exactly like the reference. */
+int tribs_gpu_retrieve_qeff(tribs_handle_t h, double current_time, double *out);
+int tribs_gpu_n_stream(tribs_handle_t h);
+int tribs_gpu_stream_cells(tribs_handle_t h, int32_t *sweep_index_out);
+
+/* tFlowResults arrays (`which` = TRIBS_R_*), `n` <= res_limit bins. */
+int tribs_gpu_get_results(tribs_handle_t h, int which, double *out, int n);
+int tribs_gpu_get_globals(tribs_handle_t h, double *out /* TRIBS_N_GLOBALS */);
+
+/* Introspection used by tests and the bench. */
+int tribs_gpu_sweep_levels(tribs_handle_t h);            /* depth of the Qpin dependency DAG */
+int tribs_gpu_device_index(tribs_handle_t h, int32_t *dev_index_of_sweep /* [n_cells] */);
+int64_t tribs_gpu_launch_count(tribs_handle_t h);        /* kernels launched so far */
+/* device time (ms, CUDA events on the compute stream) accumulated per phase since the last call
+ * with reset!=0: out[0]=unsat out[1]=sat out[2]=route out[3]=reset; enable with set_timing(1) */
+int tribs_gpu_set_timing(tribs_handle_t h, int enabled);
+int tribs_gpu_phase_ms(tribs_handle_t h, double *out4, int reset);
+
+int tribs_gpu_wait(tribs_handle_t h);                    /* cudaStreamSynchronize */
+void *tribs_gpu_stream(tribs_handle_t h);                /* cudaStream_t of the compute stream */
+int tribs_gpu_destroy(tribs_handle_t h);
+const char *tribs_gpu_last_error(void);
+int tribs_gpu_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,170 @@
+"""Shared comparison logic: step a model phase by phase and compare with reference snapshots."""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from refrun import rel_err
+
+STATE_FIELDS = ["NwtNew", "MuNew", "MiNew", "NtNew", "NfNew", "RuNew", "RiNew", "Qpin", "Qpout", "intstorm",
+                "srf", "hsrf", "sbsrf", "psrf", "esrf", "srf_hr", "cumsrf", "SoilMoisture", "SoilMoistureSC",
+                "SoilMoistureUNSC", "RootMoisture", "RootMoistureSC", "AvSoilMoisture", "Recharge", "UnSatFlowIn",
+                "UnSatFlowOut", "hsrfOccur", "sbsrfOccur", "psrfOccur", "satOccur", "RechDisch", "Rain"]
+GW_FIELDS = ["gwchange", "satsrf", "satsrfOccur", "Transmissivity"]
+RESULT_ARRAYS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac",
+                 "msm", "msmRt", "msmU", "mgw", "sat", "qunsat"]
+
+
+class GpuStepper:
+    """Drives tribs_b200 through the C ABI one phase at a time."""
+
+    def __init__(self, basin, rain_schedule):
+        from tribs_b200 import gpu, model
+        self.gpu = gpu
+        self.sim = model.Simulator(basin, rain_schedule)
+        self.n = self.sim.dev.n
+        self.boundary = np.asarray(basin["boundary"])
+        self.stream_cells = self.sim.dev.stream_cells()
+        self.limit = int(basin["res_limit"][0])
+
+    @property
+    def time(self):
+        return self.sim.timer.getCurrentTime()
+
+    def advance(self):
+        self.sim.advance()
+        self.sim.UpdatePrecipitationInput()
+
+    def unsat(self):
+        self.sim.hydro.UnSaturatedZone(self.sim.timer.getTimeStep())
+
+    def gw_due(self):
+        t = self.sim.timer
+        return self.sim.gw_on and math.fmod(t.getCurrentTime(), t.getGWTimeStep()) == 0.0
+
+    def sat(self):
+        self.sim.hydro.ResetGW()
+        self.sim.hydro.SaturatedZone(self.sim.timer.getGWTimeStep())
+
+    def route(self):
+        self.sim.flow.SurfaceFlow(True)
+        return self.sim.flow.lateral_inflow
+
+    def reset(self):
+        self.sim.hydro.Reset()
+
+    def get(self, names):
+        return self.sim.dev.sync(names)
+
+    def result(self, name):
+        return self.sim.dev.results(name, self.limit)
+
+    def globals(self):
+        return self.sim.dev.globals()
+
+
+class OracleStepper:
+    def __init__(self, basin, rain_schedule):
+        from oracle.pyoracle import OracleModel
+        self.m = OracleModel(basin, rain_schedule)
+        self.n = self.m.n
+        self.boundary = np.asarray(basin["boundary"])
+        self.stream_cells = np.nonzero(self.boundary == 3)[0].astype(np.int32)
+
+    @property
+    def time(self):
+        return self.m.time
+
+    def advance(self):
+        self.m.advance()
+
+    def unsat(self):
+        self.m.unsat()
+
+    def gw_due(self):
+        return self.m.gw_due()
+
+    def sat(self):
+        self.m.sat()
+
+    def route(self):
+        self.m.route()
+        q = self.m.retrieve_qeff()
+        return np.concatenate([q[self.stream_cells], q[-1:]])
+
+    def reset(self):
+        self.m.reset()
+
+    def get(self, names):
+        return {k: self.m.state[k] for k in names}
+
+    def result(self, name):
+        return self.m.res[name]
+
+    def globals(self):
+        from oracle.pyoracle import GLOBALS
+        return dict(zip(GLOBALS, self.m.glob))
+
+
+class Worst:
+    def __init__(self):
+        self.w = {}
+
+    def add(self, key, ref, got, info, floor):
+        e = rel_err(ref, got, floor)
+        k = int(np.argmax(e)) if e.size else 0
+        v = float(e[k]) if e.size else 0.0
+        if key not in self.w or v > self.w[key][0]:
+            self.w[key] = (v, info, k, float(np.ravel(ref)[k]) if e.size else 0.0, float(np.ravel(got)[k]) if e.size else 0.0)
+
+    def max(self):
+        return max((v[0] for v in self.w.values()), default=0.0)
+
+    def report(self, top=12):
+        rows = sorted(self.w.items(), key=lambda kv: -kv[1][0])[:top]
+        return "\n".join(f"  {k}: rel={v[0]:.3e} at {v[1]} cell {v[2]} ref={v[3]!r} got={v[4]!r}" for k, v in rows)
+
+
+def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True):
+    """Steps `stepper` n_steps times; wherever the reference has a snapshot, compares.
+    Returns a Worst() table keyed by (phase, field)."""
+    w = Worst()
+    hill = stepper.boundary == 0
+    for st in range(1, n_steps + 1):
+        stepper.advance()
+        stepper.unsat()
+        pre = f"s{st}_u_"
+        if pre + "NwtNew" in snaps:
+            got = stepper.get(STATE_FIELDS)
+            for f in STATE_FIELDS:
+                if pre + f in snaps:
+                    w.add(("u", f), snaps[pre + f], got[f], st, floor)
+        gw = stepper.gw_due()
+        if gw:
+            stepper.sat()
+        qeff = stepper.route()
+        pre = f"s{st}_r_"
+        if pre + "NwtNew" in snaps:
+            names = STATE_FIELDS + ["satsrf", "FlowVelocity", "TTime"] + (GW_FIELDS if gw else [])
+            names = list(dict.fromkeys(names))
+            got = stepper.get(names)
+            for f in names:
+                if pre + f not in snaps:
+                    continue
+                ref, g = snaps[pre + f], got[f]
+                if f == "FlowVelocity":   # stream cells are rewritten by the channel router afterwards
+                    ref, g = ref[hill], g[hill]
+                w.add(("r", f), ref, g, st, floor)
+            for nm in RESULT_ARRAYS:
+                if pre + nm in snaps:
+                    w.add(("res", nm), snaps[pre + nm], stepper.result(nm), st, floor)
+            if pre + "globals" in snaps:
+                g = stepper.globals()
+                ref = snaps[pre + "globals"]
+                w.add(("glob", "Stok"), ref[0:1], np.array([g["Stok"]]), st, floor)
+                w.add(("glob", "TotRain"), ref[1:2], np.array([g["TotRain"]]), st, floor)
+                w.add(("glob", "TotGWchange"), ref[2:3], np.array([g["TotGWchange"]]), st, 1e-6)
+                w.add(("glob", "TotMoist"), ref[3:4], np.array([g["TotMoist"]]), st, 1e-6)
+        stepper.reset()
+    return w

@@ -1,0 +1,91 @@
+"""Test helpers: run the reference harness (oracle/_ref/tribs_ref_harness — the unmodified
+reference compiled in place) on a synthetic deck and load its raw FP64 dumps.
+The binary is prebuilt by __graft_entry__.build(); it needs no access to /root/reference at
+run time, so it also runs on the GPU box."""
+from __future__ import annotations
+
+import os
+import re
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from tribs_b200.synth import BasinSpec, write_basin  # noqa: E402
+from tribs_b200.trb import read_trb  # noqa: E402
+
+HARNESS = os.path.join(ROOT, "oracle", "_ref", "tribs_ref_harness")
+
+# scenarios shared by the golden fixtures and the live parity tests
+SCENARIOS = {
+    # storm + interstorm on a deep water table: wetting-front states, lateral unsaturated flow
+    "deep": dict(runtime_h=48.0),
+    # shallow water table, heavy rain: water table at the surface, exfiltration, GW runoff
+    "shallow": dict(runtime_h=48.0, gw_depth_mm=400.0, pmean=30.0),
+    # short storm, short INTSTORMMAX: wedge destruction / redistribution, Storm_Evol
+    "redistribute": dict(runtime_h=60.0, intstormmax=8.0, stdur=3.0, istdur=12.0, gw_depth_mm=1500.0),
+}
+
+
+def have_harness() -> bool:
+    return os.path.exists(HARNESS) and os.access(HARNESS, os.X_OK)
+
+
+def spec_for(name: str, n: int, **over) -> BasinSpec:
+    kw = dict(SCENARIOS[name])
+    kw.update(over)
+    return BasinSpec(n=n, **kw)
+
+
+def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap_to=0, snap_every=1,
+                  phases="ugr", kat=False, timeout=3600):
+    """Returns (basin dict, snapshots dict, timing dict)."""
+    own = workdir is None
+    d = tempfile.mkdtemp(prefix="tribsref_") if own else workdir
+    write_basin(spec, d)
+    cmd = [HARNESS, "basin.in", "-K", "--out", d, "--snap-from", str(snap_from), "--snap-to", str(snap_to),
+           "--snap-every", str(snap_every), "--phases", phases]
+    if kat:
+        cmd.append("--kat")
+    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference harness failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    import json
+    m = re.search(r"ref_timing (\{.*\})", r.stdout)
+    timing = json.loads(m.group(1)) if m else {}
+    basin = read_trb(os.path.join(d, "basin.trb"))
+    snaps = read_trb(os.path.join(d, "steps.trb")) if snap_to >= snap_from else {}
+    katd = read_trb(os.path.join(d, "kat.trb")) if kat else {}
+    basin["_spec_pmean"] = np.array([spec.pmean])
+    basin["_spec_stdur"] = np.array([spec.stdur])
+    basin["_spec_istdur"] = np.array([spec.istdur])
+    if own:
+        import shutil
+        shutil.rmtree(d, ignore_errors=True)
+    return basin, snaps, timing, katd
+
+
+def storm_of(basin):
+    return float(basin["_spec_pmean"][0]), float(basin["_spec_stdur"][0]), float(basin["_spec_istdur"][0])
+
+
+def load_golden(name: str):
+    z = np.load(os.path.join(ROOT, "tests", "golden", name + ".npz"))
+    basin = {k[2:]: z[k] for k in z.files if k.startswith("b/")}
+    snaps = {k[2:]: z[k] for k in z.files if k.startswith("s/")}
+    kat = {k[2:]: z[k] for k in z.files if k.startswith("k/")}
+    return basin, snaps, kat
+
+
+def rel_err(ref, got, floor=1e-12):
+    ref = np.asarray(ref, float)
+    got = np.asarray(got, float)
+    den = np.maximum(np.abs(ref), floor)
+    e = np.abs(ref - got) / den
+    e[(ref == got)] = 0.0
+    return e

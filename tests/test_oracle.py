@@ -1,0 +1,74 @@
+"""CPU tests (no GPU): the C oracle against the reference's own outputs.
+
+ * golden fixtures under tests/golden/ were produced by the unmodified reference
+   (tests/golden/make_golden.py); the oracle must reproduce them bit for bit;
+ * the reference's scalar helpers (LambertW, Newton, profile integrals ...) as known answers;
+ * when the prebuilt reference harness is present, a fresh scenario is run through it live.
+"""
+import numpy as np
+import pytest
+
+from common import OracleStepper, run_and_compare
+from refrun import SCENARIOS, have_harness, load_golden, run_reference, spec_for, storm_of
+
+
+def _sched(basin):
+    from oracle.pyoracle import stochastic_storm_schedule
+    return stochastic_storm_schedule(*storm_of(basin))
+
+
+@pytest.mark.parametrize("name", list(SCENARIOS))
+def test_oracle_reproduces_reference_golden_bitwise(name, built):
+    basin, snaps, _ = load_golden(name)
+    n_steps = int(snaps["n_steps"][0])
+    w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, n_steps)
+    assert w.max() == 0.0, "oracle differs from the reference:\n" + w.report()
+    assert len(w.w) > 40   # really compared something
+
+
+def test_oracle_state_coverage(built):
+    from oracle.pyoracle import OracleModel
+    seen = np.zeros(16, dtype=np.int64)
+    for name in SCENARIOS:
+        basin, snaps, _ = load_golden(name)
+        m = OracleModel(basin, _sched(basin))
+        m.state_counts(reset=True)
+        for _ in range(int(snaps["n_steps"][0])):
+            m.step()
+        seen += np.array(m.state_counts(reset=True))
+    # unsaturated states 0,1,3,4,5,6,7,8 and all GW states but 'initial-only' must be exercised
+    for k in (0, 1, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13):
+        assert seen[k] > 0, f"state {k} never exercised: {seen}"
+
+
+def test_scalar_helpers_known_answers(built):
+    import ctypes as C
+    from oracle.pyoracle import lib
+    L = lib()
+    _, _, kat = load_golden("deep")
+    soil = kat["kat_soil"]
+    s9 = np.array([soil[0], soil[1], soil[2], soil[3], soil[4], soil[5], soil[6], soil[7], soil[9]])
+    ps = s9.ctypes.data_as(C.POINTER(C.c_double))
+    got = np.array([L.orc_kat_lambertw(z) for z in kat["lambertw_in"]])
+    assert np.array_equal(got, kat["lambertw_out"])
+    got = np.array([L.orc_kat_total_moist(ps, x) for x in kat["total_moist_in"]])
+    assert np.array_equal(got, kat["total_moist_out"])
+    got = np.array([L.orc_kat_upper_moist(ps, a, b) for a, b in zip(kat["ul_moist_nf"], kat["ul_moist_nwt"])])
+    assert np.array_equal(got, kat["upper_moist_out"])
+    got = np.array([L.orc_kat_lower_moist(ps, a, b) for a, b in zip(kat["ul_moist_nf"], kat["ul_moist_nwt"])])
+    assert np.array_equal(got, kat["lower_moist_out"])
+    got = np.array([L.orc_kat_newton1(ps, a, b) for a, b in zip(kat["newton1_dm"], kat["newton1_nwt"])])
+    assert np.array_equal(got, kat["newton1_out"])
+    got = np.array([L.orc_kat_newton2(ps, a, b, c, int(f)) for a, b, c, f in
+                    zip(kat["newton2_dm"], kat["newton2_nwt"], kat["newton2_nf"], kat["newton2_flag"])])
+    assert np.array_equal(got, kat["newton2_out"], equal_nan=True)
+    got = np.array([L.orc_kat_recharge(ps, a, b) for a, b in zip(kat["recharge_dm"], kat["recharge_nf"])])
+    assert np.array_equal(got, kat["recharge_out"])
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+def test_oracle_vs_live_reference(built):
+    spec = spec_for("deep", 14, runtime_h=30.0, seed=7)
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=480, snap_every=7)
+    w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, 480)
+    assert w.max() == 0.0, w.report()

@@ -1,0 +1,286 @@
+"""ctypes binding of libtribs_gpu.so — the C ABI declared in include/tribs_gpu.h.
+
+This module is plumbing only: it marshals numpy arrays into the C structs and calls the
+library. There is no CPU fallback: importing works anywhere, but `load()` raises if the CUDA
+library is missing and `tribs_gpu_init` fails loudly without a CUDA device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import re
+
+import numpy as np
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(PKG)
+LIB_PATH = os.path.join(PKG, "libtribs_gpu.so")
+HEADER = os.path.join(ROOT, "include", "tribs_gpu.h")
+
+
+def _fields_from_header() -> list[str]:
+    src = open(HEADER).read()
+    m = re.search(r"#define TRIBS_FIELDS\(X\) \\\n((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
+def _enum_from_header(prefix: str) -> list[str]:
+    src = open(HEADER).read()
+    names = re.findall(r"\b" + prefix + r"(\w+)\b", src.split("typedef struct tribs_ctx")[1])
+    out = []
+    for nm in names:
+        if nm not in out:
+            out.append(nm)
+    return out
+
+
+FIELDS = _fields_from_header()
+F = {nm: k for k, nm in enumerate(FIELDS)}
+RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac",
+           "msm", "msmRt", "msmU", "mgw", "sat", "qunsat"]
+GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last"]
+PHASE_UNSAT, PHASE_SAT, PHASE_ROUTE, PHASE_RESET = 1, 2, 4, 8
+RAIN_KEEP, RAIN_UNIFORM, RAIN_PER_CELL = 0, 1, 2
+
+PD = C.POINTER(C.c_double)
+PI = C.POINTER(C.c_int32)
+
+
+class Mesh(C.Structure):
+    _fields_ = [("n_cells", C.c_int32), ("n_edges", C.c_int32), ("boundary", PI), ("z", PD), ("varea", PD),
+                ("flow_slope", PD), ("flow_vedglen", PD), ("flow_dest", PI), ("stream_node", PI),
+                ("hillpath", PD), ("streampath", PD), ("contr_area", PD), ("ttime", PD), ("reach", PI),
+                ("nbr_rowptr", PI), ("nbr_col", PI), ("nbr_len", PD), ("nbr_vedglen", PD),
+                ("nbr_len_in", PD), ("nbr_vedglen_in", PD), ("nbr_listpos", PI)]
+
+
+class Params(C.Structure):
+    _fields_ = [("Ks", PD), ("ThetaS", PD), ("ThetaR", PD), ("PoreSize", PD), ("AirEBubPres", PD),
+                ("DecayF", PD), ("SatAnRatio", PD), ("UnsatAnRatio", PD), ("bedrock", PD),
+                ("BasArea", C.c_double), ("BasArea_flow", C.c_double), ("IntStormMAX", C.c_double),
+                ("surfaceSoilDepth", C.c_double), ("rootZoneDepth", C.c_double),
+                ("EToption", C.c_int32), ("Ioption", C.c_int32), ("SnOpt", C.c_int32), ("RdstrOption", C.c_int32),
+                ("velcoef", C.c_double), ("velratio", C.c_double), ("flowexp", C.c_double), ("baseflow", C.c_double),
+                ("kincoef", C.c_double), ("dtReff", C.c_double), ("outlet_contr_area", C.c_double),
+                ("tstep", C.c_double), ("gwstep", C.c_double), ("etistep", C.c_double),
+                ("output_interval", C.c_double), ("res_limit", C.c_int32), ("reserved", C.c_int32)]
+
+
+class StateT(C.Structure):
+    _fields_ = [("f", PD * len(FIELDS))]
+
+
+class Part(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_void_p), ("cell_owner", PI)]
+
+
+class Step(C.Structure):
+    _fields_ = [("current_time", C.c_double), ("dt", C.c_double), ("dt_gw", C.c_double),
+                ("elapsed_steps", C.c_int32), ("hourly_reset", C.c_int32), ("rain_mode", C.c_int32),
+                ("reserved", C.c_int32), ("rain_uniform", C.c_double), ("rain", PD), ("qstrm", PD),
+                ("qstrm_outlet", C.c_double)]
+
+
+EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
+           "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
+           "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
+           "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
+           "tribs_gpu_last_error", "tribs_gpu_abi_version"]
+
+_lib = None
+
+
+def load():
+    """Load libtribs_gpu.so (built by __graft_entry__.build()). Raises if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
+                           "tribs_b200 has no CPU path.")
+    L = C.CDLL(LIB_PATH)
+    H = C.c_void_p
+    L.tribs_gpu_init.argtypes = [C.POINTER(Mesh), C.POINTER(Params), C.POINTER(StateT), C.POINTER(Part), C.POINTER(H)]
+    L.tribs_gpu_step.argtypes = [H, C.c_uint32, C.POINTER(Step)]
+    L.tribs_gpu_sync.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
+    L.tribs_gpu_push.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
+    L.tribs_gpu_retrieve_qeff.argtypes = [H, C.c_double, PD]
+    L.tribs_gpu_n_stream.argtypes = [H]
+    L.tribs_gpu_stream_cells.argtypes = [H, PI]
+    L.tribs_gpu_get_results.argtypes = [H, C.c_int, PD, C.c_int]
+    L.tribs_gpu_get_globals.argtypes = [H, PD]
+    L.tribs_gpu_sweep_levels.argtypes = [H]
+    L.tribs_gpu_device_index.argtypes = [H, PI]
+    L.tribs_gpu_launch_count.argtypes = [H]
+    L.tribs_gpu_launch_count.restype = C.c_int64
+    L.tribs_gpu_set_timing.argtypes = [H, C.c_int]
+    L.tribs_gpu_phase_ms.argtypes = [H, PD, C.c_int]
+    L.tribs_gpu_wait.argtypes = [H]
+    L.tribs_gpu_stream.argtypes = [H]
+    L.tribs_gpu_stream.restype = C.c_void_p
+    L.tribs_gpu_destroy.argtypes = [H]
+    L.tribs_gpu_last_error.restype = C.c_char_p
+    _lib = L
+    return L
+
+
+class TribsGpuError(RuntimeError):
+    pass
+
+
+def _chk(rc: int):
+    if rc != 0:
+        raise TribsGpuError(load().tribs_gpu_last_error().decode())
+
+
+def _d(a):
+    return a.ctypes.data_as(PD)
+
+
+def _i(a):
+    return a.ctypes.data_as(PI)
+
+
+# names in a flattened-basin dict (basin.trb / tribs_b200.synthbasin) -> tribs_mesh_t members
+_MESH_F64 = {"z": "z", "varea": "varea", "flow_slope": "flow_slope", "flow_vedglen": "flow_vedglen",
+             "hillpath": "hillpath", "streampath": "streampath", "contr_area": "contr_area", "ttime": "ttime",
+             "nbr_len": "spoke_len", "nbr_vedglen": "spoke_vedglen", "nbr_len_in": "spoke_compl_len",
+             "nbr_vedglen_in": "spoke_compl_vedglen"}
+_MESH_I32 = {"boundary": "boundary", "flow_dest": "flow_dest", "stream_node": "stream_node", "reach": "reach",
+             "nbr_rowptr": "spoke_rowptr", "nbr_col": "spoke_nbr", "nbr_listpos": "spoke_edge_listpos"}
+_PRM_F64 = ["Ks", "ThetaS", "ThetaR", "PoreSize", "AirEBubPres", "DecayF", "SatAnRatio", "UnsatAnRatio", "bedrock"]
+_PRM_SC = ["BasArea", "BasArea_flow", "IntStormMAX", "surfaceSoilDepth", "rootZoneDepth", "velcoef", "velratio",
+           "flowexp", "baseflow", "kincoef", "dtReff", "outlet_contr_area", "tstep", "gwstep", "etistep",
+           "output_interval"]
+_PRM_INT = ["EToption", "Ioption", "SnOpt", "RdstrOption"]
+
+
+class GpuBasin:
+    """Owns one tribs_handle_t. `basin` is a dict of flattened arrays in sweep order."""
+
+    def __init__(self, basin: dict):
+        self.L = load()
+        b = basin
+        self.n = int(b["n_active"][0])
+        self._keep = []
+        mesh = Mesh()
+        mesh.n_cells = self.n
+        mesh.n_edges = int(b["spoke_rowptr"][-1])
+        for member, key in _MESH_F64.items():
+            a = np.ascontiguousarray(b[key], np.float64); self._keep.append(a); setattr(mesh, member, _d(a))
+        for member, key in _MESH_I32.items():
+            a = np.ascontiguousarray(b[key], np.int32); self._keep.append(a); setattr(mesh, member, _i(a))
+        prm = Params()
+        for key in _PRM_F64:
+            a = np.ascontiguousarray(b[key], np.float64); self._keep.append(a); setattr(prm, key, _d(a))
+        for key in _PRM_SC:
+            setattr(prm, key, float(b[key][0]))
+        for key in _PRM_INT:
+            setattr(prm, key, int(b[key][0]))
+        prm.res_limit = int(b["res_limit"][0])
+        st = StateT()
+        for k, nm in enumerate(FIELDS):
+            src = b.get("init_" + nm)
+            if src is not None:
+                a = np.ascontiguousarray(src, np.float64); self._keep.append(a); st.f[k] = _d(a)
+        self.h = C.c_void_p()
+        _chk(self.L.tribs_gpu_init(C.byref(mesh), C.byref(prm), C.byref(st), None, C.byref(self.h)))
+        self.tstep = prm.tstep
+        self.gwstep = prm.gwstep
+        self.etistep = prm.etistep
+        self.n_stream = self.L.tribs_gpu_n_stream(self.h)
+        self._keep.clear()
+
+    def step(self, phases: int, current_time: float, elapsed_steps: int, hourly_reset: int,
+             rain=None, qstrm=None, qstrm_outlet: float = 0.0):
+        s = Step()
+        s.current_time = current_time
+        s.dt = self.tstep
+        s.dt_gw = self.gwstep
+        s.elapsed_steps = elapsed_steps
+        s.hourly_reset = hourly_reset
+        if rain is None:
+            s.rain_mode = RAIN_KEEP
+        elif np.isscalar(rain):
+            s.rain_mode = RAIN_UNIFORM
+            s.rain_uniform = float(rain)
+        else:
+            s.rain_mode = RAIN_PER_CELL
+            s.rain = _d(rain)
+        if qstrm is not None:
+            s.qstrm = _d(qstrm)
+        s.qstrm_outlet = qstrm_outlet
+        _chk(self.L.tribs_gpu_step(self.h, phases, C.byref(s)))
+
+    def sync(self, names, out: dict | None = None) -> dict:
+        out = {} if out is None else out
+        st = StateT()
+        mask = 0
+        for nm in names:
+            if nm not in out:
+                out[nm] = np.empty(self.n)
+            st.f[F[nm]] = _d(out[nm])
+            mask |= 1 << F[nm]
+        _chk(self.L.tribs_gpu_sync(self.h, mask, C.byref(st)))
+        return out
+
+    def push(self, arrays: dict):
+        st = StateT()
+        mask = 0
+        keep = []
+        for nm, a in arrays.items():
+            a = np.ascontiguousarray(a, np.float64); keep.append(a)
+            st.f[F[nm]] = _d(a)
+            mask |= 1 << F[nm]
+        _chk(self.L.tribs_gpu_push(self.h, mask, C.byref(st)))
+
+    def retrieve_qeff(self, current_time: float) -> np.ndarray:
+        out = np.empty(self.n_stream + 1)
+        _chk(self.L.tribs_gpu_retrieve_qeff(self.h, current_time, _d(out)))
+        return out
+
+    def stream_cells(self) -> np.ndarray:
+        out = np.empty(self.n_stream, np.int32)
+        _chk(self.L.tribs_gpu_stream_cells(self.h, _i(out)))
+        return out
+
+    def results(self, name: str, nbins: int) -> np.ndarray:
+        out = np.empty(nbins)
+        _chk(self.L.tribs_gpu_get_results(self.h, RESULTS.index(name), _d(out), nbins))
+        return out
+
+    def globals(self) -> dict:
+        out = np.empty(len(GLOBALS))
+        _chk(self.L.tribs_gpu_get_globals(self.h, _d(out)))
+        return dict(zip(GLOBALS, out))
+
+    def levels(self) -> int:
+        return self.L.tribs_gpu_sweep_levels(self.h)
+
+    def launch_count(self) -> int:
+        return int(self.L.tribs_gpu_launch_count(self.h))
+
+    def set_timing(self, on: bool):
+        _chk(self.L.tribs_gpu_set_timing(self.h, int(on)))
+
+    def phase_ms(self, reset=True):
+        out = np.zeros(4)
+        _chk(self.L.tribs_gpu_phase_ms(self.h, _d(out), int(reset)))
+        return dict(zip(["unsat", "sat", "route", "reset"], out))
+
+    def wait(self):
+        _chk(self.L.tribs_gpu_wait(self.h))
+
+    def stream_handle(self) -> int:
+        return int(self.L.tribs_gpu_stream(self.h) or 0)
+
+    def close(self):
+        if self.h:
+            self.L.tribs_gpu_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

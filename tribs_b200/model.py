@@ -1,0 +1,142 @@
+"""Host-side mirror of the reference call surface for the water-balance path.
+
+`tHydroModel`, `tKinemat` and `Simulator` below keep the reference's public method names,
+argument meaning and calling order (reference: src/tHydro/tHydroModel.h:45-106,
+src/tFlowNet/tKinemat.h:127-131, src/tSimulator/tSimul.cpp:220-295, 506-520) but their bodies
+only forward to the C ABI (include/tribs_gpu.h). The decisions the reference takes on the host
+with its own timer arithmetic (`fmod` on accumulated hours, tRunTimer.cpp:436-452) are taken
+here, on the host, in the same way and passed down as flags.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+from . import gpu
+
+
+class tRunTimer:
+    """The subset of the reference timer the path depends on (src/tSimulator/tRunTimer.cpp)."""
+
+    def __init__(self, tstep_h, gwstep_h, etistep_h, end_h):
+        self.tstep, self.gwstep, self.etistep, self.endTime = tstep_h, gwstep_h, etistep_h, end_h
+        self.currentTime = 0.0
+
+    def Advance(self, dt):
+        self.currentTime += dt
+        return self.currentTime < self.endTime
+
+    def IsFinished(self):
+        return self.currentTime >= self.endTime
+
+    def getCurrentTime(self):
+        return self.currentTime
+
+    def getTimeStep(self):
+        return self.tstep
+
+    def getGWTimeStep(self):
+        return self.gwstep
+
+    def getElapsedSteps(self, t):
+        return int(t / self.tstep)
+
+
+class tHydroModel:
+    """UnSaturatedZone / ResetGW / SaturatedZone / Reset forwarded to the GPU."""
+
+    def __init__(self, dev: gpu.GpuBasin, timer: tRunTimer):
+        self.dev, self.timer = dev, timer
+        self._gw_reset_pending = False
+
+    def _flags(self):
+        t = self.timer
+        now = t.getCurrentTime()
+        hourly = int(not math.fmod(now - t.getTimeStep(), t.etistep))   # tHydroModel.cpp:700-702
+        return now, t.getElapsedSteps(now), hourly
+
+    def UnSaturatedZone(self, dt):
+        now, el, hr = self._flags()
+        self.dev.step(gpu.PHASE_UNSAT, now, el, hr)
+
+    def ResetGW(self):
+        # folded into the SAT phase (a pointer swap on the device); kept for call-surface parity
+        self._gw_reset_pending = True
+
+    def SaturatedZone(self, dtGW):
+        if not self._gw_reset_pending:
+            raise RuntimeError("SaturatedZone() must follow ResetGW(), as in Simulator::SubSurfaceHydroProcesses")
+        self._gw_reset_pending = False
+        now, el, hr = self._flags()
+        self.dev.step(gpu.PHASE_SAT, now, el, hr)
+
+    def Reset(self):
+        now, el, hr = self._flags()
+        self.dev.step(gpu.PHASE_RESET, now, el, hr)
+
+
+class tKinemat:
+    """SurfaceFlow(): hillslope routing + basin accumulations on the GPU; the kinematic-wave
+    channel solver stays with the host model and consumes `lateral_inflow`."""
+
+    def __init__(self, dev: gpu.GpuBasin, timer: tRunTimer):
+        self.dev, self.timer = dev, timer
+        self.lateral_inflow = None
+
+    def SurfaceFlow(self, fetch_qeff: bool = True):
+        now = self.timer.getCurrentTime()
+        self.dev.step(gpu.PHASE_ROUTE, now, self.timer.getElapsedSteps(now), 0)
+        if fetch_qeff:
+            self.lateral_inflow = self.dev.retrieve_qeff(now)
+
+
+class Simulator:
+    """simulation_loop() for the path: Advance, rain, UnSat, [ResetGW, Sat], SurfaceFlow, Reset."""
+
+    def __init__(self, basin: dict, rain_schedule=None, gw_on: bool | None = None):
+        self.dev = gpu.GpuBasin(basin)
+        b = basin
+        self.timer = tRunTimer(float(b["tstep"][0]), float(b["gwstep"][0]), float(b["etistep"][0]),
+                               float(b["endtime"][0]))
+        self.hydro = tHydroModel(self.dev, self.timer)
+        self.flow = tKinemat(self.dev, self.timer)
+        self.rain_schedule = rain_schedule
+        self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
+        self.step_no = 0
+
+    def UpdatePrecipitationInput(self):
+        if self.rain_schedule is None:
+            return
+        r = self.rain_schedule(self.timer.getCurrentTime())
+        now = self.timer.getCurrentTime()
+        self.dev.step(0, now, self.timer.getElapsedSteps(now), 0, rain=r)
+
+    def SubSurfaceHydroProcesses(self):
+        t = self.timer
+        self.hydro.UnSaturatedZone(t.getTimeStep())
+        gw_label = math.fmod(t.getCurrentTime(), t.getGWTimeStep())      # tSimul.cpp:511
+        if self.gw_on and not gw_label:
+            self.hydro.ResetGW()
+            self.hydro.SaturatedZone(t.getGWTimeStep())
+            return True
+        return False
+
+    def advance(self):
+        self.timer.Advance(self.timer.getTimeStep())
+        self.step_no += 1
+
+    def one_step(self, fetch_qeff=True):
+        self.advance()
+        self.UpdatePrecipitationInput()
+        did_gw = self.SubSurfaceHydroProcesses()
+        self.flow.SurfaceFlow(fetch_qeff)
+        self.hydro.Reset()
+        return did_gw
+
+    def simulation_loop(self, max_steps=None):
+        k = 0
+        while not self.timer.IsFinished() and (max_steps is None or k < max_steps):
+            self.one_step()
+            k += 1
+        return k

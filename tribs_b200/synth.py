@@ -2,7 +2,7 @@
 
 Writes a complete, self-contained reference-format input deck (``.in`` control
 file, points file, soil/land tables, ASCII grids) for a V-shaped valley TIN, so
-that the *unmodified* reference serial model (``oracle/_ref``) and the B200 path
+that the *unmodified* reference serial model and the B200 path
 are driven from identical files.
 
 Formats follow the reference readers:
