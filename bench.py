@@ -1,0 +1,368 @@
+#!/usr/bin/env python
+"""bench.py — Voronoi cell-timesteps/s of the per-timestep water balance on B200.
+
+A "step" is one reference time step of the hot path over the whole synthetic basin:
+UnSaturatedZone every step, ResetGW+SaturatedZone every GWSTEP/TIMESTEP-th step (8th at the
+standard 3.75 min / 30 min), hillslope routing + basin accumulations and Reset every step.
+
+  value  device-resident throughput (rain already on the device), CUDA-event timed on the
+         library's compute stream, max over ranks.
+  e2e    the same loop through the C ABI with HOST buffers: every step uploads a per-cell
+         rain array from pinned host memory and reads back what the host model consumes each
+         step (the stream cells' lateral inflow for the channel router + basin accumulators).
+  --impl reference   the unmodified reference (oracle/_ref/tribs_ref_harness) on the host CPU.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "voronoi_cell_timesteps_per_sec"
+UNIT = "cell-timesteps/s"
+# compulsory bytes per cell and invocation of the dominant kernel (unsat sweep)
+UNSAT_BYTES_PER_CELL = 520.0
+STEP_BYTES_PER_CELL = 677.0      # whole step, storm-only configuration
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._halt = index, [], threading.Event()
+
+    def run(self):
+        while not self._halt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(",")])
+            except Exception:
+                pass
+            self._halt.wait(0.2)
+
+    def stop(self):
+        self._halt.set()
+        self.join(timeout=3)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[k] for r in self.rows if len(r) >= 6 for k in range(4) if r[2 + k].lower() == "active"})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def storm_rain(t, pmean=20.0, stdur=6.0, istdur=18.0):
+    """STOCHASTICMODE 1 as the reference runs it: one storm, then dry (tSimul.cpp:386-406)."""
+    return pmean if t <= stdur else 0.0
+
+
+# -------------------------------------------------------------------------------- GPU arm
+def run_gpu(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tribs_b200 import gpu
+    from tribs_b200.model import Simulator
+    from tribs_b200.synthbasin import build_basin
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; tribs_b200 has no CPU path (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    side = args.side
+    basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9)
+    n = int(basin["n_active"][0])
+    sim = Simulator(basin, rain_schedule=None)
+    dev = sim.dev
+    gw_every = int(round(dev.gwstep / dev.tstep))
+    stream = torch.cuda.ExternalStream(dev.stream_handle())
+    n_stream = dev.n_stream
+
+    pinned_rain = torch.empty(n, dtype=torch.float64).pin_memory()
+    rain_np = pinned_rain.numpy()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def resident_step():
+        sim.advance()
+        t = sim.timer.getCurrentTime()
+        dev.step(0, t, sim.timer.getElapsedSteps(t), 0, rain=storm_rain(t))   # tRainfall::NewRain(double)
+        sim.SubSurfaceHydroProcesses()
+        sim.flow.SurfaceFlow(fetch_qeff=False)
+        sim.hydro.Reset()
+
+    def e2e_step():
+        sim.advance()
+        t = sim.timer.getCurrentTime()
+        rain_np.fill(storm_rain(t))            # the host model's per-cell rain (tRainfall::NewRain)
+        dev.step(0, t, sim.timer.getElapsedSteps(t), 0, rain=rain_np)
+        sim.SubSurfaceHydroProcesses()
+        sim.flow.SurfaceFlow(fetch_qeff=True)  # D2H: lateral inflow for the channel router
+        g = dev.globals()                       # D2H: basin accumulators
+        sim.hydro.Reset()
+        return g
+
+    B = max(1, args.batch)
+    pinned_rows = torch.empty((B, n), dtype=torch.float64).pin_memory() if B > 1 else None
+
+    def host_steps(k, rows=None):
+        t = sim.timer
+        out = []
+        for q in range(k):
+            sim.advance()
+            now = t.getCurrentTime()
+            r = storm_rain(now)
+            if rows is not None:
+                rows[q].fill_(r)
+                r = rows[q].numpy()
+            out.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
+                            hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
+                            sat=bool(sim.gw_on and not math.fmod(now, t.getGWTimeStep())), rain=r))
+        return out
+
+    def resident_batch(k):
+        dev.run(host_steps(k))
+
+    def e2e_batch(k):
+        dev.run(host_steps(k, pinned_rows))      # H2D: k per-cell rain arrays
+        q = dev.retrieve_qeff_steps(k)           # D2H: per-step lateral inflow for the channel router
+        g = dev.globals()                         # D2H: basin accumulators
+        return q, g
+
+    def loop(fn_single, fn_batch, k):
+        if B <= 1:
+            for _ in range(k):
+                fn_single()
+            return
+        done = 0
+        while done < k:
+            kk = min(B, k - done)
+            fn_batch(kk)
+            done += kk
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0 = time.perf_counter()
+        e0.record(stream)
+        fn(k)
+        e1.record(stream)
+        dev.wait()
+        w1 = time.perf_counter()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            tt = torch.tensor([ms], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        return ms, (w1 - w0) * 1e3
+
+    loop(resident_step, resident_batch, args.warmup)
+    dev.set_timing(True)
+    dev.phase_ms(reset=True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    l0 = dev.launch_count()
+    ms, wall_ms = timed(lambda k: loop(resident_step, resident_batch, k), args.steps)
+    launches = dev.launch_count() - l0
+    clocks = sampler.stop()
+    phases = dev.phase_ms(reset=True)
+    dev.set_timing(False)
+    # the phase timers only see the kernels; the step time also has launch gaps
+    n_unsat = args.steps
+    unsat_ms = phases["unsat"] / max(n_unsat, 1)
+
+    loop(e2e_step, e2e_batch, max(3, args.warmup // 2))
+    ems, ewall = timed(lambda k: loop(e2e_step, e2e_batch, k), args.steps)
+    # host work (numpy fill, ctypes) is part of the user-visible e2e time: use the wall clock
+    e2e_ms = max(ems, ewall)
+    if world > 1:
+        tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_ms = float(tt.item())
+
+    total_cells = n * world
+    value = total_cells * args.steps / (ms * 1e-3)
+    e2e = total_cells * args.steps / (e2e_ms * 1e-3)
+    peak, peak_kind = peaks()
+    achieved = UNSAT_BYTES_PER_CELL * n / (unsat_ms * 1e-3) / 1e9 if unsat_ms > 0 else 0.0
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"synthetic {n / 1e6:.2f}M-cell V-valley TIN per GPU, uniform storm 20 mm/h, "
+                               f"TIMESTEP 3.75 min, GWSTEP 30 min (sat zone every {gw_every}th step), ET/snow off",
+                   "cells_per_gpu": n, "stream_cells_per_gpu": n_stream, "sweep_levels": dev.levels(),
+                   "l2": "state arrays (52 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
+                   "batch_steps": B,
+                   "parallelism": "1 GPU" if world == 1 else f"{world} independent basin replicas (no halo exchange yet)"},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+                "d2h_bytes_per_step": 8 * (n_stream + 1) + 8 * len(gpu.GLOBALS)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "pipeline_kernel" if B > 1 else "unsat_sweep_kernel", "achieved": achieved, "peak": peak,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "peak_source": peak_kind, "bytes_per_cell": UNSAT_BYTES_PER_CELL,
+                     "avg_launch_ms": unsat_ms,
+                     "note": "the sweep is bound by the within-step Qpin dependency chain "
+                             f"({dev.levels()} levels), not by HBM; see DESIGN.md"},
+        "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline_sample()
+    if rank == 0:
+        print(json.dumps(line))
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# -------------------------------------------------------------------------------- CPU arms
+def _harness():
+    from refrun import HARNESS, have_harness
+    return HARNESS if have_harness() else None
+
+
+def _run_reference_sample(n_side: int, hours: float, procs: int = 1):
+    """Runs `procs` concurrent copies of the unmodified serial reference on an n_side^2-point
+    V-valley deck for `hours`; returns aggregate cell-timesteps/s of their simulation loops."""
+    import tempfile
+    from refrun import HARNESS
+    from tribs_b200.synth import BasinSpec, write_basin
+    ps, dirs = [], []
+    for k in range(procs):
+        d = tempfile.mkdtemp(prefix="tribsbench_")
+        write_basin(BasinSpec(n=n_side, runtime_h=hours, seed=1 + k), d)
+        dirs.append(d)
+    t0 = time.perf_counter()
+    for d in dirs:
+        ps.append(subprocess.Popen([HARNESS, "basin.in", "-K", "--out", d, "--no-basin"], cwd=d,
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True))
+    rate, cells, steps = 0.0, 0, 0
+    for p in ps:
+        out = p.communicate()[0]
+        for ln in out.splitlines():
+            if ln.startswith("ref_timing"):
+                j = json.loads(ln[len("ref_timing "):])
+                rate += j["cell_steps_per_s"]
+                cells, steps = j["cells"], j["steps"]
+    wall = time.perf_counter() - t0
+    import shutil
+    for d in dirs:
+        shutil.rmtree(d, ignore_errors=True)
+    return rate, cells, steps, wall
+
+
+def cpu_baseline_sample():
+    if _harness():
+        rate, cells, steps, wall = _run_reference_sample(120, 12.0, 1)
+        return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": f"unmodified serial reference (g++ -O2), {cells}-cell V-valley of the same generator, "
+                          f"{steps} steps (12 h, storm), simulation_loop only; {wall:.1f} s wall incl. setup"}
+    import numpy as np
+    from oracle.pyoracle import OracleModel
+    from tribs_b200.synthbasin import build_basin
+    b = build_basin(160, 160)
+    m = OracleModel(b, lambda t: storm_rain(t))
+    t0 = time.perf_counter()
+    for _ in range(96):
+        m.step()
+    dt = time.perf_counter() - t0
+    return {"value": int(b["n_active"][0]) * 96 / dt, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "C oracle (bit-exact restatement), 25.6k-cell synthetic V-valley, 96 steps"}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    total = args.steps + args.warmup
+    if _harness():
+        procs = max(1, min(cores, 32))
+        # size the sample so the whole run stays within a few minutes: ~150 s / total per step
+        budget = max(0.6, 150.0 / total)
+        n_side = int(max(24, min(100, math.sqrt(0.25e6 * budget / 192.0) + 2)))
+        vals = []
+        for k in range(total):
+            rate, cells, steps, wall = _run_reference_sample(n_side, 12.0, procs)
+            if k >= args.warmup:
+                vals.append((rate, wall))
+        value = statistics.mean(v[0] for v in vals)
+        ms = statistics.mean(v[1] for v in vals) * 1e3
+        kind = "reference"
+        sample = (f"{procs} concurrent processes of the unmodified serial reference (no MPI toolchain on the box, so "
+                  f"this is the optimistic all-core bound), each a {cells}-cell V-valley deck, {steps} steps")
+    else:
+        from oracle.pyoracle import OracleModel
+        from tribs_b200.synthbasin import build_basin
+        b = build_basin(96, 96)
+        m = OracleModel(b, lambda t: storm_rain(t))
+        vals = []
+        for k in range(total):
+            t0 = time.perf_counter()
+            for _ in range(32):
+                m.step()
+            dt = time.perf_counter() - t0
+            if k >= args.warmup:
+                vals.append(int(b["n_active"][0]) * 32 / dt)
+        value, ms, kind, procs = statistics.mean(vals), 0.0, "port", 1
+        sample = "C oracle port, 9.2k-cell synthetic V-valley, 32 steps per sample"
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "synthetic V-valley TIN, uniform storm 20 mm/h, TIMESTEP 3.75 min, GWSTEP 30 min, "
+                                   "ET/snow off (bounded CPU sample of the GPU arm's workload)"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--impl", default="tribs_b200", choices=["tribs_b200", "reference"])
+    ap.add_argument("--side", type=int, default=1000, help="cells per side of the synthetic basin (per GPU)")
+    ap.add_argument("--batch", type=int, default=64,
+                    help="steps per pipelined launch (tribs_gpu_run); 1 = one tribs_gpu_step sequence per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -150,6 +150,20 @@ int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *prm, const tr
  * compute stream; tribs_gpu_sync / the getters synchronise. */
 int tribs_gpu_step(tribs_handle_t h, uint32_t phase_mask, const tribs_step_t *s);
 
+/* Pipelined batch: run `n_steps` whole reference time steps (step k executes the phases in
+ * phase_masks[k]; every mask must contain UNSAT, ROUTE and RESET, SAT where the host's
+ * fmod(currentTime, GWSTEP) test says so) in ONE persistent launch. Cells advance through
+ * space-time as soon as their own inputs exist (upslope outflow of the same step, own and
+ * downslope state of the previous phase, Voronoi neighbours around a saturated-zone phase), so
+ * the long within-step dependency chain of one step overlaps with the next steps instead of
+ * serialising them. Results are bit-identical to n_steps single tribs_gpu_step calls. Forcing
+ * for all steps must be known up front (steps[k].rain_mode / rain_uniform / rain); requires
+ * flowexp == 0 (no channel feedback into hillslope velocities inside a batch).
+ * The per-step lateral inflows are kept for tribs_gpu_retrieve_qeff_steps. */
+int tribs_gpu_run(tribs_handle_t h, int n_steps, const tribs_step_t *steps, const uint32_t *phase_masks);
+/* out[k*(n_stream+1) + slot] for the steps of the last tribs_gpu_run */
+int tribs_gpu_retrieve_qeff_steps(tribs_handle_t h, int n_steps, double *out);
+
 /* Copy the fields selected by `field_mask` (TRIBS_MASK(...)) back into host SoA staging in
  * sweep order; the host shim scatters them into tCNode. Blocks until the data is on the host. */
 int tribs_gpu_sync(tribs_handle_t h, uint64_t field_mask, tribs_state_t *host);

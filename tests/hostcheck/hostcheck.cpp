@@ -36,7 +36,8 @@ void hc_unsat(int n, double **sf, int32_t **si, double **ef, double **fields, co
   DynView d;
   for (int k = 0; k < TRIBS_N_FIELDS; k++) d.f[k] = fields[k];
   ModelConst m{mc[0], mc[1], mc[2], mc[3], mc[4], mi[0], mi[1], mi[2], mi[3]};
-  StepConst t{dt, 0.0, now, elapsed, hourly_reset, 0.0};
+  StepConst t;
+  t.dt = dt; t.dt_gw = 0.0; t.now = now; t.elapsed = elapsed; t.hourly_reset = hourly_reset; t.psrf_last = 0.0;
   std::vector<double> qpin(n, 0.0);
   for (int i = 0; i < n; i++) {
     UnsatCellInputs u;
@@ -62,7 +63,8 @@ void hc_sat(int n, double **sf, int32_t **si, double **ef, double **fields, cons
   DynView d;
   for (int k = 0; k < TRIBS_N_FIELDS; k++) d.f[k] = fields[k];
   ModelConst m{mc[0], mc[1], mc[2], mc[3], mc[4], mi[0], mi[1], mi[2], mi[3]};
-  StepConst t{0.0, dtgw, now, elapsed, 0, psrf_last};
+  StepConst t;
+  t.dt = 0.0; t.dt_gw = dtgw; t.now = now; t.elapsed = elapsed; t.hourly_reset = 0; t.psrf_last = psrf_last;
   std::vector<double> elev(n), tr(n);
   for (int i = 0; i < n; i++) sat_prepare_cell(s, d, i, elev.data(), tr.data());
   for (int i = 0; i < n; i++) {

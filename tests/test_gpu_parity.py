@@ -90,3 +90,61 @@ def test_gpu_water_balance_closes(built):
     resid = gl["TotRain"] - gl["Stok"] - gl["TotMoist"] + gl["TotGWchange"]
     # lateral exports to the outlet node and the Newton tolerances leave a small residual
     assert abs(resid) < 0.02 * max(gl["TotRain"], 1.0), (gl, resid)
+
+
+# ------------------------------------------------------------------ pipelined batches (tribs_gpu_run)
+ALL_CHECK = ["NwtOld", "MuOld", "MiOld", "NtOld", "NfOld", "RuOld", "RiOld", "Qpout", "intstorm", "srf_hr", "cumsrf",
+             "SoilMoisture", "RootMoisture", "AvSoilMoisture", "Recharge", "hsrfOccur", "sbsrfOccur", "psrfOccur",
+             "satsrfOccur", "satOccur", "RechDisch", "esrf", "Transmissivity", "TTime", "FlowVelocity", "UnSatFlowIn"]
+
+
+@pytest.mark.parametrize("name,batch", [("deep", 8), ("shallow", 16), ("redistribute", 5), ("deep", 64)])
+def test_gpu_batch_is_bitwise_identical_to_single_steps(name, batch, built):
+    """tribs_gpu_run (space-time pipelined) must reproduce tribs_gpu_step exactly."""
+    basin, snaps, _ = load_golden(name)
+    n_steps = 320
+    a = GpuStepper(basin, _sched(basin))
+    qa = []
+    for _ in range(n_steps):
+        a.advance(); a.unsat()
+        if a.gw_due():
+            a.sat()
+        qa.append(a.route().copy()); a.reset()
+    b = GpuStepper(basin, _sched(basin))
+    qb = []
+    done = 0
+    while done < n_steps:
+        k = min(batch, n_steps - done)
+        b.sim.run_batch(k)
+        qb.append(b.sim.dev.retrieve_qeff_steps(k))
+        done += k
+    qb = np.concatenate(qb)
+    assert np.array_equal(np.array(qa), qb), "per-step lateral inflow differs"
+    fa, fb = a.get(ALL_CHECK), b.get(ALL_CHECK)
+    for f in ALL_CHECK:
+        assert np.array_equal(fa[f], fb[f]), f
+    for nm in ["mhydro", "HsrfRout", "SbsrfRout", "SatsrfRout", "crr", "msm", "mgw", "qunsat", "rmax", "rmin"]:
+        assert np.array_equal(a.result(nm), b.result(nm)), nm
+    assert a.globals() == b.globals()
+
+
+def test_gpu_batch_matches_live_reference_after_full_run(built):
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    spec = spec_for("deep", 48, runtime_h=36.0, seed=5)
+    n_steps = 36 * 16
+    basin, snaps, timing, _ = run_reference(spec, snap_from=n_steps, snap_to=n_steps, phases="r")
+    g = GpuStepper(basin, _sched(basin))
+    done = 0
+    while done < n_steps:
+        k = min(64, n_steps - done)
+        g.sim.run_batch(k)
+        done += k
+    got = g.get(["NwtOld", "MuOld", "NfOld", "NtOld", "cumsrf", "Qpout"])
+    pre = f"s{n_steps}_r_"
+    for f, r in (("NwtOld", "NwtNew"), ("MuOld", "MuNew"), ("NfOld", "NfNew"), ("NtOld", "NtNew"), ("cumsrf", "cumsrf"),
+                 ("Qpout", "Qpout")):
+        ref = snaps[pre + r]
+        err = np.abs(ref - got[f]) / np.maximum(np.abs(ref), ABS_FLOOR)
+        assert err.max() <= REL_TOL, (f, err.max())
+    assert np.abs(snaps[pre + "mhydro"] - g.result("mhydro")).max() <= REL_TOL * max(1e-6, np.abs(snaps[pre + "mhydro"]).max())

@@ -43,6 +43,11 @@ struct StepConst {
   double dt, dt_gw, now, elapsed;   // elapsed = (double)tRunTimer::getElapsedSteps(now)
   int32_t hourly_reset;
   double psrf_last;                 // psrf of the last swept cell (read by the saturated zone)
+  // forcing applied inside the sweep (pipelined batches): 0 keep the Rain array, 1 uniform, 2 per cell
+  int32_t rain_mode = 0;
+  double rain_uniform = 0.0;
+  const double *rain_cells = nullptr;   // device order
+  int32_t defer_esrf = 0;           // SAT: leave the raw satsrf in esrf, psrf_last is added later
 };
 
 TRIBS_HD void load_soil(Column &c, const StaticView &s, int i) {
@@ -118,15 +123,21 @@ TRIBS_HD void unsat_cell_load(UnsatCellInputs &u, const StaticView &s, const Dyn
   u.env.dest_nwt_old = dst >= 0 ? d.f[TRIBS_F_NwtOld][dst] : 0.0;
   u.env.dest_nf_old = dst >= 0 ? d.f[TRIBS_F_NfOld][dst] : 0.0;
 
+  double rain_i;
+  if (t.rain_mode == 0) rain_i = d.f[TRIBS_F_Rain][i];
+  else {
+    rain_i = (t.rain_mode == 1) ? t.rain_uniform : t.rain_cells[i];
+    d.f[TRIBS_F_Rain][i] = rain_i;   // tRainfall::NewRain
+  }
   double evsoi = d.f[TRIBS_F_EvapSoil][i], evveg = d.f[TRIBS_F_EvapDryCanopy][i];
   if (evsoi < 0.0) evsoi = 0.0;
   if (evveg < 0.0) evveg = 0.0;
   u.evsoi = evsoi; u.evveg = evveg;
   double ractual;
-  if (m.i_option == 0 && m.et_option == 0) ractual = d.f[TRIBS_F_Rain][i];
-  else if (m.i_option == 0 && m.et_option != 0) ractual = d.f[TRIBS_F_Rain][i] - evsoi - evveg;
+  if (m.i_option == 0 && m.et_option == 0) ractual = rain_i;
+  else if (m.i_option == 0 && m.et_option != 0) ractual = rain_i - evsoi - evveg;
   else if (m.i_option != 0 && m.et_option == 0) {
-    if (m.i_option != 1) ractual = d.f[TRIBS_F_Rain][i];
+    if (m.i_option != 1) ractual = rain_i;
     else ractual = d.f[TRIBS_F_NetPrecipitation][i];
   } else
     ractual = d.f[TRIBS_F_NetPrecipitation][i] - evsoi - evveg;
@@ -138,7 +149,7 @@ TRIBS_HD void unsat_cell_load(UnsatCellInputs &u, const StaticView &s, const Dyn
   }
   c.r = ractual;
   double thsurf = c.ks != 0.0 ? c.init_moist_z(0.) : 0.0;
-  if (c.ru0 == 0.0) u.kunsat = c.ks * pow(((thsurf - c.thr) / (c.ths - c.thr)), c.eps);
+  if (c.ru0 == 0.0) u.kunsat = c.ks * m_pow(((thsurf - c.thr) / (c.ths - c.thr)), c.eps);
   else u.kunsat = c.ru0;
 }
 
@@ -201,7 +212,7 @@ TRIBS_HD void sat_prepare_cell(const StaticView &s, const DynView &d, int i, dou
   if (nwt == 0.0) wt_elev[i] = s.z[i] - ((-s.psib[i]) / (cs * 1000.0));
   else wt_elev[i] = s.z[i] - (nwt / (cs * 1000.0));
   double f = s.f[i];
-  transm[i] = (s.ar[i] * s.ks[i] * (exp(-f * nwt) - exp(-f * s.bedrock[i])) / f);
+  transm[i] = (s.ar[i] * s.ks[i] * (m_exp(-f * nwt) - m_exp(-f * s.bedrock[i])) / f);
 }
 
 template <int MAXC>
@@ -258,7 +269,7 @@ TRIBS_HD double sat_gather(const StaticView &s, const DynView &d, int i, const d
   for (int k = 0; k < nq; k++) gw += q[k];
   if (best >= 0) {
     // the last edge of the cell in edge-list order decides which transmissivity is kept (2807, 2821)
-    d.f[TRIBS_F_Transmissivity][i] = best_pos ? t_i : s.ar[i] * s.ks[i] * exp(-s.f[i] * nwt_i) / s.f[i];
+    d.f[TRIBS_F_Transmissivity][i] = best_pos ? t_i : s.ar[i] * s.ks[i] * m_exp(-s.f[i] * nwt_i) / s.f[i];
   }
   return gw;
 }
@@ -280,6 +291,7 @@ TRIBS_HD int sat_cell(const StaticView &s, const DynView &d, int i, double gw, c
 
   double esrf = t.psrf_last + c.satsrf;  // stale psrf member of the unsaturated sweep (3439)
   esrf = esrf / c.cosv;
+  const double satsrf_raw = c.satsrf;
   double satsrf = c.satsrf / c.cosv;
   double srf = satsrf;
 
@@ -290,7 +302,7 @@ TRIBS_HD int sat_cell(const StaticView &s, const DynView &d, int i, double gw, c
   d.f[TRIBS_F_srf][i] = srf_tot;
   d.f[TRIBS_F_cumsrf][i] += srf_tot;  // reference double-counts here (3460-3461)
   d.f[TRIBS_F_satsrf][i] = satsrf * dtgw;
-  d.f[TRIBS_F_esrf][i] = esrf * dtgw;
+  d.f[TRIBS_F_esrf][i] = t.defer_esrf ? satsrf_raw : esrf * dtgw;
   if (satsrf > 0.0) d.f[TRIBS_F_satsrfOccur][i] = d.f[TRIBS_F_satsrfOccur][i] + floor(satsrf * 1.0E+3) + 1.0E-6;
   if (c.surf_soil_moist(1.0) / c.ths > 0.999) d.f[TRIBS_F_satOccur][i] = d.f[TRIBS_F_satOccur][i] + 1;
   d.f[TRIBS_F_RechDisch][i] = d.f[TRIBS_F_RechDisch][i] + ((c.nwt0 - c.nwt1) + satsrf * dtgw * c.cosv / c.ths) * 1.0E-3;

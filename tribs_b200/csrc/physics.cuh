@@ -29,6 +29,19 @@
 
 namespace tribs {
 
+// One out-of-line copy of each libm routine per kernel: the state machines call them from
+// ~150 sites, and inlining every call makes the sweep kernel > 600 KB of SASS (instruction-cache
+// misses on a latency-bound chain). A call costs ~20 cycles against several hundred of math.
+#if defined(__CUDA_ARCH__)
+#define TRIBS_MATH __device__ __noinline__
+#else
+#define TRIBS_MATH inline
+#endif
+TRIBS_MATH double m_exp(double x) { return exp(x); }
+TRIBS_MATH double m_log(double x) { return log(x); }
+TRIBS_MATH double m_pow(double x, double y) { return pow(x, y); }
+TRIBS_MATH double m_expm1(double x) { return expm1(x); }
+
 constexpr double kRefPi = 3.1415926;       // src/Headers/Definitions.h:54 (8 digits, on purpose)
 constexpr double kLambEps = 2.2204E-16;    // src/tHydro/tHydroModel.h:32
 constexpr double kRadar = 0.1;             // mm/h, tHydroModel.cpp:751
@@ -57,9 +70,9 @@ struct Column {
     double dm = 0.0;
     if (nwt >= fabs(psib)) {
       if (lam_one())
-        dm = thr * (nwt + psib) - fabs(psib) * (ths - thr) * log((-psib) / nwt) - ths * psib;
+        dm = thr * (nwt + psib) - fabs(psib) * (ths - thr) * m_log((-psib) / nwt) - ths * psib;
       else
-        dm = thr * (nwt + psib) - ths * psib - (ths - thr) / (lam - 1.0) * (psib + nwt * pow((-psib / nwt), lam));
+        dm = thr * (nwt + psib) - ths * psib - (ths - thr) / (lam - 1.0) * (psib + nwt * m_pow((-psib / nwt), lam));
     } else if (nwt == 0.0) {
       dm = 0.0;
     } else {
@@ -72,15 +85,15 @@ struct Column {
     double dm;
     if (nf <= (nwt + psib)) {
       if (lam_one())
-        dm = thr * nf + fabs(psib) * (ths - thr) * log(nwt / (nwt - nf));
+        dm = thr * nf + fabs(psib) * (ths - thr) * m_log(nwt / (nwt - nf));
       else
         dm = thr * nf - (ths - thr) / (lam - 1.0) *
-                            ((nf - nwt) * pow((psib / (nf - nwt)), lam) + nwt * pow((-psib / nwt), lam));
+                            ((nf - nwt) * m_pow((psib / (nf - nwt)), lam) + nwt * m_pow((-psib / nwt), lam));
     } else {
       if (lam_one())
         dm = total_moist(nwt) + ths * psib + ths * (nf - (nwt + psib));
       else
-        dm = thr * (nwt + psib) - (ths - thr) / (lam - 1.0) * (psib + nwt * pow((-psib / nwt), lam)) +
+        dm = thr * (nwt + psib) - (ths - thr) / (lam - 1.0) * (psib + nwt * m_pow((-psib / nwt), lam)) +
              ths * (nf - (nwt + psib));
     }
     return dm;
@@ -90,10 +103,10 @@ struct Column {
     double dm;
     if (nf <= (nwt + psib)) {
       if (lam_one())
-        dm = thr * (nwt + psib - nf) - fabs(psib) * (ths - thr) * log((-psib) / (nwt - nf)) - ths * psib;
+        dm = thr * (nwt + psib - nf) - fabs(psib) * (ths - thr) * m_log((-psib) / (nwt - nf)) - ths * psib;
       else
         dm = thr * (nwt + psib - nf) - ths * psib -
-             (ths - thr) / (lam - 1.0) * (psib + (nwt - nf) * pow((psib / (nf - nwt)), lam));
+             (ths - thr) / (lam - 1.0) * (psib + (nwt - nf) * m_pow((psib / (nf - nwt)), lam));
     } else
       dm = ths * (nwt - nf);
     return dm;
@@ -101,41 +114,41 @@ struct Column {
 
   // moisture held by an unsaturated wedge that reaches depth d with the top at the surface
   TRIBS_HD double wedge_cap(double d) const {
-    return eps / f * (ths - thr) * (1.0 - exp(-f * d / eps)) + thr * d;
+    return eps / f * (ths - thr) * (1.0 - m_exp(-f * d / eps)) + thr * d;
   }
 
   TRIBS_HD double init_moist_z(double nf) const {
     if (nf >= (nwt0 + psib)) return ths;
-    return (thr + (ths - thr) * pow((psib / (nf - nwt0)), lam));
+    return (thr + (ths - thr) * m_pow((psib / (nf - nwt0)), lam));
   }
   TRIBS_HD double edge_moist_z(double nf) const {
-    return (thr + exp(f * nf / eps) * (ths - thr) * pow((ru1 / ks), (1.0 / eps)));
+    return (thr + m_exp(f * nf / eps) * (ths - thr) * m_pow((ru1 / ks), (1.0 / eps)));
   }
 
   TRIBS_HD void suction(double nf) {
     if (thre == ths) {
-      double sein = pow(((thri - thr) / (ths - thr)), (3. + 1. / (lam * exp(-f * nf / 2.))));
-      g = -psib * (1. - sein) / (3 * lam * exp(-f * nf / 2.) + 1.);
+      double sein = m_pow(((thri - thr) / (ths - thr)), (3. + 1. / (lam * m_exp(-f * nf / 2.))));
+      g = -psib * (1. - sein) / (3 * lam * m_exp(-f * nf / 2.) + 1.);
     } else {
-      double sein = pow(((thri - thr) / (ths - thr)), (3. + 1. / (lam * exp(-f * nf / 2.))));
-      double se0 = pow(((thre - thr) / (ths - thr)), (3. + 1. / (lam * exp(-f * nf / 2.))));
-      g = -psib * (se0 - sein) / (3.0 * lam * exp(-f * nf / 2.) + 1.);
+      double sein = m_pow(((thri - thr) / (ths - thr)), (3. + 1. / (lam * m_exp(-f * nf / 2.))));
+      double se0 = m_pow(((thre - thr) / (ths - thr)), (3. + 1. / (lam * m_exp(-f * nf / 2.))));
+      g = -psib * (se0 - sein) / (3.0 * lam * m_exp(-f * nf / 2.) + 1.);
     }
   }
 
   TRIBS_HD double recharge_rate(double dm, double nf) const {
     double bb = (dm - thr * nf) / (ths - thr);
-    bb = bb * f / (eps * expm1(f * nf / eps));
-    return (ks * pow(bb, eps));
+    bb = bb * f / (eps * m_expm1(f * nf / eps));
+    return (ks * m_pow(bb, eps));
   }
   TRIBS_HD double unsat_lateral(double nf, double ru, double vel) const { return (nf * ru * (uar - 1.0) * vel); }
   TRIBS_HD double sat_lateral(double nt, double nf, double ru, double vel) const {
     double bb;
     if (nt == 0.0)
-      bb = (ks * uar / f * (1. - exp(-f * nf)) - ks * f * nf * nf / expm1(f * nf)) * vel;
+      bb = (ks * uar / f * (1. - m_exp(-f * nf)) - ks * f * nf * nf / m_expm1(f * nf)) * vel;
     else {
-      bb = nt * ru * (uar - 1.0) + ks * uar / f * (exp(-f * nt) - exp(-f * nf));
-      bb = (bb - ks * f * (nf - nt) * (nf - nt) / (exp(f * nf) - exp(f * nt))) * vel;
+      bb = nt * ru * (uar - 1.0) + ks * uar / f * (m_exp(-f * nt) - m_exp(-f * nf));
+      bb = (bb - ks * f * (nf - nt) * (nf - nt) / (m_exp(f * nf) - m_exp(f * nt))) * vel;
     }
     return bb;
   }
@@ -147,7 +160,7 @@ struct Column {
     qpout *= sinv;
   }
   // surface-saturated conductance integral Ks*F*Nf/(e^{F Nf}-1)
-  TRIBS_HD double ksat_mean(double nf) const { return ks * f * nf / expm1(f * nf); }
+  TRIBS_HD double ksat_mean(double nf) const { return ks * f * nf / m_expm1(f * nf); }
 
   // -------------------------------------------------------------- surface soil moisture
   TRIBS_HD double surf_soil_moist(double z) {
@@ -158,9 +171,9 @@ struct Column {
       dm = upper_moist(z, nwt1);
     else if (nf1 > 0.0 && nt1 == nf1 && nf1 < nwt1) {
       if (fabs(ru1) > 1.0E-6) {
-        nstar = log(ks / ru1) / f;
+        nstar = m_log(ks / ru1) / f;
         if (nf1 >= z)
-          dm = eps / f * (ths - thr) * (exp(f * (z - nstar) / eps) - exp(-f * nstar / eps)) + thr * z;
+          dm = eps / f * (ths - thr) * (m_exp(f * (z - nstar) / eps) - m_exp(-f * nstar / eps)) + thr * z;
         else {
           dm = upper_moist(z, nwt1);
           dm += (mu1 - mi1);
@@ -170,10 +183,10 @@ struct Column {
     } else if (nf1 > 0.0 && nt1 < nf1 && nt1 > 0.0) {
       nstar = nt1;
       if (nt1 >= z)
-        dm = eps / f * (ths - thr) * (exp(f * (z - nstar) / eps) - exp(-f * nstar / eps)) + thr * z;
+        dm = eps / f * (ths - thr) * (m_exp(f * (z - nstar) / eps) - m_exp(-f * nstar / eps)) + thr * z;
       else {
         if (nf1 >= z) {
-          dm = eps / f * (ths - thr) * (1.0 - exp(-f * nt1 / eps)) + thr * nt1;
+          dm = eps / f * (ths - thr) * (1.0 - m_exp(-f * nt1 / eps)) + thr * nt1;
           dm += ((z - nt1) * ths);
         } else if (nf1 < z) {
           dm = upper_moist(z, nwt1);
@@ -192,9 +205,9 @@ struct Column {
   }
 
   TRIBS_HD double z1z2_base(double z1, double z2, double nwt) const {
-    if (lam_one()) return thr * (z2 - z1) - fabs(psib) * (ths - thr) * log((nwt - z2) / (nwt - z1));
+    if (lam_one()) return thr * (z2 - z1) - fabs(psib) * (ths - thr) * m_log((nwt - z2) / (nwt - z1));
     return thr * (z2 - z1) - (ths - thr) / (lam - 1.0) *
-                                 ((z2 - nwt) * pow((-psib / (nwt - z2)), lam) - (z1 - nwt) * pow((-psib / (nwt - z1)), lam));
+                                 ((z2 - nwt) * m_pow((-psib / (nwt - z2)), lam) - (z1 - nwt) * m_pow((-psib / (nwt - z1)), lam));
   }
   // the reference recurses once at most (3676-3681); unrolled here
   TRIBS_HD double z1z2_moist(double z1, double z2, double nwt) const {
@@ -212,13 +225,13 @@ struct Column {
 
   // -------------------------------------------------------------- root finders
   TRIBS_HD void poly_wt(double x, double &fv, double &dv, double c1, double c2, double c3) const {
-    fv = c1 * pow(x, lam) + c3 * pow(x, (lam - 1.0)) + c2;
-    dv = c1 * lam * pow(x, (lam - 1.0)) + c3 * (lam - 1.0) * pow(x, (lam - 2.0));
+    fv = c1 * m_pow(x, lam) + c3 * m_pow(x, (lam - 1.0)) + c2;
+    dv = c1 * lam * m_pow(x, (lam - 1.0)) + c3 * (lam - 1.0) * m_pow(x, (lam - 2.0));
   }
   TRIBS_HD void poly_front(double x, double nwt, double &fv, double &dv, double c1, double c2, double c3) const {
-    fv = c1 * x * pow((nwt - x), (lam - 1.0)) + c3 * pow((nwt - x), (lam - 1.0)) - c2;
-    dv = c1 * pow((nwt - x), (lam - 1.0)) - c1 * (lam - 1.0) * x * pow((nwt - x), (lam - 2.0)) -
-         c3 * (lam - 1.0) * pow((nwt - x), (lam - 2.0));
+    fv = c1 * x * m_pow((nwt - x), (lam - 1.0)) + c3 * m_pow((nwt - x), (lam - 1.0)) - c2;
+    dv = c1 * m_pow((nwt - x), (lam - 1.0)) - c1 * (lam - 1.0) * x * m_pow((nwt - x), (lam - 2.0)) -
+         c3 * (lam - 1.0) * m_pow((nwt - x), (lam - 2.0));
   }
 
   // safeguarded Newton / bisection in a bracket (4094-4167), 30 iterations at most
@@ -259,7 +272,7 @@ struct Column {
     const double kDmin = 1.0E-5, kDxTol = 1.0E-5;
     double c1, c2, c3, fvalue = 0, fdvalue = 0, x = 0, dx = 0, xinit, xup, est = 0;
     c1 = ths - thr;
-    c2 = c1 * pow((-psib), lam) / (lam - 1.0);
+    c2 = c1 * m_pow((-psib), lam) / (lam - 1.0);
     c3 = c1 * psib / (lam - 1.0) + psib * c1 - dm;
     if (nwt == 0.0) {
       xinit = dm * (lam - 1.0) / ((ths - thr) * lam) - psib;
@@ -291,8 +304,8 @@ struct Column {
   TRIBS_HD_NOINLINE double solve_front(double dm, double nwt, double nf, int flag) const {
     double c1, c2, c3, fvalue, fdvalue, x, dx = 0;
     if (!flag) c1 = ths - thr; else c1 = -(ths - thr);
-    c2 = c1 * pow((-psib), lam) / (lam - 1);
-    c3 = c2 / pow((nwt - nf), (lam - 1)) - c1 * nf + dm;
+    c2 = c1 * m_pow((-psib), lam) / (lam - 1);
+    c3 = c2 / m_pow((nwt - nf), (lam - 1)) - c1 * nf + dm;
     int i;
     for (x = nf, i = 0; i < 30; x -= dx, i++) {
       poly_front(x, nwt, fvalue, fdvalue, c1, c2, c3);
@@ -338,36 +351,36 @@ TRIBS_HD_NOINLINE double lambert_w(double z) {
   Cx w, v, tt, ttt, t, p;
   double xx, xy = 0.0, c, fq;
   if (z == 0.0) return 0.0;
-  xx = 2.0 * exp(1.0) * z + 2.0;
+  xx = 2.0 * m_exp(1.0) * z + 2.0;
   if (xx < 0.0) { xx = fabs(xx); xx = sqrt(xx); w = Cx{-1.0, xx}; }
   else { xx = sqrt(xx) - 1.0; w = Cx{xx, 0}; }
   xx = fabs(z);
-  xx = log(xx);
+  xx = m_log(xx);
   if (z < 0.0) v = Cx{xx, kRefPi}; else v = Cx{xx, 0};
   if (z > 1.0) {
-    xy = log(xx);
+    xy = m_log(xx);
     tt = Cx{xy, 0};
     v = cx_sub(v, tt);
   } else if (z == 1.0) {
     tt = Cx{0, 0};
   } else if (z < 1.0 && z > 0.0) {
-    xy = log(fabs(xx));
+    xy = m_log(fabs(xx));
     tt = Cx{xy, kRefPi};
     v = cx_sub(v, tt);
   } else if (z < 0.0 && z > -1.0) {
     xx = atan(v.i / v.r);
-    xy = log(fabs(v.r / cos(xx)));
+    xy = m_log(fabs(v.r / cos(xx)));
     xx += kRefPi;
     tt = Cx{xy, xx};
     v = cx_sub(v, tt);
   }
-  c = fabs(z + 1.0 / exp(1.0));
+  c = fabs(z + 1.0 / m_exp(1.0));
   if (c > 1.45) w = v;
   int n = 0;
   t = Cx{1000, 1000};
   // loop test keeps the reference's && / || precedence (3893)
   while (((n < 15) && (fabs(t.r) > xy)) || (fabs(t.i) > xx)) {
-    xx = exp(w.r);
+    xx = m_exp(w.r);
     p = Cx{xx * cos(w.i), xx * sin(w.i)};
     t = cx_mul(w, p);
     t.r = t.r - z;
@@ -439,7 +452,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
           c.thri = c.init_moist_z(c.nf0);
           c.thre = c.ths;
           c.suction(c.nf0);
-          qn = c.ks * c.f * c.nf0 / expm1(c.f * c.nf0) * (c.cosv + c.g / c.nf0);
+          qn = c.ks * c.f * c.nf0 / m_expm1(c.f * c.nf0) * (c.cosv + c.g / c.nf0);
           xxsrf = qn - c.ri0 * c.cosv;
           if (c.r1 >= xxsrf) state = kPerchedSurfSat;
           else state = kStormToInter;
@@ -546,10 +559,10 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
       if (mdelt <= aa) {  // unsaturated wedge
         if (c.r1 == 0.0) {
           c.ru1 = c.ru0;
-          nstar = (log(c.ks / c.ru1)) / c.f;
+          nstar = (m_log(c.ks / c.ru1)) / c.f;
         } else {
           c.ru1 = c.recharge_rate(mdelt, c.nf0);
-          nstar = (log(c.ks / c.ru1)) / c.f;
+          nstar = (m_log(c.ks / c.ru1)) / c.f;
         }
         (void)nstar;
         if ((100. * (c.mu1 - c.mi0) / c.mi0) <= 0.05) {
@@ -572,7 +585,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
             c.qpout = 0.0;
           } else {
             c.suction(c.nf0);
-            qn = c.ru1 * c.cosv + c.ks * exp(-c.f * c.nf0) * c.g / c.nf0;
+            qn = c.ru1 * c.cosv + c.ks * m_exp(-c.f * c.nf0) * c.g / c.nf0;
             c.nf1 = c.nf0 + dt * (qn - c.ri1 * c.cosv) / (c.thre - c.thri);
             c.nt1 = c.nf1;
             if (c.nf1 < (c.nwt1 + c.psib)) {
@@ -581,8 +594,8 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
               c.ru1 = c.recharge_rate(mdelt, c.nf1);
               aa = c.wedge_cap(c.nf1);
               if (mdelt > aa) {
-                c.nt1 = (log(c.ks / c.ru1)) / c.f;
-                c.ru1 = c.ks * exp(-c.f * c.nt1);
+                c.nt1 = (m_log(c.ks / c.ru1)) / c.f;
+                c.ru1 = c.ks * m_exp(-c.f * c.nt1);
               }
             } else if (c.nf1 >= (c.nwt1 + c.psib)) {
               if ((c.mu1 - c.mi0) > 1.0E-4) {
@@ -601,7 +614,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
         c.thri = c.init_moist_z(c.nf0);
         c.thre = c.ths;
         c.suction(c.nf0);
-        qn = c.ks * c.f * (c.nf0 - c.nt0) / (exp(c.f * c.nf0) - exp(c.f * c.nt0));
+        qn = c.ks * c.f * (c.nf0 - c.nt0) / (m_exp(c.f * c.nf0) - m_exp(c.f * c.nt0));
         qn *= (c.cosv + c.g / c.nf0);
         c.nf1 = c.nf0 + dt * (qn - c.ri1 * c.cosv) / (c.ths - c.thri);
         if (fabs(c.nf1 - (c.nwt1 + c.psib)) <= 1.0E-3) {
@@ -639,10 +652,10 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
             c.nt1 = c.nf1;
             if (mdelt >= mdva) c.mu1 -= mdelt - mdva + 1.0E-4;
           } else {
-            bb = -dt * (qn - c.r1) / (c.ths - c.thr) - c.eps / c.f * exp(-c.f * c.nt0 / c.eps);
-            aa = -exp(c.f * (bb - c.nt0) / c.eps);
+            bb = -dt * (qn - c.r1) / (c.ths - c.thr) - c.eps / c.f * m_exp(-c.f * c.nt0 / c.eps);
+            aa = -m_exp(c.f * (bb - c.nt0) / c.eps);
             c.nt1 = c.nt0 + (c.eps / c.f * lambert_w(aa) - bb);
-            c.ru1 = c.ks * exp(-c.f * c.nt1);
+            c.ru1 = c.ks * m_exp(-c.f * c.nt1);
           }
         }
       }
@@ -680,14 +693,14 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
       if (c.nf0 == 0.0 && c.nt0 == 0.0) {  // a wetting front is born
         c.thri = c.init_moist_z(0.0);
         if (c.r < kunsat && c.r1 / c.cosv < kunsat) {
-          c.thre = pow((c.r1 / c.ks), (1 / c.eps)) * (c.ths - c.thr) + c.thr;
+          c.thre = m_pow((c.r1 / c.ks), (1 / c.eps)) * (c.ths - c.thr) + c.thr;
           qn = c.r1;
           c.nf1 = dt * qn / (c.thre - c.thri);
         } else if (c.r1 < c.ks) {
-          c.thre = c.thr + (c.ths - c.thr) * pow((c.r1 / c.ks), (1 / c.eps));
+          c.thre = c.thr + (c.ths - c.thr) * m_pow((c.r1 / c.ks), (1 / c.eps));
           c.suction(0.0);
           if (fabs(c.thre - c.thri) < 1.0E-4) qn = c.r1;
-          else qn = c.ks * exp(-c.f * c.r1 / (c.thre - c.thri)) * c.g * (c.thre - c.thri) / c.r1 + c.r1;
+          else qn = c.ks * m_exp(-c.f * c.r1 / (c.thre - c.thri)) * c.g * (c.thre - c.thri) / c.r1 + c.r1;
           c.nf1 = dt * qn / (c.ths - c.thri);
         } else {
           c.thre = c.ths;
@@ -709,7 +722,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
             if (fabs(mdelt - aa) <= 1.0E-6) {
               c.nt1 = c.nf1;
               c.nf1 += 1.0E-5;
-              c.ru1 = c.ks * exp(-c.f * c.nt1);
+              c.ru1 = c.ks * m_exp(-c.f * c.nt1);
             } else if (mdelt >= c.nf1 * c.ths) {
               c.thri = c.init_moist_z(c.nf1);
               c.nf1 += (mdelt - c.nf1 * c.ths) / (c.ths - c.thri);
@@ -726,7 +739,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
               }
             } else if (mdelt < c.nf1 * c.ths) {
               c.ru1 = c.recharge_rate(mdelt, c.nf1);
-              c.nt1 = (log(c.ks / c.ru1)) / c.f;
+              c.nt1 = (m_log(c.ks / c.ru1)) / c.f;
               c.nf1 += 1.0E-5;
             }
           } else
@@ -740,7 +753,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
           c.thri = c.init_moist_z(c.nf0);
           c.thre = c.ths;
           c.suction(c.nf0);
-          qn = c.ks * c.f * c.nf0 / expm1(c.f * c.nf0);
+          qn = c.ks * c.f * c.nf0 / m_expm1(c.f * c.nf0);
           if ((qn * (c.cosv + c.g / c.nf0) - c.ri0 * c.cosv) <= c.r1) {
             qn *= (c.cosv + c.g / c.nf0);
             if (c.r1 >= (qn - c.ri0 * c.cosv)) {
@@ -762,7 +775,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
           } else {
             c.thre = c.edge_moist_z(c.nf0);
             c.suction(c.nf0);
-            qn = c.ru0 * c.cosv + c.ks * exp(-c.f * c.nf0) * c.g / c.nf0;
+            qn = c.ru0 * c.cosv + c.ks * m_exp(-c.f * c.nf0) * c.g / c.nf0;
             c.nf1 = c.nf0 + dt * (qn - c.ri1 * c.cosv) / (c.ths - c.thri);
             c.nt1 = c.nf1;
             if (c.nf1 < (c.nwt1 + c.psib)) {
@@ -778,7 +791,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
           }
         } else {
           c.ru1 = c.recharge_rate(mdelt, c.nf0);
-          nstar = (log(c.ks / c.ru1)) / c.f;
+          nstar = (m_log(c.ks / c.ru1)) / c.f;
           if (nstar <= c.nf0) {
             c.nt1 = nstar;
             c.nf1 = c.nf0 + 1.0E-5;
@@ -795,7 +808,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
               else c.nt1 = c.nf1 = 0.0;
             } else {
               c.suction(c.nf0);
-              qn = c.ru1 * c.cosv + c.ks * exp(-c.f * c.nf0) * c.g / c.nf0;
+              qn = c.ru1 * c.cosv + c.ks * m_exp(-c.f * c.nf0) * c.g / c.nf0;
               c.nf1 = c.nf0 + dt * (qn - c.ri1 * c.cosv) / (c.thre - c.thri);
               c.nt1 = c.nf1;
               if (c.nf1 < (c.nwt1 + c.psib)) {
@@ -828,7 +841,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
       c.thri = c.init_moist_z(c.nf0);
       c.thre = c.ths;
       c.suction(c.nf0);
-      qn = c.ks * c.f * (c.nf0 - c.nt0) / (exp(c.f * c.nf0) - exp(c.f * c.nt0));
+      qn = c.ks * c.f * (c.nf0 - c.nt0) / (m_exp(c.f * c.nf0) - m_exp(c.f * c.nt0));
       qn *= (c.cosv + c.g / c.nf0);
       c.nf1 = c.nf0 + dt * (qn - c.ri1 * c.cosv) / (c.ths - c.thri);
       if (fabs(c.nf1 - (c.nwt1 + c.psib)) <= 1.0E-3) {
@@ -869,14 +882,14 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
             c.mu1 -= c.hsrf * dt;
             c.ru1 = c.ksat_mean(c.nf1);
           } else {
-            bb = -dt * (qn - c.r1) / (c.ths - c.thr) - c.eps / c.f * exp(-c.f * c.nt0 / c.eps);
-            aa = -exp(c.f * (bb - c.nt0) / c.eps);
+            bb = -dt * (qn - c.r1) / (c.ths - c.thr) - c.eps / c.f * m_exp(-c.f * c.nt0 / c.eps);
+            aa = -m_exp(c.f * (bb - c.nt0) / c.eps);
             c.nt1 = c.nt0 + (c.eps / c.f * lambert_w(aa) - bb);
-            c.ru1 = c.ks * exp(-c.f * c.nt1);
+            c.ru1 = c.ks * m_exp(-c.f * c.nt1);
           }
           if (c.nwt1 != 0.0) {
             aa = c.lower_moist(c.nf1, c.nwt1);
-            bb = (c.nf1 - c.nt1) * c.ths + c.eps / c.f * (c.ths - c.thr) * (1.0 - exp(-c.f * c.nt1 / c.eps)) +
+            bb = (c.nf1 - c.nt1) * c.ths + c.eps / c.f * (c.ths - c.thr) * (1.0 - m_exp(-c.f * c.nt1 / c.eps)) +
                  c.thr * c.nt1;
             if (c.mu1 > (aa + bb)) {
               c.thri = c.init_moist_z(c.nf1);
@@ -920,7 +933,7 @@ TRIBS_HD int unsat_advance(Column &c, const UnsatEnv &e, double kunsat) {
         c.thri = c.init_moist_z(c.nf0);
         c.thre = c.ths;
         c.suction(c.nf0);
-        qn = c.ks * c.f * c.nf0 / expm1(c.f * c.nf0);
+        qn = c.ks * c.f * c.nf0 / m_expm1(c.f * c.nf0);
         qn *= (c.cosv + c.g / c.nf0);
         c.r1 = rflux;
         if (c.r1 >= qn) {
@@ -1077,7 +1090,7 @@ TRIBS_HD int sat_advance(Column &c, double gw, double area, double dtgw) {
                 c.nf1 = c.nt1 = c.nwt1;
               } else {
                 c.ru1 = c.recharge_rate(mdelt, c.nf0);
-                nstar = (log(c.ks / c.ru1)) / c.f;
+                nstar = (m_log(c.ks / c.ru1)) / c.f;
                 if (nstar <= c.nf0) { c.nt1 = nstar; c.nf1 = c.nf0 + 1.0E-5; }
                 else c.nf1 = c.nt1 = c.nf0;
                 c.mu1 = c.mi1 + (c.mu0 - c.mi0);

@@ -53,6 +53,9 @@ constexpr int kTile = 32;
 constexpr int kMaxRing = 4096;
 
 // ------------------------------------------------------------------------------------ context
+struct __align__(16) PubWord { double value; long long epoch; };   // see pub_store / pub_load
+constexpr int kSegBlock = 1024;
+struct SegBoundary { long long first_key, last_key; double first_val, last_val; };
 struct RouteConst {
   double velcoef, velratio, flowexp, baseflow, kincoef, dt_reff, outlet_contr_area;
   double tstep, output_interval;
@@ -62,7 +65,7 @@ struct RouteConst {
 struct tribs_ctx {
   int device = 0;
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
-  int max_degree = 0;
+  int max_degree = 0, segment_cells = 0;
   cudaStream_t stream = nullptr;
   // host maps
   std::vector<int32_t> dev_of_sweep, sweep_of_dev, stream_cells_sweep;
@@ -70,24 +73,29 @@ struct tribs_ctx {
   StaticView sv{};
   DynView dv{};
   std::vector<void *> allocs;
-  int32_t *d_up_rowptr = nullptr, *d_up_col = nullptr, *d_ready = nullptr, *d_tile_counter = nullptr;
+  int32_t *d_up_rowptr = nullptr, *d_up_col = nullptr, *d_tile_counter = nullptr, *d_tile_order = nullptr;
+  PubWord *d_pub = nullptr;
   int32_t *d_abort = nullptr, *d_sweep_of_dev = nullptr, *d_dev_of_sweep = nullptr;
   int32_t *d_late_rowptr = nullptr, *d_late_col = nullptr;
   double *d_tile_sums = nullptr, *d_globals = nullptr, *d_wt_elev = nullptr, *d_transm = nullptr;
   double *d_stage = nullptr;
   int32_t *d_flags = nullptr;  // [0] gather overflow
   // routing
-  int32_t *d_sn_rowptr = nullptr, *d_sn_cells = nullptr, *d_sn_dev = nullptr;
+  int32_t *d_seg_cell = nullptr, *d_seg_slot = nullptr, *d_sn_dev = nullptr;
+  double *d_seg_path = nullptr, *d_seg_area = nullptr;
+  SegBoundary *d_seg_bnd = nullptr;
+  int n_seg = 0, seg_blocks = 0;
   double *d_ring = nullptr, *d_qeff_now = nullptr, *d_results = nullptr, *d_route_part = nullptr;
   int route_blocks = 0, route_window = 0;
   RouteConst rc{};
   ModelConst mc{};
   int last_sweep_dev = -1;   // device index of the last cell in sweep order
   int last_hill_dev = -1;    // device index of the last hillslope cell in sweep order
-  int epoch = 0;
+  long long epoch = 0;
   int unsat_blocks = 0, unsat_threads = 128;
   bool gw_dirty = false;
   bool new_valid = true;     // false between Reset() and the next zone update: New == Old there
+  bool at_boundary = true;   // no zone update since init / the last Reset(): Old holds the current state
   int64_t launches = 0;
   // timing
   bool timing = false;
@@ -112,13 +120,19 @@ static int dev_upload(tribs_ctx *c, T **p, const std::vector<T> &h) {
 }
 
 // ------------------------------------------------------------------------------------ device helpers
-__device__ __forceinline__ int ld_acquire(const int *p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
+// Publication word of the chained sweep: the new Qpout of a cell and the epoch (sweep number)
+// it belongs to travel in ONE 16-byte transaction, so a consumer that sees the epoch also holds
+// the value: no fence, no L1 invalidation, one L2 round trip per poll (the scheme of
+// decoupled look-back scans).
+
+__device__ __forceinline__ void pub_store(PubWord *p, double v, long long epoch) {
+  asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(p), "l"(__double_as_longlong(v)), "l"(epoch) : "memory");
 }
-__device__ __forceinline__ void st_release(int *p, int v) {
-  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+__device__ __forceinline__ bool pub_load(const PubWord *p, long long epoch, double &v) {
+  long long a, b;
+  asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+  v = __longlong_as_double(a);
+  return b == epoch;
 }
 
 __device__ __forceinline__ double warp_sum_fixed(double v) {
@@ -135,8 +149,8 @@ __device__ __forceinline__ double warp_sum_fixed(double v) {
 // even if that invariant were ever broken.
 __global__ void __launch_bounds__(128)
 unsat_sweep_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const int32_t *__restrict__ up_rowptr,
-                   const int32_t *__restrict__ up_col, int32_t *ready, int epoch, int n_tiles,
-                   int32_t *tile_counter, int32_t *abort_flag, double *tile_sums, double *globals,
+                   const int32_t *__restrict__ up_col, PubWord *pub, long long epoch, int n_tiles,
+                   const int32_t *__restrict__ tile_order, int32_t *tile_counter, int32_t *abort_flag, double *tile_sums, double *globals,
                    int last_sweep_dev) {
   const int lane = threadIdx.x & 31;
   for (;;) {
@@ -144,6 +158,7 @@ unsat_sweep_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const int
     if (lane == 0) tile = atomicAdd(tile_counter, 1);
     tile = __shfl_sync(0xffffffffu, tile, 0);
     if (tile >= n_tiles) break;
+    tile = tile_order[tile];   // levels in ascending order: inputs always belong to tiles claimed earlier
     const int i = tile * kTile + lane;
     UnsatSums sums{0.0, 0.0, 0.0, 0.0};
     if (s.boundary[i] >= 0) {
@@ -153,23 +168,22 @@ unsat_sweep_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const int
       double qpin = 0.0;
       const int k1 = up_rowptr[i + 1];
       for (int k = up_rowptr[i]; k < k1; k++) {
-        const int j = up_col[k];
-        unsigned spins = 0;
-        while (ld_acquire(ready + j) != epoch) {
-          __nanosleep(40);
-          if (((++spins) & 1023u) == 0u) {
-            if (*(volatile int32_t *)abort_flag) break;
-            if (spins > (1u << 24)) { atomicExch(abort_flag, 1); break; }
+        const PubWord *src = pub + up_col[k];
+        double v;
+        unsigned spins = 0, ns = 32;
+        while (!pub_load(src, epoch, v)) {
+          __nanosleep(ns);
+          if (ns < 256) ns += ns;
+          if (((++spins) & 255u) == 0u) {
+            if (*(volatile int32_t *)abort_flag) { v = 0.0; break; }
+            if (spins > (1u << 22)) { atomicExch(abort_flag, 1); v = 0.0; break; }
           }
         }
-        qpin += __ldcg(d.f[TRIBS_F_Qpout] + j);
+        qpin += v;
       }
       int state;
       const double qout = unsat_cell_advance(u, qpin, &state);
-      // publish the outflow first: the downslope cell is waiting for it
-      d.f[TRIBS_F_Qpout][i] = qout;
-      __threadfence();
-      st_release(ready + i, epoch);
+      pub_store(pub + i, qout, epoch);   // the downslope cell is waiting for this
       unsat_cell_store(u, d, i, qpin, m, t, sums);
       if (i == last_sweep_dev) globals[TRIBS_G_psrf_last] = u.c.psrf;
     }
@@ -266,111 +280,139 @@ __device__ __forceinline__ double hill_velocity(const StaticView &s, const DynVi
   return rc.kincoef * pow(flowout / carea, rc.flowexp);
 }
 
-__global__ void __launch_bounds__(256)
-route_cells_kernel(StaticView s, DynView d, RouteConst rc, double qstrm_outlet, int n_pad, int last_hill_dev,
-                   double *globals) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad) return;
-  int bnd = s.boundary[i];
-  if (bnd < 0) return;
-  if (bnd == 0) {
-    double hv = hill_velocity(s, d, rc, s.stream_node[i], qstrm_outlet);
-    d.f[TRIBS_F_FlowVelocity][i] = hv;
-    if (d.f[TRIBS_F_srf][i] > 0.0) d.f[TRIBS_F_TTime][i] = s.hillpath[i] / hv / 3600.;
-    if (i == last_hill_dev) globals[TRIBS_G_hillvel_last] = hv;
-  }
-}
-// stream cells keep the velocity of the last hillslope cell swept before them (stale member
-// `hillvel`, tKinemat.cpp:1084); with the reference's node order that is the last hillslope cell.
-__global__ void __launch_bounds__(256)
-route_stream_velocity_kernel(StaticView s, DynView d, int n_pad, const double *globals, double fallback, int have_hill) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad || s.boundary[i] != 3) return;
-  d.f[TRIBS_F_FlowVelocity][i] = have_hill ? globals[TRIBS_G_hillvel_last] : fallback;
+// (2) hillslope runoff -> (stream node, dtReff bin), tKinemat.cpp:941-1067.
+//     Static "segment order": every stream slot (stream cell, or the outlet node) owns a
+//     contiguous run of entries = the stream cell itself (hillslope path 0) followed by its
+//     hillslope contributors sorted by hillslope path. The dtReff bin is monotone in the path, so
+//     (slot, bin) keys are non-decreasing along the whole array and every key is ONE contiguous
+//     run: a streaming reduce-by-key. Each 1024-entry block does a warp-shuffle segmented scan,
+//     adds the runs that lie strictly inside it straight into the slot's ring of bins (unique
+//     owner, no atomics) and hands its first and last (possibly cut) runs to a sequential fix-up.
+
+__device__ __forceinline__ double slot_velocity(const StaticView &s, const DynView &d, const RouteConst &rc,
+                                                int node, double qstrm_outlet) {
+  return hill_velocity(s, d, rc, node, qstrm_outlet);
 }
 
-// (2) hillslope runoff -> (stream node, dtReff bin). One warp per stream node; its contributors
-//     are pre-sorted by hillslope path, so bins are non-decreasing along the segment and each
-//     (node, bin) sum is a run: warp-shuffle segmented scan, last lane of a run accumulates into
-//     the node's ring of bins. No atomics; the summation order is fixed by the static sort.
-__global__ void __launch_bounds__(128)
-route_stream_bins_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restrict__ sn_rowptr,
-                         const int32_t *__restrict__ sn_cells, const int32_t *__restrict__ sn_dev, int n_slots,
-                         double now, double qstrm_outlet, double *ring, double *qeff_now) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= n_slots) return;
-  const int node = sn_dev[warp];  // device index of the stream cell, -1 = the outlet node slot
+__global__ void __launch_bounds__(kSegBlock)
+route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restrict__ seg_cell,
+                 const int32_t *__restrict__ seg_slot, const double *__restrict__ seg_path,
+                 const double *__restrict__ seg_area, const int32_t *__restrict__ slot_dev, int n_seg, double now,
+                 double qstrm_outlet, double *ring, SegBoundary *bnd) {
+  __shared__ long long sh_key_last[32], sh_key_first[32];
+  __shared__ double sh_acc_last[32], sh_carry[32];
+  __shared__ int sh_single[32];
+  const int e = blockIdx.x * kSegBlock + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double dtreff = rc.dt_reff;
   const int cur = (int)ceil(now / dtreff);
   const bool at_end = ((int)ceil(now / dtreff) == (int)floor(now / dtreff));
-  double *my_ring = ring + (size_t)warp * rc.ring;
   const double same_box_div = at_end ? (rc.tstep * 3600.) : ((cur * dtreff - now + rc.tstep) * 3600.);
-
-  // the stream cell's own runoff goes to the current bin with zero travel time (1001-1016)
-  if (lane == 0 && node >= 0) {
-    double srf = d.f[TRIBS_F_srf][node];
-    if (srf > 0.0) {
-      double vr = srf * s.varea[node] / 1000.;
-      if (srf > 999999) vr = 0.;
-      my_ring[cur % rc.ring] += vr / same_box_div;
+  long long key = 0x7fffffffffffffffLL;   // padding entries sort last and carry nothing
+  double v = 0.0;
+  if (e < n_seg) {
+    const int slot = seg_slot[e];
+    const double hv = slot_velocity(s, d, rc, slot_dev[slot], qstrm_outlet);
+    const double tt = seg_path[e] / hv / 3600.;
+    const int bin = (int)ceil((now + tt) / dtreff);
+    key = ((long long)slot << 32) | (unsigned)bin;
+    const double srf = d.f[TRIBS_F_srf][seg_cell[e]];
+    if (srf > 0.0 && !(srf > 999999)) {
+      double vr = srf * seg_area[e] / 1000.;
+      v = (bin == cur) ? vr / same_box_div : vr / (dtreff * 3600.);
     }
   }
-  __syncwarp();
-  const double hv = hill_velocity(s, d, rc, node, qstrm_outlet);
-  const int k0 = sn_rowptr[warp], k1 = sn_rowptr[warp + 1];
-  for (int base = k0; base < k1; base += 32) {
-    int k = base + lane;
-    int bin = 0x7fffffff;
-    double v = 0.0;
-    if (k < k1) {
-      int cidx = sn_cells[k];
-      double srf = d.f[TRIBS_F_srf][cidx];
-      if (srf > 0.0) {
-        double vr = srf * s.varea[cidx] / 1000.;
-        if (srf > 999999) vr = 0.;
-        double tt = s.hillpath[cidx] / hv / 3600.;
-        bin = (int)ceil((now + tt) / dtreff);
-        if (bin == cur) vr /= same_box_div;
-        else vr /= (dtreff * 3600.);
-        v = vr;
-      } else
-        bin = -1;  // no contribution
-    }
-    // runs of equal bins: inclusive segmented scan over lanes
-    int prev_bin = __shfl_up_sync(0xffffffffu, bin, 1);
-    bool head = (lane == 0) || (prev_bin != bin);
-    unsigned heads = __ballot_sync(0xffffffffu, head);
-    double acc = v;
+  // warp-level segmented inclusive scan
+  long long prev_key = __shfl_up_sync(0xffffffffu, key, 1);
+  const bool head = (lane == 0) || (prev_key != key);
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  double acc = v;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      double up = __shfl_up_sync(0xffffffffu, acc, o);
-      // add only if lane-o is still inside my run: no head strictly above lane-o up to lane
-      unsigned mask_between = (lane >= o) ? (heads >> (lane - o + 1)) & ((1u << o) - 1u) : 1u;
-      if (lane >= o && mask_between == 0u) acc += up;
-    }
-    int next_bin = __shfl_down_sync(0xffffffffu, bin, 1);
-    bool tail = (lane == 31) || (next_bin != bin);
-    if (tail && bin >= 0 && bin != 0x7fffffff) my_ring[bin % rc.ring] += acc;
-    __syncwarp();
+  for (int o = 1; o < 32; o <<= 1) {
+    double up = __shfl_up_sync(0xffffffffu, acc, o);
+    // lane-o is in my run iff no head lies in (lane-o, lane]
+    unsigned between = (lane >= o) ? ((heads >> (lane - o + 1)) & ((1u << o) - 1u)) : 1u;
+    if (lane >= o && between == 0u) acc += up;
   }
-  __syncwarp();
-  // what the channel router reads this step, and consumption at the end of a dtReff interval
-  if (lane == 0) {
-    double val = my_ring[cur % rc.ring];
-    qeff_now[warp] = val;
-    if (at_end) my_ring[cur % rc.ring] = 0.0;
+  if (lane == 31) { sh_key_last[warp] = key; sh_acc_last[warp] = acc; }
+  if (lane == 0) { sh_key_first[warp] = key; sh_single[warp] = (heads == 1u); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // carry_in[w]: what the run that starts warp w already collected in earlier warps
+    sh_carry[0] = 0.0;
+    for (int w = 1; w < 32; w++) {
+      const double run_end = sh_acc_last[w - 1] + (sh_single[w - 1] ? sh_carry[w - 1] : 0.0);
+      sh_carry[w] = (sh_key_first[w] == sh_key_last[w - 1]) ? run_end : 0.0;
+    }
+    bnd[blockIdx.x] = SegBoundary{-1, -1, 0.0, 0.0};
+  }
+  __syncthreads();
+  // lanes of the first run of their warp inherit the carry
+  const bool in_first_run = ((heads & ((2u << lane) - 1u)) == 1u);
+  if (in_first_run) acc += sh_carry[warp];
+  // run tails
+  long long next_key = __shfl_down_sync(0xffffffffu, key, 1);
+  if (lane == 31) next_key = (warp < 31) ? sh_key_first[warp + 1] : ~key;  // block end always closes the run
+  const bool tail = (next_key != key);
+  const long long block_first_key = sh_key_first[0];
+  const long long block_last_key = sh_key_last[31];
+  if (tail && key != 0x7fffffffffffffffLL) {
+    const bool is_first_run = (key == block_first_key);
+    const bool is_last_run = (key == block_last_key);
+    if (is_first_run) { bnd[blockIdx.x].first_key = key; bnd[blockIdx.x].first_val = acc; }
+    if (is_last_run && !is_first_run) { bnd[blockIdx.x].last_key = key; bnd[blockIdx.x].last_val = acc; }
+    if (!is_first_run && !is_last_run) {
+      const int slot = (int)(key >> 32), bin = (int)(key & 0xffffffffLL);
+      ring[(size_t)slot * rc.ring + (bin % rc.ring)] += acc;
+    }
   }
 }
 
-// (3) tFlowNet::SurfaceFlow accumulations. Stage 1: every block reduces its cells into
-//     [window] volume bins x 5 runoff types + 10 area-weighted means, deterministically
-//     (per-warp slabs filled lane by lane, slabs added in warp order). Stage 2: one block sums
-//     the block partials in block order into the tFlowResults arrays.
+// sequential stitch of the block-boundary runs (block order = entry order), then latch what the
+// channel router reads this step and consume the bin at the end of a dtReff interval
+// (tKinemat::RetrieveQeff, tKinemat.cpp:1504-1551)
+__global__ void __launch_bounds__(1024)
+route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n_blocks, int n_slots, double now,
+                       double *ring, double *qeff_now) {
+  if (threadIdx.x == 0) {
+    long long ckey = -1;
+    double cval = 0.0;
+    auto flush = [&](long long key, double val) {
+      if (key < 0) return;
+      const int slot = (int)(key >> 32), bin = (int)(key & 0xffffffffLL);
+      ring[(size_t)slot * rc.ring + (bin % rc.ring)] += val;
+    };
+    for (int b = 0; b < n_blocks; b++) {
+      const SegBoundary x = bnd[b];
+      if (x.first_key >= 0) {
+        if (x.first_key == ckey) cval += x.first_val;
+        else { flush(ckey, cval); ckey = x.first_key; cval = x.first_val; }
+      }
+      if (x.last_key >= 0) { flush(ckey, cval); ckey = x.last_key; cval = x.last_val; }
+    }
+    flush(ckey, cval);
+  }
+  __syncthreads();
+  const int cur = (int)ceil(now / rc.dt_reff);
+  const bool at_end = ((int)ceil(now / rc.dt_reff) == (int)floor(now / rc.dt_reff));
+  for (int k = threadIdx.x; k < n_slots; k += blockDim.x) {
+    double *p = ring + (size_t)k * rc.ring + (cur % rc.ring);
+    qeff_now[k] = *p;
+    if (at_end) *p = 0.0;
+  }
+}
+
+// (3) per-cell tail of RunHydrologicRouting (FlowVelocity, travel time; tKinemat.cpp:958-970,
+//     1084) fused with the tFlowNet::SurfaceFlow accumulations (tFlowNet.cpp:758-865).
+//     Stage 1: a fixed grid; block b owns the 256-cell chunks b, b+G, b+2G ... and reduces them
+//     into [window] volume bins x 5 runoff types + 10 basin means, deterministically (per-warp
+//     slabs filled lane by lane, slabs added in warp order). Stage 2: one warp per output value
+//     sums the G block partials in a fixed order into the tFlowResults arrays.
 constexpr int kRouteWarps = 8;
 constexpr int kMeans = 10;  // crr frac msm msmRt msmU sat mgw qunsat rmax rmin
 __global__ void __launch_bounds__(kRouteWarps * 32)
-route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, double now, int n_pad, int window,
-                          int bin_base, double *part) {
+route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, double now, double qstrm_outlet,
+                          int n_pad, int window, int bin_base, int last_hill_dev, double *part, double *globals) {
   extern __shared__ double sh[];  // [kRouteWarps][5*window + kMeans]
   const int stride = 5 * window + kMeans;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -378,76 +420,101 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
   for (int k = lane; k < stride; k += 32) slab[k] = 0.0;
   if (lane == 0) { slab[5 * window + 8] = -1.0e300; slab[5 * window + 9] = 1.0e300; }
   __syncwarp();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool act = (i < n_pad) && (s.boundary[i] >= 0);
-  double vol[5] = {0, 0, 0, 0, 0};
-  int init = 0, end = -1;
-  double w_init = 0, w_mid = 0, w_end = 0;
-  double means[kMeans];
-  for (int k = 0; k < kMeans; k++) means[k] = 0.0;
-  means[8] = -1.0e300; means[9] = 1.0e300;
-  if (act) {
-    const double area = s.varea[i], areaf = area / m.bas_area_flow;
-    const double srf = d.f[TRIBS_F_srf][i];
-    const double dcalc = rc.tstep, dres = rc.output_interval, sec = rc.output_interval * 3600.0;
-    if (srf > 0.0) {
-      if (rc.flowexp > 0.0) {
-        double hv = rc.velcoef / rc.velratio, sv = rc.velcoef;
-        d.f[TRIBS_F_TTime][i] = (s.hillpath[i] / hv + s.streampath[i] / sv) / 3600.0;
-      }
-      const double tt = d.f[TRIBS_F_TTime][i];
-      vol[0] = srf * area / 1000.0;
-      vol[1] = d.f[TRIBS_F_hsrf][i] * area / 1000.0;
-      vol[2] = d.f[TRIBS_F_sbsrf][i] * area / 1000.0;
-      vol[3] = d.f[TRIBS_F_psrf][i] * area / 1000.0;
-      vol[4] = d.f[TRIBS_F_satsrf][i] * area / 1000.0;
-      init = (int)floor((tt + .01 * dcalc + now) / dres);
-      end = (int)floor((tt + .99 * dcalc + now) / dres);
-      if (init == end) { w_init = 1.0 / sec; }
-      else {
-        double dint = (init + 1) * dres - (now + tt);
-        w_init = dint / dcalc / sec;
-        if (end - init == 1) w_end = (dcalc - dint) / dcalc / sec;
+  // velocity the stream cells inherit: that of the last hillslope cell in sweep order
+  const double hv_last = last_hill_dev >= 0 ? hill_velocity(s, d, rc, s.stream_node[last_hill_dev], qstrm_outlet)
+                                            : rc.velcoef / rc.velratio;
+  if (blockIdx.x == 0 && threadIdx.x == 0) globals[TRIBS_G_hillvel_last] = hv_last;
+  const int n_chunks = (n_pad + blockDim.x - 1) / blockDim.x;
+  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
+    const int i = chunk * blockDim.x + threadIdx.x;
+    const int bnd = (i < n_pad) ? s.boundary[i] : -1;
+    const bool act = bnd >= 0;
+    double vol[5] = {0, 0, 0, 0, 0};
+    int init = 0, end = -1;
+    double w_init = 0, w_mid = 0, w_end = 0;
+    double means[kMeans];
+    for (int k = 0; k < kMeans; k++) means[k] = 0.0;
+    if (act) {
+      const double area = s.varea[i], areaf = area / m.bas_area_flow;
+      const double srf = d.f[TRIBS_F_srf][i];
+      const double dcalc = rc.tstep, dres = rc.output_interval, sec = rc.output_interval * 3600.0;
+      double tt = d.f[TRIBS_F_TTime][i];
+      if (bnd == 0) {
+        const double hv = hill_velocity(s, d, rc, s.stream_node[i], qstrm_outlet);
+        d.f[TRIBS_F_FlowVelocity][i] = hv;
+        if (srf > 0.0) { tt = s.hillpath[i] / hv / 3600.; d.f[TRIBS_F_TTime][i] = tt; }
+      } else
+        d.f[TRIBS_F_FlowVelocity][i] = hv_last;
+      if (srf > 0.0) {
+        if (rc.flowexp > 0.0) {
+          const double hv0 = rc.velcoef / rc.velratio, sv0 = rc.velcoef;
+          tt = (s.hillpath[i] / hv0 + s.streampath[i] / sv0) / 3600.0;
+          d.f[TRIBS_F_TTime][i] = tt;
+        }
+        vol[0] = srf * area / 1000.0;
+        vol[1] = d.f[TRIBS_F_hsrf][i] * area / 1000.0;
+        vol[2] = d.f[TRIBS_F_sbsrf][i] * area / 1000.0;
+        vol[3] = d.f[TRIBS_F_psrf][i] * area / 1000.0;
+        vol[4] = d.f[TRIBS_F_satsrf][i] * area / 1000.0;
+        init = (int)floor((tt + .01 * dcalc + now) / dres);
+        end = (int)floor((tt + .99 * dcalc + now) / dres);
+        if (init == end) w_init = 1.0 / sec;
         else {
-          w_mid = dres / dcalc / sec;
-          w_end = ((now + tt + dcalc) - end * dres) / dcalc / sec;
+          const double dint = (init + 1) * dres - (now + tt);
+          w_init = dint / dcalc / sec;
+          if (end - init == 1) w_end = (dcalc - dint) / dcalc / sec;
+          else {
+            w_mid = dres / dcalc / sec;
+            w_end = ((now + tt + dcalc) - end * dres) / dcalc / sec;
+          }
         }
       }
+      const double w = rc.tstep / rc.output_interval;
+      const double rain = d.f[TRIBS_F_Rain][i];
+      double cs = s.cos_gw[i];
+      if (cs < 1E-9) cs = 1.E-9;
+      means[0] = areaf * rain * rc.tstep / rc.output_interval;
+      means[1] = (rain > 0.0) ? areaf * w : 0.0;
+      means[2] = areaf * d.f[TRIBS_F_SoilMoistureSC][i] * w;
+      means[3] = areaf * d.f[TRIBS_F_RootMoistureSC][i] * w;
+      means[4] = areaf * d.f[TRIBS_F_SoilMoistureUNSC][i] * w;
+      means[5] = (d.f[TRIBS_F_SoilMoistureSC][i] >= 1) ? areaf * w : 0.0;
+      means[6] = areaf * (d.f[TRIBS_F_NwtNew][i] / cs) * w;
+      means[7] = areaf * (d.f[TRIBS_F_Qpout][i] - d.f[TRIBS_F_Qpin][i]) * 1.E-6 / area * w;
+      means[8] = rain;
+      means[9] = rain;
     }
-    const double w = rc.tstep / rc.output_interval;
-    const double rain = d.f[TRIBS_F_Rain][i];
-    double cs = s.cos_gw[i];
-    if (cs < 1E-9) cs = 1.E-9;
-    means[0] = areaf * rain * rc.tstep / rc.output_interval;
-    means[1] = (rain > 0.0) ? areaf * w : 0.0;
-    means[2] = areaf * d.f[TRIBS_F_SoilMoistureSC][i] * w;
-    means[3] = areaf * d.f[TRIBS_F_RootMoistureSC][i] * w;
-    means[4] = areaf * d.f[TRIBS_F_SoilMoistureUNSC][i] * w;
-    means[5] = (d.f[TRIBS_F_SoilMoistureSC][i] >= 1) ? areaf * w : 0.0;
-    means[6] = areaf * (d.f[TRIBS_F_NwtNew][i] / cs) * w;
-    means[7] = areaf * (d.f[TRIBS_F_Qpout][i] - d.f[TRIBS_F_Qpin][i]) * 1.E-6 / area * w;
-    means[8] = rain;
-    means[9] = rain;
-  }
-  // lane-serial fill keeps the order fixed (lane 0 first)
-  for (int l = 0; l < 32; l++) {
-    if (lane == l && act) {
-      if (end >= init) {
+    // the 8 sums: fixed-order butterfly; min/max: order free
+#pragma unroll
+    for (int k = 0; k < 8; k++) means[k] = warp_sum_fixed(means[k]);
+    double mx = act ? means[8] : -1.0e300, mn = act ? means[9] : 1.0e300;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+    }
+    if (lane == 0) {
+      for (int k = 0; k < 8; k++) slab[5 * window + k] += means[k];
+      slab[5 * window + 8] = fmax(slab[5 * window + 8], mx);
+      slab[5 * window + 9] = fmin(slab[5 * window + 9], mn);
+    }
+    // binned volumes: only runoff-producing lanes take part, lowest lane first (fixed order)
+    unsigned todo = __ballot_sync(0xffffffffu, act && end >= init);
+    while (todo) {
+      const int l = __ffs(todo) - 1;
+      todo &= todo - 1;
+      if (lane == l) {
         for (int b = init; b <= end; b++) {
-          int off = b - bin_base;
+          const int off = b - bin_base;
           if (off < 0 || off >= window) continue;
-          double wgt = (b == init) ? w_init : ((b == end) ? w_end : w_mid);
-          // volume * weight written as (value * fraction) / seconds in the reference; the
-          // fraction and 1/seconds are folded into wgt here (<= 1 ulp difference)
+          // value*fraction/seconds in the reference; fraction/seconds folded into one weight here
+          const double wgt = (b == init) ? w_init : ((b == end) ? w_end : w_mid);
           for (int k = 0; k < 5; k++)
             if (vol[k] != 0.0) slab[k * window + off] += vol[k] * wgt;
         }
       }
-      for (int k = 0; k < 8; k++) slab[5 * window + k] += means[k];
-      if (means[8] > slab[5 * window + 8]) slab[5 * window + 8] = means[8];
-      if (means[9] < slab[5 * window + 9]) slab[5 * window + 9] = means[9];
+      __syncwarp();
     }
-    __syncwarp();
   }
   __syncthreads();
   for (int k = threadIdx.x; k < stride; k += blockDim.x) {
@@ -463,24 +530,32 @@ __global__ void __launch_bounds__(256)
 route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int window, int bin_base, int cur_bin,
                           int limit, double *results) {
   const int stride = 5 * window + kMeans;
-  for (int k = threadIdx.x; k < stride; k += blockDim.x) {
-    double acc;
-    if (k == 5 * window + 8) { acc = -1.0e300; for (int b = 0; b < n_blocks; b++) acc = fmax(acc, part[(size_t)b * stride + k]); }
-    else if (k == 5 * window + 9) { acc = 1.0e300; for (int b = 0; b < n_blocks; b++) acc = fmin(acc, part[(size_t)b * stride + k]); }
-    else { acc = 0.0; for (int b = 0; b < n_blocks; b++) acc += part[(size_t)b * stride + k]; }
-    if (k < 5 * window) {
-      int type = k / window, bin = bin_base + (k % window);
-      if (bin >= 0 && bin < limit && acc != 0.0) results[(size_t)type * limit + bin] += acc;
-    } else if (cur_bin >= 0 && cur_bin < limit) {
-      int q = k - 5 * window;
-      // order of TRIBS_R_*: crr rmax rmin frac msm msmRt msmU mgw sat qunsat
-      const int map[kMeans] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
-                               TRIBS_R_sat, TRIBS_R_mgw, TRIBS_R_qunsat, TRIBS_R_rmax, TRIBS_R_rmin};
-      double *dst = results + (size_t)map[q] * limit + cur_bin;
-      if (q == 8) { if (acc > *dst) *dst = acc; }
-      else if (q == 9) { if (acc <= *dst) *dst = acc; }
-      else *dst += acc;
-    }
+  const int lane = threadIdx.x & 31;
+  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output value
+  if (k >= stride) return;
+  const bool is_max = (k == 5 * window + 8), is_min = (k == 5 * window + 9);
+  double acc = is_max ? -1.0e300 : (is_min ? 1.0e300 : 0.0);
+  for (int b = lane; b < n_blocks; b += 32) {
+    const double v = part[(size_t)b * stride + k];
+    acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const double v = __shfl_xor_sync(0xffffffffu, acc, o);
+    acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
+  }
+  if (lane != 0) return;
+  if (k < 5 * window) {
+    const int type = k / window, bin = bin_base + (k % window);
+    if (bin >= 0 && bin < limit && acc != 0.0) results[(size_t)type * limit + bin] += acc;
+  } else if (cur_bin >= 0 && cur_bin < limit) {
+    const int q = k - 5 * window;
+    const int map[kMeans] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
+                             TRIBS_R_sat, TRIBS_R_mgw, TRIBS_R_qunsat, TRIBS_R_rmax, TRIBS_R_rmin};
+    double *dst = results + (size_t)map[q] * limit + cur_bin;
+    if (q == 8) { if (acc > *dst) *dst = acc; }
+    else if (q == 9) { if (acc <= *dst) *dst = acc; }
+    else *dst += acc;
   }
 }
 
@@ -571,21 +646,87 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     nlev = std::max(nlev, lv + 1);
   }
   c->n_levels = nlev;
-  std::vector<int32_t> count(nlev, 0), start(nlev + 1, 0);
-  for (int i = 0; i < n; i++) count[level[i]]++;
-  for (int l = 0; l < nlev; l++) start[l + 1] = start[l] + ((count[l] + kTile - 1) / kTile) * kTile;
-  const int n_pad = start[nlev];
-  c->n_pad = n_pad;
-  c->n_tiles = n_pad / kTile;
-  c->dev_of_sweep.assign(n, -1);
-  c->sweep_of_dev.assign(n_pad, -1);
+  // ---- device order. Tiles (32 consecutive device cells) are the unit of scheduling, so a tile must
+  //  (a) hold cells with no flow relation among them (a warp never waits on itself) and
+  //  (b) hold cells whose inputs become ready at about the same time in EVERY phase; otherwise one
+  //      tile couples the bottom of the river of phase p to the top of the river of phase p+1 and
+  //      the phases of a pipelined batch serialise.
+  // Buckets = (stream segment, hops to the stream): the stream cells are cut, in sweep order
+  // (upstream first), into segments of G cells; a hillslope cell belongs to the segment of its
+  // stream node and to the depth class "hops along its flow path to the stream". Segments are
+  // closed under flow, depth strictly decreases along flow, and within a segment the tile
+  // dependency graph is a chain over depth. Device order = (segment, hillslope ridge-first by
+  // depth, then the segment's stream cells), so ascending tile index is a topological order.
+  std::vector<int32_t> seg(n, 0), depth(n, 0), srank(n, -1);
   {
-    std::vector<int32_t> fillp(start.begin(), start.end() - 1);
-    for (int i = 0; i < n; i++) {  // stable: sweep order inside a level
-      int dI = fillp[level[i]]++;
-      c->dev_of_sweep[i] = dI;
-      c->sweep_of_dev[dI] = i;
+    int ns = 0, max_depth = 1;
+    long n_hill = 0;
+    for (int i = n - 1; i >= 0; i--) {
+      if (mesh->boundary[i] == 3) depth[i] = 0;
+      else {
+        const int dst = mesh->flow_dest[i];
+        depth[i] = (dst < 0 || dst <= i) ? 1 : depth[dst] + 1;
+        max_depth = std::max(max_depth, (int)depth[i]);
+        n_hill++;
+      }
     }
+    for (int i = 0; i < n; i++) if (mesh->boundary[i] == 3) srank[i] = ns++;
+    long G = 1;
+    if (ns > 0 && n_hill > 0) G = std::lround(64.0 * max_depth * (double)ns / (double)n_hill);
+    G = std::max(1L, std::min(G, (long)std::max(ns, 1)));
+    if (const char *e = getenv("TRIBS_SEGMENT_CELLS")) G = std::max(1, atoi(e));
+    const int n_groups = ns > 0 ? (int)((ns + G - 1) / G) : 1;
+    for (int i = 0; i < n; i++) {
+      const int sn = mesh->boundary[i] == 3 ? i : mesh->stream_node[i];
+      seg[i] = (sn >= 0 && srank[sn] >= 0) ? (int)(srank[sn] / G) : n_groups - 1;
+    }
+    c->segment_cells = (int)G;
+  }
+  auto bucket_key = [&](int i) { return mesh->boundary[i] == 3 ? (long long)srank[i] : -(long long)depth[i]; };
+  std::vector<int32_t> order(n);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (seg[a] != seg[b]) return seg[a] < seg[b];
+    const int sa = mesh->boundary[a] == 3, sb = mesh->boundary[b] == 3;
+    if (sa != sb) return sa < sb;
+    return bucket_key(a) < bucket_key(b);
+  });
+  c->dev_of_sweep.assign(n, -1);
+  {
+    int pos = 0;
+    for (int k = 0; k < n; k++) {
+      const int i = order[k];
+      if (k > 0) {
+        const int j = order[k - 1];
+        if (seg[i] != seg[j] || (mesh->boundary[i] == 3) != (mesh->boundary[j] == 3) || bucket_key(i) != bucket_key(j))
+          pos = ((pos + kTile - 1) / kTile) * kTile;
+      }
+      c->dev_of_sweep[i] = pos++;
+    }
+    c->n_pad = ((pos + kTile - 1) / kTile) * kTile;
+  }
+  const int n_pad = c->n_pad;
+  c->n_tiles = n_pad / kTile;
+  c->sweep_of_dev.assign(n_pad, -1);
+  for (int i = 0; i < n; i++) c->sweep_of_dev[c->dev_of_sweep[i]] = i;
+  // claim order of the single-phase sweep: tiles by their topological time (longest chain of
+  // upslope tiles); ascending tile index is a valid evaluation order for this recurrence
+  {
+    std::vector<int32_t> tau(c->n_tiles, 0), tiles(c->n_tiles);
+    for (int dI = 0; dI < n_pad; dI++) {
+      const int i = c->sweep_of_dev[dI];
+      if (i < 0) continue;
+      int mval = tau[dI / kTile];
+      for (int j : early[i]) {
+        const int tj = c->dev_of_sweep[j] / kTile;
+        if (tj >= dI / kTile) { delete c; return fail("tribs_gpu_init: internal: device order is not topological"); }
+        mval = std::max(mval, tau[tj] + 1);
+      }
+      tau[dI / kTile] = mval;
+    }
+    std::iota(tiles.begin(), tiles.end(), 0);
+    std::stable_sort(tiles.begin(), tiles.end(), [&](int a, int b) { return tau[a] < tau[b]; });
+    if (dev_upload(c, &c->d_tile_order, tiles)) return 1;
   }
   auto D = [&](int sweep) { return sweep < 0 ? -1 : c->dev_of_sweep[sweep]; };
   c->last_sweep_dev = c->dev_of_sweep[n - 1];
@@ -684,16 +825,30 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
       members[slot].push_back(i);
     }
     c->last_hill_dev = last_hill >= 0 ? c->dev_of_sweep[last_hill] : -1;
-    std::vector<int32_t> rp(slots + 1, 0), cells, sdev(slots, -1);
+    std::vector<int32_t> seg_cell, seg_slot, sdev(slots, -1);
+    std::vector<double> seg_path, seg_area;
+    seg_cell.reserve(n); seg_slot.reserve(n); seg_path.reserve(n); seg_area.reserve(n);
     double max_path = 0.0;
     for (int k = 0; k < slots; k++) {
       auto &mm = members[k];
       std::stable_sort(mm.begin(), mm.end(), [&](int a, int b) { return mesh->hillpath[a] < mesh->hillpath[b]; });
-      for (int i : mm) { cells.push_back(c->dev_of_sweep[i]); max_path = std::max(max_path, mesh->hillpath[i]); }
-      rp[k + 1] = (int32_t)cells.size();
-      if (k < c->n_stream) sdev[k] = c->dev_of_sweep[scells[k]];
+      if (k < c->n_stream) {  // the stream cell itself: zero travel time, same bin arithmetic
+        sdev[k] = c->dev_of_sweep[scells[k]];
+        seg_cell.push_back(sdev[k]); seg_slot.push_back(k); seg_path.push_back(0.0);
+        seg_area.push_back(mesh->varea[scells[k]]);
+      }
+      for (int i : mm) {
+        seg_cell.push_back(c->dev_of_sweep[i]); seg_slot.push_back(k); seg_path.push_back(mesh->hillpath[i]);
+        seg_area.push_back(mesh->varea[i]);
+        max_path = std::max(max_path, mesh->hillpath[i]);
+      }
     }
-    if (dev_upload(c, &c->d_sn_rowptr, rp) || dev_upload(c, &c->d_sn_cells, cells) || dev_upload(c, &c->d_sn_dev, sdev)) return 1;
+    c->n_seg = (int)seg_cell.size();
+    c->seg_blocks = std::max(1, (c->n_seg + kSegBlock - 1) / kSegBlock);
+    if (dev_upload(c, &c->d_seg_cell, seg_cell) || dev_upload(c, &c->d_seg_slot, seg_slot) ||
+        dev_upload(c, &c->d_seg_path, seg_path) || dev_upload(c, &c->d_seg_area, seg_area) ||
+        dev_upload(c, &c->d_sn_dev, sdev) || dev_alloc(c, &c->d_seg_bnd, (size_t)c->seg_blocks))
+      return 1;
     RouteConst &rc = c->rc;
     rc.velcoef = prm->velcoef; rc.velratio = prm->velratio; rc.flowexp = prm->flowexp; rc.baseflow = prm->baseflow;
     rc.kincoef = prm->kincoef; rc.dt_reff = prm->dtReff; rc.outlet_contr_area = prm->outlet_contr_area;
@@ -726,7 +881,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     }
     c->route_window = std::max(4, (int)ceil(max_basin_tt / prm->output_interval) + 3 +
                                       (int)ceil(prm->tstep / prm->output_interval));
-    c->route_blocks = std::max(1, (n_pad + kRouteWarps * 32 - 1) / (kRouteWarps * 32));
+    c->route_blocks = std::max(1, std::min(592, (n_pad + kRouteWarps * 32 - 1) / (kRouteWarps * 32)));
     size_t stride = 5 * (size_t)c->route_window + kMeans;
     if (kRouteWarps * stride * sizeof(double) > 200 * 1024)
       return fail("tribs_gpu_init: basin travel-time window too wide for shared memory");
@@ -749,12 +904,12 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     CK(cudaMemcpy(p, h.data(), (size_t)n_pad * sizeof(double), cudaMemcpyHostToDevice));
     c->dv.f[k] = p;
   }
-  if (dev_alloc(c, &c->d_ready, (size_t)n_pad) || dev_alloc(c, &c->d_tile_counter, 4) || dev_alloc(c, &c->d_abort, 4) ||
+  if (dev_alloc(c, &c->d_pub, (size_t)n_pad) || dev_alloc(c, &c->d_tile_counter, 4) || dev_alloc(c, &c->d_abort, 4) ||
       dev_alloc(c, &c->d_flags, 4) || dev_alloc(c, &c->d_tile_sums, (size_t)4 * c->n_tiles) ||
       dev_alloc(c, &c->d_globals, (size_t)TRIBS_N_GLOBALS) || dev_alloc(c, &c->d_wt_elev, (size_t)n_pad) ||
       dev_alloc(c, &c->d_transm, (size_t)n_pad) || dev_alloc(c, &c->d_stage, (size_t)n_pad))
     return 1;
-  CK(cudaMemset(c->d_ready, 0, (size_t)n_pad * sizeof(int32_t)));
+  CK(cudaMemset(c->d_pub, 0, (size_t)n_pad * sizeof(PubWord)));
   CK(cudaMemset(c->d_tile_counter, 0, 16));
   CK(cudaMemset(c->d_abort, 0, 16));
   CK(cudaMemset(c->d_flags, 0, 16));
@@ -811,15 +966,18 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
   if (s->qstrm && c->rc.flowexp > 0.0)
     if (upload_sweep_field(c, s->qstrm, TRIBS_F_Qstrm)) return 1;
 
-  StepConst t{s->dt, s->dt_gw, s->current_time, (double)s->elapsed_steps, s->hourly_reset, 0.0};
+  StepConst t;
+  t.dt = s->dt; t.dt_gw = s->dt_gw; t.now = s->current_time; t.elapsed = (double)s->elapsed_steps;
+  t.hourly_reset = s->hourly_reset; t.psrf_last = 0.0;
 
   if (mask & TRIBS_PHASE_UNSAT) {
     PhaseTimer pt(c, 0);
     c->epoch++;
     CK(cudaMemsetAsync(c->d_tile_counter, 0, 4, st));
-    int epoch = c->epoch, n_tiles = c->n_tiles, last = c->last_sweep_dev;
-    void *args[] = {&c->sv, &c->dv, &c->mc, &t, &c->d_up_rowptr, &c->d_up_col, &c->d_ready, &epoch, &n_tiles,
-                    &c->d_tile_counter, &c->d_abort, &c->d_tile_sums, &c->d_globals, &last};
+    long long epoch = c->epoch;
+    int n_tiles = c->n_tiles, last = c->last_sweep_dev;
+    void *args[] = {&c->sv, &c->dv, &c->mc, &t, &c->d_up_rowptr, &c->d_up_col, &c->d_pub, &epoch, &n_tiles,
+                    &c->d_tile_order, &c->d_tile_counter, &c->d_abort, &c->d_tile_sums, &c->d_globals, &last};
     CK(cudaLaunchCooperativeKernel((void *)unsat_sweep_kernel, dim3(c->unsat_blocks), dim3(c->unsat_threads), args, 0, st));
     c->launches++;
     if (c->n_late > 0) {
@@ -830,6 +988,7 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
                                            TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
     c->launches++;
     c->new_valid = true;
+    c->at_boundary = false;
   }
   if (mask & TRIBS_PHASE_SAT) {
     PhaseTimer pt(c, 1);
@@ -847,27 +1006,29 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
     c->launches += 3;
     c->gw_dirty = true;
     c->new_valid = true;
+    c->at_boundary = false;
   }
   if (mask & TRIBS_PHASE_ROUTE) {
     PhaseTimer pt(c, 2);
     const double now = s->current_time;
-    route_cells_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->sv, c->dv, c->rc, s->qstrm_outlet, n_pad, c->last_hill_dev, c->d_globals);
-    route_stream_velocity_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->sv, c->dv, n_pad, c->d_globals,
-                                                                      c->rc.velcoef / c->rc.velratio, c->last_hill_dev >= 0);
     const int slots = c->n_stream + 1;
-    route_stream_bins_kernel<<<(slots * 32 + 127) / 128, 128, 0, st>>>(c->sv, c->dv, c->rc, c->d_sn_rowptr, c->d_sn_cells,
-                                                                       c->d_sn_dev, slots, now, s->qstrm_outlet, c->d_ring, c->d_qeff_now);
+    route_seg_kernel<<<c->seg_blocks, kSegBlock, 0, st>>>(c->sv, c->dv, c->rc, c->d_seg_cell, c->d_seg_slot, c->d_seg_path,
+                                                          c->d_seg_area, c->d_sn_dev, c->n_seg, now, s->qstrm_outlet,
+                                                          c->d_ring, c->d_seg_bnd);
+    route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, c->d_seg_bnd, c->seg_blocks, slots, now, c->d_ring, c->d_qeff_now);
     const int window = c->route_window;
     const int cur_bin0 = (int)floor((0.0 - .01 * c->rc.tstep + now) / c->rc.output_interval);
     const int cur_bin1 = (int)floor((0.0 - .99 * c->rc.tstep + now) / c->rc.output_interval);
     const int cur_bin = (cur_bin0 == cur_bin1) ? cur_bin0 : -1;   // store_saturation only writes when init==end
     const int bin_base = (int)floor((now + .01 * c->rc.tstep) / c->rc.output_interval);
     size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
-    route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, c->dv, c->rc, c->mc, now, n_pad, window,
-                                                                                 bin_base, c->d_route_part);
-    route_basin_stage2_kernel<<<1, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base, cur_bin,
-                                                 c->rc.res_limit, c->d_results);
-    c->launches += 5;
+    route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, c->dv, c->rc, c->mc, now, s->qstrm_outlet,
+                                                                                 n_pad, window, bin_base, c->last_hill_dev,
+                                                                                 c->d_route_part, c->d_globals);
+    const int n_vals = 5 * window + kMeans;
+    route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
+                                                                          cur_bin, c->rc.res_limit, c->d_results);
+    c->launches += 4;
   }
   if (mask & TRIBS_PHASE_RESET) {
     PhaseTimer pt(c, 3);
@@ -880,6 +1041,7 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
       c->gw_dirty = false;
     }
     c->new_valid = false;
+    c->at_boundary = true;
   }
   CK(cudaGetLastError());
   return 0;
@@ -986,5 +1148,445 @@ extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   for (void *p : c->allocs) cudaFree(p);
   cudaStreamDestroy(c->stream);
   delete c;
+  return 0;
+}
+
+// ====================================================================================
+// Pipelined batch (tribs_gpu_run): a space-time dataflow over (phase, 32-cell tile) tasks.
+//
+// Every cell carries a monotone counter done[i] = number of phases it has completed and a
+// two-slot ring of publication words {new Qpout, phase tag}. Phase with tag T reads the state
+// buffer T%2 and writes buffer (T+1)%2. A task (phase T, cell i) needs
+//   UNSAT: done[i] >= T-1, done[flow_dest] >= T-1 (reads the downslope Old values; also keeps an
+//          upslope cell at most one phase ahead of its receiver so two ring slots suffice),
+//          done[nbr] >= T-1 for all Voronoi neighbours when phase T-1 was a saturated-zone phase
+//          (they read the buffer this task overwrites), and pub[T%2][j].tag == T of every upslope j;
+//   SAT:   done[i] >= T-1 and done[nbr] >= T-1 for all Voronoi neighbours.
+// The host orders the tasks by a topological time tau computed from exactly these rules at tile
+// granularity; warps claim tasks in that order, so every dependency of a claimed task belongs to
+// a task claimed earlier by a resident warp: the polls cannot deadlock. Cross-cell data is read
+// from L2 (the library is compiled with -dlcm=cg), producers fence before publishing.
+// ====================================================================================
+struct PhaseInfo {
+  int32_t kind;         // 0 UNSAT, 1 SAT
+  int32_t step;         // step index inside the batch
+  int32_t prev_sat;     // the phase before this one was a SAT phase
+  int32_t next_sat;     // the next phase is a SAT phase: produce wt_elev / transm
+  int32_t write_slice;  // last phase of its step: snapshot the routing inputs
+  int32_t pad;
+  long long tag;        // global phase number (1-based count of completed phases once done)
+  StepConst t;
+};
+
+constexpr int kSliceFields = 12;
+__constant__ int kSliceFieldIds[kSliceFields];
+static const int kSliceFieldIdsHost[kSliceFields] = {
+    TRIBS_F_srf, TRIBS_F_hsrf, TRIBS_F_sbsrf, TRIBS_F_psrf, TRIBS_F_satsrf, TRIBS_F_Rain, TRIBS_F_SoilMoistureSC,
+    TRIBS_F_RootMoistureSC, TRIBS_F_SoilMoistureUNSC, TRIBS_F_NwtNew, TRIBS_F_Qpout, TRIBS_F_Qpin};
+
+__device__ __forceinline__ long long ld_relaxed_ll(const long long *p) {
+  long long v;
+  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_ll(long long *p, long long v) {
+  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ unsigned g_poll_cap_ns = 256;
+__device__ __forceinline__ bool wait_done(const long long *done, int j, long long need, int32_t *abort_flag) {
+  unsigned spins = 0, ns = 32;
+  const unsigned cap = g_poll_cap_ns;
+  while (ld_relaxed_ll(done + j) < need) {
+    __nanosleep(ns);
+    if (ns < cap) ns += ns;
+    if (((++spins) & 255u) == 0u) {
+      if (*(volatile int32_t *)abort_flag) return false;
+      if (spins > (1u << 22)) { atomicExch(abort_flag, 1); return false; }
+    }
+  }
+  return true;
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(128)
+pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const PhaseInfo *__restrict__ phases,
+                const int2 *__restrict__ tasks, int n_tasks, int32_t *task_counter, const int32_t *__restrict__ up_rowptr,
+                const int32_t *__restrict__ up_col, PubWord *pub, long long *done, int n_pad, double *wt_elev,
+                double *transm, double *slices, double *tile_sums, int n_tiles, double *globals, int last_sweep_dev,
+                int32_t *abort_flag, int32_t *flags) {
+  const int lane = threadIdx.x & 31;
+  for (;;) {
+    int idx = 0;
+    if (lane == 0) idx = atomicAdd(task_counter, 1);
+    idx = __shfl_sync(0xffffffffu, idx, 0);
+    if (idx >= n_tasks) break;
+    const int2 task = tasks[idx];
+    const PhaseInfo ph = phases[task.x];
+    const int i = task.y * kTile + lane;
+    const long long tag = ph.tag;
+    const DynView &d = (tag & 1) ? d_odd : d_even;   // Old = buffer tag%2, New = the other
+    const bool act = s.boundary[i] >= 0;
+    double sums[4] = {0.0, 0.0, 0.0, 0.0};
+    if (act) {
+      bool ok = wait_done(done, i, tag - 1, abort_flag);
+      const int r0 = s.nbr_rowptr[i], r1 = s.nbr_rowptr[i + 1];
+      if (ph.kind == 0) {
+        const int dst = s.flow_dest[i];
+        if (dst >= 0) ok = ok && wait_done(done, dst, tag - 1, abort_flag);
+        if (ph.prev_sat)
+          for (int k = r0; k < r1; k++) {
+            const int j = s.nbr_col[k];
+            if (j >= 0) ok = ok && wait_done(done, j, tag - 1, abort_flag);
+          }
+        __threadfence();
+        UnsatCellInputs u;
+        unsat_cell_load(u, s, d, i, m, ph.t);
+        double qpin = 0.0;
+        PubWord *ring = pub + (size_t)(tag & 1) * n_pad;
+        const int k1 = up_rowptr[i + 1];
+        for (int k = up_rowptr[i]; k < k1; k++) {
+          const PubWord *src = ring + up_col[k];
+          double v;
+          unsigned spins = 0, ns = 32;
+          const unsigned cap = g_poll_cap_ns;
+          while (!pub_load(src, tag, v)) {
+            __nanosleep(ns);
+            if (ns < cap) ns += ns;
+            if (((++spins) & 255u) == 0u) {
+              if (*(volatile int32_t *)abort_flag) { v = 0.0; break; }
+              if (spins > (1u << 22)) { atomicExch(abort_flag, 1); v = 0.0; break; }
+            }
+          }
+          qpin += v;
+        }
+        int state;
+        const double qout = unsat_cell_advance(u, qpin, &state);
+        pub_store(ring + i, qout, tag);
+        UnsatSums us;
+        unsat_cell_store(u, d, i, qpin, m, ph.t, us);
+        sums[0] = us.stok; sums[1] = us.tot_rain; sums[2] = us.tot_gw; sums[3] = us.tot_moist;
+        if (i == last_sweep_dev) globals[TRIBS_G_psrf_last] = u.c.psrf;
+        if (ph.next_sat) {
+          // ResetGW + the edge pre-pass for this cell: the post-sweep state is what SAT calls Old
+          DynView dn = d;
+          dn.f[TRIBS_F_NwtOld] = d.f[TRIBS_F_NwtNew];
+          sat_prepare_cell(s, dn, i, wt_elev, transm);
+        }
+      } else {
+        for (int k = r0; k < r1; k++) {
+          const int j = s.nbr_col[k];
+          if (j >= 0) ok = ok && wait_done(done, j, tag - 1, abort_flag);
+        }
+        __threadfence();
+        int overflow = 0;
+        const double gw = sat_gather<MAXC>(s, d, i, wt_elev, transm, &overflow);
+        if (overflow) flags[0] = 1;
+        SatSums ss;
+        sat_cell(s, d, i, gw, m, ph.t, ss);
+        sums[0] = ss.stok; sums[2] = ss.tot_gw; sums[3] = ss.tot_moist;
+      }
+      if (ph.write_slice) {
+        double *sl = slices + (size_t)ph.step * kSliceFields * n_pad + i;
+#pragma unroll
+        for (int k = 0; k < kSliceFields; k++) {
+          // no Reset() runs between the steps of a batch: a sweep-only step has no GW runoff
+          const double v = (ph.kind == 0 && k == 4) ? 0.0 : d.f[kSliceFieldIds[k]][i];
+          sl[(size_t)k * n_pad] = v;
+        }
+      }
+      __threadfence();
+      st_relaxed_ll(done + i, tag);
+      (void)ok;
+    }
+    double a = warp_sum_fixed(sums[0]), b = warp_sum_fixed(sums[1]);
+    double c2 = warp_sum_fixed(sums[2]), e = warp_sum_fixed(sums[3]);
+    if (lane == 0) {
+      double *ts = tile_sums + ((size_t)task.x * n_tiles + task.y) * 4;
+      ts[0] = a; ts[1] = b; ts[2] = c2; ts[3] = e;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+esrf_fixup_kernel(StaticView s, DynView d, int n_pad, double dtgw, const double *globals) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || s.boundary[i] < 0) return;
+  double esrf = globals[TRIBS_G_psrf_last] + d.f[TRIBS_F_esrf][i];
+  esrf = esrf / s.cosv[i];
+  d.f[TRIBS_F_esrf][i] = esrf * dtgw;
+}
+
+struct PipePlan {
+  std::vector<uint8_t> pattern;   // per step: 1 = has a SAT phase
+  std::vector<PhaseInfo> phases;  // tags/time constants are filled per run
+  int2 *d_tasks = nullptr;
+  PhaseInfo *d_phases = nullptr;
+  int n_tasks = 0, max_tau = 0;
+};
+
+struct PipeState {
+  long long *d_done = nullptr;
+  PubWord *d_pub2 = nullptr;       // [2][n_pad]
+  double *d_slices = nullptr;      // [max_steps][12][n_pad]
+  double *d_tile_sums = nullptr;   // [max_phases][n_tiles][4]
+  double *d_qeff_steps = nullptr;  // [max_steps][slots]
+  double *d_rain = nullptr;        // [max_steps][n_pad] per-cell forcing, device order
+  int32_t *d_task_counter = nullptr;
+  int max_steps = 0, last_steps = 0;
+  long long g = 0;                 // phases completed so far by every cell
+  int blocks = 0;
+  std::vector<PipePlan> plans;
+};
+static std::vector<std::pair<tribs_ctx *, PipeState *>> g_pipes;   // one PipeState per handle
+static PipeState *pipe_of(tribs_ctx *c) {
+  for (auto &p : g_pipes) if (p.first == c) return p.second;
+  g_pipes.push_back({c, new PipeState()});
+  return g_pipes.back().second;
+}
+
+static int build_plan(tribs_ctx *c, PipeState *ps, const std::vector<uint8_t> &pattern, PipePlan **out) {
+  for (auto &pl : ps->plans) if (pl.pattern == pattern) { *out = &pl; return 0; }
+  PipePlan pl;
+  pl.pattern = pattern;
+  for (size_t sidx = 0; sidx < pattern.size(); sidx++) {
+    PhaseInfo u{};
+    u.kind = 0; u.step = (int)sidx; u.write_slice = pattern[sidx] ? 0 : 1; u.next_sat = pattern[sidx];
+    pl.phases.push_back(u);
+    if (pattern[sidx]) {
+      PhaseInfo v{};
+      v.kind = 1; v.step = (int)sidx; v.write_slice = 1;
+      pl.phases.push_back(v);
+    }
+  }
+  const int P = (int)pl.phases.size();
+  for (int p = 1; p < P; p++) pl.phases[p].prev_sat = pl.phases[p - 1].kind == 1;
+  // tile-level topological times from the dependency rules of the kernel
+  const int nt = c->n_tiles, n_pad = c->n_pad;
+  std::vector<int32_t> h_up_rp(n_pad + 1), h_nbr_rp(n_pad + 1), h_fd(n_pad), h_bnd(n_pad);
+  CK(cudaMemcpy(h_up_rp.data(), c->d_up_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_nbr_rp.data(), c->sv.nbr_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_fd.data(), c->sv.flow_dest, n_pad * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_bnd.data(), c->sv.boundary, n_pad * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> h_up_col(h_up_rp[n_pad]), h_nbr_col(h_nbr_rp[n_pad]);
+  if (!h_up_col.empty()) CK(cudaMemcpy(h_up_col.data(), c->d_up_col, h_up_col.size() * 4, cudaMemcpyDeviceToHost));
+  if (!h_nbr_col.empty()) CK(cudaMemcpy(h_nbr_col.data(), c->sv.nbr_col, h_nbr_col.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> prev(nt, 0), cur(nt, 0);
+  std::vector<std::pair<int32_t, int2>> keyed;
+  keyed.reserve((size_t)P * nt);
+  for (int p = 0; p < P; p++) {
+    const PhaseInfo &ph = pl.phases[p];
+    for (int t = 0; t < nt; t++) {
+      int mval = p > 0 ? prev[t] : 0;
+      for (int lane = 0; lane < kTile; lane++) {
+        const int i = t * kTile + lane;
+        if (h_bnd[i] < 0) continue;
+        if (ph.kind == 0) {
+          if (p > 0 && h_fd[i] >= 0) mval = std::max(mval, prev[h_fd[i] / kTile]);
+          for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) mval = std::max(mval, cur[h_up_col[k] / kTile]);
+          if (p > 0 && ph.prev_sat)
+            for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++)
+              if (h_nbr_col[k] >= 0) mval = std::max(mval, prev[h_nbr_col[k] / kTile]);
+        } else if (p > 0) {
+          for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++)
+            if (h_nbr_col[k] >= 0) mval = std::max(mval, prev[h_nbr_col[k] / kTile]);
+        }
+      }
+      cur[t] = mval + 1;
+      keyed.push_back({cur[t], make_int2(p, t)});
+      pl.max_tau = std::max(pl.max_tau, cur[t]);
+    }
+    std::swap(prev, cur);
+  }
+  std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int32_t, int2> &a, const std::pair<int32_t, int2> &b) { return a.first < b.first; });
+  std::vector<int2> tasks(keyed.size());
+  for (size_t k = 0; k < keyed.size(); k++) tasks[k] = keyed[k].second;
+  pl.n_tasks = (int)tasks.size();
+  if (getenv("TRIBS_DEBUG")) {
+    // histogram of tasks per tau decile
+    fprintf(stderr, "[tribs] plan: steps=%zu phases=%d tiles=%d tasks=%d max_tau=%d levels=%d\n", pattern.size(), P, nt, pl.n_tasks, pl.max_tau, c->n_levels);
+  }
+  if (dev_upload(c, &pl.d_tasks, tasks) || dev_alloc(c, &pl.d_phases, (size_t)P)) return 1;
+  ps->plans.push_back(pl);
+  *out = &ps->plans.back();
+  return 0;
+}
+
+static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
+  if (!ps->d_done) {
+    if (dev_alloc(c, &ps->d_done, (size_t)c->n_pad) || dev_alloc(c, &ps->d_pub2, (size_t)2 * c->n_pad) ||
+        dev_alloc(c, &ps->d_task_counter, 4))
+      return 1;
+    CK(cudaMemset(ps->d_done, 0, (size_t)c->n_pad * sizeof(long long)));
+    CK(cudaMemset(ps->d_pub2, 0, (size_t)2 * c->n_pad * sizeof(PubWord)));
+    CK(cudaMemcpyToSymbol(kSliceFieldIds, kSliceFieldIdsHost, sizeof(kSliceFieldIdsHost)));
+    if (const char *e = getenv("TRIBS_POLL_CAP_NS")) {
+      unsigned cap = (unsigned)atoi(e);
+      CK(cudaMemcpyToSymbol(g_poll_cap_ns, &cap, sizeof(cap)));
+    }
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, c->device));
+    int per_sm = 0;
+    if (c->max_degree <= 16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<16>, 128, 0));
+    else if (c->max_degree <= 32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<32>, 128, 0));
+    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<64>, 128, 0));
+    if (per_sm < 1) return fail("tribs_gpu_run: pipeline_kernel does not fit on an SM");
+    ps->blocks = per_sm * prop.multiProcessorCount;
+  }
+  if (n_steps > ps->max_steps) {
+    // (re)allocate the per-step staging; old buffers stay in the handle's allocation list
+    const int slots = c->n_stream + 1;
+    if (dev_alloc(c, &ps->d_slices, (size_t)n_steps * kSliceFields * c->n_pad) ||
+        dev_alloc(c, &ps->d_tile_sums, (size_t)2 * n_steps * c->n_tiles * 4) ||
+        dev_alloc(c, &ps->d_qeff_steps, (size_t)n_steps * slots) || dev_alloc(c, &ps->d_rain, (size_t)n_steps * c->n_pad))
+      return 1;
+    ps->max_steps = n_steps;
+  }
+  return 0;
+}
+
+extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks) {
+  if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
+  CK(cudaSetDevice(c->device));
+  if (c->n_late > 0) return fail("tribs_gpu_run: the sweep order is not topological (late contributors); use tribs_gpu_step");
+  if (c->rc.flowexp > 0.0 && n_steps > 1) return fail("tribs_gpu_run: flowexp > 0 needs the channel router between steps; use tribs_gpu_step");
+  const uint32_t need = TRIBS_PHASE_UNSAT | TRIBS_PHASE_ROUTE | TRIBS_PHASE_RESET;
+  std::vector<uint8_t> pattern(n_steps);
+  for (int k = 0; k < n_steps; k++) {
+    if ((masks[k] & need) != need) return fail("tribs_gpu_run: every step must contain UNSAT, ROUTE and RESET");
+    pattern[k] = (masks[k] & TRIBS_PHASE_SAT) ? 1 : 0;
+  }
+  PipeState *ps = pipe_of(c);
+  if (ensure_pipe(c, ps, n_steps)) return 1;
+  PipePlan *pl = nullptr;
+  if (build_plan(c, ps, pattern, &pl)) return 1;
+  cudaStream_t st = c->stream;
+  const int n_pad = c->n_pad, P = (int)pl->phases.size();
+
+  // the pipeline works on fixed even/odd views; align them with the handle's current Old/New
+  if (!c->at_boundary) return fail("tribs_gpu_run: call it on a step boundary (after RESET)");
+  DynView d_even = c->dv, d_odd = c->dv;   // phase tag T: Old = buffer T%2
+  {
+    const int olds[7] = {TRIBS_F_NwtOld, TRIBS_F_MuOld, TRIBS_F_MiOld, TRIBS_F_NtOld, TRIBS_F_NfOld, TRIBS_F_RuOld, TRIBS_F_RiOld};
+    const int news[7] = {TRIBS_F_NwtNew, TRIBS_F_MuNew, TRIBS_F_MiNew, TRIBS_F_NtNew, TRIBS_F_NfNew, TRIBS_F_RuNew, TRIBS_F_RiNew};
+    // first phase has tag g+1 and must read the handle's current Old buffers
+    DynView &first = ((ps->g + 1) & 1) ? d_odd : d_even;
+    DynView &second = ((ps->g + 1) & 1) ? d_even : d_odd;
+    first = c->dv;
+    second = c->dv;
+    for (int k = 0; k < 7; k++) std::swap(second.f[olds[k]], second.f[news[k]]);
+  }
+  // per-phase constants and forcing
+  for (int p = 0; p < P; p++) {
+    PhaseInfo &ph = pl->phases[p];
+    const tribs_step_t &sp = steps[ph.step];
+    ph.tag = ps->g + 1 + p;
+    StepConst t;
+    t.dt = sp.dt; t.dt_gw = sp.dt_gw; t.now = sp.current_time; t.elapsed = (double)sp.elapsed_steps;
+    t.hourly_reset = sp.hourly_reset; t.psrf_last = 0.0; t.defer_esrf = 1;
+    t.rain_mode = 0;
+    if (ph.kind == 0) {
+      if (sp.rain_mode == TRIBS_RAIN_UNIFORM) { t.rain_mode = 1; t.rain_uniform = sp.rain_uniform; }
+      else if (sp.rain_mode == TRIBS_RAIN_PER_CELL) {
+        if (!sp.rain) return fail("tribs_gpu_run: rain_mode PER_CELL without a rain array");
+        double *dst = ps->d_rain + (size_t)ph.step * n_pad;
+        CK(cudaMemcpyAsync(c->d_stage, sp.rain, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, st));
+        scatter_from_sweep_kernel<<<(c->n + 255) / 256, 256, 0, st>>>(c->d_stage, c->d_dev_of_sweep, dst, c->n);
+        c->launches++;
+        t.rain_mode = 2; t.rain_cells = dst;
+      }
+    }
+    ph.t = t;
+  }
+  CK(cudaMemcpyAsync(pl->d_phases, pl->phases.data(), (size_t)P * sizeof(PhaseInfo), cudaMemcpyHostToDevice, st));
+  CK(cudaMemsetAsync(ps->d_task_counter, 0, 4, st));
+  {
+    PhaseTimer pt(c, 0);
+    int n_tasks = pl->n_tasks, n_tiles = c->n_tiles, last = c->last_sweep_dev, npad = n_pad;
+    void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &pl->d_phases, &pl->d_tasks, &n_tasks, &ps->d_task_counter,
+                    &c->d_up_rowptr, &c->d_up_col, &ps->d_pub2, &ps->d_done, &npad, &c->d_wt_elev, &c->d_transm,
+                    &ps->d_slices, &ps->d_tile_sums, &n_tiles, &c->d_globals, &last, &c->d_abort, &c->d_flags};
+    const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
+                     : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
+    int blocks = std::max(1, std::min(ps->blocks, (n_tasks + 3) / 4));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(128), args, 0, st));
+    c->launches++;
+    // basin accumulators, phase by phase in the reference's order
+    for (int p = 0; p < P; p++) {
+      const double *ts = ps->d_tile_sums + (size_t)p * c->n_tiles * 4;
+      if (pl->phases[p].kind == 0)
+        reduce_sums_kernel<<<1, 256, 0, st>>>(ts, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, TRIBS_G_TotRain, TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
+      else
+        reduce_sums_kernel<<<1, 256, 0, st>>>(ts, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, -1, TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
+      c->launches++;
+    }
+  }
+  ps->g += P;
+  // the handle's views after the batch: New = what the last phase wrote
+  {
+    const DynView &last_view = ((ps->g) & 1) ? d_odd : d_even;   // view of the last phase (tag == ps->g)
+    c->dv = last_view;
+    c->new_valid = true;
+  }
+  if (pattern[n_steps - 1]) {
+    esrf_fixup_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->sv, c->dv, n_pad, steps[n_steps - 1].dt_gw, c->d_globals);
+    c->launches++;
+    c->gw_dirty = true;
+  }
+  for (int k = 0; k < n_steps; k++) if (pattern[k]) c->gw_dirty = true;
+  // routing of every step from its snapshot, in step order
+  {
+    PhaseTimer pt(c, 2);
+    const int slots = c->n_stream + 1, window = c->route_window;
+    for (int k = 0; k < n_steps; k++) {
+      DynView dvs = c->dv;
+      for (int q = 0; q < kSliceFields; q++)
+        dvs.f[kSliceFieldIdsHost[q]] = ps->d_slices + ((size_t)k * kSliceFields + q) * n_pad;
+      const double now = steps[k].current_time;
+      route_seg_kernel<<<c->seg_blocks, kSegBlock, 0, st>>>(c->sv, dvs, c->rc, c->d_seg_cell, c->d_seg_slot, c->d_seg_path,
+                                                            c->d_seg_area, c->d_sn_dev, c->n_seg, now, steps[k].qstrm_outlet,
+                                                            c->d_ring, c->d_seg_bnd);
+      route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, c->d_seg_bnd, c->seg_blocks, slots, now, c->d_ring,
+                                                 ps->d_qeff_steps + (size_t)k * slots);
+      const int cur_bin0 = (int)floor((0.0 - .01 * c->rc.tstep + now) / c->rc.output_interval);
+      const int cur_bin1 = (int)floor((0.0 - .99 * c->rc.tstep + now) / c->rc.output_interval);
+      const int cur_bin = (cur_bin0 == cur_bin1) ? cur_bin0 : -1;
+      const int bin_base = (int)floor((now + .01 * c->rc.tstep) / c->rc.output_interval);
+      size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
+      route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, dvs, c->rc, c->mc, now, steps[k].qstrm_outlet,
+                                                                                   n_pad, window, bin_base, c->last_hill_dev,
+                                                                                   c->d_route_part, c->d_globals);
+      const int n_vals = 5 * window + kMeans;
+      route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
+                                                                            cur_bin, c->rc.res_limit, c->d_results);
+      c->launches += 4;
+    }
+    CK(cudaMemcpyAsync(c->d_qeff_now, ps->d_qeff_steps + (size_t)(n_steps - 1) * slots, (size_t)slots * sizeof(double),
+                       cudaMemcpyDeviceToDevice, st));
+  }
+  ps->last_steps = n_steps;
+  {  // RESET of the last step
+    PhaseTimer pt(c, 3);
+    swap_old_new(c);
+    const int zero5[5] = {TRIBS_F_Qpin, TRIBS_F_srf, TRIBS_F_sbsrf, TRIBS_F_hsrf, TRIBS_F_psrf};
+    for (int k = 0; k < 5; k++) CK(cudaMemsetAsync(c->dv.f[zero5[k]], 0, (size_t)n_pad * sizeof(double), st));
+    if (c->gw_dirty) {
+      CK(cudaMemsetAsync(c->dv.f[TRIBS_F_satsrf], 0, (size_t)n_pad * sizeof(double), st));
+      CK(cudaMemsetAsync(c->dv.f[TRIBS_F_gwchange], 0, (size_t)n_pad * sizeof(double), st));
+      c->gw_dirty = false;
+    }
+    c->new_valid = false;
+    c->at_boundary = true;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tribs_gpu_retrieve_qeff_steps(tribs_handle_t c, int n_steps, double *out) {
+  if (!c || !out) return fail("tribs_gpu_retrieve_qeff_steps: null argument");
+  PipeState *ps = pipe_of(c);
+  if (n_steps > ps->last_steps) return fail("tribs_gpu_retrieve_qeff_steps: more steps than the last tribs_gpu_run held");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(out, ps->d_qeff_steps, (size_t)n_steps * (c->n_stream + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
   return 0;
 }

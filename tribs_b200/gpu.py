@@ -81,7 +81,7 @@ class Step(C.Structure):
                 ("qstrm_outlet", C.c_double)]
 
 
-EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
+EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
@@ -102,6 +102,8 @@ def load():
     H = C.c_void_p
     L.tribs_gpu_init.argtypes = [C.POINTER(Mesh), C.POINTER(Params), C.POINTER(StateT), C.POINTER(Part), C.POINTER(H)]
     L.tribs_gpu_step.argtypes = [H, C.c_uint32, C.POINTER(Step)]
+    L.tribs_gpu_run.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32)]
+    L.tribs_gpu_retrieve_qeff_steps.argtypes = [H, C.c_int, PD]
     L.tribs_gpu_sync.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_push.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_retrieve_qeff.argtypes = [H, C.c_double, PD]
@@ -211,6 +213,39 @@ class GpuBasin:
             s.qstrm = _d(qstrm)
         s.qstrm_outlet = qstrm_outlet
         _chk(self.L.tribs_gpu_step(self.h, phases, C.byref(s)))
+
+    def run(self, steps: list[dict]):
+        """Pipelined batch. Each dict: current_time, elapsed_steps, hourly_reset, sat (bool), rain
+        (None | scalar | array), qstrm_outlet (optional)."""
+        k = len(steps)
+        arr = (Step * k)()
+        masks = (C.c_uint32 * k)()
+        keep = []
+        for q, sd in enumerate(steps):
+            s = arr[q]
+            s.current_time = sd["current_time"]
+            s.dt = self.tstep
+            s.dt_gw = self.gwstep
+            s.elapsed_steps = sd["elapsed_steps"]
+            s.hourly_reset = sd["hourly_reset"]
+            rain = sd.get("rain")
+            if rain is None:
+                s.rain_mode = RAIN_KEEP
+            elif np.isscalar(rain):
+                s.rain_mode = RAIN_UNIFORM
+                s.rain_uniform = float(rain)
+            else:
+                a = np.ascontiguousarray(rain, np.float64); keep.append(a)
+                s.rain_mode = RAIN_PER_CELL
+                s.rain = _d(a)
+            s.qstrm_outlet = sd.get("qstrm_outlet", 0.0)
+            masks[q] = PHASE_UNSAT | PHASE_ROUTE | PHASE_RESET | (PHASE_SAT if sd.get("sat") else 0)
+        _chk(self.L.tribs_gpu_run(self.h, k, arr, masks))
+
+    def retrieve_qeff_steps(self, k: int) -> np.ndarray:
+        out = np.empty((k, self.n_stream + 1))
+        _chk(self.L.tribs_gpu_retrieve_qeff_steps(self.h, k, _d(out)))
+        return out
 
     def sync(self, names, out: dict | None = None) -> dict:
         out = {} if out is None else out

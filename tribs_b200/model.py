@@ -134,6 +134,26 @@ class Simulator:
         self.hydro.Reset()
         return did_gw
 
+    def run_batch(self, k: int, rain_of_time=None, per_cell_rain=None):
+        """k whole steps in one pipelined launch (tribs_gpu_run). The host-side decisions of
+        every step (GW due, hourly reset, elapsed steps, rain) are taken here exactly as
+        one_step() would take them, then handed down together."""
+        t = self.timer
+        steps = []
+        for _ in range(k):
+            self.advance()
+            now = t.getCurrentTime()
+            sched = rain_of_time if rain_of_time is not None else self.rain_schedule
+            rain = sched(now) if sched is not None else None
+            if per_cell_rain is not None:
+                per_cell_rain.fill(0.0 if rain is None else rain)
+                rain = per_cell_rain.copy()
+            steps.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
+                              hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
+                              sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())), rain=rain))
+        self.dev.run(steps)
+        return steps
+
     def simulation_loop(self, max_steps=None):
         k = 0
         while not self.timer.IsFinished() and (max_steps is None or k < max_steps):

@@ -1,0 +1,264 @@
+"""Large synthetic basins, built directly in flattened form (no reference run needed).
+
+The reference's own mesh/flow-network setup is super-linear and is out of scope
+for the hot path, so for the 1M-50M-cell benchmark basins this module builds what that setup
+would hand to `tribs_gpu_init`: a jittered-grid TIN of a V-shaped valley with its Voronoi
+geometry, steepest-descent flow edges, stream column, sweep order (upslope cells first,
+hillslope before stream: the contract of tFlowNet::SortNodesByNetOrder, tFlowNet.cpp:429-498),
+hillslope/stream path lengths and per-cell parameters — the same dict layout the reference
+harness dumps (basin.trb), so everything downstream is shared.
+
+Triangulation: structured (each grid square split by the same diagonal), which equals the
+Delaunay triangulation for the small jitter used; Voronoi vertices are the triangle
+circumcentres, `vedglen` the distance between the two circumcentres flanking an edge and
+`varea` the shoelace area of the cell polygon (reference: tMesh.cpp:3336-3404,
+meshElements.cpp:858-867).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+# neighbour offsets (di, dj) counter-clockwise, consistent-diagonal triangulation
+_NB = [(1, 0), (1, 1), (0, 1), (-1, 0), (-1, -1), (0, -1)]
+
+
+def _circumcentre(ax, ay, bx, by, cx, cy):
+    d = 2.0 * (ax * (by - cy) + bx * (cy - ay) + cx * (ay - by))
+    a2, b2, c2 = ax * ax + ay * ay, bx * bx + by * by, cx * cx + cy * cy
+    ux = (a2 * (by - cy) + b2 * (cy - ay) + c2 * (ay - by)) / d
+    uy = (a2 * (cx - bx) + b2 * (ax - cx) + c2 * (bx - ax)) / d
+    return ux, uy
+
+
+def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, seed: int = 1,
+                slope_x: float = 0.05, slope_y: float = 0.02, stream_every: int = 0,
+                gw_depth_mm: float = 3000.0, bedrock_mm: float = 15000.0,
+                soil=(10.0, 0.45, 0.05, 0.4, -200.0, 0.001, 100.0, 100.0),
+                tstep_h: float = 0.0625, gwstep_h: float = 0.5, runtime_h: float = 48.0,
+                n_soil_classes: int = 1) -> dict:
+    """nx x ny active cells. One stream column along the valley axis (plus, with
+    stream_every=k>0, a tributary stream row every k rows draining to it). Returns the
+    flattened-basin dict in sweep order."""
+    rng = np.random.default_rng(seed)
+    # node grid with a one-node closed-boundary ring: indices 0..nx+1, 0..ny+1
+    NX, NY = nx + 2, ny + 2
+    ii, jj = np.meshgrid(np.arange(NX), np.arange(NY), indexing="xy")   # [NY, NX]
+    x = ii * spacing
+    y = jj * spacing
+    interior = (ii >= 1) & (ii <= nx) & (jj >= 1) & (jj <= ny)
+    ic = NX // 2
+    stream = interior & (ii == ic)
+    if stream_every:
+        stream |= interior & (jj % stream_every == 0)
+    jit = interior & ~stream
+    x = x + np.where(jit, rng.uniform(-jitter, jitter, x.shape), 0.0)
+    y = y + np.where(jit, rng.uniform(-jitter, jitter, y.shape), 0.0)
+    xc = ic * spacing
+    z = 100.0 + slope_y * y + slope_x * np.abs(x - xc)
+    if stream_every:
+        jm = jj % stream_every
+        z = z + 0.03 * np.minimum(jm, stream_every - jm) * spacing
+    # outlet: boundary node below the bottom stream cell
+    outlet_ij = (0, ic)
+
+    def sh(a, di, dj):
+        """a shifted so that result[j, i] = a[j+dj, i+di] (edges clamped; only interior is used)."""
+        return np.roll(np.roll(a, -dj, axis=0), -di, axis=1)
+
+    # circumcentres of the 6 triangles around every node: triangle k = (P, N_k, N_{k+1})
+    nbx = [sh(x, di, dj) for di, dj in _NB]
+    nby = [sh(y, di, dj) for di, dj in _NB]
+    ccx, ccy = [], []
+    for k in range(6):
+        k2 = (k + 1) % 6
+        ux, uy = _circumcentre(x, y, nbx[k], nby[k], nbx[k2], nby[k2])
+        ccx.append(ux); ccy.append(uy)
+    # Voronoi edge dual to spoke k joins circumcentres of triangles k-1 and k
+    vedg = [np.hypot(ccx[k] - ccx[k - 1], ccy[k] - ccy[k - 1]) for k in range(6)]
+    elen = [np.hypot(nbx[k] - x, nby[k] - y) for k in range(6)]
+    area = np.zeros_like(x)
+    for k in range(6):
+        k2 = (k + 1) % 6
+        area += ccx[k] * ccy[k2] - ccx[k2] * ccy[k]
+    area = 0.5 * np.abs(area)
+
+    # flow edge: steepest descent among the 6 neighbours; stream cells follow the stream
+    nbz = [sh(z, di, dj) for di, dj in _NB]
+    nb_stream = [sh(stream, di, dj) for di, dj in _NB]
+    nb_inter = [sh(interior, di, dj) for di, dj in _NB]
+    is_outlet = np.zeros_like(interior)
+    is_outlet[outlet_ij] = True
+    nb_outlet = [sh(is_outlet, di, dj) for di, dj in _NB]
+    slopes = np.stack([(z - nbz[k]) / elen[k] for k in range(6)])            # [6, NY, NX]
+    ok_hill = np.stack([nb_inter[k] for k in range(6)])
+    ok_strm = np.stack([nb_stream[k] | nb_outlet[k] for k in range(6)])
+    s_h = np.where(ok_hill, slopes, -np.inf)
+    s_s = np.where(ok_strm, slopes, -np.inf)
+    kbest = np.where(stream, np.argmax(s_s, axis=0), np.argmax(s_h, axis=0))
+    best_slope = np.take_along_axis(np.where(stream, s_s, s_h), kbest[None], 0)[0]
+    if not np.all(np.isfinite(best_slope[interior])):
+        raise RuntimeError("synthetic basin: a cell has no admissible downslope neighbour")
+
+    node_id = -np.ones((NY, NX), np.int64)
+    flat_int = np.flatnonzero(interior.ravel())
+    node_id.ravel()[flat_int] = np.arange(flat_int.size)
+    n = flat_int.size
+    di = np.array([d[0] for d in _NB]); dj = np.array([d[1] for d in _NB])
+    I = ii.ravel()[flat_int]; J = jj.ravel()[flat_int]
+    kb = kbest.ravel()[flat_int]
+    dest_node = node_id[J + dj[kb], I + di[kb]]          # -1 = outlet
+    is_stream = stream.ravel()[flat_int]
+
+    # depth below each cell to the outlet (pointer jumping) -> topological sweep order
+    flow_len = np.stack(elen)[kb, J, I]
+    ptr = dest_node.copy()
+    hops = np.where(ptr >= 0, 1, 0).astype(np.int64)
+    # path to the stream node / to the outlet
+    hill_ptr = np.where(is_stream, -1, dest_node)        # stops at stream cells
+    hill_d = np.where(is_stream, 0.0, flow_len)
+    hill_end = np.where(is_stream, np.arange(n), -1)     # stream node reached
+    # resolve hillslope chains by iterating level by level (depth <= nx)
+    order_depth = np.zeros(n, np.int64)
+    active = ~is_stream
+    cur = np.where(active, dest_node, -1)
+    # iterative relaxation: hillpath[i] = len + hillpath[dest], processed from stream outwards
+    hillpath = np.zeros(n)
+    stream_node = np.where(is_stream, np.arange(n), -1)
+    depth = np.zeros(n, np.int64)
+    pending = np.flatnonzero(~is_stream)
+    guard = 0
+    while pending.size:
+        d = dest_node[pending]
+        ready = (d < 0) | (stream_node[np.maximum(d, 0)] >= 0)
+        r = pending[ready]
+        dr = dest_node[r]
+        to_outlet = dr < 0
+        hillpath[r] = flow_len[r] + np.where(to_outlet, 0.0, hillpath[np.maximum(dr, 0)])
+        stream_node[r] = np.where(to_outlet, -2, stream_node[np.maximum(dr, 0)])
+        depth[r] = 1 + np.where(to_outlet, 0, depth[np.maximum(dr, 0)])
+        pending = pending[~ready]
+        guard += 1
+        if guard > 10 * (nx + ny):
+            raise RuntimeError("synthetic basin: flow graph has a cycle")
+    stream_node = np.where(stream_node == -2, -1, stream_node)
+    # stream cells: distance to outlet along the stream, and order upstream -> downstream
+    sdepth = np.zeros(n, np.int64)
+    streampath_s = np.zeros(n)
+    pend = np.flatnonzero(is_stream)
+    done = np.zeros(n, bool)
+    guard = 0
+    while pend.size:
+        d = dest_node[pend]
+        ready = (d < 0) | done[np.maximum(d, 0)]
+        r = pend[ready]
+        dr = dest_node[r]
+        streampath_s[r] = flow_len[r] + np.where(dr < 0, 0.0, streampath_s[np.maximum(dr, 0)])
+        sdepth[r] = 1 + np.where(dr < 0, 0, sdepth[np.maximum(dr, 0)])
+        done[r] = True
+        pend = pend[~ready]
+        guard += 1
+        if guard > 10 * (nx + ny):
+            raise RuntimeError("synthetic basin: stream graph has a cycle")
+    streampath = np.where(is_stream, streampath_s, streampath_s[np.maximum(stream_node, 0)] * (stream_node >= 0))
+    hillpath = np.where(is_stream, 0.0, hillpath)
+
+    # sweep order: hillslope cells far from the stream first, then stream cells upstream first
+    key = np.where(is_stream, 0, depth)
+    skey = np.where(is_stream, sdepth, 0)
+    order = np.lexsort((np.arange(n), -skey, -key, is_stream.astype(np.int64)))
+    pos = np.empty(n, np.int64)
+    pos[order] = np.arange(n)
+
+    def remap(idx):
+        return np.where(idx >= 0, pos[np.maximum(idx, 0)], -1).astype(np.int32)
+
+    def take(a2d):
+        return a2d.ravel()[flat_int][order]
+
+    # contributing area of every cell: accumulate along the sweep order (upslope first)
+    varea = take(area)
+    fdest = remap(dest_node)[order]
+    contr = varea.copy()
+    # level-synchronous accumulation (levels of the sweep DAG)
+    lvl = np.zeros(n, np.int64)
+    src = np.arange(n)
+    has = fdest >= 0
+    # a cell's level = 1 + max level of its contributors; iterate in sweep order chunks by depth
+    dd = np.where(is_stream[order], 10 ** 9 - sdepth[order], depth[order].max() + 1 - depth[order])
+    for lev in np.unique(dd):
+        sel = np.flatnonzero((dd == lev) & has)
+        np.add.at(contr, fdest[sel], contr[sel])
+
+    # spokes CSR (CCW from offset 0), columns remapped to sweep order
+    rowptr = np.arange(0, 6 * n + 1, 6, dtype=np.int32)
+    In, Jn = I[order], J[order]
+    nbr = np.empty((n, 6), np.int32)
+    slen = np.empty((n, 6)); svl = np.empty((n, 6)); slen_in = np.empty((n, 6)); svl_in = np.empty((n, 6))
+    for k in range(6):
+        nid = node_id[Jn + dj[k], In + di[k]]
+        nbr[:, k] = remap(nid)
+        slen[:, k] = elen[k][Jn, In]
+        svl[:, k] = vedg[k][Jn, In]
+        # complementary edge = spoke (k+3)%6 of the neighbour
+        k3 = (k + 3) % 6
+        jn2 = np.clip(Jn + dj[k], 0, NY - 1); in2 = np.clip(In + di[k], 0, NX - 1)
+        slen_in[:, k] = elen[k3][jn2, in2]
+        svl_in[:, k] = vedg[k3][jn2, in2]
+    listpos = np.arange(6 * n, dtype=np.int32)
+
+    kbo = kb[order]
+    flow_slope = best_slope.ravel()[flat_int][order]
+    flow_vedglen = svl[np.arange(n), kbo]
+    velcoef, velratio = 0.5, 5.0
+    hillvel, streamvel = velcoef / velratio, velcoef
+    hp, sp = hillpath[order], streampath[order]
+    ttime = (hp / hillvel + sp / streamvel) / 3600.0
+    bas_area = float(varea.sum())
+    out_interval = 1.0
+    maxtt = float(ttime.max())
+    res_limit = int(np.ceil((runtime_h + maxtt) / out_interval)) + 2
+
+    ks, ths, thr, lam, psib, f, ar, uar = soil
+    full = lambda v: np.full(n, float(v))
+    if n_soil_classes > 1:
+        cls = ((In // 64) + (Jn // 64)) % n_soil_classes
+        ks_a = ks * (1.0 + 0.25 * cls)
+        lam_a = lam * (1.0 + 0.05 * cls)
+    else:
+        ks_a, lam_a = full(ks), full(lam)
+    psib_abs = abs(psib)
+    nwt0 = full(gw_depth_mm)
+    # initial moisture = profile integral of the initial water table (tHydroModel.cpp:357-372)
+    dth = ths - thr
+    mi0 = thr * (nwt0 + psib) - ths * psib - dth / (lam_a - 1.0) * (psib + nwt0 * np.power(psib_abs / nwt0, lam_a))
+    basin = {
+        "n_active": np.array([n], np.int32), "n_nodes_total": np.array([NX * NY], np.int32),
+        "n_active_edges": np.array([6 * n], np.int32),
+        "id": np.arange(n, dtype=np.int32),
+        "boundary": np.where(is_stream[order], 3, 0).astype(np.int32),
+        "x": take(x), "y": take(y), "z": take(z), "varea": varea, "bedrock": full(bedrock_mm),
+        "flow_slope": flow_slope, "flow_len": slen[np.arange(n), kbo], "flow_vedglen": flow_vedglen,
+        "flow_dest": fdest, "stream_node": remap(stream_node)[order],
+        "hillpath": hp, "streampath": sp, "ttime": ttime, "contr_area": contr,
+        "reach": np.zeros(n, np.int32), "aspect": np.zeros(n),
+        "Ks": ks_a, "ThetaS": full(ths), "ThetaR": full(thr), "PoreSize": lam_a, "AirEBubPres": full(psib),
+        "DecayF": full(f), "SatAnRatio": full(ar), "UnsatAnRatio": full(uar),
+        "spoke_rowptr": rowptr, "spoke_nbr": nbr.ravel(), "spoke_edge_listpos": listpos,
+        "spoke_len": slen.ravel(), "spoke_vedglen": svl.ravel(),
+        "spoke_compl_len": slen_in.ravel(), "spoke_compl_vedglen": svl_in.ravel(),
+        "hillvel": np.array([hillvel]), "streamvel": np.array([streamvel]), "velratio": np.array([velratio]),
+        "velcoef": np.array([velcoef]), "flowexp": np.array([0.0]), "baseflow": np.array([0.01]),
+        "kincoef": np.array([0.1]), "dtReff": np.array([0.5]), "BasArea": np.array([bas_area]),
+        "BasArea_flow": np.array([bas_area]), "maxttime": np.array([maxtt]),
+        "outlet_stream_node": np.array([-1], np.int32), "outlet_contr_area": np.array([bas_area]),
+        "res_limit": np.array([res_limit], np.int32),
+        "IntStormMAX": np.array([10000.0]), "surfaceSoilDepth": np.array([100.0]), "rootZoneDepth": np.array([1000.0]),
+        "EToption": np.array([0], np.int32), "Ioption": np.array([0], np.int32), "SnOpt": np.array([0], np.int32),
+        "RunOnoption": np.array([0], np.int32), "RdstrOption": np.array([0], np.int32),
+        "GW_model_label": np.array([1], np.int32),
+        "tstep": np.array([tstep_h]), "gwstep": np.array([gwstep_h]), "metstep": np.array([1.0]),
+        "etistep": np.array([1.0]), "endtime": np.array([runtime_h]), "output_interval": np.array([out_interval]),
+        "init_NwtOld": nwt0, "init_NwtNew": nwt0.copy(), "init_MuOld": mi0, "init_MuNew": mi0.copy(),
+        "init_MiOld": mi0.copy(), "init_MiNew": mi0.copy(),
+    }
+    return basin
