@@ -55,6 +55,7 @@ TRIBS_HD void load_soil(Column &c, const StaticView &s, int i) {
   c.f = s.f[i]; c.ar = s.ar[i]; c.uar = s.uar[i];
   c.eps = 3 + 2 / c.lam;
   c.dbr = s.bedrock[i];
+  c.memo_ok = 0; c.memo_nwt = 0.0; c.memo_val = 0.0;
 }
 TRIBS_HD void load_old(Column &c, const DynView &d, int i) {
   c.nwt0 = c.nwt1 = d.f[TRIBS_F_NwtOld][i];
@@ -98,7 +99,7 @@ struct UnsatSums { double stok, tot_rain, tot_gw, tot_moist; };
 struct UnsatCellInputs {
   Column c;
   UnsatEnv env;
-  double varea, ractual, evsoi, evveg, kunsat, qpout_prev_raw;
+  double varea, ractual, evsoi, evveg, qpout_prev_raw;
 };
 
 // everything that does not depend on this step's lateral inflow
@@ -148,9 +149,6 @@ TRIBS_HD void unsat_cell_load(UnsatCellInputs &u, const StaticView &s, const Dyn
     if ((snwe > 1e-3) || (routewe > 0.)) ractual = 10.0 * routewe - evveg;
   }
   c.r = ractual;
-  double thsurf = c.ks != 0.0 ? c.init_moist_z(0.) : 0.0;
-  if (c.ru0 == 0.0) u.kunsat = c.ks * m_pow(((thsurf - c.thr) / (c.ths - c.thr)), c.eps);
-  else u.kunsat = c.ru0;
 }
 
 // the part that needs the lateral inflow; returns the New Qpout (mm^3/h)
@@ -159,7 +157,7 @@ TRIBS_HD double unsat_cell_advance(UnsatCellInputs &u, double qpin_raw, int *sta
   c.qpout = u.qpout_prev_raw * 1.0E-6 / u.varea;
   c.qpin = qpin_raw * 1.0E-6 / u.varea;
   c.r1 = (c.r + (c.qpin - c.qpout)) * c.cosv + 0.0;
-  *state_out = unsat_advance(c, u.env, u.kunsat);
+  *state_out = unsat_advance(c, u.env);
   return c.qpout;
 }
 

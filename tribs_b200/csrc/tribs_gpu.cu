@@ -62,8 +62,10 @@ struct RouteConst {
   int32_t res_limit, ring;
 };
 
+struct PipeState;
 struct tribs_ctx {
   int device = 0;
+  PipeState *pipe = nullptr;   // pipelined-batch state (tribs_gpu_run), created on first use
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
   int max_degree = 0, segment_cells = 0;
   cudaStream_t stream = nullptr;
@@ -74,6 +76,8 @@ struct tribs_ctx {
   DynView dv{};
   std::vector<void *> allocs;
   int32_t *d_up_rowptr = nullptr, *d_up_col = nullptr, *d_tile_counter = nullptr, *d_tile_order = nullptr;
+  int32_t *d_tile_hi = nullptr;
+  int n_hi_tiles = 0;
   PubWord *d_pub = nullptr;
   int32_t *d_abort = nullptr, *d_sweep_of_dev = nullptr, *d_dev_of_sweep = nullptr;
   int32_t *d_late_rowptr = nullptr, *d_late_col = nullptr;
@@ -709,6 +713,17 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   c->n_tiles = n_pad / kTile;
   c->sweep_of_dev.assign(n_pad, -1);
   for (int i = 0; i < n; i++) c->sweep_of_dev[c->dev_of_sweep[i]] = i;
+  // tiles on the critical cycle of a pipelined batch (river cells and the cells next to the river)
+  {
+    std::vector<int32_t> hi(c->n_tiles, 0);
+    int hi_depth = 2;
+    if (const char *e = getenv("TRIBS_HI_DEPTH")) hi_depth = atoi(e);
+    for (int i = 0; i < n; i++)
+      if (mesh->boundary[i] == 3 || depth[i] <= hi_depth) hi[c->dev_of_sweep[i] / kTile] = 1;
+    c->n_hi_tiles = 0;
+    for (int v : hi) c->n_hi_tiles += v;
+    if (dev_upload(c, &c->d_tile_hi, hi)) return 1;
+  }
   // claim order of the single-phase sweep: tiles by their topological time (longest chain of
   // upslope tiles); ascending tile index is a valid evaluation order for this recurrence
   {
@@ -1139,6 +1154,7 @@ extern "C" int tribs_gpu_wait(tribs_handle_t c) {
   return 0;
 }
 extern "C" void *tribs_gpu_stream(tribs_handle_t c) { return c ? (void *)c->stream : nullptr; }
+static void tribs_free_pipe(tribs_ctx *c);
 extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
@@ -1147,25 +1163,30 @@ extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
   for (void *p : c->allocs) cudaFree(p);
   cudaStreamDestroy(c->stream);
+  tribs_free_pipe(c);
   delete c;
   return 0;
 }
 
 // ====================================================================================
-// Pipelined batch (tribs_gpu_run): a space-time dataflow over (phase, 32-cell tile) tasks.
+// Pipelined batch (tribs_gpu_run): a space-time dataflow over (phase, 32-cell tile) tasks with a
+// device-side ready queue.
 //
-// Every cell carries a monotone counter done[i] = number of phases it has completed and a
-// two-slot ring of publication words {new Qpout, phase tag}. Phase with tag T reads the state
-// buffer T%2 and writes buffer (T+1)%2. A task (phase T, cell i) needs
-//   UNSAT: done[i] >= T-1, done[flow_dest] >= T-1 (reads the downslope Old values; also keeps an
-//          upslope cell at most one phase ahead of its receiver so two ring slots suffice),
-//          done[nbr] >= T-1 for all Voronoi neighbours when phase T-1 was a saturated-zone phase
-//          (they read the buffer this task overwrites), and pub[T%2][j].tag == T of every upslope j;
-//   SAT:   done[i] >= T-1 and done[nbr] >= T-1 for all Voronoi neighbours.
-// The host orders the tasks by a topological time tau computed from exactly these rules at tile
-// granularity; warps claim tasks in that order, so every dependency of a claimed task belongs to
-// a task claimed earlier by a resident warp: the polls cannot deadlock. Cross-cell data is read
-// from L2 (the library is compiled with -dlcm=cg), producers fence before publishing.
+// Phase with tag T reads the state buffer T%2 and writes buffer (T+1)%2; the new Qpout of a cell
+// is handed to its receiver through qpub[T%2]. At tile granularity a task (phase p, tile t) needs
+//   UNSAT: (p, u) for every tile u holding an upslope contributor of a cell of t         [Qpin]
+//          and, from the previous phase p-1: t itself and every tile holding a flow_dest of a
+//          cell of t (it reads the downslope Old values; this also keeps an upslope cell at most
+//          one phase ahead of its receiver, so two qpub buffers suffice)  -- or, when phase p-1
+//          was a saturated-zone phase, t and all Voronoi-neighbour tiles (their gathers read the
+//          buffer this task overwrites);
+//   SAT:   (p-1, t) and (p-1, v) for every Voronoi-neighbour tile v.
+// Every task has a counter of unmet inputs; a finishing warp fences, decrements the counters of
+// its dependents and pushes those that reach zero onto a global queue, from which idle warps pop.
+// No warp ever waits for a cell: all resident warps run ready work, and the long stream-cell
+// chain of one step overlaps with the bulk of the following steps. Values never depend on the
+// schedule (no atomics on data, partial sums are indexed by task). Cross-cell data is read
+// from L2 (the library is compiled with -dlcm=cg).
 // ====================================================================================
 struct PhaseInfo {
   int32_t kind;         // 0 UNSAT, 1 SAT
@@ -1173,8 +1194,8 @@ struct PhaseInfo {
   int32_t prev_sat;     // the phase before this one was a SAT phase
   int32_t next_sat;     // the next phase is a SAT phase: produce wt_elev / transm
   int32_t write_slice;  // last phase of its step: snapshot the routing inputs
-  int32_t pad;
-  long long tag;        // global phase number (1-based count of completed phases once done)
+  int32_t has_next;     // another phase follows inside the batch
+  long long tag;        // global phase number
   StepConst t;
 };
 
@@ -1184,84 +1205,118 @@ static const int kSliceFieldIdsHost[kSliceFields] = {
     TRIBS_F_srf, TRIBS_F_hsrf, TRIBS_F_sbsrf, TRIBS_F_psrf, TRIBS_F_satsrf, TRIBS_F_Rain, TRIBS_F_SoilMoistureSC,
     TRIBS_F_RootMoistureSC, TRIBS_F_SoilMoistureUNSC, TRIBS_F_NwtNew, TRIBS_F_Qpout, TRIBS_F_Qpin};
 
-__device__ __forceinline__ long long ld_relaxed_ll(const long long *p) {
-  long long v;
-  asm volatile("ld.relaxed.gpu.global.s64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+// tile-level dependency graph (three CSRs over tiles, self excluded, entries distinct)
+struct TileGraph {
+  const int32_t *up_rp, *up;      // tiles holding upslope contributors
+  const int32_t *down_rp, *down;  // tiles holding flow destinations
+  const int32_t *nbr_rp, *nbr;    // tiles holding Voronoi neighbours
+};
+
+__device__ __forceinline__ int ld_relaxed_i32(const int32_t *p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
-__device__ __forceinline__ void st_relaxed_ll(long long *p, long long v) {
-  asm volatile("st.relaxed.gpu.global.s64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+__device__ __forceinline__ void st_relaxed_i32(int32_t *p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
-__device__ unsigned g_poll_cap_ns = 256;
-__device__ __forceinline__ bool wait_done(const long long *done, int j, long long need, int32_t *abort_flag) {
-  unsigned spins = 0, ns = 32;
-  const unsigned cap = g_poll_cap_ns;
-  while (ld_relaxed_ll(done + j) < need) {
-    __nanosleep(ns);
-    if (ns < cap) ns += ns;
-    if (((++spins) & 255u) == 0u) {
-      if (*(volatile int32_t *)abort_flag) return false;
-      if (spins > (1u << 22)) { atomicExch(abort_flag, 1); return false; }
-    }
+// two ready queues: "hi" for the tiles on the critical cycle of the batch (river cells and the
+// cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
+// ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
+struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; };
+__device__ __forceinline__ void release_task(int32_t *cnt, const ReadyQueues &rq, int n_tiles, int p, int tile) {
+  const int task = p * n_tiles + tile;
+  if (atomicSub(cnt + task, 1) == 1) {
+    __threadfence();   // acquire the other producers' data before handing the task on
+    const int hi = rq.tile_hi[tile];
+    const int slot = atomicAdd(rq.ctl + (hi ? 1 : 3), 1);
+    st_relaxed_i32(rq.queue + (hi ? 0 : rq.n_tasks) + slot, task);
   }
-  return true;
 }
 
+// unmet-input counters of every task and the initially ready ones
+__global__ void __launch_bounds__(256)
+pipeline_init_kernel(TileGraph g, const PhaseInfo *__restrict__ phases, int n_phases, int n_tiles, int32_t *cnt,
+                     ReadyQueues rq) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= n_phases * n_tiles) return;
+  const int p = id / n_tiles, t = id % n_tiles;
+  const PhaseInfo ph = phases[p];
+  int c = 0;
+  if (ph.kind == 0) {
+    c += g.up_rp[t + 1] - g.up_rp[t];
+    if (p > 0) c += 1 + (ph.prev_sat ? g.nbr_rp[t + 1] - g.nbr_rp[t] : g.down_rp[t + 1] - g.down_rp[t]);
+  } else if (p > 0)
+    c += 1 + g.nbr_rp[t + 1] - g.nbr_rp[t];
+  cnt[id] = c;
+  if (c == 0) {
+    const int hi = rq.tile_hi[t];
+    rq.queue[(hi ? 0 : rq.n_tasks) + atomicAdd(rq.ctl + (hi ? 1 : 3), 1)] = id;
+  }
+}
+
+#ifndef TRIBS_PIPE_MIN_BLOCKS
+#define TRIBS_PIPE_MIN_BLOCKS 4
+#endif
 template <int MAXC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, TRIBS_PIPE_MIN_BLOCKS)
 pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const PhaseInfo *__restrict__ phases,
-                const int2 *__restrict__ tasks, int n_tasks, int32_t *task_counter, const int32_t *__restrict__ up_rowptr,
-                const int32_t *__restrict__ up_col, PubWord *pub, long long *done, int n_pad, double *wt_elev,
-                double *transm, double *slices, double *tile_sums, int n_tiles, double *globals, int last_sweep_dev,
-                int32_t *abort_flag, int32_t *flags) {
+                TileGraph g, int n_tasks, int32_t *cnt, ReadyQueues rq, int n_hi_tasks, int n_hi_blocks,
+                const int32_t *__restrict__ up_rowptr, const int32_t *__restrict__ up_col, double *qpub, int n_pad,
+                double *wt_elev, double *transm, double *slices, double *tile_sums, int n_tiles, double *globals,
+                int last_sweep_dev, int32_t *abort_flag, int32_t *flags) {
   const int lane = threadIdx.x & 31;
+  // Two ticket queues. Warp 0 of the first `n_hi_blocks` blocks (one per SM) serves the "hi" queue
+  // (river cells and the cells next to the river: their chain through all phases is the critical
+  // path and must never sit behind a backlog of bulk work); every other warp serves "lo". A warp
+  // takes a ticket (atomicAdd on the head) and waits for exactly that slot to be filled, so a
+  // newly released task is picked up at once by the warp that holds its ticket.
+  const bool hi_warp = (threadIdx.x < 32) && (blockIdx.x < (unsigned)n_hi_blocks);
+  const int my_total = hi_warp ? n_hi_tasks : n_tasks - n_hi_tasks;
+  int32_t *my_head = rq.ctl + (hi_warp ? 0 : 2);
+  const int32_t *my_queue = rq.queue + (hi_warp ? 0 : rq.n_tasks);
+  const unsigned ns_cap = hi_warp ? 128u : 2048u;
+  long long t_wait = 0, t_busy = 0, n_done = 0;
+  long long t_mark = clock64();
   for (;;) {
-    int idx = 0;
-    if (lane == 0) idx = atomicAdd(task_counter, 1);
-    idx = __shfl_sync(0xffffffffu, idx, 0);
-    if (idx >= n_tasks) break;
-    const int2 task = tasks[idx];
-    const PhaseInfo ph = phases[task.x];
-    const int i = task.y * kTile + lane;
+    int task = -1;
+    if (lane == 0) {
+      const int idx = atomicAdd(my_head, 1);
+      if (idx < my_total) {
+        unsigned spins = 0, ns = 32;
+        while ((task = ld_relaxed_i32(my_queue + idx)) < 0) {   // nothing of my class is ready yet
+          __nanosleep(ns);
+          if (ns < ns_cap) ns += ns;
+          if (((++spins) & 1023u) == 0u) {
+            if (*(volatile int32_t *)abort_flag) { task = -2; break; }
+            if (spins > (1u << 24)) { atomicExch(abort_flag, 1); task = -2; break; }
+          }
+        }
+      } else
+        task = -2;
+    }
+    task = __shfl_sync(0xffffffffu, task, 0);
+    { const long long now_c = clock64(); t_wait += now_c - t_mark; t_mark = now_c; }
+    if (task < 0) break;
+    const int p = task / n_tiles, tile = task - p * n_tiles;
+    __threadfence();   // acquire side of the producers' fence -> counter -> queue hand-off
+    const PhaseInfo ph = phases[p];
+    const int i = tile * kTile + lane;
     const long long tag = ph.tag;
     const DynView &d = (tag & 1) ? d_odd : d_even;   // Old = buffer tag%2, New = the other
     const bool act = s.boundary[i] >= 0;
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     if (act) {
-      bool ok = wait_done(done, i, tag - 1, abort_flag);
-      const int r0 = s.nbr_rowptr[i], r1 = s.nbr_rowptr[i + 1];
       if (ph.kind == 0) {
-        const int dst = s.flow_dest[i];
-        if (dst >= 0) ok = ok && wait_done(done, dst, tag - 1, abort_flag);
-        if (ph.prev_sat)
-          for (int k = r0; k < r1; k++) {
-            const int j = s.nbr_col[k];
-            if (j >= 0) ok = ok && wait_done(done, j, tag - 1, abort_flag);
-          }
-        __threadfence();
         UnsatCellInputs u;
         unsat_cell_load(u, s, d, i, m, ph.t);
+        const double *qsrc = qpub + (size_t)(tag & 1) * n_pad;
         double qpin = 0.0;
-        PubWord *ring = pub + (size_t)(tag & 1) * n_pad;
         const int k1 = up_rowptr[i + 1];
-        for (int k = up_rowptr[i]; k < k1; k++) {
-          const PubWord *src = ring + up_col[k];
-          double v;
-          unsigned spins = 0, ns = 32;
-          const unsigned cap = g_poll_cap_ns;
-          while (!pub_load(src, tag, v)) {
-            __nanosleep(ns);
-            if (ns < cap) ns += ns;
-            if (((++spins) & 255u) == 0u) {
-              if (*(volatile int32_t *)abort_flag) { v = 0.0; break; }
-              if (spins > (1u << 22)) { atomicExch(abort_flag, 1); v = 0.0; break; }
-            }
-          }
-          qpin += v;
-        }
+        for (int k = up_rowptr[i]; k < k1; k++) qpin += qsrc[up_col[k]];   // sweep order
         int state;
         const double qout = unsat_cell_advance(u, qpin, &state);
-        pub_store(ring + i, qout, tag);
+        qpub[(size_t)(tag & 1) * n_pad + i] = qout;
         UnsatSums us;
         unsat_cell_store(u, d, i, qpin, m, ph.t, us);
         sums[0] = us.stok; sums[1] = us.tot_rain; sums[2] = us.tot_gw; sums[3] = us.tot_moist;
@@ -1273,11 +1328,6 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
           sat_prepare_cell(s, dn, i, wt_elev, transm);
         }
       } else {
-        for (int k = r0; k < r1; k++) {
-          const int j = s.nbr_col[k];
-          if (j >= 0) ok = ok && wait_done(done, j, tag - 1, abort_flag);
-        }
-        __threadfence();
         int overflow = 0;
         const double gw = sat_gather<MAXC>(s, d, i, wt_elev, transm, &overflow);
         if (overflow) flags[0] = 1;
@@ -1294,16 +1344,35 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
           sl[(size_t)k * n_pad] = v;
         }
       }
-      __threadfence();
-      st_relaxed_ll(done + i, tag);
-      (void)ok;
     }
     double a = warp_sum_fixed(sums[0]), b = warp_sum_fixed(sums[1]);
     double c2 = warp_sum_fixed(sums[2]), e = warp_sum_fixed(sums[3]);
     if (lane == 0) {
-      double *ts = tile_sums + ((size_t)task.x * n_tiles + task.y) * 4;
+      double *ts = tile_sums + ((size_t)p * n_tiles + tile) * 4;
       ts[0] = a; ts[1] = b; ts[2] = c2; ts[3] = e;
     }
+    // hand the results on: fence, then lanes release the dependents in parallel
+    __threadfence();
+    __syncwarp();
+    if (ph.kind == 0) {
+      const int r0 = g.down_rp[tile], r1 = g.down_rp[tile + 1];
+      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p, g.down[k]);
+    }
+    if (ph.has_next) {
+      const bool wide = (ph.kind == 1) || ph.next_sat;   // a SAT phase on either side: neighbours
+      const int32_t *rp = wide ? g.nbr_rp : g.up_rp;
+      const int32_t *lst = wide ? g.nbr : g.up;
+      const int r0 = rp[tile], r1 = rp[tile + 1];
+      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p + 1, lst[k]);
+      if (lane == 0) release_task(cnt, rq, n_tiles, p + 1, tile);
+    }
+    { const long long now_c = clock64(); t_busy += now_c - t_mark; t_mark = now_c; n_done++; }
+  }
+  if (lane == 0) {   // scheduler statistics: [0..2] lo warps, [3..5] hi warps
+    unsigned long long *st = (unsigned long long *)(rq.ctl + 8) + (hi_warp ? 3 : 0);
+    atomicAdd(st + 0, (unsigned long long)t_wait);
+    atomicAdd(st + 1, (unsigned long long)t_busy);
+    atomicAdd(st + 2, (unsigned long long)n_done);
   }
 }
 
@@ -1319,29 +1388,25 @@ esrf_fixup_kernel(StaticView s, DynView d, int n_pad, double dtgw, const double 
 struct PipePlan {
   std::vector<uint8_t> pattern;   // per step: 1 = has a SAT phase
   std::vector<PhaseInfo> phases;  // tags/time constants are filled per run
-  int2 *d_tasks = nullptr;
   PhaseInfo *d_phases = nullptr;
-  int n_tasks = 0, max_tau = 0;
 };
 
 struct PipeState {
-  long long *d_done = nullptr;
-  PubWord *d_pub2 = nullptr;       // [2][n_pad]
+  double *d_qpub = nullptr;        // [2][n_pad] new Qpout by phase parity
   double *d_slices = nullptr;      // [max_steps][12][n_pad]
   double *d_tile_sums = nullptr;   // [max_phases][n_tiles][4]
   double *d_qeff_steps = nullptr;  // [max_steps][slots]
   double *d_rain = nullptr;        // [max_steps][n_pad] per-cell forcing, device order
-  int32_t *d_task_counter = nullptr;
+  int32_t *d_cnt = nullptr, *d_queue = nullptr, *d_headtail = nullptr;
+  TileGraph graph{};
   int max_steps = 0, last_steps = 0;
-  long long g = 0;                 // phases completed so far by every cell
-  int blocks = 0;
+  long long g = 0;                 // phases completed so far
+  int blocks = 0, n_sms = 0;
   std::vector<PipePlan> plans;
 };
-static std::vector<std::pair<tribs_ctx *, PipeState *>> g_pipes;   // one PipeState per handle
 static PipeState *pipe_of(tribs_ctx *c) {
-  for (auto &p : g_pipes) if (p.first == c) return p.second;
-  g_pipes.push_back({c, new PipeState()});
-  return g_pipes.back().second;
+  if (!c->pipe) c->pipe = new PipeState();
+  return c->pipe;
 }
 
 static int build_plan(tribs_ctx *c, PipeState *ps, const std::vector<uint8_t> &pattern, PipePlan **out) {
@@ -1359,70 +1424,74 @@ static int build_plan(tribs_ctx *c, PipeState *ps, const std::vector<uint8_t> &p
     }
   }
   const int P = (int)pl.phases.size();
-  for (int p = 1; p < P; p++) pl.phases[p].prev_sat = pl.phases[p - 1].kind == 1;
-  // tile-level topological times from the dependency rules of the kernel
-  const int nt = c->n_tiles, n_pad = c->n_pad;
-  std::vector<int32_t> h_up_rp(n_pad + 1), h_nbr_rp(n_pad + 1), h_fd(n_pad), h_bnd(n_pad);
-  CK(cudaMemcpy(h_up_rp.data(), c->d_up_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_nbr_rp.data(), c->sv.nbr_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_fd.data(), c->sv.flow_dest, n_pad * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_bnd.data(), c->sv.boundary, n_pad * 4, cudaMemcpyDeviceToHost));
-  std::vector<int32_t> h_up_col(h_up_rp[n_pad]), h_nbr_col(h_nbr_rp[n_pad]);
-  if (!h_up_col.empty()) CK(cudaMemcpy(h_up_col.data(), c->d_up_col, h_up_col.size() * 4, cudaMemcpyDeviceToHost));
-  if (!h_nbr_col.empty()) CK(cudaMemcpy(h_nbr_col.data(), c->sv.nbr_col, h_nbr_col.size() * 4, cudaMemcpyDeviceToHost));
-  std::vector<int32_t> prev(nt, 0), cur(nt, 0);
-  std::vector<std::pair<int32_t, int2>> keyed;
-  keyed.reserve((size_t)P * nt);
   for (int p = 0; p < P; p++) {
-    const PhaseInfo &ph = pl.phases[p];
-    for (int t = 0; t < nt; t++) {
-      int mval = p > 0 ? prev[t] : 0;
-      for (int lane = 0; lane < kTile; lane++) {
-        const int i = t * kTile + lane;
-        if (h_bnd[i] < 0) continue;
-        if (ph.kind == 0) {
-          if (p > 0 && h_fd[i] >= 0) mval = std::max(mval, prev[h_fd[i] / kTile]);
-          for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) mval = std::max(mval, cur[h_up_col[k] / kTile]);
-          if (p > 0 && ph.prev_sat)
-            for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++)
-              if (h_nbr_col[k] >= 0) mval = std::max(mval, prev[h_nbr_col[k] / kTile]);
-        } else if (p > 0) {
-          for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++)
-            if (h_nbr_col[k] >= 0) mval = std::max(mval, prev[h_nbr_col[k] / kTile]);
-        }
-      }
-      cur[t] = mval + 1;
-      keyed.push_back({cur[t], make_int2(p, t)});
-      pl.max_tau = std::max(pl.max_tau, cur[t]);
-    }
-    std::swap(prev, cur);
+    pl.phases[p].prev_sat = p > 0 && pl.phases[p - 1].kind == 1;
+    pl.phases[p].has_next = p + 1 < P;
   }
-  std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<int32_t, int2> &a, const std::pair<int32_t, int2> &b) { return a.first < b.first; });
-  std::vector<int2> tasks(keyed.size());
-  for (size_t k = 0; k < keyed.size(); k++) tasks[k] = keyed[k].second;
-  pl.n_tasks = (int)tasks.size();
-  if (getenv("TRIBS_DEBUG")) {
-    // histogram of tasks per tau decile
-    fprintf(stderr, "[tribs] plan: steps=%zu phases=%d tiles=%d tasks=%d max_tau=%d levels=%d\n", pattern.size(), P, nt, pl.n_tasks, pl.max_tau, c->n_levels);
-  }
-  if (dev_upload(c, &pl.d_tasks, tasks) || dev_alloc(c, &pl.d_phases, (size_t)P)) return 1;
+  if (dev_alloc(c, &pl.d_phases, (size_t)P)) return 1;
   ps->plans.push_back(pl);
   *out = &ps->plans.back();
   return 0;
 }
 
-static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
-  if (!ps->d_done) {
-    if (dev_alloc(c, &ps->d_done, (size_t)c->n_pad) || dev_alloc(c, &ps->d_pub2, (size_t)2 * c->n_pad) ||
-        dev_alloc(c, &ps->d_task_counter, 4))
-      return 1;
-    CK(cudaMemset(ps->d_done, 0, (size_t)c->n_pad * sizeof(long long)));
-    CK(cudaMemset(ps->d_pub2, 0, (size_t)2 * c->n_pad * sizeof(PubWord)));
-    CK(cudaMemcpyToSymbol(kSliceFieldIds, kSliceFieldIdsHost, sizeof(kSliceFieldIdsHost)));
-    if (const char *e = getenv("TRIBS_POLL_CAP_NS")) {
-      unsigned cap = (unsigned)atoi(e);
-      CK(cudaMemcpyToSymbol(g_poll_cap_ns, &cap, sizeof(cap)));
+// tile-level CSRs from the cell-level graph (host copies of the device arrays)
+static int build_tile_graph(tribs_ctx *c, PipeState *ps) {
+  const int nt = c->n_tiles, n_pad = c->n_pad;
+  std::vector<int32_t> h_up_rp(n_pad + 1), h_nbr_rp(n_pad + 1), h_fd(n_pad);
+  CK(cudaMemcpy(h_up_rp.data(), c->d_up_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_nbr_rp.data(), c->sv.nbr_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(h_fd.data(), c->sv.flow_dest, n_pad * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> h_up_col(h_up_rp[n_pad]), h_nbr_col(h_nbr_rp[n_pad]);
+  if (!h_up_col.empty()) CK(cudaMemcpy(h_up_col.data(), c->d_up_col, h_up_col.size() * 4, cudaMemcpyDeviceToHost));
+  if (!h_nbr_col.empty()) CK(cudaMemcpy(h_nbr_col.data(), c->sv.nbr_col, h_nbr_col.size() * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> up_rp(nt + 1, 0), down_rp(nt + 1, 0), nbr_rp(nt + 1, 0), up, down, nbr, tmp;
+  auto flush = [&](std::vector<int32_t> &dst, std::vector<int32_t> &rp, int t) {
+    std::sort(tmp.begin(), tmp.end());
+    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+    for (int v : tmp) if (v != t) dst.push_back(v);
+    rp[t + 1] = (int32_t)dst.size();
+    tmp.clear();
+  };
+  for (int t = 0; t < nt; t++) {
+    for (int l = 0; l < kTile; l++) { const int i = t * kTile + l; for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) tmp.push_back(h_up_col[k] / kTile); }
+    flush(up, up_rp, t);
+    for (int l = 0; l < kTile; l++) { const int i = t * kTile + l; if (h_fd[i] >= 0) tmp.push_back(h_fd[i] / kTile); }
+    flush(down, down_rp, t);
+    for (int l = 0; l < kTile; l++) {
+      const int i = t * kTile + l;
+      for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++) if (h_nbr_col[k] >= 0) tmp.push_back(h_nbr_col[k] / kTile);
+      if (h_fd[i] >= 0) tmp.push_back(h_fd[i] / kTile);
+      for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) tmp.push_back(h_up_col[k] / kTile);
     }
+    flush(nbr, nbr_rp, t);
+  }
+  // the neighbour relation must be symmetric for the counters to balance: symmetrise explicitly
+  {
+    std::vector<std::vector<int32_t>> adj(nt);
+    for (int t = 0; t < nt; t++) for (int k = nbr_rp[t]; k < nbr_rp[t + 1]; k++) { adj[t].push_back(nbr[k]); adj[nbr[k]].push_back(t); }
+    nbr.clear();
+    for (int t = 0; t < nt; t++) {
+      auto &a2 = adj[t];
+      std::sort(a2.begin(), a2.end());
+      a2.erase(std::unique(a2.begin(), a2.end()), a2.end());
+      for (int v : a2) nbr.push_back(v);
+      nbr_rp[t + 1] = (int32_t)nbr.size();
+    }
+  }
+  int32_t *p1, *p2, *p3, *p4, *p5, *p6;
+  if (dev_upload(c, &p1, up_rp) || dev_upload(c, &p2, up) || dev_upload(c, &p3, down_rp) || dev_upload(c, &p4, down) ||
+      dev_upload(c, &p5, nbr_rp) || dev_upload(c, &p6, nbr))
+    return 1;
+  ps->graph = TileGraph{p1, p2, p3, p4, p5, p6};
+  return 0;
+}
+
+static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
+  if (!ps->d_qpub) {
+    if (dev_alloc(c, &ps->d_qpub, (size_t)2 * c->n_pad) || dev_alloc(c, &ps->d_headtail, 4096)) return 1;
+    CK(cudaMemset(ps->d_qpub, 0, (size_t)2 * c->n_pad * sizeof(double)));
+    CK(cudaMemcpyToSymbol(kSliceFieldIds, kSliceFieldIdsHost, sizeof(kSliceFieldIdsHost)));
+    if (build_tile_graph(c, ps)) return 1;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, c->device));
     int per_sm = 0;
@@ -1431,13 +1500,15 @@ static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
     else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<64>, 128, 0));
     if (per_sm < 1) return fail("tribs_gpu_run: pipeline_kernel does not fit on an SM");
     ps->blocks = per_sm * prop.multiProcessorCount;
+    ps->n_sms = prop.multiProcessorCount;
   }
   if (n_steps > ps->max_steps) {
     // (re)allocate the per-step staging; old buffers stay in the handle's allocation list
     const int slots = c->n_stream + 1;
     if (dev_alloc(c, &ps->d_slices, (size_t)n_steps * kSliceFields * c->n_pad) ||
         dev_alloc(c, &ps->d_tile_sums, (size_t)2 * n_steps * c->n_tiles * 4) ||
-        dev_alloc(c, &ps->d_qeff_steps, (size_t)n_steps * slots) || dev_alloc(c, &ps->d_rain, (size_t)n_steps * c->n_pad))
+        dev_alloc(c, &ps->d_qeff_steps, (size_t)n_steps * slots) || dev_alloc(c, &ps->d_rain, (size_t)n_steps * c->n_pad) ||
+        dev_alloc(c, &ps->d_cnt, (size_t)2 * n_steps * c->n_tiles) || dev_alloc(c, &ps->d_queue, (size_t)4 * n_steps * c->n_tiles))
       return 1;
     ps->max_steps = n_steps;
   }
@@ -1461,21 +1532,15 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
   if (build_plan(c, ps, pattern, &pl)) return 1;
   cudaStream_t st = c->stream;
   const int n_pad = c->n_pad, P = (int)pl->phases.size();
-
-  // the pipeline works on fixed even/odd views; align them with the handle's current Old/New
   if (!c->at_boundary) return fail("tribs_gpu_run: call it on a step boundary (after RESET)");
-  DynView d_even = c->dv, d_odd = c->dv;   // phase tag T: Old = buffer T%2
+  // the pipeline works on fixed even/odd views; phase tag T reads buffer T%2
+  DynView d_even = c->dv, d_odd = c->dv;
   {
     const int olds[7] = {TRIBS_F_NwtOld, TRIBS_F_MuOld, TRIBS_F_MiOld, TRIBS_F_NtOld, TRIBS_F_NfOld, TRIBS_F_RuOld, TRIBS_F_RiOld};
     const int news[7] = {TRIBS_F_NwtNew, TRIBS_F_MuNew, TRIBS_F_MiNew, TRIBS_F_NtNew, TRIBS_F_NfNew, TRIBS_F_RuNew, TRIBS_F_RiNew};
-    // first phase has tag g+1 and must read the handle's current Old buffers
-    DynView &first = ((ps->g + 1) & 1) ? d_odd : d_even;
-    DynView &second = ((ps->g + 1) & 1) ? d_even : d_odd;
-    first = c->dv;
-    second = c->dv;
+    DynView &second = ((ps->g + 1) & 1) ? d_even : d_odd;   // the first phase (tag g+1) reads the handle's Old
     for (int k = 0; k < 7; k++) std::swap(second.f[olds[k]], second.f[news[k]]);
   }
-  // per-phase constants and forcing
   for (int p = 0; p < P; p++) {
     PhaseInfo &ph = pl->phases[p];
     const tribs_step_t &sp = steps[ph.step];
@@ -1498,18 +1563,25 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     ph.t = t;
   }
   CK(cudaMemcpyAsync(pl->d_phases, pl->phases.data(), (size_t)P * sizeof(PhaseInfo), cudaMemcpyHostToDevice, st));
-  CK(cudaMemsetAsync(ps->d_task_counter, 0, 4, st));
+  const int n_tasks = P * c->n_tiles;
+  CK(cudaMemsetAsync(ps->d_headtail, 0, 64 * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)2 * n_tasks * sizeof(int32_t), st));
   {
     PhaseTimer pt(c, 0);
-    int n_tasks = pl->n_tasks, n_tiles = c->n_tiles, last = c->last_sweep_dev, npad = n_pad;
-    void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &pl->d_phases, &pl->d_tasks, &n_tasks, &ps->d_task_counter,
-                    &c->d_up_rowptr, &c->d_up_col, &ps->d_pub2, &ps->d_done, &npad, &c->d_wt_elev, &c->d_transm,
-                    &ps->d_slices, &ps->d_tile_sums, &n_tiles, &c->d_globals, &last, &c->d_abort, &c->d_flags};
+    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks};
+    int n_hi_tasks = P * c->n_hi_tiles;
+    int n_hi_blocks = std::min(ps->blocks, ps->n_sms);
+    if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_blocks = std::max(1, std::min(ps->blocks, atoi(e)));
+    pipeline_init_kernel<<<(n_tasks + 255) / 256, 256, 0, st>>>(ps->graph, pl->d_phases, P, c->n_tiles, ps->d_cnt, rq);
+    int ntk = n_tasks, n_tiles = c->n_tiles, last = c->last_sweep_dev, npad = n_pad;
+    void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &pl->d_phases, &ps->graph, &ntk, &ps->d_cnt, &rq, &n_hi_tasks, &n_hi_blocks,
+                    &c->d_up_rowptr, &c->d_up_col, &ps->d_qpub, &npad, &c->d_wt_elev, &c->d_transm, &ps->d_slices,
+                    &ps->d_tile_sums, &n_tiles, &c->d_globals, &last, &c->d_abort, &c->d_flags};
     const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
                      : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
-    int blocks = std::max(1, std::min(ps->blocks, (n_tasks + 3) / 4));
+    int blocks = ps->blocks;
     CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(128), args, 0, st));
-    c->launches++;
+    c->launches += 2;
     // basin accumulators, phase by phase in the reference's order
     for (int p = 0; p < P; p++) {
       const double *ts = ps->d_tile_sums + (size_t)p * c->n_tiles * 4;
@@ -1520,17 +1592,21 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
       c->launches++;
     }
   }
+  if (getenv("TRIBS_DEBUG")) {
+    unsigned long long h[6];
+    CK(cudaMemcpyAsync(h, ps->d_headtail + 8, sizeof(h), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    fprintf(stderr, "[tribs] batch: phases=%d tiles=%d hi_tiles=%d | lo warps: wait %.1f%% busy/task %.1f us tasks %llu | hi warps: wait %.1f%% busy/task %.1f us tasks %llu\n",
+            P, c->n_tiles, c->n_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2],
+            100.0 * h[3] / std::max(1.0, (double)(h[3] + h[4])), h[4] / std::max(1.0, (double)h[5]) / 1.9e3, h[5]);
+  }
   ps->g += P;
   // the handle's views after the batch: New = what the last phase wrote
-  {
-    const DynView &last_view = ((ps->g) & 1) ? d_odd : d_even;   // view of the last phase (tag == ps->g)
-    c->dv = last_view;
-    c->new_valid = true;
-  }
+  c->dv = ((ps->g) & 1) ? d_odd : d_even;
+  c->new_valid = true;
   if (pattern[n_steps - 1]) {
     esrf_fixup_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->sv, c->dv, n_pad, steps[n_steps - 1].dt_gw, c->d_globals);
     c->launches++;
-    c->gw_dirty = true;
   }
   for (int k = 0; k < n_steps; k++) if (pattern[k]) c->gw_dirty = true;
   // routing of every step from its snapshot, in step order
@@ -1589,4 +1665,9 @@ extern "C" int tribs_gpu_retrieve_qeff_steps(tribs_handle_t c, int n_steps, doub
   CK(cudaMemcpyAsync(out, ps->d_qeff_steps, (size_t)n_steps * (c->n_stream + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
+}
+
+static void tribs_free_pipe(tribs_ctx *c) {
+  delete c->pipe;   // its device buffers live in the handle's allocation list
+  c->pipe = nullptr;
 }

@@ -14,7 +14,7 @@ import numpy as np
 
 PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(PKG)
-LIB_PATH = os.path.join(PKG, "libtribs_gpu.so")
+LIB_PATH = os.environ.get("TRIBS_GPU_LIB", os.path.join(PKG, "libtribs_gpu.so"))
 HEADER = os.path.join(ROOT, "include", "tribs_gpu.h")
 
 
