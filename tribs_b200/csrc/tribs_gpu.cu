@@ -378,24 +378,49 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
 __global__ void __launch_bounds__(1024)
 route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n_blocks, int n_slots, double now,
                        double *ring, double *qeff_now) {
-  if (threadIdx.x == 0) {
-    long long ckey = -1;
-    double cval = 0.0;
-    auto flush = [&](long long key, double val) {
-      if (key < 0) return;
-      const int slot = (int)(key >> 32), bin = (int)(key & 0xffffffffLL);
-      ring[(size_t)slot * rc.ring + (bin % rc.ring)] += val;
-    };
-    for (int b = 0; b < n_blocks; b++) {
-      const SegBoundary x = bnd[b];
-      if (x.first_key >= 0) {
-        if (x.first_key == ckey) cval += x.first_val;
-        else { flush(ckey, cval); ckey = x.first_key; cval = x.first_val; }
+  // The records are staged through shared memory 512 at a time (coalesced loads); one thread
+  // merges them in order into a list of finished (key, sum) runs -- sequential by nature but free
+  // of global memory -- and then all threads add the finished runs to the rings in parallel (the
+  // keys of finished runs are distinct, so there are no conflicts).
+  __shared__ SegBoundary sh_bnd[512];
+  __shared__ long long sh_out_key[1025];
+  __shared__ double sh_out_val[1025];
+  __shared__ long long sh_ckey;
+  __shared__ double sh_cval;
+  __shared__ int sh_nout;
+  if (threadIdx.x == 0) { sh_ckey = -1; sh_cval = 0.0; }
+  for (int base = 0; base < n_blocks; base += 512) {
+    const int cnt = min(512, n_blocks - base);
+    __syncthreads();
+    if ((int)threadIdx.x < cnt) sh_bnd[threadIdx.x] = bnd[base + threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      long long ckey = sh_ckey;
+      double cval = sh_cval;
+      int nout = 0;
+      auto flush = [&](long long key, double val) {
+        if (key < 0) return;
+        sh_out_key[nout] = key; sh_out_val[nout] = val; nout++;
+      };
+      for (int b = 0; b < cnt; b++) {
+        const SegBoundary x = sh_bnd[b];
+        if (x.first_key >= 0) {
+          if (x.first_key == ckey) cval += x.first_val;
+          else { flush(ckey, cval); ckey = x.first_key; cval = x.first_val; }
+        }
+        if (x.last_key >= 0) { flush(ckey, cval); ckey = x.last_key; cval = x.last_val; }
       }
-      if (x.last_key >= 0) { flush(ckey, cval); ckey = x.last_key; cval = x.last_val; }
+      if (base + 512 >= n_blocks) { flush(ckey, cval); ckey = -1; cval = 0.0; }
+      sh_ckey = ckey; sh_cval = cval; sh_nout = nout;
     }
-    flush(ckey, cval);
+    __syncthreads();
+    for (int k = threadIdx.x; k < sh_nout; k += blockDim.x) {
+      const long long key = sh_out_key[k];
+      const int slot = (int)(key >> 32), bin = (int)(key & 0xffffffffLL);
+      ring[(size_t)slot * rc.ring + (bin % rc.ring)] += sh_out_val[k];
+    }
   }
+  __threadfence();
   __syncthreads();
   const int cur = (int)ceil(now / rc.dt_reff);
   const bool at_end = ((int)ceil(now / rc.dt_reff) == (int)floor(now / rc.dt_reff));
@@ -1306,17 +1331,27 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
     const DynView &d = (tag & 1) ? d_odd : d_even;   // Old = buffer tag%2, New = the other
     const bool act = s.boundary[i] >= 0;
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
-    if (act) {
-      if (ph.kind == 0) {
-        UnsatCellInputs u;
+    UnsatCellInputs u;
+    double qpin = 0.0;
+    if (ph.kind == 0) {
+      if (act) {
         unsat_cell_load(u, s, d, i, m, ph.t);
         const double *qsrc = qpub + (size_t)(tag & 1) * n_pad;
-        double qpin = 0.0;
         const int k1 = up_rowptr[i + 1];
         for (int k = up_rowptr[i]; k < k1; k++) qpin += qsrc[up_col[k]];   // sweep order
         int state;
         const double qout = unsat_cell_advance(u, qpin, &state);
         qpub[(size_t)(tag & 1) * n_pad + i] = qout;
+      }
+      // the downslope tiles of this phase only need the new Qpout: release them before the
+      // write-back and the diagnostics, which are off the critical chain along the river
+      __threadfence();
+      __syncwarp();
+      const int r0 = g.down_rp[tile], r1 = g.down_rp[tile + 1];
+      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p, g.down[k]);
+    }
+    if (act) {
+      if (ph.kind == 0) {
         UnsatSums us;
         unsat_cell_store(u, d, i, qpin, m, ph.t, us);
         sums[0] = us.stok; sums[1] = us.tot_rain; sums[2] = us.tot_gw; sums[3] = us.tot_moist;
@@ -1354,10 +1389,6 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
     // hand the results on: fence, then lanes release the dependents in parallel
     __threadfence();
     __syncwarp();
-    if (ph.kind == 0) {
-      const int r0 = g.down_rp[tile], r1 = g.down_rp[tile + 1];
-      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p, g.down[k]);
-    }
     if (ph.has_next) {
       const bool wide = (ph.kind == 1) || ph.next_sat;   // a SAT phase on either side: neighbours
       const int32_t *rp = wide ? g.nbr_rp : g.up_rp;
