@@ -50,6 +50,9 @@
 #include "src/Headers/TemplDefinitions.h"
 #include "src/tHydro/tSnowPack.h"
 #include "src/tFlowNet/tFlowResults.h"
+// the reference-side binding of the C ABI (what INTEGRATION.md tells a maintainer to add);
+// inside tHydroModel it would have member access, here it gets it through the macro above
+#include "tribs_ref_binding.h"
 #undef private
 #undef protected
 
@@ -506,6 +509,7 @@ int main(int argc, char **argv) {
     int snap_from = 1, snap_to = 0, snap_every = 1;
     string phases = "ugre";
     bool do_kat = false, do_basin = true;
+    string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
     vector<char*> rargs;
     for (int i = 0; i < argc; i++) {
         string a = argv[i];
@@ -515,6 +519,7 @@ int main(int argc, char **argv) {
         else if (a == "--snap-every" && i + 1 < argc) snap_every = atoi(argv[++i]);
         else if (a == "--phases" && i + 1 < argc) phases = argv[++i];
         else if (a == "--kat") do_kat = true;
+        else if (a == "--gpu" && i + 1 < argc) gpu_lib = argv[++i];
         else if (a == "--no-basin") do_basin = false;
         else rargs.push_back(argv[i]);
     }
@@ -549,6 +554,11 @@ int main(int argc, char **argv) {
     if (do_basin) H.dump_basin(outdir + "/basin.trb", InputFile);
     if (do_kat) H.dump_kat(outdir + "/kat.trb");
 
+    TribsGpuBinding gpu;
+    const bool use_gpu = !gpu_lib.empty();
+    if (use_gpu) gpu.attach(&BasinMesh, &Flow, &Moisture, &Timer, gpu_lib.c_str());
+    vector<double> qout_series;
+
     std::unique_ptr<TrbWriter> sw;
     if (snap_to >= snap_from) sw.reset(new TrbWriter(outdir + "/steps.trb"));
 
@@ -566,7 +576,8 @@ int main(int argc, char **argv) {
         Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
         double t1 = now_s();
         // SubSurfaceHydroProcesses, split so the state between the two zones is observable
-        Moisture.UnSaturatedZone(Timer.getTimeStep());
+        if (use_gpu) gpu.UnSaturatedZone(Timer.getTimeStep());
+        else Moisture.UnSaturatedZone(Timer.getTimeStep());
         double t2 = now_s();
         if (snap && phases.find('u') != string::npos) {
             snprintf(pre, sizeof pre, "s%d_u_", step); H.dump_state(*sw, pre, false);
@@ -575,8 +586,8 @@ int main(int argc, char **argv) {
         Sim.GW_label = fmod(Timer.getCurrentTime(), Timer.getGWTimeStep());
         bool gw = false;
         if (SimCtrl.GW_model_label && !Sim.GW_label) {
-            Moisture.ResetGW();
-            Moisture.SaturatedZone(Timer.getGWTimeStep());
+            if (use_gpu) { gpu.ResetGW(); gpu.SaturatedZone(Timer.getGWTimeStep()); }
+            else { Moisture.ResetGW(); Moisture.SaturatedZone(Timer.getGWTimeStep()); }
             gw = true;
         }
         double t3 = now_s();
@@ -584,7 +595,9 @@ int main(int argc, char **argv) {
             snprintf(pre, sizeof pre, "s%d_g_", step); H.dump_state(*sw, pre, true);
         }
         double t3b = now_s();
+        if (use_gpu) gpu.syncToNodes();   // tKinemat / tFlowNet / tCOutput run on the host, unchanged
         Flow.SurfaceFlow();
+        qout_series.push_back(Flow.Qout);
         double t4 = now_s();
         if (snap && phases.find('r') != string::npos) {
             snprintf(pre, sizeof pre, "s%d_r_", step); H.dump_state(*sw, pre, false);
@@ -594,6 +607,7 @@ int main(int argc, char **argv) {
         Sim.OutputSimulatedVars(&Flow);
         Sim.UpdateWaterBalance(&Balance);
         Moisture.Reset();
+        if (use_gpu) gpu.Reset();
         double t5 = now_s();
         if (snap && phases.find('e') != string::npos) {
             snprintf(pre, sizeof pre, "s%d_e_", step); H.dump_state(*sw, pre, true);
@@ -604,6 +618,14 @@ int main(int argc, char **argv) {
         t_loop += (t1 - t0) + (t2 - t1) + (t3 - t2b) + (t4 - t3b) + (t5 - t4b);
     }
     if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
+    {   // outlet hydrograph of the channel router (tKinemat::Qout), one value per step
+        TrbWriter qw(outdir + (use_gpu ? "/qout_gpu.trb" : "/qout_ref.trb"));
+        qw.f64("qout", qout_series);
+        qw.f64("NwtNew", H.col([](tCNode *c) { return c->getNwtNew(); }));
+        qw.f64("MuNew", H.col([](tCNode *c) { return c->getMuNew(); }));
+        qw.f64("NfNew", H.col([](tCNode *c) { return c->getNfNew(); }));
+        qw.f64("cumsrf", H.col([](tCNode *c) { return c->getCumSrf(); }));
+    }
     Sim.end_simulation(&Flow);
 
     long ncell = (long)H.cells.size();

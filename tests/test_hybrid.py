@@ -1,0 +1,37 @@
+"""GPU test of the drop-in boundary: the reference's own objects and time loop
+(oracle/_ref/tribs_ref_harness --gpu) drive the B200 path through the binding in
+tribs_b200/host/tribs_ref_binding.h; tKinemat's channel routing, fed from the synced tCNode
+fields, must give the same outlet hydrograph as the pure reference run (north_star: outlet
+hydrograph within 1e-6 relative), and the final per-cell Nwt / Mu / Nf must agree too."""
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+from refrun import HARNESS, ROOT, have_harness, spec_for
+from tribs_b200.synth import write_basin
+from tribs_b200.trb import read_trb
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("name,n,hours", [("deep", 24, 30.0), ("shallow", 20, 30.0)])
+def test_reference_simulator_drives_gpu_path(name, n, hours, built):
+    d = tempfile.mkdtemp(prefix="tribshyb_")
+    write_basin(spec_for(name, n, runtime_h=hours, seed=2), d)
+    lib = os.path.join(ROOT, "tribs_b200", "libtribs_gpu.so")
+    for extra in ([], ["--gpu", lib]):
+        r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", *extra], cwd=d, capture_output=True,
+                           text=True, timeout=1200)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    ref, got = read_trb(os.path.join(d, "qout_ref.trb")), read_trb(os.path.join(d, "qout_gpu.trb"))
+    q0, q1 = ref["qout"], got["qout"]
+    assert q0.shape == q1.shape and q0.max() > 0.0
+    scale = max(q0.max(), 1e-12)
+    assert np.abs(q0 - q1).max() <= 1e-6 * scale, ("outlet hydrograph", np.abs(q0 - q1).max(), scale)
+    for f in ("NwtNew", "MuNew", "NfNew"):
+        err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), 1e-6)
+        assert err.max() <= 1e-6, (f, err.max())

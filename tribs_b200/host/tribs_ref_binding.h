@@ -1,0 +1,191 @@
+// tribs_ref_binding.h — the binding a tRIBS maintainer adds to drive the B200 path from the
+// reference's own objects. It is compiled against the reference headers (it is the body that
+// tHydroModel::UnSaturatedZone / ResetGW / SaturatedZone / Reset forward to) and talks to
+// libtribs_gpu.so only through the C ABI of include/tribs_gpu.h.
+//
+//   attach():  walks tMesh<tCNode> exactly like the reference's own loops
+//              (tMeshListIter::FirstP/NextP/IsActive, tEdge::getCCWEdg ...) and flattens it into
+//              tribs_mesh_t / tribs_params_t / tribs_state_t  -> tribs_gpu_init
+//   UnSaturatedZone(dt) / ResetGW() / SaturatedZone(dtGW) / Reset():  tribs_gpu_step with the
+//              flags the reference computes on the host (tRunTimer arithmetic, fmod tests)
+//   syncToNodes(mask):  tribs_gpu_sync + scatter into tCNode through its own setters, so
+//              tKinemat (channel routing), tCOutput, tWaterBalance and tRestart keep working on
+//              the host unchanged.
+//
+// In this repo the header is compiled into the reference test harness (mode --gpu), which is
+// how tests/test_hybrid.py checks that the reference's Simulator can drive the GPU path and
+// that the outlet hydrograph of tKinemat stays within 1e-6 of the pure reference run.
+#pragma once
+#include <dlfcn.h>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <unordered_map>
+#include <vector>
+
+#include "tribs_gpu.h"
+
+struct TribsGpuBinding {
+  // ---- C ABI entry points (resolved with dlsym so the host binary has no link-time dependency)
+  void *lib = nullptr;
+  decltype(&tribs_gpu_init) p_init = nullptr;
+  decltype(&tribs_gpu_step) p_step = nullptr;
+  decltype(&tribs_gpu_sync) p_sync = nullptr;
+  decltype(&tribs_gpu_destroy) p_destroy = nullptr;
+  decltype(&tribs_gpu_last_error) p_err = nullptr;
+  tribs_handle_t h = nullptr;
+
+  tMesh<tCNode> *mesh = nullptr;
+  tRunTimer *timer = nullptr;
+  std::vector<tCNode *> cells;                       // active cells in sweep (list) order
+  std::unordered_map<tNode *, int> pos;
+  std::vector<std::vector<double>> stage;            // host SoA staging, one vector per field
+  std::vector<double> rain;
+
+  [[noreturn]] void die(const char *what) {          // the reference's error convention
+    std::cout << "\nError: tribs_gpu: " << what << ": " << (p_err ? p_err() : dlerror()) << std::endl;
+    exit(2);
+  }
+  int idx(tNode *n) const { auto k = pos.find(n); return k == pos.end() ? -1 : k->second; }
+
+  void attach(tMesh<tCNode> *m, tKinemat *flow, tHydroModel *hydro, tRunTimer *t, const char *libpath) {
+    mesh = m; timer = t;
+    lib = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
+    if (!lib) die("dlopen");
+    p_init = (decltype(p_init))dlsym(lib, "tribs_gpu_init");
+    p_step = (decltype(p_step))dlsym(lib, "tribs_gpu_step");
+    p_sync = (decltype(p_sync))dlsym(lib, "tribs_gpu_sync");
+    p_destroy = (decltype(p_destroy))dlsym(lib, "tribs_gpu_destroy");
+    p_err = (decltype(p_err))dlsym(lib, "tribs_gpu_last_error");
+    if (!p_init || !p_step || !p_sync || !p_destroy || !p_err) die("dlsym");
+
+    tMeshListIter<tCNode> it(mesh->getNodeList());
+    for (tCNode *cn = it.FirstP(); it.IsActive(); cn = it.NextP()) { pos[(tNode *)cn] = (int)cells.size(); cells.push_back(cn); }
+    const int n = (int)cells.size();
+    auto col = [&](auto fn) { std::vector<double> v(n); for (int i = 0; i < n; i++) v[i] = fn(cells[i]); return v; };
+    auto icol = [&](auto fn) { std::vector<int32_t> v(n); for (int i = 0; i < n; i++) v[i] = fn(cells[i]); return v; };
+
+    // --- mesh
+    auto boundary = icol([](tCNode *c) { return c->getBoundaryFlag(); });
+    auto z = col([](tCNode *c) { return c->getZ(); });
+    auto varea = col([](tCNode *c) { return c->getVArea(); });
+    auto fslope = col([](tCNode *c) { return c->getFlowEdg()->getSlope(); });
+    auto fvl = col([](tCNode *c) { return c->getFlowEdg()->getVEdgLen(); });
+    auto fdest = icol([&](tCNode *c) { return idx(c->getFlowEdg()->getDestinationPtrNC()); });
+    auto snode = icol([&](tCNode *c) { return c->getStreamNode() ? idx((tNode *)c->getStreamNode()) : -1; });
+    auto hillpath = col([](tCNode *c) { return c->getHillPath(); });
+    auto streampath = col([](tCNode *c) { return c->getStreamPath(); });
+    auto carea = col([](tCNode *c) { return c->getContrArea(); });
+    auto ttime = col([](tCNode *c) { return c->getTTime(); });
+    auto reach = icol([](tCNode *c) { return c->getReach(); });
+    std::unordered_map<tEdge *, int> epos;
+    { tMeshListIter<tEdge> eit(mesh->getEdgeList()); int k = 0; for (tEdge *e = eit.FirstP(); eit.IsActive(); e = eit.NextP()) epos[e] = k++; }
+    std::vector<int32_t> rowptr(n + 1, 0), ncol, lpos;
+    std::vector<double> elen, evl, clen, cvl;
+    for (int i = 0; i < n; i++) {
+      tEdge *first = cells[i]->getEdg(), *e = first;
+      do {
+        ncol.push_back(idx(e->getDestinationPtrNC()));
+        elen.push_back(e->getLength()); evl.push_back(e->getVEdgLen());
+        auto ep = epos.find(e); lpos.push_back(ep == epos.end() ? -1 : ep->second);
+        tEdge *c = e->FindComplement();
+        clen.push_back(c ? c->getLength() : e->getLength()); cvl.push_back(c ? c->getVEdgLen() : e->getVEdgLen());
+        e = e->getCCWEdg();
+      } while (e != first);
+      rowptr[i + 1] = (int32_t)ncol.size();
+    }
+    tribs_mesh_t M{};
+    M.n_cells = n; M.n_edges = (int32_t)ncol.size();
+    M.boundary = boundary.data(); M.z = z.data(); M.varea = varea.data(); M.flow_slope = fslope.data();
+    M.flow_vedglen = fvl.data(); M.flow_dest = fdest.data(); M.stream_node = snode.data(); M.hillpath = hillpath.data();
+    M.streampath = streampath.data(); M.contr_area = carea.data(); M.ttime = ttime.data(); M.reach = reach.data();
+    M.nbr_rowptr = rowptr.data(); M.nbr_col = ncol.data(); M.nbr_len = elen.data(); M.nbr_vedglen = evl.data();
+    M.nbr_len_in = clen.data(); M.nbr_vedglen_in = cvl.data(); M.nbr_listpos = lpos.data();
+
+    // --- parameters (members of tHydroModel / tFlowNet / tKinemat / tRunTimer)
+    auto Ks = col([](tCNode *c) { return c->getKs(); }), ThS = col([](tCNode *c) { return c->getThetaS(); });
+    auto ThR = col([](tCNode *c) { return c->getThetaR(); }), Lam = col([](tCNode *c) { return c->getPoreSize(); });
+    auto Psib = col([](tCNode *c) { return c->getAirEBubPres(); }), F = col([](tCNode *c) { return c->getDecayF(); });
+    auto Ar = col([](tCNode *c) { return c->getSatAnRatio(); }), UAr = col([](tCNode *c) { return c->getUnsatAnRatio(); });
+    auto bedrock = col([](tCNode *c) { return c->getBedrockDepth(); });
+    tribs_params_t P{};
+    P.Ks = Ks.data(); P.ThetaS = ThS.data(); P.ThetaR = ThR.data(); P.PoreSize = Lam.data(); P.AirEBubPres = Psib.data();
+    P.DecayF = F.data(); P.SatAnRatio = Ar.data(); P.UnsatAnRatio = UAr.data(); P.bedrock = bedrock.data();
+    P.BasArea = hydro->BasArea; P.BasArea_flow = flow->BasArea; P.IntStormMAX = hydro->IntStormMAX;
+    P.surfaceSoilDepth = hydro->surfaceSoilDepth; P.rootZoneDepth = hydro->rootZoneDepth;
+    P.EToption = hydro->EToption; P.Ioption = hydro->Ioption; P.SnOpt = hydro->SnOpt; P.RdstrOption = hydro->RdstrOption;
+    P.velcoef = flow->velcoef; P.velratio = flow->velratio; P.flowexp = flow->flowexp; P.baseflow = flow->baseflow;
+    P.kincoef = flow->kincoef; P.dtReff = flow->dtReff; P.outlet_contr_area = flow->OutletNode->getContrArea();
+    P.tstep = timer->getTimeStep(); P.gwstep = timer->getGWTimeStep(); P.etistep = timer->getEtIStep();
+    P.output_interval = timer->getOutputInterval(); P.res_limit = flow->res->limit;
+
+    // --- initial state: whatever InitSet left in the nodes
+    stage.assign(TRIBS_N_FIELDS, std::vector<double>());
+    tribs_state_t S{};
+    auto put = [&](int f, std::vector<double> v) { stage[f] = std::move(v); S.f[f] = stage[f].data(); };
+    put(TRIBS_F_NwtOld, col([](tCNode *c) { return c->getNwtOld(); })); put(TRIBS_F_NwtNew, col([](tCNode *c) { return c->getNwtNew(); }));
+    put(TRIBS_F_MuOld, col([](tCNode *c) { return c->getMuOld(); }));   put(TRIBS_F_MuNew, col([](tCNode *c) { return c->getMuNew(); }));
+    put(TRIBS_F_MiOld, col([](tCNode *c) { return c->getMiOld(); }));   put(TRIBS_F_MiNew, col([](tCNode *c) { return c->getMiNew(); }));
+    put(TRIBS_F_NtOld, col([](tCNode *c) { return c->getNtOld(); }));   put(TRIBS_F_NtNew, col([](tCNode *c) { return c->getNtNew(); }));
+    put(TRIBS_F_NfOld, col([](tCNode *c) { return c->getNfOld(); }));   put(TRIBS_F_NfNew, col([](tCNode *c) { return c->getNfNew(); }));
+    put(TRIBS_F_RuOld, col([](tCNode *c) { return c->getRuOld(); }));   put(TRIBS_F_RuNew, col([](tCNode *c) { return c->getRuNew(); }));
+    put(TRIBS_F_RiOld, col([](tCNode *c) { return c->getRiOld(); }));   put(TRIBS_F_RiNew, col([](tCNode *c) { return c->getRiNew(); }));
+    put(TRIBS_F_SoilMoisture, col([](tCNode *c) { return c->getSoilMoisture(); }));
+    put(TRIBS_F_SoilMoistureSC, col([](tCNode *c) { return c->getSoilMoistureSC(); }));
+    put(TRIBS_F_SoilMoistureUNSC, col([](tCNode *c) { return c->getSoilMoistureUNSC(); }));
+    put(TRIBS_F_RootMoisture, col([](tCNode *c) { return c->getRootMoisture(); }));
+    put(TRIBS_F_RootMoistureSC, col([](tCNode *c) { return c->getRootMoistureSC(); }));
+    put(TRIBS_F_AvSoilMoisture, col([](tCNode *c) { return c->getAvSoilMoisture(); }));
+    put(TRIBS_F_TTime, ttime);
+    if (p_init(&M, &P, &S, nullptr, &h)) die("tribs_gpu_init");
+    for (auto &v : stage) v.assign(n, 0.0);
+    rain.assign(n, 0.0);
+  }
+
+  tribs_step_t flags() {
+    tribs_step_t s{};
+    s.current_time = timer->getCurrentTime();
+    s.dt = timer->getTimeStep();
+    s.dt_gw = timer->getGWTimeStep();
+    s.elapsed_steps = timer->getElapsedSteps(timer->getCurrentTime());
+    s.hourly_reset = !(fmod((timer->getCurrentTime() - timer->getTimeStep()), timer->getEtIStep()));   // tHydroModel.cpp:700
+    return s;
+  }
+  // tHydroModel::UnSaturatedZone(double dt)
+  void UnSaturatedZone(double) {
+    tribs_step_t s = flags();
+    for (size_t i = 0; i < cells.size(); i++) rain[i] = cells[i]->getRain();   // whatever tRainfall/tStorm wrote
+    s.rain_mode = TRIBS_RAIN_PER_CELL; s.rain = rain.data();
+    if (p_step(h, TRIBS_PHASE_UNSAT, &s)) die("UnSaturatedZone");
+  }
+  void ResetGW() {}   // folded into the SAT phase (a pointer swap on the device)
+  // tHydroModel::SaturatedZone(double dtGW)
+  void SaturatedZone(double) { tribs_step_t s = flags(); if (p_step(h, TRIBS_PHASE_SAT, &s)) die("SaturatedZone"); }
+  // tHydroModel::Reset()
+  void Reset() { tribs_step_t s = flags(); if (p_step(h, TRIBS_PHASE_RESET, &s)) die("Reset"); }
+
+  // the fields tKinemat / tFlowNet / tCOutput read each step
+  void syncToNodes() {
+    const int fields[] = {TRIBS_F_NwtNew, TRIBS_F_MuNew, TRIBS_F_MiNew, TRIBS_F_NtNew, TRIBS_F_NfNew, TRIBS_F_RuNew, TRIBS_F_RiNew,
+                          TRIBS_F_Qpin, TRIBS_F_Qpout, TRIBS_F_intstorm, TRIBS_F_srf, TRIBS_F_hsrf, TRIBS_F_sbsrf, TRIBS_F_psrf,
+                          TRIBS_F_satsrf, TRIBS_F_esrf, TRIBS_F_srf_hr, TRIBS_F_SoilMoisture, TRIBS_F_SoilMoistureSC,
+                          TRIBS_F_SoilMoistureUNSC, TRIBS_F_RootMoisture, TRIBS_F_RootMoistureSC, TRIBS_F_Recharge};
+    tribs_state_t S{};
+    uint64_t mask = 0;
+    for (int f : fields) { S.f[f] = stage[f].data(); mask |= TRIBS_MASK(f); }
+    if (p_sync(h, mask, &S)) die("tribs_gpu_sync");
+    for (size_t i = 0; i < cells.size(); i++) {
+      tCNode *c = cells[i];
+      c->setNwtNew(stage[TRIBS_F_NwtNew][i]); c->setMuNew(stage[TRIBS_F_MuNew][i]); c->setMiNew(stage[TRIBS_F_MiNew][i]);
+      c->setNtNew(stage[TRIBS_F_NtNew][i]); c->setNfNew(stage[TRIBS_F_NfNew][i]); c->setRuNew(stage[TRIBS_F_RuNew][i]);
+      c->setRiNew(stage[TRIBS_F_RiNew][i]); c->setQpin(stage[TRIBS_F_Qpin][i]); c->setQpout(stage[TRIBS_F_Qpout][i]);
+      c->setIntStormVar(stage[TRIBS_F_intstorm][i]); c->setsrf(stage[TRIBS_F_srf][i]); c->sethsrf(stage[TRIBS_F_hsrf][i]);
+      c->setsbsrf(stage[TRIBS_F_sbsrf][i]); c->setpsrf(stage[TRIBS_F_psrf][i]); c->setsatsrf(stage[TRIBS_F_satsrf][i]);
+      c->setesrf(stage[TRIBS_F_esrf][i]); c->setSrf_Hr(stage[TRIBS_F_srf_hr][i]);
+      c->setSoilMoisture(stage[TRIBS_F_SoilMoisture][i]); c->setSoilMoistureSC(stage[TRIBS_F_SoilMoistureSC][i]);
+      c->setSoilMoistureUNSC(stage[TRIBS_F_SoilMoistureUNSC][i]); c->setRootMoisture(stage[TRIBS_F_RootMoisture][i]);
+      c->setRootMoistureSC(stage[TRIBS_F_RootMoistureSC][i]); c->setRecharge(stage[TRIBS_F_Recharge][i]);
+    }
+  }
+  ~TribsGpuBinding() { if (h && p_destroy) p_destroy(h); }
+};

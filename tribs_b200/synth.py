@@ -116,7 +116,7 @@ def write_basin(spec: BasinSpec, outdir: str) -> str:
         ("SPOPINTRVL", 100000), ("INTSTORMMAX", spec.intstormmax), ("RAINSEARCH", 24),
         ("BASEFLOW", 0.01), ("VELOCITYCOEF", 0.5), ("KINEMVELCOEF", 0.1),
         ("VELOCITYRATIO", 5), ("FLOWEXP", 0.0), ("CHANNELROUGHNESS", 0.15),
-        ("CHANNELWIDTHCOEFF", 0), ("CHANNELWIDTH", 10), ("CHANNELWIDTHEXPNT", 0.3),
+        ("CHANNELWIDTHCOEFF", 1.0), ("CHANNELWIDTH", 10), ("CHANNELWIDTHEXPNT", 0.3),
         ("CHANNELWIDTHFILE", "none"), ("WIDTHINTERPOLATION", 0), ("OPTPERCOLATION", 0),
         ("TLINKE", 2.5), ("DEPTHTOBEDROCK", spec.bedrock_m),
         ("OPTMESHINPUT", spec.mesh_option), ("RAINSOURCE", 3), ("OPTEVAPOTRANS", 0),
