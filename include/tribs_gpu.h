@@ -112,7 +112,10 @@ enum {
   TRIBS_PHASE_UNSAT = 1,   /* UnSaturatedZone(dt) */
   TRIBS_PHASE_SAT   = 2,   /* ResetGW(); SaturatedZone(dt_gw) */
   TRIBS_PHASE_ROUTE = 4,   /* RunHydrologicRouting(); tFlowNet::SurfaceFlow() accumulations */
-  TRIBS_PHASE_RESET = 8    /* tHydroModel::Reset() */
+  TRIBS_PHASE_RESET = 8,   /* tHydroModel::Reset() */
+  /* partitioned handles: the sweep in two passes around the exchange of the river inflow */
+  TRIBS_PHASE_UNSAT_LOCAL = 16,  /* cells whose upslope inputs all live on this rank */
+  TRIBS_PHASE_UNSAT_REMOTE = 32  /* cells downstream of a cell owned by another rank */
 };
 
 enum { TRIBS_RAIN_KEEP = 0, TRIBS_RAIN_UNIFORM = 1, TRIBS_RAIN_PER_CELL = 2 };
@@ -182,6 +185,23 @@ int tribs_gpu_stream_cells(tribs_handle_t h, int32_t *sweep_index_out);
 /* tFlowResults arrays (`which` = TRIBS_R_*), `n` <= res_limit bins. */
 int tribs_gpu_get_results(tribs_handle_t h, int which, double *out, int n);
 int tribs_gpu_get_globals(tribs_handle_t h, double *out /* TRIBS_N_GLOBALS */);
+
+/* ---- partitioned runs: one reach partition per GPU (reference: tGraph, src/tGraph/tGraph.cpp:401-608,
+ * 1657-1724; the MPI messages sendQpin / sendOverlap / sendNwt become the three halo kinds below).
+ * Every rank is initialised with the WHOLE basin and then told which cells it owns
+ * (cell_owner[i] = rank of sweep cell i, from the reach partition). It advances only those; the
+ * host moves the values of boundary cells between ranks: pack on the owner, NCCL send/recv of the
+ * buffer, unpack on the reader. idx_dev / buf_dev are DEVICE pointers; idx holds device-order
+ * indices (tribs_gpu_device_index). Kinds: QPOUT = new lateral outflow of a reach outlet (1 value,
+ * unpack also marks it as published for the REMOTE pass of the sweep), STATE = the 7 New state
+ * values of cells that others read as their downslope cell, NWT = NwtNew of Voronoi neighbours
+ * across the cut (before a SAT phase). */
+enum { TRIBS_HALO_QPOUT = 0, TRIBS_HALO_STATE = 1, TRIBS_HALO_NWT = 2 };
+int tribs_gpu_set_partition(tribs_handle_t h, const int32_t *cell_owner, int rank);
+int tribs_gpu_halo_pack(tribs_handle_t h, int kind, const int32_t *idx_dev, int n, double *buf_dev);
+int tribs_gpu_halo_unpack(tribs_handle_t h, int kind, const int32_t *idx_dev, int n, const double *buf_dev);
+int tribs_gpu_set_global(tribs_handle_t h, int which, double value);   /* e.g. psrf_last from its owner */
+int tribs_gpu_padded_cells(tribs_handle_t h);
 
 /* Introspection used by tests and the bench. */
 int tribs_gpu_sweep_levels(tribs_handle_t h);            /* depth of the Qpin dependency DAG */

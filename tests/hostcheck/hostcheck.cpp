@@ -14,8 +14,10 @@ extern "C" {
 // sf order: varea z bedrock cosv sinv cos_gw vel_mm hillpath streampath contr_area ks ths thr lam psib f ar uar
 // si order: boundary flow_dest stream_node nbr_rowptr nbr_col nbr_listpos
 // ef order: nbr_len nbr_vedglen nbr_len_in nbr_vedglen_in
+static std::vector<int32_t> g_ones;
 static StaticView make_static(double **sf, int32_t **si, double **ef) {
   StaticView s;
+  s.owned = nullptr;   // single owner on the host: never read by the functions compiled here
   s.varea = sf[0]; s.z = sf[1]; s.bedrock = sf[2]; s.cosv = sf[3]; s.sinv = sf[4]; s.cos_gw = sf[5];
   s.vel_mm = sf[6]; s.hillpath = sf[7]; s.streampath = sf[8]; s.contr_area = sf[9];
   s.ks = sf[10]; s.ths = sf[11]; s.thr = sf[12]; s.lam = sf[13]; s.psib = sf[14]; s.f = sf[15];

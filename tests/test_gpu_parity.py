@@ -148,3 +148,19 @@ def test_gpu_batch_matches_live_reference_after_full_run(built):
         err = np.abs(ref - got[f]) / np.maximum(np.abs(ref), ABS_FLOOR)
         assert err.max() <= REL_TOL, (f, err.max())
     assert np.abs(snaps[pre + "mhydro"] - g.result("mhydro")).max() <= REL_TOL * max(1e-6, np.abs(snaps[pre + "mhydro"]).max())
+
+
+# ------------------------------------------------------------------ one reach partition per GPU
+@pytest.mark.parametrize("name,steps", [("deep", 200), ("shallow", 200)])
+def test_two_gpus_bitwise_equal_to_one(name, steps, built):
+    """The reference's own multi-rank contract (serial == MPI, test_big_spring.py:5-22)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs on the box")
+    from refrun import ROOT
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", f"{ROOT}/tests/mgpu_check.py", name, str(steps)],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "BITWISE EQUAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

@@ -16,6 +16,7 @@ namespace tribs {
 // static SoA, device order, length n_pad
 struct StaticView {
   const int32_t *boundary;     // 0 hillslope, 3 stream, -1 padding
+  const int32_t *owned;        // 1 = this rank computes the cell (all 1 on a single GPU)
   const int32_t *flow_dest;
   const int32_t *stream_node;
   const double *varea, *z, *bedrock;

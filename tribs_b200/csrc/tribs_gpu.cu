@@ -77,6 +77,10 @@ struct tribs_ctx {
   std::vector<void *> allocs;
   int32_t *d_up_rowptr = nullptr, *d_up_col = nullptr, *d_tile_counter = nullptr, *d_tile_order = nullptr;
   int32_t *d_tile_hi = nullptr;
+  // partitioned runs (one reach partition per GPU)
+  int32_t *d_owned = nullptr, *d_tiles_local = nullptr, *d_tiles_remote = nullptr;
+  int n_tiles_local = 0, n_tiles_remote = 0, rank = 0;
+  bool partitioned = false;
   int n_hi_tiles = 0;
   PubWord *d_pub = nullptr;
   int32_t *d_abort = nullptr, *d_sweep_of_dev = nullptr, *d_dev_of_sweep = nullptr;
@@ -165,7 +169,7 @@ unsat_sweep_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const int
     tile = tile_order[tile];   // levels in ascending order: inputs always belong to tiles claimed earlier
     const int i = tile * kTile + lane;
     UnsatSums sums{0.0, 0.0, 0.0, 0.0};
-    if (s.boundary[i] >= 0) {
+    if (s.boundary[i] >= 0 && s.owned[i]) {
       UnsatCellInputs u;
       unsat_cell_load(u, s, d, i, m, t);
       // lateral inflow: new Qpout of the upslope cells swept earlier, summed in sweep order
@@ -251,7 +255,7 @@ sat_cells_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const doubl
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   SatSums sums{0.0, 0.0, 0.0};
   t.psrf_last = globals[TRIBS_G_psrf_last];
-  if (i < n_pad && s.boundary[i] >= 0) {
+  if (i < n_pad && s.boundary[i] >= 0 && s.owned[i]) {
     int overflow = 0;
     double gw = sat_gather<MAXC>(s, d, i, wt_elev, transm, &overflow);
     if (overflow) flags[0] = 1;
@@ -321,7 +325,7 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
     const int bin = (int)ceil((now + tt) / dtreff);
     key = ((long long)slot << 32) | (unsigned)bin;
     const double srf = d.f[TRIBS_F_srf][seg_cell[e]];
-    if (srf > 0.0 && !(srf > 999999)) {
+    if (srf > 0.0 && !(srf > 999999) && s.owned[seg_cell[e]]) {
       double vr = srf * seg_area[e] / 1000.;
       v = (bin == cur) ? vr / same_box_div : vr / (dtreff * 3600.);
     }
@@ -457,7 +461,7 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
   for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
     const int i = chunk * blockDim.x + threadIdx.x;
     const int bnd = (i < n_pad) ? s.boundary[i] : -1;
-    const bool act = bnd >= 0;
+    const bool act = bnd >= 0 && s.owned[i];
     double vol[5] = {0, 0, 0, 0, 0};
     int init = 0, end = -1;
     double w_init = 0, w_mid = 0, w_end = 0;
@@ -642,10 +646,11 @@ static inline void swap_old_new(tribs_ctx *c) {
 extern "C" int tribs_gpu_abi_version(void) { return TRIBS_GPU_ABI_VERSION; }
 extern "C" const char *tribs_gpu_last_error(void) { return g_err.c_str(); }
 
+extern "C" int tribs_gpu_set_partition(tribs_handle_t c, const int32_t *cell_owner, int rank);
 extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *prm, const tribs_state_t *init,
                               const tribs_part_t *part, tribs_handle_t *out) {
   if (!mesh || !prm || !out) return fail("tribs_gpu_init: null argument");
-  if (part && part->nranks > 1) return fail("tribs_gpu_init: partitioned runs are not built yet");
+  if (part && part->nranks > 1 && !part->cell_owner) return fail("tribs_gpu_init: a partitioned init needs cell_owner");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("tribs_gpu_init: no CUDA device (this library has no CPU path)");
@@ -793,6 +798,12 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   }
 #define UPI(field, vec) { int32_t *p_; if (dev_upload(c, &p_, vec)) { return 1; } c->sv.field = p_; }
 #define UPD(field, vec) { double *p_; if (dev_upload(c, &p_, vec)) { return 1; } c->sv.field = p_; }
+  {
+    std::vector<int32_t> ones(n_pad, 0);
+    for (int i = 0; i < n; i++) ones[c->dev_of_sweep[i]] = 1;
+    if (dev_upload(c, &c->d_owned, ones)) return 1;
+    c->sv.owned = c->d_owned;
+  }
   UPI(boundary, bnd) UPI(flow_dest, fdest) UPI(stream_node, snode)
   UPD(cosv, cosv) UPD(sinv, sinv) UPD(cos_gw, cosgw) UPD(vel_mm, vel)
   UPD(varea, permute_d(mesh->varea, 1.0)) UPD(z, permute_d(mesh->z, 0.0)) UPD(bedrock, permute_d(prm->bedrock, 1.0))
@@ -969,6 +980,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     c->unsat_blocks = std::max(1, std::min(per_sm * prop.multiProcessorCount, needed));
   }
   CK(cudaDeviceSynchronize());
+  if (part && part->nranks > 1 && tribs_gpu_set_partition(c, part->cell_owner, part->rank)) return 1;
   *out = c;
   return 0;
 }
@@ -1010,23 +1022,43 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
   t.dt = s->dt; t.dt_gw = s->dt_gw; t.now = s->current_time; t.elapsed = (double)s->elapsed_steps;
   t.hourly_reset = s->hourly_reset; t.psrf_last = 0.0;
 
-  if (mask & TRIBS_PHASE_UNSAT) {
+  const bool sweep_local = mask & (TRIBS_PHASE_UNSAT | TRIBS_PHASE_UNSAT_LOCAL);
+  const bool sweep_remote = mask & (TRIBS_PHASE_UNSAT | TRIBS_PHASE_UNSAT_REMOTE);
+  if (sweep_local || sweep_remote) {
     PhaseTimer pt(c, 0);
-    c->epoch++;
-    CK(cudaMemsetAsync(c->d_tile_counter, 0, 4, st));
+    if (sweep_local) {
+      c->epoch++;
+      if (c->partitioned) CK(cudaMemsetAsync(c->d_tile_sums, 0, (size_t)4 * c->n_tiles * sizeof(double), st));
+    }
     long long epoch = c->epoch;
-    int n_tiles = c->n_tiles, last = c->last_sweep_dev;
-    void *args[] = {&c->sv, &c->dv, &c->mc, &t, &c->d_up_rowptr, &c->d_up_col, &c->d_pub, &epoch, &n_tiles,
-                    &c->d_tile_order, &c->d_tile_counter, &c->d_abort, &c->d_tile_sums, &c->d_globals, &last};
-    CK(cudaLaunchCooperativeKernel((void *)unsat_sweep_kernel, dim3(c->unsat_blocks), dim3(c->unsat_threads), args, 0, st));
-    c->launches++;
-    if (c->n_late > 0) {
-      unsat_late_qpin_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->dv, c->d_late_rowptr, c->d_late_col, n_pad);
+    int last = c->last_sweep_dev;
+    auto sweep = [&](int32_t *list, int count) -> int {
+      if (count <= 0) return 0;
+      CK(cudaMemsetAsync(c->d_tile_counter, 0, 4, st));
+      void *args[] = {&c->sv, &c->dv, &c->mc, &t, &c->d_up_rowptr, &c->d_up_col, &c->d_pub, &epoch, &count,
+                      &list, &c->d_tile_counter, &c->d_abort, &c->d_tile_sums, &c->d_globals, &last};
+      int blocks = std::max(1, std::min(c->unsat_blocks, (count + 3) / 4));
+      CK(cudaLaunchCooperativeKernel((void *)unsat_sweep_kernel, dim3(blocks), dim3(c->unsat_threads), args, 0, st));
+      c->launches++;
+      return 0;
+    };
+    if (!c->partitioned) {
+      if (sweep(c->d_tile_order, c->n_tiles)) return 1;
+    } else {
+      // pass "local": tiles whose inputs all live on this rank; pass "remote": tiles downstream of
+      // a cell another rank owns -- the host unpacks that rank's outflow between the two passes
+      if (sweep_local && sweep(c->d_tiles_local, c->n_tiles_local)) return 1;
+      if (sweep_remote && sweep(c->d_tiles_remote, c->n_tiles_remote)) return 1;
+    }
+    if (sweep_remote) {
+      if (c->n_late > 0) {
+        unsat_late_qpin_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->dv, c->d_late_rowptr, c->d_late_col, n_pad);
+        c->launches++;
+      }
+      reduce_sums_kernel<<<1, 256, 0, st>>>(c->d_tile_sums, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, TRIBS_G_TotRain,
+                                             TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
       c->launches++;
     }
-    reduce_sums_kernel<<<1, 256, 0, st>>>(c->d_tile_sums, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, TRIBS_G_TotRain,
-                                           TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
-    c->launches++;
     c->new_valid = true;
     c->at_boundary = false;
   }
@@ -1152,6 +1184,98 @@ extern "C" int tribs_gpu_get_globals(tribs_handle_t c, double *out) {
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
+
+
+// ------------------------------------------------------------------------------------ partitioned runs
+// One reach partition per GPU (reference: tGraph::partition, src/tGraph/tGraph.cpp:401-608). Every
+// rank holds the whole basin (topology and static data replicated) but advances only the cells it
+// owns; values of cells owned elsewhere are refreshed by the host through the halo pack/unpack
+// calls below and an NCCL exchange.
+extern "C" int tribs_gpu_set_partition(tribs_handle_t c, const int32_t *cell_owner, int rank) {
+  if (!c || !cell_owner) return fail("tribs_gpu_set_partition: null argument");
+  CK(cudaSetDevice(c->device));
+  const int n = c->n, n_pad = c->n_pad, nt = c->n_tiles;
+  std::vector<int32_t> owned(n_pad, 0);
+  for (int i = 0; i < n; i++) owned[c->dev_of_sweep[i]] = (cell_owner[i] == rank) ? 1 : 0;
+  std::vector<int32_t> h_up_rp(n_pad + 1);
+  CK(cudaMemcpy(h_up_rp.data(), c->d_up_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
+  std::vector<int32_t> h_up_col(h_up_rp[n_pad]), order(nt);
+  if (!h_up_col.empty()) CK(cudaMemcpy(h_up_col.data(), c->d_up_col, h_up_col.size() * 4, cudaMemcpyDeviceToHost));
+  CK(cudaMemcpy(order.data(), c->d_tile_order, nt * 4, cudaMemcpyDeviceToHost));
+  // a cell depends on another rank if an upslope contributor is not owned here, or depends itself
+  // (ascending device index is a topological order)
+  std::vector<uint8_t> dep(n_pad, 0);
+  for (int i = 0; i < n_pad; i++)
+    for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) {
+      const int j = h_up_col[k];
+      if (!owned[j] || dep[j]) { dep[i] = 1; break; }
+    }
+  std::vector<int32_t> local, remote;
+  for (int q = 0; q < nt; q++) {
+    const int t = order[q];
+    bool any = false, anydep = false;
+    for (int l = 0; l < kTile; l++) {
+      const int i = t * kTile + l;
+      if (owned[i]) { any = true; anydep = anydep || dep[i]; }
+    }
+    if (!any) continue;
+    (anydep ? remote : local).push_back(t);
+  }
+  CK(cudaMemcpy(c->d_owned, owned.data(), (size_t)n_pad * 4, cudaMemcpyHostToDevice));
+  if (dev_upload(c, &c->d_tiles_local, local) || dev_upload(c, &c->d_tiles_remote, remote)) return 1;
+  c->n_tiles_local = (int)local.size();
+  c->n_tiles_remote = (int)remote.size();
+  c->partitioned = true;
+  c->rank = rank;
+  return 0;
+}
+
+__global__ void halo_pack_kernel(DynView d, int kind, const int32_t *__restrict__ idx, int n, double *buf) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = idx[k];
+  if (kind == TRIBS_HALO_QPOUT) buf[k] = d.f[TRIBS_F_Qpout][i];
+  else if (kind == TRIBS_HALO_NWT) buf[k] = d.f[TRIBS_F_NwtNew][i];
+  else
+    for (int q = 0; q < 7; q++) buf[(size_t)q * n + k] = d.f[TRIBS_F_NwtNew + q][i];
+}
+__global__ void halo_unpack_kernel(DynView d, int kind, const int32_t *__restrict__ idx, int n, const double *buf,
+                                   PubWord *pub, long long epoch) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = idx[k];
+  if (kind == TRIBS_HALO_QPOUT) {
+    d.f[TRIBS_F_Qpout][i] = buf[k];
+    pub_store(pub + i, buf[k], epoch);   // the remote pass of the sweep reads it like a local outflow
+  } else if (kind == TRIBS_HALO_NWT) d.f[TRIBS_F_NwtNew][i] = buf[k];
+  else
+    for (int q = 0; q < 7; q++) d.f[TRIBS_F_NwtNew + q][i] = buf[(size_t)q * n + k];
+}
+extern "C" int tribs_gpu_halo_pack(tribs_handle_t c, int kind, const int32_t *idx_dev, int n, double *buf_dev) {
+  if (!c || (n > 0 && (!idx_dev || !buf_dev))) return fail("tribs_gpu_halo_pack: null argument");
+  CK(cudaSetDevice(c->device));
+  if (n > 0) { halo_pack_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->dv, kind, idx_dev, n, buf_dev); c->launches++; }
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int tribs_gpu_halo_unpack(tribs_handle_t c, int kind, const int32_t *idx_dev, int n, const double *buf_dev) {
+  if (!c || (n > 0 && (!idx_dev || !buf_dev))) return fail("tribs_gpu_halo_unpack: null argument");
+  CK(cudaSetDevice(c->device));
+  if (n > 0) {
+    halo_unpack_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(c->dv, kind, idx_dev, n, buf_dev, c->d_pub, c->epoch);
+    c->launches++;
+  }
+  CK(cudaGetLastError());
+  return 0;
+}
+extern "C" int tribs_gpu_set_global(tribs_handle_t c, int which, double value) {
+  if (!c || which < 0 || which >= TRIBS_N_GLOBALS) return fail("tribs_gpu_set_global: bad argument");
+  CK(cudaSetDevice(c->device));
+  CK(cudaMemcpyAsync(c->d_globals + which, &value, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+extern "C" int tribs_gpu_padded_cells(tribs_handle_t c) { return c ? c->n_pad : -1; }
 
 extern "C" int tribs_gpu_sweep_levels(tribs_handle_t c) { return c ? c->n_levels : -1; }
 extern "C" int tribs_gpu_device_index(tribs_handle_t c, int32_t *out) {
@@ -1329,7 +1453,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
     const int i = tile * kTile + lane;
     const long long tag = ph.tag;
     const DynView &d = (tag & 1) ? d_odd : d_even;   // Old = buffer tag%2, New = the other
-    const bool act = s.boundary[i] >= 0;
+    const bool act = s.boundary[i] >= 0 && s.owned[i];
     double sums[4] = {0.0, 0.0, 0.0, 0.0};
     UnsatCellInputs u;
     double qpin = 0.0;
@@ -1549,6 +1673,7 @@ static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
 extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks) {
   if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
   CK(cudaSetDevice(c->device));
+  if (c->partitioned) return fail("tribs_gpu_run: pipelined batches are not available on partitioned handles yet; use tribs_gpu_step");
   if (c->n_late > 0) return fail("tribs_gpu_run: the sweep order is not topological (late contributors); use tribs_gpu_step");
   if (c->rc.flowexp > 0.0 && n_steps > 1) return fail("tribs_gpu_run: flowexp > 0 needs the channel router between steps; use tribs_gpu_step");
   const uint32_t need = TRIBS_PHASE_UNSAT | TRIBS_PHASE_ROUTE | TRIBS_PHASE_RESET;
