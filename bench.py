@@ -96,15 +96,28 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     side = args.side
-    basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9)
-    n = int(basin["n_active"][0])
-    sim = Simulator(basin, rain_schedule=None)
-    dev = sim.dev
+    partitioned = world > 1 and args.mgpu == "partition"
+    if partitioned:
+        # ONE basin over all GPUs: a valley `world` times as long, cut into reach partitions along the
+        # river; every rank holds the static data of the whole basin and advances the cells it owns
+        from tribs_b200.parallel import PartitionedSimulator
+        side = args.side_mgpu
+        basin = build_basin(side, side * world, seed=1, runtime_h=1e9)
+        psim = PartitionedSimulator(basin, rank, world, rain_schedule=storm_rain)
+        dev = psim.dev
+        n = int((psim.owner == rank).sum())
+        sim = None
+    else:
+        basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9)
+        n = int(basin["n_active"][0])
+        sim = Simulator(basin, rain_schedule=None)
+        dev = sim.dev
     gw_every = int(round(dev.gwstep / dev.tstep))
     stream = torch.cuda.ExternalStream(dev.stream_handle())
     n_stream = dev.n_stream
+    n_host = dev.n      # cells in the arrays the host exchanges with this rank
 
-    pinned_rain = torch.empty(n, dtype=torch.float64).pin_memory()
+    pinned_rain = torch.empty(n_host, dtype=torch.float64).pin_memory()
     rain_np = pinned_rain.numpy()
 
     def barrier():
@@ -114,6 +127,9 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     def resident_step():
+        if partitioned:
+            psim.one_step()
+            return
         sim.advance()
         t = sim.timer.getCurrentTime()
         dev.step(0, t, sim.timer.getElapsedSteps(t), 0, rain=storm_rain(t))   # tRainfall::NewRain(double)
@@ -122,6 +138,8 @@ def run_gpu(args):
         sim.hydro.Reset()
 
     def e2e_step():
+        if partitioned:
+            return psim.one_step(rain_cells=rain_np, fetch=True)
         sim.advance()
         t = sim.timer.getCurrentTime()
         rain_np.fill(storm_rain(t))            # the host model's per-cell rain (tRainfall::NewRain)
@@ -132,8 +150,8 @@ def run_gpu(args):
         sim.hydro.Reset()
         return g
 
-    B = max(1, args.batch)
-    pinned_rows = torch.empty((B, n), dtype=torch.float64).pin_memory() if B > 1 else None
+    B = 1 if partitioned else max(1, args.batch)   # pipelined batches are single-GPU for now
+    pinned_rows = torch.empty((B, n_host), dtype=torch.float64).pin_memory() if B > 1 else None
 
     def host_steps(k, rows=None):
         t = sim.timer
@@ -214,7 +232,12 @@ def run_gpu(args):
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         e2e_ms = float(tt.item())
 
-    total_cells = n * world
+    if world > 1:   # cells advanced by all ranks together
+        tt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tt)
+        total_cells = int(tt.item())
+    else:
+        total_cells = n
     value = total_cells * args.steps / (ms * 1e-3)
     e2e = total_cells * args.steps / (e2e_ms * 1e-3)
     peak, peak_kind = peaks()
@@ -223,13 +246,16 @@ def run_gpu(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {n / 1e6:.2f}M-cell V-valley TIN per GPU, uniform storm 20 mm/h, "
+        "config": {"workload": f"synthetic {total_cells / world / 1e6:.2f}M-cell V-valley TIN per GPU, uniform storm 20 mm/h, "
                                f"TIMESTEP 3.75 min, GWSTEP 30 min (sat zone every {gw_every}th step), ET/snow off",
                    "cells_per_gpu": n, "stream_cells_per_gpu": n_stream, "sweep_levels": dev.levels(),
                    "l2": "state arrays (52 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
                    "batch_steps": B,
-                   "parallelism": "1 GPU" if world == 1 else f"{world} independent basin replicas (no halo exchange yet)"},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n,
+                   "parallelism": "1 GPU" if world == 1 else (
+                       f"one basin of {total_cells} cells, {world} reach partitions along the river, NCCL halo exchange "
+                       "every step (river inflow, water-table and downslope-state halos), single-step path" if partitioned
+                       else f"{world} independent basin replicas, no exchange")},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_host,
                 "d2h_bytes_per_step": 8 * (n_stream + 1) + 8 * len(gpu.GLOBALS)},
         "gpu_launches": int(launches),
         "clocks": clocks,
@@ -360,6 +386,10 @@ def main():
     ap.add_argument("--side", type=int, default=1000, help="cells per side of the synthetic basin (per GPU)")
     ap.add_argument("--batch", type=int, default=64,
                     help="steps per pipelined launch (tribs_gpu_run); 1 = one tribs_gpu_step sequence per step")
+    ap.add_argument("--mgpu", default="partition", choices=["partition", "replicas"],
+                    help="N>1: one reach-partitioned basin with halo exchange (default) or independent replicas")
+    ap.add_argument("--side-mgpu", type=int, default=500, help="N>1, partition mode: cells across the valley; "
+                    "the basin is side x side*N cells, i.e. side^2 per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -93,13 +93,18 @@ class PartitionedSimulator:
         for peer in sorted(self.plan[what + "_recv"]):
             self._unpack(what + "_recv", peer)
 
-    def one_step(self):
+    def one_step(self, rain_cells=None, fetch=False):
+        """rain_cells: optional host array [n] (per-cell rain of this step, sweep order);
+        fetch=True also reads back what the host model consumes each step."""
         t, dev, dist = self.timer, self.dev, self.dist
         t.Advance(t.getTimeStep())
         now = t.getCurrentTime()
         el = t.getElapsedSteps(now)
         hr = int(not math.fmod(now - t.getTimeStep(), t.etistep))
         rain = self.rain_schedule(now) if self.rain_schedule is not None else None
+        if rain_cells is not None:
+            rain_cells.fill(0.0 if rain is None else rain)
+            rain = rain_cells
         dev.step(16, now, el, hr, rain=rain)                          # TRIBS_PHASE_UNSAT_LOCAL
         for peer in sorted(self.plan["qpout_recv"]):                   # ranks upstream of me
             dist.recv(self.buf[("qpout_recv", peer)], src=peer)
@@ -117,9 +122,10 @@ class PartitionedSimulator:
             gpu._chk(dev.L.tribs_gpu_set_global(dev.h, gpu.GLOBALS.index("psrf_last"), float(v.item())))
             dev.step(gpu.PHASE_SAT, now, el, hr)
         dev.step(gpu.PHASE_ROUTE, now, el, 0)
+        out = (dev.retrieve_qeff(now), dev.globals()) if fetch else None
         self._exchange_both_ways("state")
         dev.step(gpu.PHASE_RESET, now, el, hr)
-        return did_gw
+        return out if fetch else did_gw
 
     def gather(self, names):
         """Owned values of the requested fields from every rank, assembled on every rank."""
