@@ -510,6 +510,7 @@ int main(int argc, char **argv) {
     string phases = "ugre";
     bool do_kat = false, do_basin = true;
     string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
+    double inject_evap = 0.0;   // --inject-evap R: soil evaporation R mm/h on dry steps (see below)
     vector<char*> rargs;
     for (int i = 0; i < argc; i++) {
         string a = argv[i];
@@ -520,6 +521,7 @@ int main(int argc, char **argv) {
         else if (a == "--phases" && i + 1 < argc) phases = argv[++i];
         else if (a == "--kat") do_kat = true;
         else if (a == "--gpu" && i + 1 < argc) gpu_lib = argv[++i];
+        else if (a == "--inject-evap" && i + 1 < argc) inject_evap = atof(argv[++i]);
         else if (a == "--no-basin") do_basin = false;
         else rargs.push_back(argv[i]);
     }
@@ -548,6 +550,12 @@ int main(int argc, char **argv) {
     Sim.initialize_simulation(&EvapoTrans, &SnowPack, InputFile);
     double t_setup1 = now_s();
 
+    // Net evaporation without the ET module: the unsaturated zone only sees ET through the node
+    // fields EvapSoil / EvapDryCanopy (tHydroModel.cpp:795-809). Switching its EToption on and
+    // writing EvapSoil here drives the reference's own code into the states that need R1 < 0
+    // (WTDropsFromSurf, IntStormBelow) with a forcing that is trivial to reproduce elsewhere.
+    if (inject_evap > 0.0) Moisture.EToption = 1;
+
     Harness H;
     H.mesh = &BasinMesh; H.flow = &Flow; H.hydro = &Moisture; H.timer = &Timer;
     H.index();
@@ -574,6 +582,8 @@ int main(int argc, char **argv) {
         Timer.Advance(Timer.getTimeStep());
         Sim.UpdatePrecipitationInput(Rainfall.getoptStorm());
         Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
+        if (inject_evap > 0.0)
+            for (tCNode *cn : H.cells) cn->setEvapSoil(cn->getRain() > 0.0 ? 0.0 : inject_evap);
         double t1 = now_s();
         // SubSurfaceHydroProcesses, split so the state between the two zones is observable
         if (use_gpu) gpu.UnSaturatedZone(Timer.getTimeStep());

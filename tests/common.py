@@ -5,7 +5,7 @@ import math
 
 import numpy as np
 
-from refrun import rel_err
+from refrun import evap_of, rel_err
 
 STATE_FIELDS = ["NwtNew", "MuNew", "MiNew", "NtNew", "NfNew", "RuNew", "RiNew", "Qpin", "Qpout", "intstorm",
                 "srf", "hsrf", "sbsrf", "psrf", "esrf", "srf_hr", "cumsrf", "SoilMoisture", "SoilMoistureSC",
@@ -27,6 +27,7 @@ class GpuStepper:
         self.boundary = np.asarray(basin["boundary"])
         self.stream_cells = self.sim.dev.stream_cells()
         self.limit = int(basin["res_limit"][0])
+        self.evap, self._evap_now = evap_of(basin), None
 
     @property
     def time(self):
@@ -35,6 +36,12 @@ class GpuStepper:
     def advance(self):
         self.sim.advance()
         self.sim.UpdatePrecipitationInput()
+        if self.evap > 0.0:   # the harness's injected soil evaporation: EvapSoil = rate on dry steps
+            r = self.sim.rain_schedule(self.time)
+            want = 0.0 if r > 0.0 else self.evap
+            if want != self._evap_now:
+                self.sim.dev.push({"EvapSoil": np.full(self.n, want)})
+                self._evap_now = want
 
     def unsat(self):
         self.sim.hydro.UnSaturatedZone(self.sim.timer.getTimeStep())
@@ -71,6 +78,7 @@ class OracleStepper:
         self.n = self.m.n
         self.boundary = np.asarray(basin["boundary"])
         self.stream_cells = np.nonzero(self.boundary == 3)[0].astype(np.int32)
+        self.evap = evap_of(basin)
 
     @property
     def time(self):
@@ -78,6 +86,8 @@ class OracleStepper:
 
     def advance(self):
         self.m.advance()
+        if self.evap > 0.0:
+            self.m.state["EvapSoil"][:] = np.where(self.m.state["Rain"] > 0.0, 0.0, self.evap)
 
     def unsat(self):
         self.m.unsat()

@@ -29,6 +29,9 @@ SCENARIOS = {
     "shallow": dict(runtime_h=48.0, gw_depth_mm=400.0, pmean=30.0),
     # short storm, short INTSTORMMAX: wedge destruction / redistribution, Storm_Evol
     "redistribute": dict(runtime_h=60.0, intstormmax=8.0, stdur=3.0, istdur=12.0, gw_depth_mm=1500.0),
+    # net evaporation on dry steps (injected into tCNode::EvapSoil by the harness, EToption on):
+    # water table dropping from the surface, interstorm drying below the initial profile
+    "evap": dict(runtime_h=72.0, gw_depth_mm=350.0, pmean=25.0, stdur=4.0, istdur=20.0, inject_evap=0.6),
 }
 
 
@@ -52,6 +55,8 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
            "--snap-every", str(snap_every), "--phases", phases]
     if kat:
         cmd.append("--kat")
+    if spec.inject_evap > 0.0:
+        cmd += ["--inject-evap", repr(spec.inject_evap)]
     r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=timeout)
     if r.returncode != 0:
         raise RuntimeError("reference harness failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
@@ -64,6 +69,7 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
     basin["_spec_pmean"] = np.array([spec.pmean])
     basin["_spec_stdur"] = np.array([spec.stdur])
     basin["_spec_istdur"] = np.array([spec.istdur])
+    basin["_spec_evap"] = np.array([spec.inject_evap])
     if own:
         import shutil
         shutil.rmtree(d, ignore_errors=True)
@@ -72,6 +78,10 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
 
 def storm_of(basin):
     return float(basin["_spec_pmean"][0]), float(basin["_spec_stdur"][0]), float(basin["_spec_istdur"][0])
+
+
+def evap_of(basin) -> float:
+    return float(basin["_spec_evap"][0]) if "_spec_evap" in basin else 0.0
 
 
 def load_golden(name: str):

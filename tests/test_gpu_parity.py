@@ -32,7 +32,7 @@ def test_gpu_matches_reference_golden(name, built):
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
-@pytest.mark.parametrize("name,n,hours", [("deep", 40, 30.0), ("shallow", 32, 30.0), ("redistribute", 32, 40.0)])
+@pytest.mark.parametrize("name,n,hours", [("deep", 40, 30.0), ("shallow", 32, 30.0), ("redistribute", 32, 40.0), ("evap", 32, 40.0)])
 def test_gpu_matches_live_reference(name, n, hours, built):
     """Larger basins: the reference binary itself runs on the box's CPU and is compared with."""
     spec = spec_for(name, n, runtime_h=hours, seed=3)

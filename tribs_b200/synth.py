@@ -47,6 +47,7 @@ class BasinSpec:
     land: tuple = (0.5, 0.2, 0.5, 1.0, 0.1, 3.7, 0.2, 1.0, 0.8, 100.0, 0.5, 2.0, 0.3, 0.25)
     opt_spatial: int = 0
     opt_interhydro: int = 0
+    inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
     extra: dict = field(default_factory=dict)   # keyword overrides
 
 
