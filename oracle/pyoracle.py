@@ -66,7 +66,9 @@ class Results(C.Structure):
 
 
 def build(force: bool = False) -> str:
-    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < os.path.getmtime(os.path.join(HERE, "tribs_oracle.c")):
+    newest = max(os.path.getmtime(os.path.join(HERE, f)) for f in
+                 ("tribs_oracle.c", "tribs_oracle.h", "tribs_oracle_et.c", "tribs_oracle_et.h"))
+    if force or not os.path.exists(LIB) or os.path.getmtime(LIB) < newest:
         subprocess.check_call(["make", "-C", HERE, "port"], stdout=subprocess.DEVNULL)
     return LIB
 
@@ -232,6 +234,101 @@ class OracleModel:
     def stack_of(self, i):
         st = self.stacks[i]
         return ([st.tind[k] for k in range(st.n)], [st.q[k] for k in range(st.n)])
+
+
+# ------------------------------------------------------------------ ET / interception sweeps
+def _xlist_et() -> list[str]:
+    src = open(os.path.join(HERE, "tribs_oracle_et.h")).read()
+    m = re.search(r"#define\s+ORC_ET_FIELDS\(X\)\s*\\?\n?((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
+ET_FIELDS = _xlist_et()
+
+
+class EtBasin(C.Structure):
+    _fields_ = [("n", C.c_int32)] + [(k, PD) for k in (
+        "z", "flow_slope", "aspect", "ThetaS", "ThetaR", "VolHeatCond", "SoilHeatCap", "soil_cutoff",
+        "root_cutoff", "bedrock")] + [
+        ("land_class", PI), ("land_table", PD),
+        ("et_option", C.c_int32), ("i_option", C.c_int32), ("gflux_option", C.c_int32), ("shelter_option", C.c_int32),
+        ("metstep_min", C.c_double), ("etistep_h", C.c_double), ("tlinke", C.c_double), ("temp_lapse", C.c_double),
+        ("max_interstorm", C.c_double)]
+
+
+class Met(C.Structure):
+    _fields_ = [("n_records", C.c_int32), ("cell_record", PI)] + [(k, PD) for k in (
+        "air_temp", "dew_temp", "rel_humid", "vap_press", "atm_press", "wind_speed", "sky_cover", "rad_global", "elev")]
+
+
+class EtStep(C.Structure):
+    _fields_ = [("alphaD", C.c_double), ("sinAlpha", C.c_double), ("sunaz", C.c_double), ("Io", C.c_double),
+                ("hour", C.c_int32), ("first_call", C.c_int32), ("dew_hum_flag", C.c_int32), ("ts_option", C.c_int32),
+                ("sky_flag_from", C.c_int32), ("te_met", C.c_double), ("te_eti", C.c_double)]
+
+
+class EtShared(C.Structure):
+    _fields_ = [(k, PD) for k in ("Rain", "NetPrecipitation", "EvapSoil", "EvapDryCanopy", "SoilMoisture", "RootMoisture")]
+
+
+_MET_KEYS = (("air_temp", "airTemp"), ("dew_temp", "dewTemp"), ("rel_humid", "rHumidity"), ("vap_press", "vPress"),
+             ("atm_press", "atmPress"), ("wind_speed", "windSpeed"), ("sky_cover", "skyCover"), ("rad_global", "radGlobal"))
+
+
+class OracleET:
+    """tEvapoTrans / tIntercept cell loops of the C oracle, sharing the arrays of an OracleModel."""
+
+    def __init__(self, basin: dict, model: OracleModel, host):
+        self.L = lib()
+        self.L.orc_et_potential.argtypes = [C.POINTER(EtBasin), C.POINTER(EtStep), C.POINTER(Met),
+                                            C.POINTER(PD), C.POINTER(EtShared)]
+        self.L.orc_et_components.argtypes = [C.POINTER(EtBasin), C.POINTER(EtStep), C.POINTER(Met),
+                                             C.POINTER(PD), C.POINTER(EtShared), C.c_int]
+        assert self.L.orc_et_n_fields() == len(ET_FIELDS)
+        b, n = basin, model.n
+        self.host, self.model, self.keep = host, model, {}
+        B = EtBasin()
+        B.n = n
+        for dst, src in (("z", "z"), ("flow_slope", "flow_slope"), ("aspect", "aspect"), ("ThetaS", "ThetaS"),
+                         ("ThetaR", "ThetaR"), ("VolHeatCond", "VolHeatCond"), ("SoilHeatCap", "SoilHeatCap"),
+                         ("soil_cutoff", "soil_cutoff"), ("root_cutoff", "root_cutoff"), ("bedrock", "bedrock")):
+            a = np.ascontiguousarray(b[src], np.float64); self.keep[dst] = a; setattr(B, dst, _pd(a))
+        lc = np.ascontiguousarray(b["land_class"], np.int32); self.keep["lc"] = lc; B.land_class = _pi(lc)
+        lt = np.ascontiguousarray(b["land_table"], np.float64); self.keep["lt"] = lt; B.land_table = _pd(lt)
+        B.et_option = int(b["et_option"][0]); B.i_option = int(b["et_Ioption"][0])
+        B.gflux_option = int(b["et_gFluxOption"][0]); B.shelter_option = int(b["et_shelterOption"][0])
+        B.metstep_min = float(b["et_timeStep"][0]); B.etistep_h = float(b["etistep"][0])
+        B.tlinke = float(b["et_Tlinke"][0]); B.temp_lapse = float(b["et_tempLapseRate"][0])
+        B.max_interstorm = float(b["icp_maxInterStormPeriod"][0])
+        self.B = B
+        self.f = {nm: np.array(b["init_" + nm], np.float64) if "init_" + nm in b else np.zeros(n) for nm in ET_FIELDS}
+        self.fp = (PD * len(ET_FIELDS))(*[_pd(self.f[nm]) for nm in ET_FIELDS])
+        sh = EtShared()
+        for k, _ in EtShared._fields_:
+            setattr(sh, k, _pd(model.state[k]))
+        self.sh = sh
+        self.flag = int(B.i_option != 0)
+
+    def _args(self, step: dict, rec: dict):
+        s = EtStep(**step)
+        m = Met()
+        m.n_records = self.host.ns
+        cr = self.host.cell_record; m.cell_record = _pi(cr)
+        keep = [cr]
+        for dst, src in _MET_KEYS:
+            a = np.ascontiguousarray(rec[src], np.float64); keep.append(a); setattr(m, dst, _pd(a))
+        el = np.ascontiguousarray(self.host.elev, np.float64); keep.append(el); m.elev = _pd(el)
+        return s, m, keep
+
+    def potential(self, step, rec):
+        s, m, keep = self._args(step, rec)
+        rc = self.L.orc_et_potential(C.byref(self.B), C.byref(s), C.byref(m), self.fp, C.byref(self.sh))
+        assert rc == 0, "option set not covered by the oracle"
+
+    def components(self, step, rec):
+        s, m, keep = self._args(step, rec)
+        rc = self.L.orc_et_components(C.byref(self.B), C.byref(s), C.byref(m), self.fp, C.byref(self.sh), self.flag)
+        assert rc == 0
 
 
 def stochastic_storm_schedule(pmean: float, stdur: float, istdur: float):

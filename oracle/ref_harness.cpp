@@ -94,6 +94,9 @@ struct Harness {
     tKinemat *flow;
     tHydroModel *hydro;
     tRunTimer *timer;
+    tEvapoTrans *et = nullptr;
+    tIntercept *icp = nullptr;
+    tRainfall *rainfall = nullptr;
     vector<tCNode*> cells;                    // active cells in list (sweep) order
     unordered_map<tNode*, int> pos;           // node -> index in cells
 
@@ -278,7 +281,151 @@ struct Harness {
         w.f64s("etistep", timer->getEtIStep());
         w.f64s("endtime", timer->getEndTime());
         w.f64s("output_interval", timer->getOutputInterval());
+        dump_et_setup(w);
         dump_state(w, "init_", true);
+        dump_et(w, "init_");
+    }
+
+    // -------------------------------------------------------------- ET / interception set-up
+    // What tEvapoTrans / tIntercept read per cell or hold as members (tEvapoTrans.cpp:215-253,
+    // 915-952, 3122-3330; tIntercept.cpp:44-45, 468-484): land classes, options, the weather
+    // stations' hourly records and the Thiessen assignment of cells to stations.
+    void dump_et_setup(TrbWriter &w) {
+        w.i32s("et_option", et->evapotransOption);
+        w.i32s("et_Ioption", et->Ioption);
+        w.i32s("et_metdataOption", et->metdataOption);
+        w.i32s("et_gFluxOption", et->gFluxOption);
+        w.i32s("et_luOption", et->luOption);
+        w.i32s("et_snowOption", et->snowOption);
+        w.i32s("et_shelterOption", et->shelterOption);
+        w.f64s("et_timeStep", et->timeStep);
+        w.f64s("et_Tlinke", et->Tlinke);
+        w.f64s("et_tempLapseRate", et->tempLapseRate);
+        w.f64s("icp_maxInterStormPeriod", icp->maxInterStormPeriod);
+        w.i32s("icp_option", icp->interceptOption);
+        vector<int32_t> lu(cells.size());
+        int maxc = 0;
+        for (size_t i = 0; i < cells.size(); i++) { lu[i] = cells[i]->getLandUse(); maxc = std::max(maxc, (int)lu[i]); }
+        w.i32("land_class", lu);
+        vector<double> table((size_t)(maxc + 1) * 15, 0.0);
+        vector<char> seen(maxc + 1, 0);
+        for (size_t i = 0; i < cells.size(); i++) {
+            int c = lu[i];
+            if (c < 0 || seen[c]) continue;
+            seen[c] = 1;
+            hydro->landPtr->setLandPtr(c);
+            for (int k = 1; k <= 14; k++) table[(size_t)c * 15 + k] = hydro->landPtr->getLandProp(k);
+        }
+        w.f64("land_table", table);     // row = class id, column k = getLandProp(k), k = 1..14
+        w.i32s("rain_type", rainfall->rainfallType);
+        w.i32s("rain_optStorm", rainfall->getoptStorm());
+        if (!rainfall->getoptStorm() && rainfall->rainfallType == 3) {   // gauges, tRainfall.cpp:463-503
+            rainfall->assignStationToNode();   // what NewRainData does before every use (tRainfall.cpp:470)
+            int ng = rainfall->numStations, T = rainfall->rainGauges[0].getTime();
+            vector<int32_t> gid(ng), asg(cells.size());
+            vector<double> gel(ng), ser((size_t)ng * T);
+            for (int k = 0; k < ng; k++) {
+                gid[k] = rainfall->rainGauges[k].getStation(); gel[k] = rainfall->rainGauges[k].getElev();
+                for (int t = 0; t < T; t++) ser[(size_t)k * T + t] = rainfall->rainGauges[k].getRain(t);
+            }
+            for (size_t i = 0; i < cells.size(); i++) asg[i] = rainfall->assignedRain[i];
+            w.i32("rain_gauge_id", gid); w.f64("rain_gauge_elev", gel); w.f64("rain_series", ser);
+            w.i32("rain_assigned_gauge", asg); w.i32s("rain_n_times", T);
+            w.f64s("rain_precLapseRate", rainfall->precLapseRate);
+            w.f64s("rain_dt", timer->getRainDT());
+        }
+        if (et->evapotransOption == 0 || et->metdataOption != 1 || et->weatherStations == nullptr) return;
+        int ns = et->numStations;
+        w.i32s("met_n_stations", ns);
+        vector<int32_t> sid(ns), gmt(ns), nt(ns), np(ns);
+        vector<double> lat(ns), lon(ns), oth(ns);
+        for (int k = 0; k < ns; k++) {
+            tHydroMet &st = et->weatherStations[k];
+            sid[k] = st.getStation(); gmt[k] = st.getGmt(); nt[k] = st.getTime(); np[k] = st.getParm();
+            lat[k] = st.getLat(1); lon[k] = st.getLong(1); oth[k] = st.getOther();
+        }
+        w.i32("met_station_id", sid); w.i32("met_gmt", gmt); w.i32("met_n_times", nt); w.i32("met_n_params", np);
+        w.f64("met_lat", lat); w.f64("met_long", lon); w.f64("met_other", oth);
+        int T = nt[0];
+        auto series = [&](const char *name, double (tHydroMet::*get)(int)) {
+            vector<double> v((size_t)ns * T);
+            for (int k = 0; k < ns; k++) for (int t = 0; t < T; t++) v[(size_t)k * T + t] = (et->weatherStations[k].*get)(t);
+            w.f64(name, v);
+        };
+        series("met_airTemp", &tHydroMet::getAirTemp);
+        series("met_dewTemp", &tHydroMet::getDewTemp);
+        series("met_surfTemp", &tHydroMet::getSurfTemp);
+        series("met_rHumidity", &tHydroMet::getRHumidity);
+        series("met_vPress", &tHydroMet::getVaporPress);
+        series("met_atmPress", &tHydroMet::getAtmPress);
+        series("met_windSpeed", &tHydroMet::getWindSpeed);
+        series("met_skyCover", &tHydroMet::getSkyCover);
+        series("met_radGlobal", &tHydroMet::getRadGlobal);
+        vector<int32_t> cal((size_t)T * 4);
+        for (int t = 0; t < T; t++) {
+            tHydroMet &st = et->weatherStations[0];
+            cal[t * 4 + 0] = st.getYear(t); cal[t * 4 + 1] = st.getMonth(t);
+            cal[t * 4 + 2] = st.getDay(t); cal[t * 4 + 3] = st.getHour(t);
+        }
+        w.i32("met_calendar", cal);
+        vector<int32_t> as(cells.size());
+        for (size_t i = 0; i < cells.size(); i++) as[i] = et->assignedStation[i];
+        w.i32("met_assigned_station", as);
+        w.i32s("met_tsOption", et->tsOption);
+        w.i32s("met_vapOption", et->vapOption);
+        vector<int32_t> start = {timer->year, timer->month, timer->day, timer->hour, timer->minute};
+        w.i32("timer_start", start);
+    }
+
+    // per-cell outputs of tEvapoTrans::callEvapoPotential / callEvapoTrans and tIntercept, plus
+    // the members the host-side mirror has to reproduce (sun geometry, met clock)
+    void dump_et(TrbWriter &w, const string &pre) {
+        if (!et || et->evapotransOption == 0) return;
+        w.f64(pre + "PotEvap", col([](tCNode *c) { return c->getPotEvap(); }));
+        w.f64(pre + "ActEvap", col([](tCNode *c) { return c->getActEvap(); }));
+        w.f64(pre + "SurfTemp", col([](tCNode *c) { return c->getSurfTemp(); }));
+        w.f64(pre + "SoilTemp", col([](tCNode *c) { return c->getSoilTemp(); }));
+        w.f64(pre + "NetRad", col([](tCNode *c) { return c->getNetRad(); }));
+        w.f64(pre + "GFlux", col([](tCNode *c) { return c->getGFlux(); }));
+        w.f64(pre + "HFlux", col([](tCNode *c) { return c->getHFlux(); }));
+        w.f64(pre + "LFlux", col([](tCNode *c) { return c->getLFlux(); }));
+        w.f64(pre + "LongRadIn", col([](tCNode *c) { return c->getLongRadIn(); }));
+        w.f64(pre + "LongRadOut", col([](tCNode *c) { return c->getLongRadOut(); }));
+        w.f64(pre + "ShortRadIn", col([](tCNode *c) { return c->getShortRadIn(); }));
+        w.f64(pre + "ShortRadIn_dir", col([](tCNode *c) { return c->getShortRadIn_dir(); }));
+        w.f64(pre + "ShortRadIn_dif", col([](tCNode *c) { return c->getShortRadIn_dif(); }));
+        w.f64(pre + "ShortRadSlope", col([](tCNode *c) { return c->getShortRadSlope(); }));
+        w.f64(pre + "ShortAbsbVeg", col([](tCNode *c) { return c->getShortAbsbVeg(); }));
+        w.f64(pre + "ShortAbsbSoi", col([](tCNode *c) { return c->getShortAbsbSoi(); }));
+        w.f64(pre + "AirTemp", col([](tCNode *c) { return c->getAirTemp(); }));
+        w.f64(pre + "DewTemp", col([](tCNode *c) { return c->getDewTemp(); }));
+        w.f64(pre + "RelHumid", col([](tCNode *c) { return c->getRelHumid(); }));
+        w.f64(pre + "VapPressure", col([](tCNode *c) { return c->getVapPressure(); }));
+        w.f64(pre + "SkyCover", col([](tCNode *c) { return c->getSkyCover(); }));
+        w.f64(pre + "WindSpeed", col([](tCNode *c) { return c->getWindSpeed(); }));
+        w.f64(pre + "AirPressure", col([](tCNode *c) { return c->getAirPressure(); }));
+        w.f64(pre + "CumHrsSun", col([](tCNode *c) { return c->getCumHrsSun(); }));
+        w.f64(pre + "AvEvapFract", col([](tCNode *c) { return c->getAvEvapFract(); }));
+        w.f64(pre + "SheltFact", col([](tCNode *c) { return c->getSheltFact(); }));
+        w.f64(pre + "CumRSin", col([](tCNode *c) { return c->getCumRSin(); }));
+        w.f64(pre + "EvapWetCanopy", col([](tCNode *c) { return c->getEvapWetCanopy(); }));
+        w.f64(pre + "CumTotEvap", col([](tCNode *c) { return c->getCumTotEvap(); }));
+        w.f64(pre + "CumBarEvap", col([](tCNode *c) { return c->getCumBarEvap(); }));
+        w.f64(pre + "AvET", col([](tCNode *c) { return c->getAvET(); }));
+        w.f64(pre + "InterceptLoss", col([](tCNode *c) { return c->getInterceptLoss(); }));
+        w.f64(pre + "CanStorage", col([](tCNode *c) { return c->getCanStorage(); }));
+        w.f64(pre + "CumIntercept", col([](tCNode *c) { return c->getCumIntercept(); }));
+        w.f64(pre + "StormLength", col([](tCNode *c) { return c->getStormLength(); }));
+        w.f64(pre + "EvapoTrans", col([](tCNode *c) { return c->getEvapoTrans(); }));
+        w.f64(pre + "EvapSoil", col([](tCNode *c) { return c->getEvapSoil(); }));
+        w.f64(pre + "EvapDryCanopy", col([](tCNode *c) { return c->getEvapDryCanopy(); }));
+        w.f64(pre + "NetPrecipitation", col([](tCNode *c) { return c->getNetPrecipitation(); }));
+        w.f64(pre + "Rain", col([](tCNode *c) { return c->getRain(); }));
+        vector<double> sun = {et->alphaD, et->sinAlpha, et->sunaz, et->Io, (double)et->currentTime[3],
+                              (double)et->hourlyTimeStep, (double)et->dewHumFlag, (double)et->skycover_flag,
+                              et->del, et->phi, et->tau, et->deltaT, (double)et->nodeHour,
+                              et->latitude, et->longitude, (double)et->gmt};
+        w.f64(pre + "sun", sun);
     }
 
     // -------------------------------------------------------------- dynamic state
@@ -558,6 +705,7 @@ int main(int argc, char **argv) {
 
     Harness H;
     H.mesh = &BasinMesh; H.flow = &Flow; H.hydro = &Moisture; H.timer = &Timer;
+    H.et = &EvapoTrans; H.icp = &Intercept; H.rainfall = &Rainfall;
     H.index();
     if (do_basin) H.dump_basin(outdir + "/basin.trb", InputFile);
     if (do_kat) H.dump_kat(outdir + "/kat.trb");
@@ -584,6 +732,9 @@ int main(int argc, char **argv) {
         Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
         if (inject_evap > 0.0)
             for (tCNode *cn : H.cells) cn->setEvapSoil(cn->getRain() > 0.0 ? 0.0 : inject_evap);
+        if (snap && phases.find('m') != string::npos) {
+            snprintf(pre, sizeof pre, "s%d_m_", step); H.dump_et(*sw, pre);
+        }
         double t1 = now_s();
         // SubSurfaceHydroProcesses, split so the state between the two zones is observable
         if (use_gpu) gpu.UnSaturatedZone(Timer.getTimeStep());

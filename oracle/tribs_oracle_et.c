@@ -1,0 +1,603 @@
+/* TEST INFRASTRUCTURE — NOT PRODUCT CODE. See tribs_oracle_et.h.
+ *
+ * The reference keeps the working set of one cell in tEvapoTrans / tIntercept members; here it
+ * is the struct `EtCell`, rebuilt for every cell from the arrays. Operation order follows the
+ * reference expression by expression (compile with -ffp-contract=off) so results are bit-equal.
+ */
+#include "tribs_oracle_et.h"
+#include <math.h>
+#include <stdlib.h>
+
+#define F(name) etf[ORCET_##name][i]
+
+typedef struct {
+  /* met record of the cell (tEvapoTrans::newHydroMetData, tEvapoTrans.cpp:3962-4010) */
+  double airTemp, dewTemp, rHumidity, vPress, atmPress, windSpeed, skyCover, inShortR;
+  /* derived ("C") copies the met functions leave behind */
+  double dewTempC, vPressC, rHumidityC, atmPressC, skyCoverC, windSpeedC;
+  int dewHumFlag, skyFlag, tsOption;
+  /* land / soil coefficients (setCoeffs, tEvapoTrans.cpp:915-952) */
+  double coeffAl, coeffH, coeffKt, coeffRs, coeffV, coeffSE, coeffST, coeffKs, coeffCs;
+  double betaS, betaT;
+  /* geometry */
+  double elevation, slope, aspect, shelterFactor;
+  /* sun (global) */
+  double alphaD, sinAlpha, sunaz, Io;
+  int hour;
+  /* radiation */
+  double Ic, Is, Id, Ids, Ics, SunHour, inLongR, outLongR;
+  /* energy balance */
+  double Tso, Tlo, Gso, Rah, Rstm, hFlux, lFlux, gFlux, netRadC, potEvap, actEvap;
+  double rain;
+  /* options */
+  int etOpt, gOpt, shOpt;
+  double timeStep, Tlinke;
+} EtCell;
+
+/* ---- tEvapoTrans.cpp:1224-1413 */
+static double latent_heat(const EtCell *c) { return ((597.3 - c->airTemp * 0.57) * (4186.8)); }
+static double sat_vp(const EtCell *c) { return (6.112 * exp((17.67 * c->airTemp) / (c->airTemp + 243.5))); }
+static double sat_vp_at(double t) { return (6.112 * exp((17.67 * t) / (t + 243.5))); }
+
+static double vapor_press(EtCell *c) {
+  double dewTempK, rv = 461.5, eo = 6.112, to = 273.15;
+  if (c->dewHumFlag == 0) {
+    c->vPressC = sat_vp(c) * c->rHumidity / 100.0;
+    dewTempK = 1.0 / ((1.0 / to) - (log(c->vPressC / eo) * rv / latent_heat(c)));
+    c->dewTempC = dewTempK - 273.15;
+    c->rHumidityC = c->rHumidity;
+    c->dewTemp = c->dewTempC;
+    c->vPress = c->vPressC;
+  } else if (c->dewHumFlag == 1) {
+    dewTempK = c->dewTemp + 273.15;
+    c->dewTempC = c->dewTemp;
+    c->vPressC = eo * exp((latent_heat(c) / rv) * ((1.0 / to) - (1.0 / dewTempK)));
+    c->rHumidityC = 100.0 * c->vPressC / sat_vp(c);
+    c->rHumidity = c->rHumidityC;
+    c->vPress = c->vPressC;
+  } else if (c->dewHumFlag == 2) {
+    c->vPressC = c->vPress;
+    c->rHumidityC = 100.0 * c->vPressC / sat_vp(c);
+    dewTempK = 1.0 / ((1.0 / to) - (log(c->vPressC / eo) * rv / latent_heat(c)));
+    c->dewTempC = dewTempK - 273.15;
+    c->rHumidity = c->rHumidityC;
+    c->dewTemp = c->dewTempC;
+  }
+  return c->vPressC;
+}
+
+static double total_press(EtCell *c) {
+  double atmospress;
+  if (fabs(c->atmPress - 9999.99) < 1.0E-3) atmospress = 1000.0;
+  else atmospress = c->atmPress;
+  c->atmPressC = atmospress;
+  return atmospress + vapor_press(c);
+}
+
+static double claus_clap(EtCell *c) {
+  double latHeat = latent_heat(c), esat = sat_vp(c), rv = 461.5, airTempK = c->airTemp + 273.15;
+  return 100.0 * (latHeat * esat) / (rv * pow(airTempK, 2.0));
+}
+
+static double psychometric(EtCell *c) {
+  double eps = 0.622, cp = 1013.0;
+  return ((cp * total_press(c)) / (eps * latent_heat(c)));
+}
+
+static double density_moist(EtCell *c) {
+  double Rconst = 287.6, airTempK = c->airTemp + 273.15;
+  return (100.0 * total_press(c) / (Rconst * airTempK)) * (1.0 - 0.378 * vapor_press(c) / total_press(c));
+}
+
+/* ---- tEvapoTrans.cpp:1442-1512 */
+static double aero_resist(EtCell *c) {
+  double vonKarm = 0.41, vegHeight, vegBare = 1.0, vegFrac = c->coeffV;
+  double zm, zom, zov, d, rav, ras;
+  vegHeight = (c->coeffH == 0) ? 0.1 : c->coeffH;
+  if (c->windSpeed == 0.0 || fabs(c->windSpeed - 9999.99) < 1.0E-3) c->windSpeedC = 0.1;
+  else c->windSpeedC = c->windSpeed;
+  zm = 2.0 + vegHeight; zom = 0.123 * vegHeight; zov = 0.0123 * vegHeight; d = 0.67 * vegHeight;
+  rav = log((zm - d) / zom) * log((zm - d) / zov) / (c->windSpeedC * pow(vonKarm, 2.0));
+  zm = 2.0 + vegBare; zom = 0.123 * vegBare; zov = 0.0123 * vegBare; d = 0.67 * vegBare;
+  ras = log((zm - d) / zom) * log((zm - d) / zov) / (c->windSpeedC * pow(vonKarm, 2.0));
+  return (1 - vegFrac) * ras + vegFrac * rav;
+}
+
+static double stom_resist(const EtCell *c) {
+  static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014,
+                                     0.995, 0.976, 0.976, 1.0, 1.053, 1.167, 1.354, 1.637,
+                                     2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
+  double rs = c->coeffRs * rsRatio[c->hour];
+  if (c->alphaD < 0.0) rs *= 1000.0;
+  return rs;
+}
+
+/* ---- tEvapoTrans.cpp:2048-2068 */
+static double comp_sky_cover(const EtCell *c) {
+  double sc;
+  if (c->rain > 0) sc = 10.0;
+  else sc = round(10.0 * (3.2 * c->rHumidityC / 100.0 - 2.4) / 0.8);
+  if (sc < 0) sc = 0;
+  else if (sc > 10) sc = 10.0;
+  return sc;
+}
+
+/* ---- tEvapoTrans.cpp:2004-2037 */
+static double in_long_wave(EtCell *c) {
+  double sigma = 5.67E-8, kCloud, airTempK, Ea, scover, N, v0;
+  v0 = (c->shOpt < 3) ? c->shelterFactor : 1;
+  if (c->skyFlag == 1) { c->skyCover = comp_sky_cover(c); scover = c->skyCover; }
+  else scover = c->skyCover;
+  c->skyCoverC = scover;
+  N = scover / 10.0;
+  kCloud = 1.0 + 0.17 * pow(N, 2.0);
+  airTempK = c->airTemp + 273.15;
+  Ea = 0.74 + 0.0049 * vapor_press(c);
+  return v0 * kCloud * Ea * sigma * pow(airTempK, 4.0);
+}
+
+/* ---- tEvapoTrans.cpp:1939-1993 */
+static void direct_diffuse(EtCell *c, double elev) {
+  double h0, m, pp0, Dh0ref, h0ref, drm, TnTLK, Fdh0, A1p, A1, A2, A3;
+  double pi = 4.0 * atan(1.0), T = c->Tlinke;
+  h0 = c->alphaD;
+  pp0 = exp(-elev / 8434.5);
+  Dh0ref = 0.061359 * (0.1594 + 1.123 * h0 + 0.065656 * h0 * h0) / (1 + 28.9344 * h0 + 277.3971 * h0 * h0);
+  h0ref = h0 + Dh0ref;
+  m = pp0 / (sin(h0ref * pi / 180.) + 0.50572 * pow((h0ref + 6.07995), -1.6364));
+  if (m <= 20.0) drm = 1 / (6.6296 + 1.7513 * m - 0.1202 * m * m + 0.0065 * pow(m, 3.0) - 0.00013 * pow(m, 4.0));
+  else drm = 1 / (10.4 + 0.718 * m);
+  c->Ic = c->Io * exp(-0.8662 * T * m * drm);
+  TnTLK = -0.015843 + 0.030543 * T + 0.0003797 * pow(T, 2.0);
+  A1p = 0.26463 - 0.061581 * T + 0.0031408 * pow(T, 2.0);
+  if (A1p * TnTLK < 0.0022) A1 = 0.0022 / TnTLK;
+  else A1 = A1p;
+  A2 = 2.04020 + 0.018945 * T - 0.011161 * pow(T, 2.0);
+  A3 = -1.3025 + 0.039231 * T + 0.0085079 * pow(T, 2.0);
+  Fdh0 = A1 + A2 * c->sinAlpha + A3 * pow(c->sinAlpha, 2.0);
+  c->Id = c->Io * TnTLK * Fdh0;
+}
+
+/* ---- tEvapoTrans.cpp:1751-1930 (shelter options 0 and >= 4 only; observed stations) */
+static void in_short_wave(EtCell *c, double *const *etf, int i) {
+  double N = 0, Iv = 0, Isw = 0, Ir = 0, v, cosi, vegAbs = 0.0, soilAbs = 0.0;
+  c->Ic = c->Is = c->Id = c->Ids = c->Ics = 0.0;
+  F(ShortRadIn_dir) = 0.0; F(ShortRadIn_dif) = 0.0; F(ShortRadSlope) = 0.0;
+  F(ShortAbsbVeg) = 0.0; F(ShortAbsbSoi) = 0.0;
+  c->SunHour = 0.0;
+  if (c->alphaD > 0.0) {
+    direct_diffuse(c, c->elevation);
+    N = 0;
+    if (c->tsOption > 1) {
+      double RadGlobClr = (c->inShortR / (1.0 - 0.65 * pow(N, 2.0)));
+      c->Ic = c->Ic / (c->Ic * c->sinAlpha + c->Id) * RadGlobClr;
+      c->Id = RadGlobClr - c->Ic * c->sinAlpha;
+    }
+    if (c->shOpt < 4) {
+      cosi = cos(c->slope) * c->sinAlpha + sin(c->slope) * cos(asin(c->sinAlpha)) * cos(c->sunaz - c->aspect);
+      if (cosi >= 0) { c->Ics = c->Ic * cosi; c->SunHour = 1.0; }
+      else { c->Ics = 0.0; c->SunHour = 0.0; }
+    } else { c->Ics = c->Ic; c->SunHour = 1.0; }
+    if ((c->shOpt == 0) || (c->shOpt == 3)) v = 0.5 * (1.0 + cos(c->slope));
+    else v = 1.0;
+    c->Ids = c->Id * v;
+    c->Is = (1.0 - 0.65 * pow(N, 2.0)) * (c->Ics + c->Ids);
+    if (c->shOpt == 0) { Ir = c->coeffAl * c->Is * (1 - cos(c->slope)) * 0.5; c->Is += Ir; }
+    else Ir = 0.0;
+    if (c->etOpt == 1) {
+      F(ShortRadSlope) = c->Is;
+      soilAbs = (c->Is * c->coeffKt * c->coeffV + c->Is * (1.0 - c->coeffV)) * (1.0 - c->coeffAl);
+      vegAbs = c->Is * c->coeffV * (1.0 - c->coeffKt) * (1.0 - c->coeffAl);
+      F(ShortAbsbSoi) = soilAbs; F(ShortAbsbVeg) = vegAbs;
+      Iv = soilAbs;
+    } else Iv = c->Is * (1.0 - c->coeffAl);
+    Isw = Iv;
+  } else {
+    c->Ic = c->Is = N = Iv = Isw = c->Id = c->Ids = c->Ics = Ir = 0.0;
+  }
+  if (c->tsOption > 1) F(ShortRadIn) = c->inShortR;
+  else F(ShortRadIn) = Isw;
+  F(ShortRadIn_dir) = c->Ics * (1.0 - 0.65 * pow(N, 2.0));
+  F(ShortRadIn_dif) = (c->Ids + Ir) * (1.0 - 0.65 * pow(N, 2.0));
+}
+
+/* ---- tEvapoTrans.cpp:2663-2716 */
+static double force_restore(EtCell *c, double Ts, int option) {
+  double w1, d1, k, cs, ddel, pi, dt, alpha = 0, nd, G, Tg, Tl, dg, dTgdt, dGdTg, dTK, tempo = 0;
+  dTK = 0.001;
+  pi = 4.0 * atan(1.0);
+  w1 = 2. * pi / 86400.;
+  dt = c->timeStep * 60.0;
+  cs = c->coeffCs;
+  k = c->coeffKs / c->coeffCs;
+  d1 = pow((2.0 * k / w1), 0.5);
+  ddel = 0.1;
+  nd = ddel / d1;
+  if (nd >= 0.0 && nd <= 5.0)
+    alpha = 1 + 0.943 * nd + 0.223 * pow(nd, 2.0) + 0.0168 * pow(nd, 3.0) - 0.00527 * pow(nd, 4.0);
+  Tg = Ts; Tl = c->Tlo;
+  dg = (0.5 * cs * d1) / (1.0 + (w1 * dt) / (2.0 * pow(365., 0.5)));
+  if (option == 1) {
+    dTgdt = (Tg - c->Tso) / dt;
+    G = dg * (alpha * dTgdt + w1 * (Tg - Tl));
+    c->Gso = G;
+    tempo = G;
+  } else if (option == 2) {
+    dTgdt = (Tg + dTK - c->Tso) / dt;
+    dGdTg = (dg * (alpha * dTgdt + w1 * (Tg - Tl)) - c->Gso) / dTK;
+    tempo = dGdTg;
+  }
+  return tempo;
+}
+
+/* ---- tEvapoTrans.cpp:2486-2632 */
+static void func_and_deriv(EtCell *c, double *const *etf, int i, double Tg, double *fv, double *dv, double Rabsb_soi) {
+  double Rn, Lsoi, Hsoi, lEsoi, G = 0, dQ, num, Ep = 0, Eps, LE = 0, H = 0, ccTs = 0;
+  double alpha = 1.26, sigma = 5.67E-8, Es = 0.98, Cp = 1013.0, Ch = 0.0025, rv = 461.5;
+  double rho = density_moist(c);
+  double P = total_press(c);
+  double satVap = sat_vp(c);
+  double es = vapor_press(c);
+  double lam = latent_heat(c);
+  double cc = claus_clap(c);
+  double psy = 100.0 * psychometric(c);
+  double denom = ((cc / psy) + 1.0);
+  double denomrs = ((cc / psy) + 1.0 + c->Rstm / c->Rah);
+  double pi = 4.0 * atan(1.0);
+  double DTime = c->timeStep * 60.0;
+  double dRndTg = 0, dLdTg, dHdTg = 0, dlEdTg = 0, dGdTg = 0, soiFct = 0, vegFct = 0, esat, qhSatTs, qhTa, v1;
+  v1 = (c->shOpt < 3) ? c->shelterFactor : 1;
+  F(SurfTemp) = Tg - 273.15;
+  c->inLongR = F(LongRadIn);
+  c->outLongR = v1 * Es * sigma * pow(Tg, 4.0);
+  Lsoi = c->outLongR - c->inLongR;
+  if (c->gOpt == 1) G = pow((4.0 * c->coeffKs * c->coeffCs / (pi * DTime)), 0.5) * (Tg - c->Tso);
+  else if (c->gOpt == 2) G = force_restore(c, Tg, 1);
+  Rn = Rabsb_soi - Lsoi;
+  if (c->etOpt == 1 || c->etOpt == 3) H = rho * Cp * (Tg - (c->airTemp + 273.15)) / c->Rah;
+  else if (c->etOpt == 2) H = rho * Cp * (Tg - (c->airTemp + 273.15)) * Ch * c->windSpeedC;
+  Hsoi = H;
+  if (c->etOpt == 1) {
+    dQ = (0.622 / P) * (satVap - es) * rho * lam / c->Rah;
+    soiFct = (1.0 - c->coeffV) * c->betaS;
+    vegFct = c->coeffV * c->betaT;
+    num = (cc / psy) * (Rn - G) + dQ;
+    Eps = num / denom / lam;
+    Ep = num / denomrs / lam;
+    LE = soiFct * lam * Eps + vegFct * lam * Ep;
+    Ep *= (denomrs / denom);
+  } else if (c->etOpt == 2) {
+    esat = sat_vp_at(Tg - 273.15);
+    ccTs = (lam * esat) / (rv * pow(Tg, 2.0));
+    qhSatTs = (0.622 / P) * esat;
+    qhTa = (0.622 / P) * es;
+    if (qhSatTs > qhTa) Ep = rho * Ch * (qhSatTs - qhTa) * c->windSpeedC; else Ep = 0.0;
+    LE = Ep * lam * c->betaS;
+  } else if (c->etOpt == 3) {
+    if (Rn > G) Ep = (alpha / lam) * (Rn - G) * ((cc / psy) / denom); else Ep = 0.0;
+    LE = Ep * lam * c->betaS;
+  }
+  lEsoi = LE;
+  *fv = -Rabsb_soi + Lsoi + Hsoi + lEsoi + G;
+  dLdTg = 4.0 * Es * sigma * pow(Tg, 3.0);
+  dRndTg = -dLdTg;
+  if (c->gOpt == 1) dGdTg = pow((4.0 * c->coeffKs * c->coeffCs / (pi * DTime)), 0.5);
+  else if (c->gOpt == 2) dGdTg = force_restore(c, Tg, 2);
+  if (c->etOpt == 1) {
+    dHdTg = rho * Cp / c->Rah;
+    dlEdTg = soiFct * (cc / psy) * (dRndTg - dGdTg) / denom + vegFct * (cc / psy) * (dRndTg - dGdTg) / denomrs;
+  } else if (c->etOpt == 2) {
+    dHdTg = rho * Cp * Ch * c->windSpeedC;
+    dlEdTg = lam * rho * Ch * c->windSpeedC * (0.622 / P) * ccTs * c->betaS;
+  } else if (c->etOpt == 3) {
+    dHdTg = rho * Cp / c->Rah;
+    dlEdTg = c->betaS * (alpha) * ((cc / psy) / denom) * (dRndTg - dGdTg);
+  }
+  *dv = dLdTg + dHdTg + dlEdTg + dGdTg;
+  c->hFlux = Hsoi; c->lFlux = lEsoi; c->netRadC = Rn; c->gFlux = G; c->potEvap = Ep;
+}
+
+/* ---- tEvapoTrans.cpp:2391-2474 */
+static double rtsafe_energy(EtCell *c, double *const *etf, int i, double x1, double x2, double xacc,
+                            double xguess, double Rabsb) {
+  int j;
+  double df = 0, dx = 0, dxold, f, fh = 0, fl = 0, temp, xh, xl, rts;
+  func_and_deriv(c, etf, i, x1, &fl, &df, Rabsb);
+  if (fl == 0.0) return x1;
+  func_and_deriv(c, etf, i, x2, &fh, &df, Rabsb);
+  if (fh == 0.0) return x2;
+  if (fl < 0.0) { xl = x1; xh = x2; } else { xh = x1; xl = x2; }
+  rts = xguess;
+  dxold = fabs(x2 - x1);
+  dx = dxold;
+  func_and_deriv(c, etf, i, rts, &f, &df, Rabsb);
+  for (j = 1; j <= 100; j++) {
+    if ((((rts - xh) * df - f) * ((rts - xl) * df - f) > 0.0) || (fabs(2.0 * f) > fabs(dxold * df))) {
+      dxold = dx;
+      dx = 0.5 * (xh - xl);
+      rts = xl + dx;
+      if (xl == rts) return rts;
+    } else {
+      dxold = dx;
+      dx = f / df;
+      temp = rts;
+      rts -= dx;
+      if (temp == rts) return rts;
+    }
+    if (fabs(dx) < xacc) return rts;
+    func_and_deriv(c, etf, i, rts, &f, &df, Rabsb);
+    if (f < 0.0) xl = rts; else xh = rts;
+  }
+  return xguess;
+}
+
+/* ---- tEvapoTrans.cpp:2281-2357 */
+static double energy_balance(EtCell *c, double *const *etf, int i) {
+  double f, df, Tg, soilAbs;
+  c->SunHour = 0;
+  c->inLongR = in_long_wave(c);
+  F(LongRadIn) = c->inLongR;
+  in_short_wave(c, etf, i);
+  soilAbs = F(ShortAbsbSoi);
+  c->Rah = aero_resist(c);
+  c->Rstm = stom_resist(c);
+  Tg = c->Tso;
+  Tg = rtsafe_energy(c, etf, i, 223.15, 373.15, 1.0e-5, Tg, soilAbs);
+  func_and_deriv(c, etf, i, Tg, &f, &df, soilAbs);
+  c->Tso = Tg;
+  c->Tlo += (c->gFlux * c->timeStep * 60.0) / (c->coeffCs * 33.862683 * pow((c->coeffKs / c->coeffCs / 3.6361E-05), 0.5));
+  F(SurfTemp) = Tg - 273.15;
+  F(SoilTemp) = c->Tlo - 273.15;
+  F(NetRad) = c->netRadC; F(GFlux) = c->gFlux; F(HFlux) = c->hFlux; F(LFlux) = c->lFlux;
+  F(LongRadOut) = c->outLongR;
+  return c->potEvap;
+}
+
+static void load_coeffs(const orc_et_basin *b, EtCell *c, int i) {
+  const double *lp = b->land_table + (size_t)b->land_class[i] * 15;
+  c->etOpt = b->et_option; c->gOpt = b->gflux_option; c->shOpt = b->shelter_option;
+  c->timeStep = b->metstep_min; c->Tlinke = b->tlinke;
+  c->coeffAl = c->coeffH = c->coeffKt = c->coeffRs = 0.0;
+  c->coeffV = 0.0;
+  if (b->et_option == 1) { c->coeffAl = lp[7]; c->coeffH = lp[8]; c->coeffKt = lp[9]; c->coeffRs = lp[10]; c->coeffV = lp[11]; }
+  else if (b->et_option == 2 || b->et_option == 3) { c->coeffAl = lp[7]; c->coeffV = lp[11]; }
+  else if (b->et_option == 4) c->coeffV = lp[11];
+  c->coeffSE = lp[13]; c->coeffST = lp[14];
+  if (c->coeffV >= 1.0) c->coeffV = 0.99;
+  c->coeffKs = b->VolHeatCond[i]; c->coeffCs = b->SoilHeatCap[i];
+}
+
+static void load_met(const orc_et_basin *b, const orc_et_step *s, const orc_met *m, EtCell *c, int i) {
+  int r = m->cell_record[i];
+  c->airTemp = m->air_temp[r];
+  c->airTemp += b->temp_lapse * (c->elevation - m->elev[r]);
+  c->dewTemp = m->dew_temp[r]; c->rHumidity = m->rel_humid[r]; c->vPress = m->vap_press[r];
+  c->atmPress = m->atm_press[r]; c->windSpeed = m->wind_speed[r]; c->skyCover = m->sky_cover[r];
+  c->inShortR = m->rad_global[r];
+  c->dewHumFlag = s->dew_hum_flag; c->tsOption = s->ts_option;
+  c->alphaD = s->alphaD; c->sinAlpha = s->sinAlpha; c->sunaz = s->sunaz; c->Io = s->Io; c->hour = s->hour;
+}
+
+/* tEvapoTrans::betaFunc / betaFuncT, tEvapoTrans.cpp:2911-3010 */
+static void beta_funcs(const orc_et_basin *b, const orc_et_shared *sh, EtCell *c, int i) {
+  double Thr = b->ThetaR[i], Th, ratio, beta;
+  Th = sh->SoilMoisture[i];
+  ratio = (Th - Thr) / (c->coeffSE - Thr);
+  if (ratio > 1.0) beta = 1.0; else if (ratio < 0.0) beta = 0.0; else beta = ratio;
+  if (Th <= b->soil_cutoff[i]) beta = 0.0;
+  c->betaS = beta;
+  Th = sh->RootMoisture[i];
+  ratio = (Th - Thr) / (c->coeffST - Thr);
+  if (ratio < 1.0) beta = ratio; else beta = 1.0;
+  if (Th <= b->root_cutoff[i]) beta = 0.0;
+  c->betaT = beta;
+}
+
+int orc_et_potential(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
+                     double *const *etf, const orc_et_shared *sh) {
+  if (!(b->shelter_option == 0 || b->shelter_option >= 4)) return 1;
+  if (b->et_option < 1 || b->et_option > 3) return 1;
+  for (int i = 0; i < b->n; i++) {
+    EtCell cell, *c = &cell;
+    double vPress, tmp;
+    c->rain = sh->Rain[i];
+    c->elevation = b->z[i];
+    c->slope = fabs(atan(b->flow_slope[i]));
+    c->aspect = b->aspect[i];
+    if (b->shelter_option == 0) { c->shelterFactor = 0.5 * (1 + cos(c->slope)); F(SheltFact) = c->shelterFactor; }
+    else c->shelterFactor = 1;
+    load_coeffs(b, c, i);
+    load_met(b, s, m, c, i);
+    if (s->first_call) { c->Tso = m->air_temp[m->cell_record[i]] + 273.15; c->Tlo = c->Tso; }
+    else { c->Tso = 0.0; c->Tlo = 0.0; }
+    c->skyFlag = (i >= s->sky_flag_from) || (fabs(c->skyCover - 9999.99) < 1.0E-3);
+    vPress = vapor_press(c);
+    F(AirTemp) = c->airTemp; F(DewTemp) = c->dewTemp; F(RelHumid) = c->rHumidity; F(VapPressure) = vPress;
+    if (c->skyFlag == 1) c->skyCover = comp_sky_cover(c);
+    F(SkyCover) = c->skyCover; F(WindSpeed) = c->windSpeed; F(AirPressure) = c->atmPress;
+    F(ShortRadIn) = c->inShortR;
+    if (s->first_call) { F(SoilTemp) = c->Tlo - 273.15; F(SurfTemp) = c->Tso - 273.15; }
+    if (b->i_option == 0) sh->NetPrecipitation[i] = c->rain;
+    beta_funcs(b, sh, c, i);
+    c->Tso = F(SurfTemp) + 273.15;
+    c->Tlo = F(SoilTemp) + 273.15;
+    c->Gso = 0.0;
+    /* EvapPenmanMonteith / Deardorff / PriestlyTaylor (tEvapoTrans.cpp:2790-2870) */
+    c->potEvap = 3600.0 * energy_balance(c, etf, i);
+    if (b->et_option == 1) c->actEvap = 3600.0 * (c->lFlux / (latent_heat(c)));
+    else if (b->et_option == 2) c->actEvap = c->betaS * c->potEvap;
+    else c->actEvap = c->betaS * c->potEvap;
+    /* setToNode, tEvapoTrans.cpp:3039-3076 */
+    if (c->dewHumFlag == 0) { F(DewTemp) = c->dewTempC; F(VapPressure) = c->vPressC; }
+    else if (c->dewHumFlag == 1) { F(VapPressure) = c->vPressC; F(RelHumid) = c->rHumidityC; }
+    else if (c->dewHumFlag == 2) { F(DewTemp) = c->dewTempC; F(RelHumid) = c->rHumidityC; }
+    F(PotEvap) = c->potEvap; F(ActEvap) = c->actEvap; F(AirTemp) = c->airTemp;
+    F(AirPressure) = c->atmPressC; F(SkyCover) = c->skyCoverC; F(WindSpeed) = c->windSpeedC;
+    F(CumHrsSun) += c->SunHour;
+    tmp = 0;
+    if ((fabs(c->hFlux) + fabs(c->lFlux)) > 1.0) tmp = fabs(c->lFlux) / (fabs(c->hFlux) + fabs(c->lFlux));
+    if (fabs(s->te_met - 1.0) <= 1.0E-6) F(AvEvapFract) = tmp;
+    else if (s->te_met > 1.0) F(AvEvapFract) = (F(AvEvapFract) * (s->te_met - 1.0) + tmp) / s->te_met;
+    F(SheltFact) = c->shelterFactor;
+    F(CumRSin) += c->inShortR * 3600.0;
+  }
+  return 0;
+}
+
+/* ---- tIntercept.cpp:214-253 */
+static void intercept_gray(const orc_et_basin *b, double *const *etf, const orc_et_shared *sh, int i) {
+  const double *lp = b->land_table + (size_t)b->land_class[i] * 15;
+  double coeffA = lp[1], coeffB = lp[2], coeffV = lp[11];
+  double cumIntercept, intercept, rainfall, minRainAmount = 1.0;
+  rainfall = sh->Rain[i];
+  if (rainfall <= minRainAmount) F(StormLength) += b->etistep_h; else F(StormLength) = 0.0;
+  cumIntercept = F(CumIntercept);
+  if (cumIntercept <= coeffA) intercept = rainfall; else intercept = rainfall * coeffB;
+  F(InterceptLoss) = intercept;
+  if (F(StormLength) < b->max_interstorm) F(CumIntercept) = cumIntercept + intercept * b->etistep_h;
+  else F(CumIntercept) = 0.0;
+  sh->NetPrecipitation[i] = coeffV * (rainfall - intercept) + (1 - coeffV) * rainfall;
+}
+
+/* ---- tIntercept.cpp:283-459 */
+static double rutter_fn(double C, double R, double Ep, double P, double S, double K, double bb) {
+  if (C < S) return ((1 - P) * R - (C / S) * Ep - K * exp(bb * (C - S)));
+  return ((1 - P) * R - Ep - K * exp(bb * (C - S)));
+}
+
+static void intercept_rutter(const orc_et_basin *b, double *const *etf, const orc_et_shared *sh, int i, double evaporation) {
+  const double *lp = b->land_table + (size_t)b->land_class[i] * 15;
+  double coeffP = lp[3], coeffS = lp[4], coeffK = lp[5], coeffb = lp[6], coeffV = lp[11];
+  double rainfall, prevStorage, currentStorage, throughfall, netPrecipitation, interception, cumIntercept, ctos;
+  double minRainAmount = 1.0, dt = b->etistep_h;
+  rainfall = sh->Rain[i];
+  prevStorage = F(CanStorage);
+  ctos = F(CanStorage) / coeffS;
+  if (ctos > 1) ctos = 0;
+  if (rainfall <= minRainAmount) F(StormLength) += dt; else F(StormLength) = 0.0;
+  if (prevStorage > evaporation * ctos * dt || rainfall > 0) {
+    cumIntercept = F(CumIntercept);
+    {   /* storageRungeKutta */
+      double numiter = floor(rainfall * 3.0), h, t0, tlast = dt, c0 = prevStorage, ta, tb, tc, td;
+      if (numiter < 50.0) numiter = 50.0;
+      h = dt / numiter;
+      for (t0 = 0.0; t0 < tlast; t0 += h) {
+        ta = h * rutter_fn(c0, rainfall, evaporation, coeffP, coeffS, coeffK, coeffb);
+        tb = h * rutter_fn(c0 + ta / 2.0, rainfall, evaporation, coeffP, coeffS, coeffK, coeffb);
+        tc = h * rutter_fn(c0 + tb / 2.0, rainfall, evaporation, coeffP, coeffS, coeffK, coeffb);
+        td = h * rutter_fn(c0 + tc, rainfall, evaporation, coeffP, coeffS, coeffK, coeffb);
+        c0 += (ta / 6.0 + tb / 3.0 + tc / 3.0 + td / 6.0);
+      }
+      currentStorage = c0;
+    }
+    double rain_on_canopy_vol = (1 - coeffP) * rainfall * dt;
+    double total_available_water = prevStorage + rain_on_canopy_vol;
+    if (currentStorage > total_available_water) currentStorage = total_available_water;
+    double avg_storage = (prevStorage + currentStorage) / 2.0;
+    double evapWetCanopy_rate;
+    if (avg_storage < coeffS) evapWetCanopy_rate = (avg_storage / coeffS) * evaporation;
+    else evapWetCanopy_rate = evaporation;
+    if (evapWetCanopy_rate < 0) evapWetCanopy_rate = 0.0;
+    double storage_change_vol = currentStorage - prevStorage;
+    double total_loss_vol = rain_on_canopy_vol - storage_change_vol;
+    if (total_loss_vol < 0.0) total_loss_vol = 0.0;
+    double evapWetCanopy_vol = evapWetCanopy_rate * dt;
+    if (evapWetCanopy_vol > total_loss_vol) evapWetCanopy_vol = total_loss_vol;
+    if (evapWetCanopy_vol < 0.0) evapWetCanopy_vol = 0.0;
+    double drainage_vol = total_loss_vol - evapWetCanopy_vol;
+    if (drainage_vol < 0.0) drainage_vol = 0.0;
+    if (currentStorage * 100 / coeffS <= 3) {
+      double potential_evap_vol = evaporation * dt;
+      if ((evapWetCanopy_vol + currentStorage) <= potential_evap_vol) evapWetCanopy_vol += currentStorage;
+      else drainage_vol += currentStorage;
+      currentStorage = 0.0;
+    }
+    throughfall = coeffP * rainfall;
+    netPrecipitation = (drainage_vol / dt) + throughfall;
+    if (netPrecipitation <= rainfall) interception = rainfall - netPrecipitation; else interception = 0.0;
+    netPrecipitation = coeffV * netPrecipitation + (1 - coeffV) * rainfall;
+    if (currentStorage < 0.0) currentStorage = 0.0;
+    sh->NetPrecipitation[i] = netPrecipitation;
+    F(InterceptLoss) = interception;
+    F(CanStorage) = currentStorage;
+    F(EvapWetCanopy) = evapWetCanopy_vol / dt;
+    if (F(StormLength) < b->max_interstorm) F(CumIntercept) = cumIntercept + interception * dt;
+    else F(CumIntercept) = 0.0;
+  } else {
+    sh->NetPrecipitation[i] = 0.0;
+    F(InterceptLoss) = 0.0; F(CanStorage) = 0.0; F(CumIntercept) = 0.0; F(EvapWetCanopy) = 0.0;
+  }
+}
+
+static int there_is_canopy(const orc_et_basin *b, int i) {
+  if (b->i_option == 1) return 1;
+  if (b->i_option == 2) return b->land_table[(size_t)b->land_class[i] * 15 + 3] < 0.999;
+  return 0;
+}
+
+/* ---- tEvapoTrans.cpp:980-1197 */
+int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
+                      double *const *etf, const orc_et_shared *sh, int flag) {
+  for (int i = 0; i < b->n; i++) {
+    EtCell cell, *c = &cell;
+    double potEvaporation, actEvaporation, cc, psy, ra, rs, transFactor;
+    double evapWetCanopy = 0.0, evapDryCanopy, evapSoil, evapoTranspiration;
+    if (!b->et_option) {
+      if (flag && there_is_canopy(b, i)) {
+        if (b->i_option == 1) intercept_gray(b, etf, sh, i); else intercept_rutter(b, etf, sh, i, 0.0);
+      }
+      continue;
+    }
+    c->elevation = b->z[i];
+    load_coeffs(b, c, i);
+    beta_funcs(b, sh, c, i);
+    load_met(b, s, m, c, i);
+    potEvaporation = F(PotEvap);
+    actEvaporation = F(ActEvap);
+    if (potEvaporation < 0) { potEvaporation = 0.0; F(PotEvap) = 0.0; }
+    if (actEvaporation < 0.0) { actEvaporation = 0.0; F(ActEvap) = 0.0; }
+    cc = claus_clap(c);
+    psy = psychometric(c);
+    ra = aero_resist(c);
+    rs = stom_resist(c);
+    transFactor = (cc + psy) / (cc + psy * (1 + rs / ra));
+    if (flag && (c->coeffV > 0) && there_is_canopy(b, i)) {
+      if (b->i_option == 1) {
+        double CanStorage = F(CumIntercept);
+        if (CanStorage >= potEvaporation * b->etistep_h) evapWetCanopy = potEvaporation;
+        else evapWetCanopy = CanStorage / b->etistep_h;
+        if (evapWetCanopy > potEvaporation) evapWetCanopy = potEvaporation;
+        intercept_gray(b, etf, sh, i);
+      } else if (b->i_option == 2) {
+        intercept_rutter(b, etf, sh, i, potEvaporation);
+        evapWetCanopy = F(EvapWetCanopy);
+      }
+    } else {
+      sh->NetPrecipitation[i] = sh->Rain[i];
+      evapWetCanopy = 0.0;
+    }
+    evapDryCanopy = c->betaT * ((potEvaporation - evapWetCanopy) * transFactor);
+    double potEvaporationRemaining = potEvaporation - evapWetCanopy - evapDryCanopy;
+    if (potEvaporationRemaining < 0.0) potEvaporationRemaining = 0.0;
+    evapWetCanopy *= c->coeffV;
+    evapDryCanopy *= c->coeffV;
+    if (b->bedrock[i] <= 0) evapSoil = 0;
+    else evapSoil = (1 - c->coeffV) * potEvaporationRemaining * c->betaS;
+    evapoTranspiration = evapWetCanopy + evapDryCanopy + evapSoil;
+    if (b->i_option == 1) {
+      double CanStorage = F(CumIntercept);
+      F(CumIntercept) = CanStorage - evapWetCanopy / c->coeffV * b->etistep_h;
+    }
+    F(EvapWetCanopy) = evapWetCanopy;
+    sh->EvapDryCanopy[i] = evapDryCanopy;
+    sh->EvapSoil[i] = evapSoil;
+    F(EvapoTrans) = evapoTranspiration;
+    F(CumTotEvap) += evapoTranspiration;
+    F(CumBarEvap) += evapSoil;
+    if (fabs(s->te_eti - 1.0) < 1.0E-6) F(AvET) = evapoTranspiration;
+    else if (s->te_eti > 1.0) F(AvET) = (F(AvET) * (s->te_eti - 1.0) + evapoTranspiration) / s->te_eti;
+  }
+  return 0;
+}
+
+int orc_et_n_fields(void) { return ORC_N_ET_FIELDS; }

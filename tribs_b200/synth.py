@@ -17,6 +17,7 @@ Formats follow the reference readers:
 """
 from __future__ import annotations
 
+import math
 import os
 import random
 from dataclasses import dataclass, field
@@ -47,6 +48,9 @@ class BasinSpec:
     land: tuple = (0.5, 0.2, 0.5, 1.0, 0.1, 3.7, 0.2, 1.0, 0.8, 100.0, 0.5, 2.0, 0.3, 0.25)
     opt_spatial: int = 0
     opt_interhydro: int = 0
+    forcing: str = "storm"        # "storm": STOCHASTICMODE 1 uniform storm; "met": rain gauges +
+                                  # one weather station (Penman-Monteith ET, Rutter interception)
+    n_gauges: int = 2
     inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
     extra: dict = field(default_factory=dict)   # keyword overrides
 
@@ -89,6 +93,62 @@ def _asc(path, xll, yll, size, ncell, value):
         row = " ".join([str(value)] * ncell)
         for _ in range(ncell):
             f.write(row + "\n")
+
+
+def met_series(spec: BasinSpec):
+    """Hourly forcing of the "met" decks: rain per gauge (mm/h) and one weather station's
+    PA RH XC US TA IS columns. Deterministic, smooth diurnal cycles with two wet spells."""
+    nh = int(math.ceil(spec.runtime_h)) + 2
+    rain = [[0.0] * nh for _ in range(spec.n_gauges)]
+    for g in range(spec.n_gauges):
+        for h in range(nh):
+            ph = h % 24
+            if 3 <= ph < 3 + int(spec.stdur):
+                rain[g][h] = round(spec.pmean * (0.6 + 0.4 * g) * (0.5 + 0.5 * math.sin(math.pi * (ph - 3 + 0.5) / spec.stdur)), 3)
+    met = []
+    for h in range(nh):
+        ph = h % 24
+        day = math.sin(math.pi * (ph - 6) / 12.0) if 6 <= ph <= 18 else 0.0
+        wet = any(rain[g][h] > 0 for g in range(spec.n_gauges))
+        ta = round(16.0 + 9.0 * math.sin(2 * math.pi * (ph - 9) / 24.0), 2)
+        rh = round(min(98.0, 55.0 - 25.0 * math.sin(2 * math.pi * (ph - 9) / 24.0) + (25.0 if wet else 0.0)), 2)
+        xc = 9.0 if wet else round(2.0 + 2.0 * math.cos(2 * math.pi * h / 37.0), 1)
+        us = round(2.5 + 1.5 * math.sin(2 * math.pi * h / 17.0), 2)
+        isw = round(850.0 * day * (0.25 if wet else 1.0), 1)
+        met.append((980.0, rh, xc, us, ta, isw))
+    return rain, met
+
+
+def write_met_forcing(spec: BasinSpec, outdir: str) -> dict:
+    """Rain-gauge (.sdf/.mdf, tRainfall.cpp:551-707) and weather-station files
+    (tEvapoTrans.cpp:3122-3330, columns Y M D H PA RH XC US TA IS NR); returns the keywords."""
+    rain, met = met_series(spec)
+    nh = len(met)
+    ext = (spec.n - 1) * spec.spacing
+
+    def stamp(h):
+        return f"2000 6 {1 + h // 24} {h % 24}"
+
+    with open(os.path.join(outdir, "gauges.sdf"), "w") as f:
+        f.write(f"{spec.n_gauges} 7\n")
+        for g in range(spec.n_gauges):
+            gx = ext * (g + 0.5) / spec.n_gauges
+            f.write(f"{g + 1} {outdir}/gauge{g + 1}.mdf {ext / 2:.3f} {gx:.3f} {nh} 5 110.0\n")
+            with open(os.path.join(outdir, f"gauge{g + 1}.mdf"), "w") as d:
+                d.write("Y M D H R\n")
+                for h in range(nh):
+                    d.write(f"{stamp(h)} {rain[g][h]}\n")
+    with open(os.path.join(outdir, "met.sdf"), "w") as f:
+        f.write("1 10\n")
+        f.write(f"1 {outdir}/met1.mdf 34.0 {ext / 2:.3f} -107.0 {ext / 2:.3f} -7 {nh} 11 105.0\n")
+    with open(os.path.join(outdir, "met1.mdf"), "w") as d:
+        d.write("Y M D H PA RH XC US TA IS NR\n")
+        for h in range(nh):
+            pa, rh, xc, us, ta, isw = met[h]
+            d.write(f"{stamp(h)} {pa} {rh} {xc} {us} {ta} {isw} 9999.99\n")
+    return {"STOCHASTICMODE": 0, "RAINSOURCE": 3, "GAUGESTATIONS": f"{outdir}/gauges.sdf",
+            "OPTEVAPOTRANS": 1, "OPTINTERCEPT": 2, "METDATAOPTION": 1,
+            "HYDROMETSTATIONS": f"{outdir}/met.sdf"}
 
 
 def write_basin(spec: BasinSpec, outdir: str) -> str:
@@ -138,6 +198,9 @@ def write_basin(spec: BasinSpec, outdir: str) -> str:
         ("HYDRONODELIST", "none"), ("OUTLETNODELIST", "none"),
     ]
     over = dict(spec.extra)
+    if spec.forcing == "met":
+        for k, v in write_met_forcing(spec, outdir).items():
+            over.setdefault(k, v)
     path = os.path.join(outdir, "basin.in")
     with open(path, "w") as f:
         for k, v in kv:
