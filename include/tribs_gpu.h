@@ -218,6 +218,78 @@ int tribs_gpu_destroy(tribs_handle_t h);
 const char *tribs_gpu_last_error(void);
 int tribs_gpu_abi_version(void);
 
+
+/* ==================================================================== kernel (1): ET + interception
+ * The per-cell loops of tEvapoTrans::callEvapoPotential (src/tHydro/tEvapoTrans.cpp:562-831:
+ * met assembly, betaFunc/betaFuncT 2911-3010, energyBalance 2281-2357 with inLongWave 2004,
+ * inShortWave/DirectDiffuse 1751-1993, aeroResist/stomResist 1442-1512, rtsafe_mod_energy /
+ * FunctionAndDerivative / ForceRestore 2391-2716, setToNode 3039-3076) and of
+ * tEvapoTrans::callEvapoTrans (980-1197: ComputeETComponents with tIntercept::InterceptGray /
+ * InterceptRutter, src/tHydro/tIntercept.cpp:214-459). What the reference does once per call
+ * stays with the host and arrives in tribs_et_step_t: calendar hour, sun geometry
+ * (SetSunVariables 1567-1660), the weather-station records of the hour (newHydroMetData
+ * 3962-4010) and the flags derived from record 0.
+ * Covered options: OPTEVAPOTRANS 1-3, OPTINTERCEPT 0-2, GFLUXOPTION 1-2, OPTRADSHELT 0 or 4,
+ * OPTLANDUSE 0, OPTSNOW 0, station or gridded met. Anything else fails in tribs_gpu_et_init. */
+#define TRIBS_ET_FIELDS(X) \
+  X(PotEvap) X(ActEvap) X(SurfTemp) X(SoilTemp) X(NetRad) X(GFlux) X(HFlux) X(LFlux) \
+  X(LongRadIn) X(LongRadOut) X(ShortRadIn) X(ShortRadIn_dir) X(ShortRadIn_dif) X(ShortRadSlope) \
+  X(ShortAbsbVeg) X(ShortAbsbSoi) X(AirTemp) X(DewTemp) X(RelHumid) X(VapPressure) X(SkyCover) \
+  X(WindSpeed) X(AirPressure) X(CumHrsSun) X(AvEvapFract) X(SheltFact) X(CumRSin) \
+  X(EvapWetCanopy) X(EvapoTrans) X(CumTotEvap) X(CumBarEvap) X(AvET) X(InterceptLoss) \
+  X(CanStorage) X(CumIntercept) X(StormLength)
+#define TRIBS_ET_FIELD_ENUM(name) TRIBS_ET_##name,
+typedef enum { TRIBS_ET_FIELDS(TRIBS_ET_FIELD_ENUM) TRIBS_N_ET_FIELDS } tribs_et_field_t;
+
+typedef struct {
+  const double *flow_slope;     /* [n] slope of tCNode::getFlowEdg() (tEvapoTrans.cpp:617) */
+  const double *aspect;         /* [n] tCNode::getAspect(), radians */
+  const double *vol_heat_cond;  /* [n] tCNode::getVolHeatCond() */
+  const double *soil_heat_cap;  /* [n] tCNode::getSoilHeatCap() */
+  const double *soil_cutoff;    /* [n] tCNode::getSoilCutoff() */
+  const double *root_cutoff;    /* [n] tCNode::getRootCutoff() */
+  const int32_t *land_class;    /* [n] row of land_table (tCNode::getLandUse()) */
+  int32_t n_land_classes;
+  const double *land_table;     /* [n_land_classes][15]: column k = tInvariant::getLandProp(k), k = 1..14 */
+  int32_t et_option, i_option, gflux_option, shelter_option;   /* OPTEVAPOTRANS OPTINTERCEPT GFLUXOPTION OPTRADSHELT */
+  int32_t lu_option, snow_option;                              /* must be 0 */
+  double metstep_min;           /* METSTEP (tEvapoTrans::timeStep) */
+  double etistep_h;             /* tRunTimer::getEtIStep() */
+  double tlinke, temp_lapse;    /* TLINKE, TEMPLAPSE */
+  double max_interstorm;        /* tIntercept::maxInterStormPeriod (INTSTORMMAX/2, tIntercept.cpp:44-45) */
+  const double *const *init;    /* NULL, or TRIBS_N_ET_FIELDS pointers (NULL entries = 0) */
+} tribs_et_params_t;
+
+/* one record per weather station (METDATAOPTION 1) or per cell (gridded, METDATAOPTION 2) */
+typedef struct {
+  int32_t n_records;
+  const int32_t *cell_record;   /* [n] record of each cell; NULL = as in the previous call */
+  const double *air_temp, *dew_temp, *rel_humid, *vap_press, *atm_press, *wind_speed, *sky_cover;
+  const double *rad_global;     /* tHydroMet::getRadGlobal */
+  const double *elev;           /* tHydroMet::getOther(): station elevation for TEMPLAPSE */
+} tribs_met_t;
+
+typedef struct {
+  int32_t do_potential;         /* callEvapoPotential is due (currentTime == met_hour) */
+  int32_t do_components;        /* callEvapoTrans is due (currentTime == eti_hour) */
+  int32_t intercept_flag;       /* 2nd argument of callEvapoTrans */
+  double alphaD, sinAlpha, sunaz, Io;     /* tEvapoTrans members after SetSunVariables */
+  int32_t hour;                 /* currentTime[3] */
+  int32_t first_call;           /* hourlyTimeStep == 0: soil/surface temperature start (3989-3992) */
+  int32_t dew_hum_flag;         /* 0 RH, 1 dew point, 2 vapour pressure observed (3994-4003) */
+  int32_t ts_option;            /* tEvapoTrans::tsOption (> 1: global radiation observed) */
+  int32_t sky_flag_from;        /* sweep index from which the computed sky cover applies (724-727) */
+  double te_met, te_eti;        /* getElapsedMETSteps / getElapsedETISteps(currentTime) as double */
+  const tribs_met_t *met_potential;   /* record read by callEvapoPotential */
+  const tribs_met_t *met_components;  /* record read by callEvapoTrans (met clock already advanced) */
+} tribs_et_step_t;
+
+int tribs_gpu_et_init(tribs_handle_t h, const tribs_et_params_t *prm);
+int tribs_gpu_et_step(tribs_handle_t h, const tribs_et_step_t *s);
+/* host[k] (k < TRIBS_N_ET_FIELDS) receives / supplies field k in sweep order when bit k is set */
+int tribs_gpu_et_sync(tribs_handle_t h, uint64_t et_field_mask, double *const *host);
+int tribs_gpu_et_push(tribs_handle_t h, uint64_t et_field_mask, const double *const *host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -5,7 +5,7 @@ import math
 
 import numpy as np
 
-from refrun import evap_of, rel_err
+from refrun import evap_of, has_et, rel_err
 
 STATE_FIELDS = ["NwtNew", "MuNew", "MiNew", "NtNew", "NfNew", "RuNew", "RiNew", "Qpin", "Qpout", "intstorm",
                 "srf", "hsrf", "sbsrf", "psrf", "esrf", "srf_hr", "cumsrf", "SoilMoisture", "SoilMoistureSC",
@@ -36,6 +36,7 @@ class GpuStepper:
     def advance(self):
         self.sim.advance()
         self.sim.UpdatePrecipitationInput()
+        self.sim.SurfaceHydroProcesses()
         if self.evap > 0.0:   # the harness's injected soil evaporation: EvapSoil = rate on dry steps
             r = self.sim.rain_schedule(self.time)
             want = 0.0 if r > 0.0 else self.evap
@@ -62,7 +63,13 @@ class GpuStepper:
         self.sim.hydro.Reset()
 
     def get(self, names):
-        return self.sim.dev.sync(names)
+        from tribs_b200.gpu import EF
+        main = [nm for nm in names if nm not in EF]
+        out = self.sim.dev.sync(main) if main else {}
+        et = [nm for nm in names if nm in EF]
+        if et:
+            out.update(self.sim.dev.et_sync(et))
+        return out
 
     def result(self, name):
         return self.sim.dev.results(name, self.limit)
@@ -79,6 +86,14 @@ class OracleStepper:
         self.boundary = np.asarray(basin["boundary"])
         self.stream_cells = np.nonzero(self.boundary == 3)[0].astype(np.int32)
         self.evap = evap_of(basin)
+        self.et = None
+        if has_et(basin):
+            from oracle.pyoracle import OracleET
+            from tribs_b200 import met
+            self.host = met.EvapoTransHost(basin)
+            self.et = OracleET(basin, self.m, self.host)
+            self.cal = met.Calendar(basin["timer_start"])
+            self.clock = met.MetClock(self.m.B.tstep, self.host.metstep, self.host.etistep)
 
     @property
     def time(self):
@@ -86,6 +101,13 @@ class OracleStepper:
 
     def advance(self):
         self.m.advance()
+        if self.et is not None:       # Simulator::SurfaceHydroProcesses, tSimul.cpp:419-461
+            self.cal.advance(self.m.time, self.m.B.tstep)
+            met_due, eti_due = self.clock.due(self.m.time)
+            if met_due:
+                self.et.potential(*self.host.potential_call(self.cal.hour, self.m.time))
+            if eti_due:
+                self.et.components(*self.host.components_call(self.m.time))
         if self.evap > 0.0:
             self.m.state["EvapSoil"][:] = np.where(self.m.state["Rain"] > 0.0, 0.0, self.evap)
 
@@ -107,7 +129,7 @@ class OracleStepper:
         self.m.reset()
 
     def get(self, names):
-        return {k: self.m.state[k] for k in names}
+        return {k: (self.m.state[k] if k in self.m.state else self.et.f[k]) for k in names}
 
     def result(self, name):
         return self.m.res[name]
@@ -115,6 +137,11 @@ class OracleStepper:
     def globals(self):
         from oracle.pyoracle import GLOBALS
         return dict(zip(GLOBALS, self.m.glob))
+
+
+# absolute floors of the relative comparison for ET fields that pass through zero (degC, W/m2)
+ET_FLOOR = {"SurfTemp": 1.0, "SoilTemp": 1.0, "AirTemp": 1.0, "DewTemp": 1.0, "NetRad": 1.0, "GFlux": 1.0,
+            "HFlux": 1.0, "LFlux": 1.0}
 
 
 class Worst:
@@ -143,6 +170,12 @@ def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True):
     hill = stepper.boundary == 0
     for st in range(1, n_steps + 1):
         stepper.advance()
+        pre = f"s{st}_m_"
+        if pre + "PotEvap" in snaps:
+            names = [k[len(pre):] for k in snaps if k.startswith(pre) and k != pre + "sun"]
+            got = stepper.get(names)
+            for f in names:
+                w.add(("m", f), snaps[pre + f], got[f], st, ET_FLOOR.get(f, floor))
         stepper.unsat()
         pre = f"s{st}_u_"
         if pre + "NwtNew" in snaps:

@@ -31,6 +31,9 @@ SCENARIOS = {
     "redistribute": dict(runtime_h=60.0, intstormmax=8.0, stdur=3.0, istdur=12.0, gw_depth_mm=1500.0),
     # net evaporation on dry steps (injected into tCNode::EvapSoil by the harness, EToption on):
     # water table dropping from the surface, interstorm drying below the initial profile
+    # rain gauges + one weather station: Penman-Monteith energy balance, Rutter interception
+    # (kernel 1) feeding the unsaturated zone through EvapSoil / EvapDryCanopy / NetPrecipitation
+    "met": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0),
     "evap": dict(runtime_h=72.0, gw_depth_mm=350.0, pmean=25.0, stdur=4.0, istdur=20.0, inject_evap=0.6),
 }
 
@@ -78,6 +81,19 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
 
 def storm_of(basin):
     return float(basin["_spec_pmean"][0]), float(basin["_spec_stdur"][0]), float(basin["_spec_istdur"][0])
+
+
+def schedule_for(basin):
+    """The rain forcing of a reference run as a callable of model time (scalar or per-cell mm/h)."""
+    if "rain_optStorm" in basin and not int(basin["rain_optStorm"][0]) and int(basin["rain_type"][0]) == 3:
+        from tribs_b200.met import GaugeRain
+        return GaugeRain(basin)
+    from oracle.pyoracle import stochastic_storm_schedule
+    return stochastic_storm_schedule(*storm_of(basin))
+
+
+def has_et(basin) -> bool:
+    return "et_option" in basin and int(basin["et_option"][0]) != 0
 
 
 def evap_of(basin) -> float:

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from common import STATE_FIELDS, GpuStepper, OracleStepper, run_and_compare
-from refrun import SCENARIOS, have_harness, load_golden, run_reference, spec_for, storm_of
+from refrun import SCENARIOS, have_harness, load_golden, run_reference, schedule_for, spec_for, storm_of
 
 pytestmark = pytest.mark.gpu
 
@@ -18,8 +18,7 @@ ABS_FLOOR = 1e-6   # fields are mm, mm/h, m3/s ...: 1e-6 relative to max(|ref|, 
 
 
 def _sched(basin):
-    from oracle.pyoracle import stochastic_storm_schedule
-    return stochastic_storm_schedule(*storm_of(basin))
+    return schedule_for(basin)
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))
@@ -32,12 +31,13 @@ def test_gpu_matches_reference_golden(name, built):
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
-@pytest.mark.parametrize("name,n,hours", [("deep", 40, 30.0), ("shallow", 32, 30.0), ("redistribute", 32, 40.0), ("evap", 32, 40.0)])
+@pytest.mark.parametrize("name,n,hours", [("deep", 40, 30.0), ("shallow", 32, 30.0), ("redistribute", 32, 40.0), ("evap", 32, 40.0), ("met", 32, 40.0)])
 def test_gpu_matches_live_reference(name, n, hours, built):
     """Larger basins: the reference binary itself runs on the box's CPU and is compared with."""
     spec = spec_for(name, n, runtime_h=hours, seed=3)
     n_steps = int(round(hours * 16))
-    basin, snaps, timing, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="ur")
+    basin, snaps, timing, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16,
+                                           phases="mur" if spec.forcing == "met" else "ur")
     w = run_and_compare(GpuStepper(basin, _sched(basin)), snaps, n_steps, floor=ABS_FLOOR)
     print(f"\n[{name} n={n}] cells={basin['n_active'][0]} worst:\n" + w.report(8))
     assert w.max() <= REL_TOL, w.report()

@@ -9,12 +9,11 @@ import numpy as np
 import pytest
 
 from common import OracleStepper, run_and_compare
-from refrun import SCENARIOS, have_harness, load_golden, run_reference, spec_for, storm_of
+from refrun import SCENARIOS, have_harness, load_golden, run_reference, schedule_for, spec_for, storm_of
 
 
 def _sched(basin):
-    from oracle.pyoracle import stochastic_storm_schedule
-    return stochastic_storm_schedule(*storm_of(basin))
+    return schedule_for(basin)
 
 
 @pytest.mark.parametrize("name", list(SCENARIOS))

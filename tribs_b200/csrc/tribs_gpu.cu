@@ -34,6 +34,7 @@
 #include <vector>
 
 #include "cell_update.cuh"
+#include "et_update.cuh"
 
 namespace cg = cooperative_groups;
 using namespace tribs;
@@ -66,6 +67,7 @@ struct PipeState;
 struct tribs_ctx {
   int device = 0;
   PipeState *pipe = nullptr;   // pipelined-batch state (tribs_gpu_run), created on first use
+  struct EtState *et = nullptr; // kernel (1) state (tribs_gpu_et_init)
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
   int max_degree = 0, segment_cells = 0;
   cudaStream_t stream = nullptr;
@@ -1001,6 +1003,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
 }
 
 // ------------------------------------------------------------------------------------ stepping
+static void tribs_free_et(tribs_ctx *c);
 static int check_sweep_abort(tribs_ctx *c) {
   int32_t flags[2] = {0, 0};
   CK(cudaMemcpyAsync(&flags[0], c->d_abort, 4, cudaMemcpyDeviceToHost, c->stream));
@@ -1168,6 +1171,220 @@ extern "C" int tribs_gpu_push(tribs_handle_t c, uint64_t field_mask, const tribs
   return 0;
 }
 
+
+// ====================================================================================
+// Kernel (1): ET + interception (tribs_gpu_et_*). See et_update.cuh for the cell update.
+struct EtState {
+  EtConst k{};
+  EtStatic st{};
+  EtView ev{};
+  double *d_met[2] = {nullptr, nullptr};        // [9][cap] packed records of the two met slots
+  int32_t *d_record[2] = {nullptr, nullptr};    // cell -> record, device order
+  bool have_record[2] = {false, false};
+  int met_cap = 0;
+  std::vector<double> h_met;
+  std::vector<int32_t> h_rec;
+};
+
+static void tribs_free_et(tribs_ctx *c) {
+  delete c->et;
+  c->et = nullptr;
+}
+
+__global__ void __launch_bounds__(128)
+et_cells_kernel(EtConst k, EtStatic st, EtStepDev s, EtView ev, DynView dv, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || st.boundary[i] < 0) return;
+  et_cell(k, st, s, ev, dv, i);
+}
+
+template <class T>
+static std::vector<T> to_device_order(tribs_ctx *c, const T *sweep, T pad) {
+  std::vector<T> v((size_t)c->n_pad, pad);
+  for (int d = 0; d < c->n_pad; d++) {
+    const int i = c->sweep_of_dev[d];
+    if (i >= 0) v[d] = sweep[i];
+  }
+  return v;
+}
+
+extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
+  if (!c || !p) return fail("tribs_gpu_et_init: null argument");
+  if (c->et) return fail("tribs_gpu_et_init: already initialised");
+  if (!p->flow_slope || !p->aspect || !p->vol_heat_cond || !p->soil_heat_cap || !p->soil_cutoff || !p->root_cutoff ||
+      !p->land_class || !p->land_table || p->n_land_classes <= 0)
+    return fail("tribs_gpu_et_init: missing per-cell arrays or land table");
+  if (p->et_option < 0 || p->et_option > 3) return fail("tribs_gpu_et_init: OPTEVAPOTRANS must be 0..3 (pan evaporation is not covered)");
+  if (p->i_option < 0 || p->i_option > 2) return fail("tribs_gpu_et_init: OPTINTERCEPT must be 0..2");
+  if (p->et_option && p->gflux_option != 1 && p->gflux_option != 2) return fail("tribs_gpu_et_init: GFLUXOPTION must be 1 or 2");
+  if (!(p->shelter_option == 0 || p->shelter_option >= 4)) return fail("tribs_gpu_et_init: OPTRADSHELT 1-3 (horizon angles) is not covered");
+  if (p->lu_option != 0) return fail("tribs_gpu_et_init: OPTLANDUSE 1 (dynamic land-use grids) is not covered");
+  if (p->snow_option != 0) return fail("tribs_gpu_et_init: OPTSNOW 1 is not covered");
+  if (p->et_option == 0 && p->i_option == 2) return fail("tribs_gpu_et_init: Rutter interception needs the evaporation scheme (tSimul.cpp:444-450)");
+  CK(cudaSetDevice(c->device));
+  const int n = c->n;
+  for (int i = 0; i < n; i++) {
+    if (p->land_class[i] < 0 || p->land_class[i] >= p->n_land_classes) return fail("tribs_gpu_et_init: land class out of range");
+    if (p->et_option && p->gflux_option == 2) {   // ForceRestore's validity check (tEvapoTrans.cpp:2683-2691)
+      const double w1 = 2. * (4.0 * atan(1.0)) / 86400.;
+      const double nd = 0.1 / pow((2.0 * (p->vol_heat_cond[i] / p->soil_heat_cap[i]) / w1), 0.5);
+      if (!(nd >= 0.0 && nd <= 5.0)) return fail("tribs_gpu_et_init: normalised depth of the force-restore equation out of 0..5");
+    }
+  }
+  EtState *e = new EtState();
+  c->et = e;
+  e->k.et_option = p->et_option; e->k.i_option = p->i_option; e->k.gflux_option = p->gflux_option;
+  e->k.shelter_option = p->shelter_option;
+  e->k.metstep_min = p->metstep_min; e->k.etistep_h = p->etistep_h; e->k.tlinke = p->tlinke;
+  e->k.temp_lapse = p->temp_lapse; e->k.max_interstorm = p->max_interstorm;
+  auto log_product = [](double veg) {            // numerator of aeroResist (tEvapoTrans.cpp:1464-1475)
+    const double zm = 2.0 + veg, zom = 0.123 * veg, zov = 0.0123 * veg, d = 0.67 * veg;
+    return log((zm - d) / zom) * log((zm - d) / zov);
+  };
+  e->k.ras_num = log_product(1.0);
+  {
+    const double T = p->tlinke;                  // DirectDiffuse, tEvapoTrans.cpp:1974-1984
+    e->k.tn_tlk = -0.015843 + 0.030543 * T + 0.0003797 * pow(T, 2.0);
+    const double a1p = 0.26463 - 0.061581 * T + 0.0031408 * pow(T, 2.0);
+    e->k.a1 = (a1p * e->k.tn_tlk < 0.0022) ? 0.0022 / e->k.tn_tlk : a1p;
+    e->k.a2 = 2.04020 + 0.018945 * T - 0.011161 * pow(T, 2.0);
+    e->k.a3 = -1.3025 + 0.039231 * T + 0.0085079 * pow(T, 2.0);
+  }
+  std::vector<LandClass> cls((size_t)p->n_land_classes);
+  for (int q = 0; q < p->n_land_classes; q++) {
+    const double *lp = p->land_table + (size_t)q * 15;
+    LandClass &L = cls[q];
+    L.A = lp[1]; L.B = lp[2]; L.P = lp[3]; L.S = lp[4]; L.K = lp[5]; L.b = lp[6];
+    L.Al = L.H = L.Kt = L.Rs = 0.0;
+    double V = 0.0;                              // setCoeffs, tEvapoTrans.cpp:915-952
+    if (p->et_option == 1) { L.Al = lp[7]; L.H = lp[8]; L.Kt = lp[9]; L.Rs = lp[10]; V = lp[11]; }
+    else if (p->et_option == 2 || p->et_option == 3) { L.Al = lp[7]; V = lp[11]; }
+    L.V_raw = lp[11];
+    L.V = (V >= 1.0) ? 0.99 : V;
+    L.SE = lp[13]; L.ST = lp[14];
+    L.rav_num = log_product(L.H == 0 ? 0.1 : L.H);
+  }
+  LandClass *d_cls = nullptr;
+  if (dev_upload(c, &d_cls, cls)) return 1;
+  e->st.classes = d_cls;
+  std::vector<double> cs(n), sn(n);
+  for (int i = 0; i < n; i++) {
+    const double slope = fabs(atan(p->flow_slope[i]));
+    cs[i] = cos(slope); sn[i] = sin(slope);
+  }
+  auto up = [&](const double *sweep, const double **dst) {
+    double *d = nullptr;
+    if (dev_upload(c, &d, to_device_order<double>(c, sweep, 0.0))) return 1;
+    *dst = d;
+    return 0;
+  };
+  if (up(cs.data(), &e->st.cos_slope) || up(sn.data(), &e->st.sin_slope) || up(p->aspect, &e->st.aspect) ||
+      up(p->vol_heat_cond, &e->st.heat_cond) || up(p->soil_heat_cap, &e->st.heat_cap) ||
+      up(p->soil_cutoff, &e->st.soil_cutoff) || up(p->root_cutoff, &e->st.root_cutoff)) return 1;
+  int32_t *d_lc = nullptr;
+  if (dev_upload(c, &d_lc, to_device_order<int32_t>(c, p->land_class, 0))) return 1;
+  e->st.land_class = d_lc;
+  e->st.z = c->sv.z; e->st.thr = c->sv.thr; e->st.bedrock = c->sv.bedrock;
+  e->st.boundary = c->sv.boundary; e->st.sweep_of_dev = c->d_sweep_of_dev;
+  for (int f = 0; f < TRIBS_N_ET_FIELDS; f++) {
+    const double *src = (p->init && p->init[f]) ? p->init[f] : nullptr;
+    double *d = nullptr;
+    if (src) { if (dev_upload(c, &d, to_device_order<double>(c, src, 0.0))) return 1; }
+    else {
+      if (dev_alloc(c, &d, (size_t)c->n_pad)) return 1;
+      CK(cudaMemset(d, 0, (size_t)c->n_pad * sizeof(double)));
+    }
+    e->ev.f[f] = d;
+  }
+  for (int sl = 0; sl < 2; sl++) if (dev_alloc(c, &e->d_record[sl], (size_t)c->n_pad)) return 1;
+  return 0;
+}
+
+// copies one tribs_met_t into met slot `sl`; the records travel as one packed block
+static int et_upload_met(tribs_ctx *c, int sl, const tribs_met_t *m, MetDev *out) {
+  EtState *e = c->et;
+  if (!m || m->n_records <= 0) return fail("tribs_gpu_et_step: met record missing");
+  const double *src[9] = {m->air_temp, m->dew_temp, m->rel_humid, m->vap_press, m->atm_press,
+                          m->wind_speed, m->sky_cover, m->rad_global, m->elev};
+  for (int q = 0; q < 9; q++) if (!src[q]) return fail("tribs_gpu_et_step: met series missing");
+  const int nr = m->n_records;
+  if (nr > e->met_cap) {
+    for (int q = 0; q < 2; q++) if (dev_alloc(c, &e->d_met[q], (size_t)9 * nr)) return 1;
+    e->met_cap = nr;
+  }
+  e->h_met.resize((size_t)9 * nr);
+  for (int q = 0; q < 9; q++) memcpy(e->h_met.data() + (size_t)q * nr, src[q], (size_t)nr * sizeof(double));
+  CK(cudaMemcpyAsync(e->d_met[sl], e->h_met.data(), e->h_met.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (m->cell_record) {
+    for (int i = 0; i < c->n; i++)
+      if (m->cell_record[i] < 0 || m->cell_record[i] >= nr) return fail("tribs_gpu_et_step: cell_record out of range");
+    e->h_rec = to_device_order<int32_t>(c, m->cell_record, 0);
+    CK(cudaMemcpyAsync(e->d_record[sl], e->h_rec.data(), e->h_rec.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    e->have_record[sl] = true;
+  } else if (!e->have_record[sl]) return fail("tribs_gpu_et_step: cell_record not given yet");
+  CK(cudaStreamSynchronize(c->stream));          // the host staging vectors are reused by the next call
+  double *b = e->d_met[sl];
+  out->cell_record = e->d_record[sl];
+  out->air_temp = b; out->dew_temp = b + nr; out->rel_humid = b + 2 * (size_t)nr; out->vap_press = b + 3 * (size_t)nr;
+  out->atm_press = b + 4 * (size_t)nr; out->wind_speed = b + 5 * (size_t)nr; out->sky_cover = b + 6 * (size_t)nr;
+  out->rad_global = b + 7 * (size_t)nr; out->elev = b + 8 * (size_t)nr;
+  return 0;
+}
+
+extern "C" int tribs_gpu_et_step(tribs_handle_t c, const tribs_et_step_t *s) {
+  if (!c || !s) return fail("tribs_gpu_et_step: null argument");
+  if (!c->et) return fail("tribs_gpu_et_step: call tribs_gpu_et_init first");
+  if (!s->do_potential && !s->do_components) return 0;
+  if (s->hour < 0 || s->hour > 23) return fail("tribs_gpu_et_step: hour out of range");
+  CK(cudaSetDevice(c->device));
+  EtState *e = c->et;
+  static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014,   // stomResist, tEvapoTrans.cpp:1494-1496
+                                     0.995, 0.976, 0.976, 1.0, 1.053, 1.167, 1.354, 1.637,
+                                     2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
+  EtStepDev d{};
+  d.do_potential = s->do_potential && e->k.et_option; d.do_components = s->do_components; d.intercept_flag = s->intercept_flag;
+  d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
+  d.cos_alpha = cos(asin(s->sinAlpha));
+  d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
+  d.sky_flag_from = s->sky_flag_from; d.te_met = s->te_met; d.te_eti = s->te_eti;
+  d.rs_ratio = rsRatio[s->hour];
+  if (d.do_potential && et_upload_met(c, 0, s->met_potential, &d.pot)) return 1;
+  if (d.do_components && e->k.et_option && et_upload_met(c, 1, s->met_components, &d.cmp)) return 1;
+  if (!d.do_potential && !d.do_components) return 0;
+  et_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, e->ev, c->dv, c->n_pad);
+  c->launches++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tribs_gpu_et_sync(tribs_handle_t c, uint64_t mask, double *const *host) {
+  if (!c || !host) return fail("tribs_gpu_et_sync: null argument");
+  if (!c->et) return fail("tribs_gpu_et_sync: call tribs_gpu_et_init first");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < TRIBS_N_ET_FIELDS; k++) {
+    if (!(mask & (1ull << k)) || !host[k]) continue;
+    gather_to_sweep_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->et->ev.f[k], c->d_dev_of_sweep, c->d_stage, c->n);
+    c->launches++;
+    CK(cudaMemcpyAsync(host[k], c->d_stage, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+extern "C" int tribs_gpu_et_push(tribs_handle_t c, uint64_t mask, const double *const *host) {
+  if (!c || !host) return fail("tribs_gpu_et_push: null argument");
+  if (!c->et) return fail("tribs_gpu_et_push: call tribs_gpu_et_init first");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < TRIBS_N_ET_FIELDS; k++) {
+    if (!(mask & (1ull << k)) || !host[k]) continue;
+    CK(cudaMemcpyAsync(c->d_stage, host[k], (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    scatter_from_sweep_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->d_stage, c->d_dev_of_sweep, c->et->ev.f[k], c->n);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
 extern "C" int tribs_gpu_n_stream(tribs_handle_t c) { return c ? c->n_stream : -1; }
 extern "C" int tribs_gpu_stream_cells(tribs_handle_t c, int32_t *out) {
   if (!c || !out) return fail("tribs_gpu_stream_cells: null argument");
@@ -1328,6 +1545,7 @@ extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   for (void *p : c->allocs) cudaFree(p);
   cudaStreamDestroy(c->stream);
   tribs_free_pipe(c);
+  tribs_free_et(c);
   delete c;
   return 0;
 }

@@ -34,8 +34,16 @@ def _enum_from_header(prefix: str) -> list[str]:
     return out
 
 
+def _et_fields_from_header() -> list[str]:
+    src = open(HEADER).read()
+    m = re.search(r"#define TRIBS_ET_FIELDS\(X\) \\\n((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
 FIELDS = _fields_from_header()
 F = {nm: k for k, nm in enumerate(FIELDS)}
+ET_FIELDS = _et_fields_from_header()
+EF = {nm: k for k, nm in enumerate(ET_FIELDS)}
 RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac",
            "msm", "msmRt", "msmU", "mgw", "sat", "qunsat"]
 GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last"]
@@ -81,12 +89,36 @@ class Step(C.Structure):
                 ("qstrm_outlet", C.c_double)]
 
 
+class EtParams(C.Structure):
+    _fields_ = [("flow_slope", PD), ("aspect", PD), ("vol_heat_cond", PD), ("soil_heat_cap", PD),
+                ("soil_cutoff", PD), ("root_cutoff", PD), ("land_class", PI), ("n_land_classes", C.c_int32),
+                ("land_table", PD), ("et_option", C.c_int32), ("i_option", C.c_int32), ("gflux_option", C.c_int32),
+                ("shelter_option", C.c_int32), ("lu_option", C.c_int32), ("snow_option", C.c_int32),
+                ("metstep_min", C.c_double), ("etistep_h", C.c_double), ("tlinke", C.c_double),
+                ("temp_lapse", C.c_double), ("max_interstorm", C.c_double), ("init", C.POINTER(PD))]
+
+
+class MetT(C.Structure):
+    _fields_ = [("n_records", C.c_int32), ("cell_record", PI), ("air_temp", PD), ("dew_temp", PD), ("rel_humid", PD),
+                ("vap_press", PD), ("atm_press", PD), ("wind_speed", PD), ("sky_cover", PD), ("rad_global", PD),
+                ("elev", PD)]
+
+
+class EtStep(C.Structure):
+    _fields_ = [("do_potential", C.c_int32), ("do_components", C.c_int32), ("intercept_flag", C.c_int32),
+                ("alphaD", C.c_double), ("sinAlpha", C.c_double), ("sunaz", C.c_double), ("Io", C.c_double),
+                ("hour", C.c_int32), ("first_call", C.c_int32), ("dew_hum_flag", C.c_int32), ("ts_option", C.c_int32),
+                ("sky_flag_from", C.c_int32), ("te_met", C.c_double), ("te_eti", C.c_double),
+                ("met_potential", C.POINTER(MetT)), ("met_components", C.POINTER(MetT))]
+
+
 EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
            "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
-           "tribs_gpu_padded_cells", "tribs_gpu_last_error", "tribs_gpu_abi_version"]
+           "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
+           "tribs_gpu_last_error", "tribs_gpu_abi_version"]
 
 _lib = None
 
@@ -122,6 +154,10 @@ def load():
     L.tribs_gpu_stream.argtypes = [H]
     L.tribs_gpu_stream.restype = C.c_void_p
     L.tribs_gpu_destroy.argtypes = [H]
+    L.tribs_gpu_et_init.argtypes = [H, C.POINTER(EtParams)]
+    L.tribs_gpu_et_step.argtypes = [H, C.POINTER(EtStep)]
+    L.tribs_gpu_et_sync.argtypes = [H, C.c_uint64, C.POINTER(PD)]
+    L.tribs_gpu_et_push.argtypes = [H, C.c_uint64, C.POINTER(PD)]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -269,6 +305,89 @@ class GpuBasin:
             st.f[F[nm]] = _d(a)
             mask |= 1 << F[nm]
         _chk(self.L.tribs_gpu_push(self.h, mask, C.byref(st)))
+
+    # -- kernel (1): ET + interception --------------------------------------------------------
+    _MET_KEYS = (("air_temp", "airTemp"), ("dew_temp", "dewTemp"), ("rel_humid", "rHumidity"), ("vap_press", "vPress"),
+                 ("atm_press", "atmPress"), ("wind_speed", "windSpeed"), ("sky_cover", "skyCover"),
+                 ("rad_global", "radGlobal"))
+
+    def et_init(self, basin: dict):
+        """tribs_gpu_et_init from a flattened basin (keys as dumped by the reference harness)."""
+        b, keep = basin, []
+        p = EtParams()
+        for member, key in (("flow_slope", "flow_slope"), ("aspect", "aspect"), ("vol_heat_cond", "VolHeatCond"),
+                            ("soil_heat_cap", "SoilHeatCap"), ("soil_cutoff", "soil_cutoff"), ("root_cutoff", "root_cutoff")):
+            a = np.ascontiguousarray(b[key], np.float64); keep.append(a); setattr(p, member, _d(a))
+        lc = np.ascontiguousarray(b["land_class"], np.int32); keep.append(lc); p.land_class = _i(lc)
+        lt = np.ascontiguousarray(b["land_table"], np.float64); keep.append(lt); p.land_table = _d(lt)
+        p.n_land_classes = lt.size // 15
+        p.et_option = int(b["et_option"][0]); p.i_option = int(b["et_Ioption"][0])
+        p.gflux_option = int(b["et_gFluxOption"][0]); p.shelter_option = int(b["et_shelterOption"][0])
+        p.lu_option = int(b["et_luOption"][0]); p.snow_option = int(b["et_snowOption"][0])
+        p.metstep_min = float(b["et_timeStep"][0]); p.etistep_h = float(b["etistep"][0])
+        p.tlinke = float(b["et_Tlinke"][0]); p.temp_lapse = float(b["et_tempLapseRate"][0])
+        p.max_interstorm = float(b["icp_maxInterStormPeriod"][0])
+        init = (PD * len(ET_FIELDS))()
+        for k, nm in enumerate(ET_FIELDS):
+            src = b.get("init_" + nm)
+            if src is not None:
+                a = np.ascontiguousarray(src, np.float64); keep.append(a); init[k] = _d(a)
+        p.init = C.cast(init, C.POINTER(PD))
+        _chk(self.L.tribs_gpu_et_init(self.h, C.byref(p)))
+        self._et_flag = int(p.i_option != 0)
+
+    def _met(self, rec: dict, cell_record, elev, keep):
+        m = MetT()
+        m.n_records = len(elev)
+        if cell_record is not None:
+            cr = np.ascontiguousarray(cell_record, np.int32); keep.append(cr); m.cell_record = _i(cr)
+        for member, key in self._MET_KEYS:
+            a = np.ascontiguousarray(rec[key], np.float64); keep.append(a); setattr(m, member, _d(a))
+        el = np.ascontiguousarray(elev, np.float64); keep.append(el); m.elev = _d(el)
+        return m
+
+    def et_step(self, potential=None, components=None, cell_record=None, elev=None):
+        """One call of kernel (1). *potential* / *components* are (step dict, record dict) pairs as
+        produced by tribs_b200.met.EvapoTransHost, or None when that sweep is not due."""
+        if potential is None and components is None:
+            return
+        keep = []
+        base = (potential or components)[0]
+        s = EtStep()
+        for k in ("alphaD", "sinAlpha", "sunaz", "Io", "hour", "dew_hum_flag", "ts_option"):
+            setattr(s, k, base[k])
+        s.sky_flag_from = base["sky_flag_from"]
+        s.intercept_flag = self._et_flag
+        if potential is not None:
+            st, rec = potential
+            s.do_potential = 1
+            s.first_call, s.te_met, s.sky_flag_from = st["first_call"], st["te_met"], st["sky_flag_from"]
+            mp = self._met(rec, cell_record, elev, keep)
+            s.met_potential = C.pointer(mp)
+        if components is not None:
+            st, rec = components
+            s.do_components = 1
+            s.te_eti = st["te_eti"]
+            mc = self._met(rec, cell_record, elev, keep)
+            s.met_components = C.pointer(mc)
+        _chk(self.L.tribs_gpu_et_step(self.h, C.byref(s)))
+
+    def et_sync(self, names) -> dict:
+        out = {nm: np.empty(self.n) for nm in names}
+        ptrs = (PD * len(ET_FIELDS))()
+        mask = 0
+        for nm in names:
+            ptrs[EF[nm]] = _d(out[nm]); mask |= 1 << EF[nm]
+        _chk(self.L.tribs_gpu_et_sync(self.h, mask, C.cast(ptrs, C.POINTER(PD))))
+        return out
+
+    def et_push(self, arrays: dict):
+        ptrs = (PD * len(ET_FIELDS))()
+        mask, keep = 0, []
+        for nm, a in arrays.items():
+            a = np.ascontiguousarray(a, np.float64); keep.append(a)
+            ptrs[EF[nm]] = _d(a); mask |= 1 << EF[nm]
+        _chk(self.L.tribs_gpu_et_push(self.h, mask, C.cast(ptrs, C.POINTER(PD))))
 
     def retrieve_qeff(self, current_time: float) -> np.ndarray:
         out = np.empty(self.n_stream + 1)

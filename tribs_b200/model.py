@@ -13,7 +13,7 @@ import math
 
 import numpy as np
 
-from . import gpu
+from . import gpu, met
 
 
 class tRunTimer:
@@ -23,9 +23,23 @@ class tRunTimer:
         self.tstep, self.gwstep, self.etistep, self.endTime = tstep_h, gwstep_h, etistep_h, end_h
         self.currentTime = 0.0
 
+        self.calendar = None        # met.Calendar once a start date is known
+
     def Advance(self, dt):
         self.currentTime += dt
+        if self.calendar is not None:
+            self.calendar.advance(self.currentTime, dt)
         return self.currentTime < self.endTime
+
+    @property
+    def hour(self):
+        return self.calendar.hour if self.calendar is not None else 0
+
+    def getElapsedMETSteps(self, t):
+        return int(t / self.metstep)
+
+    def getElapsedETISteps(self, t):
+        return int(t / self.etistep)
 
     def IsFinished(self):
         return self.currentTime >= self.endTime
@@ -76,6 +90,57 @@ class tHydroModel:
         self.dev.step(gpu.PHASE_RESET, now, el, hr)
 
 
+class tIntercept:
+    """Only the option query the simulator makes (tIntercept.cpp:555-563); the interception
+    models themselves run inside tEvapoTrans.callEvapoTrans on the device."""
+
+    def __init__(self, basin: dict):
+        self.interceptOption = int(basin["et_Ioption"][0]) if "et_Ioption" in basin else 0
+
+    def getIoption(self):
+        return self.interceptOption
+
+
+class tEvapoTrans:
+    """callEvapoPotential / callEvapoTrans forwarded to kernel (1). The per-call members of the
+    reference class (met clock, sun geometry, record-0 decisions) live in met.EvapoTransHost."""
+
+    def __init__(self, dev: gpu.GpuBasin, timer: tRunTimer, basin: dict):
+        self.dev, self.timer = dev, timer
+        self.evapotransOption = int(basin["et_option"][0]) if "et_option" in basin else 0
+        self.host = None
+        self._pending = None
+        if self.evapotransOption:
+            if int(basin["rain_optStorm"][0]):
+                raise NotImplementedError("stochastic weather generator (tHydroMetStoch) is not part of the path")
+            if int(basin["et_metdataOption"][0]) != 1:
+                raise NotImplementedError("only METDATAOPTION 1 (stations) is wired on the host side")
+            self.host = met.EvapoTransHost(basin)
+            timer.metstep = self.host.metstep
+            timer.calendar = met.Calendar(basin["timer_start"])
+            dev.et_init(basin)
+
+    def getEToption(self):
+        return self.evapotransOption
+
+    def callEvapoPotential(self):
+        """Queues the potential-evaporation sweep; it is launched together with callEvapoTrans when
+        both are due in the same step (the usual case), otherwise by flush()."""
+        self._pending = self.host.potential_call(self.timer.hour, self.timer.getCurrentTime())
+
+    def callEvapoTrans(self, intercept: tIntercept, flag: int):
+        comp = self.host.components_call(self.timer.getCurrentTime())
+        self.dev.et_step(potential=self._pending, components=comp,
+                         cell_record=self.host.cell_record, elev=self.host.elev)
+        self._pending = None
+
+    def flush(self):
+        if self._pending is not None:
+            self.dev.et_step(potential=self._pending, components=None,
+                             cell_record=self.host.cell_record, elev=self.host.elev)
+            self._pending = None
+
+
 class tKinemat:
     """SurfaceFlow(): hillslope routing + basin accumulations on the GPU; the kinematic-wave
     channel solver stays with the host model and consumes `lateral_inflow`."""
@@ -101,6 +166,9 @@ class Simulator:
                                float(b["endtime"][0]))
         self.hydro = tHydroModel(self.dev, self.timer)
         self.flow = tKinemat(self.dev, self.timer)
+        self.intercept = tIntercept(b)
+        self.evapotrans = tEvapoTrans(self.dev, self.timer, b)
+        self.met_clock = met.MetClock(self.timer.tstep, float(b["metstep"][0]) if "metstep" in b else self.timer.etistep, self.timer.etistep)
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
         self.step_no = 0
@@ -111,6 +179,19 @@ class Simulator:
         r = self.rain_schedule(self.timer.getCurrentTime())
         now = self.timer.getCurrentTime()
         self.dev.step(0, now, self.timer.getElapsedSteps(now), 0, rain=r)
+
+    def SurfaceHydroProcesses(self):
+        """tSimul.cpp:419-498 without the snow branch: which of the two ET sweeps are due."""
+        met_due, eti_due = self.met_clock.due(self.timer.getCurrentTime())
+        et, icp = self.evapotrans, self.intercept
+        if et.getEToption() != 0:
+            if met_due:
+                et.callEvapoPotential()
+            if eti_due:
+                et.callEvapoTrans(icp, 1 if icp.getIoption() != 0 else 0)
+            et.flush()
+        elif icp.getIoption() != 0:
+            raise NotImplementedError("interception without the evaporation scheme needs tEvapoTrans' land data wiring")
 
     def SubSurfaceHydroProcesses(self):
         t = self.timer
@@ -129,6 +210,7 @@ class Simulator:
     def one_step(self, fetch_qeff=True):
         self.advance()
         self.UpdatePrecipitationInput()
+        self.SurfaceHydroProcesses()
         did_gw = self.SubSurfaceHydroProcesses()
         self.flow.SurfaceFlow(fetch_qeff)
         self.hydro.Reset()
