@@ -31,6 +31,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 METRIC = "voronoi_cell_timesteps_per_sec"
 UNIT = "cell-timesteps/s"
 # compulsory bytes per cell and invocation of the dominant kernel (unsat sweep)
+ET_BYTES_PER_CELL = 548.0      # 236 B read + 312 B written per cell per fused ET call
 UNSAT_BYTES_PER_CELL = 520.0
 SAT_BYTES_PER_CELL = 710.0
 STEP_BYTES_PER_CELL = 677.0      # whole step, storm-only configuration
@@ -267,6 +268,8 @@ def run_gpu(args):
                              f"({dev.levels()} levels per step) times the FP64 latency of one column update; see DESIGN.md"},
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
+    if world == 1 and not args.no_et_kernel:
+        line["kernels"] = {"et_cells_kernel": time_et_kernel(dev, basin, n, stream, peak)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample()
     if rank == 0:
@@ -274,6 +277,48 @@ def run_gpu(args):
     dev.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def time_et_kernel(dev, basin, n, stream, peak, calls=24):
+    """Kernel (1) timed alone on the state the water-balance run left behind: one fused
+    potential-evaporation + ET-partition + Rutter-interception sweep per call (what the reference
+    does once per METSTEP), daytime and raining so that every branch works. Reported next to the
+    headline because it is the path's streaming, dependency-free kernel."""
+    import numpy as np
+    import torch
+    from tribs_b200 import met
+    from tribs_b200.synthbasin import add_met_forcing
+    add_met_forcing(basin)
+    dev.et_init(basin)
+    host = met.EvapoTransHost(basin)
+    rain = np.full(dev.n, 6.0)
+    dev.step(0, 0.0625, 1, 0, rain=rain)
+
+    def call(hour):
+        pot = host.potential_call(hour % 24, 0.0625 + hour)
+        cmp_ = host.components_call(0.0625 + hour)
+        dev.et_step(potential=pot, components=cmp_, cell_record=host.cell_record, elev=host.elev)
+
+    for h in range(3):
+        call(h)
+    host.hourlyTimeStep = 10            # mid-morning records: sun up
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ms = 0.0
+    for h in range(calls):
+        host.hourlyTimeStep = 10 + (h % 6)
+        pot = host.potential_call(10 + (h % 6), 10.0625 + h)
+        cmp_ = host.components_call(10.0625 + h)
+        e0.record(stream)
+        dev.et_step(potential=pot, components=cmp_, cell_record=None, elev=host.elev)
+        e1.record(stream)
+        dev.wait()
+        ms += e0.elapsed_time(e1)
+    ms /= calls
+    gbs = n * ET_BYTES_PER_CELL / (ms * 1e-3) / 1e9
+    return {"avg_launch_ms": ms, "bytes_per_cell_call": ET_BYTES_PER_CELL, "achieved": gbs, "unit": "GB/s",
+            "frac": gbs / peak if peak else None, "cells_per_s": n / (ms * 1e-3),
+            "note": "includes the H2D copy of the hour's station records (72 B per station) issued inside the call"}
 
 
 # -------------------------------------------------------------------------------- CPU arms
@@ -391,6 +436,7 @@ def main():
     ap.add_argument("--side-mgpu", type=int, default=500, help="N>1, partition mode: cells across the valley; "
                     "the basin is side x side*N cells, i.e. side^2 per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-et-kernel", action="store_true", help="skip the separate timing of kernel (1)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)

@@ -1182,11 +1182,21 @@ struct EtState {
   int32_t *d_record[2] = {nullptr, nullptr};    // cell -> record, device order
   bool have_record[2] = {false, false};
   int met_cap = 0;
-  std::vector<double> h_met;
+  // pinned staging ring for the records: a buffer is reused only after its copy has completed
+  static constexpr int kRing = 4;
+  double *h_pin[2][kRing] = {};
+  cudaEvent_t pin_ev[2][kRing] = {};
+  int pin_cap = 0, gen = 0;
   std::vector<int32_t> h_rec;
 };
 
 static void tribs_free_et(tribs_ctx *c) {
+  if (!c->et) return;
+  for (int sl = 0; sl < 2; sl++)
+    for (int g = 0; g < EtState::kRing; g++) {
+      if (c->et->h_pin[sl][g]) cudaFreeHost(c->et->h_pin[sl][g]);
+      if (c->et->pin_ev[sl][g]) cudaEventDestroy(c->et->pin_ev[sl][g]);
+    }
   delete c->et;
   c->et = nullptr;
 }
@@ -1312,17 +1322,30 @@ static int et_upload_met(tribs_ctx *c, int sl, const tribs_met_t *m, MetDev *out
     for (int q = 0; q < 2; q++) if (dev_alloc(c, &e->d_met[q], (size_t)9 * nr)) return 1;
     e->met_cap = nr;
   }
-  e->h_met.resize((size_t)9 * nr);
-  for (int q = 0; q < 9; q++) memcpy(e->h_met.data() + (size_t)q * nr, src[q], (size_t)nr * sizeof(double));
-  CK(cudaMemcpyAsync(e->d_met[sl], e->h_met.data(), e->h_met.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  if (nr > e->pin_cap) {
+    CK(cudaStreamSynchronize(c->stream));
+    for (int a = 0; a < 2; a++)
+      for (int g = 0; g < EtState::kRing; g++) {
+        if (e->h_pin[a][g]) CK(cudaFreeHost(e->h_pin[a][g]));
+        CK(cudaHostAlloc((void **)&e->h_pin[a][g], (size_t)9 * nr * sizeof(double), cudaHostAllocDefault));
+        if (!e->pin_ev[a][g]) CK(cudaEventCreateWithFlags(&e->pin_ev[a][g], cudaEventDisableTiming));
+      }
+    e->pin_cap = nr;
+  }
+  const int g = e->gen % EtState::kRing;
+  CK(cudaEventSynchronize(e->pin_ev[sl][g]));
+  double *hp = e->h_pin[sl][g];
+  for (int q = 0; q < 9; q++) memcpy(hp + (size_t)q * nr, src[q], (size_t)nr * sizeof(double));
+  CK(cudaMemcpyAsync(e->d_met[sl], hp, (size_t)9 * nr * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  CK(cudaEventRecord(e->pin_ev[sl][g], c->stream));
   if (m->cell_record) {
     for (int i = 0; i < c->n; i++)
       if (m->cell_record[i] < 0 || m->cell_record[i] >= nr) return fail("tribs_gpu_et_step: cell_record out of range");
     e->h_rec = to_device_order<int32_t>(c, m->cell_record, 0);
     CK(cudaMemcpyAsync(e->d_record[sl], e->h_rec.data(), e->h_rec.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));        // h_rec is reused by the next call
     e->have_record[sl] = true;
   } else if (!e->have_record[sl]) return fail("tribs_gpu_et_step: cell_record not given yet");
-  CK(cudaStreamSynchronize(c->stream));          // the host staging vectors are reused by the next call
   double *b = e->d_met[sl];
   out->cell_record = e->d_record[sl];
   out->air_temp = b; out->dew_temp = b + nr; out->rel_humid = b + 2 * (size_t)nr; out->vap_press = b + 3 * (size_t)nr;
@@ -1353,6 +1376,7 @@ extern "C" int tribs_gpu_et_step(tribs_handle_t c, const tribs_et_step_t *s) {
   if (!d.do_potential && !d.do_components) return 0;
   et_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, e->ev, c->dv, c->n_pad);
   c->launches++;
+  e->gen++;
   CK(cudaGetLastError());
   return 0;
 }

@@ -172,6 +172,7 @@ class Simulator:
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
         self.step_no = 0
+        self._rain_on_device = None
 
     def UpdatePrecipitationInput(self):
         if self.rain_schedule is None:
@@ -216,12 +217,26 @@ class Simulator:
         self.hydro.Reset()
         return did_gw
 
-    def run_batch(self, k: int, rain_of_time=None, per_cell_rain=None):
-        """k whole steps in one pipelined launch (tribs_gpu_run). The host-side decisions of
-        every step (GW due, hourly reset, elapsed steps, rain) are taken here exactly as
-        one_step() would take them, then handed down together."""
+    def run_batch(self, k: int, rain_of_time=None, per_cell_rain=None, collect_qeff: bool = False):
+        """k whole steps in pipelined launches (tribs_gpu_run). The host-side decisions of every
+        step (GW due, hourly reset, elapsed steps, rain) are taken here exactly as one_step()
+        would take them, then handed down together. With the evaporation scheme on, a batch ends
+        where SurfaceHydroProcesses changes the inputs of the sweep (every METSTEP / ET-I step):
+        kernel (1) runs there and the next launch starts with that step."""
         t = self.timer
-        steps = []
+        steps, out = [], []
+        et_on = self.evapotrans.getEToption() != 0
+
+        qeff = []
+
+        def flush():
+            if steps:
+                self.dev.run(steps)
+                if collect_qeff:      # per-step lateral inflows for the channel router
+                    qeff.append(self.dev.retrieve_qeff_steps(len(steps)))
+                out.extend(steps)
+                steps.clear()
+
         for _ in range(k):
             self.advance()
             now = t.getCurrentTime()
@@ -230,11 +245,30 @@ class Simulator:
             if per_cell_rain is not None:
                 per_cell_rain.fill(0.0 if rain is None else rain)
                 rain = per_cell_rain.copy()
+            # a per-cell array object that has not changed since the last upload stays on the device
+            step_rain = rain
+            if isinstance(rain, np.ndarray) and per_cell_rain is None:
+                step_rain = None if rain is self._rain_on_device else rain
+                self._rain_on_device = rain
+            if et_on:
+                met_due, eti_due = self.met_clock.due(now)
+                if met_due or eti_due:
+                    flush()
+                    if step_rain is not None:      # the ET sweep reads the Rain array of this step
+                        self.dev.step(0, now, t.getElapsedSteps(now), 0, rain=step_rain)
+                        step_rain = None if isinstance(rain, np.ndarray) else step_rain
+                    if met_due:
+                        self.evapotrans.callEvapoPotential()
+                    if eti_due:
+                        self.evapotrans.callEvapoTrans(self.intercept, 1 if self.intercept.getIoption() != 0 else 0)
+                    self.evapotrans.flush()
             steps.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
                               hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
-                              sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())), rain=rain))
-        self.dev.run(steps)
-        return steps
+                              sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())),
+                              rain=step_rain))
+        flush()
+        self.batch_qeff = np.concatenate(qeff) if qeff else None
+        return out
 
     def simulation_loop(self, max_steps=None):
         k = 0

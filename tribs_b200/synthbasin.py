@@ -262,3 +262,44 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         "init_MiOld": mi0.copy(), "init_MiNew": mi0.copy(),
     }
     return basin
+
+
+def add_met_forcing(basin: dict, hours: int = 48, et_option: int = 1, i_option: int = 2) -> dict:
+    """Adds what kernel (1) needs to a synthetic basin: one land class, per-cell thermal soil
+    properties and aspect, one weather station with the hourly series of synth.met_series.
+    Keys follow the reference-harness dump so GpuBasin.et_init / met.EvapoTransHost read them."""
+    from .synth import BasinSpec, met_series
+    n = int(basin["n_active"][0])
+    spec = BasinSpec(runtime_h=float(hours), forcing="met", pmean=12.0, stdur=5.0)
+    _, met = met_series(spec)
+    nt = len(met)
+    cols = np.array(met)                      # PA RH XC US TA IS
+    xc = 0.5 * (basin["x"].min() + basin["x"].max())
+    land = np.zeros((2, 15))
+    land[1, 1:] = spec.land
+    nd = np.full(nt, 9999.99)
+    basin.update({
+        "aspect": np.where(basin["x"] < xc, 0.5 * np.pi, 1.5 * np.pi),
+        "VolHeatCond": np.full(n, spec.soil[9]), "SoilHeatCap": np.full(n, spec.soil[10]),
+        "soil_cutoff": basin["ThetaR"] + 1e-3, "root_cutoff": basin["ThetaR"] + 1e-3,
+        "land_class": np.ones(n, np.int32), "land_table": land.ravel(),
+        "et_option": np.array([et_option], np.int32), "et_Ioption": np.array([i_option], np.int32),
+        "et_metdataOption": np.array([1], np.int32), "et_gFluxOption": np.array([2], np.int32),
+        "et_luOption": np.array([0], np.int32), "et_snowOption": np.array([0], np.int32),
+        "et_shelterOption": np.array([0], np.int32), "et_timeStep": np.array([60.0]),
+        "et_Tlinke": np.array([2.5]), "et_tempLapseRate": np.array([-0.0065]),
+        "icp_maxInterStormPeriod": np.array([5000.0]), "icp_option": np.array([i_option], np.int32),
+        "rain_type": np.array([3], np.int32), "rain_optStorm": np.array([0], np.int32),
+        "met_n_stations": np.array([1], np.int32), "met_station_id": np.array([1], np.int32),
+        "met_gmt": np.array([-7], np.int32), "met_n_times": np.array([nt], np.int32),
+        "met_n_params": np.array([11], np.int32), "met_lat": np.array([34.0]), "met_long": np.array([-107.0]),
+        "met_other": np.array([float(basin["z"].mean())]),
+        "met_airTemp": cols[:, 4].copy(), "met_dewTemp": nd.copy(), "met_surfTemp": nd.copy(),
+        "met_rHumidity": cols[:, 1].copy(), "met_vPress": nd.copy(), "met_atmPress": cols[:, 0].copy(),
+        "met_windSpeed": cols[:, 3].copy(), "met_skyCover": cols[:, 2].copy(), "met_radGlobal": cols[:, 5].copy(),
+        "met_calendar": np.array([[2000, 6, 1 + h // 24, h % 24] for h in range(nt)], np.int32).ravel(),
+        "met_assigned_station": np.ones(n, np.int32), "met_tsOption": np.array([2], np.int32),
+        "met_vapOption": np.array([1], np.int32), "timer_start": np.array([2000, 6, 1, 0, 0], np.int32),
+        "EToption": np.array([et_option], np.int32), "Ioption": np.array([i_option], np.int32),
+    })
+    return basin
