@@ -713,6 +713,8 @@ int main(int argc, char **argv) {
     TribsGpuBinding gpu;
     const bool use_gpu = !gpu_lib.empty();
     if (use_gpu) gpu.attach(&BasinMesh, &Flow, &Moisture, &Timer, gpu_lib.c_str());
+    const bool gpu_et = use_gpu && EvapoTrans.getEToption() != 0 && SnowPack.getSnowOpt() == 0;
+    if (gpu_et) gpu.attachET(&EvapoTrans, &Intercept, &Moisture);
     vector<double> qout_series;
 
     std::unique_ptr<TrbWriter> sw;
@@ -729,7 +731,14 @@ int main(int argc, char **argv) {
         double t0 = now_s();
         Timer.Advance(Timer.getTimeStep());
         Sim.UpdatePrecipitationInput(Rainfall.getoptStorm());
-        Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
+        if (gpu_et) {   // Simulator::SurfaceHydroProcesses (tSimul.cpp:419-461) with the two cell loops on the GPU
+            Sim.get_next_met();
+            if (Timer.getCurrentTime() == Sim.met_hour) gpu.callEvapoPotential();
+            if (Timer.getCurrentTime() == Sim.eti_hour) gpu.callEvapoTrans(Intercept.getIoption() != 0);
+            gpu.flushET();
+            if (snap && phases.find('m') != string::npos) gpu.syncEtToNodes();
+        } else
+            Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
         if (inject_evap > 0.0)
             for (tCNode *cn : H.cells) cn->setEvapSoil(cn->getRain() > 0.0 ? 0.0 : inject_evap);
         if (snap && phases.find('m') != string::npos) {
@@ -780,7 +789,15 @@ int main(int argc, char **argv) {
     }
     if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
     {   // outlet hydrograph of the channel router (tKinemat::Qout), one value per step
+        if (gpu_et) gpu.syncEtToNodes();
         TrbWriter qw(outdir + (use_gpu ? "/qout_gpu.trb" : "/qout_ref.trb"));
+        if (EvapoTrans.getEToption() != 0) {
+            qw.f64("PotEvap", H.col([](tCNode *c) { return c->getPotEvap(); }));
+            qw.f64("SurfTemp", H.col([](tCNode *c) { return c->getSurfTemp(); }));
+            qw.f64("CanStorage", H.col([](tCNode *c) { return c->getCanStorage(); }));
+            qw.f64("CumTotEvap", H.col([](tCNode *c) { return c->getCumTotEvap(); }));
+            qw.f64("CumIntercept", H.col([](tCNode *c) { return c->getCumIntercept(); }));
+        }
         qw.f64("qout", qout_series);
         qw.f64("NwtNew", H.col([](tCNode *c) { return c->getNwtNew(); }));
         qw.f64("MuNew", H.col([](tCNode *c) { return c->getMuNew(); }));

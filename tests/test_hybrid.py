@@ -18,10 +18,11 @@ pytestmark = pytest.mark.gpu
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
-@pytest.mark.parametrize("name,n,hours", [("deep", 24, 30.0), ("shallow", 20, 30.0)])
+@pytest.mark.parametrize("name,n,hours", [("deep", 24, 30.0), ("shallow", 20, 30.0), ("met", 20, 30.0)])
 def test_reference_simulator_drives_gpu_path(name, n, hours, built):
     d = tempfile.mkdtemp(prefix="tribshyb_")
-    write_basin(spec_for(name, n, runtime_h=hours, seed=2), d)
+    over = dict(gw_depth_mm=300.0, pmean=30.0) if name == "met" else {}   # wet enough for outlet discharge
+    write_basin(spec_for(name, n, runtime_h=hours, seed=2, **over), d)
     lib = os.path.join(ROOT, "tribs_b200", "libtribs_gpu.so")
     for extra in ([], ["--gpu", lib]):
         r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", *extra], cwd=d, capture_output=True,
@@ -35,3 +36,8 @@ def test_reference_simulator_drives_gpu_path(name, n, hours, built):
     for f in ("NwtNew", "MuNew", "NfNew"):
         err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), 1e-6)
         assert err.max() <= 1e-6, (f, err.max())
+    if name == "met":   # kernel (1) driven by the reference's tEvapoTrans / tIntercept objects
+        assert ref["CumTotEvap"].max() > 0.0
+        for f, floor in (("PotEvap", 1e-6), ("SurfTemp", 1.0), ("CanStorage", 1e-6), ("CumTotEvap", 1e-6), ("CumIntercept", 1e-6)):
+            err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), floor)
+            assert err.max() <= 1e-6, (f, err.max())

@@ -8,6 +8,9 @@
 //              tribs_mesh_t / tribs_params_t / tribs_state_t  -> tribs_gpu_init
 //   UnSaturatedZone(dt) / ResetGW() / SaturatedZone(dtGW) / Reset():  tribs_gpu_step with the
 //              flags the reference computes on the host (tRunTimer arithmetic, fmod tests)
+//   attachET() / callEvapoPotential() / callEvapoTrans(flag):  the cell loops of tEvapoTrans and
+//              tIntercept run as kernel (1); tEvapoTrans keeps what it does once per call
+//              (SetEnvironment: calendar + sun geometry, the station records of the hour)
 //   syncToNodes(mask):  tribs_gpu_sync + scatter into tCNode through its own setters, so
 //              tKinemat (channel routing), tCOutput, tWaterBalance and tRestart keep working on
 //              the host unchanged.
@@ -185,6 +188,161 @@ struct TribsGpuBinding {
       c->setSoilMoisture(stage[TRIBS_F_SoilMoisture][i]); c->setSoilMoistureSC(stage[TRIBS_F_SoilMoistureSC][i]);
       c->setSoilMoistureUNSC(stage[TRIBS_F_SoilMoistureUNSC][i]); c->setRootMoisture(stage[TRIBS_F_RootMoisture][i]);
       c->setRootMoistureSC(stage[TRIBS_F_RootMoistureSC][i]); c->setRecharge(stage[TRIBS_F_Recharge][i]);
+    }
+  }
+  // ------------------------------------------------------------------ kernel (1): ET + interception
+  // These bodies replace the cell loops of tEvapoTrans::callEvapoPotential (tEvapoTrans.cpp:603-795)
+  // and tEvapoTrans::callEvapoTrans (1010-1028); inside the reference they are member code of
+  // tEvapoTrans (they use its protected members).
+  tEvapoTrans *et = nullptr;
+  tIntercept *icp = nullptr;
+  decltype(&tribs_gpu_et_init) p_et_init = nullptr;
+  decltype(&tribs_gpu_et_step) p_et_step = nullptr;
+  decltype(&tribs_gpu_et_sync) p_et_sync = nullptr;
+  std::vector<int32_t> cell_record;
+  std::vector<double> met_a[9], met_b[9];
+  std::vector<std::vector<double>> et_stage;
+  tribs_met_t met_pot{}, met_cmp{};
+  tribs_et_step_t es{};
+
+  void attachET(tEvapoTrans *e, tIntercept *ic, tHydroModel *hydro) {
+    et = e; icp = ic;
+    p_et_init = (decltype(p_et_init))dlsym(lib, "tribs_gpu_et_init");
+    p_et_step = (decltype(p_et_step))dlsym(lib, "tribs_gpu_et_step");
+    p_et_sync = (decltype(p_et_sync))dlsym(lib, "tribs_gpu_et_sync");
+    if (!p_et_init || !p_et_step || !p_et_sync) die("dlsym (et)");
+    const int n = (int)cells.size();
+    auto col = [&](auto fn) { std::vector<double> v(n); for (int i = 0; i < n; i++) v[i] = fn(cells[i]); return v; };
+    auto fslope = col([](tCNode *c) { return c->getFlowEdg()->getSlope(); });
+    auto aspect = col([](tCNode *c) { return c->getAspect(); });
+    auto hcond = col([](tCNode *c) { return c->getVolHeatCond(); });
+    auto hcap = col([](tCNode *c) { return c->getSoilHeatCap(); });
+    auto scut = col([](tCNode *c) { return c->getSoilCutoff(); });
+    auto rcut = col([](tCNode *c) { return c->getRootCutoff(); });
+    std::vector<int32_t> lu(n);
+    int maxc = 0;
+    for (int i = 0; i < n; i++) { lu[i] = cells[i]->getLandUse(); maxc = std::max(maxc, (int)lu[i]); }
+    std::vector<double> table((size_t)(maxc + 1) * 15, 0.0);
+    for (int i = 0; i < n; i++) {                                  // tInvariant rows of the classes in use
+      hydro->landPtr->setLandPtr(lu[i]);
+      for (int k = 1; k <= 14; k++) table[(size_t)lu[i] * 15 + k] = hydro->landPtr->getLandProp(k);
+    }
+    tribs_et_params_t P{};
+    P.flow_slope = fslope.data(); P.aspect = aspect.data(); P.vol_heat_cond = hcond.data(); P.soil_heat_cap = hcap.data();
+    P.soil_cutoff = scut.data(); P.root_cutoff = rcut.data(); P.land_class = lu.data(); P.n_land_classes = maxc + 1;
+    P.land_table = table.data();
+    P.et_option = et->evapotransOption; P.i_option = et->Ioption; P.gflux_option = et->gFluxOption;
+    P.shelter_option = et->shelterOption; P.lu_option = et->luOption; P.snow_option = et->snowOption;
+    P.metstep_min = et->timeStep; P.etistep_h = timer->getEtIStep(); P.tlinke = et->Tlinke;
+    P.temp_lapse = et->tempLapseRate; P.max_interstorm = icp->maxInterStormPeriod;
+    if (p_et_init(h, &P)) die("tribs_gpu_et_init");
+    if (et->metdataOption != 1) die("only METDATAOPTION 1 is wired in this binding");
+    cell_record.resize(n);
+    for (int i = 0; i < n; i++)
+      for (int k = 0; k < et->numStations; k++)
+        if (et->assignedStation[i] == et->weatherStations[k].getStation()) cell_record[i] = k;
+    et_stage.assign(TRIBS_N_ET_FIELDS, std::vector<double>(n, 0.0));
+  }
+
+  void fillMet(int t, std::vector<double> *v, tribs_met_t &m) {      // newHydroMetData(t) for every station
+    const int ns = et->numStations;
+    for (int q = 0; q < 9; q++) v[q].resize(ns);
+    for (int k = 0; k < ns; k++) {
+      tHydroMet &st = et->weatherStations[k];
+      v[0][k] = st.getAirTemp(t); v[1][k] = st.getDewTemp(t); v[2][k] = st.getRHumidity(t); v[3][k] = st.getVaporPress(t);
+      v[4][k] = st.getAtmPress(t); v[5][k] = st.getWindSpeed(t); v[6][k] = st.getSkyCover(t); v[7][k] = st.getRadGlobal(t);
+      v[8][k] = st.getOther();
+    }
+    m.n_records = ns; m.cell_record = cell_record.data();
+    m.air_temp = v[0].data(); m.dew_temp = v[1].data(); m.rel_humid = v[2].data(); m.vap_press = v[3].data();
+    m.atm_press = v[4].data(); m.wind_speed = v[5].data(); m.sky_cover = v[6].data(); m.rad_global = v[7].data();
+    m.elev = v[8].data();
+  }
+
+  void sunAndClock() {
+    es.alphaD = et->alphaD; es.sinAlpha = et->sinAlpha; es.sunaz = et->sunaz; es.Io = et->Io;
+    es.hour = et->currentTime[3]; es.dew_hum_flag = et->dewHumFlag; es.ts_option = et->tsOption;
+  }
+
+  // tEvapoTrans::callEvapoPotential()
+  void callEvapoPotential() {
+    et->SetEnvironment();                                  // calendar + sun geometry, once per call
+    const int n = (int)cells.size(), t = et->hourlyTimeStep;
+    tribs_step_t s = flags();                              // the sweep reads this step's rain
+    for (int i = 0; i < n; i++) rain[i] = cells[i]->getRain();
+    s.rain_mode = TRIBS_RAIN_PER_CELL; s.rain = rain.data();
+    if (p_step(h, 0, &s)) die("rain upload");
+    fillMet(t, met_a, met_pot);
+    if (t == 0) {                                          // record-0 decisions, tEvapoTrans.cpp:3989-4003
+      tHydroMet &st = et->weatherStations[cell_record[n - 1]];
+      et->latitude = st.getLat(1); et->longitude = st.getLong(1); et->gmt = st.getGmt();
+      const int k = cell_record[n - 1];
+      auto nd = [](double v) { return fabs(v - 9999.99) < 1.0E-3; };
+      if (nd(met_a[1][k]) && nd(met_a[3][k])) et->dewHumFlag = 0;
+      else if (nd(met_a[2][k]) && nd(met_a[3][k])) et->dewHumFlag = 1;
+      else if (nd(met_a[2][k]) && nd(met_a[1][k])) et->dewHumFlag = 2;
+    }
+    int sky_from = et->skycover_flag ? 0 : n;              // sticky no-data switch, tEvapoTrans.cpp:724-727
+    if (!et->skycover_flag)
+      for (int i = 0; i < n; i++)
+        if (fabs(met_a[6][cell_record[i]] - 9999.99) < 1.0E-3) { sky_from = i; et->skycover_flag = 1; break; }
+    sunAndClock();
+    es.do_potential = 1; es.first_call = (t == 0); es.sky_flag_from = sky_from;
+    es.te_met = (double)timer->getElapsedMETSteps(timer->getCurrentTime());
+    es.met_potential = &met_pot;
+    et->timeCount++; et->oldTimeStep = et->hourlyTimeStep; et->hourlyTimeStep++;
+  }
+  // tEvapoTrans::callEvapoTrans(tIntercept*, int flag)
+  void callEvapoTrans(int flag) {
+    fillMet(et->hourlyTimeStep, met_b, met_cmp);
+    sunAndClock();
+    es.do_components = 1; es.intercept_flag = flag;
+    es.te_eti = (double)timer->getElapsedETISteps(timer->getCurrentTime());
+    es.met_components = &met_cmp;
+    if (!es.do_potential) es.sky_flag_from = et->skycover_flag ? 0 : (int)cells.size();
+    et->timeCount++;
+    flushET();
+  }
+  // one fused launch for the sweeps queued in this step (Simulator::SurfaceHydroProcesses)
+  void flushET() {
+    if (!es.do_potential && !es.do_components) return;
+    if (p_et_step(h, &es)) die("tribs_gpu_et_step");
+    es = tribs_et_step_t{};
+  }
+  // what tCOutput / tWaterBalance read from the nodes (only needed when an output is due)
+  void syncEtToNodes() {
+    std::vector<double *> ptr(TRIBS_N_ET_FIELDS);
+    for (int f = 0; f < TRIBS_N_ET_FIELDS; f++) ptr[f] = et_stage[f].data();
+    if (p_et_sync(h, ~0ull, ptr.data())) die("tribs_gpu_et_sync");
+    const int mf[] = {TRIBS_F_EvapSoil, TRIBS_F_EvapDryCanopy, TRIBS_F_NetPrecipitation};
+    tribs_state_t S{};
+    uint64_t mask = 0;
+    for (int f : mf) { S.f[f] = stage[f].data(); mask |= TRIBS_MASK(f); }
+    if (p_sync(h, mask, &S)) die("tribs_gpu_sync");
+    auto &E = et_stage;
+    for (size_t i = 0; i < cells.size(); i++) {
+      tCNode *c = cells[i];
+      c->setPotEvap(E[TRIBS_ET_PotEvap][i]); c->setActEvap(E[TRIBS_ET_ActEvap][i]);
+      c->setSurfTemp(E[TRIBS_ET_SurfTemp][i]); c->setSoilTemp(E[TRIBS_ET_SoilTemp][i]);
+      c->setNetRad(E[TRIBS_ET_NetRad][i]); c->setGFlux(E[TRIBS_ET_GFlux][i]); c->setHFlux(E[TRIBS_ET_HFlux][i]);
+      c->setLFlux(E[TRIBS_ET_LFlux][i]); c->setLongRadIn(E[TRIBS_ET_LongRadIn][i]); c->setLongRadOut(E[TRIBS_ET_LongRadOut][i]);
+      c->setShortRadIn(E[TRIBS_ET_ShortRadIn][i]); c->setShortRadIn_dir(E[TRIBS_ET_ShortRadIn_dir][i]);
+      c->setShortRadIn_dif(E[TRIBS_ET_ShortRadIn_dif][i]); c->setShortRadSlope(E[TRIBS_ET_ShortRadSlope][i]);
+      c->setShortAbsbVeg(E[TRIBS_ET_ShortAbsbVeg][i]); c->setShortAbsbSoi(E[TRIBS_ET_ShortAbsbSoi][i]);
+      c->setAirTemp(E[TRIBS_ET_AirTemp][i]); c->setDewTemp(E[TRIBS_ET_DewTemp][i]); c->setRelHumid(E[TRIBS_ET_RelHumid][i]);
+      c->setVapPressure(E[TRIBS_ET_VapPressure][i]); c->setSkyCover(E[TRIBS_ET_SkyCover][i]);
+      c->setWindSpeed(E[TRIBS_ET_WindSpeed][i]); c->setAirPressure(E[TRIBS_ET_AirPressure][i]);
+      c->addCumHrsSun(E[TRIBS_ET_CumHrsSun][i] - c->getCumHrsSun());
+      c->setAvEvapFract(E[TRIBS_ET_AvEvapFract][i]); c->setSheltFact(E[TRIBS_ET_SheltFact][i]);
+      c->addRSin(E[TRIBS_ET_CumRSin][i] - c->getCumRSin());
+      c->setEvapWetCanopy(E[TRIBS_ET_EvapWetCanopy][i]); c->setEvapoTrans(E[TRIBS_ET_EvapoTrans][i]);
+      c->addTotEvap(E[TRIBS_ET_CumTotEvap][i] - c->getCumTotEvap());
+      c->addBarEvap(E[TRIBS_ET_CumBarEvap][i] - c->getCumBarEvap());
+      c->setAvET(E[TRIBS_ET_AvET][i]); c->setInterceptLoss(E[TRIBS_ET_InterceptLoss][i]);
+      c->setCanStorage(E[TRIBS_ET_CanStorage][i]); c->setCumIntercept(E[TRIBS_ET_CumIntercept][i]);
+      c->setStormLength(0, 0.0); c->setStormLength(1, E[TRIBS_ET_StormLength][i]);
+      c->setEvapSoil(stage[TRIBS_F_EvapSoil][i]); c->setEvapDryCanopy(stage[TRIBS_F_EvapDryCanopy][i]);
+      c->setNetPrecipitation(stage[TRIBS_F_NetPrecipitation][i]);
     }
   }
   ~TribsGpuBinding() { if (h && p_destroy) p_destroy(h); }
