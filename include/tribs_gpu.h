@@ -43,7 +43,7 @@ typedef struct tribs_ctx *tribs_handle_t;
   X(SoilMoisture) X(SoilMoistureSC) X(SoilMoistureUNSC) X(RootMoisture) X(RootMoistureSC) \
   X(AvSoilMoisture) X(Recharge) X(UnSatFlowIn) X(UnSatFlowOut) X(Transmissivity) \
   X(hsrfOccur) X(sbsrfOccur) X(psrfOccur) X(satsrfOccur) X(satOccur) X(RechDisch) \
-  X(FlowVelocity) X(TTime) X(Qstrm) X(LiqWE) X(IceWE) X(LiqRouted)
+  X(FlowVelocity) X(TTime) X(Qstrm) X(LiqWE) X(IceWE) X(LiqRouted) X(UnSaturatedStorage) X(SaturatedStorage)
 
 #define TRIBS_FIELD_ENUM(name) TRIBS_F_##name,
 typedef enum { TRIBS_FIELDS(TRIBS_FIELD_ENUM) TRIBS_N_FIELDS } tribs_field_t;
@@ -136,7 +136,9 @@ typedef struct {
 
 /* basin accumulators returned by tribs_gpu_get_globals (tHydroModel private sums) */
 enum { TRIBS_G_Stok, TRIBS_G_TotRain, TRIBS_G_TotGWchange, TRIBS_G_TotMoist, TRIBS_G_psrf_last,
-       TRIBS_G_hillvel_last, TRIBS_N_GLOBALS };
+       TRIBS_G_hillvel_last,
+       /* tWaterBalance::BasinStorages[0], [1], [5] (tWaterBalance.cpp:283-337): running volumes, m3 */
+       TRIBS_G_BasinRain, TRIBS_G_BasinEvap, TRIBS_G_BasinRunoff, TRIBS_N_GLOBALS };
 
 /* tFlowResults arrays kept on the device (src/tFlowNet/tFlowResults.h:74-96) */
 enum { TRIBS_R_mhydro, TRIBS_R_HsrfRout, TRIBS_R_SbsrfRout, TRIBS_R_PsrfRout, TRIBS_R_SatsrfRout,
@@ -237,7 +239,7 @@ int tribs_gpu_abi_version(void);
   X(ShortAbsbVeg) X(ShortAbsbSoi) X(AirTemp) X(DewTemp) X(RelHumid) X(VapPressure) X(SkyCover) \
   X(WindSpeed) X(AirPressure) X(CumHrsSun) X(AvEvapFract) X(SheltFact) X(CumRSin) \
   X(EvapWetCanopy) X(EvapoTrans) X(CumTotEvap) X(CumBarEvap) X(AvET) X(InterceptLoss) \
-  X(CanStorage) X(CumIntercept) X(StormLength)
+  X(CanStorage) X(CumIntercept) X(StormLength) X(CanopyStorVol)
 #define TRIBS_ET_FIELD_ENUM(name) TRIBS_ET_##name,
 typedef enum { TRIBS_ET_FIELDS(TRIBS_ET_FIELD_ENUM) TRIBS_N_ET_FIELDS } tribs_et_field_t;
 

@@ -86,6 +86,7 @@ def lib():
         L.orc_sat.argtypes = [C.POINTER(Basin), C.POINTER(State), C.c_double, C.c_double]
         L.orc_route.argtypes = [C.POINTER(Basin), C.POINTER(State), C.POINTER(Results), C.c_double]
         L.orc_reset.argtypes = [C.POINTER(Basin), C.POINTER(State)]
+        L.orc_balance.argtypes = [C.POINTER(Basin), C.POINTER(State), C.c_int, C.c_int, C.c_double, PD, PD, PD, PD, PD, PD]
         L.orc_retrieve_qeff.argtypes = [C.POINTER(Basin), C.POINTER(Results), C.c_double, PD]
         L.orc_state_counts.argtypes = [C.POINTER(C.c_longlong), C.c_int]
         for nm, nargs in (("lambertw", 1),):
@@ -221,6 +222,16 @@ class OracleModel:
 
     def reset(self):
         self.L.orc_reset(C.byref(self.B), C.byref(self.S))
+
+    def balance(self, et=None, met_time=False, metstep_h=1.0):
+        """Simulator::UpdateWaterBalance (tSimul.cpp:576-585); *et* is an OracleET or None."""
+        if not hasattr(self, "basin6"):
+            self.basin6 = np.zeros(6)
+        gw_time = math.fmod(self.time, self.B.gwstep) == 0.0
+        f = (lambda nm: _pd(et.f[nm])) if et is not None else (lambda nm: None)
+        self.L.orc_balance(C.byref(self.B), C.byref(self.S), int(gw_time), int(met_time), metstep_h,
+                           f("InterceptLoss"), f("EvapWetCanopy"), f("EvapoTrans"), f("CanStorage"), f("CanopyStorVol"),
+                           _pd(self.basin6))
 
     def step(self):
         self.advance()

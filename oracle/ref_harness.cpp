@@ -283,6 +283,7 @@ struct Harness {
         w.f64s("output_interval", timer->getOutputInterval());
         dump_et_setup(w);
         dump_state(w, "init_", true);
+        w.f64("init_CanopyStorVol", col([](tCNode *c) { return c->getCanopyStorVol(); }));
         dump_et(w, "init_");
     }
 
@@ -776,6 +777,14 @@ int main(int argc, char **argv) {
         double t4b = now_s();
         Sim.OutputSimulatedVars(&Flow);
         Sim.UpdateWaterBalance(&Balance);
+        if (snap && phases.find('b') != string::npos) {   // tWaterBalance storages, before Reset()
+            snprintf(pre, sizeof pre, "s%d_b_", step);
+            sw->f64(string(pre) + "UnSaturatedStorage", H.col([](tCNode *c) { return c->getUnSaturatedStorage(); }));
+            sw->f64(string(pre) + "SaturatedStorage", H.col([](tCNode *c) { return c->getSaturatedStorage(); }));
+            sw->f64(string(pre) + "CanopyStorVol", H.col([](tCNode *c) { return c->getCanopyStorVol(); }));
+            vector<double> bs(Balance.BasinStorages, Balance.BasinStorages + 6);
+            sw->f64(string(pre) + "BasinStorages", bs);
+        }
         Moisture.Reset();
         if (use_gpu) gpu.Reset();
         double t5 = now_s();

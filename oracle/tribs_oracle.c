@@ -1684,6 +1684,54 @@ void orc_reset(const orc_basin *b, orc_state *s) {
   }
 }
 
+void orc_balance(const orc_basin *b, orc_state *s, int gw_time, int met_time, double metstep_h,
+                 const double *intercept_loss, const double *evap_wet_canopy, const double *evapotrans,
+                 const double *can_storage, double *canopy_stor_vol, double *basin6) {
+  const double unsStep = b->tstep * 60.0, satStep = b->gwstep * 60.0;   /* the keywords are in minutes */
+  int i;
+  {   /* UnSaturatedBalance, tWaterBalance.cpp:165-200 */
+    const double dt = unsStep / 60.0;
+    for (i = 0; i < b->n; i++) {
+      double QUin = s->f[ORCS_UnSatFlowIn][i], QUout = s->f[ORCS_UnSatFlowOut][i], Rech = s->f[ORCS_Recharge][i];
+      double Run = s->f[ORCS_srf][i] / unsStep, A = b->sf[ORC_varea][i], Inf = s->f[ORCS_NetPrecipitation][i];
+      double Melt = s->f[ORCS_LiqRouted][i] * 10.0, ET, DelU;
+      if (s->f[ORCS_LiqWE][i] + s->f[ORCS_IceWE][i] > 1e-4) Inf = Melt;
+      else Inf = Inf + Melt;
+      ET = s->f[ORCS_EvapSoil][i] + s->f[ORCS_EvapDryCanopy][i];
+      DelU = Inf + QUin - QUout - Rech - ET - Run;
+      s->f[ORCS_UnSaturatedStorage][i] = s->f[ORCS_UnSaturatedStorage][i] + DelU * dt * A / 1000.0;
+    }
+  }
+  if (gw_time) {   /* SaturatedBalance, tWaterBalance.cpp:234-262; QgwIn/QgwOut are never written by the model */
+    const double dt = satStep / 60.0;
+    for (i = 0; i < b->n; i++) {
+      double QSTin = 0.0 * 1.0E-9, QSTout = 0.0 * 1.0E-9, Rech = s->f[ORCS_Recharge][i];
+      double Exf = s->f[ORCS_srf][i] / satStep, A = b->sf[ORC_varea][i];
+      double DelG = QSTin - QSTout + (Rech - Exf) * A / 1000.0;
+      s->f[ORCS_SaturatedStorage][i] = s->f[ORCS_SaturatedStorage][i] + DelG * dt;
+    }
+  }
+  if (met_time && canopy_stor_vol) {   /* CanopyBalance, tWaterBalance.cpp:116-140 */
+    for (i = 0; i < b->n; i++) {
+      double DelI = intercept_loss[i] - evap_wet_canopy[i];
+      canopy_stor_vol[i] = canopy_stor_vol[i] + DelI * metstep_h * b->sf[ORC_varea][i] / 1000.0;
+    }
+  }
+  {   /* BasinStorage, tWaterBalance.cpp:283-337: three running sums; the other three keep the LAST cell's value */
+    double rain = 0.0, evap = 0.0, run = 0.0, can = 0.0, uns = 0.0, sat = 0.0;
+    for (i = 0; i < b->n; i++) {
+      double a = b->sf[ORC_varea][i] / 1000.0;
+      can = (can_storage ? can_storage[i] : 0.0) * a;
+      rain += s->f[ORCS_Rain][i] * a * unsStep / 60.0;
+      evap += (evapotrans ? evapotrans[i] : 0.0) * a * unsStep / 60.0;
+      run += s->f[ORCS_srf][i] * a;
+      uns = s->f[ORCS_MuNew][i] * a;
+      sat = b->sf[ORC_ThetaS][i] * (b->sf[ORC_bedrock][i] - s->f[ORCS_NwtNew][i]) * a;
+    }
+    basin6[0] += rain; basin6[1] += evap; basin6[2] = can; basin6[3] = uns; basin6[4] = sat; basin6[5] += run;
+  }
+}
+
 /* ------------------------------------------------------------------------------------ KATs */
 static void kat_cell(cw *c, const double *soil) {
   memset(c, 0, sizeof *c);

@@ -44,7 +44,7 @@ extern "C" {
   X(SoilMoisture) X(SoilMoistureSC) X(SoilMoistureUNSC) X(RootMoisture) X(RootMoistureSC) \
   X(AvSoilMoisture) X(Recharge) X(UnSatFlowIn) X(UnSatFlowOut) X(Transmissivity) \
   X(hsrfOccur) X(sbsrfOccur) X(psrfOccur) X(satsrfOccur) X(satOccur) X(RechDisch) \
-  X(FlowVelocity) X(TTime) X(Qstrm) X(LiqWE) X(IceWE) X(LiqRouted)
+  X(FlowVelocity) X(TTime) X(Qstrm) X(LiqWE) X(IceWE) X(LiqRouted) X(UnSaturatedStorage) X(SaturatedStorage)
 
 /* ---- basin accumulators (orc_state.glob) ---- */
 #define ORC_GLOBALS(X) \
@@ -118,6 +118,13 @@ void orc_reset_gw(const orc_basin *b, orc_state *s);
 void orc_sat(const orc_basin *b, orc_state *s, double dtgw, double current_time);
 void orc_route(const orc_basin *b, orc_state *s, orc_results *r, double current_time);
 void orc_reset(const orc_basin *b, orc_state *s);
+/* tWaterBalance::UnSaturatedBalance / SaturatedBalance / CanopyBalance / BasinStorage as
+ * Simulator::UpdateWaterBalance calls them (tSimul.cpp:576-585, tWaterBalance.cpp:116-345).
+ * gw_time: fmod(currentTime, GWSTEP) == 0; met_time: currentTime == met_hour. The three ET arrays
+ * and canopy_stor_vol may be NULL (ET off): treated as zeros / not updated. basin6 = BasinStorages. */
+void orc_balance(const orc_basin *b, orc_state *s, int gw_time, int met_time, double metstep_h,
+                 const double *intercept_loss, const double *evap_wet_canopy, const double *evapotrans,
+                 const double *can_storage, double *canopy_stor_vol, double *basin6);
 void orc_retrieve_qeff(const orc_basin *b, orc_results *r, double current_time, double *out);
 void orc_state_counts(long long *out16, int reset); /* [0..9] unsat states, [10..13] GW states */
 

@@ -27,7 +27,7 @@ extern "C" {
   X(ShortAbsbVeg) X(ShortAbsbSoi) X(AirTemp) X(DewTemp) X(RelHumid) X(VapPressure) X(SkyCover) \
   X(WindSpeed) X(AirPressure) X(CumHrsSun) X(AvEvapFract) X(SheltFact) X(CumRSin) \
   X(EvapWetCanopy) X(EvapoTrans) X(CumTotEvap) X(CumBarEvap) X(AvET) X(InterceptLoss) \
-  X(CanStorage) X(CumIntercept) X(StormLength)
+  X(CanStorage) X(CumIntercept) X(StormLength) X(CanopyStorVol)
 
 #define ORC_ET_ENUM(name) ORCET_##name,
 enum { ORC_ET_FIELDS(ORC_ET_ENUM) ORC_N_ET_FIELDS };

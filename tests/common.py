@@ -28,6 +28,7 @@ class GpuStepper:
         self.stream_cells = self.sim.dev.stream_cells()
         self.limit = int(basin["res_limit"][0])
         self.evap, self._evap_now = evap_of(basin), None
+        self.has_et = self.sim.evapotrans.getEToption() != 0
 
     @property
     def time(self):
@@ -58,6 +59,9 @@ class GpuStepper:
     def route(self):
         self.sim.flow.SurfaceFlow(True)
         return self.sim.flow.lateral_inflow
+
+    def balance(self):
+        pass   # tWaterBalance rides on the ROUTE phase of the device path
 
     def reset(self):
         self.sim.hydro.Reset()
@@ -94,6 +98,7 @@ class OracleStepper:
             self.et = OracleET(basin, self.m, self.host)
             self.cal = met.Calendar(basin["timer_start"])
             self.clock = met.MetClock(self.m.B.tstep, self.host.metstep, self.host.etistep)
+        self.has_et = self.et is not None
 
     @property
     def time(self):
@@ -104,6 +109,7 @@ class OracleStepper:
         if self.et is not None:       # Simulator::SurfaceHydroProcesses, tSimul.cpp:419-461
             self.cal.advance(self.m.time, self.m.B.tstep)
             met_due, eti_due = self.clock.due(self.m.time)
+            self._met_due = met_due
             if met_due:
                 self.et.potential(*self.host.potential_call(self.cal.hour, self.m.time))
             if eti_due:
@@ -125,6 +131,9 @@ class OracleStepper:
         q = self.m.retrieve_qeff()
         return np.concatenate([q[self.stream_cells], q[-1:]])
 
+    def balance(self):
+        self.m.balance(self.et, getattr(self, "_met_due", False), self.host.metstep if self.et is not None else 1.0)
+
     def reset(self):
         self.m.reset()
 
@@ -136,7 +145,10 @@ class OracleStepper:
 
     def globals(self):
         from oracle.pyoracle import GLOBALS
-        return dict(zip(GLOBALS, self.m.glob))
+        g = dict(zip(GLOBALS, self.m.glob))
+        b6 = getattr(self.m, "basin6", np.zeros(6))
+        g.update(BasinRain=b6[0], BasinEvap=b6[1], BasinRunoff=b6[5])
+        return g
 
 
 # absolute floors of the relative comparison for ET fields that pass through zero (degC, W/m2)
@@ -209,5 +221,16 @@ def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True):
                 w.add(("glob", "TotRain"), ref[1:2], np.array([g["TotRain"]]), st, floor)
                 w.add(("glob", "TotGWchange"), ref[2:3], np.array([g["TotGWchange"]]), st, 1e-6)
                 w.add(("glob", "TotMoist"), ref[3:4], np.array([g["TotMoist"]]), st, 1e-6)
+        stepper.balance()
+        pre = f"s{st}_b_"
+        if pre + "UnSaturatedStorage" in snaps:
+            names = ["UnSaturatedStorage", "SaturatedStorage"] + (["CanopyStorVol"] if stepper.has_et else [])
+            got = stepper.get(names)
+            for f in names:
+                w.add(("b", f), snaps[pre + f], got[f], st, floor)
+            g, ref = stepper.globals(), snaps[pre + "BasinStorages"]
+            for k, nm in ((0, "BasinRain"), (1, "BasinEvap"), (5, "BasinRunoff")):
+                w.add(("b", nm), ref[k:k + 1], np.array([g[nm]]), st, 1e-6)
         stepper.reset()
     return w
+

@@ -25,7 +25,7 @@ def main():
     for name in SCENARIOS:
         spec = spec_for(name, N)
         nsteps = int(round(spec.runtime_h * 60.0 / spec.timestep_min))
-        basin, snaps, timing, kat = run_reference(spec, snap_from=1, snap_to=nsteps, phases="mugr" if spec.forcing == "met" else "ugr", kat=True)
+        basin, snaps, timing, kat = run_reference(spec, snap_from=1, snap_to=nsteps, phases="mugrb" if spec.forcing == "met" else "ugrb", kat=True)
         keep = set()
         for h in list(range(0, int(spec.runtime_h), 8)) + [int(spec.runtime_h) - 1]:
             for k in KEEP_STEPS_PER_H:
@@ -41,7 +41,7 @@ def main():
             phase = k.split("_")[1]
             if phase == "g" or (phase == "u" and step % 8 != 0):
                 continue   # 'r' carries the post-step state; 'u' is kept on GW steps to separate the zones
-            if step in keep and (phase == "m" or field not in DROP):
+            if step in keep and (phase in ("m", "b") or field not in DROP):
                 out["s/" + k] = v
         out["s/snap_steps"] = np.array(keep, np.int32)
         out["s/n_steps"] = np.array([nsteps], np.int32)

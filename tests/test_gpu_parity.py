@@ -37,7 +37,7 @@ def test_gpu_matches_live_reference(name, n, hours, built):
     spec = spec_for(name, n, runtime_h=hours, seed=3)
     n_steps = int(round(hours * 16))
     basin, snaps, timing, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16,
-                                           phases="mur" if spec.forcing == "met" else "ur")
+                                           phases="murb" if spec.forcing == "met" else "urb")
     w = run_and_compare(GpuStepper(basin, _sched(basin)), snaps, n_steps, floor=ABS_FLOOR)
     print(f"\n[{name} n={n}] cells={basin['n_active'][0]} worst:\n" + w.report(8))
     assert w.max() <= REL_TOL, w.report()

@@ -36,7 +36,7 @@ struct EtConst {
 
 struct EtStatic {           // device order, length n_pad
   const double *z, *cos_slope, *sin_slope, *aspect, *heat_cond, *heat_cap, *soil_cutoff, *root_cutoff;
-  const double *thr, *bedrock;
+  const double *thr, *bedrock, *varea;
   const int32_t *land_class, *boundary, *sweep_of_dev;
   const LandClass *classes;
 };
@@ -48,6 +48,7 @@ struct MetDev {             // device copies of one tribs_met_t
 
 struct EtStepDev {
   int32_t do_potential, do_components, intercept_flag;
+  int32_t met_time;                                // currentTime == met_hour: tWaterBalance::CanopyBalance is due
   double alphaD, sinAlpha, sunaz, Io, cos_alpha;   // cos_alpha = cos(asin(sinAlpha)), once per call
   int32_t hour, first_call, dew_hum_flag, ts_option, sky_flag_from;
   double te_met, te_eti, rs_ratio;                 // rs_ratio = rsRatio[hour] of stomResist()
@@ -306,7 +307,7 @@ TRIBS_HD void intercept_rutter(const LandClass &lc, const EtConst &k, double rai
 // ---- the cell update -------------------------------------------------------------------------------
 #define EF(name) ev.f[TRIBS_ET_##name][i]
 
-TRIBS_HD void et_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
+TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
   const LandClass lc = st.classes[st.land_class[i]];
   const double elevation = st.z[i];
   const double rain = dv.f[TRIBS_F_Rain][i];
@@ -472,6 +473,16 @@ TRIBS_HD void et_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s, 
   EF(CumBarEvap) += soil;
   if (fabs(s.te_eti - 1.0) < 1.0E-6) EF(AvET) = et;
   else if (s.te_eti > 1.0) EF(AvET) = (EF(AvET) * (s.te_eti - 1.0) + et) / s.te_eti;
+}
+
+// the two sweeps, then the canopy water balance that Simulator::UpdateWaterBalance applies at the
+// end of a met step to the values they leave behind (tWaterBalance.cpp:116-140)
+TRIBS_HD void et_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
+  et_sweeps(k, st, s, ev, dv, i);
+  if (s.met_time) {
+    const double del_i = EF(InterceptLoss) - EF(EvapWetCanopy);
+    EF(CanopyStorVol) = EF(CanopyStorVol) + del_i * (k.metstep_min / 60.0) * st.varea[i] / 1000.0;
+  }
 }
 #undef EF
 

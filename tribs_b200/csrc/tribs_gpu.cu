@@ -70,6 +70,7 @@ struct tribs_ctx {
   struct EtState *et = nullptr; // kernel (1) state (tribs_gpu_et_init)
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
   int max_degree = 0, segment_cells = 0;
+  double gwstep_h = 0.0;
   cudaStream_t stream = nullptr;
   // host maps
   std::vector<int32_t> dev_of_sweep, sweep_of_dev, stream_cells_sweep;
@@ -444,10 +445,21 @@ route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n
 //     slabs filled lane by lane, slabs added in warp order). Stage 2: one warp per output value
 //     sums the G block partials in a fixed order into the tFlowResults arrays.
 constexpr int kRouteWarps = 8;
-constexpr int kMeans = 10;  // crr frac msm msmRt msmU sat mgw qunsat rmax rmin
+constexpr int kMeans = 13;  // crr frac msm msmRt msmU sat mgw qunsat rmax rmin + basin rain/evap/runoff volumes
+// tWaterBalance (tWaterBalance.cpp:116-345) rides on this sweep: it sits at the same place in the
+// reference's step (Simulator::UpdateWaterBalance, after SurfaceFlow, before Reset) and reads the
+// same end-of-step fields. `d` may hold per-step snapshots of some fields (batches); the
+// storages are always the live arrays.
+struct WaterBalanceArgs {
+  double *uns_storage, *sat_storage;   // tCNode::UnSaturatedStorage / SaturatedStorage
+  const double *evapotrans;            // tCNode::EvapoTranspiration (kernel 1), or nullptr
+  double gwstep_h;
+  int32_t gw_time;                     // fmod(currentTime, GWSTEP) == 0
+};
 __global__ void __launch_bounds__(kRouteWarps * 32)
 route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, double now, double qstrm_outlet,
-                          int n_pad, int window, int bin_base, int last_hill_dev, double *part, double *globals) {
+                          int n_pad, int window, int bin_base, int last_hill_dev, double *part, double *globals,
+                          WaterBalanceArgs wb) {
   extern __shared__ double sh[];  // [kRouteWarps][5*window + kMeans]
   const int stride = 5 * window + kMeans;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -518,6 +530,23 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
       means[7] = areaf * (d.f[TRIBS_F_Qpout][i] - d.f[TRIBS_F_Qpin][i]) * 1.E-6 / area * w;
       means[8] = rain;
       means[9] = rain;
+      {   // UnSaturatedBalance / SaturatedBalance / BasinStorage for this cell
+        const double uns_min = rc.tstep * 60.0, sat_min = wb.gwstep_h * 60.0, rech = d.f[TRIBS_F_Recharge][i];
+        const double melt = d.f[TRIBS_F_LiqRouted][i] * 10.0;
+        double inf = d.f[TRIBS_F_NetPrecipitation][i];
+        inf = (d.f[TRIBS_F_LiqWE][i] + d.f[TRIBS_F_IceWE][i] > 1e-4) ? melt : inf + melt;
+        const double et = d.f[TRIBS_F_EvapSoil][i] + d.f[TRIBS_F_EvapDryCanopy][i];
+        const double del_u = inf + d.f[TRIBS_F_UnSatFlowIn][i] - d.f[TRIBS_F_UnSatFlowOut][i] - rech - et - srf / uns_min;
+        wb.uns_storage[i] = wb.uns_storage[i] + del_u * (uns_min / 60.0) * area / 1000.0;
+        if (wb.gw_time) {
+          const double del_g = 0.0 - 0.0 + (rech - srf / sat_min) * area / 1000.0;
+          wb.sat_storage[i] = wb.sat_storage[i] + del_g * (sat_min / 60.0);
+        }
+        const double a = area / 1000.0;
+        means[10] = rain * a * uns_min / 60.0;
+        means[11] = (wb.evapotrans ? wb.evapotrans[i] : 0.0) * a * uns_min / 60.0;
+        means[12] = srf * a;
+      }
     }
     // the 8 sums: fixed-order butterfly; min/max: order free
 #pragma unroll
@@ -528,8 +557,11 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
       mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
       mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
     }
+#pragma unroll
+    for (int k = 10; k < kMeans; k++) means[k] = warp_sum_fixed(means[k]);
     if (lane == 0) {
       for (int k = 0; k < 8; k++) slab[5 * window + k] += means[k];
+      for (int k = 10; k < kMeans; k++) slab[5 * window + k] += means[k];
       slab[5 * window + 8] = fmax(slab[5 * window + 8], mx);
       slab[5 * window + 9] = fmin(slab[5 * window + 9], mn);
     }
@@ -563,7 +595,7 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
 
 __global__ void __launch_bounds__(256)
 route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int window, int bin_base, int cur_bin,
-                          int limit, double *results) {
+                          int limit, double *results, double *globals) {
   const int stride = 5 * window + kMeans;
   const int lane = threadIdx.x & 31;
   const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output value
@@ -583,9 +615,11 @@ route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int win
   if (k < 5 * window) {
     const int type = k / window, bin = bin_base + (k % window);
     if (bin >= 0 && bin < limit && acc != 0.0) results[(size_t)type * limit + bin] += acc;
+  } else if (k >= 5 * window + 10) {
+    globals[TRIBS_G_BasinRain + (k - 5 * window - 10)] += acc;
   } else if (cur_bin >= 0 && cur_bin < limit) {
     const int q = k - 5 * window;
-    const int map[kMeans] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
+    const int map[10] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
                              TRIBS_R_sat, TRIBS_R_mgw, TRIBS_R_qunsat, TRIBS_R_rmax, TRIBS_R_rmin};
     double *dst = results + (size_t)map[q] * limit + cur_bin;
     if (q == 8) { if (acc > *dst) *dst = acc; }
@@ -920,6 +954,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     RouteConst &rc = c->rc;
     rc.velcoef = prm->velcoef; rc.velratio = prm->velratio; rc.flowexp = prm->flowexp; rc.baseflow = prm->baseflow;
     rc.kincoef = prm->kincoef; rc.dt_reff = prm->dtReff; rc.outlet_contr_area = prm->outlet_contr_area;
+    c->gwstep_h = prm->gwstep;
     rc.tstep = prm->tstep; rc.output_interval = prm->output_interval; rc.res_limit = std::max(prm->res_limit, 1);
     // the slowest hillslope velocity bounds the furthest dtReff bin ever written
     double vmin = prm->velcoef / prm->velratio;
@@ -1014,6 +1049,7 @@ static int check_sweep_abort(tribs_ctx *c) {
   return 0;
 }
 
+static WaterBalanceArgs water_balance_args(tribs_ctx *c, double now);
 static int upload_sweep_field(tribs_ctx *c, const double *host, int field) {
   CK(cudaMemcpyAsync(c->d_stage, host, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   scatter_from_sweep_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->d_stage, c->d_dev_of_sweep, c->dv.f[field], c->n);
@@ -1114,10 +1150,10 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
     size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
     route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, c->dv, c->rc, c->mc, now, s->qstrm_outlet,
                                                                                  n_pad, window, bin_base, c->last_hill_dev,
-                                                                                 c->d_route_part, c->d_globals);
+                                                                                 c->d_route_part, c->d_globals, water_balance_args(c, now));
     const int n_vals = 5 * window + kMeans;
     route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
-                                                                          cur_bin, c->rc.res_limit, c->d_results);
+                                                                          cur_bin, c->rc.res_limit, c->d_results, c->d_globals);
     c->launches += 4;
   }
   if (mask & TRIBS_PHASE_RESET) {
@@ -1199,6 +1235,16 @@ static void tribs_free_et(tribs_ctx *c) {
     }
   delete c->et;
   c->et = nullptr;
+}
+
+static WaterBalanceArgs water_balance_args(tribs_ctx *c, double now) {
+  WaterBalanceArgs wb{};
+  wb.uns_storage = c->dv.f[TRIBS_F_UnSaturatedStorage];
+  wb.sat_storage = c->dv.f[TRIBS_F_SaturatedStorage];
+  wb.evapotrans = c->et ? c->et->ev.f[TRIBS_ET_EvapoTrans] : nullptr;
+  wb.gwstep_h = c->gwstep_h;
+  wb.gw_time = fmod(now, c->gwstep_h) == 0.0;          // Simulator::GW_label, tSimul.cpp:511
+  return wb;
 }
 
 __global__ void __launch_bounds__(128)
@@ -1294,7 +1340,7 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   int32_t *d_lc = nullptr;
   if (dev_upload(c, &d_lc, to_device_order<int32_t>(c, p->land_class, 0))) return 1;
   e->st.land_class = d_lc;
-  e->st.z = c->sv.z; e->st.thr = c->sv.thr; e->st.bedrock = c->sv.bedrock;
+  e->st.z = c->sv.z; e->st.thr = c->sv.thr; e->st.bedrock = c->sv.bedrock; e->st.varea = c->sv.varea;
   e->st.boundary = c->sv.boundary; e->st.sweep_of_dev = c->d_sweep_of_dev;
   for (int f = 0; f < TRIBS_N_ET_FIELDS; f++) {
     const double *src = (p->init && p->init[f]) ? p->init[f] : nullptr;
@@ -1366,6 +1412,7 @@ extern "C" int tribs_gpu_et_step(tribs_handle_t c, const tribs_et_step_t *s) {
                                      2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
   EtStepDev d{};
   d.do_potential = s->do_potential && e->k.et_option; d.do_components = s->do_components; d.intercept_flag = s->intercept_flag;
+  d.met_time = s->do_potential;
   d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
   d.cos_alpha = cos(asin(s->sinAlpha));
   d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
@@ -1373,7 +1420,7 @@ extern "C" int tribs_gpu_et_step(tribs_handle_t c, const tribs_et_step_t *s) {
   d.rs_ratio = rsRatio[s->hour];
   if (d.do_potential && et_upload_met(c, 0, s->met_potential, &d.pot)) return 1;
   if (d.do_components && e->k.et_option && et_upload_met(c, 1, s->met_components, &d.cmp)) return 1;
-  if (!d.do_potential && !d.do_components) return 0;
+  if (!d.do_potential && !d.do_components && !d.met_time) return 0;
   et_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, e->ev, c->dv, c->n_pad);
   c->launches++;
   e->gen++;
@@ -1605,11 +1652,12 @@ struct PhaseInfo {
   StepConst t;
 };
 
-constexpr int kSliceFields = 12;
+constexpr int kSliceFields = 15;
 __constant__ int kSliceFieldIds[kSliceFields];
 static const int kSliceFieldIdsHost[kSliceFields] = {
     TRIBS_F_srf, TRIBS_F_hsrf, TRIBS_F_sbsrf, TRIBS_F_psrf, TRIBS_F_satsrf, TRIBS_F_Rain, TRIBS_F_SoilMoistureSC,
-    TRIBS_F_RootMoistureSC, TRIBS_F_SoilMoistureUNSC, TRIBS_F_NwtNew, TRIBS_F_Qpout, TRIBS_F_Qpin};
+    TRIBS_F_RootMoistureSC, TRIBS_F_SoilMoistureUNSC, TRIBS_F_NwtNew, TRIBS_F_Qpout, TRIBS_F_Qpin,
+    TRIBS_F_Recharge, TRIBS_F_UnSatFlowIn, TRIBS_F_UnSatFlowOut};   // the last three: tWaterBalance inputs
 
 // tile-level dependency graph (three CSRs over tiles, self excluded, entries distinct)
 struct TileGraph {
@@ -1805,7 +1853,7 @@ struct PipePlan {
 
 struct PipeState {
   double *d_qpub = nullptr;        // [2][n_pad] new Qpout by phase parity
-  double *d_slices = nullptr;      // [max_steps][12][n_pad]
+  double *d_slices = nullptr;      // [max_steps][kSliceFields][n_pad]
   double *d_tile_sums = nullptr;   // [max_phases][n_tiles][4]
   double *d_qeff_steps = nullptr;  // [max_steps][slots]
   double *d_rain = nullptr;        // [max_steps][n_pad] per-cell forcing, device order
@@ -2043,10 +2091,10 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
       size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
       route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, dvs, c->rc, c->mc, now, steps[k].qstrm_outlet,
                                                                                    n_pad, window, bin_base, c->last_hill_dev,
-                                                                                   c->d_route_part, c->d_globals);
+                                                                                   c->d_route_part, c->d_globals, water_balance_args(c, now));
       const int n_vals = 5 * window + kMeans;
       route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
-                                                                            cur_bin, c->rc.res_limit, c->d_results);
+                                                                            cur_bin, c->rc.res_limit, c->d_results, c->d_globals);
       c->launches += 4;
     }
     CK(cudaMemcpyAsync(c->d_qeff_now, ps->d_qeff_steps + (size_t)(n_steps - 1) * slots, (size_t)slots * sizeof(double),

@@ -46,7 +46,8 @@ ET_FIELDS = _et_fields_from_header()
 EF = {nm: k for k, nm in enumerate(ET_FIELDS)}
 RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac",
            "msm", "msmRt", "msmU", "mgw", "sat", "qunsat"]
-GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last"]
+GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last", "BasinRain", "BasinEvap",
+           "BasinRunoff"]
 PHASE_UNSAT, PHASE_SAT, PHASE_ROUTE, PHASE_RESET = 1, 2, 4, 8
 RAIN_KEEP, RAIN_UNIFORM, RAIN_PER_CELL = 0, 1, 2
 
