@@ -95,7 +95,8 @@ def test_gpu_water_balance_closes(built):
 # ------------------------------------------------------------------ pipelined batches (tribs_gpu_run)
 ALL_CHECK = ["NwtOld", "MuOld", "MiOld", "NtOld", "NfOld", "RuOld", "RiOld", "Qpout", "intstorm", "srf_hr", "cumsrf",
              "SoilMoisture", "RootMoisture", "AvSoilMoisture", "Recharge", "hsrfOccur", "sbsrfOccur", "psrfOccur",
-             "satsrfOccur", "satOccur", "RechDisch", "esrf", "Transmissivity", "TTime", "FlowVelocity", "UnSatFlowIn"]
+             "satsrfOccur", "satOccur", "RechDisch", "esrf", "Transmissivity", "TTime", "FlowVelocity", "UnSatFlowIn",
+             "UnSaturatedStorage", "SaturatedStorage"]
 
 
 @pytest.mark.parametrize("name,batch", [("deep", 8), ("shallow", 16), ("redistribute", 5), ("deep", 64),
