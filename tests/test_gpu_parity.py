@@ -43,6 +43,34 @@ def test_gpu_matches_live_reference(name, n, hours, built):
     assert w.max() <= REL_TOL, w.report()
 
 
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("variant", ["deardorff", "priestley-taylor", "gray", "gradient-gflux", "lapse-rate",
+                                     "no-interception", "no-shelter", "sky-cover-nodata"])
+def test_gpu_et_option_variants_match_live_reference(variant, built):
+    """Kernel (1) under every option value it accepts (tribs_gpu_et_init refuses the others)."""
+    from test_oracle import et_variant_spec
+    hours = 30.0
+    spec = et_variant_spec(variant, 20, hours, 6)
+    n_steps = int(hours * 16)
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=8, phases="murb")
+    w = run_and_compare(GpuStepper(basin, _sched(basin)), snaps, n_steps, floor=ABS_FLOOR)
+    print(f"\n[{variant}] worst:\n" + w.report(6))
+    assert w.max() <= REL_TOL, w.report()
+    assert any(k[0] == "m" for k in w.w)
+
+
+def test_gpu_et_init_refuses_uncovered_options(built):
+    from tribs_b200 import gpu
+    basin, _, _ = load_golden("met")
+    for key, val in (("et_shelterOption", 2), ("et_snowOption", 1), ("et_luOption", 1), ("et_option", 4)):
+        b = dict(basin)
+        b[key] = np.array([val], np.int32)
+        dev = gpu.GpuBasin(b)
+        with pytest.raises(gpu.TribsGpuError):
+            dev.et_init(b)
+        dev.close()
+
+
 def test_gpu_run_to_run_bitwise(built):
     basin, snaps, _ = load_golden("deep")
     outs = []

@@ -76,3 +76,28 @@ def test_oracle_vs_live_reference(built):
     basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=480, snap_every=7)
     w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, 480)
     assert w.max() == 0.0, w.report()
+
+
+ET_VARIANTS = {
+    "deardorff": {"OPTEVAPOTRANS": 2}, "priestley-taylor": {"OPTEVAPOTRANS": 3}, "gray": {"OPTINTERCEPT": 1},
+    "gradient-gflux": {"GFLUXOPTION": 1}, "lapse-rate": {"TEMPLAPSE": -0.0065}, "no-interception": {"OPTINTERCEPT": 0},
+    "no-shelter": {"OPTRADSHELT": 4}, "sky-cover-nodata": {"_sky_nodata": True},
+}
+
+
+def et_variant_spec(variant, n, hours, seed):
+    extra = dict(ET_VARIANTS[variant])
+    sky = extra.pop("_sky_nodata", False)
+    return spec_for("met", n, runtime_h=hours, seed=seed, extra=extra, sky_nodata=sky)
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("variant", list(ET_VARIANTS))
+def test_oracle_et_option_variants_against_live_reference(variant, built):
+    """Every option value kernel (1) claims to cover, checked bit for bit against the reference."""
+    spec = et_variant_spec(variant, 10, 30.0, 4)
+    n_steps = 30 * 16
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=8, phases="murb")
+    w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, n_steps)
+    assert w.max() == 0.0, "oracle differs from the reference:\n" + w.report()
+    assert any(k[0] == "m" for k in w.w) and any(k[0] == "b" for k in w.w)

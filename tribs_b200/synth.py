@@ -51,6 +51,7 @@ class BasinSpec:
     forcing: str = "storm"        # "storm": STOCHASTICMODE 1 uniform storm; "met": rain gauges +
                                   # one weather station (Penman-Monteith ET, Rutter interception)
     n_gauges: int = 2
+    sky_nodata: bool = False      # met deck: write 9999.99 as sky cover (the model then derives it from RH / rain)
     inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
     extra: dict = field(default_factory=dict)   # keyword overrides
 
@@ -145,7 +146,7 @@ def write_met_forcing(spec: BasinSpec, outdir: str) -> dict:
         d.write("Y M D H PA RH XC US TA IS NR\n")
         for h in range(nh):
             pa, rh, xc, us, ta, isw = met[h]
-            d.write(f"{stamp(h)} {pa} {rh} {xc} {us} {ta} {isw} 9999.99\n")
+            d.write(f"{stamp(h)} {pa} {rh} {9999.99 if spec.sky_nodata else xc} {us} {ta} {isw} 9999.99\n")
     return {"STOCHASTICMODE": 0, "RAINSOURCE": 3, "GAUGESTATIONS": f"{outdir}/gauges.sdf",
             "OPTEVAPOTRANS": 1, "OPTINTERCEPT": 2, "METDATAOPTION": 1,
             "HYDROMETSTATIONS": f"{outdir}/met.sdf"}
