@@ -103,13 +103,13 @@ def run_gpu(args):
         # river; every rank holds the static data of the whole basin and advances the cells it owns
         from tribs_b200.parallel import PartitionedSimulator
         side = args.side_mgpu
-        basin = build_basin(side, side * world, seed=1, runtime_h=1e9)
+        basin = build_basin(side, side * world, seed=1, runtime_h=1e9, stream_every=args.stream_every)
         psim = PartitionedSimulator(basin, rank, world, rain_schedule=storm_rain)
         dev = psim.dev
         n = int((psim.owner == rank).sum())
         sim = None
     else:
-        basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9)
+        basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9, stream_every=args.stream_every)
         n = int(basin["n_active"][0])
         sim = Simulator(basin, rain_schedule=None)
         dev = sim.dev
@@ -447,6 +447,8 @@ def main():
                     help="N>1: one reach-partitioned basin with halo exchange (default) or independent replicas")
     ap.add_argument("--side-mgpu", type=int, default=500, help="N>1, partition mode: cells across the valley; "
                     "the basin is side x side*N cells, i.e. side^2 per GPU")
+    ap.add_argument("--stream-every", type=int, default=0, help="tributary stream row every K rows (0: one river, "
+                    "hillslopes as long as half the basin width)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-et-kernel", action="store_true", help="skip the separate timing of kernel (1)")
     args = ap.parse_args()

@@ -1677,7 +1677,12 @@ __device__ __forceinline__ void st_relaxed_i32(int32_t *p, int v) {
 // two ready queues: "hi" for the tiles on the critical cycle of the batch (river cells and the
 // cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
 // ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
-struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; };
+struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; };
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
 __device__ __forceinline__ void release_task(int32_t *cnt, const ReadyQueues &rq, int n_tiles, int p, int tile) {
   const int task = p * n_tiles + tile;
   if (atomicSub(cnt + task, 1) == 1) {
@@ -1720,12 +1725,12 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
                 double *wt_elev, double *transm, double *slices, double *tile_sums, int n_tiles, double *globals,
                 int last_sweep_dev, int32_t *abort_flag, int32_t *flags) {
   const int lane = threadIdx.x & 31;
-  // Two ticket queues. Warp 0 of the first `n_hi_blocks` blocks (one per SM) serves the "hi" queue
+  // Two ticket queues. `n_hi_blocks` warps, spread over the SMs (warp 0 of every block first), serve the "hi" queue
   // (river cells and the cells next to the river: their chain through all phases is the critical
   // path and must never sit behind a backlog of bulk work); every other warp serves "lo". A warp
   // takes a ticket (atomicAdd on the head) and waits for exactly that slot to be filled, so a
   // newly released task is picked up at once by the warp that holds its ticket.
-  const bool hi_warp = (threadIdx.x < 32) && (blockIdx.x < (unsigned)n_hi_blocks);
+  const bool hi_warp = (int)((threadIdx.x >> 5) * gridDim.x + blockIdx.x) < n_hi_blocks;
   const int my_total = hi_warp ? n_hi_tasks : n_tasks - n_hi_tasks;
   int32_t *my_head = rq.ctl + (hi_warp ? 0 : 2);
   const int32_t *my_queue = rq.queue + (hi_warp ? 0 : rq.n_tasks);
@@ -1753,6 +1758,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
     { const long long now_c = clock64(); t_wait += now_c - t_mark; t_mark = now_c; }
     if (task < 0) break;
     const int p = task / n_tiles, tile = task - p * n_tiles;
+    if (rq.trace && lane == 0) rq.trace[2 * (size_t)task] = global_ns();   // TRIBS_TRACE: task timeline
     __threadfence();   // acquire side of the producers' fence -> counter -> queue hand-off
     const PhaseInfo ph = phases[p];
     const int i = tile * kTile + lane;
@@ -1826,6 +1832,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
       for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p + 1, lst[k]);
       if (lane == 0) release_task(cnt, rq, n_tiles, p + 1, tile);
     }
+    if (rq.trace && lane == 0) rq.trace[2 * (size_t)task + 1] = global_ns();
     { const long long now_c = clock64(); t_busy += now_c - t_mark; t_mark = now_c; n_done++; }
   }
   if (lane == 0) {   // scheduler statistics: [0..2] lo warps, [3..5] hi warps
@@ -2029,10 +2036,22 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
   CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)2 * n_tasks * sizeof(int32_t), st));
   {
     PhaseTimer pt(c, 0);
-    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks};
+    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr};
+    const char *trace_path = getenv("TRIBS_TRACE");   // debugging aid: start/end time of every task of this launch
+    unsigned long long *d_trace = nullptr;
+    if (trace_path) {
+      CK(cudaMalloc((void **)&d_trace, (size_t)2 * n_tasks * sizeof(unsigned long long)));
+      CK(cudaMemsetAsync(d_trace, 0, (size_t)2 * n_tasks * sizeof(unsigned long long), st));
+      rq.trace = d_trace;
+    }
     int n_hi_tasks = P * c->n_hi_tiles;
-    int n_hi_blocks = std::min(ps->blocks, ps->n_sms);
-    if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_blocks = std::max(1, std::min(ps->blocks, atoi(e)));
+    // warps serving the "hi" queue: one per SM for a single river; on a dendritic network the stream
+    // tiles are a sizeable share of all tasks and get that share of the warps
+    const int total_warps = ps->blocks * 4;
+    int n_hi_blocks = std::max(std::min(ps->blocks, ps->n_sms),
+                               (int)std::lround(1.25 * total_warps * (double)c->n_hi_tiles / std::max(1, c->n_tiles)));
+    n_hi_blocks = std::min(n_hi_blocks, total_warps - std::min(ps->blocks, ps->n_sms));
+    if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_blocks = std::max(1, std::min(total_warps - 1, atoi(e)));
     pipeline_init_kernel<<<(n_tasks + 255) / 256, 256, 0, st>>>(ps->graph, pl->d_phases, P, c->n_tiles, ps->d_cnt, rq);
     int ntk = n_tasks, n_tiles = c->n_tiles, last = c->last_sweep_dev, npad = n_pad;
     void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &pl->d_phases, &ps->graph, &ntk, &ps->d_cnt, &rq, &n_hi_tasks, &n_hi_blocks,
@@ -2043,6 +2062,25 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     int blocks = ps->blocks;
     CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(128), args, 0, st));
     c->launches += 2;
+    if (d_trace) {   // file: int32 n_phases, n_tiles; per tile int32 hi flag, int32 first cell (sweep index); 2 x u64 per task
+      std::vector<unsigned long long> h((size_t)2 * n_tasks);
+      CK(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
+      CK(cudaStreamSynchronize(st));
+      CK(cudaFree(d_trace));
+      std::vector<int32_t> hi(c->n_tiles), first(c->n_tiles), kind(P);
+      CK(cudaMemcpy(hi.data(), c->d_tile_hi, hi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+      for (int t = 0; t < c->n_tiles; t++) first[t] = c->sweep_of_dev[(size_t)t * kTile];
+      for (int q = 0; q < P; q++) kind[q] = pl->phases[q].kind;
+      if (FILE *f = fopen(trace_path, "wb")) {
+        int32_t hdr[2] = {P, c->n_tiles};
+        fwrite(hdr, sizeof(int32_t), 2, f);
+        fwrite(kind.data(), sizeof(int32_t), kind.size(), f);
+        fwrite(hi.data(), sizeof(int32_t), hi.size(), f);
+        fwrite(first.data(), sizeof(int32_t), first.size(), f);
+        fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
+        fclose(f);
+      }
+    }
     // basin accumulators, phase by phase in the reference's order
     for (int p = 0; p < P; p++) {
       const double *ts = ps->d_tile_sums + (size_t)p * c->n_tiles * 4;

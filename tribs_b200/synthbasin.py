@@ -57,7 +57,8 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     z = 100.0 + slope_y * y + slope_x * np.abs(x - xc)
     if stream_every:
         jm = jj % stream_every
-        z = z + 0.03 * np.minimum(jm, stream_every - jm) * spacing
+        # local valleys towards the tributary rows; the main stem keeps its monotone profile
+        z = z + np.where(ii == ic, 0.0, 0.03 * np.minimum(jm, stream_every - jm) * spacing)
     # outlet: boundary node below the bottom stream cell
     outlet_ij = (0, ic)
 
