@@ -8,8 +8,7 @@ import torch.distributed as dist
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
-from oracle.pyoracle import stochastic_storm_schedule  # noqa: E402
-from refrun import load_golden, storm_of  # noqa: E402
+from refrun import load_golden, schedule_for  # noqa: E402
 from tribs_b200.model import Simulator  # noqa: E402
 from tribs_b200.parallel import PartitionedSimulator  # noqa: E402
 
@@ -20,19 +19,25 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     name, steps = sys.argv[1], int(sys.argv[2])
     basin, _, _ = load_golden(name)
-    ps = PartitionedSimulator(basin, rank, world, stochastic_storm_schedule(*storm_of(basin)))
+    ps = PartitionedSimulator(basin, rank, world, schedule_for(basin))
     for _ in range(steps):
         ps.one_step()
     fields = ["NwtOld", "MuOld", "MiOld", "NtOld", "NfOld", "RuOld", "RiOld", "Qpout", "cumsrf", "srf_hr", "RechDisch",
-              "Transmissivity", "AvSoilMoisture", "esrf"]
+              "Transmissivity", "AvSoilMoisture", "esrf", "UnSaturatedStorage", "SaturatedStorage"]
+    if name == "met":
+        fields += ["PotEvap", "SurfTemp", "SoilTemp", "CanStorage", "CumIntercept", "EvapSoil", "EvapDryCanopy",
+                   "NetPrecipitation", "CumTotEvap", "CanopyStorVol"]
     got = ps.gather(fields)
     qeff = ps.dev.retrieve_qeff(0.0)
     ok = True
     if rank == 0:
-        ref = Simulator(basin, stochastic_storm_schedule(*storm_of(basin)))
+        ref = Simulator(basin, schedule_for(basin))
         for _ in range(steps):
             ref.one_step()
-        want = ref.dev.sync(fields)
+        from tribs_b200.gpu import EF
+        want = ref.dev.sync([f for f in fields if f not in EF])
+        if any(f in EF for f in fields):
+            want.update(ref.dev.et_sync([f for f in fields if f in EF]))
         for f in fields:
             if not np.array_equal(want[f], got[f]):
                 k = int(np.argmax(np.abs(want[f] - got[f])))

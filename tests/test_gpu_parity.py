@@ -187,7 +187,7 @@ def test_gpu_batch_matches_live_reference_after_full_run(built):
 
 
 # ------------------------------------------------------------------ one reach partition per GPU
-@pytest.mark.parametrize("name,steps", [("deep", 200), ("shallow", 200)])
+@pytest.mark.parametrize("name,steps", [("deep", 200), ("shallow", 200), ("met", 200)])
 def test_two_gpus_bitwise_equal_to_one(name, steps, built):
     """The reference's own multi-rank contract (serial == MPI, test_big_spring.py:5-22)."""
     import subprocess

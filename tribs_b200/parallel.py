@@ -64,6 +64,13 @@ class PartitionedSimulator:
         self.timer = tRunTimer(float(b["tstep"][0]), float(b["gwstep"][0]), float(b["etistep"][0]), float(b["endtime"][0]))
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0]))
+        # kernel (1) is cell-local: every rank runs it on the replicated arrays, owned cells are exact
+        from .model import tEvapoTrans, tIntercept
+        from . import met
+        self.intercept = tIntercept(b)
+        self.evapotrans = tEvapoTrans(self.dev, self.timer, b)
+        self.met_clock = met.MetClock(self.timer.tstep, float(b["metstep"][0]) if "metstep" in b else self.timer.etistep,
+                                      self.timer.etistep)
         last_owner = int(self.owner[-1])          # owner of the last swept cell (psrf_last)
         self.psrf_owner = last_owner
 
@@ -105,6 +112,17 @@ class PartitionedSimulator:
         if rain_cells is not None:
             rain_cells.fill(0.0 if rain is None else rain)
             rain = rain_cells
+        if self.evapotrans.getEToption() != 0:                         # Simulator::SurfaceHydroProcesses
+            met_due, eti_due = self.met_clock.due(now)
+            if met_due or eti_due:
+                if rain is not None:
+                    dev.step(0, now, el, 0, rain=rain)
+                    rain = None
+                if met_due:
+                    self.evapotrans.callEvapoPotential()
+                if eti_due:
+                    self.evapotrans.callEvapoTrans(self.intercept, 1 if self.intercept.getIoption() != 0 else 0)
+                self.evapotrans.flush()
         dev.step(16, now, el, hr, rain=rain)                          # TRIBS_PHASE_UNSAT_LOCAL
         for peer in sorted(self.plan["qpout_recv"]):                   # ranks upstream of me
             dist.recv(self.buf[("qpout_recv", peer)], src=peer)
@@ -129,7 +147,11 @@ class PartitionedSimulator:
 
     def gather(self, names):
         """Owned values of the requested fields from every rank, assembled on every rank."""
-        local = self.dev.sync(names)
+        main = [nm for nm in names if nm not in gpu.EF]
+        local = self.dev.sync(main) if main else {}
+        et = [nm for nm in names if nm in gpu.EF]
+        if et:
+            local.update(self.dev.et_sync(et))
         out = {}
         for nm in names:
             a = self.torch.as_tensor(np.where(self.owner == self.rank, local[nm], 0.0), device="cuda")
