@@ -59,6 +59,30 @@ def test_gpu_et_option_variants_match_live_reference(variant, built):
     assert any(k[0] == "m" for k in w.w)
 
 
+def test_gpu_et_per_cell_met_records_equal_station_records(built):
+    """Gridded meteorology (METDATAOPTION 2) reaches kernel (1) as one record per cell: the same
+    values expanded per cell must give bit-identical results to the station form."""
+    from tribs_b200.gpu import ET_FIELDS
+    basin, _, _ = load_golden("met")
+    a, b = GpuStepper(basin, _sched(basin)), GpuStepper(basin, _sched(basin))
+    h = b.sim.evapotrans.host
+    st_idx = h.cell_record.copy()
+    station_record = h.record
+    h.record = lambda t: {k: np.ascontiguousarray(v[st_idx]) for k, v in station_record(t).items()}
+    h.cell_record = np.arange(b.n, dtype=np.int32)
+    h.elev, h.lat, h.long, h.gmt_st = h.elev[st_idx], h.lat[st_idx], h.long[st_idx], h.gmt_st[st_idx]
+    for g in (a, b):
+        for _ in range(120):
+            g.advance(); g.unsat()
+            if g.gw_due():
+                g.sat()
+            g.route(); g.reset()
+    ea, eb = a.get(ET_FIELDS), b.get(ET_FIELDS)
+    for f in ET_FIELDS:
+        assert np.array_equal(ea[f], eb[f]), f
+    assert np.abs(ea["LFlux"]).max() > 0
+
+
 def test_gpu_et_init_refuses_uncovered_options(built):
     from tribs_b200 import gpu
     basin, _, _ = load_golden("met")

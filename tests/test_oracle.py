@@ -101,3 +101,30 @@ def test_oracle_et_option_variants_against_live_reference(variant, built):
     w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, n_steps)
     assert w.max() == 0.0, "oracle differs from the reference:\n" + w.report()
     assert any(k[0] == "m" for k in w.w) and any(k[0] == "b" for k in w.w)
+
+
+def test_host_sun_geometry_and_met_clock_match_reference_bitwise(built):
+    """tribs_b200/met.py (calendar, SetSunVariables, met clock) against the members the reference
+    harness dumped after every SurfaceHydroProcesses call of the 'met' run."""
+    from tribs_b200 import met
+    basin, snaps, _ = load_golden("met")
+    host = met.EvapoTransHost(basin)
+    cal = met.Calendar(basin["timer_start"])
+    tstep = float(basin["tstep"][0])
+    clock = met.MetClock(tstep, host.metstep, host.etistep)
+    t, checked = 0.0, 0
+    for st in range(1, int(snaps["n_steps"][0]) + 1):
+        t += tstep
+        cal.advance(t, tstep)
+        met_due, eti_due = clock.due(t)
+        if met_due:
+            host.potential_call(cal.hour, t)
+        key = f"s{st}_m_sun"
+        if key in snaps:
+            ref = snaps[key]   # alphaD sinAlpha sunaz Io hour hourlyTimeStep dewHumFlag skycover_flag ...
+            got = np.array([host.sun[0], host.sun[1], host.sun[2], host.sun[3], host.hour, host.hourlyTimeStep,
+                            host.dewHumFlag, host.skycover_flag])
+            assert np.array_equal(ref[:8], got), (st, ref[:8], got)
+            assert (ref[13], ref[14], ref[15]) == (host.latitude, host.longitude, host.gmt)
+            checked += 1
+    assert checked >= 20
