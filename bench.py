@@ -243,6 +243,13 @@ def run_gpu(args):
     e2e = total_cells * args.steps / (e2e_ms * 1e-3)
     peak, peak_kind = peaks()
     achieved = bytes_per_launch / (unsat_ms * 1e-3) / 1e9 if unsat_ms > 0 else 0.0
+    traffic = None      # DRAM bytes of one launch from the committed ncu capture, if it is of this configuration
+    try:
+        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))["pipeline_kernel"]
+        if B > 1 and tr["cells"] == n and tr["steps_per_launch"] == int(steps_per_launch):
+            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+    except (OSError, KeyError, ValueError):
+        pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -261,11 +268,12 @@ def run_gpu(args):
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": {"bound": "hbm", "kernel": "pipeline_kernel" if B > 1 else "unsat_sweep_kernel", "achieved": achieved, "peak": peak,
-                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": None,
+                     "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
                      "peak_source": peak_kind, "bytes_per_cell_step": UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every,
                      "avg_launch_ms": unsat_ms, "steps_per_launch": steps_per_launch,
-                     "note": "not HBM-bound yet: the run time follows the dependency chain along the river "
-                             f"({dev.levels()} levels per step) times the FP64 latency of one column update; see DESIGN.md"},
+                     "note": "not HBM-bound: bound by instruction delivery (74 % of the working warps' stall samples are "
+                             "no_instruction) and, once per storm, by the ridge-to-river dependency chain "
+                             f"({dev.levels()} levels) of the slow post-storm step; see DESIGN.md 4.2"},
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
     if world == 1 and not args.no_et_kernel:
