@@ -1680,7 +1680,7 @@ __device__ __forceinline__ void st_relaxed_i32(int32_t *p, int v) {
 // two ready queues: "hi" for the tiles on the critical cycle of the batch (river cells and the
 // cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
 // ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
-struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; };
+struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; unsigned cap_hi_ns, cap_lo_ns; };
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
@@ -1737,7 +1737,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
   const int my_total = hi_warp ? n_hi_tasks : n_tasks - n_hi_tasks;
   int32_t *my_head = rq.ctl + (hi_warp ? 0 : 2);
   const int32_t *my_queue = rq.queue + (hi_warp ? 0 : rq.n_tasks);
-  const unsigned ns_cap = hi_warp ? 128u : 2048u;
+  const unsigned ns_cap = hi_warp ? rq.cap_hi_ns : rq.cap_lo_ns;   // back-off ceiling of the queue poll
   long long t_wait = 0, t_busy = 0, n_done = 0;
   long long t_mark = clock64();
   for (;;) {
@@ -2039,7 +2039,10 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
   CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)2 * n_tasks * sizeof(int32_t), st));
   {
     PhaseTimer pt(c, 0);
-    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr};
+    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr, 128u, 16384u};   // lo ceiling: idle pollers cost the working warps instruction-fetch
+    // bandwidth; measured on the 1M-cell batch 2 us: 373, 16 us: 423, 32 us: 426, 64 us: 397, 128 us: 351 M cell-timesteps/s
+    if (const char *e = getenv("TRIBS_POLL_CAP_NS")) rq.cap_lo_ns = (unsigned)std::max(32, atoi(e));
+    if (const char *e = getenv("TRIBS_POLL_CAP_HI_NS")) rq.cap_hi_ns = (unsigned)std::max(32, atoi(e));
     const char *trace_path = getenv("TRIBS_TRACE");   // debugging aid: start/end time of every task of this launch
     unsigned long long *d_trace = nullptr;
     if (trace_path) {
