@@ -257,6 +257,20 @@ def _xlist_et() -> list[str]:
 ET_FIELDS = _xlist_et()
 
 
+def _xlist_snow() -> list[str]:
+    src = open(os.path.join(HERE, "tribs_oracle_et.h")).read()
+    m = re.search(r"#define\s+ORC_SNOW_FIELDS\(X\)\s*\\?\n?((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
+SNOW_FIELDS = _xlist_snow()
+
+
+class SnowArgs(C.Structure):
+    _fields_ = [("min_sn_temp", C.c_double), ("snliqfrac", C.c_double), ("hill_albedo_option", C.c_int32),
+                ("hourly_time_step", C.c_int32), ("LiqWE", PD), ("IceWE", PD), ("LiqRouted", PD)]
+
+
 class EtBasin(C.Structure):
     _fields_ = [("n", C.c_int32)] + [(k, PD) for k in (
         "z", "flow_slope", "aspect", "ThetaS", "ThetaR", "VolHeatCond", "SoilHeatCap", "soil_cutoff",
@@ -319,6 +333,20 @@ class OracleET:
             setattr(sh, k, _pd(model.state[k]))
         self.sh = sh
         self.flag = int(B.i_option != 0)
+        self.snow = int(b["et_snowOption"][0]) != 0 if "et_snowOption" in b else False
+        if self.snow:
+            self.L.orc_snow_pack.argtypes = [C.POINTER(EtBasin), C.POINTER(SnowArgs), C.POINTER(EtStep), C.POINTER(Met),
+                                             C.POINTER(PD), C.POINTER(PD), C.POINTER(EtShared), C.c_int, PD]
+            assert self.L.orc_snow_n_fields() == len(SNOW_FIELDS)
+            for nm in SNOW_FIELDS:
+                self.f[nm] = np.array(b["init_" + nm], np.float64) if "init_" + nm in b else np.zeros(n)
+            self.sfp = (PD * len(SNOW_FIELDS))(*[_pd(self.f[nm]) for nm in SNOW_FIELDS])
+            self.members = np.array([0.88, 0.0, 0.0])     # albedo, Uerr, snCanWE (tSnowPack.cpp:103-150)
+            a = SnowArgs()
+            a.min_sn_temp = float(b["sn_minSnTemp"][0]); a.snliqfrac = float(b["sn_snliqfrac"][0])
+            a.hill_albedo_option = int(b["sn_hillAlbedoOption"][0])
+            a.LiqWE, a.IceWE, a.LiqRouted = _pd(model.state["LiqWE"]), _pd(model.state["IceWE"]), _pd(model.state["LiqRouted"])
+            self.sn_args = a
 
     def _args(self, step: dict, rec: dict):
         s = EtStep(**step)
@@ -335,6 +363,14 @@ class OracleET:
         s, m, keep = self._args(step, rec)
         rc = self.L.orc_et_potential(C.byref(self.B), C.byref(s), C.byref(m), self.fp, C.byref(self.sh))
         assert rc == 0, "option set not covered by the oracle"
+
+    def snow_pack(self, step, rec, hourly):
+        """tSnowPack::callSnowPack (replaces both ET sweeps under OPTSNOW); hourly = the met clock of the call."""
+        s, m, keep = self._args(step, rec)
+        self.sn_args.hourly_time_step = int(hourly)
+        rc = self.L.orc_snow_pack(C.byref(self.B), C.byref(self.sn_args), C.byref(s), C.byref(m), self.fp, self.sfp,
+                                  C.byref(self.sh), self.flag, _pd(self.members))
+        assert rc == 0
 
     def components(self, step, rec):
         s, m, keep = self._args(step, rec)

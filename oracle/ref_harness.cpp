@@ -97,6 +97,7 @@ struct Harness {
     tEvapoTrans *et = nullptr;
     tIntercept *icp = nullptr;
     tRainfall *rainfall = nullptr;
+    tSnowPack *snow = nullptr;
     vector<tCNode*> cells;                    // active cells in list (sweep) order
     unordered_map<tNode*, int> pos;           // node -> index in cells
 
@@ -291,18 +292,25 @@ struct Harness {
     // What tEvapoTrans / tIntercept read per cell or hold as members (tEvapoTrans.cpp:215-253,
     // 915-952, 3122-3330; tIntercept.cpp:44-45, 468-484): land classes, options, the weather
     // stations' hourly records and the Thiessen assignment of cells to stations.
+    // with OPTSNOW the simulator drives the tSnowPack object (a tEvapoTrans) instead: its members count
+    tEvapoTrans *active_et() { return (et->snowOption && snow) ? static_cast<tEvapoTrans *>(snow) : et; }
+
     void dump_et_setup(TrbWriter &w) {
-        w.i32s("et_option", et->evapotransOption);
-        w.i32s("et_Ioption", et->Ioption);
-        w.i32s("et_metdataOption", et->metdataOption);
-        w.i32s("et_gFluxOption", et->gFluxOption);
-        w.i32s("et_luOption", et->luOption);
-        w.i32s("et_snowOption", et->snowOption);
-        w.i32s("et_shelterOption", et->shelterOption);
-        w.f64s("et_timeStep", et->timeStep);
-        w.f64s("et_Tlinke", et->Tlinke);
-        w.f64s("et_tempLapseRate", et->tempLapseRate);
+        tEvapoTrans *E = active_et();
+        w.i32s("et_option", E->evapotransOption);
+        w.i32s("et_Ioption", E->Ioption);
+        w.i32s("et_metdataOption", E->metdataOption);
+        w.i32s("et_gFluxOption", E->gFluxOption);
+        w.i32s("et_luOption", E->luOption);
+        w.i32s("et_snowOption", E->snowOption);
+        w.i32s("et_shelterOption", E->shelterOption);
+        w.f64s("et_timeStep", E->timeStep);
+        w.f64s("et_Tlinke", E->Tlinke);
+        w.f64s("et_tempLapseRate", E->tempLapseRate);
         w.f64s("icp_maxInterStormPeriod", icp->maxInterStormPeriod);
+        w.f64s("sn_minSnTemp", snow->minSnTemp);
+        w.f64s("sn_snliqfrac", snow->snliqfrac);
+        w.i32s("sn_hillAlbedoOption", snow->hillAlbedoOption);
         w.i32s("icp_option", icp->interceptOption);
         vector<int32_t> lu(cells.size());
         int maxc = 0;
@@ -335,13 +343,13 @@ struct Harness {
             w.f64s("rain_precLapseRate", rainfall->precLapseRate);
             w.f64s("rain_dt", timer->getRainDT());
         }
-        if (et->evapotransOption == 0 || et->metdataOption != 1 || et->weatherStations == nullptr) return;
-        int ns = et->numStations;
+        if (E->evapotransOption == 0 || E->metdataOption != 1 || E->weatherStations == nullptr) return;
+        int ns = E->numStations;
         w.i32s("met_n_stations", ns);
         vector<int32_t> sid(ns), gmt(ns), nt(ns), np(ns);
         vector<double> lat(ns), lon(ns), oth(ns);
         for (int k = 0; k < ns; k++) {
-            tHydroMet &st = et->weatherStations[k];
+            tHydroMet &st = E->weatherStations[k];
             sid[k] = st.getStation(); gmt[k] = st.getGmt(); nt[k] = st.getTime(); np[k] = st.getParm();
             lat[k] = st.getLat(1); lon[k] = st.getLong(1); oth[k] = st.getOther();
         }
@@ -350,7 +358,7 @@ struct Harness {
         int T = nt[0];
         auto series = [&](const char *name, double (tHydroMet::*get)(int)) {
             vector<double> v((size_t)ns * T);
-            for (int k = 0; k < ns; k++) for (int t = 0; t < T; t++) v[(size_t)k * T + t] = (et->weatherStations[k].*get)(t);
+            for (int k = 0; k < ns; k++) for (int t = 0; t < T; t++) v[(size_t)k * T + t] = (E->weatherStations[k].*get)(t);
             w.f64(name, v);
         };
         series("met_airTemp", &tHydroMet::getAirTemp);
@@ -364,16 +372,16 @@ struct Harness {
         series("met_radGlobal", &tHydroMet::getRadGlobal);
         vector<int32_t> cal((size_t)T * 4);
         for (int t = 0; t < T; t++) {
-            tHydroMet &st = et->weatherStations[0];
+            tHydroMet &st = E->weatherStations[0];
             cal[t * 4 + 0] = st.getYear(t); cal[t * 4 + 1] = st.getMonth(t);
             cal[t * 4 + 2] = st.getDay(t); cal[t * 4 + 3] = st.getHour(t);
         }
         w.i32("met_calendar", cal);
         vector<int32_t> as(cells.size());
-        for (size_t i = 0; i < cells.size(); i++) as[i] = et->assignedStation[i];
+        for (size_t i = 0; i < cells.size(); i++) as[i] = E->assignedStation[i];
         w.i32("met_assigned_station", as);
-        w.i32s("met_tsOption", et->tsOption);
-        w.i32s("met_vapOption", et->vapOption);
+        w.i32s("met_tsOption", E->tsOption);
+        w.i32s("met_vapOption", E->vapOption);
         vector<int32_t> start = {timer->year, timer->month, timer->day, timer->hour, timer->minute};
         w.i32("timer_start", start);
     }
@@ -382,6 +390,7 @@ struct Harness {
     // the members the host-side mirror has to reproduce (sun geometry, met clock)
     void dump_et(TrbWriter &w, const string &pre) {
         if (!et || et->evapotransOption == 0) return;
+        tEvapoTrans *E = active_et();
         w.f64(pre + "PotEvap", col([](tCNode *c) { return c->getPotEvap(); }));
         w.f64(pre + "ActEvap", col([](tCNode *c) { return c->getActEvap(); }));
         w.f64(pre + "SurfTemp", col([](tCNode *c) { return c->getSurfTemp(); }));
@@ -422,10 +431,27 @@ struct Harness {
         w.f64(pre + "EvapDryCanopy", col([](tCNode *c) { return c->getEvapDryCanopy(); }));
         w.f64(pre + "NetPrecipitation", col([](tCNode *c) { return c->getNetPrecipitation(); }));
         w.f64(pre + "Rain", col([](tCNode *c) { return c->getRain(); }));
-        vector<double> sun = {et->alphaD, et->sinAlpha, et->sunaz, et->Io, (double)et->currentTime[3],
-                              (double)et->hourlyTimeStep, (double)et->dewHumFlag, (double)et->skycover_flag,
-                              et->del, et->phi, et->tau, et->deltaT, (double)et->nodeHour,
-                              et->latitude, et->longitude, (double)et->gmt};
+        if (et->snowOption) {   // tSnowPack state, fluxes and integrated outputs (tSnowPack.cpp:1052-1135)
+#define SNF(name, getter) w.f64(pre + name, col([](tCNode *c) { return c->getter(); }))
+            SNF("LiqWE", getLiqWE); SNF("IceWE", getIceWE); SNF("SnTempC", getSnTempC); SNF("LiqRouted", getLiqRouted);
+            SNF("CrustAge", getCrustAge); SNF("DensityAge", getDensityAge); SNF("EvapoTransAge", getEvapoTransAge);
+            SNF("SnSub", getSnSub); SNF("SnEvap", getSnEvap); SNF("DU", getDU); SNF("Unode", getUnode); SNF("Uerror", getUerror);
+            SNF("SnLHF", getSnLHF); SNF("SnSHF", getSnSHF); SNF("SnGHF", getSnGHF); SNF("SnPHF", getSnPHF);
+            SNF("SnRLout", getSnRLout); SNF("SnRLin", getSnRLin); SNF("SnRSin", getSnRSin);
+            SNF("IntSWE", getIntSWE); SNF("IntPrec", getIntPrec); SNF("IntSnUnload", getIntSnUnload); SNF("IntSub", getIntSub);
+            SNF("CumIntSub", getCumIntSub); SNF("CumIntUnl", getCumIntUnl);
+            SNF("CumLHF", getCumLHF); SNF("CumMelt", getCumMelt); SNF("CumSHF", getCumSHF); SNF("CumSnSub", getCumSnSub);
+            SNF("CumSnEvap", getCumSnEvap); SNF("CumPHF", getCumPHF); SNF("CumRLin", getCumRLin); SNF("CumRLout", getCumRLout);
+            SNF("CumGHF", getCumGHF); SNF("CumUerror", getCumUerror); SNF("CumHrsSnow", getCumHrsSnow);
+            SNF("PersTimeMax", getPersTimeMax); SNF("PersTime", getPersTime); SNF("PeakSWE", getPeakSWE);
+            SNF("PeakSWETemp", getPeakSWETemp); SNF("InitPackTime", getInitPackTime); SNF("InitPackTimeTemp", getInitPackTimeTemp);
+            SNF("PeakPackTime", getPeakPackTime);
+#undef SNF
+        }
+        vector<double> sun = {E->alphaD, E->sinAlpha, E->sunaz, E->Io, (double)E->currentTime[3],
+                              (double)E->hourlyTimeStep, (double)E->dewHumFlag, (double)E->skycover_flag,
+                              E->del, E->phi, E->tau, E->deltaT, (double)E->nodeHour,
+                              E->latitude, E->longitude, (double)E->gmt};
         w.f64(pre + "sun", sun);
     }
 
@@ -706,7 +732,7 @@ int main(int argc, char **argv) {
 
     Harness H;
     H.mesh = &BasinMesh; H.flow = &Flow; H.hydro = &Moisture; H.timer = &Timer;
-    H.et = &EvapoTrans; H.icp = &Intercept; H.rainfall = &Rainfall;
+    H.et = &EvapoTrans; H.icp = &Intercept; H.rainfall = &Rainfall; H.snow = &SnowPack;
     H.index();
     if (do_basin) H.dump_basin(outdir + "/basin.trb", InputFile);
     if (do_kat) H.dump_kat(outdir + "/kat.trb");

@@ -7,8 +7,10 @@
 #include "tribs_oracle_et.h"
 #include <math.h>
 #include <stdlib.h>
+#include <string.h>
 
 #define F(name) etf[ORCET_##name][i]
+#define SF(name) snf[ORCSN_##name][i]
 
 typedef struct {
   /* met record of the cell (tEvapoTrans::newHydroMetData, tEvapoTrans.cpp:3962-4010) */
@@ -32,6 +34,8 @@ typedef struct {
   /* options */
   int etOpt, gOpt, shOpt;
   double timeStep, Tlinke;
+  double *const *snf;   /* snow fields of the nodes, or NULL without OPTSNOW */
+  double coeffLAI;
 } EtCell;
 
 /* ---- tEvapoTrans.cpp:1224-1413 */
@@ -350,6 +354,11 @@ static double energy_balance(EtCell *c, double *const *etf, int i) {
   F(SoilTemp) = c->Tlo - 273.15;
   F(NetRad) = c->netRadC; F(GFlux) = c->gFlux; F(HFlux) = c->hFlux; F(LFlux) = c->lFlux;
   F(LongRadOut) = c->outLongR;
+  if (c->snf) {   /* energyBalance clears the snow fluxes of the node, tEvapoTrans.cpp:2343-2351 */
+    double *const *snf = c->snf;
+    SF(SnLHF) = 0.0; SF(SnSHF) = 0.0; SF(SnSub) = 0.0; SF(SnEvap) = 0.0; SF(SnPHF) = 0.0; SF(SnGHF) = 0.0;
+    SF(SnRLin) = 0.0; SF(SnRLout) = 0.0; SF(SnRSin) = 0.0;
+  }
   return c->potEvap;
 }
 
@@ -393,53 +402,68 @@ static void beta_funcs(const orc_et_basin *b, const orc_et_shared *sh, EtCell *c
   c->betaT = beta;
 }
 
+/* met assembly of one cell: the part of callEvapoPotential / callSnowPack before the evaporation method */
+static void met_assembly(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
+                         double *const *etf, const orc_et_shared *sh, int i, EtCell *c) {
+  double vPress;
+  c->snf = NULL;
+  c->coeffLAI = b->land_table[(size_t)b->land_class[i] * 15 + 12];
+  c->rain = sh->Rain[i];
+  c->elevation = b->z[i];
+  c->slope = fabs(atan(b->flow_slope[i]));
+  c->aspect = b->aspect[i];
+  if (b->shelter_option == 0) { c->shelterFactor = 0.5 * (1 + cos(c->slope)); F(SheltFact) = c->shelterFactor; }
+  else c->shelterFactor = 1;
+  load_coeffs(b, c, i);
+  load_met(b, s, m, c, i);
+  if (s->first_call) { c->Tso = m->air_temp[m->cell_record[i]] + 273.15; c->Tlo = c->Tso; }
+  else { c->Tso = 0.0; c->Tlo = 0.0; }
+  c->skyFlag = (i >= s->sky_flag_from) || (fabs(c->skyCover - 9999.99) < 1.0E-3);
+  vPress = vapor_press(c);
+  F(AirTemp) = c->airTemp; F(DewTemp) = c->dewTemp; F(RelHumid) = c->rHumidity; F(VapPressure) = vPress;
+  if (c->skyFlag == 1) c->skyCover = comp_sky_cover(c);
+  F(SkyCover) = c->skyCover; F(WindSpeed) = c->windSpeed; F(AirPressure) = c->atmPress;
+  F(ShortRadIn) = c->inShortR;
+  if (s->first_call) { F(SoilTemp) = c->Tlo - 273.15; F(SurfTemp) = c->Tso - 273.15; }
+  if (b->i_option == 0) sh->NetPrecipitation[i] = c->rain;
+  beta_funcs(b, sh, c, i);
+  c->Tso = F(SurfTemp) + 273.15;
+  c->Tlo = F(SoilTemp) + 273.15;
+  c->Gso = 0.0;
+}
+
+/* EvapPenmanMonteith / Deardorff / PriestlyTaylor (tEvapoTrans.cpp:2790-2870) */
+static void evap_method(const orc_et_basin *b, double *const *etf, int i, EtCell *c) {
+  c->potEvap = 3600.0 * energy_balance(c, etf, i);
+  if (b->et_option == 1) c->actEvap = 3600.0 * (c->lFlux / (latent_heat(c)));
+  else c->actEvap = c->betaS * c->potEvap;
+}
+
+/* setToNode, tEvapoTrans.cpp:3039-3076 */
+static void set_to_node(const orc_et_step *s, double *const *etf, int i, EtCell *c) {
+  double tmp = 0;
+  if (c->dewHumFlag == 0) { F(DewTemp) = c->dewTempC; F(VapPressure) = c->vPressC; }
+  else if (c->dewHumFlag == 1) { F(VapPressure) = c->vPressC; F(RelHumid) = c->rHumidityC; }
+  else if (c->dewHumFlag == 2) { F(DewTemp) = c->dewTempC; F(RelHumid) = c->rHumidityC; }
+  F(PotEvap) = c->potEvap; F(ActEvap) = c->actEvap; F(AirTemp) = c->airTemp;
+  F(AirPressure) = c->atmPressC; F(SkyCover) = c->skyCoverC; F(WindSpeed) = c->windSpeedC;
+  F(CumHrsSun) += c->SunHour;
+  if ((fabs(c->hFlux) + fabs(c->lFlux)) > 1.0) tmp = fabs(c->lFlux) / (fabs(c->hFlux) + fabs(c->lFlux));
+  if (fabs(s->te_met - 1.0) <= 1.0E-6) F(AvEvapFract) = tmp;
+  else if (s->te_met > 1.0) F(AvEvapFract) = (F(AvEvapFract) * (s->te_met - 1.0) + tmp) / s->te_met;
+  F(SheltFact) = c->shelterFactor;
+  F(CumRSin) += c->inShortR * 3600.0;
+}
+
 int orc_et_potential(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
                      double *const *etf, const orc_et_shared *sh) {
   if (!(b->shelter_option == 0 || b->shelter_option >= 4)) return 1;
   if (b->et_option < 1 || b->et_option > 3) return 1;
   for (int i = 0; i < b->n; i++) {
     EtCell cell, *c = &cell;
-    double vPress, tmp;
-    c->rain = sh->Rain[i];
-    c->elevation = b->z[i];
-    c->slope = fabs(atan(b->flow_slope[i]));
-    c->aspect = b->aspect[i];
-    if (b->shelter_option == 0) { c->shelterFactor = 0.5 * (1 + cos(c->slope)); F(SheltFact) = c->shelterFactor; }
-    else c->shelterFactor = 1;
-    load_coeffs(b, c, i);
-    load_met(b, s, m, c, i);
-    if (s->first_call) { c->Tso = m->air_temp[m->cell_record[i]] + 273.15; c->Tlo = c->Tso; }
-    else { c->Tso = 0.0; c->Tlo = 0.0; }
-    c->skyFlag = (i >= s->sky_flag_from) || (fabs(c->skyCover - 9999.99) < 1.0E-3);
-    vPress = vapor_press(c);
-    F(AirTemp) = c->airTemp; F(DewTemp) = c->dewTemp; F(RelHumid) = c->rHumidity; F(VapPressure) = vPress;
-    if (c->skyFlag == 1) c->skyCover = comp_sky_cover(c);
-    F(SkyCover) = c->skyCover; F(WindSpeed) = c->windSpeed; F(AirPressure) = c->atmPress;
-    F(ShortRadIn) = c->inShortR;
-    if (s->first_call) { F(SoilTemp) = c->Tlo - 273.15; F(SurfTemp) = c->Tso - 273.15; }
-    if (b->i_option == 0) sh->NetPrecipitation[i] = c->rain;
-    beta_funcs(b, sh, c, i);
-    c->Tso = F(SurfTemp) + 273.15;
-    c->Tlo = F(SoilTemp) + 273.15;
-    c->Gso = 0.0;
-    /* EvapPenmanMonteith / Deardorff / PriestlyTaylor (tEvapoTrans.cpp:2790-2870) */
-    c->potEvap = 3600.0 * energy_balance(c, etf, i);
-    if (b->et_option == 1) c->actEvap = 3600.0 * (c->lFlux / (latent_heat(c)));
-    else if (b->et_option == 2) c->actEvap = c->betaS * c->potEvap;
-    else c->actEvap = c->betaS * c->potEvap;
-    /* setToNode, tEvapoTrans.cpp:3039-3076 */
-    if (c->dewHumFlag == 0) { F(DewTemp) = c->dewTempC; F(VapPressure) = c->vPressC; }
-    else if (c->dewHumFlag == 1) { F(VapPressure) = c->vPressC; F(RelHumid) = c->rHumidityC; }
-    else if (c->dewHumFlag == 2) { F(DewTemp) = c->dewTempC; F(RelHumid) = c->rHumidityC; }
-    F(PotEvap) = c->potEvap; F(ActEvap) = c->actEvap; F(AirTemp) = c->airTemp;
-    F(AirPressure) = c->atmPressC; F(SkyCover) = c->skyCoverC; F(WindSpeed) = c->windSpeedC;
-    F(CumHrsSun) += c->SunHour;
-    tmp = 0;
-    if ((fabs(c->hFlux) + fabs(c->lFlux)) > 1.0) tmp = fabs(c->lFlux) / (fabs(c->hFlux) + fabs(c->lFlux));
-    if (fabs(s->te_met - 1.0) <= 1.0E-6) F(AvEvapFract) = tmp;
-    else if (s->te_met > 1.0) F(AvEvapFract) = (F(AvEvapFract) * (s->te_met - 1.0) + tmp) / s->te_met;
-    F(SheltFact) = c->shelterFactor;
-    F(CumRSin) += c->inShortR * 3600.0;
+    met_assembly(b, s, m, etf, sh, i, c);
+    evap_method(b, etf, i, c);
+    set_to_node(s, etf, i, c);
   }
   return 0;
 }
@@ -536,9 +560,9 @@ static int there_is_canopy(const orc_et_basin *b, int i) {
 }
 
 /* ---- tEvapoTrans.cpp:980-1197 */
-int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
-                      double *const *etf, const orc_et_shared *sh, int flag) {
-  for (int i = 0; i < b->n; i++) {
+static void components_cell(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
+                            double *const *etf, const orc_et_shared *sh, int flag, int i) {
+  {
     EtCell cell, *c = &cell;
     double potEvaporation, actEvaporation, cc, psy, ra, rs, transFactor;
     double evapWetCanopy = 0.0, evapDryCanopy, evapSoil, evapoTranspiration;
@@ -546,7 +570,7 @@ int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met
       if (flag && there_is_canopy(b, i)) {
         if (b->i_option == 1) intercept_gray(b, etf, sh, i); else intercept_rutter(b, etf, sh, i, 0.0);
       }
-      continue;
+      return;
     }
     c->elevation = b->z[i];
     load_coeffs(b, c, i);
@@ -597,7 +621,414 @@ int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met
     if (fabs(s->te_eti - 1.0) < 1.0E-6) F(AvET) = evapoTranspiration;
     else if (s->te_eti > 1.0) F(AvET) = (F(AvET) * (s->te_eti - 1.0) + evapoTranspiration) / s->te_eti;
   }
+}
+
+int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
+                      double *const *etf, const orc_et_shared *sh, int flag) {
+  for (int i = 0; i < b->n; i++) components_cell(b, s, m, etf, sh, flag, i);
   return 0;
 }
 
 int orc_et_n_fields(void) { return ORC_N_ET_FIELDS; }
+
+/* ==================================================================== snow pack (tSnowPack.cpp) */
+typedef struct {   /* the tSnowPack members one cell works with */
+  double liqWE, iceWE, snWE, snSub, snEvap, liqRoute, Utot, Usn, Uwat, Utotold, liqWatCont;
+  double liqTempC, iceTempC, snTempC, crustAge, densityAge, ETAge;
+  double H, L, G, Prec, Rn, dUint, RLin, RLout, RSin, Uerr, snPrec, liqPrec, snUnload, snCanWE;
+  double Qcs, I, Iold, Imax, LAI, Lm, airTempK, phfOnOff, albedo, snDepthm, snOnOff;
+  double peakSnWE, peakSnWEtemp, persMax, persMaxtemp, inittime, inittimeTemp, peaktime;
+  double timeSteph, timeSteps, timeStepm, minSnTemp, snliqfrac;
+  int hillAlbedoOption, hourly;
+} Snow;
+
+static const double rholiqkg = 1000.0, rhoicekg = 920.0, rhoAir = 1.3, cpicekJ = 2.1, cpwaterkJ = 4.190, cpairkJ = 1.006;
+static const double latFreezekJ = 334.0, latVapkJ = 2470.0, latSubkJ = 334.0 + 2470.0;
+static const double naughttokilo = 1e-3, kilotonaught = 1e3, naughttocm = 100.0, cmtonaught = 0.01, ctom = 10.0, mtoc = 0.1;
+#define REF_PI 3.1415926
+
+/* tSnowPack.cpp:1244-1290 */
+static double snow_frac(const EtCell *c) {
+  double Ta = c->airTemp, RH = c->rHumidity, Tw, f1;
+  Tw = Ta * atan(0.151977 * pow(RH + 8.313659, 0.5)) + atan(Ta + RH) - atan(RH - 1.676331) +
+       0.00391838 * pow(RH, 1.5) * atan(0.023101 * RH) - 4.686035;
+  f1 = 1 + 6.99 * pow(10, -5) * exp(2 * (Tw + 3.97));
+  if (Tw > 5) return 0;
+  return 1 / f1;
+}
+
+/* tSnowPack.cpp:1373-1480 */
+static double res_fact(const EtCell *c, const Snow *w) {
+  const double vonKarm = 0.41, g = 9.81, Ri_cr = 0.1;
+  double windSpeedC, windSpeedS, ra, vegHeight, vegFrac, vegBare, zm, zom, zov, d, rav, ras;
+  windSpeedC = (c->windSpeed == 0.0 || fabs(c->windSpeed - 9999.99) < 1e-3) ? 0.01 : c->windSpeed;
+  vegHeight = (c->coeffH <= 0) ? 0.1 : c->coeffH;
+  vegHeight = (vegHeight > w->snDepthm) ? vegHeight - w->snDepthm : 0.1;
+  vegBare = 0.1;
+  vegFrac = c->coeffV;
+  if (w->snDepthm < c->coeffH) windSpeedS = windSpeedC * exp(-0.5 * c->coeffLAI * (1.0 - (w->snDepthm / c->coeffH)));
+  else windSpeedS = windSpeedC;
+  zm = 2.0 + vegHeight; zom = 0.123 * vegHeight; zov = 0.0123 * vegHeight; d = 0.67 * vegHeight;
+  rav = log((zm - d) / zom) * log((zm - d) / zov) / (windSpeedC * pow(vonKarm, 2));
+  zm = 2.0 + vegBare; zom = 0.123 * vegBare; zov = 0.0123 * vegBare; d = 0.67 * vegBare;
+  ras = log((zm - d) / zom) * log((zm - d) / zov) / (windSpeedS * pow(vonKarm, 2));
+  ra = (1 - vegFrac) * ras + vegFrac * rav;
+  double Ts = (w->liqWE > 1e-5) ? 273.15 : w->snTempC + 273.15;
+  double Ta = c->airTemp + 273.15, T_avg = 0.5 * (Ta + Ts);
+  double zm_eff = (0.1 > 2.0 - w->snDepthm) ? 0.1 : 2.0 - w->snDepthm;
+  double z0 = 0.123 * vegHeight;
+  double RiB = (g * zm_eff * (Ta - Ts)) / (T_avg * windSpeedS * windSpeedS);
+  double Ri_u = 1.0 / (log(zm_eff / z0) + 5.0), C_stab;
+  if (RiB < 0.0) C_stab = pow(1.0 - 16.0 * RiB, 0.5);
+  else if (RiB <= Ri_u) C_stab = 1.0 / pow(1.0 - (RiB / Ri_cr), 2.0);
+  else C_stab = 1.0 / pow(1.0 - (Ri_u / Ri_cr), 2.0);
+  if (C_stab > 15.0) C_stab = 15.0;
+  ra *= C_stab;
+  return 1.0 / ra;
+}
+
+/* tSnowPack.cpp:1177-1236 */
+static double latent_hf(const EtCell *c, const Snow *w, double Kaero) {
+  double t = (w->liqWE > 1e-5) ? 0.0 : w->snTempC;
+  if (t == 0.0) return (latVapkJ * 0.622 * rhoAir * Kaero * (c->vPress - 6.111) / c->atmPress);
+  return (latSubkJ * 0.622 * rhoAir * Kaero * (c->vPress - 6.112 * exp((17.67 * t) / (t + 243.5))) / c->atmPress);
+}
+static double sensible_hf(const EtCell *c, const Snow *w, double Kaero) {
+  double t = (w->liqWE > 1e-5) ? 0.0 : w->snTempC;
+  return (rhoAir * cpairkJ * Kaero * ((c->airTemp + 273.15) - (t + 273.15)));
+}
+
+/* tSnowPack.cpp:1298-1328 */
+static double precip_hf(const EtCell *c, Snow *w) {
+  double phf = 0;
+  w->snPrec = (snow_frac(c) * (c->rain + ctom * w->snUnload)) * mtoc;
+  w->liqPrec = ((1 - snow_frac(c)) * (c->rain + ctom * w->snUnload)) * mtoc;
+  if (c->airTemp > 0)
+    phf = (cmtonaught * w->snPrec * 0 * rholiqkg * cpicekJ + cmtonaught * w->liqPrec * (latFreezekJ + c->airTemp * rholiqkg * cpwaterkJ)) / 3600;
+  else if (c->airTemp <= 0)
+    phf = (cmtonaught * w->snPrec * c->airTemp * rholiqkg * cpicekJ + cmtonaught * w->liqPrec * latFreezekJ * rholiqkg) / 3600;
+  return phf;
+}
+
+/* tSnowPack.cpp:1336-1365 */
+static double aging_albedo(const Snow *w) {
+  double alb;
+  if (w->liqWE < 1.0E-5) alb = 0.85 * pow(0.96, pow(w->crustAge / 24.0, 0.58));
+  else alb = 0.85 * pow(0.87, pow(w->crustAge / 24.0, 0.46));
+  if (alb < 0.45) alb = 0.45;
+  return alb;
+}
+
+/* tSnowPack.cpp:944-990 */
+static void update_ripe(const EtCell *c, Snow *w, double precip) {
+  w->snEvap = (1 - c->coeffV) * latent_hf(c, w, res_fact(c, w)) * w->timeSteps / (rholiqkg * latVapkJ);
+  w->liqWE += cmtonaught * ((mtoc * precip) * (1 - snow_frac(c))) * w->timeSteps / 3600;
+  if (w->liqWE + w->snEvap <= 0) { w->snEvap = w->liqWE; w->liqWE = 0; }
+  else w->liqWE += w->snEvap;
+  w->iceWE += cmtonaught * (mtoc * (precip * snow_frac(c))) * w->timeSteps / 3600;
+  w->snSub = 0.0;
+}
+static void update_solid(const EtCell *c, Snow *w, double precip) {
+  w->liqWE += cmtonaught * (mtoc * (precip * (1 - snow_frac(c)))) * w->timeSteps / 3600;
+  w->snEvap = 0.0;
+  w->snSub = (1 - c->coeffV) * latent_hf(c, w, res_fact(c, w)) * w->timeSteps / (rholiqkg * latSubkJ);
+  w->iceWE += cmtonaught * (mtoc * (precip * snow_frac(c))) * w->timeSteps / 3600;
+  if (w->iceWE + w->snSub <= 0) { w->snSub = w->iceWE; w->iceWE = 0; }
+  else w->iceWE += w->snSub;
+}
+
+/* tSnowPack.cpp:1574-1748 (shelter options 0 and >= 4) */
+static double in_short_wave_sn(EtCell *c, Snow *w, double *const *etf, int i, int snow_option) {
+  double Is = 0, N = 0, Iv = 0, Isw = 0, Ir = 0, v, cosi, hillalbedo = 0;
+  c->Ic = c->Id = c->Ids = c->Ics = 0.0;
+  c->SunHour = 0.0;
+  if (c->alphaD > 0.0) {
+    direct_diffuse(c, c->elevation);
+    N = 0;
+    if (c->tsOption > 1) {
+      double RadGlobClr = (c->inShortR / (1.0 - 0.65 * pow(N, 2.0)));
+      c->Ic = c->Ic / (c->Ic * c->sinAlpha + c->Id) * RadGlobClr;
+      c->Id = RadGlobClr - c->Ic * c->sinAlpha;
+    }
+    if (c->shOpt < 4) {
+      cosi = 1.0 * (cos(c->slope) * c->sinAlpha + sin(c->slope) * cos(asin(c->sinAlpha)) * cos(c->sunaz - c->aspect));
+      if (cosi >= 0.0) { c->Ics = c->Ic * cosi; c->SunHour = 1.0; }
+      else { c->Ics = 0.0; c->SunHour = 0.0; }
+    } else { c->Ics = 1.0 * c->Ic; c->SunHour = 1.0; }
+    if (c->shOpt == 0 || c->shOpt == 3) v = 0.5 * (1 + cos(c->slope));
+    else v = 1.0;
+    c->Ids = c->Id * v;
+    Is = (1.0 - 0.65 * pow(N, 2)) * (c->Ics + c->Ids);
+    if (w->hillAlbedoOption == 0) hillalbedo = w->albedo;
+    else if (w->hillAlbedoOption == 1) hillalbedo = c->coeffAl;
+    else if (w->hillAlbedoOption == 2) {
+      if (w->snCanWE == 0) hillalbedo = c->coeffV * c->coeffAl + (1 - c->coeffV) * w->albedo;
+      else hillalbedo = w->albedo;
+    }
+    if (c->shOpt == 0) { Ir = hillalbedo * Is * (1 - cos(c->slope)) * 0.5; Is += Ir; }
+    else Ir = 0.0;
+    if ((c->etOpt == 1) || snow_option) Iv = Is * exp((c->coeffKt - 1) * c->coeffLAI) * c->coeffV + Is * (1.0 - c->coeffV);
+    else Iv = Is;
+    Isw = Iv * (1.0 - w->albedo);
+  } else {
+    c->Ic = Is = N = Iv = Isw = c->Id = c->Ids = c->Ics = Ir = 0.0;
+  }
+  c->Is = Is;
+  if (c->tsOption > 1) F(ShortRadIn) = c->inShortR;
+  else F(ShortRadIn) = Isw;
+  F(ShortRadIn_dir) = c->Ics * (1.0 - 0.65 * pow(N, 2.0));
+  F(ShortRadIn_dif) = (c->Ids + Ir) * (1.0 - 0.65 * pow(N, 2.0));
+  return Isw;
+}
+
+/* tSnowPack.cpp:1940-2001 */
+static void snow_eb(EtCell *c, Snow *w, double *const *etf, double *const *snf, int i) {
+  double sigma = 5.67e-8, v1 = 1, snTempK, resFact;
+  snTempK = w->snTempC + 273.15;
+  resFact = res_fact(c, w);
+  w->H = sensible_hf(c, w, resFact);
+  w->L = latent_hf(c, w, resFact);
+  w->Prec = w->phfOnOff * precip_hf(c, w);
+  w->RSin = naughttokilo * in_short_wave_sn(c, w, etf, i, 1);
+  w->RLin = naughttokilo * in_long_wave(c);
+  w->RLout = -naughttokilo * v1 * 0.9 * sigma * pow(snTempK, 4.0);
+  c->inShortR = kilotonaught * w->RSin;
+  c->inLongR = kilotonaught * w->RLin;
+  c->outLongR = kilotonaught * w->RLout;
+  F(HFlux) = 0.0; F(LFlux) = 0.0; F(LongRadIn) = 0.0; F(LongRadOut) = 0.0; F(ShortAbsbVeg) = 0.0; F(ShortAbsbSoi) = 0.0;
+  SF(SnLHF) = w->L * kilotonaught; SF(SnSHF) = w->H * kilotonaught; SF(SnPHF) = w->Prec * kilotonaught;
+  SF(SnGHF) = w->G * kilotonaught; SF(SnRLin) = w->RLin * kilotonaught; SF(SnRLout) = w->RLout * kilotonaught;
+  SF(SnRSin) = w->RSin * kilotonaught;
+  w->Rn = w->RSin + w->RLin + w->RLout;
+  w->G = 0;
+  w->dUint = (w->H + w->Rn + w->L + w->Prec + w->G) * w->timeSteps;
+  w->Utot += w->dUint;
+}
+
+/* tSnowPack.cpp:1492-1568 */
+static void compute_sub(const EtCell *c, Snow *w) {
+  const double kc = 0.010, iceRad = 500e-6, Mwater = 18.01, R = 8313.0, RdryAir = 287.0, nu = 1.3e-5, KtAtm = 0.024, beta = 0.9;
+  double Sp, acoefficient, windSpeedC, Re, Sh, Nu, esatIce, rhoVap, D, Omega, dmdt, psiS, Ce;
+  Sp = REF_PI * pow(iceRad, 2.0) * (1 - w->albedo) * c->inShortR;
+  acoefficient = beta * c->coeffLAI;
+  windSpeedC = c->windSpeed * exp(-acoefficient * 0.4);
+  Re = 2 * iceRad * windSpeedC / nu;
+  Sh = 1.79 + 0.606 * pow(Re, 0.5);
+  Nu = Sh;
+  esatIce = 611.15 * exp(22.452 * (w->airTempK - 273.16) / (w->airTempK - 0.61));
+  rhoVap = 0.622 * esatIce / (RdryAir * w->airTempK);
+  D = 2.06e-5 * pow(w->airTempK / 273.0, 1.75);
+  Omega = (1 / (KtAtm * w->airTempK * Nu)) * (1000 * latSubkJ * Mwater / (R * w->airTempK) - 1);
+  dmdt = (2.0 * REF_PI * iceRad * (c->rHumidityC / 100 - 1) - Sp * Omega) / (1000 * latSubkJ * Omega + (1 / (D * rhoVap * Sh)));
+  psiS = dmdt / ((4.0 / 3.0) * REF_PI * rhoicekg * iceRad * iceRad * iceRad);
+  Ce = kc * pow(w->I / w->Imax, -0.4);
+  w->Qcs = Ce * w->I * psiS * w->timeSteps;
+}
+
+static void set_to_node_snp(Snow *w, const orc_snow_args *sn, double *const *etf, double *const *snf, int i) {
+  sn->LiqWE[i] = w->liqWE; sn->IceWE[i] = w->iceWE;
+  SF(SnTempC) = w->snTempC; SF(CrustAge) = w->crustAge; SF(DensityAge) = w->densityAge; SF(EvapoTransAge) = w->ETAge;
+  SF(SnSub) = w->snSub; SF(SnEvap) = w->snEvap;
+  sn->LiqRouted[i] = w->liqRoute;
+  SF(DU) = w->dUint; SF(Unode) = w->Utot; SF(Uerror) = w->Uerr;
+  if ((w->iceWE + w->liqWE) <= 1e-5) { w->persMaxtemp = 0.0; w->inittimeTemp = 0.0; }
+  if (w->snWE > 1e-5) {
+    w->persMaxtemp += 1.0;
+    if (w->persMaxtemp > w->persMax) {
+      w->persMax = w->persMaxtemp;
+      if (w->persMaxtemp - 1 < 1) w->inittimeTemp = w->hourly;
+    }
+  }
+  if (w->snWE >= w->peakSnWE) { w->peakSnWE = w->snWE; w->peaktime = w->hourly; w->inittime = w->inittimeTemp; }
+  SF(PersTimeMax) = w->persMax; SF(PersTime) = w->persMaxtemp; SF(PeakSWE) = w->peakSnWE;
+  SF(PeakPackTime) = (double)w->peaktime; SF(InitPackTime) = (double)w->inittime; SF(InitPackTimeTemp) = (double)w->inittimeTemp;
+  SF(CumLHF) += w->L; SF(CumSnSub) += w->snSub; SF(CumSnEvap) += w->snEvap; SF(CumMelt) += w->liqRoute;
+  SF(CumSHF) += w->H * w->timeSteps; SF(CumPHF) += w->Prec * w->timeSteps; SF(CumGHF) += w->G * w->timeSteps;
+  SF(CumRLin) += w->RLin * w->timeSteps; SF(CumRLout) += w->RLout * w->timeSteps;
+  F(CumRSin) += w->RSin * w->timeSteps;
+  SF(CumUerror) += w->Uerr * w->timeSteps;
+  SF(CumHrsSnow) += w->snOnOff;
+  w->L = w->H = w->Prec = w->G = w->RLin = w->RLout = w->RSin = w->dUint = 0.0;
+  w->liqRoute = 0.0;
+}
+
+/* route liquid above the holding capacity (tSnowPack.cpp:536-553, 655-672) */
+static void route_excess_liquid(Snow *w) {
+  if (w->liqWE > w->snliqfrac * w->iceWE) {
+    if (w->liqWE != w->snWE) {
+      w->liqRoute = (w->liqWE - w->snliqfrac * w->iceWE);
+      w->liqWE = w->liqWE - w->liqRoute;
+      w->snWE = w->liqWE + w->iceWE;
+    } else {
+      w->liqRoute = w->snWE;
+      w->liqWE = 0.0; w->iceWE = 0.0; w->snWE = 0.0;
+    }
+  }
+}
+
+int orc_snow_pack(const orc_et_basin *b, const orc_snow_args *sn, const orc_et_step *s, const orc_met *m,
+                  double *const *etf, double *const *snf, const orc_et_shared *sh, int flag, double *members) {
+  Snow W, *w = &W;
+  if (!(b->shelter_option == 0 || b->shelter_option >= 4)) return 1;
+  if (b->et_option < 1 || b->et_option > 3) return 1;
+  memset(w, 0, sizeof W);
+  w->albedo = members[0]; w->Uerr = members[1]; w->snCanWE = members[2];
+  w->timeStepm = b->metstep_min; w->timeSteph = w->timeStepm / 60.0; w->timeSteps = 60.0 * w->timeStepm;
+  w->minSnTemp = sn->min_sn_temp; w->snliqfrac = sn->snliqfrac; w->hillAlbedoOption = sn->hill_albedo_option;
+  w->hourly = sn->hourly_time_step;
+  for (int i = 0; i < b->n; i++) {
+    EtCell cell, *c = &cell;
+    double precip = 0.0, vegHeight = 0;
+    w->snOnOff = 0.0;
+    met_assembly(b, s, m, etf, sh, i, c);
+    c->snf = snf;
+    /* getFrNodeSnP, tSnowPack.cpp:999-1044 */
+    w->liqWE = sn->LiqWE[i]; w->iceWE = sn->IceWE[i]; w->liqRoute = 0.0;
+    w->snWE = w->liqWE + w->iceWE;
+    if (w->snWE > 1e-4) { w->snTempC = SF(SnTempC); w->iceTempC = w->snTempC; w->liqTempC = 0.0; }
+    else if (c->airTemp > 0.0) { w->snTempC = 0.0; w->iceTempC = 0.0; w->liqTempC = 0.0; }
+    else if (c->airTemp <= 0.0) { w->snTempC = c->airTemp; w->iceTempC = c->airTemp; w->liqTempC = c->airTemp; }
+    w->crustAge = SF(CrustAge); w->densityAge = SF(DensityAge); w->ETAge = SF(EvapoTransAge);
+    w->persMax = SF(PersTimeMax); w->persMaxtemp = SF(PersTime); w->peakSnWE = SF(PeakSWE); w->peakSnWEtemp = SF(PeakSWETemp);
+    w->inittime = SF(InitPackTime); w->inittimeTemp = SF(InitPackTimeTemp); w->peaktime = SF(PeakPackTime);
+    sn->LiqRouted[i] = 0.0;
+    w->snUnload = 0.0;
+
+    if ((w->snWE <= 1e-4) && (c->rain * snow_frac(c) <= 5e-2) && rholiqkg * cmtonaught * SF(IntSWE) < 1e-3) {
+      /* no snow anywhere: the ET path */
+      evap_method(b, etf, i, c);
+      set_to_node(s, etf, i, c);
+      components_cell(b, s, m, etf, sh, flag, i);
+      w->snTempC = 0.0; w->snWE = 0.0; w->snSub = 0.0; w->snEvap = 0.0;
+      w->dUint = w->RLin = w->RLout = w->RSin = w->H = w->L = w->G = w->Prec = 0.0;
+      w->ETAge = w->ETAge + w->timeStepm;
+      w->liqRoute = 0.0; w->iceWE = 0.0; w->liqWE = 0.0; w->Utot = 0.0; w->Usn = 0.0; w->Uwat = 0.0;
+      w->snTempC = 0.0; w->crustAge = 0.0; w->densityAge = 0.0;
+      SF(IntSub) = 0.0;
+      set_to_node_snp(w, sn, etf, snf, i);
+    } else {
+      if (b->i_option && there_is_canopy(b, i)) {
+        /* callSnowIntercept, tSnowPack.cpp:769-934 */
+        double CanStorage = F(CanStorage), prec = sh->Rain[i], Isnow, throughfall, subFrac, unlFrac;
+        int fl = 1;
+        c->rHumidity = F(RelHumid); c->vPress = F(VapPressure); c->dewTemp = F(DewTemp); c->windSpeed = F(WindSpeed);
+        c->atmPress = F(AirPressure); c->inShortR = F(ShortRadIn); c->airTemp = F(AirTemp);
+        w->airTempK = c->airTemp + 273.15;
+        w->LAI = c->coeffLAI;
+        w->Iold = rholiqkg * cmtonaught * SF(IntSWE);
+        w->Qcs = 0.0; w->Lm = 0.0;
+        if ((prec * snow_frac(c) < 1e-4) && (w->Iold < 1e-3)) {
+          w->I = w->Iold = w->Lm = w->Qcs = 0.0;
+          evap_method(b, etf, i, c);
+          F(NetRad) = 0.0; F(GFlux) = 0.0; F(HFlux) = 0.0; F(LFlux) = 0.0; F(LongRadOut) = 0.0;
+          F(SurfTemp) = SF(SnTempC); F(SoilTemp) = SF(SnTempC);
+          set_to_node(s, etf, i, c);
+          F(ActEvap) = 0.0;
+          components_cell(b, s, m, etf, sh, 1, i);
+          SF(IntSWE) = 0; SF(IntSnUnload) = 0; SF(IntSub) = 0; SF(IntPrec) = 0;
+          sh->EvapSoil[i] = 0.0;
+        } else {
+          if (CanStorage > 1e-5) { w->Iold += CanStorage; F(CanStorage) = 0.0; fl = 0; }
+          w->Imax = 4.4 * w->LAI;
+          Isnow = 0.7 * (w->Imax - w->Iold) * (1 - exp(-prec / w->Imax));
+          w->I = w->Iold + Isnow;
+          throughfall = prec - Isnow;
+          if (w->Iold > 0.0 && fl) {
+            compute_sub(c, w);
+            if (w->airTempK >= 273.16) w->Lm = 5.8e-5 * (w->airTempK - 273.16) * w->timeSteps;
+            else w->Lm = 0.0;
+          } else { w->Qcs = 0.0; w->Lm = 0.0; }
+          w->I += w->Qcs - w->Lm;
+          if (w->I < 0.0) {
+            if (w->Qcs < 0.0) { subFrac = fabs(w->Qcs) / (fabs(w->Qcs) + w->Lm); unlFrac = w->Lm / (fabs(w->Qcs) + w->Lm); }
+            else { subFrac = 0.0; unlFrac = 1.0; }
+            w->Qcs -= w->I * subFrac;
+            w->Lm += w->I * unlFrac;
+            w->I = 0.0;
+          }
+          w->Iold = w->I;
+          SF(IntSWE) = naughttocm * (1 / rholiqkg) * w->I;
+          SF(IntSnUnload) = naughttocm * (1 / rholiqkg) * w->Lm * c->coeffV;
+          SF(IntSub) = naughttocm * (1 / rholiqkg) * w->Qcs * c->coeffV;
+          SF(CumIntSub) += naughttocm * (1 / rholiqkg) * w->Qcs * c->coeffV;
+          SF(CumIntUnl) += naughttocm * (1 / rholiqkg) * w->Lm * c->coeffV;
+          SF(IntPrec) = Isnow * (1 / rholiqkg) * naughttocm;
+          sh->NetPrecipitation[i] = (throughfall * c->coeffV) + (sh->Rain[i] * (1 - c->coeffV));
+          F(EvapWetCanopy) = 0.0; sh->EvapDryCanopy[i] = 0.0; sh->EvapSoil[i] = 0.0; F(EvapoTrans) = 0.0; F(PotEvap) = 0.0;
+        }
+        w->snUnload = SF(IntSnUnload);
+        w->snCanWE = SF(IntSWE);
+      } else {
+        sh->NetPrecipitation[i] = c->rain;
+      }
+      precip = sh->NetPrecipitation[i];
+      precip += w->snUnload * ctom;
+      w->snDepthm = cmtonaught * w->snWE / 0.312;
+      w->iceWE = w->iceWE * cmtonaught; w->liqWE = w->liqWE * cmtonaught; w->snWE = w->iceWE + w->liqWE;
+      vegHeight = (c->coeffH == 0) ? 0.1 : c->coeffH;
+      (void)vegHeight;
+      if (c->airTemp > 0.0) w->snTempC = 0.0; else w->snTempC = c->airTemp;
+      if (w->snWE < 1e-5) {
+        w->phfOnOff = 0.0; w->densityAge = 0.0; w->crustAge = 0.0;
+        if (w->snTempC == 0.0) update_ripe(c, w, precip); else update_solid(c, w, precip);
+        w->snWE = w->iceWE + w->liqWE;
+        w->snSub *= naughttocm; w->snEvap *= naughttocm;
+        w->L = w->H = w->G = w->Prec = w->Utotold = 0.0;
+        route_excess_liquid(w);
+        if (w->liqWE < 0) { w->liqWE = 0; w->snWE = w->iceWE; }
+        w->Utot = w->dUint = w->iceWE * rhoicekg * cpicekJ * w->snTempC + w->liqWE * rholiqkg * latFreezekJ;
+      } else {
+        w->phfOnOff = 1.0;
+        w->densityAge = (w->snWE * w->densityAge) / (w->snWE + mtoc * precip);
+        if (precip * snow_frac(c) > 1e-3) w->crustAge = 0.0;
+        if (w->snTempC == 0.0) update_ripe(c, w, precip); else update_solid(c, w, precip);
+        w->snWE = w->iceWE + w->liqWE;
+        w->snSub *= naughttocm; w->snEvap *= naughttocm;
+        w->ETAge = 0.0;
+        w->L = latent_hf(c, w, res_fact(c, w));
+        w->Prec = precip_hf(c, w);
+        if ((w->snWE <= 5e-6) || (w->snTempC < -800.0)) {
+          w->liqRoute = 0.0; w->snWE = 0.0; w->iceWE = 0.0; w->liqWE = 0.0; w->Utot = 0.0; w->Usn = 0.0; w->Uwat = 0.0;
+          w->snTempC = 0.0; w->crustAge = 0.0; w->densityAge = 0.0;
+        } else {
+          w->Utot = w->Utotold = w->iceWE * rhoicekg * cpicekJ * w->snTempC + w->liqWE * rholiqkg * latFreezekJ;
+          w->albedo = aging_albedo(w);
+          snow_eb(c, w, etf, snf, i);
+          w->Uerr = (w->Utot - w->Utotold) - w->dUint;
+          if (w->Utot < 0.0) {
+            w->Usn = w->Utot; w->Uwat = 0.0; w->liqWatCont = 0.0; w->liqWE = 0.0; w->liqTempC = 0.0;
+            w->iceWE = w->snWE;
+            if (w->iceWE < 0.1 && w->iceWE > 0) w->iceTempC = w->Usn / (cpicekJ * rhoicekg * 0.1);
+            else w->iceTempC = w->Usn / (cpicekJ * rhoicekg * w->snWE);
+            if (w->iceTempC <= w->minSnTemp) w->iceTempC = w->minSnTemp;
+            w->snTempC = w->iceTempC;
+          } else {
+            w->Uwat = w->Utot; w->Usn = 0.0;
+            w->liqWE = w->Uwat / (latFreezekJ * rholiqkg);
+            if (w->liqWE >= w->snWE) w->liqWE = w->snWE;
+            w->iceWE = w->snWE - w->liqWE;
+            route_excess_liquid(w);
+            w->snTempC = 0.0; w->iceTempC = 0.0; w->liqTempC = 0.0;
+          }
+        }
+      }
+      if (w->snWE <= 5e-6) {
+        w->liqRoute += w->snWE;
+        w->snWE = 0.0; w->liqWE = 0.0; w->iceWE = 0.0; w->crustAge = 0.0; w->densityAge = 0.0;
+        w->Utot = 0.0; w->Usn = 0.0; w->Uwat = 0.0;
+      } else {
+        w->crustAge += w->timeSteph; w->densityAge += w->timeSteph; w->snOnOff = 1.0;
+      }
+      w->snWE = naughttocm * w->snWE; w->iceWE = naughttocm * w->iceWE; w->liqWE = naughttocm * w->liqWE;
+      w->liqRoute = naughttocm * w->liqRoute;
+      sh->EvapSoil[i] = 0.0;
+      F(ActEvap) = 0.0;
+      F(EvapoTrans) = F(EvapWetCanopy) + sh->EvapDryCanopy[i];
+      set_to_node_snp(w, sn, etf, snf, i);
+    }
+  }
+  members[0] = w->albedo; members[1] = w->Uerr; members[2] = w->snCanWE;
+  return 0;
+}
+
+int orc_snow_n_fields(void) { return ORC_N_SNOW_FIELDS; }

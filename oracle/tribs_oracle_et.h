@@ -75,6 +75,34 @@ int orc_et_components(const orc_et_basin *b, const orc_et_step *s, const orc_met
                       double *const *etf, const orc_et_shared *sh, int flag);
 int orc_et_n_fields(void);
 
+/* ---------------------------------------------------------------- snow (tSnowPack::callSnowPack)
+ * Single-layer snow pack energy/mass balance with canopy snow interception
+ * (src/tHydro/tSnowPack.cpp:249-757, 769-934, 944-2001). The reference keeps some working values in
+ * class members that are NOT reset for every cell (`albedo` is read by computeSub before the
+ * cell's own agingAlbedo; `Uerr` is written only when the energy balance ran): they carry over
+ * from the previous cell in sweep order and from the previous call. `members` holds them between
+ * calls: [0] albedo (start 0.88), [1] Uerr (start 0), [2] snCanWE (start 0). */
+#define ORC_SNOW_FIELDS(X) \
+  X(SnTempC) X(CrustAge) X(DensityAge) X(EvapoTransAge) X(SnSub) X(SnEvap) X(DU) X(Unode) X(Uerror) \
+  X(SnLHF) X(SnSHF) X(SnGHF) X(SnPHF) X(SnRLout) X(SnRLin) X(SnRSin) \
+  X(IntSWE) X(IntPrec) X(IntSnUnload) X(IntSub) X(CumIntSub) X(CumIntUnl) \
+  X(CumLHF) X(CumMelt) X(CumSHF) X(CumSnSub) X(CumSnEvap) X(CumPHF) X(CumRLin) X(CumRLout) X(CumGHF) \
+  X(CumUerror) X(CumHrsSnow) X(PersTimeMax) X(PersTime) X(PeakSWE) X(PeakSWETemp) X(InitPackTime) \
+  X(InitPackTimeTemp) X(PeakPackTime)
+#define ORC_SNOW_ENUM(name) ORCSN_##name,
+enum { ORC_SNOW_FIELDS(ORC_SNOW_ENUM) ORC_N_SNOW_FIELDS };
+
+typedef struct {
+  double min_sn_temp, snliqfrac;   /* MINSNTEMP, SNLIQFRAC */
+  int32_t hill_albedo_option;      /* HILLALBOPT */
+  int32_t hourly_time_step;        /* tEvapoTrans::hourlyTimeStep of this call */
+  double *LiqWE, *IceWE, *LiqRouted;   /* arrays shared with the water-balance sweeps */
+} orc_snow_args;
+
+int orc_snow_pack(const orc_et_basin *b, const orc_snow_args *sn, const orc_et_step *s, const orc_met *m,
+                  double *const *etf, double *const *snf, const orc_et_shared *sh, int flag, double *members);
+int orc_snow_n_fields(void);
+
 #ifdef __cplusplus
 }
 #endif

@@ -110,10 +110,17 @@ class OracleStepper:
             self.cal.advance(self.m.time, self.m.B.tstep)
             met_due, eti_due = self.clock.due(self.m.time)
             self._met_due = met_due
-            if met_due:
-                self.et.potential(*self.host.potential_call(self.cal.hour, self.m.time))
-            if eti_due:
-                self.et.components(*self.host.components_call(self.m.time))
+            if self.et.snow:     # tSimul.cpp:464-492: callSnowPack at met_hour replaces both sweeps
+                if met_due:
+                    hourly = self.host.hourlyTimeStep
+                    step, rec = self.host.potential_call(self.cal.hour, self.m.time)
+                    step["te_eti"] = float(int(self.m.time / self.host.etistep))
+                    self.et.snow_pack(step, rec, hourly)
+            else:
+                if met_due:
+                    self.et.potential(*self.host.potential_call(self.cal.hour, self.m.time))
+                if eti_due:
+                    self.et.components(*self.host.components_call(self.m.time))
         if self.evap > 0.0:
             self.m.state["EvapSoil"][:] = np.where(self.m.state["Rain"] > 0.0, 0.0, self.evap)
 

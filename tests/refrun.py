@@ -34,6 +34,9 @@ SCENARIOS = {
     # rain gauges + one weather station: Penman-Monteith energy balance, Rutter interception
     # (kernel 1) feeding the unsaturated zone through EvapSoil / EvapDryCanopy / NetPrecipitation
     "met": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0),
+    # the same with sub-zero temperatures and OPTSNOW 1: snow pack energy balance, canopy snow
+    # interception, melt routed to the unsaturated zone (oracle only so far: no device kernel yet)
+    "snow": dict(runtime_h=72.0, forcing="met", winter=True, gw_depth_mm=1500.0, pmean=6.0, stdur=5.0),
     "evap": dict(runtime_h=72.0, gw_depth_mm=350.0, pmean=25.0, stdur=4.0, istdur=20.0, inject_evap=0.6),
 }
 
@@ -90,6 +93,10 @@ def schedule_for(basin):
         return GaugeRain(basin)
     from oracle.pyoracle import stochastic_storm_schedule
     return stochastic_storm_schedule(*storm_of(basin))
+
+
+# scenarios the device path covers (tSnowPack has an oracle but no kernel yet)
+GPU_SCENARIOS = [k for k in SCENARIOS if k != "snow"]
 
 
 def has_et(basin) -> bool:

@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 from common import STATE_FIELDS, GpuStepper, OracleStepper, run_and_compare
-from refrun import SCENARIOS, have_harness, load_golden, run_reference, schedule_for, spec_for, storm_of
+from refrun import GPU_SCENARIOS, have_harness, load_golden, run_reference, schedule_for, spec_for, storm_of
 
 pytestmark = pytest.mark.gpu
 
@@ -21,7 +21,7 @@ def _sched(basin):
     return schedule_for(basin)
 
 
-@pytest.mark.parametrize("name", list(SCENARIOS))
+@pytest.mark.parametrize("name", GPU_SCENARIOS)
 def test_gpu_matches_reference_golden(name, built):
     basin, snaps, _ = load_golden(name)
     n_steps = int(snaps["n_steps"][0])

@@ -128,3 +128,17 @@ def test_host_sun_geometry_and_met_clock_match_reference_bitwise(built):
             assert (ref[13], ref[14], ref[15]) == (host.latitude, host.longitude, host.gmt)
             checked += 1
     assert checked >= 20
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("extra", [{}, {"OPTINTERCEPT": 0}, {"HILLALBOPT": 2}, {"GFLUXOPTION": 1}])
+def test_oracle_snow_against_live_reference(extra, built):
+    """tSnowPack restatement on a fresh winter run (other basin, longer, option variants): bit for bit,
+    including the members the reference carries from cell to cell (albedo, Uerr)."""
+    spec = spec_for("snow", 12, runtime_h=96.0, seed=9, pmean=8.0, extra=extra)
+    n_steps = 96 * 16
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="murb")
+    w = run_and_compare(OracleStepper(basin, _sched(basin)), snaps, n_steps)
+    assert w.max() == 0.0, "oracle differs from the reference:\n" + w.report()
+    assert ("m", "IceWE") in w.w and ("m", "CumMelt") in w.w
+    assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0

@@ -111,7 +111,7 @@ def sun_variables(latitude, longitude, gmt, node_hour, cal_ymd, etistep_h):
     elif pi <= tau <= 2.0 * pi:
         if sunaz < 0.0:
             sunaz += pi
-    io = 1367.0 / math.pow(r, 2.0)
+    io = 1367.0 / (r * r)      # the compiler turns the reference's pow(r, 2.0) into r*r
     return alpha_d, sin_alpha, sunaz, io
 
 

@@ -51,6 +51,7 @@ class BasinSpec:
     forcing: str = "storm"        # "storm": STOCHASTICMODE 1 uniform storm; "met": rain gauges +
                                   # one weather station (Penman-Monteith ET, Rutter interception)
     n_gauges: int = 2
+    winter: bool = False          # met deck: sub-zero air temperatures and OPTSNOW 1
     sky_nodata: bool = False      # met deck: write 9999.99 as sky cover (the model then derives it from RH / rain)
     inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
     extra: dict = field(default_factory=dict)   # keyword overrides
@@ -111,7 +112,8 @@ def met_series(spec: BasinSpec):
         ph = h % 24
         day = math.sin(math.pi * (ph - 6) / 12.0) if 6 <= ph <= 18 else 0.0
         wet = any(rain[g][h] > 0 for g in range(spec.n_gauges))
-        ta = round(16.0 + 9.0 * math.sin(2 * math.pi * (ph - 9) / 24.0), 2)
+        ta = round((-4.0 if spec.winter else 16.0) + (7.0 if spec.winter else 9.0) * math.sin(2 * math.pi * (ph - 9) / 24.0)
+                   + (4.0 * math.sin(2 * math.pi * h / 90.0) if spec.winter else 0.0), 2)
         rh = round(min(98.0, 55.0 - 25.0 * math.sin(2 * math.pi * (ph - 9) / 24.0) + (25.0 if wet else 0.0)), 2)
         xc = 9.0 if wet else round(2.0 + 2.0 * math.cos(2 * math.pi * h / 37.0), 1)
         us = round(2.5 + 1.5 * math.sin(2 * math.pi * h / 17.0), 2)
@@ -147,9 +149,12 @@ def write_met_forcing(spec: BasinSpec, outdir: str) -> dict:
         for h in range(nh):
             pa, rh, xc, us, ta, isw = met[h]
             d.write(f"{stamp(h)} {pa} {rh} {9999.99 if spec.sky_nodata else xc} {us} {ta} {isw} 9999.99\n")
-    return {"STOCHASTICMODE": 0, "RAINSOURCE": 3, "GAUGESTATIONS": f"{outdir}/gauges.sdf",
-            "OPTEVAPOTRANS": 1, "OPTINTERCEPT": 2, "METDATAOPTION": 1,
-            "HYDROMETSTATIONS": f"{outdir}/met.sdf"}
+    kw = {"STOCHASTICMODE": 0, "RAINSOURCE": 3, "GAUGESTATIONS": f"{outdir}/gauges.sdf",
+          "OPTEVAPOTRANS": 1, "OPTINTERCEPT": 2, "METDATAOPTION": 1,
+          "HYDROMETSTATIONS": f"{outdir}/met.sdf"}
+    if spec.winter:
+        kw["OPTSNOW"] = 1
+    return kw
 
 
 def write_basin(spec: BasinSpec, outdir: str) -> str:
