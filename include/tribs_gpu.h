@@ -292,6 +292,41 @@ int tribs_gpu_et_step(tribs_handle_t h, const tribs_et_step_t *s);
 int tribs_gpu_et_sync(tribs_handle_t h, uint64_t et_field_mask, double *const *host);
 int tribs_gpu_et_push(tribs_handle_t h, uint64_t et_field_mask, const double *const *host);
 
+/* ------------------------------------------------------------------ snow pack (OPTSNOW 1)
+ * The cell loop of tSnowPack::callSnowPack (src/tHydro/tSnowPack.cpp:249-757: pack mass and
+ * energy balance 944-1365, 1940-2001, turbulent exchange 1373-1480, short wave on snow 1574-1748,
+ * melt routing, peak/persistence trackers 1052-1135), which under OPTSNOW replaces both ET sweeps
+ * at every METSTEP (tSimul.cpp:464-492); cells without snow take the ET path of kernel (1).
+ * Covered: OPTINTERCEPT 0. With a canopy the reference's callSnowIntercept reads the albedo the
+ * PREVIOUS cell in sweep order left in a class member (tSnowPack.cpp:1492) - a sweep-order scan
+ * that is not built yet, so tribs_gpu_snow_init refuses OPTINTERCEPT != 0. The energy-balance
+ * closure error (Uerror, CumUerror: round-off noise that the reference also carries from cell
+ * to cell) is written per cell from the cell's own balance. */
+#define TRIBS_SNOW_FIELDS(X) \
+  X(SnTempC) X(CrustAge) X(DensityAge) X(EvapoTransAge) X(SnSub) X(SnEvap) X(DU) X(Unode) X(Uerror) \
+  X(SnLHF) X(SnSHF) X(SnGHF) X(SnPHF) X(SnRLout) X(SnRLin) X(SnRSin) \
+  X(IntSWE) X(IntPrec) X(IntSnUnload) X(IntSub) X(CumIntSub) X(CumIntUnl) \
+  X(CumLHF) X(CumMelt) X(CumSHF) X(CumSnSub) X(CumSnEvap) X(CumPHF) X(CumRLin) X(CumRLout) X(CumGHF) \
+  X(CumUerror) X(CumHrsSnow) X(PersTimeMax) X(PersTime) X(PeakSWE) X(PeakSWETemp) X(InitPackTime) \
+  X(InitPackTimeTemp) X(PeakPackTime)
+#define TRIBS_SNOW_FIELD_ENUM(name) TRIBS_SN_##name,
+typedef enum { TRIBS_SNOW_FIELDS(TRIBS_SNOW_FIELD_ENUM) TRIBS_N_SNOW_FIELDS } tribs_snow_field_t;
+
+typedef struct {
+  double min_sn_temp;           /* MINSNTEMP */
+  double snliqfrac;             /* SNLIQFRAC */
+  int32_t hill_albedo_option;   /* HILLALBOPT (0 or 1; 2 needs the canopy path) */
+  int32_t reserved;
+  const double *const *init;    /* NULL, or TRIBS_N_SNOW_FIELDS pointers (NULL entries = 0) */
+} tribs_snow_params_t;
+
+/* after tribs_gpu_et_init (with snow_option = 1 in its parameters) */
+int tribs_gpu_snow_init(tribs_handle_t h, const tribs_snow_params_t *prm);
+/* one callSnowPack: `s` as for tribs_gpu_et_step (do_potential set, met_potential = the record of
+ * the hour, te_met and te_eti filled); hourly_time_step = tEvapoTrans::hourlyTimeStep of the call */
+int tribs_gpu_snow_step(tribs_handle_t h, const tribs_et_step_t *s, int32_t hourly_time_step);
+int tribs_gpu_snow_sync(tribs_handle_t h, uint64_t snow_field_mask, double *const *host);
+
 #ifdef __cplusplus
 }
 #endif

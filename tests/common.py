@@ -67,12 +67,15 @@ class GpuStepper:
         self.sim.hydro.Reset()
 
     def get(self, names):
-        from tribs_b200.gpu import EF
-        main = [nm for nm in names if nm not in EF]
+        from tribs_b200.gpu import EF, F, SNF
+        main = [nm for nm in names if nm in F]
         out = self.sim.dev.sync(main) if main else {}
-        et = [nm for nm in names if nm in EF]
+        et = [nm for nm in names if nm in EF and nm not in F]
         if et:
             out.update(self.sim.dev.et_sync(et))
+        sn = [nm for nm in names if nm in SNF and nm not in F and nm not in EF]
+        if sn:
+            out.update(self.sim.dev.snow_sync(sn))
         return out
 
     def result(self, name):

@@ -59,6 +59,24 @@ def test_gpu_et_option_variants_match_live_reference(variant, built):
     assert any(k[0] == "m" for k in w.w)
 
 
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("extra", [{"OPTINTERCEPT": 0}, {"OPTINTERCEPT": 0, "GFLUXOPTION": 1}])
+def test_gpu_snow_pack_matches_live_reference(extra, built):
+    """tSnowPack::callSnowPack without a canopy on the device (winter run with accumulation, melt and
+    rain on snow). The energy-balance closure error (1e-14 round-off noise that the reference also
+    drags from cell to cell) is not compared."""
+    spec = spec_for("snow", 20, runtime_h=96.0, seed=9, pmean=8.0, extra=extra)
+    n_steps = 96 * 16
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="murb")
+    for k in [k for k in snaps if k.endswith("_m_Uerror") or k.endswith("_m_CumUerror")]:
+        del snaps[k]
+    w = run_and_compare(GpuStepper(basin, _sched(basin)), snaps, n_steps, floor=ABS_FLOOR)
+    print("\n[snow] worst:\n" + w.report(8))
+    assert w.max() <= REL_TOL, w.report()
+    assert ("m", "IceWE") in w.w and ("m", "CumMelt") in w.w
+    assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0
+
+
 def test_gpu_et_per_cell_met_records_equal_station_records(built):
     """Gridded meteorology (METDATAOPTION 2) reaches kernel (1) as one record per cell: the same
     values expanded per cell must give bit-identical results to the station form."""
@@ -86,6 +104,7 @@ def test_gpu_et_per_cell_met_records_equal_station_records(built):
 def test_gpu_et_init_refuses_uncovered_options(built):
     from tribs_b200 import gpu
     basin, _, _ = load_golden("met")
+    # (OPTSNOW 1 together with a canopy: the golden met deck has OPTINTERCEPT 2)
     for key, val in (("et_shelterOption", 2), ("et_snowOption", 1), ("et_luOption", 1), ("et_option", 4)):
         b = dict(basin)
         b[key] = np.array([val], np.int32)

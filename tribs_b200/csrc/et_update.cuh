@@ -23,7 +23,7 @@ namespace tribs {
 
 struct LandClass {          // one row of the land table + values derived once on the host
   double A, B, P, S, K, b;  // interception: Gray storage/coefficient, Rutter throughfall/capacity/drainage
-  double Al, H, Kt, Rs, V_raw, V, SE, ST;
+  double Al, H, Kt, Rs, V_raw, V, SE, ST, LAI;
   double rav_num;           // log((zm-d)/zom)*log((zm-d)/zov) for the class's vegetation height
 };
 

@@ -35,6 +35,7 @@
 
 #include "cell_update.cuh"
 #include "et_update.cuh"
+#include "snow_update.cuh"
 
 namespace cg = cooperative_groups;
 using namespace tribs;
@@ -1227,6 +1228,11 @@ struct EtState {
   cudaEvent_t pin_ev[2][kRing] = {};
   int pin_cap = 0, gen = 0;
   std::vector<int32_t> h_rec;
+  // snow pack (tribs_gpu_snow_init)
+  int snow_option = 0;
+  bool snow_ready = false;
+  SnowConst sc{};
+  SnowView snv{};
 };
 
 static void tribs_free_et(tribs_ctx *c) {
@@ -1278,7 +1284,9 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   if (p->et_option && p->gflux_option != 1 && p->gflux_option != 2) return fail("tribs_gpu_et_init: GFLUXOPTION must be 1 or 2");
   if (!(p->shelter_option == 0 || p->shelter_option >= 4)) return fail("tribs_gpu_et_init: OPTRADSHELT 1-3 (horizon angles) is not covered");
   if (p->lu_option != 0) return fail("tribs_gpu_et_init: OPTLANDUSE 1 (dynamic land-use grids) is not covered");
-  if (p->snow_option != 0) return fail("tribs_gpu_et_init: OPTSNOW 1 is not covered");
+  if (p->snow_option != 0 && p->i_option != 0)
+    return fail("tribs_gpu_et_init: OPTSNOW 1 with canopy interception is not covered (sweep-order albedo carry-over, see DESIGN.md)");
+  if (p->snow_option != 0 && p->et_option == 0) return fail("tribs_gpu_et_init: OPTSNOW 1 needs the evaporation scheme");
   if (p->et_option == 0 && p->i_option == 2) return fail("tribs_gpu_et_init: Rutter interception needs the evaporation scheme (tSimul.cpp:444-450)");
   CK(cudaSetDevice(c->device));
   const int n = c->n;
@@ -1294,6 +1302,7 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   c->et = e;
   e->k.et_option = p->et_option; e->k.i_option = p->i_option; e->k.gflux_option = p->gflux_option;
   e->k.shelter_option = p->shelter_option;
+  e->snow_option = p->snow_option;
   e->k.metstep_min = p->metstep_min; e->k.etistep_h = p->etistep_h; e->k.tlinke = p->tlinke;
   e->k.temp_lapse = p->temp_lapse; e->k.max_interstorm = p->max_interstorm;
   auto log_product = [](double veg) {            // numerator of aeroResist (tEvapoTrans.cpp:1464-1475)
@@ -1320,7 +1329,7 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
     else if (p->et_option == 2 || p->et_option == 3) { L.Al = lp[7]; V = lp[11]; }
     L.V_raw = lp[11];
     L.V = (V >= 1.0) ? 0.99 : V;
-    L.SE = lp[13]; L.ST = lp[14];
+    L.SE = lp[13]; L.ST = lp[14]; L.LAI = lp[12];
     L.rav_num = log_product(L.H == 0 ? 0.1 : L.H);
   }
   LandClass *d_cls = nullptr;
@@ -1403,9 +1412,79 @@ static int et_upload_met(tribs_ctx *c, int sl, const tribs_met_t *m, MetDev *out
   return 0;
 }
 
+__global__ void __launch_bounds__(128)
+snow_cells_kernel(EtConst k, EtStatic st, EtStepDev s, SnowConst sc, EtView ev, SnowView sv, DynView dv, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || st.boundary[i] < 0) return;
+  snow_cell_step(k, st, s, sc, ev, sv, dv, i);
+}
+
+extern "C" int tribs_gpu_snow_init(tribs_handle_t c, const tribs_snow_params_t *p) {
+  if (!c || !p) return fail("tribs_gpu_snow_init: null argument");
+  if (!c->et || !c->et->snow_option) return fail("tribs_gpu_snow_init: call tribs_gpu_et_init with snow_option = 1 first");
+  if (c->et->snow_ready) return fail("tribs_gpu_snow_init: already initialised");
+  if (p->hill_albedo_option != 0 && p->hill_albedo_option != 1) return fail("tribs_gpu_snow_init: HILLALBOPT 2 needs the canopy path, not covered");
+  CK(cudaSetDevice(c->device));
+  EtState *e = c->et;
+  e->sc.min_sn_temp = p->min_sn_temp; e->sc.snliqfrac = p->snliqfrac; e->sc.hill_albedo_option = p->hill_albedo_option;
+  for (int f = 0; f < TRIBS_N_SNOW_FIELDS; f++) {
+    const double *src = (p->init && p->init[f]) ? p->init[f] : nullptr;
+    double *d = nullptr;
+    if (src) { if (dev_upload(c, &d, to_device_order<double>(c, src, 0.0))) return 1; }
+    else {
+      if (dev_alloc(c, &d, (size_t)c->n_pad)) return 1;
+      CK(cudaMemset(d, 0, (size_t)c->n_pad * sizeof(double)));
+    }
+    e->snv.f[f] = d;
+  }
+  e->snow_ready = true;
+  return 0;
+}
+
+extern "C" int tribs_gpu_snow_step(tribs_handle_t c, const tribs_et_step_t *s, int32_t hourly_time_step) {
+  if (!c || !s) return fail("tribs_gpu_snow_step: null argument");
+  if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_step: call tribs_gpu_snow_init first");
+  if (s->hour < 0 || s->hour > 23) return fail("tribs_gpu_snow_step: hour out of range");
+  CK(cudaSetDevice(c->device));
+  EtState *e = c->et;
+  static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014, 0.995, 0.976, 0.976, 1.0,
+                                     1.053, 1.167, 1.354, 1.637, 2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
+  EtStepDev d{};
+  d.do_potential = 1; d.do_components = 1; d.intercept_flag = 0; d.met_time = 1;   // callSnowPack runs at met_hour only
+  d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
+  d.cos_alpha = cos(asin(s->sinAlpha));
+  d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
+  d.sky_flag_from = s->sky_flag_from; d.te_met = s->te_met; d.te_eti = s->te_eti;
+  d.rs_ratio = rsRatio[s->hour];
+  if (et_upload_met(c, 0, s->met_potential, &d.pot)) return 1;
+  d.cmp = d.pot;        // ComputeETComponents runs inside the same cell loop, before the met clock advances
+  SnowConst sc = e->sc;
+  sc.hourly = hourly_time_step;
+  snow_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, c->n_pad);
+  c->launches++;
+  e->gen++;
+  CK(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int tribs_gpu_snow_sync(tribs_handle_t c, uint64_t mask, double *const *host) {
+  if (!c || !host) return fail("tribs_gpu_snow_sync: null argument");
+  if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_sync: call tribs_gpu_snow_init first");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < TRIBS_N_SNOW_FIELDS; k++) {
+    if (!(mask & (1ull << k)) || !host[k]) continue;
+    gather_to_sweep_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->et->snv.f[k], c->d_dev_of_sweep, c->d_stage, c->n);
+    c->launches++;
+    CK(cudaMemcpyAsync(host[k], c->d_stage, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
 extern "C" int tribs_gpu_et_step(tribs_handle_t c, const tribs_et_step_t *s) {
   if (!c || !s) return fail("tribs_gpu_et_step: null argument");
   if (!c->et) return fail("tribs_gpu_et_step: call tribs_gpu_et_init first");
+  if (c->et->snow_option) return fail("tribs_gpu_et_step: with OPTSNOW 1 the simulator calls tribs_gpu_snow_step instead");
   if (!s->do_potential && !s->do_components) return 0;
   if (s->hour < 0 || s->hour > 23) return fail("tribs_gpu_et_step: hour out of range");
   CK(cudaSetDevice(c->device));

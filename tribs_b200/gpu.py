@@ -42,8 +42,16 @@ def _et_fields_from_header() -> list[str]:
 
 FIELDS = _fields_from_header()
 F = {nm: k for k, nm in enumerate(FIELDS)}
+def _snow_fields_from_header() -> list[str]:
+    src = open(HEADER).read()
+    m = re.search(r"#define TRIBS_SNOW_FIELDS\(X\) \\\n((?:.*\\\n)*.*)\n", src)
+    return re.findall(r"X\((\w+)\)", m.group(1))
+
+
 ET_FIELDS = _et_fields_from_header()
 EF = {nm: k for k, nm in enumerate(ET_FIELDS)}
+SNOW_FIELDS = _snow_fields_from_header()
+SNF = {nm: k for k, nm in enumerate(SNOW_FIELDS)}
 RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac",
            "msm", "msmRt", "msmU", "mgw", "sat", "qunsat"]
 GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last", "BasinRain", "BasinEvap",
@@ -113,12 +121,18 @@ class EtStep(C.Structure):
                 ("met_potential", C.POINTER(MetT)), ("met_components", C.POINTER(MetT))]
 
 
+class SnowParams(C.Structure):
+    _fields_ = [("min_sn_temp", C.c_double), ("snliqfrac", C.c_double), ("hill_albedo_option", C.c_int32),
+                ("reserved", C.c_int32), ("init", C.POINTER(PD))]
+
+
 EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
            "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
            "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
+           "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync",
            "tribs_gpu_last_error", "tribs_gpu_abi_version"]
 
 _lib = None
@@ -159,6 +173,9 @@ def load():
     L.tribs_gpu_et_step.argtypes = [H, C.POINTER(EtStep)]
     L.tribs_gpu_et_sync.argtypes = [H, C.c_uint64, C.POINTER(PD)]
     L.tribs_gpu_et_push.argtypes = [H, C.c_uint64, C.POINTER(PD)]
+    L.tribs_gpu_snow_init.argtypes = [H, C.POINTER(SnowParams)]
+    L.tribs_gpu_snow_step.argtypes = [H, C.POINTER(EtStep), C.c_int32]
+    L.tribs_gpu_snow_sync.argtypes = [H, C.c_uint64, C.POINTER(PD)]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -372,6 +389,40 @@ class GpuBasin:
             mc = self._met(rec, cell_record, elev, keep)
             s.met_components = C.pointer(mc)
         _chk(self.L.tribs_gpu_et_step(self.h, C.byref(s)))
+
+    def snow_init(self, basin: dict):
+        b, keep = basin, []
+        p = SnowParams()
+        p.min_sn_temp = float(b["sn_minSnTemp"][0]); p.snliqfrac = float(b["sn_snliqfrac"][0])
+        p.hill_albedo_option = int(b["sn_hillAlbedoOption"][0])
+        init = (PD * len(SNOW_FIELDS))()
+        for k, nm in enumerate(SNOW_FIELDS):
+            src = b.get("init_" + nm)
+            if src is not None:
+                a = np.ascontiguousarray(src, np.float64); keep.append(a); init[k] = _d(a)
+        p.init = C.cast(init, C.POINTER(PD))
+        _chk(self.L.tribs_gpu_snow_init(self.h, C.byref(p)))
+
+    def snow_step(self, step: dict, rec: dict, hourly: int, cell_record=None, elev=None):
+        """One tSnowPack::callSnowPack; *step*/*rec* as produced by met.EvapoTransHost.potential_call."""
+        keep = []
+        s = EtStep()
+        for k in ("alphaD", "sinAlpha", "sunaz", "Io", "hour", "dew_hum_flag", "ts_option", "first_call", "te_met",
+                  "te_eti", "sky_flag_from"):
+            setattr(s, k, step[k])
+        s.do_potential = 1
+        m = self._met(rec, cell_record, elev, keep)
+        s.met_potential = C.pointer(m)
+        _chk(self.L.tribs_gpu_snow_step(self.h, C.byref(s), int(hourly)))
+
+    def snow_sync(self, names) -> dict:
+        out = {nm: np.empty(self.n) for nm in names}
+        ptrs = (PD * len(SNOW_FIELDS))()
+        mask = 0
+        for nm in names:
+            ptrs[SNF[nm]] = _d(out[nm]); mask |= 1 << SNF[nm]
+        _chk(self.L.tribs_gpu_snow_sync(self.h, mask, C.cast(ptrs, C.POINTER(PD))))
+        return out
 
     def et_sync(self, names) -> dict:
         out = {nm: np.empty(self.n) for nm in names}

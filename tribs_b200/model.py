@@ -119,9 +119,25 @@ class tEvapoTrans:
             timer.metstep = self.host.metstep
             timer.calendar = met.Calendar(basin["timer_start"])
             dev.et_init(basin)
+            self.snowOption = int(basin["et_snowOption"][0]) if "et_snowOption" in basin else 0
+            if self.snowOption:
+                dev.snow_init(basin)
+
+    snowOption = 0
 
     def getEToption(self):
         return self.evapotransOption
+
+    def getSnowOpt(self):
+        return self.snowOption
+
+    def callSnowPack(self, intercept, flag: int):
+        """tSnowPack::callSnowPack(tIntercept*, int): one sweep that replaces both ET sweeps."""
+        now = self.timer.getCurrentTime()
+        hourly = self.host.hourlyTimeStep
+        step, rec = self.host.potential_call(self.timer.hour, now)
+        step["te_eti"] = float(self.timer.getElapsedETISteps(now))
+        self.dev.snow_step(step, rec, hourly, cell_record=self.host.cell_record, elev=self.host.elev)
 
     def callEvapoPotential(self):
         """Queues the potential-evaporation sweep; it is launched together with callEvapoTrans when
@@ -185,7 +201,10 @@ class Simulator:
         """tSimul.cpp:419-498 without the snow branch: which of the two ET sweeps are due."""
         met_due, eti_due = self.met_clock.due(self.timer.getCurrentTime())
         et, icp = self.evapotrans, self.intercept
-        if et.getEToption() != 0:
+        if et.getEToption() != 0 and et.getSnowOpt() != 0:       # snow active: tSimul.cpp:464-492
+            if met_due:
+                et.callSnowPack(icp, 1 if icp.getIoption() != 0 else 0)
+        elif et.getEToption() != 0:
             if met_due:
                 et.callEvapoPotential()
             if eti_due:
@@ -257,11 +276,15 @@ class Simulator:
                     if step_rain is not None:      # the ET sweep reads the Rain array of this step
                         self.dev.step(0, now, t.getElapsedSteps(now), 0, rain=step_rain)
                         step_rain = None if isinstance(rain, np.ndarray) else step_rain
-                    if met_due:
-                        self.evapotrans.callEvapoPotential()
-                    if eti_due:
-                        self.evapotrans.callEvapoTrans(self.intercept, 1 if self.intercept.getIoption() != 0 else 0)
-                    self.evapotrans.flush()
+                    if self.evapotrans.getSnowOpt() != 0:
+                        if met_due:
+                            self.evapotrans.callSnowPack(self.intercept, 0)
+                    else:
+                        if met_due:
+                            self.evapotrans.callEvapoPotential()
+                        if eti_due:
+                            self.evapotrans.callEvapoTrans(self.intercept, 1 if self.intercept.getIoption() != 0 else 0)
+                        self.evapotrans.flush()
             steps.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
                               hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
                               sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())),
