@@ -50,10 +50,31 @@ def _free_port():
     return port
 
 
+def _bench_like_basin(world):
+    """The basin shape bench.py uses for N GPUs: a valley N times as long as it is wide."""
+    from tribs_b200.synthbasin import build_basin
+    return build_basin(24, 24 * world, seed=1, runtime_h=1.0)
+
+
+@pytest.mark.parametrize("world", [4, 8])
+def test_plans_of_the_multi_gpu_bench_basin(world):
+    b = _bench_like_basin(world)
+    owner = cell_owner(b, world)
+    assert set(np.unique(owner)) == set(range(world))
+    plans = [halo_plan(b, owner, r) for r in range(world)]
+    for a in range(world):
+        for kind in ("qpout", "state", "nwt"):
+            for peer, cells in plans[a][kind + "_send"].items():
+                assert np.array_equal(cells, plans[peer][kind + "_recv"][a]), (kind, a, peer)
+        # the river runs through the ranks in order: outflow only goes to higher ranks
+        assert all(peer > a for peer in plans[a]["qpout_send"])
+    assert sum(p["owned"].size for p in plans) == owner.size
+
+
 def _worker(rank, world, port, name, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    b, _, _ = load_golden(name)
+    b = _bench_like_basin(world) if name == "bench" else load_golden(name)[0]
     owner = cell_owner(b, world)
     plan = halo_plan(b, owner, rank)
     n = owner.size
@@ -88,11 +109,12 @@ def _worker(rank, world, port, name, out):
     dist.destroy_process_group()
 
 
-def test_halo_exchange_protocol_over_gloo_world2():
+@pytest.mark.parametrize("world,name", [(2, "deep"), (4, "bench")])
+def test_halo_exchange_protocol_over_gloo(world, name):
     ctx = mp.get_context("spawn")
     out = ctx.Queue()
     port = _free_port()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, "deep", out)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, name, out)) for r in range(world)]
     for p in procs:
         p.start()
     for p in procs:
