@@ -257,7 +257,7 @@ def run_gpu(args):
         "config": {"workload": f"synthetic {total_cells / world / 1e6:.2f}M-cell V-valley TIN per GPU, uniform storm 20 mm/h, "
                                f"TIMESTEP 3.75 min, GWSTEP 30 min (sat zone every {gw_every}th step), ET/snow off",
                    "cells_per_gpu": n, "stream_cells_per_gpu": n_stream, "sweep_levels": dev.levels(),
-                   "l2": "state arrays (52 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
+                   "l2": "state arrays (54 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
                    "batch_steps": B,
                    "parallelism": "1 GPU" if world == 1 else (
                        f"one basin of {total_cells} cells, {world} reach partitions along the river, NCCL halo exchange "

@@ -4,6 +4,7 @@
 // compared bit-for-bit with the oracle / the reference dumps. Cells are visited sequentially
 // in sweep order, which is one valid schedule of the device sweep.
 #include "../../tribs_b200/csrc/cell_update.cuh"
+#include "../../tribs_b200/csrc/snow_update.cuh"
 #include <vector>
 #include <cstring>
 
@@ -79,4 +80,61 @@ void hc_sat(int n, double **sf, int32_t **si, double **ef, double **fields, cons
 }
 
 double hc_lambert_w(double z) { return lambert_w(z); }
+
+// ---- kernel (1) and the snow pack: one call of the cell loop, cells in sweep order ----------------
+// ci: et_option i_option gflux_option shelter_option | cd: metstep_min etistep_h tlinke temp_lapse max_interstorm
+// est: z flow_slope aspect heat_cond heat_cap soil_cutoff root_cutoff thr bedrock varea
+// si: do_potential do_components intercept_flag hour first_call dew_hum_flag ts_option sky_flag_from met_time
+// sd: alphaD sinAlpha sunaz Io te_met te_eti
+// met_pot / met_cmp: air_temp dew_temp rel_humid vap_press atm_press wind_speed sky_cover rad_global elev
+// snow: NULL, or {min_sn_temp, snliqfrac, hill_albedo_option, hourly}: run callSnowPack instead
+int hc_n_et_fields() { return TRIBS_N_ET_FIELDS; }
+int hc_n_snow_fields() { return TRIBS_N_SNOW_FIELDS; }
+void hc_et_step(int n, const int32_t *ci, const double *cd, double **est, const int32_t *land_class, const double *land_table,
+                int n_classes, const int32_t *si, const double *sd, const int32_t *cell_record, double **met_pot,
+                double **met_cmp, double **etf, double **fields, const double *snow, double **snf) {
+  EtConst k{};
+  k.et_option = ci[0]; k.i_option = ci[1]; k.gflux_option = ci[2]; k.shelter_option = ci[3];
+  k.metstep_min = cd[0]; k.etistep_h = cd[1]; k.tlinke = cd[2]; k.temp_lapse = cd[3]; k.max_interstorm = cd[4];
+  et_derived_constants(k);
+  std::vector<LandClass> cls(n_classes);
+  for (int q = 0; q < n_classes; q++) cls[q] = make_land_class(land_table + (size_t)q * 15, k.et_option);
+  std::vector<double> cs(n), sn(n);
+  std::vector<int32_t> bnd(n, 0), order(n);
+  for (int i = 0; i < n; i++) { const double sl = fabs(atan(est[1][i])); cs[i] = cos(sl); sn[i] = sin(sl); order[i] = i; }
+  EtStatic st{};
+  st.z = est[0]; st.cos_slope = cs.data(); st.sin_slope = sn.data(); st.aspect = est[2]; st.heat_cond = est[3];
+  st.heat_cap = est[4]; st.soil_cutoff = est[5]; st.root_cutoff = est[6]; st.thr = est[7]; st.bedrock = est[8]; st.varea = est[9];
+  st.land_class = land_class; st.boundary = bnd.data(); st.sweep_of_dev = order.data(); st.classes = cls.data();
+  static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014, 0.995, 0.976, 0.976, 1.0,
+                                     1.053, 1.167, 1.354, 1.637, 2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
+  EtStepDev s{};
+  s.do_potential = si[0] && k.et_option; s.do_components = si[1]; s.intercept_flag = si[2]; s.hour = si[3]; s.first_call = si[4];
+  s.dew_hum_flag = si[5]; s.ts_option = si[6]; s.sky_flag_from = si[7]; s.met_time = si[8];
+  s.alphaD = sd[0]; s.sinAlpha = sd[1]; s.sunaz = sd[2]; s.Io = sd[3]; s.te_met = sd[4]; s.te_eti = sd[5];
+  s.cos_alpha = cos(asin(s.sinAlpha));
+  s.rs_ratio = rsRatio[s.hour];
+  auto met = [&](double **m) {
+    MetDev d{};
+    d.cell_record = cell_record;
+    d.air_temp = m[0]; d.dew_temp = m[1]; d.rel_humid = m[2]; d.vap_press = m[3]; d.atm_press = m[4];
+    d.wind_speed = m[5]; d.sky_cover = m[6]; d.rad_global = m[7]; d.elev = m[8];
+    return d;
+  };
+  s.pot = met(met_pot);
+  s.cmp = met(met_cmp ? met_cmp : met_pot);
+  EtView ev;
+  for (int f = 0; f < TRIBS_N_ET_FIELDS; f++) ev.f[f] = etf[f];
+  DynView dv;
+  for (int f = 0; f < TRIBS_N_FIELDS; f++) dv.f[f] = fields[f];
+  if (!snow) {
+    for (int i = 0; i < n; i++) et_cell(k, st, s, ev, dv, i);
+    return;
+  }
+  SnowConst sc{snow[0], snow[1], (int32_t)snow[2], (int32_t)snow[3]};
+  SnowView sv;
+  for (int f = 0; f < TRIBS_N_SNOW_FIELDS; f++) sv.f[f] = snf[f];
+  s.do_potential = 1; s.do_components = 1; s.intercept_flag = 0; s.met_time = 1; s.cmp = s.pot;
+  for (int i = 0; i < n; i++) snow_cell_step(k, st, s, sc, ev, sv, dv, i);
+}
 }

@@ -91,3 +91,149 @@ def test_device_headers_match_oracle_on_host(name, built):
         for f in ("Qpin", "srf", "sbsrf", "hsrf", "psrf", "satsrf", "gwchange"):
             fields[f][:] = 0.0
     assert np.array_equal(glob[:4], m.glob[:4])
+
+
+# ------------------------------------------------------------------ kernel (1) / snow device headers
+def _hc_lib():
+    L = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so"))
+    L.hc_et_step.argtypes = [C.c_int, PI, PD, C.POINTER(PD), PI, PD, C.c_int, PI, PD, PI, C.POINTER(PD), C.POINTER(PD),
+                             C.POINTER(PD), C.POINTER(PD), PD, C.POINTER(PD)]
+    return L
+
+
+class _EtHostCheck:
+    """Runs et_update.cuh / snow_update.cuh (compiled for the host) on a copy of the state the
+    oracle is about to update and compares what both leave behind."""
+
+    MAIN = ("Rain", "NetPrecipitation", "EvapSoil", "EvapDryCanopy", "SoilMoisture", "RootMoisture", "LiqWE", "IceWE",
+            "LiqRouted")
+
+    def __init__(self, basin, stepper, tol):
+        from oracle.pyoracle import ET_FIELDS, SNOW_FIELDS
+        from tribs_b200.gpu import ET_FIELDS as GET, FIELDS, SNOW_FIELDS as GSN
+        assert ET_FIELDS == GET and SNOW_FIELDS == GSN
+        self.L, self.b, self.o, self.tol = _hc_lib(), basin, stepper, tol
+        self.et_names, self.sn_names, self.fields = ET_FIELDS, SNOW_FIELDS, FIELDS
+        assert self.L.hc_n_et_fields() == len(ET_FIELDS) and self.L.hc_n_snow_fields() == len(SNOW_FIELDS)
+        self.worst, self.calls = 0.0, 0
+        b = basin
+        self.n = int(b["n_active"][0])
+        self.ci = np.array([b["et_option"][0], b["et_Ioption"][0], b["et_gFluxOption"][0], b["et_shelterOption"][0]], np.int32)
+        self.cd = np.array([b["et_timeStep"][0], b["etistep"][0], b["et_Tlinke"][0], b["et_tempLapseRate"][0],
+                            b["icp_maxInterStormPeriod"][0]], np.float64)
+        self.est = [np.ascontiguousarray(b[k], np.float64) for k in
+                    ("z", "flow_slope", "aspect", "VolHeatCond", "SoilHeatCap", "soil_cutoff", "root_cutoff", "ThetaR",
+                     "bedrock", "varea")]
+        self.lc = np.ascontiguousarray(b["land_class"], np.int32)
+        self.lt = np.ascontiguousarray(b["land_table"], np.float64)
+
+    def snapshot(self):
+        et = self.o.et
+        self.snap_et = {k: et.f[k].copy() for k in self.et_names}
+        self.snap_sn = {k: et.f[k].copy() for k in self.sn_names} if et.snow else {}
+        self.snap_main = {k: self.o.m.state[k].copy() for k in self.MAIN}
+
+    def run_and_compare(self, pot, cmp_, snow_hourly=None):
+        host = self.o.host
+        step = (pot or cmp_)[0]
+        si = np.array([pot is not None, cmp_ is not None, int(self.ci[1] != 0), step["hour"],
+                       pot[0]["first_call"] if pot else 0, step["dew_hum_flag"], step["ts_option"],
+                       (pot or cmp_)[0]["sky_flag_from"], pot is not None], np.int32)
+        sd = np.array([step["alphaD"], step["sinAlpha"], step["sunaz"], step["Io"], pot[0]["te_met"] if pot else 0.0,
+                       (cmp_ or pot)[0]["te_eti"]], np.float64)
+        keys = ("airTemp", "dewTemp", "rHumidity", "vPress", "atmPress", "windSpeed", "skyCover", "radGlobal")
+
+        def met(rec):
+            arrs = [np.ascontiguousarray(rec[k], np.float64) for k in keys] + [np.ascontiguousarray(host.elev, np.float64)]
+            return arrs, _ptab(arrs, PD)
+
+        keep_p, mp = met((pot or cmp_)[1])
+        keep_c, mc = met((cmp_ or pot)[1])
+        etf = [self.snap_et[k] for k in self.et_names]
+        fields = [self.snap_main[k] if k in self.snap_main else np.zeros(self.n) for k in self.fields]
+        snow, snf_tab, snf = None, None, []
+        if snow_hourly is not None:
+            snow = np.array([self.b["sn_minSnTemp"][0], self.b["sn_snliqfrac"][0], self.b["sn_hillAlbedoOption"][0],
+                             snow_hourly], np.float64)
+            snf = [self.snap_sn[k] for k in self.sn_names]
+            snf_tab = _ptab(snf, PD)
+        self.L.hc_et_step(self.n, self.ci.ctypes.data_as(PI), self.cd.ctypes.data_as(PD), _ptab(self.est, PD),
+                          self.lc.ctypes.data_as(PI), self.lt.ctypes.data_as(PD), self.lt.size // 15,
+                          si.ctypes.data_as(PI), sd.ctypes.data_as(PD), host.cell_record.ctypes.data_as(PI), mp, mc,
+                          _ptab(etf, PD), _ptab(fields, PD), snow.ctypes.data_as(PD) if snow is not None else None, snf_tab)
+        et = self.o.et
+        floor = {"SurfTemp": 1.0, "SoilTemp": 1.0, "AirTemp": 1.0, "DewTemp": 1.0, "NetRad": 1.0, "GFlux": 1.0, "HFlux": 1.0,
+                 "LFlux": 1.0, "SnTempC": 1.0, "Uerror": 1e9, "CumUerror": 1e9, "DU": 1e-3, "Unode": 1e-3}
+        for names, got_of in ((self.et_names, lambda k: self.snap_et[k]), (self.sn_names if snow is not None else [], lambda k: self.snap_sn[k]),
+                              (self.MAIN, lambda k: fields[self.fields.index(k)])):
+            for k in names:
+                if k == "CanopyStorVol":   # the device applies CanopyBalance inside this sweep, the oracle at the end of the step
+                    continue
+                ref = et.f[k] if k in et.f else self.o.m.state[k]
+                err = np.abs(ref - got_of(k)) / np.maximum(np.abs(ref), floor.get(k, 1e-9))
+                assert err.max() <= self.tol, (k, self.calls, float(err.max()), ref[np.argmax(err)], got_of(k)[np.argmax(err)])
+                self.worst = max(self.worst, float(err.max()))
+        self.calls += 1
+
+
+def _drive_with_host_check(basin, n_steps, tol):
+    from common import OracleStepper
+    from refrun import schedule_for
+    o = OracleStepper(basin, schedule_for(basin))
+    hc = _EtHostCheck(basin, o, tol)
+    for _ in range(n_steps):
+        o.m.advance()
+        o.cal.advance(o.m.time, o.m.B.tstep)
+        met_due, eti_due = o.clock.due(o.m.time)
+        o._met_due = met_due
+        if o.et.snow:
+            if met_due:
+                hourly = o.host.hourlyTimeStep
+                step, rec = o.host.potential_call(o.cal.hour, o.m.time)
+                step["te_eti"] = float(int(o.m.time / o.host.etistep))
+                hc.snapshot()
+                o.et.snow_pack(step, rec, hourly)
+                hc.run_and_compare((step, rec), (step, rec), snow_hourly=hourly)
+        elif met_due or eti_due:
+            pot = o.host.potential_call(o.cal.hour, o.m.time) if met_due else None
+            cmp_ = o.host.components_call(o.m.time) if eti_due else None
+            hc.snapshot()
+            if pot:
+                o.et.potential(*pot)
+            if cmp_:
+                o.et.components(*cmp_)
+            hc.run_and_compare(pot, cmp_)
+        o.unsat()
+        if o.gw_due():
+            o.sat()
+        o.route(); o.balance(); o.reset()
+    return hc
+
+
+def test_et_device_header_matches_oracle_on_host(built):
+    """et_update.cuh (the source of et_cells_kernel) compiled with g++: every call of the fused
+    potential-ET + ET-partition + Rutter sweep against the bit-exact oracle on the same inputs."""
+    basin, snaps, _ = load_golden("met")
+    hc = _drive_with_host_check(basin, int(snaps["n_steps"][0]), tol=1e-9)
+    assert hc.calls >= 40 and hc.worst < 1e-9
+
+
+@pytest.mark.parametrize("variant", ["deardorff", "priestley-taylor", "gray", "gradient-gflux", "sky-cover-nodata"])
+def test_et_device_header_option_variants_on_host(variant, built):
+    from refrun import have_harness, run_reference
+    from test_oracle import et_variant_spec
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    basin, _, _, _ = run_reference(et_variant_spec(variant, 10, 30.0, 4))
+    hc = _drive_with_host_check(basin, 30 * 16, tol=1e-9)
+    assert hc.calls >= 25
+
+
+def test_snow_device_header_matches_oracle_on_host(built):
+    from refrun import have_harness, run_reference, spec_for
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    basin, _, _, _ = run_reference(spec_for("snow", 10, runtime_h=96.0, seed=9, pmean=8.0, extra={"OPTINTERCEPT": 0}))
+    hc = _drive_with_host_check(basin, 96 * 16, tol=1e-9)
+    assert hc.calls >= 90
+    assert np.abs(hc.o.et.f["CumMelt"]).max() > 0

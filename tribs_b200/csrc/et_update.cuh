@@ -34,6 +34,34 @@ struct EtConst {
   double tn_tlk, a1, a2, a3;   // Linke-turbidity polynomials of DirectDiffuse (functions of TLINKE only)
 };
 
+// ---- host-side set-up shared by tribs_gpu_et_init and the host check of this header ----------------
+inline double et_log_product(double veg) {       // numerator of aeroResist (tEvapoTrans.cpp:1464-1475)
+  const double zm = 2.0 + veg, zom = 0.123 * veg, zov = 0.0123 * veg, d = 0.67 * veg;
+  return log((zm - d) / zom) * log((zm - d) / zov);
+}
+inline void et_derived_constants(EtConst &k) {   // needs k.tlinke
+  k.ras_num = et_log_product(1.0);
+  const double T = k.tlinke;                     // DirectDiffuse, tEvapoTrans.cpp:1974-1984
+  k.tn_tlk = -0.015843 + 0.030543 * T + 0.0003797 * pow(T, 2.0);
+  const double a1p = 0.26463 - 0.061581 * T + 0.0031408 * pow(T, 2.0);
+  k.a1 = (a1p * k.tn_tlk < 0.0022) ? 0.0022 / k.tn_tlk : a1p;
+  k.a2 = 2.04020 + 0.018945 * T - 0.011161 * pow(T, 2.0);
+  k.a3 = -1.3025 + 0.039231 * T + 0.0085079 * pow(T, 2.0);
+}
+inline LandClass make_land_class(const double *lp, int et_option) {   // lp[k] = tInvariant::getLandProp(k)
+  LandClass L;
+  L.A = lp[1]; L.B = lp[2]; L.P = lp[3]; L.S = lp[4]; L.K = lp[5]; L.b = lp[6];
+  L.Al = L.H = L.Kt = L.Rs = 0.0;
+  double V = 0.0;                                // setCoeffs, tEvapoTrans.cpp:915-952
+  if (et_option == 1) { L.Al = lp[7]; L.H = lp[8]; L.Kt = lp[9]; L.Rs = lp[10]; V = lp[11]; }
+  else if (et_option == 2 || et_option == 3) { L.Al = lp[7]; V = lp[11]; }
+  L.V_raw = lp[11];
+  L.V = (V >= 1.0) ? 0.99 : V;
+  L.SE = lp[13]; L.ST = lp[14]; L.LAI = lp[12];
+  L.rav_num = et_log_product(L.H == 0 ? 0.1 : L.H);
+  return L;
+}
+
 struct EtStatic {           // device order, length n_pad
   const double *z, *cos_slope, *sin_slope, *aspect, *heat_cond, *heat_cap, *soil_cutoff, *root_cutoff;
   const double *thr, *bedrock, *varea;

@@ -1305,33 +1305,9 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   e->snow_option = p->snow_option;
   e->k.metstep_min = p->metstep_min; e->k.etistep_h = p->etistep_h; e->k.tlinke = p->tlinke;
   e->k.temp_lapse = p->temp_lapse; e->k.max_interstorm = p->max_interstorm;
-  auto log_product = [](double veg) {            // numerator of aeroResist (tEvapoTrans.cpp:1464-1475)
-    const double zm = 2.0 + veg, zom = 0.123 * veg, zov = 0.0123 * veg, d = 0.67 * veg;
-    return log((zm - d) / zom) * log((zm - d) / zov);
-  };
-  e->k.ras_num = log_product(1.0);
-  {
-    const double T = p->tlinke;                  // DirectDiffuse, tEvapoTrans.cpp:1974-1984
-    e->k.tn_tlk = -0.015843 + 0.030543 * T + 0.0003797 * pow(T, 2.0);
-    const double a1p = 0.26463 - 0.061581 * T + 0.0031408 * pow(T, 2.0);
-    e->k.a1 = (a1p * e->k.tn_tlk < 0.0022) ? 0.0022 / e->k.tn_tlk : a1p;
-    e->k.a2 = 2.04020 + 0.018945 * T - 0.011161 * pow(T, 2.0);
-    e->k.a3 = -1.3025 + 0.039231 * T + 0.0085079 * pow(T, 2.0);
-  }
+  et_derived_constants(e->k);
   std::vector<LandClass> cls((size_t)p->n_land_classes);
-  for (int q = 0; q < p->n_land_classes; q++) {
-    const double *lp = p->land_table + (size_t)q * 15;
-    LandClass &L = cls[q];
-    L.A = lp[1]; L.B = lp[2]; L.P = lp[3]; L.S = lp[4]; L.K = lp[5]; L.b = lp[6];
-    L.Al = L.H = L.Kt = L.Rs = 0.0;
-    double V = 0.0;                              // setCoeffs, tEvapoTrans.cpp:915-952
-    if (p->et_option == 1) { L.Al = lp[7]; L.H = lp[8]; L.Kt = lp[9]; L.Rs = lp[10]; V = lp[11]; }
-    else if (p->et_option == 2 || p->et_option == 3) { L.Al = lp[7]; V = lp[11]; }
-    L.V_raw = lp[11];
-    L.V = (V >= 1.0) ? 0.99 : V;
-    L.SE = lp[13]; L.ST = lp[14]; L.LAI = lp[12];
-    L.rav_num = log_product(L.H == 0 ? 0.1 : L.H);
-  }
+  for (int q = 0; q < p->n_land_classes; q++) cls[q] = make_land_class(p->land_table + (size_t)q * 15, p->et_option);
   LandClass *d_cls = nullptr;
   if (dev_upload(c, &d_cls, cls)) return 1;
   e->st.classes = d_cls;
