@@ -297,11 +297,14 @@ int tribs_gpu_et_push(tribs_handle_t h, uint64_t et_field_mask, const double *co
  * energy balance 944-1365, 1940-2001, turbulent exchange 1373-1480, short wave on snow 1574-1748,
  * melt routing, peak/persistence trackers 1052-1135), which under OPTSNOW replaces both ET sweeps
  * at every METSTEP (tSimul.cpp:464-492); cells without snow take the ET path of kernel (1).
- * Covered: OPTINTERCEPT 0. With a canopy the reference's callSnowIntercept reads the albedo the
- * PREVIOUS cell in sweep order left in a class member (tSnowPack.cpp:1492) - a sweep-order scan
- * that is not built yet, so tribs_gpu_snow_init refuses OPTINTERCEPT != 0. The energy-balance
- * closure error (Uerror, CumUerror: round-off noise that the reference also carries from cell
- * to cell) is written per cell from the cell's own balance. */
+ * With a canopy (OPTINTERCEPT 1/2) callSnowIntercept (769-934) and computeSub (1492-1568) run
+ * first. There the reference reads two class members before the current cell has written them -
+ * `albedo` (computeSub) and, under HILLALBOPT 2, `snCanWE` (inShortWaveSn) - so they hold what the
+ * last cell BEFORE it in sweep order (or the last of the previous call) left behind. The device
+ * reproduces that order dependence with a last-writer scan over sweep positions: store-free probe
+ * rounds of the cell update until the carried values are settled (normally two), then one commit.
+ * The energy-balance closure error (Uerror, CumUerror: round-off noise that the reference also
+ * carries from cell to cell) is written per cell from the cell's own balance. */
 #define TRIBS_SNOW_FIELDS(X) \
   X(SnTempC) X(CrustAge) X(DensityAge) X(EvapoTransAge) X(SnSub) X(SnEvap) X(DU) X(Unode) X(Uerror) \
   X(SnLHF) X(SnSHF) X(SnGHF) X(SnPHF) X(SnRLout) X(SnRLin) X(SnRSin) \
@@ -315,7 +318,7 @@ typedef enum { TRIBS_SNOW_FIELDS(TRIBS_SNOW_FIELD_ENUM) TRIBS_N_SNOW_FIELDS } tr
 typedef struct {
   double min_sn_temp;           /* MINSNTEMP */
   double snliqfrac;             /* SNLIQFRAC */
-  int32_t hill_albedo_option;   /* HILLALBOPT (0 or 1; 2 needs the canopy path) */
+  int32_t hill_albedo_option;   /* HILLALBOPT 0..2 */
   int32_t reserved;
   const double *const *init;    /* NULL, or TRIBS_N_SNOW_FIELDS pointers (NULL entries = 0) */
 } tribs_snow_params_t;
@@ -326,6 +329,10 @@ int tribs_gpu_snow_init(tribs_handle_t h, const tribs_snow_params_t *prm);
  * the hour, te_met and te_eti filled); hourly_time_step = tEvapoTrans::hourlyTimeStep of the call */
 int tribs_gpu_snow_step(tribs_handle_t h, const tribs_et_step_t *s, int32_t hourly_time_step);
 int tribs_gpu_snow_sync(tribs_handle_t h, uint64_t snow_field_mask, double *const *host);
+/* the tSnowPack members that outlive a call (members[0] = albedo, members[1] = snCanWE, as the last
+ * swept cell left them; what a restart has to carry) and the number of probe rounds of the last call
+ * (0 without a canopy); either pointer may be NULL */
+int tribs_gpu_snow_members(tribs_handle_t h, double *members, int32_t *probe_rounds);
 
 #ifdef __cplusplus
 }

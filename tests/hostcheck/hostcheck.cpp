@@ -6,6 +6,7 @@
 #include "../../tribs_b200/csrc/cell_update.cuh"
 #include "../../tribs_b200/csrc/snow_update.cuh"
 #include <vector>
+#include <algorithm>
 #include <cstring>
 
 using namespace tribs;
@@ -87,12 +88,13 @@ double hc_lambert_w(double z) { return lambert_w(z); }
 // si: do_potential do_components intercept_flag hour first_call dew_hum_flag ts_option sky_flag_from met_time
 // sd: alphaD sinAlpha sunaz Io te_met te_eti
 // met_pot / met_cmp: air_temp dew_temp rel_humid vap_press atm_press wind_speed sky_cover rad_global elev
-// snow: NULL, or {min_sn_temp, snliqfrac, hill_albedo_option, hourly}: run callSnowPack instead
+// snow: NULL, or {min_sn_temp, snliqfrac, hill_albedo_option, hourly, albedo member, snCanWE member, probe rounds}:
+// run callSnowPack instead; entries 4..6 are updated
 int hc_n_et_fields() { return TRIBS_N_ET_FIELDS; }
 int hc_n_snow_fields() { return TRIBS_N_SNOW_FIELDS; }
 void hc_et_step(int n, const int32_t *ci, const double *cd, double **est, const int32_t *land_class, const double *land_table,
                 int n_classes, const int32_t *si, const double *sd, const int32_t *cell_record, double **met_pot,
-                double **met_cmp, double **etf, double **fields, const double *snow, double **snf) {
+                double **met_cmp, double **etf, double **fields, double *snow, double **snf) {
   EtConst k{};
   k.et_option = ci[0]; k.i_option = ci[1]; k.gflux_option = ci[2]; k.shelter_option = ci[3];
   k.metstep_min = cd[0]; k.etistep_h = cd[1]; k.tlinke = cd[2]; k.temp_lapse = cd[3]; k.max_interstorm = cd[4];
@@ -134,7 +136,59 @@ void hc_et_step(int n, const int32_t *ci, const double *cd, double **est, const 
   SnowConst sc{snow[0], snow[1], (int32_t)snow[2], (int32_t)snow[3]};
   SnowView sv;
   for (int f = 0; f < TRIBS_N_SNOW_FIELDS; f++) sv.f[f] = snf[f];
-  s.do_potential = 1; s.do_components = 1; s.intercept_flag = 0; s.met_time = 1; s.cmp = s.pot;
-  for (int i = 0; i < n; i++) snow_cell_step(k, st, s, sc, ev, sv, dv, i);
+  s.do_potential = 1; s.do_components = 1; s.intercept_flag = k.i_option != 0; s.met_time = 1; s.cmp = s.pot;
+  SnowProbe pr;
+  if (k.i_option == 0) {
+    for (int i = 0; i < n; i++) snow_cell_step(k, st, s, sc, ev, sv, dv, i, 0.88, 0.0, pr);
+    return;
+  }
+  // the protocol of snow_step_with_canopy (tribs_gpu.cu) with host loops for the kernels and the scan:
+  // store-free probe rounds until the answers repeat, last-writer scans, one commit
+  std::vector<int32_t> key_alb[2], key_can[2], last_alb(n + 1), last_can(n + 1), sensitive(n);
+  std::vector<double> val_alb[2], val_can[2];
+  for (int b = 0; b < 2; b++) { key_alb[b].assign(n + 1, 0); key_can[b].assign(n + 1, 0); val_alb[b].assign(n, 0.0); val_can[b].assign(n, 0.0); }
+  double *members = snow + 4;
+  auto scan = [&](const std::vector<int32_t> &key, std::vector<int32_t> &last) {
+    int32_t run = 0;
+    for (int p = 0; p <= n; p++) { last[p] = run; run = std::max(run, key[p]); }
+  };
+  auto carried = [&](const std::vector<int32_t> &last, const std::vector<double> &val, double member, int pos) {
+    return last[pos] > 0 ? val[last[pos] - 1] : member;
+  };
+  int n_sensitive = 0;
+  for (int i = 0; i < n; i++) {
+    snow_cell_t<false>(k, st, s, sc, ev, sv, dv, i, members[0], 0.0, pr);
+    sensitive[i] = pr.sensitive; n_sensitive += pr.sensitive;
+    key_alb[0][i] = pr.alb_writer ? i + 1 : 0; val_alb[0][i] = pr.alb_value;
+    key_can[0][i] = pr.can_writer ? i + 1 : 0; val_can[0][i] = pr.can_value;
+  }
+  scan(key_alb[0], last_alb);
+  int buf = 0, rounds = 1;
+  while (n_sensitive > 0) {
+    const int rd = buf, wr = buf ^ 1;
+    bool changed = false;
+    for (int i = 0; i < n; i++) {
+      if (!sensitive[i]) {
+        key_alb[wr][i] = key_alb[rd][i]; val_alb[wr][i] = val_alb[rd][i]; key_can[wr][i] = key_can[rd][i]; val_can[wr][i] = val_can[rd][i];
+        continue;
+      }
+      snow_cell_t<false>(k, st, s, sc, ev, sv, dv, i, carried(last_alb, val_alb[rd], members[0], i), 0.0, pr);
+      const int32_t ka = pr.alb_writer ? i + 1 : 0, kc = pr.can_writer ? i + 1 : 0;
+      if (ka != key_alb[rd][i] || kc != key_can[rd][i] || memcmp(&pr.alb_value, &val_alb[rd][i], 8) || memcmp(&pr.can_value, &val_can[rd][i], 8))
+        changed = true;
+      key_alb[wr][i] = ka; val_alb[wr][i] = pr.alb_value; key_can[wr][i] = kc; val_can[wr][i] = pr.can_value;
+    }
+    rounds++;
+    buf = wr;
+    if (!changed) break;
+    scan(key_alb[buf], last_alb);
+  }
+  scan(key_can[buf], last_can);
+  for (int i = 0; i < n; i++)
+    snow_cell_step(k, st, s, sc, ev, sv, dv, i, carried(last_alb, val_alb[buf], members[0], i),
+                   carried(last_can, val_can[buf], members[1], i), pr);
+  if (last_alb[n] > 0) members[0] = val_alb[buf][last_alb[n] - 1];
+  if (last_can[n] > 0) members[1] = val_can[buf][last_can[n] - 1];
+  snow[6] = rounds;
 }
 }

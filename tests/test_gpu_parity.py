@@ -104,8 +104,7 @@ def test_gpu_et_per_cell_met_records_equal_station_records(built):
 def test_gpu_et_init_refuses_uncovered_options(built):
     from tribs_b200 import gpu
     basin, _, _ = load_golden("met")
-    # (OPTSNOW 1 together with a canopy: the golden met deck has OPTINTERCEPT 2)
-    for key, val in (("et_shelterOption", 2), ("et_snowOption", 1), ("et_luOption", 1), ("et_option", 4)):
+    for key, val in (("et_shelterOption", 2), ("et_luOption", 1), ("et_option", 4)):
         b = dict(basin)
         b[key] = np.array([val], np.int32)
         dev = gpu.GpuBasin(b)

@@ -115,7 +115,7 @@ class _EtHostCheck:
         self.L, self.b, self.o, self.tol = _hc_lib(), basin, stepper, tol
         self.et_names, self.sn_names, self.fields = ET_FIELDS, SNOW_FIELDS, FIELDS
         assert self.L.hc_n_et_fields() == len(ET_FIELDS) and self.L.hc_n_snow_fields() == len(SNOW_FIELDS)
-        self.worst, self.calls = 0.0, 0
+        self.worst, self.calls, self.rounds = 0.0, 0, []
         b = basin
         self.n = int(b["n_active"][0])
         self.ci = np.array([b["et_option"][0], b["et_Ioption"][0], b["et_gFluxOption"][0], b["et_shelterOption"][0]], np.int32)
@@ -132,6 +132,7 @@ class _EtHostCheck:
         self.snap_et = {k: et.f[k].copy() for k in self.et_names}
         self.snap_sn = {k: et.f[k].copy() for k in self.sn_names} if et.snow else {}
         self.snap_main = {k: self.o.m.state[k].copy() for k in self.MAIN}
+        self.snap_members = et.members.copy() if et.snow else None
 
     def run_and_compare(self, pot, cmp_, snow_hourly=None):
         host = self.o.host
@@ -154,7 +155,7 @@ class _EtHostCheck:
         snow, snf_tab, snf = None, None, []
         if snow_hourly is not None:
             snow = np.array([self.b["sn_minSnTemp"][0], self.b["sn_snliqfrac"][0], self.b["sn_hillAlbedoOption"][0],
-                             snow_hourly], np.float64)
+                             snow_hourly, self.snap_members[0], self.snap_members[2], 0.0], np.float64)
             snf = [self.snap_sn[k] for k in self.sn_names]
             snf_tab = _ptab(snf, PD)
         self.L.hc_et_step(self.n, self.ci.ctypes.data_as(PI), self.cd.ctypes.data_as(PD), _ptab(self.est, PD),
@@ -173,6 +174,10 @@ class _EtHostCheck:
                 err = np.abs(ref - got_of(k)) / np.maximum(np.abs(ref), floor.get(k, 1e-9))
                 assert err.max() <= self.tol, (k, self.calls, float(err.max()), ref[np.argmax(err)], got_of(k)[np.argmax(err)])
                 self.worst = max(self.worst, float(err.max()))
+        if snow is not None and self.ci[1] != 0:     # canopy: the members the call leaves behind, and the probe rounds
+            assert snow[4] == et.members[0] or abs(snow[4] - et.members[0]) <= self.tol, (snow[4], et.members[0])
+            assert abs(snow[5] - et.members[2]) <= self.tol * max(1.0, abs(et.members[2])), (snow[5], et.members[2])
+            self.rounds.append(int(snow[6]))
         self.calls += 1
 
 
@@ -237,3 +242,20 @@ def test_snow_device_header_matches_oracle_on_host(built):
     hc = _drive_with_host_check(basin, 96 * 16, tol=1e-9)
     assert hc.calls >= 90
     assert np.abs(hc.o.et.f["CumMelt"]).max() > 0
+
+
+@pytest.mark.parametrize("extra", [{}, {"HILLALBOPT": 2}, {"OPTINTERCEPT": 1}])
+def test_snow_with_canopy_device_header_matches_oracle_on_host(extra, built):
+    """OPTSNOW 1 with a canopy: the reference carries `albedo` / `snCanWE` from cell to cell in sweep
+    order. The host check runs the same probe / last-writer scan / commit protocol as
+    snow_step_with_canopy (tribs_gpu.cu) on the device's cell update and must land on what the
+    sequential oracle (bit-exact against the reference) leaves behind."""
+    from refrun import have_harness, run_reference, spec_for
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    basin, _, _, _ = run_reference(spec_for("snow", 10, runtime_h=96.0, seed=9, pmean=8.0, extra=extra))
+    assert int(basin["et_Ioption"][0]) != 0
+    hc = _drive_with_host_check(basin, 96 * 16, tol=1e-9)
+    assert hc.calls >= 90
+    assert np.abs(hc.o.et.f["CumIntSub"]).max() > 0 and np.abs(hc.o.et.f["CumMelt"]).max() > 0
+    assert max(hc.rounds) >= 2 and max(hc.rounds) <= 4, hc.rounds

@@ -1,0 +1,34 @@
+"""GPU parity of tSnowPack::callSnowPack with a canopy (OPTSNOW 1 + OPTINTERCEPT 1/2), through the
+C ABI, against live runs of the reference binary. The reference carries two class members
+(`albedo`, `snCanWE`) from cell to cell in sweep order; the device reproduces that with store-free
+probe rounds + a last-writer scan + one commit (snow_step_with_canopy, tribs_gpu.cu)."""
+import numpy as np
+import pytest
+
+from common import GpuStepper, run_and_compare
+from refrun import have_harness, run_reference, schedule_for, spec_for
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6
+ABS_FLOOR = 1e-6
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("extra", [{}, {"HILLALBOPT": 2}, {"OPTINTERCEPT": 1}])
+def test_gpu_snow_pack_with_canopy_matches_live_reference(extra, built):
+    spec = spec_for("snow", 20, runtime_h=96.0, seed=9, pmean=8.0, extra=extra)
+    n_steps = 96 * 16
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="murb")
+    assert int(basin["et_Ioption"][0]) != 0
+    for k in [k for k in snaps if k.endswith("_m_Uerror") or k.endswith("_m_CumUerror")]:
+        del snaps[k]      # energy-balance closure error: 1e-14 round-off noise, see include/tribs_gpu.h
+    g = GpuStepper(basin, schedule_for(basin))
+    w = run_and_compare(g, snaps, n_steps, floor=ABS_FLOOR)
+    print("\n[snow+canopy] worst:\n" + w.report(8))
+    assert w.max() <= REL_TOL, w.report()
+    assert ("m", "IntSWE") in w.w and ("m", "CumIntSub") in w.w and ("m", "CumMelt") in w.w
+    assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumIntSub")) > 0.0
+    assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0
+    members, rounds = g.sim.dev.snow_members()
+    assert 0.45 <= members[0] <= 0.88 and rounds >= 1

@@ -335,7 +335,10 @@ TRIBS_HD void intercept_rutter(const LandClass &lc, const EtConst &k, double rai
 // ---- the cell update -------------------------------------------------------------------------------
 #define EF(name) ev.f[TRIBS_ET_##name][i]
 
-TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
+// kStore = false evaluates the cell without leaving anything behind (the snow path probes cells
+// that way, snow_update.cuh). Returns the net precipitation below the canopy.
+template <bool kStore>
+TRIBS_HD double et_sweeps_t(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
   const LandClass lc = st.classes[st.land_class[i]];
   const double elevation = st.z[i];
   const double rain = dv.f[TRIBS_F_Rain][i];
@@ -358,7 +361,7 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
       const double t0 = s.pot.air_temp[s.pot.cell_record[i]] + 273.15;
       soilT = t0 - 273.15; surfT = t0 - 273.15;
     } else { surfT = EF(SurfTemp); soilT = EF(SoilTemp); }
-    if (k.i_option == 0) dv.f[TRIBS_F_NetPrecipitation][i] = rain;
+    if (kStore && k.i_option == 0) dv.f[TRIBS_F_NetPrecipitation][i] = rain;
 
     EnergyBalance eb;
     eb.et_option = k.et_option;
@@ -426,6 +429,7 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
     potEvap = 3600.0 * eb.potEvap;
     actEvap = (k.et_option == 1) ? 3600.0 * (eb.lFlux / a.lam) : potEvap * betaS;
 
+    if (kStore) {
     EF(SurfTemp) = Tg - 273.15; EF(SoilTemp) = tlo - 273.15;
     EF(NetRad) = eb.netRad; EF(GFlux) = eb.gFlux; EF(HFlux) = eb.hFlux; EF(LFlux) = eb.lFlux;
     EF(LongRadIn) = eb.inLongR; EF(LongRadOut) = eb.outLongR;
@@ -443,11 +447,12 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
     EF(SheltFact) = shelter;
     EF(CumRSin) += a.inShortR * 3600.0;
     EF(PotEvap) = potEvap; EF(ActEvap) = actEvap;
+    }
   } else if (s.do_components && k.et_option) {
     potEvap = EF(PotEvap); actEvap = EF(ActEvap);
   }
 
-  if (!s.do_components) return;
+  if (!s.do_components) return dv.f[TRIBS_F_NetPrecipitation][i];
   Canopy can;
   can.StormLength = EF(StormLength); can.CumIntercept = EF(CumIntercept); can.CanStorage = EF(CanStorage);
   can.InterceptLoss = EF(InterceptLoss); can.EvapWetCanopy = EF(EvapWetCanopy);
@@ -456,16 +461,18 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
   if (!k.et_option) {
     if (s.intercept_flag && canopy) {
       if (k.i_option == 1) intercept_gray(lc, k, rain, can); else intercept_rutter(lc, k, rain, 0.0, can);
+      if (kStore) {
       EF(StormLength) = can.StormLength; EF(CumIntercept) = can.CumIntercept; EF(CanStorage) = can.CanStorage;
       EF(InterceptLoss) = can.InterceptLoss; EF(EvapWetCanopy) = can.EvapWetCanopy;
       dv.f[TRIBS_F_NetPrecipitation][i] = can.NetPrecipitation;
+      }
     }
-    return;
+    return can.NetPrecipitation;
   }
   MetAir a;
   a.load(s.cmp, i, elevation, k.temp_lapse, s.dew_hum_flag);
-  if (potEvap < 0) { potEvap = 0.0; EF(PotEvap) = 0.0; }
-  if (actEvap < 0.0) { actEvap = 0.0; EF(ActEvap) = 0.0; }
+  if (potEvap < 0) { potEvap = 0.0; if (kStore) EF(PotEvap) = 0.0; }
+  if (actEvap < 0.0) { actEvap = 0.0; if (kStore) EF(ActEvap) = 0.0; }
   const double ra = a.aero_resist(lc, k.ras_num);
   // the reference mixes a x100 Clausius-Clapeyron slope with an unscaled psychrometric constant here
   const double transFactor = (a.cc + a.psy_raw) / (a.cc + a.psy_raw * (1 + rs / ra));
@@ -490,6 +497,7 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
   const double soil = (st.bedrock[i] <= 0) ? 0.0 : (1 - lc.V) * remaining * betaS;
   const double et = wet + dry + soil;
   if (k.i_option == 1) can.CumIntercept = can.CumIntercept - wet / lc.V * k.etistep_h;
+  if (!kStore) return can.NetPrecipitation;
   EF(StormLength) = can.StormLength; EF(CumIntercept) = can.CumIntercept; EF(CanStorage) = can.CanStorage;
   EF(InterceptLoss) = can.InterceptLoss;
   dv.f[TRIBS_F_NetPrecipitation][i] = can.NetPrecipitation;
@@ -501,6 +509,10 @@ TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s
   EF(CumBarEvap) += soil;
   if (fabs(s.te_eti - 1.0) < 1.0E-6) EF(AvET) = et;
   else if (s.te_eti > 1.0) EF(AvET) = (EF(AvET) * (s.te_eti - 1.0) + et) / s.te_eti;
+  return can.NetPrecipitation;
+}
+TRIBS_HD void et_sweeps(const EtConst &k, const EtStatic &st, const EtStepDev &s, const EtView &ev, const DynView &dv, int i) {
+  et_sweeps_t<true>(k, st, s, ev, dv, i);
 }
 
 // the two sweeps, then the canopy water balance that Simulator::UpdateWaterBalance applies at the

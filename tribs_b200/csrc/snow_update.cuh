@@ -1,10 +1,19 @@
-// Snow pack cell update (tSnowPack::callSnowPack without canopy interception). One thread per cell.
+// Snow pack cell update (tSnowPack::callSnowPack incl. callSnowIntercept). One thread per cell.
 // Reference behaviour restated here (src/tHydro/tSnowPack.cpp):
 //   getFrNodeSnP 999-1044 / setToNodeSnP 1052-1135 -> load / store of SnowCell
 //   updateRipeSnowPack / updateSolidSnowPack 944-990, snowFracCalc 1244-1290, resFactCalc 1373-1480,
 //   latentHFCalc / sensibleHFCalc 1177-1236, precipitationHFCalc 1298-1328, agingAlbedo 1336-1365,
 //   inShortWaveSn 1574-1748, snowEB 1940-2001, the pack bookkeeping of callSnowPack 440-700.
+//   callSnowIntercept 769-934, computeSub 1492-1568 -> snow_canopy_sublimation().
 // Cells without snow on the ground, in the air or in the canopy take the ET path (et_sweeps).
+//
+// With a canopy the reference reads two tSnowPack members before the current cell has written them:
+// `albedo` (computeSub) and, under HILLALBOPT 2, `snCanWE` (inShortWaveSn of a cell without canopy).
+// They therefore hold what the last cell *before it in sweep order* left there (or the last one of
+// the previous call). The device reproduces that with a last-writer scan over sweep positions:
+// snow_cell_t<false> ("probe") evaluates a cell without storing anything and reports whether and what
+// it would write to the two members; the probe is repeated for the cells whose answer can depend on
+// the incoming albedo until no answer changes; snow_cell_t<true> then commits with the final values.
 #pragma once
 #include "et_update.cuh"
 
@@ -15,6 +24,12 @@ struct SnowConst {
   int32_t hill_albedo_option, hourly;
 };
 struct SnowView { double *f[TRIBS_N_SNOW_FIELDS]; };
+
+// what a cell found in / leaves in the tSnowPack members that outlive it (see the header comment)
+struct SnowProbe {
+  int32_t alb_writer, can_writer, sensitive;   // sensitive: the cell's results depend on the incoming albedo
+  double alb_value, can_value;
+};
 
 struct SnowCell {
   double liqWE, iceWE, snWE, snSub, snEvap, liqRoute, Utot, snTempC, crustAge, densityAge, ETAge;
@@ -71,9 +86,9 @@ TRIBS_HD double snow_sensible_hf(const MetAir &a, const SnowCell &w, double Kaer
   const double t = (w.liqWE > 1e-5) ? 0.0 : w.snTempC;
   return (rhoAir * cpairkJ * Kaero * ((a.airTemp + 273.15) - (t + 273.15)));
 }
-TRIBS_HD double snow_precip_hf(const MetAir &a, double rain, double sfrac) {
+TRIBS_HD double snow_precip_hf(const MetAir &a, double rain, double sfrac, double snUnload) {
   using namespace snowk;
-  const double snPrec = (sfrac * (rain + 10.0 * 0.0)) * mtoc, liqPrec = ((1 - sfrac) * (rain + 10.0 * 0.0)) * mtoc;
+  const double snPrec = (sfrac * (rain + 10.0 * snUnload)) * mtoc, liqPrec = ((1 - sfrac) * (rain + 10.0 * snUnload)) * mtoc;
   if (a.airTemp > 0)
     return (cmtonaught * snPrec * 0 * rholiqkg * cpicekJ + cmtonaught * liqPrec * (latFreezekJ + a.airTemp * rholiqkg * cpwaterkJ)) / 3600;
   return (cmtonaught * snPrec * a.airTemp * rholiqkg * cpicekJ + cmtonaught * liqPrec * latFreezekJ * rholiqkg) / 3600;
@@ -109,6 +124,27 @@ TRIBS_HD void snow_route_excess(SnowCell &w, double snliqfrac) {
   }
 }
 
+// computeSub, tSnowPack.cpp:1492-1568: sublimation of intercepted snow over one met step [mm]
+TRIBS_HD double snow_canopy_sublimation(const MetAir &a, const LandClass &lc, double albedo, double I, double Imax,
+                                        double airTempK, double time_s) {
+  using namespace snowk;
+  const double PI = 3.1415926;
+  const double kc = 0.010, iceRad = 500e-6, Mwater = 18.01, R = 8313.0, RdryAir = 287.0, nu = 1.3e-5, KtAtm = 0.024, beta = 0.9;
+  const double Sp = PI * (iceRad * iceRad) * (1 - albedo) * a.inShortR;
+  const double windSpeedC = a.windSpeed * exp(-(beta * lc.LAI) * 0.4);
+  const double Re = 2 * iceRad * windSpeedC / nu;
+  const double Sh = 1.79 + 0.606 * sqrt(Re);
+  const double Nu = Sh;
+  const double esatIce = 611.15 * exp(22.452 * (airTempK - 273.16) / (airTempK - 0.61));
+  const double rhoVap = 0.622 * esatIce / (RdryAir * airTempK);
+  const double D = 2.06e-5 * pow(airTempK / 273.0, 1.75);
+  const double Omega = (1 / (KtAtm * airTempK * Nu)) * (1000 * latSubkJ * Mwater / (R * airTempK) - 1);
+  const double dmdt = (2.0 * PI * iceRad * (a.rHumidityC / 100 - 1) - Sp * Omega) / (1000 * latSubkJ * Omega + (1 / (D * rhoVap * Sh)));
+  const double psiS = dmdt / ((4.0 / 3.0) * PI * rhoicekg * iceRad * iceRad * iceRad);
+  const double Ce = kc * pow(I / Imax, -0.4);
+  return Ce * I * psiS * time_s;
+}
+
 #define EF(name) ev.f[TRIBS_ET_##name][i]
 #define SNF(name) sv.f[TRIBS_SN_##name][i]
 
@@ -137,9 +173,13 @@ TRIBS_HD void snow_store(SnowCell &w, const SnowConst &sc, const SnowView &sv, c
   SNF(CumHrsSnow) += w.snOnOff;
 }
 
-TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s, const SnowConst &sc, const EtView &ev,
-                        const SnowView &sv, const DynView &dv, int i) {
+// One cell of callSnowPack. alb_in / can_in: the tSnowPack members `albedo` and `snCanWE` as the
+// cell finds them; pr: what it leaves there. kStore = false touches no array.
+template <bool kStore>
+TRIBS_HD void snow_cell_t(const EtConst &k, const EtStatic &st, const EtStepDev &s, const SnowConst &sc, const EtView &ev,
+                          const SnowView &sv, const DynView &dv, int i, double alb_in, double can_in, SnowProbe &pr) {
   using namespace snowk;
+  pr.alb_writer = 0; pr.can_writer = 0; pr.sensitive = 0; pr.alb_value = 0.0; pr.can_value = 0.0;
   const LandClass lc = st.classes[st.land_class[i]];
   const double rain = dv.f[TRIBS_F_Rain][i];
   const double time_m = k.metstep_min, time_h = time_m / 60.0, time_s = 60.0 * time_m;
@@ -149,14 +189,18 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
   SnowCell w{};
   w.liqWE = dv.f[TRIBS_F_LiqWE][i]; w.iceWE = dv.f[TRIBS_F_IceWE][i];
   w.snWE = w.liqWE + w.iceWE;
-  if (w.snWE > 1e-4) w.snTempC = SNF(SnTempC);
+  const double snTempNode = SNF(SnTempC);
+  if (w.snWE > 1e-4) w.snTempC = snTempNode;
   else w.snTempC = (a.airTemp > 0.0) ? 0.0 : a.airTemp;
   w.crustAge = SNF(CrustAge); w.densityAge = SNF(DensityAge); w.ETAge = SNF(EvapoTransAge);
   w.persMax = SNF(PersTimeMax); w.persMaxtemp = SNF(PersTime); w.peakSnWE = SNF(PeakSWE);
   w.inittime = SNF(InitPackTime); w.inittimeTemp = SNF(InitPackTimeTemp); w.peaktime = SNF(PeakPackTime);
   w.Uerr = SNF(Uerror);
+  w.albedo = alb_in;
+  const double intSWE_node = SNF(IntSWE);
 
-  if ((w.snWE <= 1e-4) && (rain * sfrac <= 5e-2) && rholiqkg * cmtonaught * SNF(IntSWE) < 1e-3) {
+  if ((w.snWE <= 1e-4) && (rain * sfrac <= 5e-2) && rholiqkg * cmtonaught * intSWE_node < 1e-3) {
+    if (!kStore) return;
     et_sweeps(k, st, s, ev, dv, i);                      // no snow anywhere: kernel (1)'s two sweeps
     SNF(SnLHF) = 0.0; SNF(SnSHF) = 0.0; SNF(SnPHF) = 0.0; SNF(SnGHF) = 0.0; SNF(SnRLin) = 0.0; SNF(SnRLout) = 0.0; SNF(SnRSin) = 0.0;
     w.snTempC = 0.0; w.snWE = 0.0; w.snSub = 0.0; w.snEvap = 0.0;
@@ -171,15 +215,76 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
   const double shelter = (k.shelter_option == 0) ? 0.5 * (1 + cos_s) : 1.0;
   const bool sky_flag = (st.sweep_of_dev[i] >= s.sky_flag_from) || (fabs(a.skyCover - 9999.99) < 1.0E-3);
   if (sky_flag) a.skyCover = a.sky_from_humidity(rain);
-  if (k.shelter_option == 0) EF(SheltFact) = shelter;
-  EF(AirTemp) = a.airTemp; EF(DewTemp) = a.dewTemp; EF(RelHumid) = a.rHumidity; EF(VapPressure) = a.vPressC;
-  EF(SkyCover) = a.skyCover; EF(WindSpeed) = a.windSpeed; EF(AirPressure) = a.atmPress;
-  if (s.first_call) {
-    const double t0 = s.pot.air_temp[s.pot.cell_record[i]] + 273.15;
-    EF(SoilTemp) = t0 - 273.15; EF(SurfTemp) = t0 - 273.15;
+  if (kStore) {
+    if (k.shelter_option == 0) EF(SheltFact) = shelter;
+    EF(AirTemp) = a.airTemp; EF(DewTemp) = a.dewTemp; EF(RelHumid) = a.rHumidity; EF(VapPressure) = a.vPressC;
+    EF(SkyCover) = a.skyCover; EF(WindSpeed) = a.windSpeed; EF(AirPressure) = a.atmPress;
+    if (s.first_call) {
+      const double t0 = s.pot.air_temp[s.pot.cell_record[i]] + 273.15;
+      EF(SoilTemp) = t0 - 273.15; EF(SurfTemp) = t0 - 273.15;
+    }
   }
-  dv.f[TRIBS_F_NetPrecipitation][i] = rain;             // no canopy (OPTINTERCEPT 0)
-  const double precip = rain;
+  double precip = rain, snUnload = 0.0, snCanWE = can_in;
+  bool shortrad_from_met = true;                          // F(ShortRadIn) = observed value unless the ET path ran
+  if ((k.i_option == 1) || (k.i_option == 2 && lc.P < 0.999)) {
+    // ---- callSnowIntercept, tSnowPack.cpp:769-934
+    const double canStorage = EF(CanStorage), prec = rain;
+    const double airTempK = a.airTemp + 273.15;
+    double Iold = rholiqkg * cmtonaught * intSWE_node;
+    if ((prec * sfrac < 1e-4) && (Iold < 1e-3)) {
+      // nothing frozen in the canopy: the soil energy balance and the rain interception run under the
+      // pack, their fluxes are then cleared (the reference's choice)
+      precip = et_sweeps_t<kStore>(k, st, s, ev, dv, i);
+      shortrad_from_met = false;
+      if (kStore) {
+        EF(NetRad) = 0.0; EF(GFlux) = 0.0; EF(HFlux) = 0.0; EF(LFlux) = 0.0; EF(LongRadOut) = 0.0;
+        EF(SurfTemp) = snTempNode; EF(SoilTemp) = snTempNode;
+        EF(ActEvap) = 0.0;
+        SNF(SnLHF) = 0.0; SNF(SnSHF) = 0.0; SNF(SnPHF) = 0.0; SNF(SnGHF) = 0.0; SNF(SnRLin) = 0.0; SNF(SnRLout) = 0.0; SNF(SnRSin) = 0.0;
+        SNF(IntSWE) = 0.0; SNF(IntSnUnload) = 0.0; SNF(IntSub) = 0.0; SNF(IntPrec) = 0.0;
+        dv.f[TRIBS_F_EvapSoil][i] = 0.0;
+      }
+      snUnload = 0.0; snCanWE = 0.0;
+    } else {
+      bool fl = true;
+      if (canStorage > 1e-5) { Iold += canStorage; fl = false; if (kStore) EF(CanStorage) = 0.0; }
+      const double Imax = 4.4 * lc.LAI;
+      const double Isnow = 0.7 * (Imax - Iold) * (1 - exp(-prec / Imax));
+      double I = Iold + Isnow, Qcs = 0.0, Lm = 0.0;
+      const double throughfall = prec - Isnow;
+      if (Iold > 0.0 && fl) {
+        Qcs = snow_canopy_sublimation(a, lc, alb_in, I, Imax, airTempK, time_s);
+        pr.sensitive = 1;
+        Lm = (airTempK >= 273.16) ? 5.8e-5 * (airTempK - 273.16) * time_s : 0.0;
+      }
+      I += Qcs - Lm;
+      if (I < 0.0) {
+        double subFrac, unlFrac;
+        if (Qcs < 0.0) { subFrac = fabs(Qcs) / (fabs(Qcs) + Lm); unlFrac = Lm / (fabs(Qcs) + Lm); }
+        else { subFrac = 0.0; unlFrac = 1.0; }
+        Qcs -= I * subFrac;
+        Lm += I * unlFrac;
+        I = 0.0;
+      }
+      const double intSWE = naughttocm * (1 / rholiqkg) * I;
+      const double unload = naughttocm * (1 / rholiqkg) * Lm * lc.V;
+      const double sub = naughttocm * (1 / rholiqkg) * Qcs * lc.V;
+      precip = (throughfall * lc.V) + (rain * (1 - lc.V));
+      if (kStore) {
+        SNF(IntSWE) = intSWE; SNF(IntSnUnload) = unload; SNF(IntSub) = sub;
+        SNF(CumIntSub) += sub; SNF(CumIntUnl) += unload;
+        SNF(IntPrec) = Isnow * (1 / rholiqkg) * naughttocm;
+        dv.f[TRIBS_F_NetPrecipitation][i] = precip;
+        EF(EvapWetCanopy) = 0.0; dv.f[TRIBS_F_EvapDryCanopy][i] = 0.0; dv.f[TRIBS_F_EvapSoil][i] = 0.0;
+        EF(EvapoTrans) = 0.0; EF(PotEvap) = 0.0;
+      }
+      snUnload = unload; snCanWE = intSWE;
+    }
+    pr.can_writer = 1; pr.can_value = snCanWE;
+  } else if (kStore) {
+    dv.f[TRIBS_F_NetPrecipitation][i] = rain;
+  }
+  precip += snUnload * 10.0;
   w.snDepthm = cmtonaught * w.snWE / 0.312;
   w.iceWE = w.iceWE * cmtonaught; w.liqWE = w.liqWE * cmtonaught; w.snWE = w.iceWE + w.liqWE;
   w.snTempC = (a.airTemp > 0.0) ? 0.0 : a.airTemp;
@@ -192,7 +297,7 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
     snow_route_excess(w, sc.snliqfrac);
     if (w.liqWE < 0) { w.liqWE = 0; w.snWE = w.iceWE; }
     w.Utot = w.dUint = w.iceWE * rhoicekg * cpicekJ * w.snTempC + w.liqWE * rholiqkg * latFreezekJ;
-    EF(ShortRadIn) = a.inShortR;
+    if (kStore && shortrad_from_met) EF(ShortRadIn) = a.inShortR;
   } else {
     w.phfOnOff = 1.0;
     w.densityAge = (w.snWE * w.densityAge) / (w.snWE + mtoc * precip);
@@ -202,19 +307,21 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
     w.snSub *= naughttocm; w.snEvap *= naughttocm;
     w.ETAge = 0.0;
     w.L = snow_latent_hf(a, w, snow_res_fact(a, lc, w));
-    w.Prec = snow_precip_hf(a, rain, sfrac);
-    EF(ShortRadIn) = a.inShortR;
+    w.Prec = snow_precip_hf(a, rain, sfrac, snUnload);
+    if (kStore && shortrad_from_met) EF(ShortRadIn) = a.inShortR;
     if ((w.snWE <= 5e-6) || (w.snTempC < -800.0)) {
       w.liqRoute = 0.0; w.snWE = 0.0; w.iceWE = 0.0; w.liqWE = 0.0; w.Utot = 0.0; w.snTempC = 0.0; w.crustAge = 0.0; w.densityAge = 0.0;
     } else {
       const double Utotold = w.iceWE * rhoicekg * cpicekJ * w.snTempC + w.liqWE * rholiqkg * latFreezekJ;
       w.Utot = Utotold;
       w.albedo = snow_aging_albedo(w);
+      pr.alb_writer = 1; pr.alb_value = w.albedo;
+      if (!kStore) return;
       // ---- snowEB
       const double resFact = snow_res_fact(a, lc, w);
       w.H = snow_sensible_hf(a, w, resFact);
       w.L = snow_latent_hf(a, w, resFact);
-      w.Prec = w.phfOnOff * snow_precip_hf(a, rain, sfrac);
+      w.Prec = w.phfOnOff * snow_precip_hf(a, rain, sfrac, snUnload);
       double Isw = 0.0;
       if (s.alphaD > 0.0) {                               // inShortWaveSn
         const double pi = 4.0 * atan(1.0), h0 = s.alphaD, pp0 = exp(-st.z[i] / 8434.5);
@@ -233,7 +340,9 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
         const double v = (k.shelter_option == 0 || k.shelter_option == 3) ? 0.5 * (1 + cos_s) : 1.0;
         const double Ids = Id * v;
         double Is = (Ics + Ids), Ir = 0.0;
-        const double hillalbedo = (sc.hill_albedo_option == 1) ? lc.Al : w.albedo;
+        double hillalbedo = w.albedo;                     // HILLALBOPT 0
+        if (sc.hill_albedo_option == 1) hillalbedo = lc.Al;
+        else if (sc.hill_albedo_option == 2 && snCanWE == 0) hillalbedo = lc.V * lc.Al + (1 - lc.V) * w.albedo;
         if (k.shelter_option == 0) { Ir = hillalbedo * Is * (1 - cos_s) * 0.5; Is += Ir; }
         const double Iv = Is * exp((lc.Kt - 1) * lc.LAI) * lc.V + Is * (1.0 - lc.V);
         Isw = Iv * (1.0 - w.albedo);
@@ -271,6 +380,7 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
       }
     }
   }
+  if (!kStore) return;
   if (w.snWE <= 5e-6) {
     w.liqRoute += w.snWE;
     w.snWE = 0.0; w.liqWE = 0.0; w.iceWE = 0.0; w.crustAge = 0.0; w.densityAge = 0.0; w.Utot = 0.0;
@@ -284,8 +394,8 @@ TRIBS_HD void snow_cell(const EtConst &k, const EtStatic &st, const EtStepDev &s
 
 // callSnowPack for one cell, then the canopy water balance of a met step (as in et_cell)
 TRIBS_HD void snow_cell_step(const EtConst &k, const EtStatic &st, const EtStepDev &s, const SnowConst &sc, const EtView &ev,
-                             const SnowView &sv, const DynView &dv, int i) {
-  snow_cell(k, st, s, sc, ev, sv, dv, i);
+                             const SnowView &sv, const DynView &dv, int i, double alb_in, double can_in, SnowProbe &pr) {
+  snow_cell_t<true>(k, st, s, sc, ev, sv, dv, i, alb_in, can_in, pr);
   if (s.met_time) {
     const double del_i = EF(InterceptLoss) - EF(EvapWetCanopy);
     EF(CanopyStorVol) = EF(CanopyStorVol) + del_i * (k.metstep_min / 60.0) * st.varea[i] / 1000.0;

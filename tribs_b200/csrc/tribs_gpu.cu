@@ -24,6 +24,7 @@
 //   reduce_sums_kernel   fixed-order reduction of the per-tile basin accumulators.
 #include <cuda_runtime.h>
 #include <cooperative_groups.h>
+#include <cub/device/device_scan.cuh>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -1214,6 +1215,19 @@ extern "C" int tribs_gpu_push(tribs_handle_t c, uint64_t field_mask, const tribs
 
 // ====================================================================================
 // Kernel (1): ET + interception (tribs_gpu_et_*). See et_update.cuh for the cell update.
+// last-writer scan of the tSnowPack members along the sweep, see snow_probe_kernel
+struct SnowCarry {
+  int32_t *key_alb[2] = {nullptr, nullptr}, *key_can[2] = {nullptr, nullptr};   // [n + 1], ping-pong between probe rounds
+  double *val_alb[2] = {nullptr, nullptr}, *val_can[2] = {nullptr, nullptr};    // [n]
+  int32_t *last_alb = nullptr, *last_can = nullptr;                             // [n + 1] scanned keys
+  uint8_t *sensitive = nullptr;                                                 // [n_pad] device order
+  double *members = nullptr;                                                    // [2] albedo, snCanWE between calls
+  int32_t *flags = nullptr;                                                     // [2] changed, n_sensitive
+};
+struct MaxKey {
+  __host__ __device__ int32_t operator()(int32_t a, int32_t b) const { return a > b ? a : b; }
+};
+
 struct EtState {
   EtConst k{};
   EtStatic st{};
@@ -1233,6 +1247,13 @@ struct EtState {
   bool snow_ready = false;
   SnowConst sc{};
   SnowView snv{};
+  // carry-over of the tSnowPack members `albedo` and `snCanWE` along the sweep (canopy runs only)
+  SnowCarry carry{};
+  void *d_scan_tmp = nullptr;
+  size_t scan_tmp_bytes = 0;
+  int32_t *h_flags = nullptr;                   // pinned: [0] any answer changed, [1] cells that depend on the incoming albedo
+  int last_probe_rounds = 0;
+  double members[2] = {0.88, 0.0};              // tSnowPack constructor values (tSnowPack.cpp:103-150)
 };
 
 static void tribs_free_et(tribs_ctx *c) {
@@ -1242,6 +1263,7 @@ static void tribs_free_et(tribs_ctx *c) {
       if (c->et->h_pin[sl][g]) cudaFreeHost(c->et->h_pin[sl][g]);
       if (c->et->pin_ev[sl][g]) cudaEventDestroy(c->et->pin_ev[sl][g]);
     }
+  if (c->et->h_flags) cudaFreeHost(c->et->h_flags);
   delete c->et;
   c->et = nullptr;
 }
@@ -1284,8 +1306,6 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   if (p->et_option && p->gflux_option != 1 && p->gflux_option != 2) return fail("tribs_gpu_et_init: GFLUXOPTION must be 1 or 2");
   if (!(p->shelter_option == 0 || p->shelter_option >= 4)) return fail("tribs_gpu_et_init: OPTRADSHELT 1-3 (horizon angles) is not covered");
   if (p->lu_option != 0) return fail("tribs_gpu_et_init: OPTLANDUSE 1 (dynamic land-use grids) is not covered");
-  if (p->snow_option != 0 && p->i_option != 0)
-    return fail("tribs_gpu_et_init: OPTSNOW 1 with canopy interception is not covered (sweep-order albedo carry-over, see DESIGN.md)");
   if (p->snow_option != 0 && p->et_option == 0) return fail("tribs_gpu_et_init: OPTSNOW 1 needs the evaporation scheme");
   if (p->et_option == 0 && p->i_option == 2) return fail("tribs_gpu_et_init: Rutter interception needs the evaporation scheme (tSimul.cpp:444-450)");
   CK(cudaSetDevice(c->device));
@@ -1392,14 +1412,74 @@ __global__ void __launch_bounds__(128)
 snow_cells_kernel(EtConst k, EtStatic st, EtStepDev s, SnowConst sc, EtView ev, SnowView sv, DynView dv, int n_pad) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad || st.boundary[i] < 0) return;
-  snow_cell_step(k, st, s, sc, ev, sv, dv, i);
+  SnowProbe pr;
+  snow_cell_step(k, st, s, sc, ev, sv, dv, i, 0.88, 0.0, pr);   // no canopy: nothing reads the carried members
+}
+
+// ---- canopy runs: last-writer scan of the tSnowPack members along the sweep (snow_update.cuh) ----
+// Per sweep position p: key = p + 1 if the cell at p writes the member, else 0; an exclusive
+// max-scan of the keys gives every position the last writer before it.
+__device__ __forceinline__ double carried_in(const int32_t *last, const double *val, const double *member, int pos) {
+  const int32_t q = last[pos];
+  return q > 0 ? val[q - 1] : *member;
+}
+
+// round 0: every cell answers with the member values of the previous call; later rounds: the cells
+// whose answer can depend on the incoming albedo answer again with the scanned values of the
+// previous round (buffer `rd`), everybody else repeats its answer
+__global__ void __launch_bounds__(128)
+snow_probe_kernel(EtConst k, EtStatic st, EtStepDev s, SnowConst sc, EtView ev, SnowView sv, DynView dv, SnowCarry cy,
+                  int round, int rd, int wr, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || st.boundary[i] < 0) return;
+  const int pos = st.sweep_of_dev[i];
+  if (round > 0 && !cy.sensitive[i]) {
+    cy.key_alb[wr][pos] = cy.key_alb[rd][pos]; cy.val_alb[wr][pos] = cy.val_alb[rd][pos];
+    cy.key_can[wr][pos] = cy.key_can[rd][pos]; cy.val_can[wr][pos] = cy.val_can[rd][pos];
+    return;
+  }
+  const double alb_in = (round == 0) ? cy.members[0] : carried_in(cy.last_alb, cy.val_alb[rd], cy.members, pos);
+  SnowProbe pr;
+  snow_cell_t<false>(k, st, s, sc, ev, sv, dv, i, alb_in, 0.0, pr);
+  const int32_t ka = pr.alb_writer ? pos + 1 : 0, kc = pr.can_writer ? pos + 1 : 0;
+  if (round == 0) {
+    cy.sensitive[i] = (uint8_t)pr.sensitive;
+    if (pr.sensitive) atomicAdd(&cy.flags[1], 1);
+  } else if (ka != cy.key_alb[rd][pos] || kc != cy.key_can[rd][pos] ||
+             __double_as_longlong(pr.alb_value) != __double_as_longlong(cy.val_alb[rd][pos]) ||
+             __double_as_longlong(pr.can_value) != __double_as_longlong(cy.val_can[rd][pos])) {
+    cy.flags[0] = 1;
+  }
+  cy.key_alb[wr][pos] = ka; cy.val_alb[wr][pos] = pr.alb_value;
+  cy.key_can[wr][pos] = kc; cy.val_can[wr][pos] = pr.can_value;
+}
+
+__global__ void __launch_bounds__(128)
+snow_commit_kernel(EtConst k, EtStatic st, EtStepDev s, SnowConst sc, EtView ev, SnowView sv, DynView dv, SnowCarry cy,
+                   int buf, int n_pad) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_pad || st.boundary[i] < 0) return;
+  const int pos = st.sweep_of_dev[i];
+  const double alb_in = carried_in(cy.last_alb, cy.val_alb[buf], cy.members, pos);
+  const double can_in = carried_in(cy.last_can, cy.val_can[buf], cy.members + 1, pos);
+  SnowProbe pr;
+  snow_cell_step(k, st, s, sc, ev, sv, dv, i, alb_in, can_in, pr);
+}
+
+// what the last cell of the sweep leaves in the members for the next call
+__global__ void snow_members_kernel(SnowCarry cy, int buf, int n) {
+  if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const int32_t qa = cy.last_alb[n], qc = cy.last_can[n];
+    if (qa > 0) cy.members[0] = cy.val_alb[buf][qa - 1];
+    if (qc > 0) cy.members[1] = cy.val_can[buf][qc - 1];
+  }
 }
 
 extern "C" int tribs_gpu_snow_init(tribs_handle_t c, const tribs_snow_params_t *p) {
   if (!c || !p) return fail("tribs_gpu_snow_init: null argument");
   if (!c->et || !c->et->snow_option) return fail("tribs_gpu_snow_init: call tribs_gpu_et_init with snow_option = 1 first");
   if (c->et->snow_ready) return fail("tribs_gpu_snow_init: already initialised");
-  if (p->hill_albedo_option != 0 && p->hill_albedo_option != 1) return fail("tribs_gpu_snow_init: HILLALBOPT 2 needs the canopy path, not covered");
+  if (p->hill_albedo_option < 0 || p->hill_albedo_option > 2) return fail("tribs_gpu_snow_init: HILLALBOPT must be 0..2");
   CK(cudaSetDevice(c->device));
   EtState *e = c->et;
   e->sc.min_sn_temp = p->min_sn_temp; e->sc.snliqfrac = p->snliqfrac; e->sc.hill_albedo_option = p->hill_albedo_option;
@@ -1413,7 +1493,74 @@ extern "C" int tribs_gpu_snow_init(tribs_handle_t c, const tribs_snow_params_t *
     }
     e->snv.f[f] = d;
   }
+  if (e->k.i_option != 0) {     // canopy: buffers of the last-writer scan (snow_probe_kernel)
+    SnowCarry &cy = e->carry;
+    const size_t n1 = (size_t)c->n + 1;
+    for (int b = 0; b < 2; b++) {
+      if (dev_alloc(c, &cy.key_alb[b], n1) || dev_alloc(c, &cy.key_can[b], n1) ||
+          dev_alloc(c, &cy.val_alb[b], (size_t)c->n) || dev_alloc(c, &cy.val_can[b], (size_t)c->n)) return 1;
+      CK(cudaMemset(cy.key_alb[b], 0, n1 * sizeof(int32_t)));
+      CK(cudaMemset(cy.key_can[b], 0, n1 * sizeof(int32_t)));
+      CK(cudaMemset(cy.val_alb[b], 0, (size_t)c->n * sizeof(double)));
+      CK(cudaMemset(cy.val_can[b], 0, (size_t)c->n * sizeof(double)));
+    }
+    if (dev_alloc(c, &cy.last_alb, n1) || dev_alloc(c, &cy.last_can, n1) || dev_alloc(c, &cy.sensitive, (size_t)c->n_pad) ||
+        dev_alloc(c, &cy.members, (size_t)2) || dev_alloc(c, &cy.flags, (size_t)2)) return 1;
+    CK(cudaMemset(cy.last_alb, 0, n1 * sizeof(int32_t)));
+    CK(cudaMemset(cy.last_can, 0, n1 * sizeof(int32_t)));
+    CK(cudaMemset(cy.sensitive, 0, (size_t)c->n_pad));
+    CK(cudaMemcpy(cy.members, e->members, 2 * sizeof(double), cudaMemcpyHostToDevice));
+    size_t bytes = 0;
+    CK(cub::DeviceScan::ExclusiveScan(nullptr, bytes, cy.key_alb[0], cy.last_alb, MaxKey(), (int32_t)0, (int)n1, c->stream));
+    uint8_t *tmp = nullptr;
+    if (dev_alloc(c, &tmp, bytes ? bytes : 1)) return 1;
+    e->d_scan_tmp = tmp; e->scan_tmp_bytes = bytes;
+    CK(cudaHostAlloc((void **)&e->h_flags, 2 * sizeof(int32_t), cudaHostAllocDefault));
+  }
   e->snow_ready = true;
+  return 0;
+}
+
+// One callSnowPack over a basin with canopy: probe rounds until the carried members are settled, then commit.
+static int snow_step_with_canopy(tribs_ctx *c, const EtStepDev &d, const SnowConst &sc) {
+  EtState *e = c->et;
+  SnowCarry &cy = e->carry;
+  const int n1 = c->n + 1, grid = (c->n_pad + 127) / 128;
+  auto scan = [&](const int32_t *key, int32_t *last) {
+    size_t bytes = e->scan_tmp_bytes;
+    return cub::DeviceScan::ExclusiveScan(e->d_scan_tmp, bytes, key, last, MaxKey(), (int32_t)0, n1, c->stream);
+  };
+  auto read_flags = [&]() {
+    CK(cudaMemcpyAsync(e->h_flags, cy.flags, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return 0;
+  };
+  CK(cudaMemsetAsync(cy.flags, 0, 2 * sizeof(int32_t), c->stream));
+  snow_probe_kernel<<<grid, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, cy, 0, 1, 0, c->n_pad);
+  c->launches++;
+  CK(scan(cy.key_alb[0], cy.last_alb));
+  if (read_flags()) return 1;
+  int buf = 0, rounds = 1;
+  if (e->h_flags[1] > 0) {
+    for (;;) {
+      if (rounds > c->n + 1) return fail("tribs_gpu_snow_step: the albedo carry-over did not settle");
+      const int rd = buf, wr = buf ^ 1;
+      CK(cudaMemsetAsync(cy.flags, 0, sizeof(int32_t), c->stream));
+      snow_probe_kernel<<<grid, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, cy, rounds, rd, wr, c->n_pad);
+      c->launches++;
+      rounds++;
+      if (read_flags()) return 1;
+      buf = wr;
+      if (!e->h_flags[0]) break;            // same answers as the round before: last_alb already belongs to them
+      CK(scan(cy.key_alb[buf], cy.last_alb));
+    }
+  }
+  e->last_probe_rounds = rounds;
+  CK(scan(cy.key_can[buf], cy.last_can));
+  snow_commit_kernel<<<grid, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, cy, buf, c->n_pad);
+  snow_members_kernel<<<1, 32, 0, c->stream>>>(cy, buf, c->n);
+  c->launches += 2;
+  CK(cudaGetLastError());
   return 0;
 }
 
@@ -1426,7 +1573,8 @@ extern "C" int tribs_gpu_snow_step(tribs_handle_t c, const tribs_et_step_t *s, i
   static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014, 0.995, 0.976, 0.976, 1.0,
                                      1.053, 1.167, 1.354, 1.637, 2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
   EtStepDev d{};
-  d.do_potential = 1; d.do_components = 1; d.intercept_flag = 0; d.met_time = 1;   // callSnowPack runs at met_hour only
+  d.do_potential = 1; d.do_components = 1; d.met_time = 1;   // callSnowPack runs at met_hour only
+  d.intercept_flag = e->k.i_option != 0;                      // tSimul.cpp:474 / 489
   d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
   d.cos_alpha = cos(asin(s->sinAlpha));
   d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
@@ -1436,8 +1584,12 @@ extern "C" int tribs_gpu_snow_step(tribs_handle_t c, const tribs_et_step_t *s, i
   d.cmp = d.pot;        // ComputeETComponents runs inside the same cell loop, before the met clock advances
   SnowConst sc = e->sc;
   sc.hourly = hourly_time_step;
-  snow_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, c->n_pad);
-  c->launches++;
+  if (e->k.i_option != 0) {
+    if (snow_step_with_canopy(c, d, sc)) return 1;
+  } else {
+    snow_cells_kernel<<<(c->n_pad + 127) / 128, 128, 0, c->stream>>>(e->k, e->st, d, sc, e->ev, e->snv, c->dv, c->n_pad);
+    c->launches++;
+  }
   e->gen++;
   CK(cudaGetLastError());
   return 0;
@@ -1454,6 +1606,22 @@ extern "C" int tribs_gpu_snow_sync(tribs_handle_t c, uint64_t mask, double *cons
     CK(cudaMemcpyAsync(host[k], c->d_stage, (size_t)c->n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CK(cudaStreamSynchronize(c->stream));
   }
+  return 0;
+}
+
+extern "C" int tribs_gpu_snow_members(tribs_handle_t c, double *members, int32_t *probe_rounds) {
+  if (!c) return fail("tribs_gpu_snow_members: null argument");
+  if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_members: call tribs_gpu_snow_init first");
+  EtState *e = c->et;
+  if (members) {
+    members[0] = e->members[0]; members[1] = e->members[1];
+    if (e->carry.members) {
+      CK(cudaSetDevice(c->device));
+      CK(cudaMemcpyAsync(members, e->carry.members, 2 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+      CK(cudaStreamSynchronize(c->stream));
+    }
+  }
+  if (probe_rounds) *probe_rounds = e->last_probe_rounds;
   return 0;
 }
 

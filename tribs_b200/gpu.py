@@ -132,7 +132,7 @@ EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retri
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
            "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
            "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
-           "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync",
+           "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync", "tribs_gpu_snow_members",
            "tribs_gpu_last_error", "tribs_gpu_abi_version"]
 
 _lib = None
@@ -176,6 +176,7 @@ def load():
     L.tribs_gpu_snow_init.argtypes = [H, C.POINTER(SnowParams)]
     L.tribs_gpu_snow_step.argtypes = [H, C.POINTER(EtStep), C.c_int32]
     L.tribs_gpu_snow_sync.argtypes = [H, C.c_uint64, C.POINTER(PD)]
+    L.tribs_gpu_snow_members.argtypes = [H, PD, C.POINTER(C.c_int32)]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -414,6 +415,12 @@ class GpuBasin:
         m = self._met(rec, cell_record, elev, keep)
         s.met_potential = C.pointer(m)
         _chk(self.L.tribs_gpu_snow_step(self.h, C.byref(s), int(hourly)))
+
+    def snow_members(self):
+        """(albedo, snCanWE) as the last swept cell left them, and the probe rounds of the last call."""
+        m, r = np.zeros(2), C.c_int32(0)
+        _chk(self.L.tribs_gpu_snow_members(self.h, _d(m), C.byref(r)))
+        return m, int(r.value)
 
     def snow_sync(self, names) -> dict:
         out = {nm: np.empty(self.n) for nm in names}
