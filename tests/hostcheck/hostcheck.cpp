@@ -82,6 +82,11 @@ void hc_sat(int n, double **sf, int32_t **si, double **ef, double **fields, cons
 
 double hc_lambert_w(double z) { return lambert_w(z); }
 
+// const_math.cuh (TRIBS_CONST_MATH): the same source the device compiles, IEEE operations only
+void hc_cm_exp(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = cm::exp_c(x[i]); }
+void hc_cm_log(const double *x, double *y, int n) { for (int i = 0; i < n; i++) y[i] = cm::log_c(x[i]); }
+void hc_cm_pow(const double *x, const double *e, double *y, int n) { for (int i = 0; i < n; i++) y[i] = cm::pow_c(x[i], e[i]); }
+
 // ---- kernel (1) and the snow pack: one call of the cell loop, cells in sweep order ----------------
 // ci: et_option i_option gflux_option shelter_option | cd: metstep_min etistep_h tlinke temp_lapse max_interstorm
 // est: z flow_slope aspect heat_cond heat_cap soil_cutoff root_cutoff thr bedrock varea

@@ -278,8 +278,13 @@ TRIBS_HD void intercept_gray(const LandClass &lc, const EtConst &k, double rainf
   c.NetPrecipitation = lc.V_raw * (rainfall - intercept) + (1 - lc.V_raw) * rainfall;
 }
 
+#if defined(__CUDA_ARCH__) && defined(TRIBS_CONST_MATH)
+#define TRIBS_ET_EXP(x) cm::exp_c(x)      // constant-bank coefficients, const_math.cuh
+#else
+#define TRIBS_ET_EXP(x) exp(x)
+#endif
 TRIBS_HD double rutter_rate(const LandClass &lc, double C, double R, double Ep) {
-  const double drain = lc.K * exp(lc.b * (C - lc.S));
+  const double drain = lc.K * TRIBS_ET_EXP(lc.b * (C - lc.S));
   return (C < lc.S) ? ((1 - lc.P) * R - (C / lc.S) * Ep - drain) : ((1 - lc.P) * R - Ep - drain);
 }
 

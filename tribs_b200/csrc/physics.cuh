@@ -18,6 +18,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include "const_math.cuh"
 
 #if defined(__CUDACC__)
 #define TRIBS_HD __host__ __device__ __forceinline__
@@ -37,6 +38,13 @@ namespace tribs {
 #else
 #define TRIBS_MATH inline
 #endif
+#if defined(__CUDA_ARCH__) && defined(TRIBS_CONST_MATH)
+// exp / log with their coefficients in the constant bank (const_math.cuh): fewer instructions in the
+// routines that carry most of the sweep's instruction stream; x^y as exp(y ln x) as below.
+TRIBS_MATH double m_exp(double x) { return cm::exp_c(x); }
+TRIBS_MATH double m_log(double x) { return cm::log_c(x); }
+TRIBS_MATH double m_pow(double x, double y) { return cm::pow_c(x, y); }
+#else
 TRIBS_MATH double m_exp(double x) { return exp(x); }
 TRIBS_MATH double m_log(double x) { return log(x); }
 #if defined(__CUDA_ARCH__) && defined(TRIBS_FAST_POW)
@@ -46,6 +54,7 @@ TRIBS_MATH double m_log(double x) { return log(x); }
 TRIBS_MATH double m_pow(double x, double y) { return (x > 0.0) ? exp(y * log(x)) : pow(x, y); }
 #else
 TRIBS_MATH double m_pow(double x, double y) { return pow(x, y); }
+#endif
 #endif
 TRIBS_MATH double m_expm1(double x) { return expm1(x); }
 
