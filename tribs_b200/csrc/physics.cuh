@@ -38,7 +38,8 @@ namespace tribs {
 #else
 #define TRIBS_MATH inline
 #endif
-#if defined(__CUDA_ARCH__) && defined(TRIBS_CONST_MATH)
+#if defined(TRIBS_CONST_MATH) && (defined(__CUDA_ARCH__) || defined(TRIBS_CONST_MATH_HOST))
+// (TRIBS_CONST_MATH_HOST: tests/exp_perturb.py runs the host build of these headers with the same routines)
 // exp / log with their coefficients in the constant bank (const_math.cuh): fewer instructions in the
 // routines that carry most of the sweep's instruction stream; x^y as exp(y ln x) as below.
 TRIBS_MATH double m_exp(double x) { return cm::exp_c(x); }
