@@ -32,3 +32,16 @@ def test_gpu_snow_pack_with_canopy_matches_live_reference(extra, built):
     assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0
     members, rounds = g.sim.dev.snow_members()
     assert 0.45 <= members[0] <= 0.88 and rounds >= 1
+
+
+def test_gpu_snow_golden_fixture(built):
+    """The committed snow fixture (tests/golden/snow.npz: winter met, Rutter canopy, 1 152 steps of the
+    reference with melt and rain on snow) through the device path."""
+    from refrun import load_golden
+    basin, snaps, _ = load_golden("snow")
+    snaps = {k: v for k, v in snaps.items() if not (k.endswith("_m_Uerror") or k.endswith("_m_CumUerror"))}
+    n_steps = int(snaps["n_steps"][0])
+    w = run_and_compare(GpuStepper(basin, schedule_for(basin)), snaps, n_steps, floor=ABS_FLOOR)
+    print("\n[snow golden] worst:\n" + w.report(8))
+    assert w.max() <= REL_TOL, w.report()
+    assert ("m", "IntSWE") in w.w and ("m", "IceWE") in w.w
