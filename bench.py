@@ -279,7 +279,7 @@ def run_gpu(args):
     if world == 1 and not args.no_et_kernel:
         line["kernels"] = {"et_cells_kernel": time_et_kernel(dev, basin, n, stream, peak)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample()
+        line["cpu_baseline"] = cpu_baseline_sample(side)
     if rank == 0:
         print(json.dumps(line))
     dev.close()
@@ -377,8 +377,39 @@ def _run_reference_sample(n_side: int, hours: float, procs: int = 1):
     return rate, cells, steps, wall
 
 
-def cpu_baseline_sample():
+def _reference_on_bench_basin(side: int, steps: int):
+    """The unmodified serial reference on the GPU arm's own basin: build_basin(side, side, seed=1) is
+    written as OPTMESHINPUT 9 files (tribs_b200/meshb.py), which the reference reads without its
+    super-linear mesh / flow-network set-up, and runs the first `steps` steps of the storm."""
+    import shutil
+    import tempfile
+    from refrun import HARNESS, write_meshb_deck
+    d = tempfile.mkdtemp(prefix="tribsbench_")
+    t0 = time.perf_counter()
+    try:
+        write_meshb_deck(side, d, seed=1, runtime_h=24.0)
+        r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", "--max-steps", str(steps)], cwd=d,
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
+        for ln in r.stdout.splitlines():
+            if ln.startswith("ref_timing"):
+                j = json.loads(ln[len("ref_timing "):])
+                return j["cell_steps_per_s"], j["cells"], j["steps"], j.get("setup_s", 0.0), time.perf_counter() - t0
+    except (OSError, subprocess.SubprocessError):
+        pass
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    return None
+
+
+def cpu_baseline_sample(side: int = 1000):
     if _harness():
+        got = _reference_on_bench_basin(side, 8)
+        if got:
+            rate, cells, steps, setup_s, wall = got
+            return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
+                    "sample": f"unmodified serial reference (g++ -O2) on the GPU arm's own basin ({cells} cells, read as "
+                              f"OPTMESHINPUT 9 files), the first {steps} steps of the storm, simulation_loop only; "
+                              f"{wall:.0f} s wall incl. writing the deck and {setup_s:.0f} s of reference set-up"}
         rate, cells, steps, wall = _run_reference_sample(120, 12.0, 1)
         return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
                 "sample": f"unmodified serial reference (g++ -O2), {cells}-cell V-valley of the same generator, "

@@ -672,6 +672,56 @@ struct Harness {
     }
 };
 
+// ---------------------------------------------------------------------------------
+// --dump-meshb DIR: the mesh and flow network the reference has just built, in the OPTMESHINPUT 9
+// ("MeshBuilder") binary formats its own readers define (tMesh::MakeMeshFromMeshBuilder,
+// tMesh.cpp:1076-1306; tFlowNet::ReadFlowNetFromMeshBuilder, tFlowNet.cpp:117-175). Used to check
+// tribs_b200/meshb.py (which writes the same files for the large synthetic basins) against the
+// reference: a deck re-run with OPTMESHINPUT 9 on these files must reproduce the run bit for bit.
+template <class T> static void bput(ofstream &f, T v) { f.write((const char *)&v, sizeof(T)); }
+
+static void dump_meshb(const string &dir, tMesh<tCNode> &mesh, tKinemat &flow) {
+    ofstream nf(dir + "/nodes.meshb", ios::binary), ef(dir + "/edges.meshb", ios::binary), ff(dir + "/flow.meshb", ios::binary);
+    tMeshListIter<tCNode> ni(mesh.getNodeList());
+    bput<int>(nf, mesh.getNodeList()->getSize());
+    for (tCNode *c = ni.FirstP(); !ni.AtEnd(); c = ni.NextP()) {
+        bput<int>(nf, c->getID()); bput<int>(nf, c->getBoundaryFlag());
+        bput<double>(nf, c->getX()); bput<double>(nf, c->getY()); bput<double>(nf, c->getZ()); bput<double>(nf, c->getVArea());
+        bput<int>(nf, c->getEdg()->getID()); bput<int>(nf, c->getFloodStatus()); bput<int>(nf, c->getTracer());
+        bput<double>(nf, c->getHillPath()); bput<double>(nf, c->getTTime());
+        bput<double>(nf, c->getSrf()); bput<double>(nf, c->getHsrf()); bput<double>(nf, c->getPsrf());
+        bput<double>(nf, c->getSatsrf()); bput<double>(nf, c->getSbsrf()); bput<double>(nf, c->getEvapoTrans());
+        bput<double>(nf, c->getSoilMoistureSC()); bput<double>(nf, c->getSoilMoistureUNSC()); bput<double>(nf, c->getRootMoistureSC());
+        bput<double>(nf, c->getContrArea()); bput<double>(nf, c->getNwtNew()); bput<double>(nf, c->getRain());
+        bput<double>(nf, c->getCurvature()); bput<double>(nf, c->getStreamPath());
+        bput<int>(nf, c->getReach());
+        bput<int>(nf, c->getFlowEdg() ? c->getFlowEdg()->getID() : -1);
+        bput<int>(nf, c->getStreamNode() ? c->getStreamNode()->getID() : -1);
+    }
+    tMeshListIter<tEdge> ei(mesh.getEdgeList());
+    bput<int>(ef, mesh.getEdgeList()->getSize());
+    for (tEdge *e = ei.FirstP(); !ei.AtEnd(); e = ei.NextP()) {
+        tArray<double> rv = e->getRVtx();
+        bput<int>(ef, e->getID()); bput<double>(ef, rv[0]); bput<double>(ef, rv[1]);
+        bput<double>(ef, e->getLength()); bput<double>(ef, e->getSlope()); bput<double>(ef, e->getVEdgLen());
+        bput<int>(ef, e->getOriginPtrNC()->getID()); bput<int>(ef, e->getDestinationPtrNC()->getID());
+        bput<int>(ef, e->getCCWEdg()->getID());
+    }
+    bput<double>(ff, flow.hillvel); bput<double>(ff, flow.streamvel); bput<double>(ff, flow.velratio); bput<double>(ff, flow.velcoef);
+    bput<double>(ff, flow.flowexp); bput<double>(ff, flow.baseflow); bput<double>(ff, flow.flowout); bput<double>(ff, flow.maxttime);
+    bput<double>(ff, flow.dist_hill_max); bput<double>(ff, flow.dist_stream_max); bput<double>(ff, flow.BasArea);
+    bput<int>(ff, flow.OutletNode->getID());
+    tPtrList<tCNode> *lists[3] = {&flow.HeadsLst, &flow.NodesLstH, &flow.NodesLstO};
+    for (auto *L : lists) {
+        tPtrListIter<tCNode> it(*L);
+        bput<int>(ff, L->getSize());
+        for (tCNode *c = it.FirstP(); !it.AtEnd(); c = it.NextP()) bput<int>(ff, c->getID());
+    }
+    tListIter<int> ci(flow.NNodes);
+    bput<int>(ff, flow.NNodes.getSize());
+    for (int *v = ci.FirstP(); !ci.AtEnd(); v = ci.NextP()) bput<int>(ff, *v);
+}
+
 static double now_s() {
     using namespace std::chrono;
     return duration<double>(steady_clock::now().time_since_epoch()).count();
@@ -683,6 +733,8 @@ int main(int argc, char **argv) {
     int snap_from = 1, snap_to = 0, snap_every = 1;
     string phases = "ugre";
     bool do_kat = false, do_basin = true;
+    int max_steps = 0;   // --max-steps N: leave the loop after N steps (RUNTIME still sizes the hydrograph arrays)
+    string meshb_dir; // --dump-meshb <dir>: write the OPTMESHINPUT 9 files of the mesh / flow network just built
     string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
     double inject_evap = 0.0;   // --inject-evap R: soil evaporation R mm/h on dry steps (see below)
     vector<char*> rargs;
@@ -697,6 +749,8 @@ int main(int argc, char **argv) {
         else if (a == "--gpu" && i + 1 < argc) gpu_lib = argv[++i];
         else if (a == "--inject-evap" && i + 1 < argc) inject_evap = atof(argv[++i]);
         else if (a == "--no-basin") do_basin = false;
+        else if (a == "--dump-meshb" && i + 1 < argc) meshb_dir = argv[++i];
+        else if (a == "--max-steps" && i + 1 < argc) max_steps = atoi(argv[++i]);
         else rargs.push_back(argv[i]);
     }
     int rargc = (int)rargs.size();
@@ -709,6 +763,7 @@ int main(int argc, char **argv) {
     tRunTimer Timer(InputFile);
     tMesh<tCNode> BasinMesh(&SimCtrl, InputFile);
     tKinemat Flow(&SimCtrl, &BasinMesh, InputFile, &Timer);
+    if (!meshb_dir.empty()) dump_meshb(meshb_dir, BasinMesh, Flow);
     tResample RsmplMaster(&SimCtrl, &BasinMesh);
     tShelter Shelter(&SimCtrl, &BasinMesh, InputFile);
     tCOutput<tCNode> Output(&SimCtrl, &BasinMesh, InputFile, &RsmplMaster, &Timer);
@@ -751,7 +806,7 @@ int main(int argc, char **argv) {
     int step = 0;
     double t_loop = 0.0, t_unsat = 0.0, t_sat = 0.0, t_route = 0.0, t_rest = 0.0;
     vector<int32_t> snap_steps;
-    while (!Timer.IsFinished()) {
+    while (!Timer.IsFinished() && !(max_steps > 0 && step >= max_steps)) {
         step++;
         bool snap = sw && step >= snap_from && step <= snap_to && ((step - snap_from) % snap_every == 0);
         char pre[64];

@@ -82,6 +82,24 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
     return basin, snaps, timing, katd
 
 
+def write_meshb_deck(side: int, workdir: str, seed: int = 1, runtime_h: float = 24.0):
+    """A deck the reference can run at any size: synthbasin.build_basin(side, side) written as
+    OPTMESHINPUT 9 files (no mesh construction, no flow-network set-up in the reference), the initial
+    water table per Voronoi cell (OPTGWFILE 1, tHydroModel.cpp:249-269; the coarse gw.asc grid would
+    make tResample intersect it with every cell polygon). Returns build_basin's dict."""
+    from tribs_b200.synthbasin import build_basin
+    write_basin(spec_for("deep", side + 2, runtime_h=runtime_h, seed=seed), workdir)   # .in, soil / land grids
+    basin = build_basin(side, side, seed=seed, runtime_h=runtime_h, mesh_dir=workdir)
+    inp = os.path.join(workdir, "basin.in")
+    txt = re.sub(r"(OPTMESHINPUT:\s*\n)\s*\d+", r"\g<1>9", open(inp).read())
+    txt = re.sub(r"(OPTGWFILE:\s*\n)\s*\d+", r"\g<1>1", txt)
+    txt = re.sub(r"(GWATERFILE:\s*\n)\s*\S+", r"\g<1>gw.vor", txt)
+    open(inp, "w").write(txt)
+    with open(os.path.join(workdir, "gw.vor"), "w") as f:
+        f.write("".join(f"{i} {v!r}\n" for i, v in enumerate(np.asarray(basin["init_NwtOld"]).tolist())))
+    return basin
+
+
 def storm_of(basin):
     return float(basin["_spec_pmean"][0]), float(basin["_spec_stdur"][0]), float(basin["_spec_istdur"][0])
 

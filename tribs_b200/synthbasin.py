@@ -35,10 +35,11 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
                 gw_depth_mm: float = 3000.0, bedrock_mm: float = 15000.0,
                 soil=(10.0, 0.45, 0.05, 0.4, -200.0, 0.001, 100.0, 100.0),
                 tstep_h: float = 0.0625, gwstep_h: float = 0.5, runtime_h: float = 48.0,
-                n_soil_classes: int = 1) -> dict:
+                n_soil_classes: int = 1, mesh_dir: str | None = None) -> dict:
     """nx x ny active cells. One stream column along the valley axis (plus, with
     stream_every=k>0, a tributary stream row every k rows draining to it). Returns the
-    flattened-basin dict in sweep order."""
+    flattened-basin dict in sweep order. With mesh_dir, the same basin is also written there as the
+    reference's OPTMESHINPUT 9 files (meshb.py), so the reference itself can run it."""
     rng = np.random.default_rng(seed)
     # node grid with a one-node closed-boundary ring: indices 0..nx+1, 0..ny+1
     NX, NY = nx + 2, ny + 2
@@ -205,7 +206,44 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         jn2 = np.clip(Jn + dj[k], 0, NY - 1); in2 = np.clip(In + di[k], 0, NX - 1)
         slen_in[:, k] = elen[k3][jn2, in2]
         svl_in[:, k] = vedg[k3][jn2, in2]
-    listpos = np.arange(6 * n, dtype=np.int32)
+    # directed-edge ids and the order of the reference's edge list (tMesh::MakeMeshFromMeshBuilder keeps
+    # file order, complementary edges adjacent): a pair belongs to its endpoint with the lower node id
+    # (active cells: sweep position; then the outlet; then the closed ring), pairs are written owner by
+    # owner, spoke by spoke; edges with a closed end, or between two open ends, are inactive
+    gid = np.full(NX * NY, -1, np.int64)                  # node id per grid position
+    gid[flat_int[order]] = np.arange(n)
+    out_flat = outlet_ij[0] * NX + outlet_ij[1]
+    gid[out_flat] = n
+    ring = np.flatnonzero(gid < 0)
+    gid[ring] = n + 1 + np.arange(ring.size)
+    gI, gJ = ii.ravel(), jj.ravel()
+    g_of_id = np.empty(NX * NY, np.int64)
+    g_of_id[gid] = np.arange(NX * NY)
+    exists = np.stack([(gI + di[k] >= 0) & (gI + di[k] < NX) & (gJ + dj[k] >= 0) & (gJ + dj[k] < NY) for k in range(6)], 1)
+    nb_flat = np.stack([np.clip(gJ + dj[k], 0, NY - 1) * NX + np.clip(gI + di[k], 0, NX - 1) for k in range(6)], 1)
+    nb_id = np.where(exists, gid[nb_flat], -1)
+    owned = exists & (gid[:, None] < nb_id)                # [grid, k]
+    own_g = g_of_id[:, None].repeat(6, 1)                  # rows in id order
+    owned_by_id = owned[g_of_id]                           # [id, k]
+    pair_rank = np.cumsum(owned_by_id.ravel()) - 1         # file index of the pair, for owned (id, k)
+    eid = np.full((NX * NY, 6), -1, np.int64)              # directed edge id per (grid, k)
+    oid, ok_ = np.nonzero(owned_by_id)
+    og = g_of_id[oid]
+    pr = pair_rank.reshape(-1, 6)[oid, ok_]
+    eid[og, ok_] = 2 * pr
+    eid[nb_flat[og, ok_], (ok_ + 3) % 6] = 2 * pr + 1
+    closed = np.ones(NX * NY, bool)
+    closed[flat_int] = False
+    closed[out_flat] = False
+    is_open = np.zeros(NX * NY, bool)
+    is_open[out_flat] = True
+    pair_active = ~closed[og] & ~closed[nb_flat[og, ok_]] & ~(is_open[og] & is_open[nb_flat[og, ok_]])
+    act_rank = np.cumsum(pair_active) - 1
+    epos = np.full(2 * pr.size, -1, np.int64)              # position in the active edge list per edge id
+    epos[2 * pr[pair_active]] = 2 * act_rank[pair_active]
+    epos[2 * pr[pair_active] + 1] = 2 * act_rank[pair_active] + 1
+    cell_g = flat_int[order]                               # grid position of every active cell, sweep order
+    listpos = epos[eid[cell_g]].ravel().astype(np.int32)
 
     kbo = kb[order]
     flow_slope = best_slope.ravel()[flat_int][order]
@@ -234,7 +272,7 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     mi0 = thr * (nwt0 + psib) - ths * psib - dth / (lam_a - 1.0) * (psib + nwt0 * np.power(psib_abs / nwt0, lam_a))
     basin = {
         "n_active": np.array([n], np.int32), "n_nodes_total": np.array([NX * NY], np.int32),
-        "n_active_edges": np.array([6 * n], np.int32),
+        "n_active_edges": np.array([2 * int(pair_active.sum())], np.int32),
         "id": np.arange(n, dtype=np.int32),
         "boundary": np.where(is_stream[order], 3, 0).astype(np.int32),
         "x": take(x), "y": take(y), "z": take(z), "varea": varea, "bedrock": full(bedrock_mm),
@@ -262,6 +300,67 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         "init_NwtOld": nwt0, "init_NwtNew": nwt0.copy(), "init_MuOld": mi0, "init_MuNew": mi0.copy(),
         "init_MiOld": mi0.copy(), "init_MiNew": mi0.copy(),
     }
+    if mesh_dir is not None:
+        from .meshb import EDGE_DTYPE, NODE_DTYPE, write_meshb
+        G = NX * NY
+        nodes = np.zeros(G, NODE_DTYPE)                    # rows in id order = file order
+        g = g_of_id
+        act = np.arange(G) < n
+        nodes["id"] = np.arange(G)
+        nodes["boundary"] = np.where(act, np.where(np.arange(G) < n, np.append(basin["boundary"], np.zeros(G - n, np.int32)), 0), 1)
+        nodes["boundary"][n] = 2
+        nodes["x"], nodes["y"], nodes["z"] = x.ravel()[g], y.ravel()[g], z.ravel()[g]
+        nodes["varea"][:n] = varea
+        first_k = np.argmax(exists[g], axis=1)
+        nodes["first_edge"] = eid[g, first_k]
+        nodes["tracer"] = (np.arange(G) <= n).astype(np.int32)
+        nodes["hillpath"][:n], nodes["traveltime"][:n], nodes["streampath"][:n] = hp, ttime, sp
+        nodes["contr_area"][:n] = contr
+        nodes["contr_area"][n] = bas_area
+        nodes["reach"] = np.where(np.arange(G) <= n, 0, -1)
+        nodes["flow_edge"] = -1
+        nodes["flow_edge"][:n] = eid[cell_g, kbo]
+        nodes["stream_node"] = -1
+        sn = basin["stream_node"]
+        nodes["stream_node"][:n] = np.where(basin["boundary"] == 3, -1, sn)
+        ne = 2 * pr.size
+        edges = np.zeros(ne, EDGE_DTYPE)
+        edges["id"] = np.arange(ne)
+        ccx_a, ccy_a = np.stack([c.ravel() for c in ccx], 1), np.stack([c.ravel() for c in ccy], 1)
+        elen_a, vedg_a = np.stack([e.ravel() for e in elen], 1), np.stack([v.ravel() for v in vedg], 1)
+        zf, xf, yf = z.ravel(), x.ravel(), y.ravel()
+        for side in (0, 1):                                # the owner's edge, then its complement
+            og_s = og if side == 0 else nb_flat[og, ok_]
+            k_s = ok_ if side == 0 else (ok_ + 3) % 6
+            dg_s = nb_flat[og_s, k_s]
+            e = edges[side::2]
+            inner = ~closed[og_s] | is_open[og_s]
+            mx, my = 0.5 * (xf[og_s] + xf[dg_s]), 0.5 * (yf[og_s] + yf[dg_s])
+            with np.errstate(all="ignore"):
+                rvx, rvy = ccx_a[og_s, (k_s - 1) % 6], ccy_a[og_s, (k_s - 1) % 6]
+                ve = vedg_a[og_s, k_s]
+            okv = inner & np.isfinite(rvx) & np.isfinite(rvy) & ~is_open[og_s]
+            e["rvx"], e["rvy"] = np.where(okv, rvx, mx), np.where(okv, rvy, my)
+            ln = np.hypot(xf[dg_s] - xf[og_s], yf[dg_s] - yf[og_s])
+            ln = np.where(~closed[og_s] & ~is_open[og_s], elen_a[og_s, k_s], ln)
+            e["length"] = ln
+            e["slope"] = (zf[og_s] - zf[dg_s]) / ln
+            e["vedglen"] = np.where(np.isfinite(ve), ve, 0.0)
+            e["orig"], e["dest"] = gid[og_s], gid[dg_s]
+            nk = (k_s + 1) % 6                             # next existing spoke counter-clockwise
+            for _ in range(5):
+                miss = ~exists[og_s, nk]
+                if not miss.any():
+                    break
+                nk = np.where(miss, (nk + 1) % 6, nk)
+            e["ccw"] = eid[og_s, nk]
+            edges[side::2] = e
+        heads = np.flatnonzero((basin["boundary"] == 3) & ~np.isin(np.arange(n), fdest[basin["boundary"] == 3]))
+        flow = dict(hillvel=hillvel, streamvel=streamvel, velratio=velratio, velcoef=velcoef, flowexp=0.0, baseflow=0.01,
+                    flowout=0.01, maxttime=maxtt, dist_hill_max=float(hp.max()), dist_stream_max=float(sp.max()),
+                    BasArea=bas_area, outlet=n, heads=heads, reach_heads=heads[:1], reach_outlets=[n],
+                    reach_sizes=[int((basin["boundary"] == 3).sum()) + 1])
+        write_meshb(mesh_dir, nodes, edges, flow)
     return basin
 
 
