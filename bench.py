@@ -434,20 +434,50 @@ def run_reference_arm(args):
     cores = os.cpu_count() or 1
     total = args.steps + args.warmup
     if _harness():
+        # One unmodified serial reference process per host core (no MPI toolchain on the box: the optimistic
+        # all-core bound), each on a basin of the GPU arm's generator read as OPTMESHINPUT 9 files. A "step" is one
+        # simulated TIMESTEP of all processes together; the first `warmup` steps are left out of the timing
+        # (--time-from). The basin side is bounded so that the run ends within a few minutes.
+        import shutil
+        import tempfile
+        from refrun import HARNESS, write_meshb_deck
         procs = max(1, min(cores, 32))
-        # size the sample so the whole run stays within a few minutes: ~150 s / total per step
-        budget = max(0.6, 150.0 / total)
-        n_side = int(max(24, min(100, math.sqrt(0.25e6 * budget / 192.0) + 2)))
-        vals = []
-        for k in range(total):
-            rate, cells, steps, wall = _run_reference_sample(n_side, 12.0, procs)
-            if k >= args.warmup:
-                vals.append((rate, wall))
-        value = statistics.mean(v[0] for v in vals)
-        ms = statistics.mean(v[1] for v in vals) * 1e3
-        kind = "reference"
+        try:
+            avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
+        except (ValueError, OSError):
+            avail_gb = 64.0
+        side = int(min(args.side, math.sqrt(150.0 * 0.3e6 / total), math.sqrt(0.5 * avail_gb / procs / 6e-6)))
+        side = max(side, 64)
+        base = tempfile.mkdtemp(prefix="tribsbench_ref_")
+        src = os.path.join(base, "deck")
+        os.makedirs(src)
+        write_meshb_deck(side, src, seed=1, runtime_h=24.0)
+        dirs = []
+        for k in range(procs):
+            d = os.path.join(base, f"p{k}")
+            shutil.copytree(src, d)
+            dirs.append(d)
+        t0 = time.perf_counter()
+        ps = [subprocess.Popen([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", "--max-steps", str(total),
+                                "--time-from", str(args.warmup)], cwd=d, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+              for d in dirs]
+        rate, loop_s, cells, steps = 0.0, 0.0, 0, 0
+        for p in ps:
+            for ln in p.communicate()[0].splitlines():
+                if ln.startswith("ref_timing"):
+                    j = json.loads(ln[len("ref_timing "):])
+                    rate += j["cell_steps_per_s"]
+                    loop_s = max(loop_s, j["loop_s"])
+                    cells, steps = j["cells"], j["steps"]
+        wall = time.perf_counter() - t0
+        shutil.rmtree(base, ignore_errors=True)
+        if steps != args.steps:
+            raise SystemExit("bench.py --impl reference: a reference process did not finish")
+        value, ms, kind = rate, loop_s / steps * 1e3, "reference"
         sample = (f"{procs} concurrent processes of the unmodified serial reference (no MPI toolchain on the box, so "
-                  f"this is the optimistic all-core bound), each a {cells}-cell V-valley deck, {steps} steps")
+                  f"this is the optimistic all-core bound), each on a {cells}-cell basin of the GPU arm's generator read "
+                  f"as OPTMESHINPUT 9 files; {args.warmup} warm-up + {steps} timed simulation steps of the storm, "
+                  f"simulation_loop only; {wall:.0f} s wall incl. set-up")
     else:
         from oracle.pyoracle import OracleModel
         from tribs_b200.synthbasin import build_basin

@@ -734,6 +734,7 @@ int main(int argc, char **argv) {
     string phases = "ugre";
     bool do_kat = false, do_basin = true;
     int max_steps = 0;   // --max-steps N: leave the loop after N steps (RUNTIME still sizes the hydrograph arrays)
+    int time_from = 0;   // --time-from W: the first W steps are warm-up, left out of the timing line
     string meshb_dir; // --dump-meshb <dir>: write the OPTMESHINPUT 9 files of the mesh / flow network just built
     string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
     double inject_evap = 0.0;   // --inject-evap R: soil evaporation R mm/h on dry steps (see below)
@@ -751,6 +752,7 @@ int main(int argc, char **argv) {
         else if (a == "--no-basin") do_basin = false;
         else if (a == "--dump-meshb" && i + 1 < argc) meshb_dir = argv[++i];
         else if (a == "--max-steps" && i + 1 < argc) max_steps = atoi(argv[++i]);
+        else if (a == "--time-from" && i + 1 < argc) time_from = atoi(argv[++i]);
         else rargs.push_back(argv[i]);
     }
     int rargc = (int)rargs.size();
@@ -797,6 +799,8 @@ int main(int argc, char **argv) {
     if (use_gpu) gpu.attach(&BasinMesh, &Flow, &Moisture, &Timer, gpu_lib.c_str());
     const bool gpu_et = use_gpu && EvapoTrans.getEToption() != 0 && SnowPack.getSnowOpt() == 0;
     if (gpu_et) gpu.attachET(&EvapoTrans, &Intercept, &Moisture);
+    const bool gpu_snow = use_gpu && EvapoTrans.getEToption() != 0 && SnowPack.getSnowOpt() != 0;
+    if (gpu_snow) gpu.attachSnow(&SnowPack, &Intercept, &Moisture);
     vector<double> qout_series;
 
     std::unique_ptr<TrbWriter> sw;
@@ -819,6 +823,10 @@ int main(int argc, char **argv) {
             if (Timer.getCurrentTime() == Sim.eti_hour) gpu.callEvapoTrans(Intercept.getIoption() != 0);
             gpu.flushET();
             if (snap && phases.find('m') != string::npos) gpu.syncEtToNodes();
+        } else if (gpu_snow) {   // the snow branch of SurfaceHydroProcesses (tSimul.cpp:464-492), cell loop on the GPU
+            Sim.get_next_met();
+            if (Timer.getCurrentTime() == Sim.met_hour) gpu.callSnowPack(Intercept.getIoption() != 0);
+            if (snap && phases.find('m') != string::npos) gpu.syncSnowToNodes();
         } else
             Sim.SurfaceHydroProcesses(&EvapoTrans, &Intercept, &SnowPack);
         if (inject_evap > 0.0)
@@ -873,13 +881,16 @@ int main(int argc, char **argv) {
             snprintf(pre, sizeof pre, "s%d_e_", step); H.dump_state(*sw, pre, true);
         }
         if (snap) snap_steps.push_back(step);
-        t_rest += (t1 - t0) + (t5 - t4b);
-        t_unsat += t2 - t1; t_sat += t3 - t2b; t_route += t4 - t3b;
-        t_loop += (t1 - t0) + (t2 - t1) + (t3 - t2b) + (t4 - t3b) + (t5 - t4b);
+        if (step > time_from) {
+            t_rest += (t1 - t0) + (t5 - t4b);
+            t_unsat += t2 - t1; t_sat += t3 - t2b; t_route += t4 - t3b;
+            t_loop += (t1 - t0) + (t2 - t1) + (t3 - t2b) + (t4 - t3b) + (t5 - t4b);
+        }
     }
     if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
     {   // outlet hydrograph of the channel router (tKinemat::Qout), one value per step
         if (gpu_et) gpu.syncEtToNodes();
+        if (gpu_snow) gpu.syncSnowToNodes();
         TrbWriter qw(outdir + (use_gpu ? "/qout_gpu.trb" : "/qout_ref.trb"));
         if (EvapoTrans.getEToption() != 0) {
             qw.f64("PotEvap", H.col([](tCNode *c) { return c->getPotEvap(); }));
@@ -887,6 +898,15 @@ int main(int argc, char **argv) {
             qw.f64("CanStorage", H.col([](tCNode *c) { return c->getCanStorage(); }));
             qw.f64("CumTotEvap", H.col([](tCNode *c) { return c->getCumTotEvap(); }));
             qw.f64("CumIntercept", H.col([](tCNode *c) { return c->getCumIntercept(); }));
+        }
+        if (SnowPack.getSnowOpt() != 0) {
+            qw.f64("IceWE", H.col([](tCNode *c) { return c->getIceWE(); }));
+            qw.f64("LiqWE", H.col([](tCNode *c) { return c->getLiqWE(); }));
+            qw.f64("IntSWE", H.col([](tCNode *c) { return c->getIntSWE(); }));
+            qw.f64("SnTempC", H.col([](tCNode *c) { return c->getSnTempC(); }));
+            qw.f64("CumMelt", H.col([](tCNode *c) { return c->getCumMelt(); }));
+            qw.f64("CumIntSub", H.col([](tCNode *c) { return c->getCumIntSub(); }));
+            qw.f64("PeakSWE", H.col([](tCNode *c) { return c->getPeakSWE(); }));
         }
         qw.f64("qout", qout_series);
         qw.f64("NwtNew", H.col([](tCNode *c) { return c->getNwtNew(); }));
@@ -900,8 +920,8 @@ int main(int argc, char **argv) {
     printf("\nref_timing {\"cells\": %ld, \"steps\": %d, \"setup_s\": %.6f, \"loop_s\": %.6f, "
            "\"unsat_s\": %.6f, \"sat_s\": %.6f, \"route_s\": %.6f, \"other_s\": %.6f, "
            "\"cell_steps_per_s\": %.6e}\n",
-           ncell, step, t_setup1 - t_setup0, t_loop, t_unsat, t_sat, t_route, t_rest,
-           t_loop > 0 ? (double)ncell * step / t_loop : 0.0);
+           ncell, step - time_from, t_setup1 - t_setup0, t_loop, t_unsat, t_sat, t_route, t_rest,
+           t_loop > 0 ? (double)ncell * (step - time_from) / t_loop : 0.0);
     fflush(stdout);
     return 0;
 }

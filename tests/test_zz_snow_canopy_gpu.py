@@ -45,3 +45,30 @@ def test_gpu_snow_golden_fixture(built):
     print("\n[snow golden] worst:\n" + w.report(8))
     assert w.max() <= REL_TOL, w.report()
     assert ("m", "IntSWE") in w.w and ("m", "IceWE") in w.w
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+def test_reference_simulator_drives_gpu_snow_path(built):
+    """The drop-in boundary for OPTSNOW 1: the reference's own objects and time loop
+    (tribs_ref_harness --gpu) call TribsGpuBinding::callSnowPack (tribs_b200/host/tribs_ref_binding.h)
+    where Simulator::SurfaceHydroProcesses calls tSnowPack::callSnowPack; pack, canopy snow and the
+    water balance underneath must end where the pure reference run ends."""
+    import os
+    import subprocess
+    import tempfile
+    from refrun import HARNESS, ROOT
+    from tribs_b200.synth import write_basin
+    from tribs_b200.trb import read_trb
+    d = tempfile.mkdtemp(prefix="tribshyb_snow_")
+    write_basin(spec_for("snow", 16, runtime_h=72.0, seed=4, pmean=8.0), d)
+    lib = os.path.join(ROOT, "tribs_b200", "libtribs_gpu.so")
+    for extra in ([], ["--gpu", lib]):
+        r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", *extra], cwd=d, capture_output=True,
+                           text=True, timeout=1200)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    ref, got = read_trb(os.path.join(d, "qout_ref.trb")), read_trb(os.path.join(d, "qout_gpu.trb"))
+    assert ref["IceWE"].max() > 0 and np.abs(ref["CumIntSub"]).max() > 0
+    for f, floor in (("NwtNew", 1e-6), ("MuNew", 1e-6), ("NfNew", 1e-6), ("IceWE", 1e-6), ("LiqWE", 1e-6), ("IntSWE", 1e-6),
+                     ("SnTempC", 1.0), ("CumMelt", 1e-6), ("CumIntSub", 1e-6), ("PeakSWE", 1e-6), ("SurfTemp", 1.0)):
+        err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), floor)
+        assert err.max() <= REL_TOL, (f, float(err.max()))

@@ -264,7 +264,7 @@ struct TribsGpuBinding {
     es.hour = et->currentTime[3]; es.dew_hum_flag = et->dewHumFlag; es.ts_option = et->tsOption;
   }
 
-  // tEvapoTrans::callEvapoPotential()
+  // tEvapoTrans::callEvapoPotential() (also the head and tail of tSnowPack::callSnowPack, tSnowPack.cpp:249-285, 731-733)
   void callEvapoPotential() {
     et->SetEnvironment();                                  // calendar + sun geometry, once per call
     const int n = (int)cells.size(), t = et->hourlyTimeStep;
@@ -343,6 +343,71 @@ struct TribsGpuBinding {
       c->setStormLength(0, 0.0); c->setStormLength(1, E[TRIBS_ET_StormLength][i]);
       c->setEvapSoil(stage[TRIBS_F_EvapSoil][i]); c->setEvapDryCanopy(stage[TRIBS_F_EvapDryCanopy][i]);
       c->setNetPrecipitation(stage[TRIBS_F_NetPrecipitation][i]);
+    }
+  }
+  // ------------------------------------------------------------------ snow pack (OPTSNOW 1)
+  // tSnowPack derives from tEvapoTrans; under OPTSNOW the simulator calls SnowPack->callSnowPack(Intercept, flag)
+  // at every met hour instead of the two ET sweeps (tSimul.cpp:464-492). attachSnow() = attachET() on that object
+  // + tribs_gpu_snow_init; callSnowPack() = the call's host part (SetEnvironment, the hour's station records,
+  // the record-0 decisions, the clocks) + one tribs_gpu_snow_step for the cell loop (tSnowPack.cpp:286-725).
+  tSnowPack *snow = nullptr;
+  decltype(&tribs_gpu_snow_init) p_snow_init = nullptr;
+  decltype(&tribs_gpu_snow_step) p_snow_step = nullptr;
+  decltype(&tribs_gpu_snow_sync) p_snow_sync = nullptr;
+  std::vector<std::vector<double>> snow_stage;
+
+  void attachSnow(tSnowPack *sp, tIntercept *ic, tHydroModel *hydro) {
+    snow = sp;
+    attachET(sp, ic, hydro);                               // the tEvapoTrans members of the tSnowPack object
+    p_snow_init = (decltype(p_snow_init))dlsym(lib, "tribs_gpu_snow_init");
+    p_snow_step = (decltype(p_snow_step))dlsym(lib, "tribs_gpu_snow_step");
+    p_snow_sync = (decltype(p_snow_sync))dlsym(lib, "tribs_gpu_snow_sync");
+    if (!p_snow_init || !p_snow_step || !p_snow_sync) die("dlsym (snow)");
+    tribs_snow_params_t P{};
+    P.min_sn_temp = sp->minSnTemp; P.snliqfrac = sp->snliqfrac; P.hill_albedo_option = sp->hillAlbedoOption;
+    if (p_snow_init(h, &P)) die("tribs_gpu_snow_init");
+    snow_stage.assign(TRIBS_N_SNOW_FIELDS, std::vector<double>(cells.size(), 0.0));
+  }
+  // tSnowPack::callSnowPack(tIntercept*, int flag); flag = (Ioption != 0), which the library knows from et_init
+  void callSnowPack(int) {
+    const int t = et->hourlyTimeStep;                      // tEvapoTrans::hourlyTimeStep of this call
+    callEvapoPotential();                                  // fills `es` (do_potential, met record, clocks) and advances them
+    es.te_eti = (double)timer->getElapsedETISteps(timer->getCurrentTime());
+    if (p_snow_step(h, &es, t)) die("tribs_gpu_snow_step");
+    es = tribs_et_step_t{};
+  }
+  void syncSnowToNodes() {
+    syncEtToNodes();
+    std::vector<double *> ptr(TRIBS_N_SNOW_FIELDS);
+    for (int f = 0; f < TRIBS_N_SNOW_FIELDS; f++) ptr[f] = snow_stage[f].data();
+    if (p_snow_sync(h, ~0ull, ptr.data())) die("tribs_gpu_snow_sync");
+    const int mf[] = {TRIBS_F_LiqWE, TRIBS_F_IceWE, TRIBS_F_LiqRouted};
+    tribs_state_t S{};
+    uint64_t mask = 0;
+    for (int f : mf) { S.f[f] = stage[f].data(); mask |= TRIBS_MASK(f); }
+    if (p_sync(h, mask, &S)) die("tribs_gpu_sync");
+    auto &W = snow_stage;
+    for (size_t i = 0; i < cells.size(); i++) {
+      tCNode *c = cells[i];
+      c->setLiqWE(stage[TRIBS_F_LiqWE][i]); c->setIceWE(stage[TRIBS_F_IceWE][i]); c->setLiqRouted(stage[TRIBS_F_LiqRouted][i]);
+      c->setSnTempC(W[TRIBS_SN_SnTempC][i]); c->setCrustAge(W[TRIBS_SN_CrustAge][i]); c->setDensityAge(W[TRIBS_SN_DensityAge][i]);
+      c->setEvapoTransAge(W[TRIBS_SN_EvapoTransAge][i]); c->setSnSub(W[TRIBS_SN_SnSub][i]); c->setSnEvap(W[TRIBS_SN_SnEvap][i]);
+      c->setDU(W[TRIBS_SN_DU][i]); c->setUnode(W[TRIBS_SN_Unode][i]); c->setUerror(W[TRIBS_SN_Uerror][i]);
+      c->setSnLHF(W[TRIBS_SN_SnLHF][i]); c->setSnSHF(W[TRIBS_SN_SnSHF][i]); c->setSnGHF(W[TRIBS_SN_SnGHF][i]);
+      c->setSnPHF(W[TRIBS_SN_SnPHF][i]); c->setSnRLout(W[TRIBS_SN_SnRLout][i]); c->setSnRLin(W[TRIBS_SN_SnRLin][i]);
+      c->setSnRSin(W[TRIBS_SN_SnRSin][i]);
+      c->setIntSWE(W[TRIBS_SN_IntSWE][i]); c->setIntPrec(W[TRIBS_SN_IntPrec][i]); c->setIntSnUnload(W[TRIBS_SN_IntSnUnload][i]);
+      c->setIntSub(W[TRIBS_SN_IntSub][i]);
+      c->addIntSub(W[TRIBS_SN_CumIntSub][i] - c->getCumIntSub()); c->addIntUnl(W[TRIBS_SN_CumIntUnl][i] - c->getCumIntUnl());
+      c->addLatHF(W[TRIBS_SN_CumLHF][i] - c->getCumLHF()); c->addMelt(W[TRIBS_SN_CumMelt][i] - c->getCumMelt());
+      c->addSHF(W[TRIBS_SN_CumSHF][i] - c->getCumSHF()); c->addSnSub(W[TRIBS_SN_CumSnSub][i] - c->getCumSnSub());
+      c->addSnEvap(W[TRIBS_SN_CumSnEvap][i] - c->getCumSnEvap()); c->addPHF(W[TRIBS_SN_CumPHF][i] - c->getCumPHF());
+      c->addRLin(W[TRIBS_SN_CumRLin][i] - c->getCumRLin()); c->addRLout(W[TRIBS_SN_CumRLout][i] - c->getCumRLout());
+      c->addGHF(W[TRIBS_SN_CumGHF][i] - c->getCumGHF()); c->addCumUerror(W[TRIBS_SN_CumUerror][i] - c->getCumUerror());
+      c->addCumHrsSnow(W[TRIBS_SN_CumHrsSnow][i] - c->getCumHrsSnow());
+      c->setPersTimeMax(W[TRIBS_SN_PersTimeMax][i]); c->setPersTime(W[TRIBS_SN_PersTime][i]); c->setPeakSWE(W[TRIBS_SN_PeakSWE][i]);
+      c->setPeakSWETemp(W[TRIBS_SN_PeakSWETemp][i]); c->setInitPackTime(W[TRIBS_SN_InitPackTime][i]);
+      c->setInitPackTimeTemp(W[TRIBS_SN_InitPackTimeTemp][i]); c->setPeakPackTime(W[TRIBS_SN_PeakPackTime][i]);
     }
   }
   ~TribsGpuBinding() { if (h && p_destroy) p_destroy(h); }

@@ -305,10 +305,10 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         G = NX * NY
         nodes = np.zeros(G, NODE_DTYPE)                    # rows in id order = file order
         g = g_of_id
-        act = np.arange(G) < n
         nodes["id"] = np.arange(G)
-        nodes["boundary"] = np.where(act, np.where(np.arange(G) < n, np.append(basin["boundary"], np.zeros(G - n, np.int32)), 0), 1)
-        nodes["boundary"][n] = 2
+        nodes["boundary"] = 1                               # closed ring ...
+        nodes["boundary"][:n] = basin["boundary"]           # ... active cells (0 hillslope, 3 stream) ...
+        nodes["boundary"][n] = 2                            # ... and the outlet
         nodes["x"], nodes["y"], nodes["z"] = x.ravel()[g], y.ravel()[g], z.ravel()[g]
         nodes["varea"][:n] = varea
         first_k = np.argmax(exists[g], axis=1)
