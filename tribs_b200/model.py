@@ -172,6 +172,33 @@ class tKinemat:
             self.lateral_inflow = self.dev.retrieve_qeff(now)
 
 
+class tCOutput:
+    """tCOutput::WriteDynamicVars (tOutput.cpp:1238-1400) from the device state: the fields the file
+    needs are synced (only when an output is due), the reference's text format is written by
+    output.write_dynamic_vars. Qstrm / Hlev belong to the host's channel router and are passed in."""
+
+    NEEDS = ["NwtNew", "MuNew", "MiNew", "NfNew", "NtNew", "Qpout", "Qpin", "srf_hr", "Rain", "SnTempC", "IceWE", "LiqWE",
+             "SnSub", "SnEvap", "LiqRouted", "Unode", "SnLHF", "SnSHF", "SnGHF", "SnPHF", "SnRLout", "SnRLin", "SnRSin",
+             "Uerror", "IntSWE", "IntSub", "IntSnUnload", "SoilMoistureSC", "RootMoistureSC", "CanStorage", "ActEvap",
+             "EvapSoil", "EvapoTrans", "GFlux", "HFlux", "LFlux", "FlowVelocity"]
+
+    def __init__(self, dev: gpu.GpuBasin, basin: dict, prefix: str, et_on: bool, snow_on: bool):
+        self.dev, self.basin, self.prefix, self.et_on, self.snow_on = dev, basin, prefix, et_on, snow_on
+
+    def WriteDynamicVars(self, time_h: float, channel: dict | None = None) -> str:
+        from . import output
+        main = [nm for nm in self.NEEDS if nm in gpu.F]
+        state = self.dev.sync(main)
+        if self.et_on:
+            state.update(self.dev.et_sync([nm for nm in self.NEEDS if nm in gpu.EF and nm not in gpu.F]))
+        if self.snow_on:
+            state.update(self.dev.snow_sync([nm for nm in self.NEEDS if nm in gpu.SNF and nm not in gpu.F and nm not in gpu.EF]))
+        state.update(channel or {})
+        path = output.dynamic_vars_name(self.prefix, time_h)
+        output.write_dynamic_vars(path, self.basin, state)
+        return path
+
+
 class Simulator:
     """simulation_loop() for the path: Advance, rain, UnSat, [ResetGW, Sat], SurfaceFlow, Reset."""
 
