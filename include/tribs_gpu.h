@@ -231,8 +231,9 @@ int tribs_gpu_abi_version(void);
  * stays with the host and arrives in tribs_et_step_t: calendar hour, sun geometry
  * (SetSunVariables 1567-1660), the weather-station records of the hour (newHydroMetData
  * 3962-4010) and the flags derived from record 0.
- * Covered options: OPTEVAPOTRANS 1-3, OPTINTERCEPT 0-2, GFLUXOPTION 1-2, OPTRADSHELT 0 or 4,
- * OPTLANDUSE 0, OPTSNOW 0, station or gridded met. Anything else fails in tribs_gpu_et_init. */
+ * Covered options: OPTEVAPOTRANS 1-3, OPTINTERCEPT 0-2, GFLUXOPTION 1-2, OPTRADSHELT 0-4 (1-3 with
+ * tShelter's per-cell values, see tribs_et_params_t), OPTLANDUSE 0, OPTSNOW 0/1 (1: tribs_gpu_snow_*
+ * below), station or gridded met. Anything else fails in tribs_gpu_et_init. */
 #define TRIBS_ET_FIELDS(X) \
   X(PotEvap) X(ActEvap) X(SurfTemp) X(SoilTemp) X(NetRad) X(GFlux) X(HFlux) X(LFlux) \
   X(LongRadIn) X(LongRadOut) X(ShortRadIn) X(ShortRadIn_dir) X(ShortRadIn_dif) X(ShortRadSlope) \
@@ -254,12 +255,17 @@ typedef struct {
   int32_t n_land_classes;
   const double *land_table;     /* [n_land_classes][15]: column k = tInvariant::getLandProp(k), k = 1..14 */
   int32_t et_option, i_option, gflux_option, shelter_option;   /* OPTEVAPOTRANS OPTINTERCEPT GFLUXOPTION OPTRADSHELT */
-  int32_t lu_option, snow_option;                              /* must be 0 */
+  int32_t lu_option, snow_option;                              /* OPTLANDUSE (must be 0), OPTSNOW (1: tribs_gpu_snow_init follows) */
   double metstep_min;           /* METSTEP (tEvapoTrans::timeStep) */
   double etistep_h;             /* tRunTimer::getEtIStep() */
   double tlinke, temp_lapse;    /* TLINKE, TEMPLAPSE */
   double max_interstorm;        /* tIntercept::maxInterStormPeriod (INTSTORMMAX/2, tIntercept.cpp:44-45) */
   const double *const *init;    /* NULL, or TRIBS_N_ET_FIELDS pointers (NULL entries = 0) */
+  /* OPTRADSHELT 1-3 (tShelter): init[TRIBS_ET_SheltFact] carries the sky-view factor of every cell and
+   * hor_angle_0000 [n] is tCNode::getHorAngle0000() in radians - the only horizon angle
+   * tEvapoTrans::aboveHorizon (tEvapoTrans.cpp:2080-2270) ends up using (its sector test is always
+   * true, so the first case decides). NULL for OPTRADSHELT 0 and >= 4. */
+  const double *hor_angle_0000;
 } tribs_et_params_t;
 
 /* one record per weather station (METDATAOPTION 1) or per cell (gridded, METDATAOPTION 2) */

@@ -278,7 +278,7 @@ class EtBasin(C.Structure):
         ("land_class", PI), ("land_table", PD),
         ("et_option", C.c_int32), ("i_option", C.c_int32), ("gflux_option", C.c_int32), ("shelter_option", C.c_int32),
         ("metstep_min", C.c_double), ("etistep_h", C.c_double), ("tlinke", C.c_double), ("temp_lapse", C.c_double),
-        ("max_interstorm", C.c_double)]
+        ("max_interstorm", C.c_double), ("hor_angle_0000", PD)]
 
 
 class Met(C.Structure):
@@ -325,6 +325,8 @@ class OracleET:
         B.metstep_min = float(b["et_timeStep"][0]); B.etistep_h = float(b["etistep"][0])
         B.tlinke = float(b["et_Tlinke"][0]); B.temp_lapse = float(b["et_tempLapseRate"][0])
         B.max_interstorm = float(b["icp_maxInterStormPeriod"][0])
+        if "hor_angle_0000" in b:         # tShelter's horizon angle at azimuth 0 (OPTRADSHELT 1-3)
+            ha = np.ascontiguousarray(b["hor_angle_0000"], np.float64); self.keep["ha"] = ha; B.hor_angle_0000 = _pd(ha)
         self.B = B
         self.f = {nm: np.array(b["init_" + nm], np.float64) if "init_" + nm in b else np.zeros(n) for nm in ET_FIELDS}
         self.fp = (PD * len(ET_FIELDS))(*[_pd(self.f[nm]) for nm in ET_FIELDS])

@@ -304,6 +304,8 @@ struct Harness {
         w.i32s("et_luOption", E->luOption);
         w.i32s("et_snowOption", E->snowOption);
         w.i32s("et_shelterOption", E->shelterOption);
+        // tShelter's per-node horizon angle at azimuth 0: the only one tEvapoTrans::aboveHorizon ends up using
+        w.f64("hor_angle_0000", col([](tCNode *c) { return c->getHorAngle0000(); }));
         w.f64s("et_timeStep", E->timeStep);
         w.f64s("et_Tlinke", E->Tlinke);
         w.f64s("et_tempLapseRate", E->tempLapseRate);

@@ -22,7 +22,7 @@ typedef struct {
   double coeffAl, coeffH, coeffKt, coeffRs, coeffV, coeffSE, coeffST, coeffKs, coeffCs;
   double betaS, betaT;
   /* geometry */
-  double elevation, slope, aspect, shelterFactor;
+  double elevation, slope, aspect, shelterFactor, horAngle0000;
   /* sun (global) */
   double alphaD, sinAlpha, sunaz, Io;
   int hour;
@@ -162,7 +162,12 @@ static void direct_diffuse(EtCell *c, double elev) {
   c->Id = c->Io * TnTLK * Fdh0;
 }
 
-/* ---- tEvapoTrans.cpp:1751-1930 (shelter options 0 and >= 4 only; observed stations) */
+/* ---- tEvapoTrans::aboveHorizon, tEvapoTrans.cpp:2080-2270. The sector test `(x < 12.25) || (x >= -12.25)` is
+ * always true, so the first of the 16 cases (azimuth 0) runs, sets `dummy`, and the loop ends: the
+ * horizon angle at azimuth 0 alone decides whether the cell sees the sun. */
+static double above_horizon(const EtCell *c) { return (c->horAngle0000 * (180 / 3.1416) < c->alphaD) ? 1.0 : 0.0; }
+
+/* ---- tEvapoTrans.cpp:1751-1930 (observed stations) */
 static void in_short_wave(EtCell *c, double *const *etf, int i) {
   double N = 0, Iv = 0, Isw = 0, Ir = 0, v, cosi, vegAbs = 0.0, soilAbs = 0.0;
   c->Ic = c->Is = c->Id = c->Ids = c->Ics = 0.0;
@@ -182,11 +187,14 @@ static void in_short_wave(EtCell *c, double *const *etf, int i) {
       if (cosi >= 0) { c->Ics = c->Ic * cosi; c->SunHour = 1.0; }
       else { c->Ics = 0.0; c->SunHour = 0.0; }
     } else { c->Ics = c->Ic; c->SunHour = 1.0; }
-    if ((c->shOpt == 0) || (c->shOpt == 3)) v = 0.5 * (1.0 + cos(c->slope));
+    if ((c->shOpt == 2) || (c->shOpt == 1)) { c->Ics *= above_horizon(c); c->SunHour *= above_horizon(c); }
+    if ((c->shOpt > 0) && (c->shOpt < 3)) v = c->shelterFactor;
+    else if ((c->shOpt == 0) || (c->shOpt == 3)) v = 0.5 * (1.0 + cos(c->slope));
     else v = 1.0;
     c->Ids = c->Id * v;
     c->Is = (1.0 - 0.65 * pow(N, 2.0)) * (c->Ics + c->Ids);
     if (c->shOpt == 0) { Ir = c->coeffAl * c->Is * (1 - cos(c->slope)) * 0.5; c->Is += Ir; }
+    else if ((c->shOpt > 1) && (c->shOpt < 4)) { Ir = c->coeffAl * c->Is * (0.5 * (1 + cos(c->slope)) - c->shelterFactor); c->Is += Ir; }
     else Ir = 0.0;
     if (c->etOpt == 1) {
       F(ShortRadSlope) = c->Is;
@@ -412,7 +420,11 @@ static void met_assembly(const orc_et_basin *b, const orc_et_step *s, const orc_
   c->elevation = b->z[i];
   c->slope = fabs(atan(b->flow_slope[i]));
   c->aspect = b->aspect[i];
-  if (b->shelter_option == 0) { c->shelterFactor = 0.5 * (1 + cos(c->slope)); F(SheltFact) = c->shelterFactor; }
+  c->horAngle0000 = 0.0;
+  if ((b->shelter_option > 0) && (b->shelter_option < 4)) {   /* tShelter's sky-view factor lives in the node */
+    c->shelterFactor = F(SheltFact);
+    c->horAngle0000 = b->hor_angle_0000[i];
+  } else if (b->shelter_option == 0) { c->shelterFactor = 0.5 * (1 + cos(c->slope)); F(SheltFact) = c->shelterFactor; }
   else c->shelterFactor = 1;
   load_coeffs(b, c, i);
   load_met(b, s, m, c, i);
@@ -457,7 +469,7 @@ static void set_to_node(const orc_et_step *s, double *const *etf, int i, EtCell 
 
 int orc_et_potential(const orc_et_basin *b, const orc_et_step *s, const orc_met *m,
                      double *const *etf, const orc_et_shared *sh) {
-  if (!(b->shelter_option == 0 || b->shelter_option >= 4)) return 1;
+  if (b->shelter_option >= 1 && b->shelter_option <= 3 && !b->hor_angle_0000) return 1;
   if (b->et_option < 1 || b->et_option > 3) return 1;
   for (int i = 0; i < b->n; i++) {
     EtCell cell, *c = &cell;
@@ -755,7 +767,9 @@ static double in_short_wave_sn(EtCell *c, Snow *w, double *const *etf, int i, in
       if (cosi >= 0.0) { c->Ics = c->Ic * cosi; c->SunHour = 1.0; }
       else { c->Ics = 0.0; c->SunHour = 0.0; }
     } else { c->Ics = 1.0 * c->Ic; c->SunHour = 1.0; }
-    if (c->shOpt == 0 || c->shOpt == 3) v = 0.5 * (1 + cos(c->slope));
+    if ((c->shOpt == 2) || (c->shOpt == 1)) { c->Ics *= above_horizon(c); c->SunHour *= above_horizon(c); }
+    if ((c->shOpt > 0) && (c->shOpt < 3)) v = c->shelterFactor;
+    else if (c->shOpt == 0 || c->shOpt == 3) v = 0.5 * (1 + cos(c->slope));
     else v = 1.0;
     c->Ids = c->Id * v;
     Is = (1.0 - 0.65 * pow(N, 2)) * (c->Ics + c->Ids);
@@ -766,6 +780,7 @@ static double in_short_wave_sn(EtCell *c, Snow *w, double *const *etf, int i, in
       else hillalbedo = w->albedo;
     }
     if (c->shOpt == 0) { Ir = hillalbedo * Is * (1 - cos(c->slope)) * 0.5; Is += Ir; }
+    else if ((c->shOpt > 1) && (c->shOpt < 4)) { Ir = hillalbedo * Is * (0.5 * (1 + cos(c->slope)) - c->shelterFactor); Is += Ir; }
     else Ir = 0.0;
     if ((c->etOpt == 1) || snow_option) Iv = Is * exp((c->coeffKt - 1) * c->coeffLAI) * c->coeffV + Is * (1.0 - c->coeffV);
     else Iv = Is;
@@ -783,7 +798,8 @@ static double in_short_wave_sn(EtCell *c, Snow *w, double *const *etf, int i, in
 
 /* tSnowPack.cpp:1940-2001 */
 static void snow_eb(EtCell *c, Snow *w, double *const *etf, double *const *snf, int i) {
-  double sigma = 5.67e-8, v1 = 1, snTempK, resFact;
+  double sigma = 5.67e-8, v1, snTempK, resFact;
+  v1 = (c->shOpt > 0 && c->shOpt < 3) ? c->shelterFactor : 1;   /* tSnowPack.cpp:1945-1948 */
   snTempK = w->snTempC + 273.15;
   resFact = res_fact(c, w);
   w->H = sensible_hf(c, w, resFact);
@@ -869,7 +885,7 @@ static void route_excess_liquid(Snow *w) {
 int orc_snow_pack(const orc_et_basin *b, const orc_snow_args *sn, const orc_et_step *s, const orc_met *m,
                   double *const *etf, double *const *snf, const orc_et_shared *sh, int flag, double *members) {
   Snow W, *w = &W;
-  if (!(b->shelter_option == 0 || b->shelter_option >= 4)) return 1;
+  if (b->shelter_option >= 1 && b->shelter_option <= 3 && !b->hor_angle_0000) return 1;
   if (b->et_option < 1 || b->et_option > 3) return 1;
   memset(w, 0, sizeof W);
   w->albedo = members[0]; w->Uerr = members[1]; w->snCanWE = members[2];

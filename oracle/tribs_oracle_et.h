@@ -43,6 +43,7 @@ typedef struct {
   double etistep_h;               /* tRunTimer::getEtIStep() */
   double tlinke, temp_lapse;
   double max_interstorm;          /* tIntercept::maxInterStormPeriod = INTSTORMMAX/2 */
+  const double *hor_angle_0000;   /* OPTRADSHELT 1-3: tCNode::getHorAngle0000() [rad] (tShelter); NULL otherwise */
 } orc_et_basin;
 
 /* one met record per station (or per cell for gridded data), values of one hour */

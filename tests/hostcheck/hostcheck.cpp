@@ -89,7 +89,7 @@ void hc_cm_pow(const double *x, const double *e, double *y, int n) { for (int i 
 
 // ---- kernel (1) and the snow pack: one call of the cell loop, cells in sweep order ----------------
 // ci: et_option i_option gflux_option shelter_option | cd: metstep_min etistep_h tlinke temp_lapse max_interstorm
-// est: z flow_slope aspect heat_cond heat_cap soil_cutoff root_cutoff thr bedrock varea
+// est: z flow_slope aspect heat_cond heat_cap soil_cutoff root_cutoff thr bedrock varea hor_angle_0000
 // si: do_potential do_components intercept_flag hour first_call dew_hum_flag ts_option sky_flag_from met_time
 // sd: alphaD sinAlpha sunaz Io te_met te_eti
 // met_pot / met_cmp: air_temp dew_temp rel_humid vap_press atm_press wind_speed sky_cover rad_global elev
@@ -112,6 +112,7 @@ void hc_et_step(int n, const int32_t *ci, const double *cd, double **est, const 
   EtStatic st{};
   st.z = est[0]; st.cos_slope = cs.data(); st.sin_slope = sn.data(); st.aspect = est[2]; st.heat_cond = est[3];
   st.heat_cap = est[4]; st.soil_cutoff = est[5]; st.root_cutoff = est[6]; st.thr = est[7]; st.bedrock = est[8]; st.varea = est[9];
+  st.hor_angle_0000 = est[10];
   st.land_class = land_class; st.boundary = bnd.data(); st.sweep_of_dev = order.data(); st.classes = cls.data();
   static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014, 0.995, 0.976, 0.976, 1.0,
                                      1.053, 1.167, 1.354, 1.637, 2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};

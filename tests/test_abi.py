@@ -54,3 +54,31 @@ def test_product_does_not_reference_the_oracle():
                 if re.search(r"(from|import)\s+oracle|oracle/|tribs_oracle|pyoracle", txt):
                     bad.append(f)
     assert not bad, f"product sources mention the oracle: {bad}"
+
+
+def test_ctypes_structs_have_the_layout_of_the_c_header(tmp_path):
+    """Every struct that crosses the C ABI is declared twice: in include/tribs_gpu.h and as a ctypes
+    Structure in tribs_b200/gpu.py. A tiny C program prints sizeof / offsetof for each field (a field
+    missing on the C side fails to compile) and the numbers must equal ctypes' own."""
+    import ctypes as C
+    import subprocess
+    from tribs_b200 import gpu
+    pairs = [("tribs_mesh_t", gpu.Mesh), ("tribs_params_t", gpu.Params), ("tribs_state_t", gpu.StateT),
+             ("tribs_part_t", gpu.Part), ("tribs_step_t", gpu.Step), ("tribs_et_params_t", gpu.EtParams),
+             ("tribs_met_t", gpu.MetT), ("tribs_et_step_t", gpu.EtStep), ("tribs_snow_params_t", gpu.SnowParams)]
+    lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/tribs_gpu.h"', "int main(void) {"]
+    for cname, cls in pairs:
+        lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname}.{fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    r = subprocess.run(["gcc", "-o", str(exe), str(src)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = dict(ln.split() for ln in subprocess.run([str(exe)], capture_output=True, text=True).stdout.splitlines())
+    for cname, cls in pairs:
+        assert int(got[cname]) == C.sizeof(cls), (cname, got[cname], C.sizeof(cls))
+        for fname, _ in cls._fields_:
+            assert int(got[f"{cname}.{fname}"]) == getattr(cls, fname).offset, (cname, fname)

@@ -124,6 +124,7 @@ class _EtHostCheck:
         self.est = [np.ascontiguousarray(b[k], np.float64) for k in
                     ("z", "flow_slope", "aspect", "VolHeatCond", "SoilHeatCap", "soil_cutoff", "root_cutoff", "ThetaR",
                      "bedrock", "varea")]
+        self.est.append(np.ascontiguousarray(b["hor_angle_0000"], np.float64) if "hor_angle_0000" in b else np.zeros(self.n))
         self.lc = np.ascontiguousarray(b["land_class"], np.int32)
         self.lt = np.ascontiguousarray(b["land_table"], np.float64)
 
@@ -259,3 +260,17 @@ def test_snow_with_canopy_device_header_matches_oracle_on_host(extra, built):
     assert hc.calls >= 90
     assert np.abs(hc.o.et.f["CumIntSub"]).max() > 0 and np.abs(hc.o.et.f["CumMelt"]).max() > 0
     assert max(hc.rounds) >= 2 and max(hc.rounds) <= 4, hc.rounds
+
+
+@pytest.mark.parametrize("name,option", [("met", 1), ("met", 2), ("met", 3), ("snow", 1), ("snow", 2), ("snow", 3)])
+def test_radiation_sheltering_device_header_matches_oracle_on_host(name, option, built):
+    """OPTRADSHELT 1-3 in et_update.cuh / snow_update.cuh (tShelter's sky-view factor from the node, the
+    horizon angle at azimuth 0, land-view reflection) against the oracle, which is bit-exact against the
+    reference for these options (tests/test_oracle.py)."""
+    from refrun import have_harness, run_reference, spec_for
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    basin, _, _, _ = run_reference(spec_for(name, 10, runtime_h=40.0, seed=5, dem_ridge=300.0, extra={"OPTRADSHELT": option}))
+    assert int(basin["et_shelterOption"][0]) == option and "hor_angle_0000" in basin
+    hc = _drive_with_host_check(basin, 40 * 16, tol=1e-9)
+    assert hc.calls >= 35

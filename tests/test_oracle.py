@@ -142,3 +142,21 @@ def test_oracle_snow_against_live_reference(extra, built):
     assert w.max() == 0.0, "oracle differs from the reference:\n" + w.report()
     assert ("m", "IceWE") in w.w and ("m", "CumMelt") in w.w
     assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("name,option", [("met", 1), ("met", 2), ("met", 3), ("snow", 1), ("snow", 2), ("snow", 3)])
+def test_oracle_radiation_sheltering_against_live_reference(name, option, built):
+    """OPTRADSHELT 1-3 (tShelter's sky-view factor and horizon angle from a DEM with a 300 m wall on
+    its east margin): the oracle's short / long wave terms for the ET and the snow path, bit for
+    bit. (The device path still refuses these option values; this pins the oracle for it.)"""
+    hours = 30.0
+    spec = spec_for(name, 12, runtime_h=hours, seed=4, dem_ridge=300.0, extra={"OPTRADSHELT": option})
+    n_steps = int(hours * 16)
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="murb")
+    assert int(basin["et_shelterOption"][0]) == option
+    sf = basin["init_SheltFact"]
+    assert 0.3 < sf.min() < sf.max() < 0.9            # the wall shades the cells next to it more than the others
+    w = run_and_compare(OracleStepper(basin, schedule_for(basin)), snaps, n_steps, floor=1e-6)
+    assert w.max() == 0.0, w.report()
+    assert ("m", "ShortRadIn") in w.w and ("m", "LongRadIn") in w.w

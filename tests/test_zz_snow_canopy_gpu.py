@@ -48,6 +48,25 @@ def test_gpu_snow_golden_fixture(built):
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("name,option", [("met", 2), ("met", 3), ("snow", 1)])
+def test_gpu_radiation_sheltering_matches_live_reference(name, option, built):
+    """OPTRADSHELT 1-3: tShelter's sky-view factor (init SheltFact) and horizon angle at azimuth 0 reach
+    kernel (1) / the snow kernels through tribs_et_params_t; a DEM with a 300 m wall on its east
+    margin makes the factor vary from cell to cell."""
+    hours = 40.0
+    spec = spec_for(name, 16, runtime_h=hours, seed=5, dem_ridge=300.0, extra={"OPTRADSHELT": option})
+    n_steps = int(hours * 16)
+    basin, snaps, _, _ = run_reference(spec, snap_from=1, snap_to=n_steps, snap_every=16, phases="murb")
+    assert int(basin["et_shelterOption"][0]) == option
+    for k in [k for k in snaps if k.endswith("_m_Uerror") or k.endswith("_m_CumUerror")]:
+        del snaps[k]
+    w = run_and_compare(GpuStepper(basin, schedule_for(basin)), snaps, n_steps, floor=ABS_FLOOR)
+    print(f"\n[shelter {option} {name}] worst:\n" + w.report(6))
+    assert w.max() <= REL_TOL, w.report()
+    assert ("m", "LongRadIn") in w.w and ("m", "ShortRadIn") in w.w
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
 def test_reference_simulator_drives_gpu_snow_path(built):
     """The drop-in boundary for OPTSNOW 1: the reference's own objects and time loop
     (tribs_ref_harness --gpu) call TribsGpuBinding::callSnowPack (tribs_b200/host/tribs_ref_binding.h)

@@ -65,6 +65,7 @@ inline LandClass make_land_class(const double *lp, int et_option) {   // lp[k] =
 struct EtStatic {           // device order, length n_pad
   const double *z, *cos_slope, *sin_slope, *aspect, *heat_cond, *heat_cap, *soil_cutoff, *root_cutoff;
   const double *thr, *bedrock, *varea;
+  const double *hor_angle_0000;   // OPTRADSHELT 1-3: tShelter's horizon angle at azimuth 0 [rad], else nullptr
   const int32_t *land_class, *boundary, *sweep_of_dev;
   const LandClass *classes;
 };
@@ -340,6 +341,18 @@ TRIBS_HD void intercept_rutter(const LandClass &lc, const EtConst &k, double rai
 // ---- the cell update -------------------------------------------------------------------------------
 #define EF(name) ev.f[TRIBS_ET_##name][i]
 
+// Radiation sheltering (OPTRADSHELT; tEvapoTrans.cpp:621-686, 1826-1887, aboveHorizon 2080-2270).
+TRIBS_HD double shelter_factor(const EtConst &k, const EtView &ev, int i, double cos_s) {
+  if (k.shelter_option > 0 && k.shelter_option < 4) return EF(SheltFact);   // tShelter's sky-view factor, static
+  return (k.shelter_option == 0) ? 0.5 * (1 + cos_s) : 1.0;
+}
+// the sector test of aboveHorizon is always true: its first case (azimuth 0) decides
+TRIBS_HD double above_horizon(double hor_angle_0000, double alphaD) { return (hor_angle_0000 * (180 / 3.1416) < alphaD) ? 1.0 : 0.0; }
+TRIBS_HD double diffuse_view(const EtConst &k, double shelter, double cos_s) {
+  if (k.shelter_option > 0 && k.shelter_option < 3) return shelter;
+  return (k.shelter_option == 0 || k.shelter_option == 3) ? 0.5 * (1.0 + cos_s) : 1.0;
+}
+
 // kStore = false evaluates the cell without leaving anything behind (the snow path probes cells
 // that way, snow_update.cuh). Returns the net precipitation below the canopy.
 template <bool kStore>
@@ -358,7 +371,8 @@ TRIBS_HD double et_sweeps_t(const EtConst &k, const EtStatic &st, const EtStepDe
     MetAir a;
     a.load(s.pot, i, elevation, k.temp_lapse, s.dew_hum_flag);
     const double cos_s = st.cos_slope[i], sin_s = st.sin_slope[i];
-    const double shelter = (k.shelter_option == 0) ? 0.5 * (1 + cos_s) : 1.0;
+    // sky-view factor: local slope only (OPTRADSHELT 0), tShelter's value kept in the node (1-3), none (>= 4)
+    const double shelter = shelter_factor(k, ev, i, cos_s);
     const bool sky_flag = (st.sweep_of_dev[i] >= s.sky_flag_from) || (fabs(a.skyCover - 9999.99) < 1.0E-3);
     if (sky_flag) a.skyCover = a.sky_from_humidity(rain);
     double surfT, soilT;
@@ -405,10 +419,15 @@ TRIBS_HD double et_sweeps_t(const EtConst &k, const EtStatic &st, const EtStepDe
         const double cosi = cos_s * s.sinAlpha + sin_s * s.cos_alpha * cos(s.sunaz - st.aspect[i]);
         if (cosi >= 0) { Ics = Ic * cosi; sunHour = 1.0; }
       } else { Ics = Ic; sunHour = 1.0; }
-      const double v = (k.shelter_option == 0 || k.shelter_option == 3) ? 0.5 * (1.0 + cos_s) : 1.0;
+      if (k.shelter_option == 1 || k.shelter_option == 2) {
+        const double seen = above_horizon(st.hor_angle_0000[i], s.alphaD);
+        Ics *= seen; sunHour *= seen;
+      }
+      const double v = diffuse_view(k, shelter, cos_s);
       Ids = Id * v;
       Is = (Ics + Ids);
       if (k.shelter_option == 0) { Ir = lc.Al * Is * (1 - cos_s) * 0.5; Is += Ir; }
+      else if (k.shelter_option > 1 && k.shelter_option < 4) { Ir = lc.Al * Is * (0.5 * (1 + cos_s) - shelter); Is += Ir; }
       if (k.et_option == 1) {
         soilAbs = (Is * lc.Kt * lc.V + Is * (1.0 - lc.V)) * (1.0 - lc.Al);
         vegAbs = Is * lc.V * (1.0 - lc.Kt) * (1.0 - lc.Al);

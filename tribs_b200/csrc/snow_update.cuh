@@ -212,7 +212,7 @@ TRIBS_HD void snow_cell_t(const EtConst &k, const EtStatic &st, const EtStepDev 
   }
   // ---- met assembly of callSnowPack for a snow cell (node fields the ET path would have written)
   const double cos_s = st.cos_slope[i], sin_s = st.sin_slope[i];
-  const double shelter = (k.shelter_option == 0) ? 0.5 * (1 + cos_s) : 1.0;
+  const double shelter = shelter_factor(k, ev, i, cos_s);
   const bool sky_flag = (st.sweep_of_dev[i] >= s.sky_flag_from) || (fabs(a.skyCover - 9999.99) < 1.0E-3);
   if (sky_flag) a.skyCover = a.sky_from_humidity(rain);
   if (kStore) {
@@ -337,13 +337,15 @@ TRIBS_HD void snow_cell_t(const EtConst &k, const EtStatic &st, const EtStepDev 
           const double cosi = 1.0 * (cos_s * s.sinAlpha + sin_s * s.cos_alpha * cos(s.sunaz - st.aspect[i]));
           if (cosi >= 0.0) Ics = Ic * cosi;
         } else Ics = Ic;
-        const double v = (k.shelter_option == 0 || k.shelter_option == 3) ? 0.5 * (1 + cos_s) : 1.0;
+        if (k.shelter_option == 1 || k.shelter_option == 2) Ics *= above_horizon(st.hor_angle_0000[i], s.alphaD);
+        const double v = diffuse_view(k, shelter, cos_s);
         const double Ids = Id * v;
         double Is = (Ics + Ids), Ir = 0.0;
         double hillalbedo = w.albedo;                     // HILLALBOPT 0
         if (sc.hill_albedo_option == 1) hillalbedo = lc.Al;
         else if (sc.hill_albedo_option == 2 && snCanWE == 0) hillalbedo = lc.V * lc.Al + (1 - lc.V) * w.albedo;
         if (k.shelter_option == 0) { Ir = hillalbedo * Is * (1 - cos_s) * 0.5; Is += Ir; }
+        else if (k.shelter_option > 1 && k.shelter_option < 4) { Ir = hillalbedo * Is * (0.5 * (1 + cos_s) - shelter); Is += Ir; }
         const double Iv = Is * exp((lc.Kt - 1) * lc.LAI) * lc.V + Is * (1.0 - lc.V);
         Isw = Iv * (1.0 - w.albedo);
         IdsIr = Ids + Ir;
@@ -356,7 +358,11 @@ TRIBS_HD void snow_cell_t(const EtConst &k, const EtStatic &st, const EtStepDev 
         const double Ea = 0.74 + 0.0049 * a.vPressC, tk = a.airTemp + 273.15, tk2 = tk * tk;
         w.RLin = naughttokilo * (v0 * kCloud * Ea * 5.67E-8 * (tk2 * tk2));
       }
-      { const double tk = w.snTempC + 273.15, tk2 = tk * tk; w.RLout = -naughttokilo * 1.0 * 0.9 * 5.67e-8 * (tk2 * tk2); }
+      {                                                  // snowEB: long wave out, scaled by the sky view under OPTRADSHELT 1-2
+        const double v1 = (k.shelter_option > 0 && k.shelter_option < 3) ? shelter : 1.0;
+        const double tk = w.snTempC + 273.15, tk2 = tk * tk;
+        w.RLout = -naughttokilo * v1 * 0.9 * 5.67e-8 * (tk2 * tk2);
+      }
       EF(HFlux) = 0.0; EF(LFlux) = 0.0; EF(LongRadIn) = 0.0; EF(LongRadOut) = 0.0; EF(ShortAbsbVeg) = 0.0; EF(ShortAbsbSoi) = 0.0;
       SNF(SnLHF) = w.L * kilotonaught; SNF(SnSHF) = w.H * kilotonaught; SNF(SnPHF) = w.Prec * kilotonaught;
       SNF(SnGHF) = 0.0 * kilotonaught; SNF(SnRLin) = w.RLin * kilotonaught; SNF(SnRLout) = w.RLout * kilotonaught;

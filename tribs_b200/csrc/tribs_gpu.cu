@@ -1304,7 +1304,9 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   if (p->et_option < 0 || p->et_option > 3) return fail("tribs_gpu_et_init: OPTEVAPOTRANS must be 0..3 (pan evaporation is not covered)");
   if (p->i_option < 0 || p->i_option > 2) return fail("tribs_gpu_et_init: OPTINTERCEPT must be 0..2");
   if (p->et_option && p->gflux_option != 1 && p->gflux_option != 2) return fail("tribs_gpu_et_init: GFLUXOPTION must be 1 or 2");
-  if (!(p->shelter_option == 0 || p->shelter_option >= 4)) return fail("tribs_gpu_et_init: OPTRADSHELT 1-3 (horizon angles) is not covered");
+  if (p->shelter_option >= 1 && p->shelter_option <= 3 &&
+      (!p->hor_angle_0000 || !p->init || !p->init[TRIBS_ET_SheltFact]))
+    return fail("tribs_gpu_et_init: OPTRADSHELT 1-3 needs tShelter's sky-view factor (init[SheltFact]) and hor_angle_0000");
   if (p->lu_option != 0) return fail("tribs_gpu_et_init: OPTLANDUSE 1 (dynamic land-use grids) is not covered");
   if (p->snow_option != 0 && p->et_option == 0) return fail("tribs_gpu_et_init: OPTSNOW 1 needs the evaporation scheme");
   if (p->et_option == 0 && p->i_option == 2) return fail("tribs_gpu_et_init: Rutter interception needs the evaporation scheme (tSimul.cpp:444-450)");
@@ -1345,6 +1347,8 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
   if (up(cs.data(), &e->st.cos_slope) || up(sn.data(), &e->st.sin_slope) || up(p->aspect, &e->st.aspect) ||
       up(p->vol_heat_cond, &e->st.heat_cond) || up(p->soil_heat_cap, &e->st.heat_cap) ||
       up(p->soil_cutoff, &e->st.soil_cutoff) || up(p->root_cutoff, &e->st.root_cutoff)) return 1;
+  e->st.hor_angle_0000 = nullptr;
+  if (p->shelter_option >= 1 && p->shelter_option <= 3 && up(p->hor_angle_0000, &e->st.hor_angle_0000)) return 1;
   int32_t *d_lc = nullptr;
   if (dev_upload(c, &d_lc, to_device_order<int32_t>(c, p->land_class, 0))) return 1;
   e->st.land_class = d_lc;

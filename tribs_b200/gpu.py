@@ -104,7 +104,8 @@ class EtParams(C.Structure):
                 ("land_table", PD), ("et_option", C.c_int32), ("i_option", C.c_int32), ("gflux_option", C.c_int32),
                 ("shelter_option", C.c_int32), ("lu_option", C.c_int32), ("snow_option", C.c_int32),
                 ("metstep_min", C.c_double), ("etistep_h", C.c_double), ("tlinke", C.c_double),
-                ("temp_lapse", C.c_double), ("max_interstorm", C.c_double), ("init", C.POINTER(PD))]
+                ("temp_lapse", C.c_double), ("max_interstorm", C.c_double), ("init", C.POINTER(PD)),
+                ("hor_angle_0000", PD)]
 
 
 class MetT(C.Structure):
@@ -352,6 +353,8 @@ class GpuBasin:
             if src is not None:
                 a = np.ascontiguousarray(src, np.float64); keep.append(a); init[k] = _d(a)
         p.init = C.cast(init, C.POINTER(PD))
+        if "hor_angle_0000" in b and 1 <= p.shelter_option <= 3:      # tShelter's horizon angle at azimuth 0
+            a = np.ascontiguousarray(b["hor_angle_0000"], np.float64); keep.append(a); p.hor_angle_0000 = _d(a)
         _chk(self.L.tribs_gpu_et_init(self.h, C.byref(p)))
         self._et_flag = int(p.i_option != 0)
 

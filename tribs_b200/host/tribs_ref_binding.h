@@ -231,6 +231,14 @@ struct TribsGpuBinding {
     P.flow_slope = fslope.data(); P.aspect = aspect.data(); P.vol_heat_cond = hcond.data(); P.soil_heat_cap = hcap.data();
     P.soil_cutoff = scut.data(); P.root_cutoff = rcut.data(); P.land_class = lu.data(); P.n_land_classes = maxc + 1;
     P.land_table = table.data();
+    std::vector<double> shelt, hor0;                       // OPTRADSHELT 1-3: what tShelter left in the nodes
+    std::vector<const double *> init0(TRIBS_N_ET_FIELDS, nullptr);
+    if (et->shelterOption >= 1 && et->shelterOption <= 3) {
+      shelt = col([](tCNode *c) { return c->getSheltFact(); });
+      hor0 = col([](tCNode *c) { return c->getHorAngle0000(); });
+      init0[TRIBS_ET_SheltFact] = shelt.data();
+      P.init = init0.data(); P.hor_angle_0000 = hor0.data();
+    }
     P.et_option = et->evapotransOption; P.i_option = et->Ioption; P.gflux_option = et->gFluxOption;
     P.shelter_option = et->shelterOption; P.lu_option = et->luOption; P.snow_option = et->snowOption;
     P.metstep_min = et->timeStep; P.etistep_h = timer->getEtIStep(); P.tlinke = et->Tlinke;

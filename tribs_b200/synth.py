@@ -53,6 +53,7 @@ class BasinSpec:
     n_gauges: int = 2
     winter: bool = False          # met deck: sub-zero air temperatures and OPTSNOW 1
     sky_nodata: bool = False      # met deck: write 9999.99 as sky cover (the model then derives it from RH / rain)
+    dem_ridge: float = 0.0        # OPTRADSHELT 1-3: height of a wall on the east margin of the DEM (m), to cast shade
     inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
     extra: dict = field(default_factory=dict)   # keyword overrides
 
@@ -204,6 +205,17 @@ def write_basin(spec: BasinSpec, outdir: str) -> str:
         ("HYDRONODELIST", "none"), ("OUTLETNODELIST", "none"),
     ]
     over = dict(spec.extra)
+    if int(over.get("OPTRADSHELT", 0)) in (1, 2, 3):      # tShelter derives horizon angles from a DEM grid (DEMFILE)
+        h, n = spec.spacing, spec.n
+        xc = (n // 2) * h
+        with open(os.path.join(outdir, "dem.asc"), "w") as f:
+            m = n + 8                                      # 4 cells of margin around the points
+            f.write(f"ncols {m}\nnrows {m}\nxllcorner {-4.5 * h}\nyllcorner {-4.5 * h}\ncellsize {h}\nNODATA_value -9999\n")
+            for j in range(m - 1, -1, -1):                 # rows from north to south
+                y = (j - 4) * h
+                f.write(" ".join(repr(100.0 + spec.slope_y * y + spec.slope_x * abs((i - 4) * h - xc)
+                                      + (spec.dem_ridge if i >= m - 3 else 0.0)) for i in range(m)) + "\n")
+        over.setdefault("DEMFILE", "dem.asc")
     if spec.forcing == "met":
         for k, v in write_met_forcing(spec, outdir).items():
             over.setdefault(k, v)
