@@ -82,14 +82,16 @@ def run_reference(spec: BasinSpec, workdir: str | None = None, snap_from=1, snap
     return basin, snaps, timing, katd
 
 
-def write_meshb_deck(side: int, workdir: str, seed: int = 1, runtime_h: float = 24.0):
+def write_meshb_deck(side: int, workdir: str, seed: int = 1, runtime_h: float = 24.0, scenario: str = "deep", **over):
     """A deck the reference can run at any size: synthbasin.build_basin(side, side) written as
     OPTMESHINPUT 9 files (no mesh construction, no flow-network set-up in the reference), the initial
     water table per Voronoi cell (OPTGWFILE 1, tHydroModel.cpp:249-269; the coarse gw.asc grid would
-    make tResample intersect it with every cell polygon). Returns build_basin's dict."""
+    make tResample intersect it with every cell polygon). `scenario` / `over` as for spec_for (forcing
+    files, options). Returns build_basin's dict."""
     from tribs_b200.synthbasin import build_basin
-    write_basin(spec_for("deep", side + 2, runtime_h=runtime_h, seed=seed), workdir)   # .in, soil / land grids
-    basin = build_basin(side, side, seed=seed, runtime_h=runtime_h, mesh_dir=workdir)
+    spec = spec_for(scenario, side + 2, runtime_h=runtime_h, seed=seed, **over)
+    write_basin(spec, workdir)                                                          # .in, soil / land grids, forcing
+    basin = build_basin(side, side, seed=seed, runtime_h=runtime_h, mesh_dir=workdir, gw_depth_mm=spec.gw_depth_mm)
     inp = os.path.join(workdir, "basin.in")
     txt = re.sub(r"(OPTMESHINPUT:\s*\n)\s*\d+", r"\g<1>9", open(inp).read())
     txt = re.sub(r"(OPTGWFILE:\s*\n)\s*\d+", r"\g<1>1", txt)
@@ -98,6 +100,31 @@ def write_meshb_deck(side: int, workdir: str, seed: int = 1, runtime_h: float = 
     with open(os.path.join(workdir, "gw.vor"), "w") as f:
         f.write("".join(f"{i} {v!r}\n" for i, v in enumerate(np.asarray(basin["init_NwtOld"]).tolist())))
     return basin
+
+
+def run_reference_meshb(side: int, scenario: str, runtime_h: float, seed: int = 1, snap_from=1, snap_to=0, snap_every=1,
+                        phases="ugr", timeout=3600, **over):
+    """run_reference on a synthetic basin the reference READS (OPTMESHINPUT 9) instead of building it:
+    set-up stays linear, so decks of 1e4-1e6 cells are affordable. Returns (basin, snapshots, timing)
+    with the basin as flattened by the reference itself."""
+    import json
+    d = tempfile.mkdtemp(prefix="tribsref9_")
+    write_meshb_deck(side, d, seed=seed, runtime_h=runtime_h, scenario=scenario, **over)
+    cmd = [HARNESS, "basin.in", "-K", "--out", d, "--snap-from", str(snap_from), "--snap-to", str(snap_to),
+           "--snap-every", str(snap_every), "--phases", phases]
+    r = subprocess.run(cmd, cwd=d, capture_output=True, text=True, timeout=timeout)
+    if r.returncode != 0:
+        raise RuntimeError("reference harness failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
+    m = re.search(r"ref_timing (\{.*\})", r.stdout)
+    timing = json.loads(m.group(1)) if m else {}
+    basin = read_trb(os.path.join(d, "basin.trb"))
+    snaps = read_trb(os.path.join(d, "steps.trb")) if snap_to >= snap_from else {}
+    spec = spec_for(scenario, side + 2, runtime_h=runtime_h, seed=seed, **over)
+    basin["_spec_pmean"], basin["_spec_stdur"] = np.array([spec.pmean]), np.array([spec.stdur])
+    basin["_spec_istdur"], basin["_spec_evap"] = np.array([spec.istdur]), np.array([spec.inject_evap])
+    import shutil
+    shutil.rmtree(d, ignore_errors=True)
+    return basin, snaps, timing
 
 
 def storm_of(basin):

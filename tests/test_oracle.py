@@ -160,3 +160,19 @@ def test_oracle_radiation_sheltering_against_live_reference(name, option, built)
     w = run_and_compare(OracleStepper(basin, schedule_for(basin)), snaps, n_steps, floor=1e-6)
     assert w.max() == 0.0, w.report()
     assert ("m", "ShortRadIn") in w.w and ("m", "LongRadIn") in w.w
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("name,hours,extra", [("snow", 60.0, dict(pmean=8.0)), ("met", 30.0, {})])
+def test_oracle_on_a_basin_the_reference_reads_as_meshbuilder_files(name, hours, extra, built):
+    """refrun.run_reference_meshb (the reference reads the synthetic basin as OPTMESHINPUT 9 files, so
+    set-up stays linear in the number of cells): the path the 10k-cell GPU tests and the 1M-cell
+    fixture use, here with the ET / snow forcing on 2 500 cells; the oracle stays bit-exact."""
+    from refrun import run_reference_meshb
+    n_steps = int(hours * 16)
+    basin, snaps, timing = run_reference_meshb(50, name, hours, seed=9, snap_from=16, snap_to=n_steps, snap_every=64,
+                                               phases="mur", **extra)
+    assert int(basin["n_active"][0]) == 2500 and timing["setup_s"] < 5.0
+    w = run_and_compare(OracleStepper(basin, schedule_for(basin)), snaps, n_steps, floor=1e-6)
+    assert w.max() == 0.0, w.report()
+    assert ("m", "PotEvap") in w.w and ("u", "NwtNew") in w.w

@@ -67,6 +67,30 @@ def test_gpu_radiation_sheltering_matches_live_reference(name, option, built):
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("name,hours,extra", [("snow", 48.0, dict(pmean=8.0)), ("met", 30.0, {})])
+def test_gpu_kernel1_and_snow_on_a_10k_cell_basin_match_live_reference(name, hours, extra, built):
+    """Kernel (1) and the snow kernels beyond a few thread blocks: a 100 x 100-cell basin that the
+    reference READS (OPTMESHINPUT 9 files from synthbasin, refrun.run_reference_meshb) - 79 blocks per
+    launch, and a last-writer scan of the carried snow members that spans several scan tiles."""
+    from refrun import run_reference_meshb
+    n_steps = int(hours * 16)
+    basin, snaps, timing = run_reference_meshb(100, name, hours, seed=9, snap_from=16, snap_to=n_steps, snap_every=64,
+                                               phases="mur", **extra)
+    assert int(basin["n_active"][0]) == 10000
+    for k in [k for k in snaps if k.endswith("_m_Uerror") or k.endswith("_m_CumUerror")]:
+        del snaps[k]
+    g = GpuStepper(basin, schedule_for(basin))
+    w = run_and_compare(g, snaps, n_steps, floor=ABS_FLOOR)
+    print(f"\n[{name}, 10k cells] worst:\n" + w.report(6))
+    assert w.max() <= REL_TOL, w.report()
+    if name == "snow":
+        assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumIntSub")) > 0.0
+        assert g.sim.dev.snow_members()[1] >= 1
+    else:
+        assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_PotEvap")) > 0.0
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
 def test_reference_simulator_drives_gpu_snow_path(built):
     """The drop-in boundary for OPTSNOW 1: the reference's own objects and time loop
     (tribs_ref_harness --gpu) call TribsGpuBinding::callSnowPack (tribs_b200/host/tribs_ref_binding.h)
