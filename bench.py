@@ -224,8 +224,14 @@ def run_gpu(args):
     steps_per_launch = args.steps / n_launch
     bytes_per_launch = n * steps_per_launch * (UNSAT_BYTES_PER_CELL + (SAT_BYTES_PER_CELL / gw_every if B > 1 else 0.0))
 
-    loop(e2e_step, e2e_batch, max(3, args.warmup // 2))
+    e2e_warm = max(3, args.warmup // 2)
+    loop(e2e_step, e2e_batch, e2e_warm)
     ems, ewall = timed(lambda k: loop(e2e_step, e2e_batch, k), args.steps)
+    # which simulated steps each number covers: the storm (20 mm/h) ends at step 96 and the first dry steps are the
+    # expensive ones (most columns change state), so the two windows are not equally hard
+    v0 = args.warmup + 1
+    e0 = args.warmup + args.steps + e2e_warm + 1
+    windows = {"value": [v0, v0 + args.steps - 1], "e2e": [e0, e0 + args.steps - 1], "storm_ends_at_step": 96}
     # host work (numpy fill, ctypes) is part of the user-visible e2e time: use the wall clock
     e2e_ms = max(ems, ewall)
     if world > 1:
@@ -258,7 +264,7 @@ def run_gpu(args):
                                f"TIMESTEP 3.75 min, GWSTEP 30 min (sat zone every {gw_every}th step), ET/snow off",
                    "cells_per_gpu": n, "stream_cells_per_gpu": n_stream, "sweep_levels": dev.levels(),
                    "l2": "state arrays (54 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
-                   "batch_steps": B,
+                   "batch_steps": B, "timed_steps": windows,
                    "parallelism": "1 GPU" if world == 1 else (
                        f"one basin of {total_cells} cells, {world} reach partitions along the river, NCCL halo exchange "
                        "every step (river inflow, water-table and downslope-state halos), single-step path" if partitioned
