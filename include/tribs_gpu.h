@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TRIBS_GPU_ABI_VERSION 1
+#define TRIBS_GPU_ABI_VERSION 2   /* 2: tribs_et_params_t.hor_angle_0000, tribs_gpu_snow_members */
 
 typedef struct tribs_ctx *tribs_handle_t;
 

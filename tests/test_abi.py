@@ -23,7 +23,9 @@ def test_library_exports_every_declared_symbol(built):
     for nm in names:
         assert hasattr(L, nm), f"{nm} declared in include/tribs_gpu.h but not exported"
     assert sorted(gpu.EXPORTS) == names
-    assert L.tribs_gpu_abi_version() == 1
+    import re as _re
+    want = int(_re.search(r"#define\s+TRIBS_GPU_ABI_VERSION\s+(\d+)", open(f"{ROOT}/include/tribs_gpu.h").read()).group(1))
+    assert L.tribs_gpu_abi_version() == want == 2
 
 
 def test_field_table_matches_between_header_and_binding(built):

@@ -148,6 +148,10 @@ def load():
         raise RuntimeError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'`. "
                            "tribs_b200 has no CPU path.")
     L = C.CDLL(LIB_PATH)
+    want = int(re.search(r"#define\s+TRIBS_GPU_ABI_VERSION\s+(\d+)", open(HEADER).read()).group(1))
+    if L.tribs_gpu_abi_version() != want:      # a library built from an older header: the struct layouts differ
+        raise RuntimeError(f"{LIB_PATH} has ABI version {L.tribs_gpu_abi_version()}, include/tribs_gpu.h has {want}: rebuild "
+                           "(python -c 'import __graft_entry__ as g; g.build()')")
     H = C.c_void_p
     L.tribs_gpu_init.argtypes = [C.POINTER(Mesh), C.POINTER(Params), C.POINTER(StateT), C.POINTER(Part), C.POINTER(H)]
     L.tribs_gpu_step.argtypes = [H, C.c_uint32, C.POINTER(Step)]

@@ -61,6 +61,12 @@ struct TribsGpuBinding {
     p_destroy = (decltype(p_destroy))dlsym(lib, "tribs_gpu_destroy");
     p_err = (decltype(p_err))dlsym(lib, "tribs_gpu_last_error");
     if (!p_init || !p_step || !p_sync || !p_destroy || !p_err) die("dlsym");
+    auto p_abi = (decltype(&tribs_gpu_abi_version))dlsym(lib, "tribs_gpu_abi_version");
+    if (!p_abi || p_abi() != TRIBS_GPU_ABI_VERSION) {       // struct layouts of another header version
+      std::fprintf(stderr, "\nError: tribs_gpu: %s was built for ABI %d, this binding for %d\n", libpath, p_abi ? p_abi() : -1,
+                   TRIBS_GPU_ABI_VERSION);
+      std::exit(2);
+    }
 
     tMeshListIter<tCNode> it(mesh->getNodeList());
     for (tCNode *cn = it.FirstP(); it.IsActive(); cn = it.NextP()) { pos[(tNode *)cn] = (int)cells.size(); cells.push_back(cn); }
