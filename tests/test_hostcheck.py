@@ -235,11 +235,12 @@ def test_et_device_header_option_variants_on_host(variant, built):
     assert hc.calls >= 25
 
 
-def test_snow_device_header_matches_oracle_on_host(built):
+@pytest.mark.parametrize("extra", [{"OPTINTERCEPT": 0}, {"OPTINTERCEPT": 0, "HILLALBOPT": 2}, {"OPTINTERCEPT": 0, "HILLALBOPT": 1}])
+def test_snow_device_header_matches_oracle_on_host(extra, built):
     from refrun import have_harness, run_reference, spec_for
     if not have_harness():
         pytest.skip("oracle/_ref/tribs_ref_harness not built")
-    basin, _, _, _ = run_reference(spec_for("snow", 10, runtime_h=96.0, seed=9, pmean=8.0, extra={"OPTINTERCEPT": 0}))
+    basin, _, _, _ = run_reference(spec_for("snow", 10, runtime_h=96.0, seed=9, pmean=8.0, extra=extra))
     hc = _drive_with_host_check(basin, 96 * 16, tol=1e-9)
     assert hc.calls >= 90
     assert np.abs(hc.o.et.f["CumMelt"]).max() > 0

@@ -131,7 +131,8 @@ def test_host_sun_geometry_and_met_clock_match_reference_bitwise(built):
 
 
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
-@pytest.mark.parametrize("extra", [{}, {"OPTINTERCEPT": 0}, {"HILLALBOPT": 2}, {"GFLUXOPTION": 1}])
+@pytest.mark.parametrize("extra", [{}, {"OPTINTERCEPT": 0}, {"HILLALBOPT": 2}, {"GFLUXOPTION": 1},
+                                   {"OPTINTERCEPT": 0, "HILLALBOPT": 2}, {"OPTINTERCEPT": 1, "HILLALBOPT": 1}])
 def test_oracle_snow_against_live_reference(extra, built):
     """tSnowPack restatement on a fresh winter run (other basin, longer, option variants): bit for bit,
     including the members the reference carries from cell to cell (albedo, Uerr)."""
