@@ -339,6 +339,9 @@ int tribs_gpu_snow_sync(tribs_handle_t h, uint64_t snow_field_mask, double *cons
  * swept cell left them; what a restart has to carry) and the number of probe rounds of the last call
  * (0 without a canopy); either pointer may be NULL */
 int tribs_gpu_snow_members(tribs_handle_t h, double *members, int32_t *probe_rounds);
+/* restart: the snow fields and the two carried members back onto the device (tSnowPack::readRestart's part) */
+int tribs_gpu_snow_push(tribs_handle_t h, uint64_t snow_field_mask, const double *const *host);
+int tribs_gpu_snow_set_members(tribs_handle_t h, const double *members);
 
 #ifdef __cplusplus
 }

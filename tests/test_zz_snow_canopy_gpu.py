@@ -119,3 +119,38 @@ def test_reference_simulator_drives_gpu_snow_path(built):
                      ("SnTempC", 1.0), ("CumMelt", 1e-6), ("CumIntSub", 1e-6), ("PeakSWE", 1e-6), ("SurfTemp", 1.0)):
         err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), floor)
         assert err.max() <= REL_TOL, (f, float(err.max()))
+
+
+def test_gpu_snow_state_round_trips_through_sync_and_push(built):
+    """What a restart needs from the snow path: every snow field and the two carried members can be
+    read (tribs_gpu_snow_sync / _members), written back (tribs_gpu_snow_push / _set_members) into a
+    second instance, and both then advance identically."""
+    from refrun import load_golden
+    from tribs_b200.gpu import ET_FIELDS, SNOW_FIELDS
+    basin, _, _ = load_golden("snow")
+    a, b = GpuStepper(basin, schedule_for(basin)), GpuStepper(basin, schedule_for(basin))
+
+    def step(g, k):
+        for _ in range(k):
+            g.advance(); g.unsat()
+            if g.gw_due():
+                g.sat()
+            g.route(); g.reset()
+
+    step(a, 160)
+    step(b, 160)
+    sn = a.sim.dev.snow_sync(SNOW_FIELDS)
+    members, _ = a.sim.dev.snow_members()
+    assert np.abs(sn["IntSWE"]).max() > 0
+    b.sim.dev.snow_push({k: np.zeros_like(v) for k, v in sn.items()}, members=[0.5, 0.0])     # scramble b ...
+    assert np.array_equal(b.sim.dev.snow_sync(["IntSWE"])["IntSWE"], np.zeros_like(sn["IntSWE"]))
+    b.sim.dev.snow_push(sn, members=members)                                                   # ... and restore it
+    back = b.sim.dev.snow_sync(SNOW_FIELDS)
+    for k in SNOW_FIELDS:
+        assert np.array_equal(back[k], sn[k]), k
+    assert np.array_equal(b.sim.dev.snow_members()[0], members)
+    step(a, 48)
+    step(b, 48)
+    fa, fb = a.get(SNOW_FIELDS + ["LiqWE", "IceWE", "NwtNew"]), b.get(SNOW_FIELDS + ["LiqWE", "IceWE", "NwtNew"])
+    for k in fa:
+        assert np.array_equal(fa[k], fb[k]), k

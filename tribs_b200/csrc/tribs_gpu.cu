@@ -1613,6 +1613,33 @@ extern "C" int tribs_gpu_snow_sync(tribs_handle_t c, uint64_t mask, double *cons
   return 0;
 }
 
+extern "C" int tribs_gpu_snow_push(tribs_handle_t c, uint64_t mask, const double *const *host) {
+  if (!c || !host) return fail("tribs_gpu_snow_push: null argument");
+  if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_push: call tribs_gpu_snow_init first");
+  CK(cudaSetDevice(c->device));
+  for (int k = 0; k < TRIBS_N_SNOW_FIELDS; k++) {
+    if (!(mask & (1ull << k)) || !host[k]) continue;
+    CK(cudaMemcpyAsync(c->d_stage, host[k], (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    scatter_from_sweep_kernel<<<(c->n + 255) / 256, 256, 0, c->stream>>>(c->d_stage, c->d_dev_of_sweep, c->et->snv.f[k], c->n);
+    c->launches++;
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
+extern "C" int tribs_gpu_snow_set_members(tribs_handle_t c, const double *members) {
+  if (!c || !members) return fail("tribs_gpu_snow_set_members: null argument");
+  if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_set_members: call tribs_gpu_snow_init first");
+  EtState *e = c->et;
+  e->members[0] = members[0]; e->members[1] = members[1];
+  if (e->carry.members) {
+    CK(cudaSetDevice(c->device));
+    CK(cudaMemcpyAsync(e->carry.members, e->members, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+  }
+  return 0;
+}
+
 extern "C" int tribs_gpu_snow_members(tribs_handle_t c, double *members, int32_t *probe_rounds) {
   if (!c) return fail("tribs_gpu_snow_members: null argument");
   if (!c->et || !c->et->snow_ready) return fail("tribs_gpu_snow_members: call tribs_gpu_snow_init first");

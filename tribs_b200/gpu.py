@@ -134,6 +134,7 @@ EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retri
            "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
            "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
            "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync", "tribs_gpu_snow_members",
+           "tribs_gpu_snow_push", "tribs_gpu_snow_set_members",
            "tribs_gpu_last_error", "tribs_gpu_abi_version"]
 
 _lib = None
@@ -182,6 +183,8 @@ def load():
     L.tribs_gpu_snow_step.argtypes = [H, C.POINTER(EtStep), C.c_int32]
     L.tribs_gpu_snow_sync.argtypes = [H, C.c_uint64, C.POINTER(PD)]
     L.tribs_gpu_snow_members.argtypes = [H, PD, C.POINTER(C.c_int32)]
+    L.tribs_gpu_snow_push.argtypes = [H, C.c_uint64, C.POINTER(PD)]
+    L.tribs_gpu_snow_set_members.argtypes = [H, PD]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -428,6 +431,19 @@ class GpuBasin:
         m, r = np.zeros(2), C.c_int32(0)
         _chk(self.L.tribs_gpu_snow_members(self.h, _d(m), C.byref(r)))
         return m, int(r.value)
+
+    def snow_push(self, arrays: dict, members=None):
+        """Snow fields (and, optionally, the carried members) back onto the device: a restart."""
+        ptrs = (PD * len(SNOW_FIELDS))()
+        mask, keep = 0, []
+        for nm, a in arrays.items():
+            a = np.ascontiguousarray(a, np.float64); keep.append(a)
+            ptrs[SNF[nm]] = _d(a); mask |= 1 << SNF[nm]
+        if mask:
+            _chk(self.L.tribs_gpu_snow_push(self.h, mask, C.cast(ptrs, C.POINTER(PD))))
+        if members is not None:
+            m = np.ascontiguousarray(members, np.float64)
+            _chk(self.L.tribs_gpu_snow_set_members(self.h, _d(m)))
 
     def snow_sync(self, names) -> dict:
         out = {nm: np.empty(self.n) for nm in names}
