@@ -63,3 +63,19 @@ def test_reference_runs_the_synthetic_bench_basin_and_the_oracle_matches_bitwise
     patched = {k.split("/", 2)[2] for k in z.files if k.startswith("patch/")}
     assert patched <= {"varea", "stream_node", "BasArea", "res_limit"}, patched
     assert z["s128/res/mhydro"].max() > 0 and (z["s128/NfOld"] > 0).any()
+
+
+def test_bench_cpu_legs_run_the_reference_on_the_bench_generator(built):
+    """bench.py's two CPU legs (cpu_baseline of the GPU arm, and --impl reference) at a size the CPU
+    suite affords: both must come from the unmodified reference reading MeshBuilder decks."""
+    import json
+    import bench
+    cb = bench.cpu_baseline_sample(side=40)
+    assert cb["kind"] == "reference" and cb["cores"] == 1 and cb["value"] > 1e4 and "1600 cells" in cb["sample"]
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "3", "--warmup", "2",
+                        "--side", "48"], capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-1500:]
+    line = json.loads(r.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["steps"] == 3 and line["cpu_baseline"]["kind"] == "reference"
+    assert line["value"] == line["e2e"]["value"] > 1e4 and line["cpu_baseline"]["cores"] >= 1
+    assert "4096-cell" in line["cpu_baseline"]["sample"]        # the arm never goes below 64 x 64 cells per process
