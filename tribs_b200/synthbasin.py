@@ -111,56 +111,49 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     dest_node = node_id[J + dj[kb], I + di[kb]]          # -1 = outlet
     is_stream = stream.ravel()[flat_int]
 
-    # depth below each cell to the outlet (pointer jumping) -> topological sweep order
     flow_len = np.stack(elen)[kb, J, I]
-    ptr = dest_node.copy()
-    hops = np.where(ptr >= 0, 1, 0).astype(np.int64)
-    # path to the stream node / to the outlet
-    hill_ptr = np.where(is_stream, -1, dest_node)        # stops at stream cells
-    hill_d = np.where(is_stream, 0.0, flow_len)
-    hill_end = np.where(is_stream, np.arange(n), -1)     # stream node reached
-    # resolve hillslope chains by iterating level by level (depth <= nx)
-    order_depth = np.zeros(n, np.int64)
-    active = ~is_stream
-    cur = np.where(active, dest_node, -1)
-    # iterative relaxation: hillpath[i] = len + hillpath[dest], processed from stream outwards
+    # Hops to the stream (hillslope cells) / to the outlet (stream cells) by pointer doubling: exact integers
+    # in O(n log depth). The path lengths are then accumulated level by level, from the stream outwards,
+    # in the association len_i + (len_{i+1} + ...) - the loops below visit every cell once.
+    def hops_to_root(nxt):
+        """nxt[i] = next cell of the same kind on the path, or -1; returns 1 + number of such successors."""
+        d = np.where(nxt >= -1, 1, 0).astype(np.int64)
+        p = nxt.copy()
+        while True:
+            m = np.flatnonzero(p >= 0)
+            if m.size == 0:
+                return d
+            d[m] += d[p[m]]
+            p[m] = p[p[m]]
+
+    def levels_of(depth_of, members):
+        """members sorted by depth (stable), as a list of index arrays, one per level 1, 2, ..."""
+        o = members[np.argsort(depth_of[members], kind="stable")]
+        dv = depth_of[o]
+        cuts = np.flatnonzero(np.diff(dv)) + 1
+        return np.split(o, cuts)
+
+    dn = np.maximum(dest_node, 0)
+    hill = ~is_stream
+    nxt_h = np.where(hill & (dest_node >= 0) & hill[dn], dest_node, -1)
+    depth = np.where(hill, hops_to_root(nxt_h), 0)
     hillpath = np.zeros(n)
     stream_node = np.where(is_stream, np.arange(n), -1)
-    depth = np.zeros(n, np.int64)
-    pending = np.flatnonzero(~is_stream)
-    guard = 0
-    while pending.size:
-        d = dest_node[pending]
-        ready = (d < 0) | (stream_node[np.maximum(d, 0)] >= 0)
-        r = pending[ready]
+    for r in levels_of(depth, np.flatnonzero(hill)):
         dr = dest_node[r]
         to_outlet = dr < 0
         hillpath[r] = flow_len[r] + np.where(to_outlet, 0.0, hillpath[np.maximum(dr, 0)])
         stream_node[r] = np.where(to_outlet, -2, stream_node[np.maximum(dr, 0)])
-        depth[r] = 1 + np.where(to_outlet, 0, depth[np.maximum(dr, 0)])
-        pending = pending[~ready]
-        guard += 1
-        if guard > 10 * (nx + ny):
-            raise RuntimeError("synthetic basin: flow graph has a cycle")
+    if (stream_node[hill] == -1).any():
+        raise RuntimeError("synthetic basin: flow graph has a cycle")
     stream_node = np.where(stream_node == -2, -1, stream_node)
     # stream cells: distance to outlet along the stream, and order upstream -> downstream
-    sdepth = np.zeros(n, np.int64)
+    nxt_s = np.where(is_stream & (dest_node >= 0) & is_stream[dn], dest_node, -1)
+    sdepth = np.where(is_stream, hops_to_root(nxt_s), 0)
     streampath_s = np.zeros(n)
-    pend = np.flatnonzero(is_stream)
-    done = np.zeros(n, bool)
-    guard = 0
-    while pend.size:
-        d = dest_node[pend]
-        ready = (d < 0) | done[np.maximum(d, 0)]
-        r = pend[ready]
+    for r in levels_of(sdepth, np.flatnonzero(is_stream)):
         dr = dest_node[r]
         streampath_s[r] = flow_len[r] + np.where(dr < 0, 0.0, streampath_s[np.maximum(dr, 0)])
-        sdepth[r] = 1 + np.where(dr < 0, 0, sdepth[np.maximum(dr, 0)])
-        done[r] = True
-        pend = pend[~ready]
-        guard += 1
-        if guard > 10 * (nx + ny):
-            raise RuntimeError("synthetic basin: stream graph has a cycle")
     streampath = np.where(is_stream, streampath_s, streampath_s[np.maximum(stream_node, 0)] * (stream_node >= 0))
     hillpath = np.where(is_stream, 0.0, hillpath)
 
@@ -187,8 +180,9 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     has = fdest >= 0
     # a cell's level = 1 + max level of its contributors; iterate in sweep order chunks by depth
     dd = np.where(is_stream[order], 10 ** 9 - sdepth[order], depth[order].max() + 1 - depth[order])
-    for lev in np.unique(dd):
-        sel = np.flatnonzero((dd == lev) & has)
+    o = np.argsort(dd, kind="stable")
+    o = o[has[o]]
+    for sel in np.split(o, np.flatnonzero(np.diff(dd[o])) + 1):
         np.add.at(contr, fdest[sel], contr[sel])
 
     # spokes CSR (CCW from offset 0), columns remapped to sweep order
