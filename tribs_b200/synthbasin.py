@@ -217,7 +217,6 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     nb_flat = np.stack([np.clip(gJ + dj[k], 0, NY - 1) * NX + np.clip(gI + di[k], 0, NX - 1) for k in range(6)], 1)
     nb_id = np.where(exists, gid[nb_flat], -1)
     owned = exists & (gid[:, None] < nb_id)                # [grid, k]
-    own_g = g_of_id[:, None].repeat(6, 1)                  # rows in id order
     owned_by_id = owned[g_of_id]                           # [id, k]
     pair_rank = np.cumsum(owned_by_id.ravel()) - 1         # file index of the pair, for owned (id, k)
     eid = np.full((NX * NY, 6), -1, np.int64)              # directed edge id per (grid, k)
