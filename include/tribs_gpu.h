@@ -181,6 +181,11 @@ int tribs_gpu_push(tribs_handle_t h, uint64_t field_mask, const tribs_state_t *h
  * for the outlet node in the last slot. `out` has tribs_gpu_n_stream()+1 entries. Consumes
  * the bin at the end of a dtReff interval exactly like the reference. */
 int tribs_gpu_retrieve_qeff(tribs_handle_t h, double current_time, double *out);
+/* The device's form of the per-stream-cell (TimeInd, Qeff) stacks (tKinemat.cpp:1023-1067, what a restart
+ * has to carry for the channel router): out[slot * n_bins + k] = content of the dtReff bin
+ * ceil(current_time / dtReff) + k of stream slot `slot` (slots as for tribs_gpu_retrieve_qeff) after the
+ * ROUTE phase of the step that ended at current_time. */
+int tribs_gpu_pending_qeff(tribs_handle_t h, double current_time, int n_bins, double *out);
 int tribs_gpu_n_stream(tribs_handle_t h);
 int tribs_gpu_stream_cells(tribs_handle_t h, int32_t *sweep_index_out);
 

@@ -60,6 +60,10 @@ class GpuStepper:
         self.sim.flow.SurfaceFlow(True)
         return self.sim.flow.lateral_inflow
 
+    def pending(self, n_bins):
+        """[n_stream, n_bins] dtReff bins from the current one on: the device's (TimeInd, Qeff) stacks."""
+        return self.sim.dev.pending_qeff(self.time, n_bins)[:-1]
+
     def balance(self):
         pass   # tWaterBalance rides on the ROUTE phase of the device path
 
@@ -141,6 +145,16 @@ class OracleStepper:
         q = self.m.retrieve_qeff()
         return np.concatenate([q[self.stream_cells], q[-1:]])
 
+    def pending(self, n_bins):
+        cur = int(math.ceil(self.time / self.m.B.dtReff))
+        out = np.zeros((self.stream_cells.size, n_bins))
+        for k, i in enumerate(self.stream_cells):
+            for tind, q in zip(*self.m.stack_of(int(i))):
+                if not 0 <= tind - cur < n_bins:
+                    raise AssertionError(f"oracle stack of cell {i} holds bin {tind}, current bin {cur}")
+                out[k, tind - cur] = q
+        return out
+
     def balance(self):
         self.m.balance(self.et, getattr(self, "_met_due", False), self.host.metstep if self.et is not None else 1.0)
 
@@ -171,6 +185,7 @@ class Worst:
         self.w = {}
 
     def add(self, key, ref, got, info, floor):
+        ref, got = np.ravel(ref), np.ravel(got)
         e = rel_err(ref, got, floor)
         k = int(np.argmax(e)) if e.size else 0
         v = float(e[k]) if e.size else 0.0
@@ -185,9 +200,32 @@ class Worst:
         return "\n".join(f"  {k}: rel={v[0]:.3e} at {v[1]} cell {v[2]} ref={v[3]!r} got={v[4]!r}" for k, v in rows)
 
 
-def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True):
+QEFF_BINS = 24      # dtReff bins compared from the current one on (hillslope travel times stay far below 12 h here)
+
+
+def reference_stacks(snaps, pre, stream_cells, cur, n_bins=QEFF_BINS):
+    """The reference's (TimeInd, Qeff) stacks of a snapshot (tKinemat.cpp:1023-1067, dumped after
+    tKinemat::SurfaceFlow, i.e. after RetrieveQeff consumed what it consumes) as a dense
+    [n_stream, n_bins] array of dtReff bins cur, cur+1, ..."""
+    slot = {int(c): k for k, c in enumerate(stream_cells)}
+    out = np.zeros((len(stream_cells), n_bins))
+    node, off = snaps[pre + "qeff_node"], snaps[pre + "qeff_off"]
+    tind, val = snaps[pre + "qeff_tind"], snaps[pre + "qeff_val"]
+    for k, c in enumerate(node):
+        for e in range(off[k], off[k + 1]):
+            b = int(tind[e]) - cur
+            if not 0 <= b < n_bins:
+                raise AssertionError(f"reference stack of cell {c} holds bin {tind[e]}, current bin {cur}")
+            out[slot[int(c)], b] = val[e]
+    return out
+
+
+def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True, dt_reff=0.5):
     """Steps `stepper` n_steps times; wherever the reference has a snapshot, compares.
-    Returns a Worst() table keyed by (phase, field)."""
+    Returns a Worst() table keyed by (phase, field). With stack_check, kernel (4)'s own output is
+    compared too: the pending dtReff bins of every stream cell against the reference's stacks and,
+    on the steps where RetrieveQeff (tKinemat.cpp:1504-1551) leaves the current bin in place, the
+    lateral inflow it returned."""
     w = Worst()
     hill = stepper.boundary == 0
     for st in range(1, n_steps + 1):
@@ -221,6 +259,13 @@ def run_and_compare(stepper, snaps, n_steps, floor=1e-9, stack_check=True):
                 if f == "FlowVelocity":   # stream cells are rewritten by the channel router afterwards
                     ref, g = ref[hill], g[hill]
                 w.add(("r", f), ref, g, st, floor)
+            if stack_check and pre + "qeff_node" in snaps:
+                now = stepper.time
+                cur = int(math.ceil(now / dt_reff))
+                ref = reference_stacks(snaps, pre, stepper.stream_cells, cur)
+                w.add(("r", "QeffBins"), ref, stepper.pending(QEFF_BINS), st, 1e-12)
+                if math.ceil(now / dt_reff) != math.floor(now / dt_reff):   # bin not consumed: still at the stack's front
+                    w.add(("r", "Qeff"), ref[:, 0], np.asarray(qeff)[:-1], st, 1e-12)
             for nm in RESULT_ARRAYS:
                 if pre + nm in snaps:
                     w.add(("res", nm), snaps[pre + nm], stepper.result(nm), st, floor)

@@ -148,6 +148,14 @@ __device__ __forceinline__ bool pub_load(const PubWord *p, long long epoch, doub
   return b == epoch;
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+// A consumer that has waited this long (wall time on the device, not a poll count) for an input that
+// never arrives raises the handle's abort flag; the host turns it into an error at the next getter.
+constexpr unsigned long long kSpinTimeoutNs = 60ull * 1000000000ull;
 __device__ __forceinline__ double warp_sum_fixed(double v) {
   // butterfly in a fixed order: the result depends only on the 32 inputs
 #pragma unroll
@@ -184,12 +192,15 @@ unsat_sweep_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const int
         const PubWord *src = pub + up_col[k];
         double v;
         unsigned spins = 0, ns = 32;
+        unsigned long long t_first = 0;
         while (!pub_load(src, epoch, v)) {
           __nanosleep(ns);
           if (ns < 256) ns += ns;
           if (((++spins) & 255u) == 0u) {
             if (*(volatile int32_t *)abort_flag) { v = 0.0; break; }
-            if (spins > (1u << 22)) { atomicExch(abort_flag, 1); v = 0.0; break; }
+            const unsigned long long t_now = global_ns();
+            if (!t_first) t_first = t_now;
+            else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(abort_flag, 1); v = 0.0; break; }
           }
         }
         qpin += v;
@@ -1723,13 +1734,33 @@ extern "C" int tribs_gpu_retrieve_qeff(tribs_handle_t c, double current_time, do
   (void)current_time;  // the ROUTE phase of that step already latched and consumed the bin
   if (!c || !out) return fail("tribs_gpu_retrieve_qeff: null argument");
   CK(cudaSetDevice(c->device));
+  if (check_sweep_abort(c)) return 1;
   CK(cudaMemcpyAsync(out, c->d_qeff_now, (size_t)(c->n_stream + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+// The device's form of the (TimeInd, Qeff) stacks (tKinemat.cpp:1023-1067): out[slot * n_bins + k] is what
+// the dtReff bin ceil(current_time / dtReff) + k of stream slot `slot` holds after the ROUTE phase of
+// the step that ended at current_time (k = 0 is the bin RetrieveQeff reads; it is empty again once it
+// has been consumed at the end of its interval). What a restart has to carry for the channel router.
+extern "C" int tribs_gpu_pending_qeff(tribs_handle_t c, double current_time, int n_bins, double *out) {
+  if (!c || !out || n_bins <= 0) return fail("tribs_gpu_pending_qeff: bad argument");
+  CK(cudaSetDevice(c->device));
+  if (check_sweep_abort(c)) return 1;
+  const int slots = c->n_stream + 1, ring = c->rc.ring;
+  std::vector<double> h((size_t)slots * ring);
+  CK(cudaMemcpyAsync(h.data(), c->d_ring, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  const int cur = (int)ceil(current_time / c->rc.dt_reff);
+  for (int sl = 0; sl < slots; sl++)
+    for (int k = 0; k < n_bins; k++)
+      out[(size_t)sl * n_bins + k] = k < ring ? h[(size_t)sl * ring + ((cur + k) % ring)] : 0.0;
   return 0;
 }
 extern "C" int tribs_gpu_get_results(tribs_handle_t c, int which, double *out, int nbins) {
   if (!c || !out || which < 0 || which >= TRIBS_N_RESULTS) return fail("tribs_gpu_get_results: bad argument");
   CK(cudaSetDevice(c->device));
+  if (check_sweep_abort(c)) return 1;
   nbins = std::min(nbins, (int)c->rc.res_limit);
   CK(cudaMemcpyAsync(out, c->d_results + (size_t)which * c->rc.res_limit, (size_t)nbins * sizeof(double),
                      cudaMemcpyDeviceToHost, c->stream));
@@ -1859,8 +1890,7 @@ extern "C" int tribs_gpu_phase_ms(tribs_handle_t c, double *out4, int reset) {
 extern "C" int tribs_gpu_wait(tribs_handle_t c) {
   if (!c) return fail("tribs_gpu_wait: null handle");
   CK(cudaSetDevice(c->device));
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
+  return check_sweep_abort(c);   // synchronises; a batch that aborted (tribs_gpu_run reports late) fails here
 }
 extern "C" void *tribs_gpu_stream(tribs_handle_t c) { return c ? (void *)c->stream : nullptr; }
 static void tribs_free_pipe(tribs_ctx *c);
@@ -1935,11 +1965,6 @@ __device__ __forceinline__ void st_relaxed_i32(int32_t *p, int v) {
 // cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
 // ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
 struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; unsigned cap_hi_ns, cap_lo_ns; };
-__device__ __forceinline__ unsigned long long global_ns() {
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-  return t;
-}
 __device__ __forceinline__ void release_task(int32_t *cnt, const ReadyQueues &rq, int n_tiles, int p, int tile) {
   const int task = p * n_tiles + tile;
   if (atomicSub(cnt + task, 1) == 1) {
@@ -2000,12 +2025,15 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const
       const int idx = atomicAdd(my_head, 1);
       if (idx < my_total) {
         unsigned spins = 0, ns = 32;
+        unsigned long long t_first = 0;
         while ((task = ld_relaxed_i32(my_queue + idx)) < 0) {   // nothing of my class is ready yet
           __nanosleep(ns);
           if (ns < ns_cap) ns += ns;
-          if (((++spins) & 1023u) == 0u) {
+          if (((++spins) & 255u) == 0u) {
             if (*(volatile int32_t *)abort_flag) { task = -2; break; }
-            if (spins > (1u << 24)) { atomicExch(abort_flag, 1); task = -2; break; }
+            const unsigned long long t_now = global_ns();
+            if (!t_first) t_first = t_now;
+            else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(abort_flag, 1); task = -2; break; }
           }
         }
       } else
@@ -2421,6 +2449,7 @@ extern "C" int tribs_gpu_retrieve_qeff_steps(tribs_handle_t c, int n_steps, doub
   PipeState *ps = pipe_of(c);
   if (n_steps > ps->last_steps) return fail("tribs_gpu_retrieve_qeff_steps: more steps than the last tribs_gpu_run held");
   CK(cudaSetDevice(c->device));
+  if (check_sweep_abort(c)) return 1;
   CK(cudaMemcpyAsync(out, ps->d_qeff_steps, (size_t)n_steps * (c->n_stream + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;

@@ -128,6 +128,7 @@ class SnowParams(C.Structure):
 
 
 EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
+           "tribs_gpu_pending_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
@@ -161,6 +162,7 @@ def load():
     L.tribs_gpu_sync.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_push.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_retrieve_qeff.argtypes = [H, C.c_double, PD]
+    L.tribs_gpu_pending_qeff.argtypes = [H, C.c_double, C.c_int, PD]
     L.tribs_gpu_n_stream.argtypes = [H]
     L.tribs_gpu_stream_cells.argtypes = [H, PI]
     L.tribs_gpu_get_results.argtypes = [H, C.c_int, PD, C.c_int]
@@ -271,9 +273,15 @@ class GpuBasin:
             s.rain_mode = RAIN_UNIFORM
             s.rain_uniform = float(rain)
         else:
+            rain = np.ascontiguousarray(rain, np.float64)      # held until the call returns
+            if rain.size != self.n:
+                raise ValueError(f"rain has {rain.size} entries, the basin has {self.n} cells")
             s.rain_mode = RAIN_PER_CELL
             s.rain = _d(rain)
         if qstrm is not None:
+            qstrm = np.ascontiguousarray(qstrm, np.float64)
+            if qstrm.size != self.n:
+                raise ValueError(f"qstrm has {qstrm.size} entries, the basin has {self.n} cells")
             s.qstrm = _d(qstrm)
         s.qstrm_outlet = qstrm_outlet
         _chk(self.L.tribs_gpu_step(self.h, phases, C.byref(s)))
@@ -474,6 +482,12 @@ class GpuBasin:
     def retrieve_qeff(self, current_time: float) -> np.ndarray:
         out = np.empty(self.n_stream + 1)
         _chk(self.L.tribs_gpu_retrieve_qeff(self.h, current_time, _d(out)))
+        return out
+
+    def pending_qeff(self, current_time: float, n_bins: int) -> np.ndarray:
+        """[n_stream + 1, n_bins]: the dtReff bins from the current one on (the (TimeInd, Qeff) stacks)."""
+        out = np.empty((self.n_stream + 1, n_bins))
+        _chk(self.L.tribs_gpu_pending_qeff(self.h, current_time, n_bins, _d(out)))
         return out
 
     def stream_cells(self) -> np.ndarray:

@@ -215,7 +215,6 @@ class Simulator:
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
         self.step_no = 0
-        self._rain_on_device = None
 
     def UpdatePrecipitationInput(self):
         if self.rain_schedule is None:
@@ -291,11 +290,10 @@ class Simulator:
             if per_cell_rain is not None:
                 per_cell_rain.fill(0.0 if rain is None else rain)
                 rain = per_cell_rain.copy()
-            # a per-cell array object that has not changed since the last upload stays on the device
+            # per-cell arrays are uploaded every step: an identity cache cannot see in-place refills, scalar
+            # steps in between or uploads made by other entry points (a static gauge map + K gauge values per
+            # step is the cheap form of spatially varying rain, see tribs_gpu_set_rain_gauges)
             step_rain = rain
-            if isinstance(rain, np.ndarray) and per_cell_rain is None:
-                step_rain = None if rain is self._rain_on_device else rain
-                self._rain_on_device = rain
             if et_on:
                 met_due, eti_due = self.met_clock.due(now)
                 if met_due or eti_due:

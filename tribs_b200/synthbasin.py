@@ -119,12 +119,14 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         """nxt[i] = next cell of the same kind on the path, or -1; returns 1 + number of such successors."""
         d = np.where(nxt >= -1, 1, 0).astype(np.int64)
         p = nxt.copy()
-        while True:
+        # pointer doubling reaches every root within ceil(log2 n) + 1 rounds; more means a cycle
+        for _ in range(int(np.ceil(np.log2(max(nxt.size, 2)))) + 2):
             m = np.flatnonzero(p >= 0)
             if m.size == 0:
                 return d
             d[m] += d[p[m]]
             p[m] = p[p[m]]
+        raise RuntimeError("synthetic basin: flow graph has a cycle")
 
     def levels_of(depth_of, members):
         """members sorted by depth (stable), as a list of index arrays, one per level 1, 2, ..."""
