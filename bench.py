@@ -79,6 +79,71 @@ def storm_rain(t, pmean=20.0, stdur=6.0, istdur=18.0):
 
 
 # -------------------------------------------------------------------------------- GPU arm
+WORKLOAD = {
+    2: "synthetic V-valley TIN, uniform storm 20 mm/h, TIMESTEP 3.75 min, GWSTEP 30 min, ET/snow off",
+    3: "synthetic V-valley TIN, rain gauges + weather station, Penman-Monteith ET + Rutter interception every "
+       "METSTEP 60 min, TIMESTEP 3.75 min, GWSTEP 30 min",
+}
+
+
+def self_check(rank, world, steps=32, side=120):
+    """N > 1, before anything is timed: the `world` ranks advance a basin of side x side*world cells together
+    (peer-memory halos, pipelined batches) and rank 0 compares every owned cell value, the hydrograph arrays, the
+    basin accumulators and the per-step lateral inflows with ONE GPU running the same partition layout.
+    Bit equality or the run stops (the reference's serial == MPI contract, test_big_spring.py:5-22)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from tribs_b200.model import Simulator
+    from tribs_b200.partition import cell_owner
+    from tribs_b200.peers import PeerSimulator
+    from tribs_b200.synthbasin import build_basin
+    fields = ["NwtOld", "MuOld", "MiOld", "NtOld", "NfOld", "RuOld", "RiOld", "Qpout", "intstorm", "srf_hr", "cumsrf",
+              "SoilMoisture", "RootMoisture", "AvSoilMoisture", "Recharge", "RechDisch", "esrf", "Transmissivity", "TTime",
+              "UnSaturatedStorage", "SaturatedStorage", "gwchange", "satsrfOccur", "sbsrfOccur"]
+    results = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "rmax", "rmin", "frac", "msm", "msmRt",
+               "msmU", "mgw", "sat", "qunsat"]
+    basin = build_basin(side, side * world, seed=2, runtime_h=48.0, gw_depth_mm=900.0)
+    owner = cell_owner(basin, world)
+    rain = lambda t: 25.0 if t <= 1.0 else 0.0      # storm, then the first dry steps (every column changes state)
+    ps = PeerSimulator(basin, rank, world, owner=owner, max_batch_steps=16)
+    q = []
+    for _ in range(steps // 16):
+        ps.run_batch(16, rain_of_time=rain)
+        q.append(ps.dev.retrieve_qeff_steps(16))
+    got = ps.gather(fields)
+    lim = int(basin["res_limit"][0])
+    res = {nm: ps.dev.results(nm, lim) for nm in results}
+    glob = ps.dev.globals()
+    bad = []
+    if rank == 0:
+        ref = Simulator(basin, part=dict(rank=0, nranks=1, cell_owner=owner))
+        qr = []
+        for _ in range(steps // 16):
+            ref.run_batch(16, rain_of_time=rain, collect_qeff=True)
+            qr.append(ref.batch_qeff)
+        want = ref.dev.sync(fields)
+        bad += [f for f in fields if not np.array_equal(want[f], got[f])]
+        bad += [nm for nm in results if not np.array_equal(ref.dev.results(nm, lim), res[nm])]
+        g1 = ref.dev.globals()
+        bad += [k for k in ("Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "BasinRain", "BasinRunoff") if g1[k] != glob[k]]
+        if not np.array_equal(np.concatenate(qr), np.concatenate(q)):
+            bad.append("qeff_steps")
+        if not (np.abs(want["cumsrf"]).max() > 0 and np.abs(res["mhydro"]).max() > 0):
+            bad.append("no runoff produced: the check is vacuous")
+        ref.dev.close()
+    flag = torch.tensor([float(len(bad))], device="cuda")
+    dist.broadcast(flag, src=0)
+    ps.dev.close()
+    info = {"cells": int(basin["n_active"][0]), "ranks": world, "steps": steps, "fields": len(fields), "result_arrays": len(results),
+            "bitwise_equal_to_one_gpu": not bad, "different": bad}
+    if rank == 0:
+        print("bench.py self-check: " + json.dumps(info), file=sys.stderr, flush=True)
+    if flag.item() != 0:
+        raise SystemExit("bench.py: the partitioned run differs from the one-GPU run; refusing to time it")
+    return info
+
+
 def run_gpu(args):
     import numpy as np
     import torch
@@ -97,29 +162,32 @@ def run_gpu(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     side = args.side
+    B = max(1, min(args.batch, args.steps))
+    runtime_h = 24.0 + (args.warmup + 2 * args.steps + 64) * 0.0625
+    check = None
     partitioned = world > 1 and args.mgpu == "partition"
     if partitioned:
-        # ONE basin over all GPUs: a valley `world` times as long, cut into reach partitions along the
-        # river; every rank holds the static data of the whole basin and advances the cells it owns
-        from tribs_b200.parallel import PartitionedSimulator
-        side = args.side_mgpu
-        basin = build_basin(side, side * world, seed=1, runtime_h=1e9, stream_every=args.stream_every)
-        psim = PartitionedSimulator(basin, rank, world, rain_schedule=storm_rain)
-        dev = psim.dev
-        n = int((psim.owner == rank).sum())
-        sim = None
+        # ONE basin over all GPUs: a valley `world` times as long (side x side*world cells, side^2 per GPU), cut
+        # into reach partitions along the river; boundary values travel through peer memory inside the batch kernel
+        from tribs_b200.partition import cell_owner
+        from tribs_b200.peers import PeerSimulator
+        if not args.no_self_check:
+            check = self_check(rank, world)
+        basin = build_basin(side, side * world, seed=1, runtime_h=runtime_h, stream_every=args.stream_every)
+        owner = cell_owner(basin, world)
+        sim = PeerSimulator(basin, rank, world, owner=owner, max_batch_steps=B)
+        n = int((owner == rank).sum())
+        sim.advance = lambda: sim.timer.Advance(sim.timer.getTimeStep())
     else:
-        basin = build_basin(side, side, seed=1 + rank, runtime_h=1e9, stream_every=args.stream_every)
+        basin = build_basin(side, side, seed=1 + rank, runtime_h=runtime_h, stream_every=args.stream_every)
         n = int(basin["n_active"][0])
         sim = Simulator(basin, rain_schedule=None)
-        dev = sim.dev
+    dev = sim.dev
     gw_every = int(round(dev.gwstep / dev.tstep))
     stream = torch.cuda.ExternalStream(dev.stream_handle())
     n_stream = dev.n_stream
     n_host = dev.n      # cells in the arrays the host exchanges with this rank
-
-    pinned_rain = torch.empty(n_host, dtype=torch.float64).pin_memory()
-    rain_np = pinned_rain.numpy()
+    dev.reserve_batch(B)      # the batch buffers exist before anything is timed
 
     def barrier():
         torch.cuda.synchronize()
@@ -127,32 +195,14 @@ def run_gpu(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def resident_step():
-        if partitioned:
-            psim.one_step()
-            return
-        sim.advance()
-        t = sim.timer.getCurrentTime()
-        dev.step(0, t, sim.timer.getElapsedSteps(t), 0, rain=storm_rain(t))   # tRainfall::NewRain(double)
-        sim.SubSurfaceHydroProcesses()
-        sim.flow.SurfaceFlow(fetch_qeff=False)
-        sim.hydro.Reset()
-
-    def e2e_step():
-        if partitioned:
-            return psim.one_step(rain_cells=rain_np, fetch=True)
-        sim.advance()
-        t = sim.timer.getCurrentTime()
-        rain_np.fill(storm_rain(t))            # the host model's per-cell rain (tRainfall::NewRain)
-        dev.step(0, t, sim.timer.getElapsedSteps(t), 0, rain=rain_np)
-        sim.SubSurfaceHydroProcesses()
-        sim.flow.SurfaceFlow(fetch_qeff=True)  # D2H: lateral inflow for the channel router
-        g = dev.globals()                       # D2H: basin accumulators
-        sim.hydro.Reset()
-        return g
-
-    B = 1 if partitioned else max(1, args.batch)   # pipelined batches are single-GPU for now
-    pinned_rows = torch.empty((B, n_host), dtype=torch.float64).pin_memory() if B > 1 else None
+    # e2e forcing: the host hands over one value per rain gauge and step (tRainfall's gauge input, RAINSOURCE 3;
+    # the Thiessen map cell -> gauge is static and lives on the device), from pinned host memory
+    n_gauges = 16
+    bx, by = np.asarray(basin["x"]), np.asarray(basin["y"])
+    gx = np.minimum((4 * (bx - bx.min()) / max(np.ptp(bx), 1e-9)).astype(np.int32), 3)
+    gy = np.minimum((4 * (by - by.min()) / max(np.ptp(by), 1e-9)).astype(np.int32), 3)
+    dev.set_rain_gauges((gy * 4 + gx).astype(np.int32), n_gauges)
+    pinned_rows = torch.empty((B, n_gauges), dtype=torch.float64).pin_memory()
 
     def host_steps(k, rows=None):
         t = sim.timer
@@ -163,7 +213,7 @@ def run_gpu(args):
             r = storm_rain(now)
             if rows is not None:
                 rows[q].fill_(r)
-                r = rows[q].numpy()
+                r = gpu.GaugeRain(rows[q].numpy())
             out.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
                             hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
                             sat=bool(sim.gw_on and not math.fmod(now, t.getGWTimeStep())), rain=r))
@@ -173,16 +223,12 @@ def run_gpu(args):
         dev.run(host_steps(k))
 
     def e2e_batch(k):
-        dev.run(host_steps(k, pinned_rows))      # H2D: k per-cell rain arrays
+        dev.run(host_steps(k, pinned_rows))      # H2D: k x n_gauges rain values
         q = dev.retrieve_qeff_steps(k)           # D2H: per-step lateral inflow for the channel router
         g = dev.globals()                         # D2H: basin accumulators
         return q, g
 
-    def loop(fn_single, fn_batch, k):
-        if B <= 1:
-            for _ in range(k):
-                fn_single()
-            return
+    def loop(fn_batch, k):
         done = 0
         while done < k:
             kk = min(B, k - done)
@@ -206,32 +252,35 @@ def run_gpu(args):
             ms = float(tt.item())
         return ms, (w1 - w0) * 1e3
 
-    loop(resident_step, resident_batch, args.warmup)
+    # warm-up, then `value` and `e2e` over the SAME simulated steps (warmup+1 .. warmup+steps, what the reference
+    # arm times too): the state after the warm-up is kept on the device and restored between the two legs
+    loop(resident_batch, args.warmup)
+    dev.wait()
+    dev.snapshot()
+    t_mark = sim.timer.currentTime
     dev.set_timing(True)
     dev.phase_ms(reset=True)
     sampler = ClockSampler(local)
     sampler.start()
     l0 = dev.launch_count()
-    ms, wall_ms = timed(lambda k: loop(resident_step, resident_batch, k), args.steps)
+    ms, wall_ms = timed(lambda k: loop(resident_batch, k), args.steps)
     launches = dev.launch_count() - l0
     clocks = sampler.stop()
     phases = dev.phase_ms(reset=True)
     dev.set_timing(False)
-    # dominant kernel: the sweep (single steps) or the pipelined batch kernel, which runs the
-    # unsaturated sweep of every step and the saturated zone of every gw_every-th step
-    n_launch = args.steps if B <= 1 else math.ceil(args.steps / B)
+    # dominant kernel: the pipelined batch kernel, which runs the unsaturated sweep of every step and the
+    # saturated zone of every gw_every-th step
+    n_launch = math.ceil(args.steps / B)
     unsat_ms = phases["unsat"] / max(n_launch, 1)
     steps_per_launch = args.steps / n_launch
-    bytes_per_launch = n * steps_per_launch * (UNSAT_BYTES_PER_CELL + (SAT_BYTES_PER_CELL / gw_every if B > 1 else 0.0))
+    bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every
+    bytes_per_launch = n * steps_per_launch * bytes_per_cell_step
 
-    e2e_warm = max(3, args.warmup // 2)
-    loop(e2e_step, e2e_batch, e2e_warm)
-    ems, ewall = timed(lambda k: loop(e2e_step, e2e_batch, k), args.steps)
-    # which simulated steps each number covers: the storm (20 mm/h) ends at step 96 and the first dry steps are the
-    # expensive ones (most columns change state), so the two windows are not equally hard
+    dev.rollback()
+    sim.timer.currentTime = t_mark
+    ems, ewall = timed(lambda k: loop(e2e_batch, k), args.steps)
     v0 = args.warmup + 1
-    e0 = args.warmup + args.steps + e2e_warm + 1
-    windows = {"value": [v0, v0 + args.steps - 1], "e2e": [e0, e0 + args.steps - 1], "storm_ends_at_step": 96}
+    windows = {"value": [v0, v0 + args.steps - 1], "e2e": [v0, v0 + args.steps - 1], "storm_ends_at_step": 96}
     # host work (numpy fill, ctypes) is part of the user-visible e2e time: use the wall clock
     e2e_ms = max(ems, ewall)
     if world > 1:
@@ -249,39 +298,41 @@ def run_gpu(args):
     e2e = total_cells * args.steps / (e2e_ms * 1e-3)
     peak, peak_kind = peaks()
     achieved = bytes_per_launch / (unsat_ms * 1e-3) / 1e9 if unsat_ms > 0 else 0.0
-    traffic = None      # DRAM bytes of one launch from the committed ncu capture, if it is of this configuration
+    traffic = None      # DRAM bytes of one launch: bytes per cell-timestep of the committed ncu capture x this launch's units
     try:
-        tr = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01_traffic.json")))["pipeline_kernel"]
-        if B > 1 and tr["cells"] == n and tr["steps_per_launch"] == int(steps_per_launch):
-            traffic = tr["dram_bytes_read"] + tr["dram_bytes_write"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))["pipeline_kernel"]
+        traffic = tr["dram_bytes_per_cell_step"] * n * steps_per_launch
     except (OSError, KeyError, ValueError):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"synthetic {total_cells / world / 1e6:.2f}M-cell V-valley TIN per GPU, uniform storm 20 mm/h, "
-                               f"TIMESTEP 3.75 min, GWSTEP 30 min (sat zone every {gw_every}th step), ET/snow off",
-                   "cells_per_gpu": n, "stream_cells_per_gpu": n_stream, "sweep_levels": dev.levels(),
+        "config": {"workload": WORKLOAD[2],
+                   "cells_per_gpu": n, "total_cells": total_cells, "stream_cells": n_stream, "sweep_levels": dev.levels(),
                    "l2": "state arrays (54 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
                    "batch_steps": B, "timed_steps": windows,
                    "parallelism": "1 GPU" if world == 1 else (
-                       f"one basin of {total_cells} cells, {world} reach partitions along the river, NCCL halo exchange "
-                       "every step (river inflow, water-table and downslope-state halos), single-step path" if partitioned
+                       f"one basin of {total_cells} cells, {world} reach partitions along the river (one per GPU, "
+                       f"{n} cells each), pipelined batches of {B} steps; river inflow, water-table and downslope-state "
+                       "halos stored into peer memory by the batch kernel, dependent work released with system-scope "
+                       "atomics over NVLink (no host exchange, no NCCL on the data path)" if partitioned
                        else f"{world} independent basin replicas, no exchange")},
-        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_host,
-                "d2h_bytes_per_step": 8 * (n_stream + 1) + 8 * len(gpu.GLOBALS)},
+        "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": 8 * n_gauges * world,
+                "d2h_bytes_per_step": (8 * (n_stream + 1) + 8 * len(gpu.GLOBALS)) * world},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "pipeline_kernel" if B > 1 else "unsat_sweep_kernel", "achieved": achieved, "peak": peak,
+        "roofline": {"bound": "hbm", "kernel": "pipeline_kernel", "achieved": achieved, "peak": peak,
                      "unit": "GB/s", "frac": achieved / peak if peak else None, "traffic": traffic,
-                     "peak_source": peak_kind, "bytes_per_cell_step": UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every,
+                     "peak_source": peak_kind, "bytes_per_cell_step": bytes_per_cell_step,
                      "avg_launch_ms": unsat_ms, "steps_per_launch": steps_per_launch,
-                     "note": "not HBM-bound: bound by instruction delivery (74 % of the working warps' stall samples are "
-                             "no_instruction) and, once per storm, by the ridge-to-river dependency chain "
-                             f"({dev.levels()} levels) of the slow post-storm step; see DESIGN.md 4.2"},
+                     "note": "not HBM-bound: a dependency-chained FP64 state machine; bound by instruction issue of the working "
+                             f"warps and by the ridge-to-outlet chain ({dev.levels()} levels) at the start and end of a batch; "
+                             "see DESIGN.md 4.2"},
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
+    if check is not None:
+        line["self_check"] = check
     if world == 1 and not args.no_et_kernel:
         line["kernels"] = {"et_cells_kernel": time_et_kernel(dev, basin, n, stream, peak)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -502,8 +553,7 @@ def run_reference_arm(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "synthetic V-valley TIN, uniform storm 20 mm/h, TIMESTEP 3.75 min, GWSTEP 30 min, "
-                                   "ET/snow off (bounded CPU sample of the GPU arm's workload)"},
+            "config": {"workload": WORKLOAD[2], "sample": "bounded CPU sample of the GPU arm's workload, see cpu_baseline"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -512,16 +562,14 @@ def run_reference_arm(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=128)
-    ap.add_argument("--warmup", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="tribs_b200", choices=["tribs_b200", "reference"])
     ap.add_argument("--side", type=int, default=1000, help="cells per side of the synthetic basin (per GPU)")
-    ap.add_argument("--batch", type=int, default=64,
-                    help="steps per pipelined launch (tribs_gpu_run); 1 = one tribs_gpu_step sequence per step")
+    ap.add_argument("--batch", type=int, default=256, help="steps per pipelined launch (tribs_gpu_run), at most --steps")
     ap.add_argument("--mgpu", default="partition", choices=["partition", "replicas"],
                     help="N>1: one reach-partitioned basin with halo exchange (default) or independent replicas")
-    ap.add_argument("--side-mgpu", type=int, default=500, help="N>1, partition mode: cells across the valley; "
-                    "the basin is side x side*N cells, i.e. side^2 per GPU")
+    ap.add_argument("--no-self-check", action="store_true", help="N>1: skip the bit-equality check against one GPU")
     ap.add_argument("--stream-every", type=int, default=0, help="tributary stream row every K rows (0: one river, "
                     "hillslopes as long as half the basin width)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TRIBS_GPU_ABI_VERSION 2   /* 2: tribs_et_params_t.hor_angle_0000, tribs_gpu_snow_members */
+#define TRIBS_GPU_ABI_VERSION 3   /* 3: tribs_part_t (peer-memory partitions), rain gauges, tribs_gpu_pending_qeff */
 
 typedef struct tribs_ctx *tribs_handle_t;
 
@@ -100,11 +100,24 @@ typedef struct {
   double *f[TRIBS_N_FIELDS];
 } tribs_state_t;
 
-/* ------------------------------------------------------------------ multi-GPU partition (optional) */
+/* ------------------------------------------------------------------ multi-GPU partition (optional)
+ * Replaces, for this path, tGraph's reach partition and tParallel's messages (src/tGraph/tGraph.cpp:401-608,
+ * 2035-2155, 2431-2479; src/tParallel/tParallel.cpp:195-246). cell_owner[i] is the partition of sweep cell i
+ * (tCNode::getReach() through reach2partition). Cells are laid out partition by partition; every basin sum is
+ * formed per partition and the partitions are added in partition order, so a run over nranks GPUs is
+ * bit-identical to a run of the same partition layout on one GPU (nranks == 1, n_parts > 1).
+ * With nranks > 1 every rank is initialised with the whole basin and advances the cells of partition `rank`;
+ * boundary values (lateral outflow of reach outlets, the state a remote upslope cell or Voronoi neighbour
+ * reads) are stored straight into the peers' device memory by the kernels and dependent work on a peer is
+ * released with system-scope atomics over NVLink: no host exchange inside tribs_gpu_run. The ranks make
+ * their memory known to each other once, through tribs_gpu_ipc_export / tribs_gpu_attach_peers (one process
+ * per GPU; the host moves the 64-byte handles with whatever it has - MPI_Allgather in the reference's
+ * tParallel, torch.distributed here) or tribs_gpu_attach_local (several handles in one process). */
 typedef struct {
-  int32_t rank, nranks;
-  const void *nccl_unique_id;   /* 128-byte ncclUniqueId shared by all ranks, NULL for nranks==1 */
-  const int32_t *cell_owner;    /* [n_cells_global] owning rank of every cell of the global basin */
+  int32_t rank, nranks;         /* this handle's partition among nranks GPUs; nranks == 1: one GPU runs all partitions */
+  int32_t n_parts;              /* partitions in cell_owner; must equal nranks when nranks > 1 */
+  int32_t max_batch_steps;      /* nranks > 1: largest n_steps of tribs_gpu_run (its buffers are exported once) */
+  const int32_t *cell_owner;    /* [n_cells] partition of every cell of the basin */
 } tribs_part_t;
 
 /* ------------------------------------------------------------------ stepping */
@@ -118,7 +131,9 @@ enum {
   TRIBS_PHASE_UNSAT_REMOTE = 32  /* cells downstream of a cell owned by another rank */
 };
 
-enum { TRIBS_RAIN_KEEP = 0, TRIBS_RAIN_UNIFORM = 1, TRIBS_RAIN_PER_CELL = 2 };
+/* GAUGES: tRainfall's gauge forcing (RAINSOURCE 3, src/tRasTin/tRainfall.cpp:305-391): `rain` holds one value per
+ * gauge, every cell takes the value of its gauge (tribs_gpu_set_rain_gauges: the static Thiessen map) */
+enum { TRIBS_RAIN_KEEP = 0, TRIBS_RAIN_UNIFORM = 1, TRIBS_RAIN_PER_CELL = 2, TRIBS_RAIN_GAUGES = 3 };
 
 typedef struct {
   double current_time;      /* tRunTimer::getCurrentTime() after Advance(), hours */
@@ -129,7 +144,7 @@ typedef struct {
   int32_t rain_mode;        /* TRIBS_RAIN_* : tRainfall::NewRain for this step */
   int32_t reserved;
   double rain_uniform;      /* mm/h, rain_mode == UNIFORM */
-  const double *rain;       /* host [n] mm/h, rain_mode == PER_CELL */
+  const double *rain;       /* host [n] mm/h, rain_mode == PER_CELL; host [n_gauges], rain_mode == GAUGES */
   const double *qstrm;      /* host [n] tCNode::Qstrm (stream cells) or NULL: only read if flowexp>0 */
   double qstrm_outlet;      /* OutletNode->getQstrm() */
 } tribs_step_t;
@@ -193,12 +208,28 @@ int tribs_gpu_stream_cells(tribs_handle_t h, int32_t *sweep_index_out);
 int tribs_gpu_get_results(tribs_handle_t h, int which, double *out, int n);
 int tribs_gpu_get_globals(tribs_handle_t h, double *out /* TRIBS_N_GLOBALS */);
 
-/* ---- partitioned runs: one reach partition per GPU (reference: tGraph, src/tGraph/tGraph.cpp:401-608,
- * 1657-1724; the MPI messages sendQpin / sendOverlap / sendNwt become the three halo kinds below).
- * Every rank is initialised with the WHOLE basin and then told which cells it owns
- * (cell_owner[i] = rank of sweep cell i, from the reach partition). It advances only those; the
- * host moves the values of boundary cells between ranks: pack on the owner, NCCL send/recv of the
- * buffer, unpack on the reader. idx_dev / buf_dev are DEVICE pointers; idx holds device-order
+/* The static part of gauge rainfall: cell_gauge[i] = index of the rain gauge whose Thiessen polygon holds
+ * sweep cell i (tRainfall::setRainInput's nearest-station search / the .sdf station list). Afterwards a step
+ * with rain_mode GAUGES uploads n_gauges values instead of n_cells. */
+int tribs_gpu_set_rain_gauges(tribs_handle_t h, int32_t n_gauges, const int32_t *cell_gauge);
+
+/* ---- partitioned runs, peer memory (tribs_part_t.nranks > 1). After tribs_gpu_init on every rank:
+ * tribs_gpu_ipc_export fills the 64-byte handle of this rank's exported memory; the host gathers the handles
+ * of all ranks (rank order) and passes them to tribs_gpu_attach_peers on every rank. tribs_gpu_attach_local
+ * is the same for `nranks` handles that live in one process (they may share a device: each then uses
+ * 1/n of its SMs' resident blocks). tribs_gpu_run then advances all partitions together: every rank calls it
+ * with the same steps; it returns without waiting (peers are awaited on the device). The hydrograph arrays,
+ * basin accumulators and per-step lateral inflows are complete on every rank after the call. */
+#define TRIBS_IPC_HANDLE_BYTES 64
+int tribs_gpu_ipc_export(tribs_handle_t h, void *handle_out /* TRIBS_IPC_HANDLE_BYTES */);
+int tribs_gpu_attach_peers(tribs_handle_t h, const void *handles /* nranks x TRIBS_IPC_HANDLE_BYTES, rank order */);
+int tribs_gpu_attach_local(const tribs_handle_t *handles, int nranks);
+/* device-index range [begin, end) of the cells this handle advances (the whole basin unless nranks > 1) */
+int tribs_gpu_owned_range(tribs_handle_t h, int32_t *begin, int32_t *end);
+
+/* ---- partitioned runs, single steps with a host exchange (the reference's own message pattern: sendQpin /
+ * sendOverlap / sendNwt become the three halo kinds below, moved by the host with NCCL between
+ * pack on the owner and unpack on the reader). idx_dev / buf_dev are DEVICE pointers; idx holds device-order
  * indices (tribs_gpu_device_index). Kinds: QPOUT = new lateral outflow of a reach outlet (1 value,
  * unpack also marks it as published for the REMOTE pass of the sweep), STATE = the 7 New state
  * values of cells that others read as their downslope cell, NWT = NwtNew of Voronoi neighbours
@@ -209,6 +240,19 @@ int tribs_gpu_halo_pack(tribs_handle_t h, int kind, const int32_t *idx_dev, int 
 int tribs_gpu_halo_unpack(tribs_handle_t h, int kind, const int32_t *idx_dev, int n, const double *buf_dev);
 int tribs_gpu_set_global(tribs_handle_t h, int which, double value);   /* e.g. psrf_last from its owner */
 int tribs_gpu_padded_cells(tribs_handle_t h);
+
+/* ---- state of a handle
+ * tribs_gpu_snapshot keeps one device-side copy of everything the path evolves (all dynamic, ET, snow fields,
+ * pending hillslope inflow bins, tFlowResults arrays, basin accumulators); tribs_gpu_rollback returns to it.
+ * tribs_gpu_save_state / tribs_gpu_load_state write / read the same content as a binary checkpoint on a step
+ * boundary (what tRestart / tCNode::writeRestart do for this path, src/tSimulator/tRestart.cpp; per-cell arrays
+ * in sweep order, so the file does not depend on the partition layout).
+ * tribs_gpu_reserve_batch sizes the buffers of tribs_gpu_run for n_steps ahead of the first batch. */
+int tribs_gpu_snapshot(tribs_handle_t h);
+int tribs_gpu_rollback(tribs_handle_t h);
+int tribs_gpu_save_state(tribs_handle_t h, const char *path);
+int tribs_gpu_load_state(tribs_handle_t h, const char *path);
+int tribs_gpu_reserve_batch(tribs_handle_t h, int n_steps);
 
 /* Introspection used by tests and the bench. */
 int tribs_gpu_sweep_levels(tribs_handle_t h);            /* depth of the Qpin dependency DAG */

@@ -4,7 +4,7 @@ import numpy as np, torch
 from tribs_b200.model import Simulator
 from tribs_b200.synthbasin import build_basin
 side=int(sys.argv[1]); B=int(sys.argv[2]); reps=int(sys.argv[3])
-b=build_basin(side,side,runtime_h=1e9)
+b=build_basin(side,side,runtime_h=240.0)
 sim=Simulator(b, rain_schedule=lambda t: 20.0 if t<=6 else 0.0)
 dev=sim.dev
 for r in range(reps):

@@ -32,7 +32,7 @@ def _ptab(arrs, T):
 
 def main(lib, side, n_steps):
     L = C.CDLL(lib)
-    b = build_basin(side, side, seed=1, runtime_h=1e9)
+    b = build_basin(side, side, seed=1, runtime_h=240.0)
     n = int(b["n_active"][0])
     m = OracleModel(b, storm_rain)
     alpha = np.arctan(b["flow_slope"])

@@ -13,7 +13,7 @@ os.makedirs("gpurun_out", exist_ok=True)
 from tribs_b200.model import Simulator  # noqa: E402
 from tribs_b200.synthbasin import build_basin  # noqa: E402
 
-basin = build_basin(side, side, seed=1, runtime_h=1e9)
+basin = build_basin(side, side, seed=1, runtime_h=240.0)
 sim = Simulator(basin, rain_schedule=lambda t: 20.0 if (t % 24.0) <= 6.0 else 0.0)
 sim.run_batch(B)
 os.environ["TRIBS_TRACE"] = path

@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     assert sorted(gpu.EXPORTS) == names
     import re as _re
     want = int(_re.search(r"#define\s+TRIBS_GPU_ABI_VERSION\s+(\d+)", open(f"{ROOT}/include/tribs_gpu.h").read()).group(1))
-    assert L.tribs_gpu_abi_version() == want == 2
+    assert L.tribs_gpu_abi_version() == want == 3
 
 
 def test_field_table_matches_between_header_and_binding(built):

@@ -30,7 +30,7 @@ def main():
     from tribs_b200.model import Simulator
     from tribs_b200.synthbasin import build_basin
     t0 = time.perf_counter()
-    basin = build_basin(a.side, a.side, seed=1, runtime_h=1e9, stream_every=0)
+    basin = build_basin(a.side, a.side, seed=1, runtime_h=240.0, stream_every=0)
     sim = Simulator(basin, rain_schedule=None)
     dev, t = sim.dev, sim.timer
     setup_s = time.perf_counter() - t0

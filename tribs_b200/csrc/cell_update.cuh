@@ -44,10 +44,12 @@ struct StepConst {
   double dt, dt_gw, now, elapsed;   // elapsed = (double)tRunTimer::getElapsedSteps(now)
   int32_t hourly_reset;
   double psrf_last;                 // psrf of the last swept cell (read by the saturated zone)
-  // forcing applied inside the sweep (pipelined batches): 0 keep the Rain array, 1 uniform, 2 per cell
+  // forcing applied inside the sweep (pipelined batches): 0 keep the Rain array, 1 uniform, 2 per cell,
+  // 3 per rain gauge (rain_cells = the step's gauge values, rain_gauge = gauge of every cell)
   int32_t rain_mode = 0;
   double rain_uniform = 0.0;
   const double *rain_cells = nullptr;   // device order
+  const int32_t *rain_gauge = nullptr;  // device order
   int32_t defer_esrf = 0;           // SAT: leave the raw satsrf in esrf, psrf_last is added later
 };
 
@@ -128,7 +130,7 @@ TRIBS_HD void unsat_cell_load(UnsatCellInputs &u, const StaticView &s, const Dyn
   double rain_i;
   if (t.rain_mode == 0) rain_i = d.f[TRIBS_F_Rain][i];
   else {
-    rain_i = (t.rain_mode == 1) ? t.rain_uniform : t.rain_cells[i];
+    rain_i = (t.rain_mode == 1) ? t.rain_uniform : ((t.rain_mode == 2) ? t.rain_cells[i] : t.rain_cells[t.rain_gauge[i]]);
     d.f[TRIBS_F_Rain][i] = rain_i;   // tRainfall::NewRain
   }
   double evsoi = d.f[TRIBS_F_EvapSoil][i], evveg = d.f[TRIBS_F_EvapDryCanopy][i];

@@ -30,6 +30,7 @@
 #include <string.h>
 #include <math.h>
 #include <algorithm>
+#include <chrono>
 #include <numeric>
 #include <string>
 #include <vector>
@@ -65,10 +66,39 @@ struct RouteConst {
   int32_t res_limit, ring;
 };
 
+constexpr int kMaxParts = 16;
+// Memory other ranks map (cudaIpc) or address directly (several handles in one process): one allocation per
+// handle, carved by a bump allocator in the same order on every rank, so an address on a peer is
+// peer_base + (my_address - my_base).
+struct Slab { char *base = nullptr; size_t cap = 0, used = 0; };
+// hillslope routing entries of one partition (see route_seg_kernel)
+struct SegPart {
+  int32_t *cell = nullptr, *slot = nullptr;
+  double *path = nullptr, *area = nullptr;
+  struct SegBoundary *bnd = nullptr;
+  int n_seg = 0, blocks = 0;
+};
 struct PipeState;
 struct tribs_ctx {
   int device = 0;
+  // partitions (tribs_part_t): cells are laid out partition by partition; sums are formed per partition
+  int n_parts = 1, n_ranks = 1;
+  std::vector<int> part_begin, part_end;     // device-index range of every partition (tile aligned)
+  std::vector<int> my_parts;                 // partitions this handle computes
+  int own_begin = 0, own_end = 0;            // device-index range this handle computes
+  std::vector<int32_t> sweep_owner;          // partition of every sweep cell (empty: one partition)
+  Slab slab{};
+  std::vector<SegPart> seg_parts;
+  int tile_bins = 1, rec_stride = 15;        // per-tile routing record: 14 + 5 * tile_bins doubles
+  double *d_tile_rec = nullptr;              // [n_own_tiles][rec_stride] single-step routing records
+  double *d_part_vec = nullptr, *d_block_part = nullptr, *d_sums_part = nullptr;
+  struct StepBins *d_stepbins = nullptr;     // single-step routing: output bins of the step
+  int32_t *d_one = nullptr;                  // device constant 1
+  int32_t *d_gauge_of_cell = nullptr;        // device order, tribs_gpu_set_rain_gauges
+  double *d_gauge_vals = nullptr;
+  int n_gauges = 0;
   PipeState *pipe = nullptr;   // pipelined-batch state (tribs_gpu_run), created on first use
+  struct StateSnapshot *snap = nullptr;   // tribs_gpu_snapshot
   struct EtState *et = nullptr; // kernel (1) state (tribs_gpu_et_init)
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
   int max_degree = 0, segment_cells = 0;
@@ -85,6 +115,7 @@ struct tribs_ctx {
   // partitioned runs (one reach partition per GPU)
   int32_t *d_owned = nullptr, *d_tiles_local = nullptr, *d_tiles_remote = nullptr;
   int n_tiles_local = 0, n_tiles_remote = 0, rank = 0;
+  bool topo_order = true;     // ascending tile index is a topological order of the lateral-flow DAG
   bool partitioned = false;
   int n_hi_tiles = 0;
   PubWord *d_pub = nullptr;
@@ -94,12 +125,9 @@ struct tribs_ctx {
   double *d_stage = nullptr;
   int32_t *d_flags = nullptr;  // [0] gather overflow
   // routing
-  int32_t *d_seg_cell = nullptr, *d_seg_slot = nullptr, *d_sn_dev = nullptr;
-  double *d_seg_path = nullptr, *d_seg_area = nullptr;
-  SegBoundary *d_seg_bnd = nullptr;
-  int n_seg = 0, seg_blocks = 0;
-  double *d_ring = nullptr, *d_qeff_now = nullptr, *d_results = nullptr, *d_route_part = nullptr;
-  int route_blocks = 0, route_window = 0;
+  int32_t *d_sn_dev = nullptr;
+  double *d_ring = nullptr, *d_qeff_now = nullptr, *d_results = nullptr;
+  int route_window = 0;
   RouteConst rc{};
   ModelConst mc{};
   int last_sweep_dev = -1;   // device index of the last cell in sweep order
@@ -123,6 +151,16 @@ static int dev_alloc(tribs_ctx *c, T **p, size_t count) {
   CK(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
   c->allocs.push_back(q);
   *p = (T *)q;
+  return 0;
+}
+// memory peers address: from the slab when the handle has one (nranks > 1), else an ordinary allocation
+template <class T>
+static int shared_alloc(tribs_ctx *c, T **p, size_t count) {
+  if (!c->slab.base) return dev_alloc(c, p, count);
+  const size_t bytes = ((std::max<size_t>(count, 1) * sizeof(T)) + 255) & ~(size_t)255;
+  if (c->slab.used + bytes > c->slab.cap) { g_err = "internal: exported memory slab too small"; return 1; }
+  *p = (T *)(c->slab.base + c->slab.used);
+  c->slab.used += bytes;
   return 0;
 }
 template <class T>
@@ -233,28 +271,6 @@ __global__ void unsat_late_qpin_kernel(DynView d, const int32_t *late_rowptr, co
   if (late_rowptr[i + 1] > late_rowptr[i]) d.f[TRIBS_F_Qpin][i] = q;
 }
 
-// fixed-order reduction of per-tile partials: one block, each thread strides, then a shared tree
-__global__ void __launch_bounds__(256)
-reduce_sums_kernel(const double *__restrict__ tile_sums, int n_tiles, int width, double *globals,
-                   int g0, int g1, int g2, int g3) {
-  __shared__ double sh[4][256];
-  double acc[4] = {0, 0, 0, 0};
-  for (int tix = threadIdx.x; tix < n_tiles; tix += 256)
-    for (int k = 0; k < width; k++) acc[k] += tile_sums[width * tix + k];
-  for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = acc[k];
-  __syncthreads();
-  for (int o = 128; o > 0; o >>= 1) {
-    if (threadIdx.x < o)
-      for (int k = 0; k < 4; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
-    __syncthreads();
-  }
-  if (threadIdx.x == 0) {
-    int g[4] = {g0, g1, g2, g3};
-    for (int k = 0; k < width; k++)
-      if (g[k] >= 0) globals[g[k]] += sh[k][0];
-  }
-}
-
 // ------------------------------------------------------------------------------------ SAT
 __global__ void __launch_bounds__(256)
 sat_prepare_kernel(StaticView s, DynView d, double *wt_elev, double *transm, int n_pad) {
@@ -322,7 +338,7 @@ __global__ void __launch_bounds__(kSegBlock)
 route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restrict__ seg_cell,
                  const int32_t *__restrict__ seg_slot, const double *__restrict__ seg_path,
                  const double *__restrict__ seg_area, const int32_t *__restrict__ slot_dev, int n_seg, double now,
-                 double qstrm_outlet, double *ring, SegBoundary *bnd) {
+                 double qstrm_outlet, const double *__restrict__ srf_of_cell, double *ring, SegBoundary *bnd) {
   __shared__ long long sh_key_last[32], sh_key_first[32];
   __shared__ double sh_acc_last[32], sh_carry[32];
   __shared__ int sh_single[32];
@@ -340,7 +356,7 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
     const double tt = seg_path[e] / hv / 3600.;
     const int bin = (int)ceil((now + tt) / dtreff);
     key = ((long long)slot << 32) | (unsigned)bin;
-    const double srf = d.f[TRIBS_F_srf][seg_cell[e]];
+    const double srf = srf_of_cell[seg_cell[e]];   // the live array, or a per-step snapshot of it (batches)
     if (srf > 0.0 && !(srf > 999999) && s.owned[seg_cell[e]]) {
       double vr = srf * seg_area[e] / 1000.;
       v = (bin == cur) ? vr / same_box_div : vr / (dtreff * 3600.);
@@ -392,12 +408,11 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
   }
 }
 
-// sequential stitch of the block-boundary runs (block order = entry order), then latch what the
-// channel router reads this step and consume the bin at the end of a dtReff interval
-// (tKinemat::RetrieveQeff, tKinemat.cpp:1504-1551)
+// sequential stitch of the block-boundary runs (block order = entry order) of one partition; the
+// latch of what the channel router reads (tKinemat::RetrieveQeff, tKinemat.cpp:1504-1551) follows in
+// route_latch_kernel once every partition has added its runs
 __global__ void __launch_bounds__(1024)
-route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n_blocks, int n_slots, double now,
-                       double *ring, double *qeff_now) {
+route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n_blocks, double *ring) {
   // The records are staged through shared memory 512 at a time (coalesced loads); one thread
   // merges them in order into a list of finished (key, sum) runs -- sequential by nature but free
   // of global memory -- and then all threads add the finished runs to the rings in parallel (the
@@ -440,161 +455,231 @@ route_seg_fixup_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd, int n
       ring[(size_t)slot * rc.ring + (bin % rc.ring)] += sh_out_val[k];
     }
   }
-  __threadfence();
-  __syncthreads();
+}
+// what the channel router reads this step; the bin is consumed at the end of its dtReff interval
+__global__ void __launch_bounds__(256)
+route_latch_kernel(RouteConst rc, int n_slots, double now, double *ring, double *qeff_now) {
   const int cur = (int)ceil(now / rc.dt_reff);
   const bool at_end = ((int)ceil(now / rc.dt_reff) == (int)floor(now / rc.dt_reff));
-  for (int k = threadIdx.x; k < n_slots; k += blockDim.x) {
-    double *p = ring + (size_t)k * rc.ring + (cur % rc.ring);
-    qeff_now[k] = *p;
-    if (at_end) *p = 0.0;
-  }
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_slots) return;
+  double *p = ring + (size_t)k * rc.ring + (cur % rc.ring);
+  qeff_now[k] = *p;
+  if (at_end) *p = 0.0;
 }
 
 // (3) per-cell tail of RunHydrologicRouting (FlowVelocity, travel time; tKinemat.cpp:958-970,
-//     1084) fused with the tFlowNet::SurfaceFlow accumulations (tFlowNet.cpp:758-865).
-//     Stage 1: a fixed grid; block b owns the 256-cell chunks b, b+G, b+2G ... and reduces them
-//     into [window] volume bins x 5 runoff types + 10 basin means, deterministically (per-warp
-//     slabs filled lane by lane, slabs added in warp order). Stage 2: one warp per output value
-//     sums the G block partials in a fixed order into the tFlowResults arrays.
+//     1084) fused with the tFlowNet::SurfaceFlow accumulations (tFlowNet.cpp:758-865) and tWaterBalance.
+//     Every 32-cell tile leaves one record per step: 13 basin terms (sums by a fixed butterfly, max, min)
+//     and its runoff volumes x 5 types in the `K` output bins from its first one on (the cells of a tile are
+//     of one (segment, depth) bucket, so their travel times are close; K is planned at init). The records
+//     are written by the last task of a tile in its step (pipelined batches: no per-cell snapshot of 15
+//     fields any more) or by route_tiles_kernel (single steps), then reduced in a fixed order:
+//     tiles -> blocks of a partition (tile_reduce_kernel) -> partition (part_reduce_kernel) -> partitions
+//     in partition order (combine_results_kernel). The grouping depends on the partition layout only, so
+//     one GPU and N GPUs give the same bits.
 constexpr int kRouteWarps = 8;
 constexpr int kMeans = 13;  // crr frac msm msmRt msmU sat mgw qunsat rmax rmin + basin rain/evap/runoff volumes
+constexpr int kRecBins = 14;          // record layout: [0..12] the terms above, [13] first bin (-1: no runoff), then [5][K]
+constexpr int kReduceBlocksMax = 64;
 // tWaterBalance (tWaterBalance.cpp:116-345) rides on this sweep: it sits at the same place in the
 // reference's step (Simulator::UpdateWaterBalance, after SurfaceFlow, before Reset) and reads the
-// same end-of-step fields. `d` may hold per-step snapshots of some fields (batches); the
-// storages are always the live arrays.
+// same end-of-step fields.
 struct WaterBalanceArgs {
   double *uns_storage, *sat_storage;   // tCNode::UnSaturatedStorage / SaturatedStorage
   const double *evapotrans;            // tCNode::EvapoTranspiration (kernel 1), or nullptr
   double gwstep_h;
   int32_t gw_time;                     // fmod(currentTime, GWSTEP) == 0
 };
+struct PartVecs { const double *v[kMaxParts]; int n; };
+struct StepBins { int32_t bin_base, cur_bin; };
+struct RouteStep {
+  double now, qstrm_outlet, hv_last;
+  int32_t gw_time;       // Simulator::GW_label == 0 (tSimul.cpp:511)
+  int32_t satsrf_zero;   // batches: a step without a saturated-zone phase has no groundwater runoff (no Reset() in between)
+};
+
+// one warp = one tile; `rec` (lane 0 writes) has 14 + 5K doubles
+__device__ __forceinline__ void route_tile_record(const StaticView &s, const DynView &d, const RouteConst &rc,
+                                                  const ModelConst &m, const WaterBalanceArgs &wb, const RouteStep &rs,
+                                                  int i, bool act, int lane, int K, double *rec, int32_t *flags) {
+  double vol[5] = {0, 0, 0, 0, 0};
+  int init = 0, end = -1;
+  double w_init = 0, w_mid = 0, w_end = 0;
+  double means[kMeans];
+#pragma unroll
+  for (int k = 0; k < kMeans; k++) means[k] = 0.0;
+  const double now = rs.now;
+  if (act) {
+    const int bnd = s.boundary[i];
+    const double area = s.varea[i], areaf = area / m.bas_area_flow;
+    const double srf = d.f[TRIBS_F_srf][i];
+    const double dcalc = rc.tstep, dres = rc.output_interval, sec = rc.output_interval * 3600.0;
+    double tt = d.f[TRIBS_F_TTime][i];
+    if (bnd == 0) {
+      const double hv = hill_velocity(s, d, rc, s.stream_node[i], rs.qstrm_outlet);
+      d.f[TRIBS_F_FlowVelocity][i] = hv;
+      if (srf > 0.0) { tt = s.hillpath[i] / hv / 3600.; d.f[TRIBS_F_TTime][i] = tt; }
+    } else
+      d.f[TRIBS_F_FlowVelocity][i] = rs.hv_last;
+    if (srf > 0.0) {
+      if (rc.flowexp > 0.0) {
+        const double hv0 = rc.velcoef / rc.velratio, sv0 = rc.velcoef;
+        tt = (s.hillpath[i] / hv0 + s.streampath[i] / sv0) / 3600.0;
+        d.f[TRIBS_F_TTime][i] = tt;
+      }
+      vol[0] = srf * area / 1000.0;
+      vol[1] = d.f[TRIBS_F_hsrf][i] * area / 1000.0;
+      vol[2] = d.f[TRIBS_F_sbsrf][i] * area / 1000.0;
+      vol[3] = d.f[TRIBS_F_psrf][i] * area / 1000.0;
+      vol[4] = rs.satsrf_zero ? 0.0 : d.f[TRIBS_F_satsrf][i] * area / 1000.0;
+      init = (int)floor((tt + .01 * dcalc + now) / dres);
+      end = (int)floor((tt + .99 * dcalc + now) / dres);
+      if (init == end) w_init = 1.0 / sec;
+      else {
+        const double dint = (init + 1) * dres - (now + tt);
+        w_init = dint / dcalc / sec;
+        if (end - init == 1) w_end = (dcalc - dint) / dcalc / sec;
+        else {
+          w_mid = dres / dcalc / sec;
+          w_end = ((now + tt + dcalc) - end * dres) / dcalc / sec;
+        }
+      }
+    }
+    const double w = rc.tstep / rc.output_interval;
+    const double rain = d.f[TRIBS_F_Rain][i];
+    double cs = s.cos_gw[i];
+    if (cs < 1E-9) cs = 1.E-9;
+    means[0] = areaf * rain * rc.tstep / rc.output_interval;
+    means[1] = (rain > 0.0) ? areaf * w : 0.0;
+    means[2] = areaf * d.f[TRIBS_F_SoilMoistureSC][i] * w;
+    means[3] = areaf * d.f[TRIBS_F_RootMoistureSC][i] * w;
+    means[4] = areaf * d.f[TRIBS_F_SoilMoistureUNSC][i] * w;
+    means[5] = (d.f[TRIBS_F_SoilMoistureSC][i] >= 1) ? areaf * w : 0.0;
+    means[6] = areaf * (d.f[TRIBS_F_NwtNew][i] / cs) * w;
+    means[7] = areaf * (d.f[TRIBS_F_Qpout][i] - d.f[TRIBS_F_Qpin][i]) * 1.E-6 / area * w;
+    means[8] = rain;
+    means[9] = rain;
+    {   // UnSaturatedBalance / SaturatedBalance / BasinStorage for this cell
+      const double uns_min = rc.tstep * 60.0, sat_min = wb.gwstep_h * 60.0, rech = d.f[TRIBS_F_Recharge][i];
+      const double melt = d.f[TRIBS_F_LiqRouted][i] * 10.0;
+      double inf = d.f[TRIBS_F_NetPrecipitation][i];
+      inf = (d.f[TRIBS_F_LiqWE][i] + d.f[TRIBS_F_IceWE][i] > 1e-4) ? melt : inf + melt;
+      const double et = d.f[TRIBS_F_EvapSoil][i] + d.f[TRIBS_F_EvapDryCanopy][i];
+      const double del_u = inf + d.f[TRIBS_F_UnSatFlowIn][i] - d.f[TRIBS_F_UnSatFlowOut][i] - rech - et - srf / uns_min;
+      wb.uns_storage[i] = wb.uns_storage[i] + del_u * (uns_min / 60.0) * area / 1000.0;
+      if (rs.gw_time) {
+        const double del_g = 0.0 - 0.0 + (rech - srf / sat_min) * area / 1000.0;
+        wb.sat_storage[i] = wb.sat_storage[i] + del_g * (sat_min / 60.0);
+      }
+      const double a = area / 1000.0;
+      means[10] = rain * a * uns_min / 60.0;
+      means[11] = (wb.evapotrans ? wb.evapotrans[i] : 0.0) * a * uns_min / 60.0;
+      means[12] = srf * a;
+    }
+  }
+  // the sums: fixed-order butterfly; min/max: order free
+#pragma unroll
+  for (int k = 0; k < 8; k++) means[k] = warp_sum_fixed(means[k]);
+  double mx = act ? means[8] : -1.0e300, mn = act ? means[9] : 1.0e300;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
+  }
+#pragma unroll
+  for (int k = 10; k < kMeans; k++) means[k] = warp_sum_fixed(means[k]);
+  means[8] = mx; means[9] = mn;
+  if (lane == 0) {
+#pragma unroll
+    for (int k = 0; k < kMeans; k++) rec[k] = means[k];
+  }
+  // binned volumes of the runoff-producing lanes, from the tile's first bin on
+  const bool has = act && end >= init;
+  int b0 = has ? init : 0x7fffffff, b1 = has ? end : -0x7fffffff;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    b0 = min(b0, __shfl_xor_sync(0xffffffffu, b0, o));
+    b1 = max(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+  }
+  if (b0 == 0x7fffffff) {
+    if (lane == 0) rec[13] = -1.0;
+    return;
+  }
+  if (b1 - b0 >= K) {   // more bins than planned at init: the run must not go on silently
+    if (lane == 0) flags[1] = 1;
+    b1 = b0 + K - 1;
+  }
+  if (lane == 0) rec[13] = (double)b0;
+  for (int k = 0; k < K; k++) {
+    const int b = b0 + k;
+    double wgt = 0.0;
+    if (has && b >= init && b <= end) wgt = (b == init) ? w_init : ((b == end) ? w_end : w_mid);
+    const bool any = b <= b1;       // uniform
+#pragma unroll
+    for (int q = 0; q < 5; q++) {
+      // value * fraction / seconds in the reference; fraction / seconds folded into one weight here
+      const double v = any ? warp_sum_fixed(vol[q] * wgt) : 0.0;
+      if (lane == 0) rec[kRecBins + q * K + k] = v;
+    }
+  }
+}
+
+// single steps: one warp per tile of this handle's range
+__global__ void __launch_bounds__(128)
+route_tiles_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, WaterBalanceArgs wb, RouteStep rs, int cell_begin,
+                   int n_tiles, int last_hill_dev, int K, double *recs, double *globals, int32_t *flags) {
+  const int lane = threadIdx.x & 31;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (t >= n_tiles) return;
+  // velocity the stream cells inherit: that of the last hillslope cell in sweep order
+  rs.hv_last = last_hill_dev >= 0 ? hill_velocity(s, d, rc, s.stream_node[last_hill_dev], rs.qstrm_outlet)
+                                  : rc.velcoef / rc.velratio;
+  if (t == 0 && lane == 0) globals[TRIBS_G_hillvel_last] = rs.hv_last;
+  const int i = cell_begin + t * kTile + lane;
+  const bool act = s.boundary[i] >= 0 && s.owned[i];
+  route_tile_record(s, d, rc, m, wb, rs, i, act, lane, K, recs + (size_t)t * (kRecBins + 5 * K), flags);
+}
+
+// records of one partition's tiles -> G block partials per step. Block (g, step): warp w takes the tiles
+// g*8+w, g*8+w+8G, ... of the partition in that order and adds their records into its shared slab (lanes
+// over the record's entries); the slabs are added in warp order. part[(step*G + g)*stride + k].
 __global__ void __launch_bounds__(kRouteWarps * 32)
-route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, double now, double qstrm_outlet,
-                          int n_pad, int window, int bin_base, int last_hill_dev, double *part, double *globals,
-                          WaterBalanceArgs wb) {
+tile_reduce_kernel(const double *__restrict__ recs, size_t step_stride, int tile0, int n_tiles, int K, int window,
+                   const StepBins *__restrict__ sb, double *part, int32_t *flags) {
   extern __shared__ double sh[];  // [kRouteWarps][5*window + kMeans]
-  const int stride = 5 * window + kMeans;
+  const int stride = 5 * window + kMeans, R = kRecBins + 5 * K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int G = gridDim.x, g = blockIdx.x, step = blockIdx.y;
   double *slab = sh + warp * stride;
   for (int k = lane; k < stride; k += 32) slab[k] = 0.0;
   if (lane == 0) { slab[5 * window + 8] = -1.0e300; slab[5 * window + 9] = 1.0e300; }
   __syncwarp();
-  // velocity the stream cells inherit: that of the last hillslope cell in sweep order
-  const double hv_last = last_hill_dev >= 0 ? hill_velocity(s, d, rc, s.stream_node[last_hill_dev], qstrm_outlet)
-                                            : rc.velcoef / rc.velratio;
-  if (blockIdx.x == 0 && threadIdx.x == 0) globals[TRIBS_G_hillvel_last] = hv_last;
-  const int n_chunks = (n_pad + blockDim.x - 1) / blockDim.x;
-  for (int chunk = blockIdx.x; chunk < n_chunks; chunk += gridDim.x) {
-    const int i = chunk * blockDim.x + threadIdx.x;
-    const int bnd = (i < n_pad) ? s.boundary[i] : -1;
-    const bool act = bnd >= 0 && s.owned[i];
-    double vol[5] = {0, 0, 0, 0, 0};
-    int init = 0, end = -1;
-    double w_init = 0, w_mid = 0, w_end = 0;
-    double means[kMeans];
-    for (int k = 0; k < kMeans; k++) means[k] = 0.0;
-    if (act) {
-      const double area = s.varea[i], areaf = area / m.bas_area_flow;
-      const double srf = d.f[TRIBS_F_srf][i];
-      const double dcalc = rc.tstep, dres = rc.output_interval, sec = rc.output_interval * 3600.0;
-      double tt = d.f[TRIBS_F_TTime][i];
-      if (bnd == 0) {
-        const double hv = hill_velocity(s, d, rc, s.stream_node[i], qstrm_outlet);
-        d.f[TRIBS_F_FlowVelocity][i] = hv;
-        if (srf > 0.0) { tt = s.hillpath[i] / hv / 3600.; d.f[TRIBS_F_TTime][i] = tt; }
-      } else
-        d.f[TRIBS_F_FlowVelocity][i] = hv_last;
-      if (srf > 0.0) {
-        if (rc.flowexp > 0.0) {
-          const double hv0 = rc.velcoef / rc.velratio, sv0 = rc.velcoef;
-          tt = (s.hillpath[i] / hv0 + s.streampath[i] / sv0) / 3600.0;
-          d.f[TRIBS_F_TTime][i] = tt;
-        }
-        vol[0] = srf * area / 1000.0;
-        vol[1] = d.f[TRIBS_F_hsrf][i] * area / 1000.0;
-        vol[2] = d.f[TRIBS_F_sbsrf][i] * area / 1000.0;
-        vol[3] = d.f[TRIBS_F_psrf][i] * area / 1000.0;
-        vol[4] = d.f[TRIBS_F_satsrf][i] * area / 1000.0;
-        init = (int)floor((tt + .01 * dcalc + now) / dres);
-        end = (int)floor((tt + .99 * dcalc + now) / dres);
-        if (init == end) w_init = 1.0 / sec;
-        else {
-          const double dint = (init + 1) * dres - (now + tt);
-          w_init = dint / dcalc / sec;
-          if (end - init == 1) w_end = (dcalc - dint) / dcalc / sec;
-          else {
-            w_mid = dres / dcalc / sec;
-            w_end = ((now + tt + dcalc) - end * dres) / dcalc / sec;
-          }
+  const int bin_base = sb[step].bin_base;
+  const double *base = recs + (size_t)step * step_stride;
+  for (int t = g * kRouteWarps + warp; t < n_tiles; t += G * kRouteWarps) {
+    const double *rec = base + (size_t)(tile0 + t) * R;
+    if (lane < kMeans) {
+      const double v = rec[lane];
+      double *dst = slab + 5 * window + lane;
+      if (lane == 8) *dst = fmax(*dst, v);
+      else if (lane == 9) *dst = fmin(*dst, v);
+      else *dst += v;
+    }
+    const double b0d = rec[13];
+    if (b0d >= 0.0) {
+      const int off0 = (int)b0d - bin_base;
+      for (int e = lane; e < 5 * K; e += 32) {
+        const int q = e / K, k = e - q * K;
+        const double v = rec[kRecBins + e];
+        if (v != 0.0) {
+          const int off = off0 + k;
+          if (off < 0 || off >= window) flags[1] = 1;
+          else slab[q * window + off] += v;
         }
       }
-      const double w = rc.tstep / rc.output_interval;
-      const double rain = d.f[TRIBS_F_Rain][i];
-      double cs = s.cos_gw[i];
-      if (cs < 1E-9) cs = 1.E-9;
-      means[0] = areaf * rain * rc.tstep / rc.output_interval;
-      means[1] = (rain > 0.0) ? areaf * w : 0.0;
-      means[2] = areaf * d.f[TRIBS_F_SoilMoistureSC][i] * w;
-      means[3] = areaf * d.f[TRIBS_F_RootMoistureSC][i] * w;
-      means[4] = areaf * d.f[TRIBS_F_SoilMoistureUNSC][i] * w;
-      means[5] = (d.f[TRIBS_F_SoilMoistureSC][i] >= 1) ? areaf * w : 0.0;
-      means[6] = areaf * (d.f[TRIBS_F_NwtNew][i] / cs) * w;
-      means[7] = areaf * (d.f[TRIBS_F_Qpout][i] - d.f[TRIBS_F_Qpin][i]) * 1.E-6 / area * w;
-      means[8] = rain;
-      means[9] = rain;
-      {   // UnSaturatedBalance / SaturatedBalance / BasinStorage for this cell
-        const double uns_min = rc.tstep * 60.0, sat_min = wb.gwstep_h * 60.0, rech = d.f[TRIBS_F_Recharge][i];
-        const double melt = d.f[TRIBS_F_LiqRouted][i] * 10.0;
-        double inf = d.f[TRIBS_F_NetPrecipitation][i];
-        inf = (d.f[TRIBS_F_LiqWE][i] + d.f[TRIBS_F_IceWE][i] > 1e-4) ? melt : inf + melt;
-        const double et = d.f[TRIBS_F_EvapSoil][i] + d.f[TRIBS_F_EvapDryCanopy][i];
-        const double del_u = inf + d.f[TRIBS_F_UnSatFlowIn][i] - d.f[TRIBS_F_UnSatFlowOut][i] - rech - et - srf / uns_min;
-        wb.uns_storage[i] = wb.uns_storage[i] + del_u * (uns_min / 60.0) * area / 1000.0;
-        if (wb.gw_time) {
-          const double del_g = 0.0 - 0.0 + (rech - srf / sat_min) * area / 1000.0;
-          wb.sat_storage[i] = wb.sat_storage[i] + del_g * (sat_min / 60.0);
-        }
-        const double a = area / 1000.0;
-        means[10] = rain * a * uns_min / 60.0;
-        means[11] = (wb.evapotrans ? wb.evapotrans[i] : 0.0) * a * uns_min / 60.0;
-        means[12] = srf * a;
-      }
     }
-    // the 8 sums: fixed-order butterfly; min/max: order free
-#pragma unroll
-    for (int k = 0; k < 8; k++) means[k] = warp_sum_fixed(means[k]);
-    double mx = act ? means[8] : -1.0e300, mn = act ? means[9] : 1.0e300;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-      mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, o));
-    }
-#pragma unroll
-    for (int k = 10; k < kMeans; k++) means[k] = warp_sum_fixed(means[k]);
-    if (lane == 0) {
-      for (int k = 0; k < 8; k++) slab[5 * window + k] += means[k];
-      for (int k = 10; k < kMeans; k++) slab[5 * window + k] += means[k];
-      slab[5 * window + 8] = fmax(slab[5 * window + 8], mx);
-      slab[5 * window + 9] = fmin(slab[5 * window + 9], mn);
-    }
-    // binned volumes: only runoff-producing lanes take part, lowest lane first (fixed order)
-    unsigned todo = __ballot_sync(0xffffffffu, act && end >= init);
-    while (todo) {
-      const int l = __ffs(todo) - 1;
-      todo &= todo - 1;
-      if (lane == l) {
-        for (int b = init; b <= end; b++) {
-          const int off = b - bin_base;
-          if (off < 0 || off >= window) continue;
-          // value*fraction/seconds in the reference; fraction/seconds folded into one weight here
-          const double wgt = (b == init) ? w_init : ((b == end) ? w_end : w_mid);
-          for (int k = 0; k < 5; k++)
-            if (vol[k] != 0.0) slab[k * window + off] += vol[k] * wgt;
-        }
-      }
-      __syncwarp();
-    }
+    __syncwarp();
   }
   __syncthreads();
   for (int k = threadIdx.x; k < stride; k += blockDim.x) {
@@ -602,21 +687,22 @@ route_basin_stage1_kernel(StaticView s, DynView d, RouteConst rc, ModelConst m, 
     if (k == 5 * window + 8) { for (int wv = 1; wv < kRouteWarps; wv++) acc = fmax(acc, sh[wv * stride + k]); }
     else if (k == 5 * window + 9) { for (int wv = 1; wv < kRouteWarps; wv++) acc = fmin(acc, sh[wv * stride + k]); }
     else { for (int wv = 1; wv < kRouteWarps; wv++) acc += sh[wv * stride + k]; }
-    part[(size_t)blockIdx.x * stride + k] = acc;
+    part[((size_t)step * G + g) * stride + k] = acc;
   }
 }
 
+// G block partials -> the partition's vector of a step: one warp per value, fixed order
 __global__ void __launch_bounds__(256)
-route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int window, int bin_base, int cur_bin,
-                          int limit, double *results, double *globals) {
+part_reduce_kernel(const double *__restrict__ part, int G, int window, int n_steps, double *vec) {
   const int stride = 5 * window + kMeans;
   const int lane = threadIdx.x & 31;
-  const int k = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // one warp per output value
-  if (k >= stride) return;
+  const long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= (long long)n_steps * stride) return;
+  const int step = (int)(w / stride), k = (int)(w - (long long)step * stride);
   const bool is_max = (k == 5 * window + 8), is_min = (k == 5 * window + 9);
   double acc = is_max ? -1.0e300 : (is_min ? 1.0e300 : 0.0);
-  for (int b = lane; b < n_blocks; b += 32) {
-    const double v = part[(size_t)b * stride + k];
+  for (int b = lane; b < G; b += 32) {
+    const double v = part[((size_t)step * G + b) * stride + k];
     acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
   }
 #pragma unroll
@@ -624,20 +710,78 @@ route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int win
     const double v = __shfl_xor_sync(0xffffffffu, acc, o);
     acc = is_max ? fmax(acc, v) : (is_min ? fmin(acc, v) : acc + v);
   }
-  if (lane != 0) return;
-  if (k < 5 * window) {
-    const int type = k / window, bin = bin_base + (k % window);
-    if (bin >= 0 && bin < limit && acc != 0.0) results[(size_t)type * limit + bin] += acc;
-  } else if (k >= 5 * window + 10) {
-    globals[TRIBS_G_BasinRain + (k - 5 * window - 10)] += acc;
-  } else if (cur_bin >= 0 && cur_bin < limit) {
-    const int q = k - 5 * window;
-    const int map[10] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
-                             TRIBS_R_sat, TRIBS_R_mgw, TRIBS_R_qunsat, TRIBS_R_rmax, TRIBS_R_rmin};
+  if (lane == 0) vec[(size_t)step * stride + k] = acc;
+}
+
+// The partitions' vectors, added in partition order, go into the tFlowResults arrays step by step
+// (tFlowResults::store_* 857-1161; what tParallel::sum/min/max do in write_inter_hyd 531-561, with a fixed
+// order). vec[r] may live on another rank. One thread per (runoff type, output bin) and one per basin term.
+__global__ void __launch_bounds__(256)
+combine_results_kernel(PartVecs pv, const StepBins *__restrict__ sb, int n_steps, int window, int limit, int bin_lo,
+                       int n_bins, double *results, double *globals) {
+  const int stride = 5 * window + kMeans;
+  const int tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid < 5 * n_bins) {
+    const int type = tid / n_bins, bin = bin_lo + tid - type * n_bins;
+    if (bin < 0 || bin >= limit) return;
+    double acc = results[(size_t)type * limit + bin];
+    for (int st = 0; st < n_steps; st++) {
+      const int off = bin - sb[st].bin_base;
+      if (off < 0 || off >= window) continue;
+      double tot = 0.0;
+      for (int r = 0; r < pv.n; r++) tot += pv.v[r][(size_t)st * stride + type * window + off];
+      if (tot != 0.0) acc += tot;
+    }
+    results[(size_t)type * limit + bin] = acc;
+    return;
+  }
+  const int q = tid - 5 * n_bins;
+  if (q >= kMeans) return;
+  const int map[10] = {TRIBS_R_crr, TRIBS_R_frac, TRIBS_R_msm, TRIBS_R_msmRt, TRIBS_R_msmU,
+                       TRIBS_R_sat, TRIBS_R_mgw, TRIBS_R_qunsat, TRIBS_R_rmax, TRIBS_R_rmin};
+  for (int st = 0; st < n_steps; st++) {
+    double tot = (q == 8) ? -1.0e300 : ((q == 9) ? 1.0e300 : 0.0);
+    for (int r = 0; r < pv.n; r++) {
+      const double v = pv.v[r][(size_t)st * stride + 5 * window + q];
+      tot = (q == 8) ? fmax(tot, v) : ((q == 9) ? fmin(tot, v) : tot + v);
+    }
+    if (q >= 10) { globals[TRIBS_G_BasinRain + (q - 10)] += tot; continue; }
+    const int cur_bin = sb[st].cur_bin;     // store_saturation etc. only write when init == end
+    if (cur_bin < 0 || cur_bin >= limit) continue;
     double *dst = results + (size_t)map[q] * limit + cur_bin;
-    if (q == 8) { if (acc > *dst) *dst = acc; }
-    else if (q == 9) { if (acc <= *dst) *dst = acc; }
-    else *dst += acc;
+    if (q == 8) { if (tot > *dst) *dst = tot; }
+    else if (q == 9) { if (tot <= *dst) *dst = tot; }
+    else *dst += tot;
+  }
+}
+
+// basin accumulators of tHydroModel: per-tile partials of one partition -> [phase][4] (block = phase),
+// then the partitions in order, phase by phase in the reference's order
+__global__ void __launch_bounds__(256)
+sums_reduce_kernel(const double *__restrict__ tile_sums, size_t phase_stride, int tile0, int n_tiles, double *out) {
+  __shared__ double sh[4][256];
+  const double *ts = tile_sums + (size_t)blockIdx.x * phase_stride + (size_t)tile0 * 4;
+  double acc[4] = {0, 0, 0, 0};
+  for (int tix = threadIdx.x; tix < n_tiles; tix += 256)
+    for (int k = 0; k < 4; k++) acc[k] += ts[4 * (size_t)tix + k];
+  for (int k = 0; k < 4; k++) sh[k][threadIdx.x] = acc[k];
+  __syncthreads();
+  for (int o = 128; o > 0; o >>= 1) {
+    if (threadIdx.x < o)
+      for (int k = 0; k < 4; k++) sh[k][threadIdx.x] += sh[k][threadIdx.x + o];
+    __syncthreads();
+  }
+  if (threadIdx.x < 4) out[(size_t)blockIdx.x * 4 + threadIdx.x] = sh[threadIdx.x][0];
+}
+__global__ void combine_sums_kernel(PartVecs pv, const int32_t *__restrict__ phase_is_sat, int n_phases, double *globals) {
+  const int k = threadIdx.x;
+  if (k >= 4) return;
+  const int g[4] = {TRIBS_G_Stok, TRIBS_G_TotRain, TRIBS_G_TotGWchange, TRIBS_G_TotMoist};
+  for (int p = 0; p < n_phases; p++) {
+    if (k == 1 && phase_is_sat && phase_is_sat[p]) continue;
+    double tot = 0.0;
+    for (int r = 0; r < pv.n; r++) tot += pv.v[r][(size_t)p * 4 + k];
+    globals[g[k]] += tot;
   }
 }
 
@@ -645,6 +789,10 @@ route_basin_stage2_kernel(const double *__restrict__ part, int n_blocks, int win
 __global__ void fill_kernel(double *p, double v, int n) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
+}
+__global__ void gauge_fill_kernel(double *rain, const double *__restrict__ vals, const int32_t *__restrict__ gauge_of_cell, int n) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n && gauge_of_cell[i] >= 0) rain[i] = vals[gauge_of_cell[i]];
 }
 __global__ void gather_to_sweep_kernel(const double *__restrict__ src, const int32_t *__restrict__ dev_of_sweep,
                                        double *dst, int n) {
@@ -696,6 +844,8 @@ extern "C" int tribs_gpu_abi_version(void) { return TRIBS_GPU_ABI_VERSION; }
 extern "C" const char *tribs_gpu_last_error(void) { return g_err.c_str(); }
 
 extern "C" int tribs_gpu_set_partition(tribs_handle_t c, const int32_t *cell_owner, int rank);
+static PipeState *pipe_of(tribs_ctx *c);
+static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps);
 extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *prm, const tribs_state_t *init,
                               const tribs_part_t *part, tribs_handle_t *out) {
   if (!mesh || !prm || !out) return fail("tribs_gpu_init: null argument");
@@ -705,11 +855,32 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     return fail("tribs_gpu_init: no CUDA device (this library has no CPU path)");
   const int n = mesh->n_cells;
   if (n <= 0) return fail("tribs_gpu_init: empty mesh");
+  const bool dbg = getenv("TRIBS_DEBUG") != nullptr;
+  const auto t_init0 = std::chrono::steady_clock::now();
+  auto tick = [&](const char *what) {
+    if (dbg) fprintf(stderr, "[tribs] init %-28s %8.3f s\n", what,
+                     std::chrono::duration<double>(std::chrono::steady_clock::now() - t_init0).count());
+  };
   tribs_ctx *c = new tribs_ctx();
   CK(cudaGetDevice(&c->device));
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
   c->n = n;
   c->n_edges = mesh->n_edges;
+  // ---- partitions: layout by partition; with nranks > 1 this handle advances partition `rank`
+  const int32_t *owner = (part && part->cell_owner) ? part->cell_owner : nullptr;
+  c->n_ranks = part ? std::max(1, (int)part->nranks) : 1;
+  c->rank = (part && c->n_ranks > 1) ? part->rank : 0;
+  c->n_parts = owner ? std::max(1, (int)part->n_parts) : 1;
+  if (c->n_ranks > 1 && c->n_parts != c->n_ranks) { delete c; return fail("tribs_gpu_init: n_parts must equal nranks when nranks > 1"); }
+  if (c->n_parts > kMaxParts) { delete c; return fail("tribs_gpu_init: more than 16 partitions"); }
+  if (c->n_ranks > 1 && (c->rank < 0 || c->rank >= c->n_ranks)) { delete c; return fail("tribs_gpu_init: rank out of range"); }
+  if (c->n_ranks > 1 && part->max_batch_steps <= 0) { delete c; return fail("tribs_gpu_init: nranks > 1 needs max_batch_steps"); }
+  if (owner) {
+    c->sweep_owner.assign(owner, owner + n);
+    for (int i = 0; i < n; i++)
+      if (owner[i] < 0 || owner[i] >= c->n_parts) { delete c; return fail("tribs_gpu_init: cell_owner out of range"); }
+  }
+  auto own_of = [&](int i) { return owner ? owner[i] : 0; };
 
   // ---- sweep schedule: level of every cell in the within-step Qpin DAG
   std::vector<std::vector<int32_t>> early(n), late(n);
@@ -729,6 +900,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     nlev = std::max(nlev, lv + 1);
   }
   c->n_levels = nlev;
+  tick("levels");
   // ---- device order. Tiles (32 consecutive device cells) are the unit of scheduling, so a tile must
   //  (a) hold cells with no flow relation among them (a warp never waits on itself) and
   //  (b) hold cells whose inputs become ready at about the same time in EVERY phase; otherwise one
@@ -787,29 +959,49 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   std::vector<int32_t> order(n);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    if (own_of(a) != own_of(b)) return own_of(a) < own_of(b);
     if (seg[a] != seg[b]) return seg[a] < seg[b];
     const int sa = mesh->boundary[a] == 3, sb = mesh->boundary[b] == 3;
     if (sa != sb) return sa < sb;
     return bucket_key(a) < bucket_key(b);
   });
   c->dev_of_sweep.assign(n, -1);
+  c->part_begin.assign(c->n_parts, -1);
+  c->part_end.assign(c->n_parts, -1);
   {
     int pos = 0;
     for (int k = 0; k < n; k++) {
       const int i = order[k];
       if (k > 0) {
         const int j = order[k - 1];
-        if (seg[i] != seg[j] || (mesh->boundary[i] == 3) != (mesh->boundary[j] == 3) || bucket_key(i) != bucket_key(j))
+        if (own_of(i) != own_of(j) || seg[i] != seg[j] || (mesh->boundary[i] == 3) != (mesh->boundary[j] == 3) ||
+            bucket_key(i) != bucket_key(j))
           pos = ((pos + kTile - 1) / kTile) * kTile;
       }
+      if (c->part_begin[own_of(i)] < 0) c->part_begin[own_of(i)] = pos;
       c->dev_of_sweep[i] = pos++;
     }
     c->n_pad = ((pos + kTile - 1) / kTile) * kTile;
+    // ranges are contiguous and ascending; a partition without cells is an empty range
+    int next = c->n_pad;
+    for (int r = c->n_parts - 1; r >= 0; r--) {
+      if (c->part_begin[r] < 0) c->part_begin[r] = next;
+      c->part_end[r] = next;
+      next = c->part_begin[r];
+    }
   }
   const int n_pad = c->n_pad;
+  if (c->n_ranks > 1) {
+    c->my_parts = {c->rank};
+    c->own_begin = c->part_begin[c->rank]; c->own_end = c->part_end[c->rank];
+  } else {
+    for (int r = 0; r < c->n_parts; r++) c->my_parts.push_back(r);
+    c->own_begin = 0; c->own_end = n_pad;
+  }
   c->n_tiles = n_pad / kTile;
   c->sweep_of_dev.assign(n_pad, -1);
   for (int i = 0; i < n; i++) c->sweep_of_dev[c->dev_of_sweep[i]] = i;
+  tick("device order");
   // tiles on the critical cycle of a pipelined batch (river cells and the cells next to the river)
   {
     std::vector<int32_t> hi(c->n_tiles, 0);
@@ -821,21 +1013,37 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     for (int v : hi) c->n_hi_tiles += v;
     if (dev_upload(c, &c->d_tile_hi, hi)) return 1;
   }
-  // claim order of the single-phase sweep: tiles by their topological time (longest chain of
-  // upslope tiles); ascending tile index is a valid evaluation order for this recurrence
+  // claim order of the single-phase sweep: tiles by their topological time (longest chain of upslope
+  // tiles). Within a partition ascending tile index is a topological order by construction; across
+  // partitions it is one when the partitions are numbered along the flow.
   {
-    std::vector<int32_t> tau(c->n_tiles, 0), tiles(c->n_tiles);
-    for (int dI = 0; dI < n_pad; dI++) {
-      const int i = c->sweep_of_dev[dI];
-      if (i < 0) continue;
-      int mval = tau[dI / kTile];
+    const int nt = c->n_tiles;
+    std::vector<std::vector<int32_t>> dn(nt);
+    std::vector<int32_t> indeg(nt, 0), tau(nt, 0), tiles;
+    for (int i = 0; i < n; i++) {
+      const int ti = c->dev_of_sweep[i] / kTile;
       for (int j : early[i]) {
         const int tj = c->dev_of_sweep[j] / kTile;
-        if (tj >= dI / kTile) { delete c; return fail("tribs_gpu_init: internal: device order is not topological"); }
-        mval = std::max(mval, tau[tj] + 1);
+        if (tj == ti) { delete c; return fail("tribs_gpu_init: internal: a tile holds two cells with a flow relation"); }
+        if (tj > ti) c->topo_order = false;
+        dn[tj].push_back(ti);
       }
-      tau[dI / kTile] = mval;
     }
+    for (int t = 0; t < nt; t++) {
+      std::sort(dn[t].begin(), dn[t].end());
+      dn[t].erase(std::unique(dn[t].begin(), dn[t].end()), dn[t].end());
+      for (int v : dn[t]) indeg[v]++;
+    }
+    tiles.reserve(nt);
+    for (int t = 0; t < nt; t++) if (!indeg[t]) tiles.push_back(t);
+    for (size_t q = 0; q < tiles.size(); q++) {
+      const int t = tiles[q];
+      for (int v : dn[t]) {
+        tau[v] = std::max(tau[v], tau[t] + 1);
+        if (--indeg[v] == 0) tiles.push_back(v);
+      }
+    }
+    if ((int)tiles.size() != nt) { delete c; return fail("tribs_gpu_init: internal: the tiles' flow relation has a cycle"); }
     std::iota(tiles.begin(), tiles.end(), 0);
     std::stable_sort(tiles.begin(), tiles.end(), [&](int a, int b) { return tau[a] < tau[b]; });
     if (dev_upload(c, &c->d_tile_order, tiles)) return 1;
@@ -843,6 +1051,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   auto D = [&](int sweep) { return sweep < 0 ? -1 : c->dev_of_sweep[sweep]; };
   c->last_sweep_dev = c->dev_of_sweep[n - 1];
 
+  tick("tile order");
   // ---- static arrays in device order
   auto permute_d = [&](const double *src, double padv) {
     std::vector<double> v(n_pad, padv);
@@ -867,7 +1076,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
 #define UPD(field, vec) { double *p_; if (dev_upload(c, &p_, vec)) { return 1; } c->sv.field = p_; }
   {
     std::vector<int32_t> ones(n_pad, 0);
-    for (int i = 0; i < n; i++) ones[c->dev_of_sweep[i]] = 1;
+    for (int i = 0; i < n; i++) ones[c->dev_of_sweep[i]] = (c->n_ranks == 1 || own_of(i) == c->rank) ? 1 : 0;
     if (dev_upload(c, &c->d_owned, ones)) return 1;
     c->sv.owned = c->d_owned;
   }
@@ -880,6 +1089,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   UPD(lam, permute_d(prm->PoreSize, 0.5)) UPD(psib, permute_d(prm->AirEBubPres, -100.0)) UPD(f, permute_d(prm->DecayF, 0.01))
   UPD(ar, permute_d(prm->SatAnRatio, 1.0)) UPD(uar, permute_d(prm->UnsatAnRatio, 1.0))
 
+  tick("static arrays");
   // ---- neighbour CSR in device order
   {
     std::vector<int32_t> rp(n_pad + 1, 0), col, lpos;
@@ -907,6 +1117,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     UPI(nbr_rowptr, rp) UPI(nbr_col, col) UPI(nbr_listpos, lpos)
     UPD(nbr_len, len) UPD(nbr_vedglen, vl) UPD(nbr_len_in, len_in) UPD(nbr_vedglen_in, vl_in)
   }
+  tick("neighbour CSR");
   // ---- upslope contributor CSRs (rows in device order, entries by sweep position)
   {
     std::vector<int32_t> rp(n_pad + 1, 0), col, lrp(n_pad + 1, 0), lcol;
@@ -924,7 +1135,10 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   }
   if (dev_upload(c, &c->d_dev_of_sweep, c->dev_of_sweep) || dev_upload(c, &c->d_sweep_of_dev, c->sweep_of_dev)) return 1;
 
-  // ---- routing structures: contributors of every stream cell sorted by (hillpath, sweep pos)
+  tick("contributor CSRs");
+  // ---- routing structures: contributors of every stream cell sorted by (hillpath, sweep pos); one set of
+  //      entry arrays per partition (a stream cell and its hillslope always share a partition), so a
+  //      partition's sums group the same way on one GPU and on many
   {
     std::vector<int32_t> scells;  // sweep indices of stream cells, sweep order
     for (int i = 0; i < n; i++) if (mesh->boundary[i] == 3) scells.push_back(i);
@@ -934,6 +1148,8 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     std::vector<int32_t> slot_of(n, -1);
     for (int k = 0; k < c->n_stream; k++) slot_of[scells[k]] = k;
     std::vector<std::vector<int32_t>> members(slots);
+    std::vector<int32_t> slot_part(slots, -1);
+    for (int k = 0; k < c->n_stream; k++) slot_part[k] = own_of(scells[k]);
     int last_hill = -1;
     for (int i = 0; i < n; i++) {
       if (mesh->boundary[i] != 0) continue;
@@ -941,32 +1157,41 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
       int sn = mesh->stream_node[i];
       int slot = (sn >= 0 && slot_of[sn] >= 0) ? slot_of[sn] : c->n_stream;
       members[slot].push_back(i);
+      if (slot_part[slot] < 0) slot_part[slot] = own_of(i);
+      if (slot_part[slot] != own_of(i))
+        return fail("tribs_gpu_init: a hillslope cell and its stream node lie in different partitions (partitions must follow reaches)");
     }
+    if (slot_part[c->n_stream] < 0) slot_part[c->n_stream] = c->n_parts - 1;
     c->last_hill_dev = last_hill >= 0 ? c->dev_of_sweep[last_hill] : -1;
-    std::vector<int32_t> seg_cell, seg_slot, sdev(slots, -1);
-    std::vector<double> seg_path, seg_area;
-    seg_cell.reserve(n); seg_slot.reserve(n); seg_path.reserve(n); seg_area.reserve(n);
+    std::vector<int32_t> sdev(slots, -1);
+    for (int k = 0; k < c->n_stream; k++) sdev[k] = c->dev_of_sweep[scells[k]];
     double max_path = 0.0;
-    for (int k = 0; k < slots; k++) {
-      auto &mm = members[k];
-      std::stable_sort(mm.begin(), mm.end(), [&](int a, int b) { return mesh->hillpath[a] < mesh->hillpath[b]; });
-      if (k < c->n_stream) {  // the stream cell itself: zero travel time, same bin arithmetic
-        sdev[k] = c->dev_of_sweep[scells[k]];
-        seg_cell.push_back(sdev[k]); seg_slot.push_back(k); seg_path.push_back(0.0);
-        seg_area.push_back(mesh->varea[scells[k]]);
+    for (int i = 0; i < n; i++) if (mesh->boundary[i] == 0) max_path = std::max(max_path, mesh->hillpath[i]);
+    c->seg_parts.assign(c->n_parts, SegPart{});
+    for (int r : c->my_parts) {
+      std::vector<int32_t> seg_cell, seg_slot;
+      std::vector<double> seg_path, seg_area;
+      for (int k = 0; k < slots; k++) {
+        if (slot_part[k] != r) continue;
+        auto &mm = members[k];
+        std::stable_sort(mm.begin(), mm.end(), [&](int a, int b) { return mesh->hillpath[a] < mesh->hillpath[b]; });
+        if (k < c->n_stream) {  // the stream cell itself: zero travel time, same bin arithmetic
+          seg_cell.push_back(sdev[k]); seg_slot.push_back(k); seg_path.push_back(0.0);
+          seg_area.push_back(mesh->varea[scells[k]]);
+        }
+        for (int i : mm) {
+          seg_cell.push_back(c->dev_of_sweep[i]); seg_slot.push_back(k); seg_path.push_back(mesh->hillpath[i]);
+          seg_area.push_back(mesh->varea[i]);
+        }
       }
-      for (int i : mm) {
-        seg_cell.push_back(c->dev_of_sweep[i]); seg_slot.push_back(k); seg_path.push_back(mesh->hillpath[i]);
-        seg_area.push_back(mesh->varea[i]);
-        max_path = std::max(max_path, mesh->hillpath[i]);
-      }
+      SegPart &sp = c->seg_parts[r];
+      sp.n_seg = (int)seg_cell.size();
+      sp.blocks = std::max(1, (sp.n_seg + kSegBlock - 1) / kSegBlock);
+      if (dev_upload(c, &sp.cell, seg_cell) || dev_upload(c, &sp.slot, seg_slot) || dev_upload(c, &sp.path, seg_path) ||
+          dev_upload(c, &sp.area, seg_area) || dev_alloc(c, &sp.bnd, (size_t)sp.blocks))
+        return 1;
     }
-    c->n_seg = (int)seg_cell.size();
-    c->seg_blocks = std::max(1, (c->n_seg + kSegBlock - 1) / kSegBlock);
-    if (dev_upload(c, &c->d_seg_cell, seg_cell) || dev_upload(c, &c->d_seg_slot, seg_slot) ||
-        dev_upload(c, &c->d_seg_path, seg_path) || dev_upload(c, &c->d_seg_area, seg_area) ||
-        dev_upload(c, &c->d_sn_dev, sdev) || dev_alloc(c, &c->d_seg_bnd, (size_t)c->seg_blocks))
-      return 1;
+    if (dev_upload(c, &c->d_sn_dev, sdev)) return 1;
     RouteConst &rc = c->rc;
     rc.velcoef = prm->velcoef; rc.velratio = prm->velratio; rc.flowexp = prm->flowexp; rc.baseflow = prm->baseflow;
     rc.kincoef = prm->kincoef; rc.dt_reff = prm->dtReff; rc.outlet_contr_area = prm->outlet_contr_area;
@@ -987,9 +1212,9 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     CK(cudaMemset(c->d_ring, 0, (size_t)slots * ring * sizeof(double)));
     CK(cudaMemset(c->d_qeff_now, 0, (size_t)slots * sizeof(double)));
     if (dev_alloc(c, &c->d_results, (size_t)TRIBS_N_RESULTS * rc.res_limit)) return 1;
-    std::vector<double> r0((size_t)TRIBS_N_RESULTS * rc.res_limit, 0.0);
-    for (int k = 0; k < rc.res_limit; k++) r0[(size_t)TRIBS_R_rmin * rc.res_limit + k] = 9999.99;  // tFlowResults.cpp:224
-    CK(cudaMemcpy(c->d_results, r0.data(), r0.size() * sizeof(double), cudaMemcpyHostToDevice));
+    CK(cudaMemset(c->d_results, 0, (size_t)TRIBS_N_RESULTS * rc.res_limit * sizeof(double)));
+    fill_kernel<<<(rc.res_limit + 255) / 256, 256>>>(c->d_results + (size_t)TRIBS_R_rmin * rc.res_limit, 9999.99, rc.res_limit);  // tFlowResults.cpp:224
+    CK(cudaGetLastError());
     // window of output bins one step can touch: longest basin travel time / output interval
     double max_basin_tt = 0.0;
     for (int i = 0; i < n; i++) {
@@ -1000,22 +1225,53 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     }
     c->route_window = std::max(4, (int)ceil(max_basin_tt / prm->output_interval) + 3 +
                                       (int)ceil(prm->tstep / prm->output_interval));
-    c->route_blocks = std::max(1, std::min(592, (n_pad + kRouteWarps * 32 - 1) / (kRouteWarps * 32)));
     size_t stride = 5 * (size_t)c->route_window + kMeans;
     if (kRouteWarps * stride * sizeof(double) > 200 * 1024)
       return fail("tribs_gpu_init: basin travel-time window too wide for shared memory");
-    if (dev_alloc(c, &c->d_route_part, (size_t)c->route_blocks * stride)) return 1;
-    CK(cudaFuncSetAttribute(route_basin_stage1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CK(cudaFuncSetAttribute(tile_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                             (int)(kRouteWarps * stride * sizeof(double))));
+    // Output bins one 32-cell tile can touch in one step: its cells are of one (segment, depth) bucket, so
+    // their travel times are close. With flowexp == 0 the travel time used for binning is static: the
+    // hillslope-only time for hillslope cells (rewritten before it is used, tKinemat.cpp:958-970), the
+    // initial one for stream cells.
+    int K = c->route_window;
+    if (!(prm->flowexp > 0.0)) {
+      const double hv0 = prm->velcoef / prm->velratio;
+      std::vector<double> lo(c->n_tiles, 1e300), hi(c->n_tiles, -1e300);
+      for (int i = 0; i < n; i++) {
+        const double tt = mesh->boundary[i] == 0 ? mesh->hillpath[i] / hv0 / 3600. : (mesh->ttime ? mesh->ttime[i] : 0.0);
+        const int t = c->dev_of_sweep[i] / kTile;
+        lo[t] = std::min(lo[t], tt); hi[t] = std::max(hi[t], tt);
+      }
+      K = 1;
+      for (int t = 0; t < c->n_tiles; t++)
+        if (hi[t] >= lo[t]) K = std::max(K, (int)floor((hi[t] - lo[t] + 0.98 * prm->tstep) / prm->output_interval) + 2);
+      K = std::min(K, c->route_window);
+    }
+    c->tile_bins = K;
+    c->rec_stride = kRecBins + 5 * K;
   }
+  tick("routing structures");
   c->mc.int_storm_max = prm->IntStormMAX; c->mc.surface_depth = prm->surfaceSoilDepth; c->mc.root_depth = prm->rootZoneDepth;
   c->mc.bas_area = prm->BasArea; c->mc.bas_area_flow = prm->BasArea_flow;
   c->mc.et_option = prm->EToption; c->mc.i_option = prm->Ioption; c->mc.sn_opt = prm->SnOpt; c->mc.rdstr_option = prm->RdstrOption;
 
+  // ---- memory the peers address (nranks > 1): one allocation, carved identically on every rank
+  if (c->n_ranks > 1) {
+    const size_t S = (size_t)part->max_batch_steps, P2 = 2 * S, nt = (size_t)c->n_tiles;
+    const size_t stride = 5 * (size_t)c->route_window + kMeans;
+    size_t bytes = ((size_t)TRIBS_N_FIELDS + 4) * ((size_t)n_pad * 8 + 256)      // fields, qpub x2, wt_elev, transm
+                   + 3 * P2 * nt * 4 + (size_t)c->n_parts * (S * stride + P2 * 4) * 8 + S * (size_t)(c->n_stream + 1) * 8 + (1u << 20);
+    void *q = nullptr;
+    CK(cudaMalloc(&q, bytes));
+    CK(cudaMemset(q, 0, bytes));
+    c->allocs.push_back(q);
+    c->slab.base = (char *)q; c->slab.cap = bytes; c->slab.used = 0;
+  }
   // ---- dynamic fields
   for (int k = 0; k < TRIBS_N_FIELDS; k++) {
     double *p;
-    if (dev_alloc(c, &p, (size_t)n_pad)) return 1;
+    if (shared_alloc(c, &p, (size_t)n_pad)) return 1;
     std::vector<double> h(n_pad, 0.0);
     const double *src = (init && init->f[k]) ? init->f[k] : nullptr;
     if (k == TRIBS_F_TTime && !src) src = mesh->ttime;
@@ -1025,9 +1281,20 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   }
   if (dev_alloc(c, &c->d_pub, (size_t)n_pad) || dev_alloc(c, &c->d_tile_counter, 4) || dev_alloc(c, &c->d_abort, 4) ||
       dev_alloc(c, &c->d_flags, 4) || dev_alloc(c, &c->d_tile_sums, (size_t)4 * c->n_tiles) ||
-      dev_alloc(c, &c->d_globals, (size_t)TRIBS_N_GLOBALS) || dev_alloc(c, &c->d_wt_elev, (size_t)n_pad) ||
-      dev_alloc(c, &c->d_transm, (size_t)n_pad) || dev_alloc(c, &c->d_stage, (size_t)n_pad))
+      dev_alloc(c, &c->d_globals, (size_t)TRIBS_N_GLOBALS) || shared_alloc(c, &c->d_wt_elev, (size_t)n_pad) ||
+      shared_alloc(c, &c->d_transm, (size_t)n_pad) || dev_alloc(c, &c->d_stage, (size_t)n_pad))
     return 1;
+  {
+    const int32_t one = 1;
+    if (dev_alloc(c, &c->d_stepbins, 1) || dev_alloc(c, &c->d_one, 1)) return 1;
+    CK(cudaMemcpy(c->d_one, &one, sizeof(one), cudaMemcpyHostToDevice));
+  }
+  {   // buffers of the single-step routing path and of the per-partition sums
+    const size_t own_tiles = (size_t)(c->own_end - c->own_begin) / kTile, stride = 5 * (size_t)c->route_window + kMeans;
+    if (dev_alloc(c, &c->d_tile_rec, own_tiles * c->rec_stride) || dev_alloc(c, &c->d_block_part, (size_t)kReduceBlocksMax * stride * c->n_parts) ||
+        dev_alloc(c, &c->d_part_vec, stride * kMaxParts) || dev_alloc(c, &c->d_sums_part, (size_t)4 * kMaxParts))
+      return 1;
+  }
   CK(cudaMemset(c->d_pub, 0, (size_t)n_pad * sizeof(PubWord)));
   CK(cudaMemset(c->d_tile_counter, 0, 16));
   CK(cudaMemset(c->d_abort, 0, 16));
@@ -1035,6 +1302,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
   CK(cudaMemset(c->d_globals, 0, TRIBS_N_GLOBALS * sizeof(double)));
   CK(cudaMemset(c->d_tile_sums, 0, (size_t)4 * c->n_tiles * sizeof(double)));
 
+  tick("dynamic fields");
   // ---- persistent grid of the sweep: as many co-resident blocks as the device holds
   {
     cudaDeviceProp prop;
@@ -1047,8 +1315,11 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     int needed = (c->n_tiles + warps_per_block - 1) / warps_per_block;
     c->unsat_blocks = std::max(1, std::min(per_sm * prop.multiProcessorCount, needed));
   }
+  tick("sweep grid");
+  // nranks > 1: the batch buffers the peers address are carved now, in the same order on every rank
+  if (c->n_ranks > 1 && ensure_pipe(c, pipe_of(c), part->max_batch_steps)) return 1;
   CK(cudaDeviceSynchronize());
-  if (part && part->nranks > 1 && tribs_gpu_set_partition(c, part->cell_owner, part->rank)) return 1;
+  tick("done");
   *out = c;
   return 0;
 }
@@ -1056,12 +1327,16 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
 // ------------------------------------------------------------------------------------ stepping
 static void tribs_free_et(tribs_ctx *c);
 static int check_sweep_abort(tribs_ctx *c) {
-  int32_t flags[2] = {0, 0};
+  int32_t flags[2] = {0, 0}, two[2] = {0, 0};
+  CK(cudaMemcpyAsync(two, c->d_flags, 8, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaMemcpyAsync(&flags[0], c->d_abort, 4, cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaMemcpyAsync(&flags[1], c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaMemcpyAsync(&flags[1], c->d_flags, 4, cudaMemcpyDeviceToHost, c->stream));   // bit 0 gather overflow, bit 1 bin overflow
   CK(cudaStreamSynchronize(c->stream));
-  if (flags[0]) return fail("unsat sweep aborted: an upslope cell never published its outflow (schedule bug)");
-  if (flags[1]) return fail("saturated zone: more non-zero edge fluxes at a cell than the gather buffer holds");
+  flags[1] = (two[0] ? 1 : 0) | (two[1] ? 2 : 0);
+  if (flags[0] == 2) return fail("a peer rank did not reach the batch barrier within the time limit");
+  if (flags[0]) return fail("sweep aborted: an input never arrived within the time limit (a schedule bug, or a peer rank that stopped)");
+  if (flags[1] & 1) return fail("saturated zone: more non-zero edge fluxes at a cell than the gather buffer holds");
+  if (flags[1] & 2) return fail("routing: a tile touched more output bins in one step than planned at init (travel times changed?)");
   return 0;
 }
 
@@ -1073,8 +1348,52 @@ static int upload_sweep_field(tribs_ctx *c, const double *host, int field) {
   return 0;
 }
 
+static inline int reduce_blocks(int n_tiles) { return std::max(1, std::min(kReduceBlocksMax, (n_tiles + 511) / 512)); }
+static inline int part_tiles(const tribs_ctx *c, int r) { return (c->part_end[r] - c->part_begin[r]) / kTile; }
+
+// basin accumulators: per-tile partials [n_phases][...] of this handle's partitions -> d_part[r][n_phases][4],
+// then (single GPU) the partitions in partition order. buf_tile0 = global index of the buffer's first tile.
+static int reduce_sums_local(tribs_ctx *c, const double *tile_sums, size_t phase_stride, int buf_tile0, int n_phases,
+                             double *d_part) {
+  for (int r : c->my_parts) {
+    sums_reduce_kernel<<<n_phases, 256, 0, c->stream>>>(tile_sums, phase_stride, c->part_begin[r] / kTile - buf_tile0,
+                                                         part_tiles(c, r), d_part + (size_t)r * n_phases * 4);
+    c->launches++;
+  }
+  return 0;
+}
+
+// hillslope routing of one step from `srf_of_cell` (indexable by device index) into the rings, then the latch
+static int route_segments(tribs_ctx *c, const DynView &dv, const double *srf_of_cell, double now, double qstrm_outlet,
+                          double *qeff_out) {
+  cudaStream_t st = c->stream;
+  for (int r : c->my_parts) {
+    const SegPart &sp = c->seg_parts[r];
+    if (sp.n_seg == 0) continue;
+    route_seg_kernel<<<sp.blocks, kSegBlock, 0, st>>>(c->sv, dv, c->rc, sp.cell, sp.slot, sp.path, sp.area, c->d_sn_dev, sp.n_seg,
+                                                      now, qstrm_outlet, srf_of_cell, c->d_ring, sp.bnd);
+    route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, sp.bnd, sp.blocks, c->d_ring);
+    c->launches += 2;
+  }
+  const int slots = c->n_stream + 1;
+  route_latch_kernel<<<(slots + 255) / 256, 256, 0, st>>>(c->rc, slots, now, c->d_ring, qeff_out);
+  c->launches++;
+  return 0;
+}
+
+static inline StepBins step_bins(const tribs_ctx *c, double now) {
+  const int cur_bin0 = (int)floor((0.0 - .01 * c->rc.tstep + now) / c->rc.output_interval);
+  const int cur_bin1 = (int)floor((0.0 - .99 * c->rc.tstep + now) / c->rc.output_interval);
+  StepBins b;
+  b.cur_bin = (cur_bin0 == cur_bin1) ? cur_bin0 : -1;   // store_saturation only writes when init==end
+  b.bin_base = (int)floor((now + .01 * c->rc.tstep) / c->rc.output_interval);
+  return b;
+}
+
 extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_t *s) {
   if (!c || !s) return fail("tribs_gpu_step: null argument");
+  if (c->n_ranks > 1 && (mask & ~0u) != 0)
+    return fail("tribs_gpu_step: a peer-memory partition (nranks > 1) advances through tribs_gpu_run only");
   CK(cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
   const int n_pad = c->n_pad;
@@ -1084,6 +1403,11 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
   } else if (s->rain_mode == TRIBS_RAIN_PER_CELL) {
     if (!s->rain) return fail("tribs_gpu_step: rain_mode PER_CELL without a rain array");
     if (upload_sweep_field(c, s->rain, TRIBS_F_Rain)) return 1;
+  } else if (s->rain_mode == TRIBS_RAIN_GAUGES) {
+    if (!s->rain || !c->d_gauge_of_cell) return fail("tribs_gpu_step: rain_mode GAUGES needs tribs_gpu_set_rain_gauges and the gauge values");
+    CK(cudaMemcpyAsync(c->d_gauge_vals, s->rain, (size_t)c->n_gauges * sizeof(double), cudaMemcpyHostToDevice, st));
+    gauge_fill_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->dv.f[TRIBS_F_Rain], c->d_gauge_vals, c->d_gauge_of_cell, n_pad);
+    c->launches++;
   }
   if (s->qstrm && c->rc.flowexp > 0.0)
     if (upload_sweep_field(c, s->qstrm, TRIBS_F_Qstrm)) return 1;
@@ -1125,8 +1449,11 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
         unsat_late_qpin_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->dv, c->d_late_rowptr, c->d_late_col, n_pad);
         c->launches++;
       }
-      reduce_sums_kernel<<<1, 256, 0, st>>>(c->d_tile_sums, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, TRIBS_G_TotRain,
-                                             TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
+      if (reduce_sums_local(c, c->d_tile_sums, 0, 0, 1, c->d_sums_part)) return 1;
+      PartVecs pv{};
+      pv.n = c->n_parts;
+      for (int r = 0; r < c->n_parts; r++) pv.v[r] = c->d_sums_part + (size_t)r * 4;
+      combine_sums_kernel<<<1, 32, 0, st>>>(pv, nullptr, 1, c->d_globals);
       c->launches++;
     }
     c->new_valid = true;
@@ -1143,8 +1470,11 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
       sat_cells_kernel<32><<<blocks, 128, 0, st>>>(c->sv, c->dv, c->mc, t, c->d_wt_elev, c->d_transm, n_pad, c->d_tile_sums, c->d_flags, c->d_globals);
     else
       sat_cells_kernel<64><<<blocks, 128, 0, st>>>(c->sv, c->dv, c->mc, t, c->d_wt_elev, c->d_transm, n_pad, c->d_tile_sums, c->d_flags, c->d_globals);
-    reduce_sums_kernel<<<1, 256, 0, st>>>(c->d_tile_sums, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, -1,
-                                           TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
+    if (reduce_sums_local(c, c->d_tile_sums, 0, 0, 1, c->d_sums_part)) return 1;
+    PartVecs pv{};
+    pv.n = c->n_parts;
+    for (int r = 0; r < c->n_parts; r++) pv.v[r] = c->d_sums_part + (size_t)r * 4;
+    combine_sums_kernel<<<1, 32, 0, st>>>(pv, c->d_one, 1, c->d_globals);   // a SAT phase: no TotRain term
     c->launches += 3;
     c->gw_dirty = true;
     c->new_valid = true;
@@ -1153,24 +1483,31 @@ extern "C" int tribs_gpu_step(tribs_handle_t c, uint32_t mask, const tribs_step_
   if (mask & TRIBS_PHASE_ROUTE) {
     PhaseTimer pt(c, 2);
     const double now = s->current_time;
-    const int slots = c->n_stream + 1;
-    route_seg_kernel<<<c->seg_blocks, kSegBlock, 0, st>>>(c->sv, c->dv, c->rc, c->d_seg_cell, c->d_seg_slot, c->d_seg_path,
-                                                          c->d_seg_area, c->d_sn_dev, c->n_seg, now, s->qstrm_outlet,
-                                                          c->d_ring, c->d_seg_bnd);
-    route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, c->d_seg_bnd, c->seg_blocks, slots, now, c->d_ring, c->d_qeff_now);
-    const int window = c->route_window;
-    const int cur_bin0 = (int)floor((0.0 - .01 * c->rc.tstep + now) / c->rc.output_interval);
-    const int cur_bin1 = (int)floor((0.0 - .99 * c->rc.tstep + now) / c->rc.output_interval);
-    const int cur_bin = (cur_bin0 == cur_bin1) ? cur_bin0 : -1;   // store_saturation only writes when init==end
-    const int bin_base = (int)floor((now + .01 * c->rc.tstep) / c->rc.output_interval);
-    size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
-    route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, c->dv, c->rc, c->mc, now, s->qstrm_outlet,
-                                                                                 n_pad, window, bin_base, c->last_hill_dev,
-                                                                                 c->d_route_part, c->d_globals, water_balance_args(c, now));
-    const int n_vals = 5 * window + kMeans;
-    route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
-                                                                          cur_bin, c->rc.res_limit, c->d_results, c->d_globals);
-    c->launches += 4;
+    if (route_segments(c, c->dv, c->dv.f[TRIBS_F_srf], now, s->qstrm_outlet, c->d_qeff_now)) return 1;
+    const int window = c->route_window, K = c->tile_bins;
+    const size_t stride = 5 * (size_t)window + kMeans;
+    const StepBins sb = step_bins(c, now);
+    CK(cudaMemcpyAsync(c->d_stepbins, &sb, sizeof(sb), cudaMemcpyHostToDevice, st));
+    WaterBalanceArgs wb = water_balance_args(c, now);
+    RouteStep rs{now, s->qstrm_outlet, 0.0, wb.gw_time, 0};
+    const int own_tiles = (c->own_end - c->own_begin) / kTile;
+    route_tiles_kernel<<<(own_tiles * 32 + 127) / 128, 128, 0, st>>>(c->sv, c->dv, c->rc, c->mc, wb, rs, c->own_begin, own_tiles,
+                                                                      c->last_hill_dev, K, c->d_tile_rec, c->d_globals, c->d_flags);
+    c->launches++;
+    PartVecs pv{};
+    pv.n = c->n_parts;
+    for (int r = 0; r < c->n_parts; r++) {
+      const int nt = part_tiles(c, r), G = reduce_blocks(nt);
+      double *bp = c->d_block_part + (size_t)r * kReduceBlocksMax * stride, *vec = c->d_part_vec + (size_t)r * stride;
+      tile_reduce_kernel<<<dim3(G, 1), kRouteWarps * 32, kRouteWarps * stride * sizeof(double), st>>>(
+          c->d_tile_rec, 0, (c->part_begin[r] - c->own_begin) / kTile, nt, K, window, c->d_stepbins, bp, c->d_flags);
+      part_reduce_kernel<<<((int)stride * 32 + 255) / 256, 256, 0, st>>>(bp, G, window, 1, vec);
+      pv.v[r] = vec;
+      c->launches += 2;
+    }
+    combine_results_kernel<<<(5 * window + kMeans + 255) / 256, 256, 0, st>>>(pv, c->d_stepbins, 1, window, c->rc.res_limit,
+                                                                              sb.bin_base, window, c->d_results, c->d_globals);
+    c->launches++;
   }
   if (mask & TRIBS_PHASE_RESET) {
     PhaseTimer pt(c, 3);
@@ -1894,6 +2231,7 @@ extern "C" int tribs_gpu_wait(tribs_handle_t c) {
 }
 extern "C" void *tribs_gpu_stream(tribs_handle_t c) { return c ? (void *)c->stream : nullptr; }
 static void tribs_free_pipe(tribs_ctx *c);
+static void tribs_free_snapshot(tribs_ctx *c);
 extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
@@ -1904,558 +2242,10 @@ extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   cudaStreamDestroy(c->stream);
   tribs_free_pipe(c);
   tribs_free_et(c);
+  tribs_free_snapshot(c);
   delete c;
   return 0;
 }
 
-// ====================================================================================
-// Pipelined batch (tribs_gpu_run): a space-time dataflow over (phase, 32-cell tile) tasks with a
-// device-side ready queue.
-//
-// Phase with tag T reads the state buffer T%2 and writes buffer (T+1)%2; the new Qpout of a cell
-// is handed to its receiver through qpub[T%2]. At tile granularity a task (phase p, tile t) needs
-//   UNSAT: (p, u) for every tile u holding an upslope contributor of a cell of t         [Qpin]
-//          and, from the previous phase p-1: t itself and every tile holding a flow_dest of a
-//          cell of t (it reads the downslope Old values; this also keeps an upslope cell at most
-//          one phase ahead of its receiver, so two qpub buffers suffice)  -- or, when phase p-1
-//          was a saturated-zone phase, t and all Voronoi-neighbour tiles (their gathers read the
-//          buffer this task overwrites);
-//   SAT:   (p-1, t) and (p-1, v) for every Voronoi-neighbour tile v.
-// Every task has a counter of unmet inputs; a finishing warp fences, decrements the counters of
-// its dependents and pushes those that reach zero onto a global queue, from which idle warps pop.
-// No warp ever waits for a cell: all resident warps run ready work, and the long stream-cell
-// chain of one step overlaps with the bulk of the following steps. Values never depend on the
-// schedule (no atomics on data, partial sums are indexed by task). Cross-cell data is read
-// from L2 (the library is compiled with -dlcm=cg).
-// ====================================================================================
-struct PhaseInfo {
-  int32_t kind;         // 0 UNSAT, 1 SAT
-  int32_t step;         // step index inside the batch
-  int32_t prev_sat;     // the phase before this one was a SAT phase
-  int32_t next_sat;     // the next phase is a SAT phase: produce wt_elev / transm
-  int32_t write_slice;  // last phase of its step: snapshot the routing inputs
-  int32_t has_next;     // another phase follows inside the batch
-  long long tag;        // global phase number
-  StepConst t;
-};
-
-constexpr int kSliceFields = 15;
-__constant__ int kSliceFieldIds[kSliceFields];
-static const int kSliceFieldIdsHost[kSliceFields] = {
-    TRIBS_F_srf, TRIBS_F_hsrf, TRIBS_F_sbsrf, TRIBS_F_psrf, TRIBS_F_satsrf, TRIBS_F_Rain, TRIBS_F_SoilMoistureSC,
-    TRIBS_F_RootMoistureSC, TRIBS_F_SoilMoistureUNSC, TRIBS_F_NwtNew, TRIBS_F_Qpout, TRIBS_F_Qpin,
-    TRIBS_F_Recharge, TRIBS_F_UnSatFlowIn, TRIBS_F_UnSatFlowOut};   // the last three: tWaterBalance inputs
-
-// tile-level dependency graph (three CSRs over tiles, self excluded, entries distinct)
-struct TileGraph {
-  const int32_t *up_rp, *up;      // tiles holding upslope contributors
-  const int32_t *down_rp, *down;  // tiles holding flow destinations
-  const int32_t *nbr_rp, *nbr;    // tiles holding Voronoi neighbours
-};
-
-__device__ __forceinline__ int ld_relaxed_i32(const int32_t *p) {
-  int v;
-  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void st_relaxed_i32(int32_t *p, int v) {
-  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
-}
-// two ready queues: "hi" for the tiles on the critical cycle of the batch (river cells and the
-// cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
-// ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
-struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; unsigned cap_hi_ns, cap_lo_ns; };
-__device__ __forceinline__ void release_task(int32_t *cnt, const ReadyQueues &rq, int n_tiles, int p, int tile) {
-  const int task = p * n_tiles + tile;
-  if (atomicSub(cnt + task, 1) == 1) {
-    __threadfence();   // acquire the other producers' data before handing the task on
-    const int hi = rq.tile_hi[tile];
-    const int slot = atomicAdd(rq.ctl + (hi ? 1 : 3), 1);
-    st_relaxed_i32(rq.queue + (hi ? 0 : rq.n_tasks) + slot, task);
-  }
-}
-
-// unmet-input counters of every task and the initially ready ones
-__global__ void __launch_bounds__(256)
-pipeline_init_kernel(TileGraph g, const PhaseInfo *__restrict__ phases, int n_phases, int n_tiles, int32_t *cnt,
-                     ReadyQueues rq) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= n_phases * n_tiles) return;
-  const int p = id / n_tiles, t = id % n_tiles;
-  const PhaseInfo ph = phases[p];
-  int c = 0;
-  if (ph.kind == 0) {
-    c += g.up_rp[t + 1] - g.up_rp[t];
-    if (p > 0) c += 1 + (ph.prev_sat ? g.nbr_rp[t + 1] - g.nbr_rp[t] : g.down_rp[t + 1] - g.down_rp[t]);
-  } else if (p > 0)
-    c += 1 + g.nbr_rp[t + 1] - g.nbr_rp[t];
-  cnt[id] = c;
-  if (c == 0) {
-    const int hi = rq.tile_hi[t];
-    rq.queue[(hi ? 0 : rq.n_tasks) + atomicAdd(rq.ctl + (hi ? 1 : 3), 1)] = id;
-  }
-}
-
-#ifndef TRIBS_PIPE_MIN_BLOCKS
-#define TRIBS_PIPE_MIN_BLOCKS 4
-#endif
-template <int MAXC>
-__global__ void __launch_bounds__(128, TRIBS_PIPE_MIN_BLOCKS)
-pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, const PhaseInfo *__restrict__ phases,
-                TileGraph g, int n_tasks, int32_t *cnt, ReadyQueues rq, int n_hi_tasks, int n_hi_blocks,
-                const int32_t *__restrict__ up_rowptr, const int32_t *__restrict__ up_col, double *qpub, int n_pad,
-                double *wt_elev, double *transm, double *slices, double *tile_sums, int n_tiles, double *globals,
-                int last_sweep_dev, int32_t *abort_flag, int32_t *flags) {
-  const int lane = threadIdx.x & 31;
-  // Two ticket queues. `n_hi_blocks` warps, spread over the SMs (warp 0 of every block first), serve the "hi" queue
-  // (river cells and the cells next to the river: their chain through all phases is the critical
-  // path and must never sit behind a backlog of bulk work); every other warp serves "lo". A warp
-  // takes a ticket (atomicAdd on the head) and waits for exactly that slot to be filled, so a
-  // newly released task is picked up at once by the warp that holds its ticket.
-  const bool hi_warp = (int)((threadIdx.x >> 5) * gridDim.x + blockIdx.x) < n_hi_blocks;
-  const int my_total = hi_warp ? n_hi_tasks : n_tasks - n_hi_tasks;
-  int32_t *my_head = rq.ctl + (hi_warp ? 0 : 2);
-  const int32_t *my_queue = rq.queue + (hi_warp ? 0 : rq.n_tasks);
-  const unsigned ns_cap = hi_warp ? rq.cap_hi_ns : rq.cap_lo_ns;   // back-off ceiling of the queue poll
-  long long t_wait = 0, t_busy = 0, n_done = 0;
-  long long t_mark = clock64();
-  for (;;) {
-    int task = -1;
-    if (lane == 0) {
-      const int idx = atomicAdd(my_head, 1);
-      if (idx < my_total) {
-        unsigned spins = 0, ns = 32;
-        unsigned long long t_first = 0;
-        while ((task = ld_relaxed_i32(my_queue + idx)) < 0) {   // nothing of my class is ready yet
-          __nanosleep(ns);
-          if (ns < ns_cap) ns += ns;
-          if (((++spins) & 255u) == 0u) {
-            if (*(volatile int32_t *)abort_flag) { task = -2; break; }
-            const unsigned long long t_now = global_ns();
-            if (!t_first) t_first = t_now;
-            else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(abort_flag, 1); task = -2; break; }
-          }
-        }
-      } else
-        task = -2;
-    }
-    task = __shfl_sync(0xffffffffu, task, 0);
-    { const long long now_c = clock64(); t_wait += now_c - t_mark; t_mark = now_c; }
-    if (task < 0) break;
-    const int p = task / n_tiles, tile = task - p * n_tiles;
-    if (rq.trace && lane == 0) rq.trace[2 * (size_t)task] = global_ns();   // TRIBS_TRACE: task timeline
-    __threadfence();   // acquire side of the producers' fence -> counter -> queue hand-off
-    const PhaseInfo ph = phases[p];
-    const int i = tile * kTile + lane;
-    const long long tag = ph.tag;
-    const DynView &d = (tag & 1) ? d_odd : d_even;   // Old = buffer tag%2, New = the other
-    const bool act = s.boundary[i] >= 0 && s.owned[i];
-    double sums[4] = {0.0, 0.0, 0.0, 0.0};
-    UnsatCellInputs u;
-    double qpin = 0.0;
-    if (ph.kind == 0) {
-      if (act) {
-        unsat_cell_load(u, s, d, i, m, ph.t);
-        const double *qsrc = qpub + (size_t)(tag & 1) * n_pad;
-        const int k1 = up_rowptr[i + 1];
-        for (int k = up_rowptr[i]; k < k1; k++) qpin += qsrc[up_col[k]];   // sweep order
-        int state;
-        const double qout = unsat_cell_advance(u, qpin, &state);
-        qpub[(size_t)(tag & 1) * n_pad + i] = qout;
-      }
-      // the downslope tiles of this phase only need the new Qpout: release them before the
-      // write-back and the diagnostics, which are off the critical chain along the river
-      __threadfence();
-      __syncwarp();
-      const int r0 = g.down_rp[tile], r1 = g.down_rp[tile + 1];
-      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p, g.down[k]);
-    }
-    if (act) {
-      if (ph.kind == 0) {
-        UnsatSums us;
-        unsat_cell_store(u, d, i, qpin, m, ph.t, us);
-        sums[0] = us.stok; sums[1] = us.tot_rain; sums[2] = us.tot_gw; sums[3] = us.tot_moist;
-        if (i == last_sweep_dev) globals[TRIBS_G_psrf_last] = u.c.psrf;
-        if (ph.next_sat) {
-          // ResetGW + the edge pre-pass for this cell: the post-sweep state is what SAT calls Old
-          DynView dn = d;
-          dn.f[TRIBS_F_NwtOld] = d.f[TRIBS_F_NwtNew];
-          sat_prepare_cell(s, dn, i, wt_elev, transm);
-        }
-      } else {
-        int overflow = 0;
-        const double gw = sat_gather<MAXC>(s, d, i, wt_elev, transm, &overflow);
-        if (overflow) flags[0] = 1;
-        SatSums ss;
-        sat_cell(s, d, i, gw, m, ph.t, ss);
-        sums[0] = ss.stok; sums[2] = ss.tot_gw; sums[3] = ss.tot_moist;
-      }
-      if (ph.write_slice) {
-        double *sl = slices + (size_t)ph.step * kSliceFields * n_pad + i;
-#pragma unroll
-        for (int k = 0; k < kSliceFields; k++) {
-          // no Reset() runs between the steps of a batch: a sweep-only step has no GW runoff
-          const double v = (ph.kind == 0 && k == 4) ? 0.0 : d.f[kSliceFieldIds[k]][i];
-          sl[(size_t)k * n_pad] = v;
-        }
-      }
-    }
-    double a = warp_sum_fixed(sums[0]), b = warp_sum_fixed(sums[1]);
-    double c2 = warp_sum_fixed(sums[2]), e = warp_sum_fixed(sums[3]);
-    if (lane == 0) {
-      double *ts = tile_sums + ((size_t)p * n_tiles + tile) * 4;
-      ts[0] = a; ts[1] = b; ts[2] = c2; ts[3] = e;
-    }
-    // hand the results on: fence, then lanes release the dependents in parallel
-    __threadfence();
-    __syncwarp();
-    if (ph.has_next) {
-      const bool wide = (ph.kind == 1) || ph.next_sat;   // a SAT phase on either side: neighbours
-      const int32_t *rp = wide ? g.nbr_rp : g.up_rp;
-      const int32_t *lst = wide ? g.nbr : g.up;
-      const int r0 = rp[tile], r1 = rp[tile + 1];
-      for (int k = r0 + lane; k < r1; k += 32) release_task(cnt, rq, n_tiles, p + 1, lst[k]);
-      if (lane == 0) release_task(cnt, rq, n_tiles, p + 1, tile);
-    }
-    if (rq.trace && lane == 0) rq.trace[2 * (size_t)task + 1] = global_ns();
-    { const long long now_c = clock64(); t_busy += now_c - t_mark; t_mark = now_c; n_done++; }
-  }
-  if (lane == 0) {   // scheduler statistics: [0..2] lo warps, [3..5] hi warps
-    unsigned long long *st = (unsigned long long *)(rq.ctl + 8) + (hi_warp ? 3 : 0);
-    atomicAdd(st + 0, (unsigned long long)t_wait);
-    atomicAdd(st + 1, (unsigned long long)t_busy);
-    atomicAdd(st + 2, (unsigned long long)n_done);
-  }
-}
-
-__global__ void __launch_bounds__(256)
-esrf_fixup_kernel(StaticView s, DynView d, int n_pad, double dtgw, const double *globals) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n_pad || s.boundary[i] < 0) return;
-  double esrf = globals[TRIBS_G_psrf_last] + d.f[TRIBS_F_esrf][i];
-  esrf = esrf / s.cosv[i];
-  d.f[TRIBS_F_esrf][i] = esrf * dtgw;
-}
-
-struct PipePlan {
-  std::vector<uint8_t> pattern;   // per step: 1 = has a SAT phase
-  std::vector<PhaseInfo> phases;  // tags/time constants are filled per run
-  PhaseInfo *d_phases = nullptr;
-};
-
-struct PipeState {
-  double *d_qpub = nullptr;        // [2][n_pad] new Qpout by phase parity
-  double *d_slices = nullptr;      // [max_steps][kSliceFields][n_pad]
-  double *d_tile_sums = nullptr;   // [max_phases][n_tiles][4]
-  double *d_qeff_steps = nullptr;  // [max_steps][slots]
-  double *d_rain = nullptr;        // [max_steps][n_pad] per-cell forcing, device order
-  int32_t *d_cnt = nullptr, *d_queue = nullptr, *d_headtail = nullptr;
-  TileGraph graph{};
-  int max_steps = 0, last_steps = 0;
-  long long g = 0;                 // phases completed so far
-  int blocks = 0, n_sms = 0;
-  std::vector<PipePlan> plans;
-};
-static PipeState *pipe_of(tribs_ctx *c) {
-  if (!c->pipe) c->pipe = new PipeState();
-  return c->pipe;
-}
-
-static int build_plan(tribs_ctx *c, PipeState *ps, const std::vector<uint8_t> &pattern, PipePlan **out) {
-  for (auto &pl : ps->plans) if (pl.pattern == pattern) { *out = &pl; return 0; }
-  PipePlan pl;
-  pl.pattern = pattern;
-  for (size_t sidx = 0; sidx < pattern.size(); sidx++) {
-    PhaseInfo u{};
-    u.kind = 0; u.step = (int)sidx; u.write_slice = pattern[sidx] ? 0 : 1; u.next_sat = pattern[sidx];
-    pl.phases.push_back(u);
-    if (pattern[sidx]) {
-      PhaseInfo v{};
-      v.kind = 1; v.step = (int)sidx; v.write_slice = 1;
-      pl.phases.push_back(v);
-    }
-  }
-  const int P = (int)pl.phases.size();
-  for (int p = 0; p < P; p++) {
-    pl.phases[p].prev_sat = p > 0 && pl.phases[p - 1].kind == 1;
-    pl.phases[p].has_next = p + 1 < P;
-  }
-  if (dev_alloc(c, &pl.d_phases, (size_t)P)) return 1;
-  ps->plans.push_back(pl);
-  *out = &ps->plans.back();
-  return 0;
-}
-
-// tile-level CSRs from the cell-level graph (host copies of the device arrays)
-static int build_tile_graph(tribs_ctx *c, PipeState *ps) {
-  const int nt = c->n_tiles, n_pad = c->n_pad;
-  std::vector<int32_t> h_up_rp(n_pad + 1), h_nbr_rp(n_pad + 1), h_fd(n_pad);
-  CK(cudaMemcpy(h_up_rp.data(), c->d_up_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_nbr_rp.data(), c->sv.nbr_rowptr, (n_pad + 1) * 4, cudaMemcpyDeviceToHost));
-  CK(cudaMemcpy(h_fd.data(), c->sv.flow_dest, n_pad * 4, cudaMemcpyDeviceToHost));
-  std::vector<int32_t> h_up_col(h_up_rp[n_pad]), h_nbr_col(h_nbr_rp[n_pad]);
-  if (!h_up_col.empty()) CK(cudaMemcpy(h_up_col.data(), c->d_up_col, h_up_col.size() * 4, cudaMemcpyDeviceToHost));
-  if (!h_nbr_col.empty()) CK(cudaMemcpy(h_nbr_col.data(), c->sv.nbr_col, h_nbr_col.size() * 4, cudaMemcpyDeviceToHost));
-  std::vector<int32_t> up_rp(nt + 1, 0), down_rp(nt + 1, 0), nbr_rp(nt + 1, 0), up, down, nbr, tmp;
-  auto flush = [&](std::vector<int32_t> &dst, std::vector<int32_t> &rp, int t) {
-    std::sort(tmp.begin(), tmp.end());
-    tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
-    for (int v : tmp) if (v != t) dst.push_back(v);
-    rp[t + 1] = (int32_t)dst.size();
-    tmp.clear();
-  };
-  for (int t = 0; t < nt; t++) {
-    for (int l = 0; l < kTile; l++) { const int i = t * kTile + l; for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) tmp.push_back(h_up_col[k] / kTile); }
-    flush(up, up_rp, t);
-    for (int l = 0; l < kTile; l++) { const int i = t * kTile + l; if (h_fd[i] >= 0) tmp.push_back(h_fd[i] / kTile); }
-    flush(down, down_rp, t);
-    for (int l = 0; l < kTile; l++) {
-      const int i = t * kTile + l;
-      for (int k = h_nbr_rp[i]; k < h_nbr_rp[i + 1]; k++) if (h_nbr_col[k] >= 0) tmp.push_back(h_nbr_col[k] / kTile);
-      if (h_fd[i] >= 0) tmp.push_back(h_fd[i] / kTile);
-      for (int k = h_up_rp[i]; k < h_up_rp[i + 1]; k++) tmp.push_back(h_up_col[k] / kTile);
-    }
-    flush(nbr, nbr_rp, t);
-  }
-  // the neighbour relation must be symmetric for the counters to balance: symmetrise explicitly
-  {
-    std::vector<std::vector<int32_t>> adj(nt);
-    for (int t = 0; t < nt; t++) for (int k = nbr_rp[t]; k < nbr_rp[t + 1]; k++) { adj[t].push_back(nbr[k]); adj[nbr[k]].push_back(t); }
-    nbr.clear();
-    for (int t = 0; t < nt; t++) {
-      auto &a2 = adj[t];
-      std::sort(a2.begin(), a2.end());
-      a2.erase(std::unique(a2.begin(), a2.end()), a2.end());
-      for (int v : a2) nbr.push_back(v);
-      nbr_rp[t + 1] = (int32_t)nbr.size();
-    }
-  }
-  int32_t *p1, *p2, *p3, *p4, *p5, *p6;
-  if (dev_upload(c, &p1, up_rp) || dev_upload(c, &p2, up) || dev_upload(c, &p3, down_rp) || dev_upload(c, &p4, down) ||
-      dev_upload(c, &p5, nbr_rp) || dev_upload(c, &p6, nbr))
-    return 1;
-  ps->graph = TileGraph{p1, p2, p3, p4, p5, p6};
-  return 0;
-}
-
-static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
-  if (!ps->d_qpub) {
-    if (dev_alloc(c, &ps->d_qpub, (size_t)2 * c->n_pad) || dev_alloc(c, &ps->d_headtail, 4096)) return 1;
-    CK(cudaMemset(ps->d_qpub, 0, (size_t)2 * c->n_pad * sizeof(double)));
-    CK(cudaMemcpyToSymbol(kSliceFieldIds, kSliceFieldIdsHost, sizeof(kSliceFieldIdsHost)));
-    if (build_tile_graph(c, ps)) return 1;
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, c->device));
-    int per_sm = 0;
-    if (c->max_degree <= 16) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<16>, 128, 0));
-    else if (c->max_degree <= 32) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<32>, 128, 0));
-    else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pipeline_kernel<64>, 128, 0));
-    if (per_sm < 1) return fail("tribs_gpu_run: pipeline_kernel does not fit on an SM");
-    ps->blocks = per_sm * prop.multiProcessorCount;
-    ps->n_sms = prop.multiProcessorCount;
-  }
-  if (n_steps > ps->max_steps) {
-    // (re)allocate the per-step staging; old buffers stay in the handle's allocation list
-    const int slots = c->n_stream + 1;
-    if (dev_alloc(c, &ps->d_slices, (size_t)n_steps * kSliceFields * c->n_pad) ||
-        dev_alloc(c, &ps->d_tile_sums, (size_t)2 * n_steps * c->n_tiles * 4) ||
-        dev_alloc(c, &ps->d_qeff_steps, (size_t)n_steps * slots) || dev_alloc(c, &ps->d_rain, (size_t)n_steps * c->n_pad) ||
-        dev_alloc(c, &ps->d_cnt, (size_t)2 * n_steps * c->n_tiles) || dev_alloc(c, &ps->d_queue, (size_t)4 * n_steps * c->n_tiles))
-      return 1;
-    ps->max_steps = n_steps;
-  }
-  return 0;
-}
-
-extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks) {
-  if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
-  CK(cudaSetDevice(c->device));
-  if (c->partitioned) return fail("tribs_gpu_run: pipelined batches are not available on partitioned handles yet; use tribs_gpu_step");
-  if (c->n_late > 0) return fail("tribs_gpu_run: the sweep order is not topological (late contributors); use tribs_gpu_step");
-  if (c->rc.flowexp > 0.0 && n_steps > 1) return fail("tribs_gpu_run: flowexp > 0 needs the channel router between steps; use tribs_gpu_step");
-  const uint32_t need = TRIBS_PHASE_UNSAT | TRIBS_PHASE_ROUTE | TRIBS_PHASE_RESET;
-  std::vector<uint8_t> pattern(n_steps);
-  for (int k = 0; k < n_steps; k++) {
-    if ((masks[k] & need) != need) return fail("tribs_gpu_run: every step must contain UNSAT, ROUTE and RESET");
-    pattern[k] = (masks[k] & TRIBS_PHASE_SAT) ? 1 : 0;
-  }
-  PipeState *ps = pipe_of(c);
-  if (ensure_pipe(c, ps, n_steps)) return 1;
-  PipePlan *pl = nullptr;
-  if (build_plan(c, ps, pattern, &pl)) return 1;
-  cudaStream_t st = c->stream;
-  const int n_pad = c->n_pad, P = (int)pl->phases.size();
-  if (!c->at_boundary) return fail("tribs_gpu_run: call it on a step boundary (after RESET)");
-  // the pipeline works on fixed even/odd views; phase tag T reads buffer T%2
-  DynView d_even = c->dv, d_odd = c->dv;
-  {
-    const int olds[7] = {TRIBS_F_NwtOld, TRIBS_F_MuOld, TRIBS_F_MiOld, TRIBS_F_NtOld, TRIBS_F_NfOld, TRIBS_F_RuOld, TRIBS_F_RiOld};
-    const int news[7] = {TRIBS_F_NwtNew, TRIBS_F_MuNew, TRIBS_F_MiNew, TRIBS_F_NtNew, TRIBS_F_NfNew, TRIBS_F_RuNew, TRIBS_F_RiNew};
-    DynView &second = ((ps->g + 1) & 1) ? d_even : d_odd;   // the first phase (tag g+1) reads the handle's Old
-    for (int k = 0; k < 7; k++) std::swap(second.f[olds[k]], second.f[news[k]]);
-  }
-  for (int p = 0; p < P; p++) {
-    PhaseInfo &ph = pl->phases[p];
-    const tribs_step_t &sp = steps[ph.step];
-    ph.tag = ps->g + 1 + p;
-    StepConst t;
-    t.dt = sp.dt; t.dt_gw = sp.dt_gw; t.now = sp.current_time; t.elapsed = (double)sp.elapsed_steps;
-    t.hourly_reset = sp.hourly_reset; t.psrf_last = 0.0; t.defer_esrf = 1;
-    t.rain_mode = 0;
-    if (ph.kind == 0) {
-      if (sp.rain_mode == TRIBS_RAIN_UNIFORM) { t.rain_mode = 1; t.rain_uniform = sp.rain_uniform; }
-      else if (sp.rain_mode == TRIBS_RAIN_PER_CELL) {
-        if (!sp.rain) return fail("tribs_gpu_run: rain_mode PER_CELL without a rain array");
-        double *dst = ps->d_rain + (size_t)ph.step * n_pad;
-        CK(cudaMemcpyAsync(c->d_stage, sp.rain, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, st));
-        scatter_from_sweep_kernel<<<(c->n + 255) / 256, 256, 0, st>>>(c->d_stage, c->d_dev_of_sweep, dst, c->n);
-        c->launches++;
-        t.rain_mode = 2; t.rain_cells = dst;
-      }
-    }
-    ph.t = t;
-  }
-  CK(cudaMemcpyAsync(pl->d_phases, pl->phases.data(), (size_t)P * sizeof(PhaseInfo), cudaMemcpyHostToDevice, st));
-  const int n_tasks = P * c->n_tiles;
-  CK(cudaMemsetAsync(ps->d_headtail, 0, 64 * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)2 * n_tasks * sizeof(int32_t), st));
-  {
-    PhaseTimer pt(c, 0);
-    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr, 128u, 16384u};   // lo ceiling: idle pollers cost the working warps instruction-fetch
-    // bandwidth; measured on the 1M-cell batch 2 us: 373, 16 us: 423, 32 us: 426, 64 us: 397, 128 us: 351 M cell-timesteps/s
-    if (const char *e = getenv("TRIBS_POLL_CAP_NS")) rq.cap_lo_ns = (unsigned)std::max(32, atoi(e));
-    if (const char *e = getenv("TRIBS_POLL_CAP_HI_NS")) rq.cap_hi_ns = (unsigned)std::max(32, atoi(e));
-    const char *trace_path = getenv("TRIBS_TRACE");   // debugging aid: start/end time of every task of this launch
-    unsigned long long *d_trace = nullptr;
-    if (trace_path) {
-      CK(cudaMalloc((void **)&d_trace, (size_t)2 * n_tasks * sizeof(unsigned long long)));
-      CK(cudaMemsetAsync(d_trace, 0, (size_t)2 * n_tasks * sizeof(unsigned long long), st));
-      rq.trace = d_trace;
-    }
-    int n_hi_tasks = P * c->n_hi_tiles;
-    // warps serving the "hi" queue: one per SM for a single river; on a dendritic network the stream
-    // tiles are a sizeable share of all tasks and get that share of the warps
-    const int total_warps = ps->blocks * 4;
-    int n_hi_blocks = std::max(std::min(ps->blocks, ps->n_sms),
-                               (int)std::lround(1.25 * total_warps * (double)c->n_hi_tiles / std::max(1, c->n_tiles)));
-    n_hi_blocks = std::min(n_hi_blocks, total_warps - std::min(ps->blocks, ps->n_sms));
-    if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_blocks = std::max(1, std::min(total_warps - 1, atoi(e)));
-    pipeline_init_kernel<<<(n_tasks + 255) / 256, 256, 0, st>>>(ps->graph, pl->d_phases, P, c->n_tiles, ps->d_cnt, rq);
-    int ntk = n_tasks, n_tiles = c->n_tiles, last = c->last_sweep_dev, npad = n_pad;
-    void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &pl->d_phases, &ps->graph, &ntk, &ps->d_cnt, &rq, &n_hi_tasks, &n_hi_blocks,
-                    &c->d_up_rowptr, &c->d_up_col, &ps->d_qpub, &npad, &c->d_wt_elev, &c->d_transm, &ps->d_slices,
-                    &ps->d_tile_sums, &n_tiles, &c->d_globals, &last, &c->d_abort, &c->d_flags};
-    const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
-                     : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
-    int blocks = ps->blocks;
-    CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(128), args, 0, st));
-    c->launches += 2;
-    if (d_trace) {   // file: int32 n_phases, n_tiles; per tile int32 hi flag, int32 first cell (sweep index); 2 x u64 per task
-      std::vector<unsigned long long> h((size_t)2 * n_tasks);
-      CK(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
-      CK(cudaStreamSynchronize(st));
-      CK(cudaFree(d_trace));
-      std::vector<int32_t> hi(c->n_tiles), first(c->n_tiles), kind(P);
-      CK(cudaMemcpy(hi.data(), c->d_tile_hi, hi.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-      for (int t = 0; t < c->n_tiles; t++) first[t] = c->sweep_of_dev[(size_t)t * kTile];
-      for (int q = 0; q < P; q++) kind[q] = pl->phases[q].kind;
-      if (FILE *f = fopen(trace_path, "wb")) {
-        int32_t hdr[2] = {P, c->n_tiles};
-        fwrite(hdr, sizeof(int32_t), 2, f);
-        fwrite(kind.data(), sizeof(int32_t), kind.size(), f);
-        fwrite(hi.data(), sizeof(int32_t), hi.size(), f);
-        fwrite(first.data(), sizeof(int32_t), first.size(), f);
-        fwrite(h.data(), sizeof(unsigned long long), h.size(), f);
-        fclose(f);
-      }
-    }
-    // basin accumulators, phase by phase in the reference's order
-    for (int p = 0; p < P; p++) {
-      const double *ts = ps->d_tile_sums + (size_t)p * c->n_tiles * 4;
-      if (pl->phases[p].kind == 0)
-        reduce_sums_kernel<<<1, 256, 0, st>>>(ts, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, TRIBS_G_TotRain, TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
-      else
-        reduce_sums_kernel<<<1, 256, 0, st>>>(ts, c->n_tiles, 4, c->d_globals, TRIBS_G_Stok, -1, TRIBS_G_TotGWchange, TRIBS_G_TotMoist);
-      c->launches++;
-    }
-  }
-  if (getenv("TRIBS_DEBUG")) {
-    unsigned long long h[6];
-    CK(cudaMemcpyAsync(h, ps->d_headtail + 8, sizeof(h), cudaMemcpyDeviceToHost, st));
-    CK(cudaStreamSynchronize(st));
-    fprintf(stderr, "[tribs] batch: phases=%d tiles=%d hi_tiles=%d | lo warps: wait %.1f%% busy/task %.1f us tasks %llu | hi warps: wait %.1f%% busy/task %.1f us tasks %llu\n",
-            P, c->n_tiles, c->n_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2],
-            100.0 * h[3] / std::max(1.0, (double)(h[3] + h[4])), h[4] / std::max(1.0, (double)h[5]) / 1.9e3, h[5]);
-  }
-  ps->g += P;
-  // the handle's views after the batch: New = what the last phase wrote
-  c->dv = ((ps->g) & 1) ? d_odd : d_even;
-  c->new_valid = true;
-  if (pattern[n_steps - 1]) {
-    esrf_fixup_kernel<<<(n_pad + 255) / 256, 256, 0, st>>>(c->sv, c->dv, n_pad, steps[n_steps - 1].dt_gw, c->d_globals);
-    c->launches++;
-  }
-  for (int k = 0; k < n_steps; k++) if (pattern[k]) c->gw_dirty = true;
-  // routing of every step from its snapshot, in step order
-  {
-    PhaseTimer pt(c, 2);
-    const int slots = c->n_stream + 1, window = c->route_window;
-    for (int k = 0; k < n_steps; k++) {
-      DynView dvs = c->dv;
-      for (int q = 0; q < kSliceFields; q++)
-        dvs.f[kSliceFieldIdsHost[q]] = ps->d_slices + ((size_t)k * kSliceFields + q) * n_pad;
-      const double now = steps[k].current_time;
-      route_seg_kernel<<<c->seg_blocks, kSegBlock, 0, st>>>(c->sv, dvs, c->rc, c->d_seg_cell, c->d_seg_slot, c->d_seg_path,
-                                                            c->d_seg_area, c->d_sn_dev, c->n_seg, now, steps[k].qstrm_outlet,
-                                                            c->d_ring, c->d_seg_bnd);
-      route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, c->d_seg_bnd, c->seg_blocks, slots, now, c->d_ring,
-                                                 ps->d_qeff_steps + (size_t)k * slots);
-      const int cur_bin0 = (int)floor((0.0 - .01 * c->rc.tstep + now) / c->rc.output_interval);
-      const int cur_bin1 = (int)floor((0.0 - .99 * c->rc.tstep + now) / c->rc.output_interval);
-      const int cur_bin = (cur_bin0 == cur_bin1) ? cur_bin0 : -1;
-      const int bin_base = (int)floor((now + .01 * c->rc.tstep) / c->rc.output_interval);
-      size_t shmem = (size_t)kRouteWarps * (5 * (size_t)window + kMeans) * sizeof(double);
-      route_basin_stage1_kernel<<<c->route_blocks, kRouteWarps * 32, shmem, st>>>(c->sv, dvs, c->rc, c->mc, now, steps[k].qstrm_outlet,
-                                                                                   n_pad, window, bin_base, c->last_hill_dev,
-                                                                                   c->d_route_part, c->d_globals, water_balance_args(c, now));
-      const int n_vals = 5 * window + kMeans;
-      route_basin_stage2_kernel<<<(n_vals * 32 + 255) / 256, 256, 0, st>>>(c->d_route_part, c->route_blocks, window, bin_base,
-                                                                            cur_bin, c->rc.res_limit, c->d_results, c->d_globals);
-      c->launches += 4;
-    }
-    CK(cudaMemcpyAsync(c->d_qeff_now, ps->d_qeff_steps + (size_t)(n_steps - 1) * slots, (size_t)slots * sizeof(double),
-                       cudaMemcpyDeviceToDevice, st));
-  }
-  ps->last_steps = n_steps;
-  {  // RESET of the last step
-    PhaseTimer pt(c, 3);
-    swap_old_new(c);
-    const int zero5[5] = {TRIBS_F_Qpin, TRIBS_F_srf, TRIBS_F_sbsrf, TRIBS_F_hsrf, TRIBS_F_psrf};
-    for (int k = 0; k < 5; k++) CK(cudaMemsetAsync(c->dv.f[zero5[k]], 0, (size_t)n_pad * sizeof(double), st));
-    if (c->gw_dirty) {
-      CK(cudaMemsetAsync(c->dv.f[TRIBS_F_satsrf], 0, (size_t)n_pad * sizeof(double), st));
-      CK(cudaMemsetAsync(c->dv.f[TRIBS_F_gwchange], 0, (size_t)n_pad * sizeof(double), st));
-      c->gw_dirty = false;
-    }
-    c->new_valid = false;
-    c->at_boundary = true;
-  }
-  CK(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int tribs_gpu_retrieve_qeff_steps(tribs_handle_t c, int n_steps, double *out) {
-  if (!c || !out) return fail("tribs_gpu_retrieve_qeff_steps: null argument");
-  PipeState *ps = pipe_of(c);
-  if (n_steps > ps->last_steps) return fail("tribs_gpu_retrieve_qeff_steps: more steps than the last tribs_gpu_run held");
-  CK(cudaSetDevice(c->device));
-  if (check_sweep_abort(c)) return 1;
-  CK(cudaMemcpyAsync(out, ps->d_qeff_steps, (size_t)n_steps * (c->n_stream + 1) * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
-  return 0;
-}
-
-static void tribs_free_pipe(tribs_ctx *c) {
-  delete c->pipe;   // its device buffers live in the handle's allocation list
-  c->pipe = nullptr;
-}
+#include "pipeline.cuh"
+#include "checkpoint.cuh"

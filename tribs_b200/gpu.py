@@ -57,7 +57,15 @@ RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "PsrfRout", "SatsrfRout", "crr", "
 GLOBALS = ["Stok", "TotRain", "TotGWchange", "TotMoist", "psrf_last", "hillvel_last", "BasinRain", "BasinEvap",
            "BasinRunoff"]
 PHASE_UNSAT, PHASE_SAT, PHASE_ROUTE, PHASE_RESET = 1, 2, 4, 8
-RAIN_KEEP, RAIN_UNIFORM, RAIN_PER_CELL = 0, 1, 2
+RAIN_KEEP, RAIN_UNIFORM, RAIN_PER_CELL, RAIN_GAUGES = 0, 1, 2, 3
+IPC_HANDLE_BYTES = 64
+
+
+class GaugeRain:
+    """Rain of one step given per rain gauge (tribs_gpu_set_rain_gauges holds the cell -> gauge map)."""
+
+    def __init__(self, values):
+        self.values = np.ascontiguousarray(values, np.float64)
 
 PD = C.POINTER(C.c_double)
 PI = C.POINTER(C.c_int32)
@@ -88,7 +96,8 @@ class StateT(C.Structure):
 
 
 class Part(C.Structure):
-    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("nccl_unique_id", C.c_void_p), ("cell_owner", PI)]
+    _fields_ = [("rank", C.c_int32), ("nranks", C.c_int32), ("n_parts", C.c_int32), ("max_batch_steps", C.c_int32),
+                ("cell_owner", PI)]
 
 
 class Step(C.Structure):
@@ -132,7 +141,9 @@ EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retri
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
            "tribs_gpu_phase_ms", "tribs_gpu_wait", "tribs_gpu_stream", "tribs_gpu_destroy",
-           "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
+           "tribs_gpu_set_rain_gauges", "tribs_gpu_ipc_export", "tribs_gpu_attach_peers", "tribs_gpu_attach_local",
+           "tribs_gpu_owned_range", "tribs_gpu_snapshot", "tribs_gpu_rollback", "tribs_gpu_save_state",
+           "tribs_gpu_load_state", "tribs_gpu_reserve_batch", "tribs_gpu_set_partition", "tribs_gpu_halo_pack", "tribs_gpu_halo_unpack", "tribs_gpu_set_global",
            "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
            "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync", "tribs_gpu_snow_members",
            "tribs_gpu_snow_push", "tribs_gpu_snow_set_members",
@@ -187,6 +198,16 @@ def load():
     L.tribs_gpu_snow_members.argtypes = [H, PD, C.POINTER(C.c_int32)]
     L.tribs_gpu_snow_push.argtypes = [H, C.c_uint64, C.POINTER(PD)]
     L.tribs_gpu_snow_set_members.argtypes = [H, PD]
+    L.tribs_gpu_set_rain_gauges.argtypes = [H, C.c_int32, PI]
+    L.tribs_gpu_ipc_export.argtypes = [H, C.c_void_p]
+    L.tribs_gpu_attach_peers.argtypes = [H, C.c_void_p]
+    L.tribs_gpu_attach_local.argtypes = [C.POINTER(H), C.c_int]
+    L.tribs_gpu_owned_range.argtypes = [H, PI, PI]
+    L.tribs_gpu_snapshot.argtypes = [H]
+    L.tribs_gpu_rollback.argtypes = [H]
+    L.tribs_gpu_save_state.argtypes = [H, C.c_char_p]
+    L.tribs_gpu_load_state.argtypes = [H, C.c_char_p]
+    L.tribs_gpu_reserve_batch.argtypes = [H, C.c_int]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -226,7 +247,10 @@ _PRM_INT = ["EToption", "Ioption", "SnOpt", "RdstrOption"]
 class GpuBasin:
     """Owns one tribs_handle_t. `basin` is a dict of flattened arrays in sweep order."""
 
-    def __init__(self, basin: dict):
+    def __init__(self, basin: dict, part: dict | None = None):
+        """part (optional): rank, nranks, cell_owner [n] and, for nranks > 1, max_batch_steps: the reach
+        partition of tribs_part_t. nranks == 1 with several partitions in cell_owner lays the basin out
+        and sums it like the multi-GPU run, on one GPU."""
         self.L = load()
         b = basin
         self.n = int(b["n_active"][0])
@@ -252,7 +276,20 @@ class GpuBasin:
             if src is not None:
                 a = np.ascontiguousarray(src, np.float64); self._keep.append(a); st.f[k] = _d(a)
         self.h = C.c_void_p()
-        _chk(self.L.tribs_gpu_init(C.byref(mesh), C.byref(prm), C.byref(st), None, C.byref(self.h)))
+        pt = None
+        self.rank, self.nranks = 0, 1
+        if part is not None:
+            own = np.ascontiguousarray(part["cell_owner"], np.int32); self._keep.append(own)
+            if own.size != self.n:
+                raise ValueError("cell_owner must have one entry per active cell")
+            pt = Part()
+            pt.rank, pt.nranks = int(part.get("rank", 0)), int(part.get("nranks", 1))
+            pt.n_parts = int(part.get("n_parts", own.max() + 1 if pt.nranks == 1 else pt.nranks))
+            pt.max_batch_steps = int(part.get("max_batch_steps", 64))
+            pt.cell_owner = _i(own)
+            self.rank, self.nranks = pt.rank, pt.nranks
+        _chk(self.L.tribs_gpu_init(C.byref(mesh), C.byref(prm), C.byref(st), C.byref(pt) if pt is not None else None,
+                                   C.byref(self.h)))
         self.tstep = prm.tstep
         self.gwstep = prm.gwstep
         self.etistep = prm.etistep
@@ -269,6 +306,9 @@ class GpuBasin:
         s.hourly_reset = hourly_reset
         if rain is None:
             s.rain_mode = RAIN_KEEP
+        elif isinstance(rain, GaugeRain):
+            s.rain_mode = RAIN_GAUGES
+            s.rain = _d(rain.values)
         elif np.isscalar(rain):
             s.rain_mode = RAIN_UNIFORM
             s.rain_uniform = float(rain)
@@ -303,16 +343,68 @@ class GpuBasin:
             rain = sd.get("rain")
             if rain is None:
                 s.rain_mode = RAIN_KEEP
+            elif isinstance(rain, GaugeRain):
+                keep.append(rain.values)
+                s.rain_mode = RAIN_GAUGES
+                s.rain = _d(rain.values)
             elif np.isscalar(rain):
                 s.rain_mode = RAIN_UNIFORM
                 s.rain_uniform = float(rain)
             else:
                 a = np.ascontiguousarray(rain, np.float64); keep.append(a)
+                if a.size != self.n:
+                    raise ValueError(f"rain has {a.size} entries, the basin has {self.n} cells")
                 s.rain_mode = RAIN_PER_CELL
                 s.rain = _d(a)
             s.qstrm_outlet = sd.get("qstrm_outlet", 0.0)
             masks[q] = PHASE_UNSAT | PHASE_ROUTE | PHASE_RESET | (PHASE_SAT if sd.get("sat") else 0)
         _chk(self.L.tribs_gpu_run(self.h, k, arr, masks))
+
+    # -- rain gauges and peer-memory partitions --------------------------------------------------
+    def set_rain_gauges(self, cell_gauge, n_gauges: int | None = None):
+        g = np.ascontiguousarray(cell_gauge, np.int32)
+        _chk(self.L.tribs_gpu_set_rain_gauges(self.h, int(g.max()) + 1 if n_gauges is None else int(n_gauges), _i(g)))
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(IPC_HANDLE_BYTES)
+        _chk(self.L.tribs_gpu_ipc_export(self.h, buf))
+        return buf.raw
+
+    def attach_peers(self, handles: list[bytes]):
+        blob = b"".join(handles)
+        if len(blob) != IPC_HANDLE_BYTES * self.nranks:
+            raise ValueError("one 64-byte handle per rank, in rank order")
+        _chk(self.L.tribs_gpu_attach_peers(self.h, C.create_string_buffer(blob, len(blob))))
+
+    @staticmethod
+    def attach_local(devs: list["GpuBasin"]):
+        arr = (C.c_void_p * len(devs))(*[d.h for d in devs])
+        _chk(load().tribs_gpu_attach_local(arr, len(devs)))
+
+    def snapshot(self):
+        _chk(self.L.tribs_gpu_snapshot(self.h))
+
+    def rollback(self):
+        _chk(self.L.tribs_gpu_rollback(self.h))
+
+    def save_state(self, path: str):
+        _chk(self.L.tribs_gpu_save_state(self.h, path.encode()))
+
+    def load_state(self, path: str):
+        _chk(self.L.tribs_gpu_load_state(self.h, path.encode()))
+
+    def reserve_batch(self, n_steps: int):
+        _chk(self.L.tribs_gpu_reserve_batch(self.h, int(n_steps)))
+
+    def owned_range(self):
+        a, b = C.c_int32(0), C.c_int32(0)
+        _chk(self.L.tribs_gpu_owned_range(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def device_index(self) -> np.ndarray:
+        out = np.empty(self.n, np.int32)
+        _chk(self.L.tribs_gpu_device_index(self.h, _i(out)))
+        return out
 
     def retrieve_qeff_steps(self, k: int) -> np.ndarray:
         out = np.empty((k, self.n_stream + 1))

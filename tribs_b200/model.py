@@ -202,8 +202,8 @@ class tCOutput:
 class Simulator:
     """simulation_loop() for the path: Advance, rain, UnSat, [ResetGW, Sat], SurfaceFlow, Reset."""
 
-    def __init__(self, basin: dict, rain_schedule=None, gw_on: bool | None = None):
-        self.dev = gpu.GpuBasin(basin)
+    def __init__(self, basin: dict, rain_schedule=None, gw_on: bool | None = None, part: dict | None = None):
+        self.dev = gpu.GpuBasin(basin, part=part)
         b = basin
         self.timer = tRunTimer(float(b["tstep"][0]), float(b["gwstep"][0]), float(b["etistep"][0]),
                                float(b["endtime"][0]))
