@@ -70,7 +70,7 @@ void hc_sat(int n, double **sf, int32_t **si, double **ef, double **fields, cons
   StepConst t;
   t.dt = 0.0; t.dt_gw = dtgw; t.now = now; t.elapsed = elapsed; t.hourly_reset = 0; t.psrf_last = psrf_last;
   std::vector<double> elev(n), tr(n);
-  for (int i = 0; i < n; i++) sat_prepare_cell(s, d, i, elev.data(), tr.data());
+  for (int i = 0; i < n; i++) sat_prepare_cell(s, d.f[TRIBS_F_NwtOld], i, elev.data(), tr.data());
   for (int i = 0; i < n; i++) {
     double gw = sat_gather<32>(s, d, i, elev.data(), tr.data(), overflow);
     SatSums sums;

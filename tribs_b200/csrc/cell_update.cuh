@@ -207,8 +207,8 @@ TRIBS_HD void unsat_cell_store(UnsatCellInputs &u, const DynView &d, int i, doub
 
 // ---------------------------------------------------------------------------------- phase SAT
 // pre-pass: water-table elevation and finite-depth transmissivity of every cell (2686-2717, 2758)
-TRIBS_HD void sat_prepare_cell(const StaticView &s, const DynView &d, int i, double *wt_elev, double *transm) {
-  double nwt = d.f[TRIBS_F_NwtOld][i];
+TRIBS_HD void sat_prepare_cell(const StaticView &s, const double *nwt_old, int i, double *wt_elev, double *transm) {
+  double nwt = nwt_old[i];
   double cs = s.cos_gw[i];
   if (nwt == 0.0) wt_elev[i] = s.z[i] - ((-s.psib[i]) / (cs * 1000.0));
   else wt_elev[i] = s.z[i] - (nwt / (cs * 1000.0));

@@ -254,98 +254,11 @@ struct Column {
     return (z2 - z1) * ths;
   }
 
-  // -------------------------------------------------------------- root finders
-  TRIBS_HD void poly_wt(double x, double &fv, double &dv, double c1, double c2, double c3) const {
-    fv = c1 * m_pow(x, lam) + c3 * m_pow(x, (lam - 1.0)) + c2;
-    dv = c1 * lam * m_pow(x, (lam - 1.0)) + c3 * (lam - 1.0) * m_pow(x, (lam - 2.0));
-  }
-  TRIBS_HD void poly_front(double x, double nwt, double &fv, double &dv, double c1, double c2, double c3) const {
-    fv = c1 * x * m_pow((nwt - x), (lam - 1.0)) + c3 * m_pow((nwt - x), (lam - 1.0)) - c2;
-    dv = c1 * m_pow((nwt - x), (lam - 1.0)) - c1 * (lam - 1.0) * x * m_pow((nwt - x), (lam - 2.0)) -
-         c3 * (lam - 1.0) * m_pow((nwt - x), (lam - 2.0));
-  }
-
-  // safeguarded Newton / bisection in a bracket (4094-4167), 30 iterations at most
-  TRIBS_HD double bracketed_root(double c1, double c2, double c3, double x1, double x2, double xacc, double xguess) const {
-    double df = 0.0, dx, dxold, fx, fh = 0.0, fl = 0.0, temp, xh, xl, rts;
-    poly_wt(x1, fl, df, c1, c2, c3);
-    poly_wt(x2, fh, df, c1, c2, c3);
-    if ((fl > 0.0 && fh > 0.0) || (fl < 0.0 && fh < 0.0)) return xguess;
-    if (fl == 0.0) return x1;
-    if (fh == 0.0) return x2;
-    if (fl < 0.0) { xl = x1; xh = x2; } else { xh = x1; xl = x2; }
-    rts = xguess;
-    dxold = fabs(x2 - x1);
-    dx = dxold;
-    poly_wt(rts, fx, df, c1, c2, c3);
-    for (int j = 1; j <= 30; j++) {
-      if ((((rts - xh) * df - fx) * ((rts - xl) * df - fx) > 0.0) || (fabs(2.0 * fx) > fabs(dxold * df))) {
-        dxold = dx;
-        dx = 0.5 * (xh - xl);
-        rts = xl + dx;
-        if (xl == rts) return rts;
-      } else {
-        dxold = dx;
-        dx = fx / df;
-        temp = rts;
-        rts -= dx;
-        if (temp == rts) return rts;
-      }
-      if (fabs(dx) < xacc) return rts;
-      poly_wt(rts, fx, df, c1, c2, c3);
-      if (fx < 0.0) xl = rts; else xh = rts;
-    }
-    return xguess;
-  }
-
-  // water-table depth whose initial profile has moisture deficit dm (3937-4020)
-  TRIBS_HD_NOINLINE double solve_wt(double dm, double nwt) {
-    const double kDmin = 1.0E-5, kDxTol = 1.0E-5;
-    double c1, c2, c3, fvalue = 0, fdvalue = 0, x = 0, dx = 0, xinit, xup, est = 0;
-    c1 = ths - thr;
-    c2 = c1 * m_pow((-psib), lam) / (lam - 1.0);
-    c3 = c1 * psib / (lam - 1.0) + psib * c1 - dm;
-    if (nwt == 0.0) {
-      xinit = dm * (lam - 1.0) / ((ths - thr) * lam) - psib;
-      xinit += 50.0;
-      if (xinit <= fabs(psib)) xinit = fabs(psib) + 50.0;
-    } else
-      xinit = nwt;
-    if (lam < 5.0) {
-      if ((ths * nwt - total_moist(nwt)) > dm) xup = ceil(nwt);
-      else xup = dbr + 1.0;
-      x = bracketed_root(c1, c2, c3, dm / (ths - thr) + fabs(psib), xup, kDxTol, xinit);
-    }
-    if (lam >= 5.0 || fabs(x - xinit) <= 1.0E-7) {
-      int i;
-      for (x = xinit, i = 0; i < 30; x -= dx, i++) {
-        poly_wt(x, fvalue, fdvalue, c1, c2, c3);
-        if (fabs(fdvalue) < kDmin) { est = x; break; }
-        dx = fvalue / fdvalue;
-        if (fabs(dx) < kDxTol) { est = x; break; }
-      }
-      if ((fabs(fdvalue) < kDmin) || (fabs(dx) < kDxTol)) x = est;
-      else x = nwt;
-    }
-    if (x > dbr) x = dbr;
-    return x;
-  }
-
+  // -------------------------------------------------------------- root finders (bodies below the struct)
+  // water-table depth whose initial profile has moisture deficit dm (3937-4020); see solve_wt_soil
+  TRIBS_HD double solve_wt(double dm, double nwt) const;
   // wetting-front depth after dm is taken from (flag 0) / added to (flag 1) the wedge (4037-4082)
-  TRIBS_HD_NOINLINE double solve_front(double dm, double nwt, double nf, int flag) const {
-    double c1, c2, c3, fvalue, fdvalue, x, dx = 0;
-    if (!flag) c1 = ths - thr; else c1 = -(ths - thr);
-    c2 = c1 * m_pow((-psib), lam) / (lam - 1);
-    c3 = c2 / m_pow((nwt - nf), (lam - 1)) - c1 * nf + dm;
-    int i;
-    for (x = nf, i = 0; i < 30; x -= dx, i++) {
-      poly_front(x, nwt, fvalue, fdvalue, c1, c2, c3);
-      dx = fvalue / fdvalue;
-      if (fabs(dx) < kDxTol2()) return x;
-    }
-    return nf;
-  }
-  TRIBS_HD static constexpr double kDxTol2() { return 1.0E-5; }
+  TRIBS_HD double solve_front(double dm, double nwt, double nf, int flag) const;
 
   // re-initialise the profile for water table nwt1: Mi = Mu = total moisture, no wedge rates
   TRIBS_HD void settle_profile() {
@@ -353,6 +266,122 @@ struct Column {
     mu1 = mi1;
   }
 };
+
+// ------------------------------------------------------------------ root finders, out of line
+// The two solvers are called from ~20 sites of the state machines. They take the five soil numbers
+// they need BY VALUE and return the root, so that no address of the caller's Column escapes: the
+// column then lives in registers instead of a stack frame that every helper call would force the
+// compiler to keep current (the round-1 kernel carried 1 KB of stack per thread for this).
+struct SoilK { double ths, thr, psib, lam, dbr; };
+
+TRIBS_HD void soil_poly_wt(const SoilK &k, double x, double &fv, double &dv, double c1, double c2, double c3) {
+  fv = c1 * m_pow(x, k.lam) + c3 * m_pow(x, (k.lam - 1.0)) + c2;
+  dv = c1 * k.lam * m_pow(x, (k.lam - 1.0)) + c3 * (k.lam - 1.0) * m_pow(x, (k.lam - 2.0));
+}
+
+// safeguarded Newton / bisection in a bracket (4094-4167), 30 iterations at most
+TRIBS_HD double soil_bracketed_root(const SoilK &k, double c1, double c2, double c3, double x1, double x2, double xacc, double xguess) {
+  double df = 0.0, dx, dxold, fx, fh = 0.0, fl = 0.0, temp, xh, xl, rts;
+  soil_poly_wt(k, x1, fl, df, c1, c2, c3);
+  soil_poly_wt(k, x2, fh, df, c1, c2, c3);
+  if ((fl > 0.0 && fh > 0.0) || (fl < 0.0 && fh < 0.0)) return xguess;
+  if (fl == 0.0) return x1;
+  if (fh == 0.0) return x2;
+  if (fl < 0.0) { xl = x1; xh = x2; } else { xh = x1; xl = x2; }
+  rts = xguess;
+  dxold = fabs(x2 - x1);
+  dx = dxold;
+  soil_poly_wt(k, rts, fx, df, c1, c2, c3);
+  for (int j = 1; j <= 30; j++) {
+    if ((((rts - xh) * df - fx) * ((rts - xl) * df - fx) > 0.0) || (fabs(2.0 * fx) > fabs(dxold * df))) {
+      dxold = dx;
+      dx = 0.5 * (xh - xl);
+      rts = xl + dx;
+      if (xl == rts) return rts;
+    } else {
+      dxold = dx;
+      dx = fx / df;
+      temp = rts;
+      rts -= dx;
+      if (temp == rts) return rts;
+    }
+    if (fabs(dx) < xacc) return rts;
+    soil_poly_wt(k, rts, fx, df, c1, c2, c3);
+    if (fx < 0.0) xl = rts; else xh = rts;
+  }
+  return xguess;
+}
+
+// total moisture above a water table at depth nwt (tHydroModel::get_Total_Moist 2240-2262) without the
+// member side effect (the reference zeroes NwtNew when the table lies inside the capillary fringe; every
+// caller of the solver assigns NwtNew from its result right afterwards, so the side effect never shows)
+TRIBS_HD double soil_total_moist(const SoilK &k, double nwt) {
+  double dm = 0.0;
+  if (nwt >= fabs(k.psib)) {
+    if (k.lam > (1.0 - 1.0E-6) && k.lam < (1.0 + 1.0E-6))
+      dm = k.thr * (nwt + k.psib) - fabs(k.psib) * (k.ths - k.thr) * m_log((-k.psib) / nwt) - k.ths * k.psib;
+    else
+      dm = k.thr * (nwt + k.psib) - k.ths * k.psib - (k.ths - k.thr) / (k.lam - 1.0) * (k.psib + nwt * m_pow((-k.psib / nwt), k.lam));
+  }
+  return dm;
+}
+
+// water-table depth whose initial profile has moisture deficit dm (3937-4020)
+TRIBS_HD_NOINLINE double solve_wt_soil(SoilK k, double dm, double nwt) {
+  const double kDmin = 1.0E-5, kDxTol = 1.0E-5;
+  double c1, c2, c3, fvalue = 0, fdvalue = 0, x = 0, dx = 0, xinit, xup, est = 0;
+  c1 = k.ths - k.thr;
+  c2 = c1 * m_pow((-k.psib), k.lam) / (k.lam - 1.0);
+  c3 = c1 * k.psib / (k.lam - 1.0) + k.psib * c1 - dm;
+  if (nwt == 0.0) {
+    xinit = dm * (k.lam - 1.0) / ((k.ths - k.thr) * k.lam) - k.psib;
+    xinit += 50.0;
+    if (xinit <= fabs(k.psib)) xinit = fabs(k.psib) + 50.0;
+  } else
+    xinit = nwt;
+  if (k.lam < 5.0) {
+    if ((k.ths * nwt - soil_total_moist(k, nwt)) > dm) xup = ceil(nwt);
+    else xup = k.dbr + 1.0;
+    x = soil_bracketed_root(k, c1, c2, c3, dm / (k.ths - k.thr) + fabs(k.psib), xup, kDxTol, xinit);
+  }
+  if (k.lam >= 5.0 || fabs(x - xinit) <= 1.0E-7) {
+    int i;
+    for (x = xinit, i = 0; i < 30; x -= dx, i++) {
+      soil_poly_wt(k, x, fvalue, fdvalue, c1, c2, c3);
+      if (fabs(fdvalue) < kDmin) { est = x; break; }
+      dx = fvalue / fdvalue;
+      if (fabs(dx) < kDxTol) { est = x; break; }
+    }
+    if ((fabs(fdvalue) < kDmin) || (fabs(dx) < kDxTol)) x = est;
+    else x = nwt;
+  }
+  if (x > k.dbr) x = k.dbr;
+  return x;
+}
+
+// wetting-front depth after dm is taken from (flag 0) / added to (flag 1) the wedge (4037-4082)
+TRIBS_HD_NOINLINE double solve_front_soil(SoilK k, double dm, double nwt, double nf, int flag) {
+  double c1, c2, c3, fvalue, fdvalue, x, dx = 0;
+  if (!flag) c1 = k.ths - k.thr; else c1 = -(k.ths - k.thr);
+  c2 = c1 * m_pow((-k.psib), k.lam) / (k.lam - 1);
+  c3 = c2 / m_pow((nwt - nf), (k.lam - 1)) - c1 * nf + dm;
+  int i;
+  for (x = nf, i = 0; i < 30; x -= dx, i++) {
+    fvalue = c1 * x * m_pow((nwt - x), (k.lam - 1.0)) + c3 * m_pow((nwt - x), (k.lam - 1.0)) - c2;
+    fdvalue = c1 * m_pow((nwt - x), (k.lam - 1.0)) - c1 * (k.lam - 1.0) * x * m_pow((nwt - x), (k.lam - 2.0)) -
+              c3 * (k.lam - 1.0) * m_pow((nwt - x), (k.lam - 2.0));
+    dx = fvalue / fdvalue;
+    if (fabs(dx) < 1.0E-5) return x;
+  }
+  return nf;
+}
+
+TRIBS_HD double Column::solve_wt(double dm, double nwt) const {
+  return solve_wt_soil(SoilK{ths, thr, psib, lam, dbr}, dm, nwt);
+}
+TRIBS_HD double Column::solve_front(double dm, double nwt, double nf, int flag) const {
+  return solve_front_soil(SoilK{ths, thr, psib, lam, dbr}, dm, nwt, nf, flag);
+}
 
 // ------------------------------------------------------------------ Lambert W (principal branch)
 struct Cx { double r, i; };

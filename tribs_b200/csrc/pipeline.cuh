@@ -171,8 +171,12 @@ __global__ void peer_barrier_kernel(PeerView pv, long long *flags, long long epo
 #ifndef TRIBS_PIPE_MIN_BLOCKS
 #define TRIBS_PIPE_MIN_BLOCKS 4
 #endif
+#ifndef TRIBS_PIPE_THREADS
+#define TRIBS_PIPE_THREADS 128
+#endif
+constexpr int kPipeThreads = TRIBS_PIPE_THREADS, kPipeWarps = kPipeThreads / 32;
 template <int MAXC>
-__global__ void __launch_bounds__(128, TRIBS_PIPE_MIN_BLOCKS)
+__global__ void __launch_bounds__(kPipeThreads, TRIBS_PIPE_MIN_BLOCKS)
 pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, RouteConst rc, PipeArgs a) {
   const int lane = threadIdx.x & 31;
   // Two ticket queues. `n_hi_warps` warps, spread over the SMs (warp 0 of every block first), serve the "hi" queue
@@ -180,18 +184,43 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
   // path and must never sit behind a backlog of bulk work); every other warp serves "lo". A warp
   // takes a ticket (atomicAdd on the head) and waits for exactly that slot to be filled, so a
   // newly released task is picked up at once by the warp that holds its ticket.
+#ifdef TRIBS_BLOCK_TICKETS
+  // The four warps of a "lo" block take four consecutive tickets together. Tiles of one bucket and phase are
+  // released together and sit next to each other in the queue, so the warps of a block run the same part of
+  // the (large, branchy) column code at about the same time and share its lines in the SM's instruction
+  // cache (32 KB against ~80 KB of hot code) instead of 24 warps streaming 24 different parts of it.
+  const bool hi_warp = (int)blockIdx.x * kPipeWarps < a.n_hi_warps;     // whole blocks serve the "hi" queue
+  __shared__ int sh_ticket;
+#else
   const bool hi_warp = (int)((threadIdx.x >> 5) * gridDim.x + blockIdx.x) < a.n_hi_warps;
+#endif
   const int my_total = hi_warp ? a.n_hi_tasks : a.n_lo_tasks;
   int32_t *my_head = a.rq.ctl + (hi_warp ? 0 : 2);
   const int32_t *my_queue = a.rq.queue + (hi_warp ? 0 : a.rq.n_tasks);
   const unsigned ns_cap = hi_warp ? a.rq.cap_hi_ns : a.rq.cap_lo_ns;   // back-off ceiling of the queue poll
   const bool multi = a.pv.n_ranks > 1;
-  long long t_wait = 0, t_busy = 0, n_done = 0;
+  long long t_wait = 0, t_busy = 0, n_done = 0, t_bar = 0;
   long long t_mark = clock64();
   for (;;) {
     int task = -1;
+#ifdef TRIBS_BLOCK_TICKETS
+    int blk_idx = 0;
+    if (!hi_warp) {
+      const long long tb0 = clock64();
+      __syncthreads();
+      if (threadIdx.x == 0) sh_ticket = *(volatile int32_t *)a.abort_flag ? 0x7fffffff : atomicAdd(my_head, kPipeWarps);
+      __syncthreads();
+      t_bar += clock64() - tb0;
+      blk_idx = sh_ticket;
+      if (blk_idx >= my_total) break;      // uniform over the block
+    }
+#endif
     if (lane == 0) {
+#ifdef TRIBS_BLOCK_TICKETS
+      const int idx = hi_warp ? atomicAdd(my_head, 1) : blk_idx + (int)(threadIdx.x >> 5);
+#else
       const int idx = atomicAdd(my_head, 1);
+#endif
       if (idx < my_total) {
         unsigned spins = 0, ns = 32;
         unsigned long long t_first = 0;
@@ -210,7 +239,11 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
     }
     task = __shfl_sync(0xffffffffu, task, 0);
     { const long long now_c = clock64(); t_wait += now_c - t_mark; t_mark = now_c; }
+#ifdef TRIBS_BLOCK_TICKETS
+    if (task < 0) { if (hi_warp) break; else continue; }   // a lo warp past the end leaves with its block
+#else
     if (task < 0) break;
+#endif
     const int p = task / a.n_tiles, tile = task - p * a.n_tiles;
     if (a.rq.trace && lane == 0) a.rq.trace[2 * (size_t)task] = global_ns();   // TRIBS_TRACE: task timeline
     fence_tasks(multi);   // acquire side of the producers' fence -> counter -> queue hand-off
@@ -251,9 +284,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
         if (i == a.last_sweep_dev) *a.psrf_slot = u.c.psrf;
         if (next_sat) {
           // ResetGW + the edge pre-pass for this cell: the post-sweep state is what SAT calls Old
-          DynView dn = d;
-          dn.f[TRIBS_F_NwtOld] = d.f[TRIBS_F_NwtNew];
-          sat_prepare_cell(s, dn, i, a.wt_elev, a.transm);
+          sat_prepare_cell(s, d.f[TRIBS_F_NwtNew], i, a.wt_elev, a.transm);
         }
       } else {
         int overflow = 0;
@@ -307,6 +338,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
     atomicAdd(st + 0, (unsigned long long)t_wait);
     atomicAdd(st + 1, (unsigned long long)t_busy);
     atomicAdd(st + 2, (unsigned long long)n_done);
+    if (!hi_warp) atomicAdd((unsigned long long *)(a.rq.ctl + 8) + 6, (unsigned long long)t_bar);
   }
 }
 
@@ -498,7 +530,7 @@ static int build_tile_graph(tribs_ctx *c, PipeState *ps) {
 
 template <int MAXC>
 static int pipe_occupancy(int *per_sm) {
-  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, pipeline_kernel<MAXC>, 128, 0) != cudaSuccess;
+  return cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, pipeline_kernel<MAXC>, kPipeThreads, 0) != cudaSuccess;
 }
 
 static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
@@ -663,10 +695,19 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     const int blocks = std::max(1, ps->blocks / std::max(1, ps->share));
     // warps serving the "hi" queue: one per SM for a single river; on a dendritic network the stream
     // tiles are a sizeable share of all tasks and get that share of the warps
-    const int total_warps = blocks * 4;
+    const int total_warps = blocks * kPipeWarps;
+#ifdef TRIBS_BLOCK_TICKETS
+    // whole blocks: the hi tasks are about as long as the others but lie on the chain every hillslope waits for;
+    // measured on the 1M-cell valley (5 % hi tiles, 2368 warps): 160 warps 697 M, 256: 768 M, 400: 747 M, 600: 692 M
+    int n_hi_warps = std::max(std::min(total_warps / 2, ps->n_sms),
+                              (int)std::lround(2.2 * total_warps * (double)ps->my_hi_tiles / std::max(1, own_tiles)));
+    n_hi_warps = ((n_hi_warps + kPipeWarps - 1) / kPipeWarps) * kPipeWarps;
+    n_hi_warps = std::max(kPipeWarps, std::min(n_hi_warps, total_warps - kPipeWarps));
+#else
     int n_hi_warps = std::max(std::min(blocks, ps->n_sms),
                               (int)std::lround(1.25 * total_warps * (double)ps->my_hi_tiles / std::max(1, own_tiles)));
     n_hi_warps = std::min(n_hi_warps, total_warps - std::min(blocks, ps->n_sms));
+#endif
     if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_warps = std::max(1, std::min(total_warps - 1, atoi(e)));
     const long long n_init = (long long)P * own_tiles;
     pipeline_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(ps->graph, ps->d_phases, P, c->n_tiles, tile0, own_tiles,
@@ -688,7 +729,7 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &c->rc, &a};
     const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
                      : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
-    CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(128), args, 0, st));
+    CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kPipeThreads), args, 0, st));
     c->launches++;
     if (d_trace) {   // file: int32 n_phases, n_tiles; per tile int32 hi flag, int32 first cell (sweep index); 2 x u64 per task
       std::vector<unsigned long long> h((size_t)2 * n_tasks);
@@ -713,11 +754,11 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     if (reduce_sums_local(c, ps->d_tile_sums, (size_t)own_tiles * 4, tile0, P, ps->d_sums_part) ) return 1;
   }
   if (getenv("TRIBS_DEBUG") && c->n_ranks == 1) {
-    unsigned long long h[6];
+    unsigned long long h[7];
     CK(cudaMemcpyAsync(h, ps->d_headtail + 8, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
-    fprintf(stderr, "[tribs] rank %d batch: phases=%d tiles=%d hi_tiles=%d | lo warps: wait %.1f%% busy/task %.1f us tasks %llu | hi warps: wait %.1f%% busy/task %.1f us tasks %llu\n",
-            c->rank, P, own_tiles, ps->my_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2],
+    fprintf(stderr, "[tribs] rank %d batch: phases=%d tiles=%d hi_tiles=%d | lo warps: wait %.1f%% busy/task %.1f us tasks %llu (block barrier %.1f%%) | hi warps: wait %.1f%% busy/task %.1f us tasks %llu\n",
+            c->rank, P, own_tiles, ps->my_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2], 100.0 * h[6] / std::max(1.0, (double)(h[0] + h[1])),
             100.0 * h[3] / std::max(1.0, (double)(h[3] + h[4])), h[4] / std::max(1.0, (double)h[5]) / 1.9e3, h[5]);
   }
   ps->g += P;

@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(256)
 sat_prepare_kernel(StaticView s, DynView d, double *wt_elev, double *transm, int n_pad) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_pad || s.boundary[i] < 0) return;
-  sat_prepare_cell(s, d, i, wt_elev, transm);
+  sat_prepare_cell(s, d.f[TRIBS_F_NwtOld], i, wt_elev, transm);
 }
 
 template <int MAXC>
