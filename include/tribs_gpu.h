@@ -344,6 +344,11 @@ typedef struct {
 int tribs_gpu_et_init(tribs_handle_t h, const tribs_et_params_t *prm);
 int tribs_gpu_et_step(tribs_handle_t h, const tribs_et_step_t *s);
 /* host[k] (k < TRIBS_N_ET_FIELDS) receives / supplies field k in sweep order when bit k is set */
+/* tribs_gpu_run with kernel (1) inside the batch: et_steps[k] (or NULL) is what tribs_gpu_et_step would be called
+ * with before the sweep of step k (Simulator::SurfaceHydroProcesses, tSimul.cpp:419-461). The records of all ET
+ * steps of the batch are copied before the call returns. OPTSNOW 0 only (the snow pack runs between batches). */
+int tribs_gpu_run_et(tribs_handle_t h, int n_steps, const tribs_step_t *steps, const uint32_t *phase_masks,
+                     const tribs_et_step_t *const *et_steps);
 int tribs_gpu_et_sync(tribs_handle_t h, uint64_t et_field_mask, double *const *host);
 int tribs_gpu_et_push(tribs_handle_t h, uint64_t et_field_mask, const double *const *host);
 

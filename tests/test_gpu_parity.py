@@ -229,16 +229,19 @@ def test_gpu_batch_matches_live_reference_after_full_run(built):
 
 
 # ------------------------------------------------------------------ one reach partition per GPU
-@pytest.mark.parametrize("name,steps", [("deep", 200), ("shallow", 200), ("met", 200)])
-def test_two_gpus_bitwise_equal_to_one(name, steps, built):
-    """The reference's own multi-rank contract (serial == MPI, test_big_spring.py:5-22)."""
+@pytest.mark.parametrize("side,steps", [(60, 32), (150, 48)])
+def test_ranks_on_separate_gpus_bitwise_equal_to_one(side, steps, built):
+    """The reference's own multi-rank contract (serial == MPI, test_big_spring.py:5-22), one process per GPU over
+    cudaIpc + NVLink. On a one-GPU box the same protocol is covered by tests/test_gpu_peers.py (ranks as handles of
+    one process), so nothing N>1-specific goes untested there."""
     import subprocess
     import sys
     import torch
-    if torch.cuda.device_count() < 2:
-        pytest.skip("needs 2 GPUs on the box")
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("one GPU on the box: see tests/test_gpu_peers.py for the same protocol with in-process ranks")
     from refrun import ROOT
-    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                        "--master-addr", "127.0.0.1", "--master-port", "29541", f"{ROOT}/tests/mgpu_check.py", name, str(steps)],
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+                        "--master-addr", "127.0.0.1", "--master-port", "29541", f"{ROOT}/tests/mgpu_check.py", str(side), str(steps)],
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "BITWISE EQUAL" in r.stdout, r.stdout[-2000:] + r.stderr[-2000:]

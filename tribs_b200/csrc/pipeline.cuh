@@ -29,8 +29,10 @@
 // only per-cell snapshot a batch keeps is the runoff the hillslope routing (route_seg_kernel) reads.
 // ====================================================================================
 struct PhaseInfo {
-  int32_t kind;         // 0 UNSAT, 1 SAT
+  int32_t kind;         // 0 UNSAT, 1 SAT, 2 ET (kernel (1): callEvapoPotential / callEvapoTrans before the step's sweep)
   int32_t step;         // step index inside the batch
+  int32_t et_index;     // kind 2: which EtStepDev of the batch
+  int32_t pad_;
   int32_t prev_sat;     // the phase before this one was a SAT phase
   int32_t next_sat;     // the next phase is a SAT phase: produce wt_elev / transm
   int32_t last_of_step; // last phase of its step: routing record + runoff snapshot
@@ -97,8 +99,16 @@ struct PipeArgs {
   int32_t n_pad, n_tiles, tile0, n_own_tiles, own_begin, n_own, K, rec_stride, last_sweep_dev;
   int32_t n_hi_tasks, n_lo_tasks, n_hi_warps;
   int32_t *abort_flag, *flags;
+  const struct EtPack *et;         // kernel (1)'s constants, static arrays and fields (batches with ET phases)
+  const EtStepDev *et_steps;       // one per ET phase of the batch
   PeerView pv;
 };
+struct EtPack { EtConst k; EtStatic st; EtView ev; };
+// kernel (1) for one cell inside a batch: out of line, so that its 168 registers' worth of temporaries
+// live in this call's frame instead of raising the register count of every sweep task
+__device__ __noinline__ void et_phase_cell(const EtPack *et, const EtStepDev *s, const DynView *d, int i) {
+  et_cell(et->k, et->st, *s, et->ev, *d, i);
+}
 
 __device__ __forceinline__ void fence_tasks(bool sys) {
   if (sys) __threadfence_system(); else __threadfence();
@@ -131,8 +141,8 @@ pipeline_init_kernel(TileGraph g, const PhaseInfo *__restrict__ phases, int n_ph
   const int p = (int)(id / n_own_tiles), t = tile0 + (int)(id - (long long)p * n_own_tiles);
   const PhaseInfo &ph = phases[p];
   int c = 0;
-  if (ph.kind == 0) {
-    c += g.up_rp[t + 1] - g.up_rp[t];
+  if (ph.kind == 0 || ph.kind == 2) {   // an ET phase waits like a sweep, without the same-phase inflow
+    if (ph.kind == 0) c += g.up_rp[t + 1] - g.up_rp[t];
     if (p > 0) c += 1 + (ph.prev_sat ? g.nbr_rp[t + 1] - g.nbr_rp[t] : g.down_rp[t + 1] - g.down_rp[t]);
   } else if (p > 0)
     c += 1 + g.nbr_rp[t + 1] - g.nbr_rp[t];
@@ -276,7 +286,15 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
       const int r0 = a.g.down_rp[tile], r1 = a.g.down_rp[tile + 1];
       for (int k = r0 + lane; k < r1; k += 32) release_task(a, p, a.g.down[k]);
     }
-    if (act) {
+    if (kind == 2) {
+      if (act) {
+        // tRainfall::NewRain comes before SurfaceHydroProcesses in the reference's step: the ET sweep reads this step's rain
+        if (ph.t.rain_mode != 0)
+          d.f[TRIBS_F_Rain][i] = (ph.t.rain_mode == 1) ? ph.t.rain_uniform
+                                 : ((ph.t.rain_mode == 2) ? ph.t.rain_cells[i] : ph.t.rain_cells[ph.t.rain_gauge[i]]);
+        et_phase_cell(a.et, a.et_steps + ph.et_index, &d, i);
+      }
+    } else if (act) {
       if (kind == 0) {
         UnsatSums us;
         unsat_cell_store(u, d, i, qpin, m, ph.t, us);
@@ -389,6 +407,12 @@ struct PipeState {
   double *d_psrf = nullptr;        // psrf of the last swept cell (exported)
   long long *d_bar = nullptr;      // [kMaxParts] barrier flags (exported)
   PhaseInfo *d_phases = nullptr;
+  EtPack *d_etpack = nullptr;      // kernel (1) inside batches
+  EtPack h_etpack{};
+  EtStepDev *d_et_steps = nullptr; // [max_steps]
+  double *d_met_batch = nullptr;   // [max_steps][2][9 * met_cap] station records of the batch's ET phases
+  int met_batch_cap = 0;
+  std::vector<EtStepDev> h_et_steps;
   StepBins *d_bins = nullptr;
   int32_t *d_is_sat = nullptr;
   int32_t *d_cnt = nullptr, *d_queue = nullptr, *d_headtail = nullptr;
@@ -414,11 +438,17 @@ static int build_plan(PipeState *ps, const std::vector<uint8_t> &pattern, PipePl
   if (ps->plans.size() >= 8) ps->plans.erase(ps->plans.begin());   // host memory only; oldest first
   PipePlan pl;
   pl.pattern = pattern;
+  int n_et = 0;
   for (size_t sidx = 0; sidx < pattern.size(); sidx++) {
+    if (pattern[sidx] & 2) {
+      PhaseInfo e{};
+      e.kind = 2; e.step = (int)sidx; e.et_index = n_et++;
+      pl.phases.push_back(e);
+    }
     PhaseInfo u{};
-    u.kind = 0; u.step = (int)sidx; u.last_of_step = pattern[sidx] ? 0 : 1; u.next_sat = pattern[sidx];
+    u.kind = 0; u.step = (int)sidx; u.last_of_step = (pattern[sidx] & 1) ? 0 : 1; u.next_sat = pattern[sidx] & 1;
     pl.phases.push_back(u);
-    if (pattern[sidx]) {
+    if (pattern[sidx] & 1) {
       PhaseInfo v{};
       v.kind = 1; v.step = (int)sidx; v.last_of_step = 1;
       pl.phases.push_back(v);
@@ -428,7 +458,7 @@ static int build_plan(PipeState *ps, const std::vector<uint8_t> &pattern, PipePl
   for (int p = 0; p < P; p++) {
     pl.phases[p].prev_sat = p > 0 && pl.phases[p - 1].kind == 1;
     pl.phases[p].has_next = p + 1 < P;
-    pl.is_sat.push_back(pl.phases[p].kind);
+    pl.is_sat.push_back(pl.phases[p].kind == 1 ? 1 : 0);
   }
   pl.bins.resize(pattern.size());
   ps->plans.push_back(pl);
@@ -564,17 +594,19 @@ static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
       if (it != c->allocs.end()) { cudaFree(q); c->allocs.erase(it); }
     };
     drop(ps->d_srf); drop(ps->d_recs); drop(ps->d_tile_sums); drop(ps->d_qeff_out); drop(ps->d_rain); drop(ps->d_block_part);
-    drop(ps->d_phases); drop(ps->d_bins); drop(ps->d_is_sat);
+    drop(ps->d_phases); drop(ps->d_bins); drop(ps->d_is_sat); drop(ps->d_et_steps); drop(ps->d_met_batch);
+    ps->d_met_batch = nullptr; ps->met_batch_cap = 0;
     if (!c->slab.base) { drop(ps->d_qeff_steps); drop(ps->d_part_vec); drop(ps->d_sums_part); drop(ps->d_cnt); drop(ps->d_queue); }
     const size_t S = (size_t)n_steps, slots = (size_t)c->n_stream + 1;
-    if (shared_alloc(c, &ps->d_cnt, 2 * S * c->n_tiles) || shared_alloc(c, &ps->d_queue, 4 * S * c->n_tiles) ||
-        shared_alloc(c, &ps->d_part_vec, (size_t)c->n_parts * S * stride) || shared_alloc(c, &ps->d_sums_part, (size_t)c->n_parts * 2 * S * 4) ||
+    if (shared_alloc(c, &ps->d_cnt, 3 * S * c->n_tiles) || shared_alloc(c, &ps->d_queue, 6 * S * c->n_tiles) ||
+        shared_alloc(c, &ps->d_part_vec, (size_t)c->n_parts * S * stride) || shared_alloc(c, &ps->d_sums_part, (size_t)c->n_parts * 3 * S * 4) ||
         shared_alloc(c, &ps->d_qeff_steps, S * slots))
       return 1;
     if (dev_alloc(c, &ps->d_srf, S * n_own) || dev_alloc(c, &ps->d_recs, S * own_tiles * c->rec_stride) ||
-        dev_alloc(c, &ps->d_tile_sums, 2 * S * own_tiles * 4) || dev_alloc(c, &ps->d_qeff_out, S * slots) ||
+        dev_alloc(c, &ps->d_tile_sums, 3 * S * own_tiles * 4) || dev_alloc(c, &ps->d_qeff_out, S * slots) ||
         dev_alloc(c, &ps->d_block_part, c->my_parts.size() * S * kReduceBlocksMax * stride) ||
-        dev_alloc(c, &ps->d_phases, 2 * S) || dev_alloc(c, &ps->d_bins, S) || dev_alloc(c, &ps->d_is_sat, 2 * S))
+        dev_alloc(c, &ps->d_phases, 3 * S) || dev_alloc(c, &ps->d_bins, S) || dev_alloc(c, &ps->d_is_sat, 3 * S) ||
+        dev_alloc(c, &ps->d_et_steps, S) || (!ps->d_etpack && dev_alloc(c, &ps->d_etpack, 1)))
       return 1;
     ps->d_rain = nullptr;      // allocated when a step brings per-cell rain
     ps->max_steps = n_steps;
@@ -595,7 +627,75 @@ static const T *peer_host_ptr(tribs_ctx *c, PipeState *ps, int r, const T *mine)
   return (const T *)(ps->peer_base[r] + ((const char *)mine - c->slab.base));
 }
 
+// host-side part of tribs_gpu_et_step for one ET phase of a batch: the device form of the step and its station
+// records, staged into this phase's slice of the batch's record buffer
+static int stage_et_phase(tribs_ctx *c, PipeState *ps, int index, const tribs_et_step_t *s, EtStepDev *out) {
+  EtState *e = c->et;
+  if (s->hour < 0 || s->hour > 23) return fail("tribs_gpu_run_et: hour out of range");
+  static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014,   // stomResist, tEvapoTrans.cpp:1494-1496
+                                     0.995, 0.976, 0.976, 1.0, 1.053, 1.167, 1.354, 1.637,
+                                     2.043, 2.66, 3.215, 3.507, 3.689, 3.818, 3.923, 4.024};
+  EtStepDev d{};
+  d.do_potential = s->do_potential && e->k.et_option; d.do_components = s->do_components; d.intercept_flag = s->intercept_flag;
+  d.met_time = s->do_potential;
+  d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
+  d.cos_alpha = cos(asin(s->sinAlpha));
+  d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
+  d.sky_flag_from = s->sky_flag_from; d.te_met = s->te_met; d.te_eti = s->te_eti;
+  d.rs_ratio = rsRatio[s->hour];
+  const tribs_met_t *mets[2] = {d.do_potential ? s->met_potential : nullptr,
+                                (d.do_components && e->k.et_option) ? s->met_components : nullptr};
+  for (int sl = 0; sl < 2; sl++) {
+    const tribs_met_t *m = mets[sl];
+    if (!m) continue;
+    if (m->n_records <= 0) return fail("tribs_gpu_run_et: met record missing");
+    const double *src[9] = {m->air_temp, m->dew_temp, m->rel_humid, m->vap_press, m->atm_press,
+                            m->wind_speed, m->sky_cover, m->rad_global, m->elev};
+    for (int q = 0; q < 9; q++) if (!src[q]) return fail("tribs_gpu_run_et: met series missing");
+    const int nr = m->n_records;
+    if (nr > ps->met_batch_cap) {
+      if (ps->met_batch_cap > 0) return fail("tribs_gpu_run_et: the number of met records grew inside a run");
+      if (dev_alloc(c, &ps->d_met_batch, (size_t)ps->max_steps * 2 * 9 * nr)) return 1;
+      ps->met_batch_cap = nr;
+    }
+    if (m->cell_record) {
+      for (int i = 0; i < c->n; i++)
+        if (m->cell_record[i] < 0 || m->cell_record[i] >= nr) return fail("tribs_gpu_run_et: cell_record out of range");
+      e->h_rec = to_device_order<int32_t>(c, m->cell_record, 0);
+      CK(cudaMemcpyAsync(e->d_record[sl], e->h_rec.data(), e->h_rec.size() * sizeof(int32_t), cudaMemcpyHostToDevice, c->stream));
+      CK(cudaStreamSynchronize(c->stream));        // h_rec is reused by the next call
+      e->have_record[sl] = true;
+    } else if (!e->have_record[sl]) return fail("tribs_gpu_run_et: cell_record not given yet");
+    std::vector<double> pack((size_t)9 * nr);
+    for (int q = 0; q < 9; q++) memcpy(pack.data() + (size_t)q * nr, src[q], (size_t)nr * sizeof(double));
+    double *b = ps->d_met_batch + ((size_t)index * 2 + sl) * 9 * ps->met_batch_cap;
+    CK(cudaMemcpyAsync(b, pack.data(), pack.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));   // pageable: staged before the call returns
+    MetDev &o = sl == 0 ? d.pot : d.cmp;
+    o.cell_record = e->d_record[sl];
+    o.air_temp = b; o.dew_temp = b + nr; o.rel_humid = b + 2 * (size_t)nr; o.vap_press = b + 3 * (size_t)nr;
+    o.atm_press = b + 4 * (size_t)nr; o.wind_speed = b + 5 * (size_t)nr; o.sky_cover = b + 6 * (size_t)nr;
+    o.rad_global = b + 7 * (size_t)nr; o.elev = b + 8 * (size_t)nr;
+  }
+  *out = d;
+  return 0;
+}
+
+static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
+                     const tribs_et_step_t *const *et_steps);
 extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks) {
+  return run_batch(c, n_steps, steps, masks, nullptr);
+}
+// The same with kernel (1) inside the batch: et_steps[k] (or NULL) is what tribs_gpu_et_step would be called with
+// before the sweep of step k (Simulator::SurfaceHydroProcesses, tSimul.cpp:419-461). The ET / interception update
+// of a cell only needs that cell, so it is one more phase of the tile's dataflow: no launch boundary, no
+// basin-wide wait at every METSTEP.
+extern "C" int tribs_gpu_run_et(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
+                                const tribs_et_step_t *const *et_steps) {
+  return run_batch(c, n_steps, steps, masks, et_steps);
+}
+
+static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
+                     const tribs_et_step_t *const *et_steps) {
   if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
   CK(cudaSetDevice(c->device));
   if (c->partitioned) return fail("tribs_gpu_run: this handle was partitioned with tribs_gpu_set_partition (host-exchanged single steps); "
@@ -607,6 +707,11 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
   for (int k = 0; k < n_steps; k++) {
     if ((masks[k] & need) != need) return fail("tribs_gpu_run: every step must contain UNSAT, ROUTE and RESET");
     pattern[k] = (masks[k] & TRIBS_PHASE_SAT) ? 1 : 0;
+    if (et_steps && et_steps[k] && (et_steps[k]->do_potential || et_steps[k]->do_components)) {
+      if (!c->et) return fail("tribs_gpu_run_et: call tribs_gpu_et_init first");
+      if (c->et->snow_option) return fail("tribs_gpu_run_et: with OPTSNOW 1 the snow pack runs between batches (tribs_gpu_snow_step)");
+      pattern[k] |= 2;
+    }
   }
   PipeState *ps = pipe_of(c);
   if (c->n_ranks > 1 && !ps->attached) return fail("tribs_gpu_run: nranks > 1 needs tribs_gpu_attach_peers / tribs_gpu_attach_local first");
@@ -629,43 +734,61 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
   }
   const double hv0 = c->rc.velcoef / c->rc.velratio;
   int bin_lo = 0x7fffffff, bin_hi = -0x7fffffff;
-  for (int p = 0; p < P; p++) {
-    PhaseInfo &ph = pl->phases[p];
-    const tribs_step_t &sp = steps[ph.step];
-    ph.tag = ps->g + 1 + p;
+  std::vector<StepConst> step_const(n_steps);
+  for (int k = 0; k < n_steps; k++) {
+    const tribs_step_t &sp = steps[k];
     StepConst t;
     t.dt = sp.dt; t.dt_gw = sp.dt_gw; t.now = sp.current_time; t.elapsed = (double)sp.elapsed_steps;
     t.hourly_reset = sp.hourly_reset; t.psrf_last = 0.0; t.defer_esrf = 1;
     t.rain_mode = 0;
-    if (ph.kind == 0) {
-      if (sp.rain_mode == TRIBS_RAIN_UNIFORM) { t.rain_mode = 1; t.rain_uniform = sp.rain_uniform; }
-      else if (sp.rain_mode == TRIBS_RAIN_PER_CELL) {
-        if (!sp.rain) return fail("tribs_gpu_run: rain_mode PER_CELL without a rain array");
-        if (!ps->d_rain && dev_alloc(c, &ps->d_rain, (size_t)ps->max_steps * n_own)) return 1;
-        double *dst = ps->d_rain + (size_t)ph.step * n_own;
-        CK(cudaMemcpyAsync(c->d_stage, sp.rain, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, st));
-        scatter_rain_kernel<<<(c->n + 255) / 256, 256, 0, st>>>(c->d_stage, c->d_dev_of_sweep, dst, c->n, c->own_begin, c->own_end);
-        c->launches++;
-        t.rain_mode = 2; t.rain_cells = dst - c->own_begin;
-      } else if (sp.rain_mode == TRIBS_RAIN_GAUGES) {
-        if (!sp.rain || !c->d_gauge_of_cell) return fail("tribs_gpu_run: rain_mode GAUGES needs tribs_gpu_set_rain_gauges and the gauge values");
-        if (ps->gauge_cap < ps->max_steps * c->n_gauges) {
-          if (dev_alloc(c, &ps->d_gauge, (size_t)ps->max_steps * c->n_gauges)) return 1;
-          ps->gauge_cap = ps->max_steps * c->n_gauges;
-        }
-        double *dst = ps->d_gauge + (size_t)ph.step * c->n_gauges;
-        CK(cudaMemcpyAsync(dst, sp.rain, (size_t)c->n_gauges * sizeof(double), cudaMemcpyHostToDevice, st));
-        t.rain_mode = 3; t.rain_cells = dst; t.rain_gauge = c->d_gauge_of_cell;
+    if (sp.rain_mode == TRIBS_RAIN_UNIFORM) { t.rain_mode = 1; t.rain_uniform = sp.rain_uniform; }
+    else if (sp.rain_mode == TRIBS_RAIN_PER_CELL) {
+      if (!sp.rain) return fail("tribs_gpu_run: rain_mode PER_CELL without a rain array");
+      if (!ps->d_rain && dev_alloc(c, &ps->d_rain, (size_t)ps->max_steps * n_own)) return 1;
+      double *dst = ps->d_rain + (size_t)k * n_own;
+      CK(cudaMemcpyAsync(c->d_stage, sp.rain, (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, st));
+      scatter_rain_kernel<<<(c->n + 255) / 256, 256, 0, st>>>(c->d_stage, c->d_dev_of_sweep, dst, c->n, c->own_begin, c->own_end);
+      c->launches++;
+      t.rain_mode = 2; t.rain_cells = dst - c->own_begin;
+    } else if (sp.rain_mode == TRIBS_RAIN_GAUGES) {
+      if (!sp.rain || !c->d_gauge_of_cell) return fail("tribs_gpu_run: rain_mode GAUGES needs tribs_gpu_set_rain_gauges and the gauge values");
+      if (ps->gauge_cap < ps->max_steps * c->n_gauges) {
+        if (dev_alloc(c, &ps->d_gauge, (size_t)ps->max_steps * c->n_gauges)) return 1;
+        ps->gauge_cap = ps->max_steps * c->n_gauges;
       }
+      double *dst = ps->d_gauge + (size_t)k * c->n_gauges;
+      CK(cudaMemcpyAsync(dst, sp.rain, (size_t)c->n_gauges * sizeof(double), cudaMemcpyHostToDevice, st));
+      t.rain_mode = 3; t.rain_cells = dst; t.rain_gauge = c->d_gauge_of_cell;
     }
-    ph.t = t;
+    step_const[k] = t;
+  }
+  int n_state = 0, n_et = 0;
+  ps->h_et_steps.clear();
+  for (int p = 0; p < P; p++) {
+    PhaseInfo &ph = pl->phases[p];
+    const tribs_step_t &sp = steps[ph.step];
+    ph.tag = ps->g + 1 + n_state;      // an ET phase carries the tag of the sweep that follows it
+    if (ph.kind != 2) n_state++;
+    else {
+      EtStepDev d{};
+      if (stage_et_phase(c, ps, n_et, et_steps[ph.step], &d)) return 1;
+      ps->h_et_steps.push_back(d);
+      n_et++;
+    }
+    ph.t = step_const[ph.step];
     ph.rs = RouteStep{sp.current_time, sp.qstrm_outlet, hv0, (int32_t)(fmod(sp.current_time, c->gwstep_h) == 0.0),
-                      (int32_t)(pattern[ph.step] ? 0 : 1)};
+                      (int32_t)((pattern[ph.step] & 1) ? 0 : 1)};
     if (ph.last_of_step) {
       pl->bins[ph.step] = step_bins(c, sp.current_time);
       bin_lo = std::min(bin_lo, pl->bins[ph.step].bin_base);
       bin_hi = std::max(bin_hi, pl->bins[ph.step].bin_base + window);
     }
+  }
+  if (n_et > 0) {
+    ps->h_etpack.k = c->et->k; ps->h_etpack.st = c->et->st; ps->h_etpack.ev = c->et->ev;
+    CK(cudaMemcpyAsync(ps->d_etpack, &ps->h_etpack, sizeof(EtPack), cudaMemcpyHostToDevice, st));
+    CK(cudaMemcpyAsync(ps->d_et_steps, ps->h_et_steps.data(), (size_t)n_et * sizeof(EtStepDev), cudaMemcpyHostToDevice, st));
+    c->et->gen += n_et;
   }
   CK(cudaMemcpyAsync(ps->d_phases, pl->phases.data(), (size_t)P * sizeof(PhaseInfo), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ps->d_bins, pl->bins.data(), (size_t)n_steps * sizeof(StepBins), cudaMemcpyHostToDevice, st));
@@ -726,6 +849,7 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     a.K = c->tile_bins; a.rec_stride = c->rec_stride; a.last_sweep_dev = c->last_sweep_dev;
     a.n_hi_tasks = P * ps->my_hi_tiles; a.n_lo_tasks = P * (own_tiles - ps->my_hi_tiles); a.n_hi_warps = n_hi_warps;
     a.abort_flag = c->d_abort; a.flags = c->d_flags; a.pv = pv;
+    a.et = ps->d_etpack; a.et_steps = ps->d_et_steps;
     void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &c->rc, &a};
     const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
                      : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
@@ -761,11 +885,11 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
             c->rank, P, own_tiles, ps->my_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2], 100.0 * h[6] / std::max(1.0, (double)(h[0] + h[1])),
             100.0 * h[3] / std::max(1.0, (double)(h[3] + h[4])), h[4] / std::max(1.0, (double)h[5]) / 1.9e3, h[5]);
   }
-  ps->g += P;
+  ps->g += n_state;
   // the handle's views after the batch: New = what the last phase wrote
   c->dv = ((ps->g) & 1) ? d_odd : d_even;
   c->new_valid = true;
-  for (int k = 0; k < n_steps; k++) if (pattern[k]) c->gw_dirty = true;
+  for (int k = 0; k < n_steps; k++) if (pattern[k] & 1) c->gw_dirty = true;
   {
     PhaseTimer pt(c, 2);
     // hillslope routing of every step from its runoff snapshot, in step order
@@ -817,7 +941,7 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
     set_global_kernel<<<1, 1, 0, st>>>(c->d_globals, TRIBS_G_psrf_last, psrf_src);
     c->launches++;
     CK(cudaMemcpyAsync(c->d_globals + TRIBS_G_hillvel_last, &hv0, sizeof(double), cudaMemcpyHostToDevice, st));
-    if (pattern[n_steps - 1]) {
+    if (pattern[n_steps - 1] & 1) {
       esrf_fixup_kernel<<<(n_own + 255) / 256, 256, 0, st>>>(c->sv, c->dv, c->own_begin, c->own_end, steps[n_steps - 1].dt_gw,
                                                              c->d_globals + TRIBS_G_psrf_last);
       c->launches++;

@@ -136,7 +136,7 @@ class SnowParams(C.Structure):
                 ("reserved", C.c_int32), ("init", C.POINTER(PD))]
 
 
-EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
+EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_run_et", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
            "tribs_gpu_pending_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
@@ -169,6 +169,7 @@ def load():
     L.tribs_gpu_init.argtypes = [C.POINTER(Mesh), C.POINTER(Params), C.POINTER(StateT), C.POINTER(Part), C.POINTER(H)]
     L.tribs_gpu_step.argtypes = [H, C.c_uint32, C.POINTER(Step)]
     L.tribs_gpu_run.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32)]
+    L.tribs_gpu_run_et.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(EtStep))]
     L.tribs_gpu_retrieve_qeff_steps.argtypes = [H, C.c_int, PD]
     L.tribs_gpu_sync.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_push.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
@@ -358,7 +359,16 @@ class GpuBasin:
                 s.rain = _d(a)
             s.qstrm_outlet = sd.get("qstrm_outlet", 0.0)
             masks[q] = PHASE_UNSAT | PHASE_ROUTE | PHASE_RESET | (PHASE_SAT if sd.get("sat") else 0)
-        _chk(self.L.tribs_gpu_run(self.h, k, arr, masks))
+        if any(sd.get("et") is not None for sd in steps):
+            ets = (C.POINTER(EtStep) * k)()
+            for q, sd in enumerate(steps):
+                if sd.get("et") is not None:
+                    es = self._et_step_struct(*sd["et"], keep=keep)
+                    keep.append(es)
+                    ets[q] = C.pointer(es)
+            _chk(self.L.tribs_gpu_run_et(self.h, k, arr, masks, ets))
+        else:
+            _chk(self.L.tribs_gpu_run(self.h, k, arr, masks))
 
     # -- rain gauges and peer-memory partitions --------------------------------------------------
     def set_rain_gauges(self, cell_gauge, n_gauges: int | None = None):
@@ -481,6 +491,10 @@ class GpuBasin:
         if potential is None and components is None:
             return
         keep = []
+        s = self._et_step_struct(potential, components, cell_record, elev, keep)
+        _chk(self.L.tribs_gpu_et_step(self.h, C.byref(s)))
+
+    def _et_step_struct(self, potential, components, cell_record, elev, keep):
         base = (potential or components)[0]
         s = EtStep()
         for k in ("alphaD", "sinAlpha", "sunaz", "Io", "hour", "dew_hum_flag", "ts_option"):
@@ -492,14 +506,16 @@ class GpuBasin:
             s.do_potential = 1
             s.first_call, s.te_met, s.sky_flag_from = st["first_call"], st["te_met"], st["sky_flag_from"]
             mp = self._met(rec, cell_record, elev, keep)
+            keep.append(mp)
             s.met_potential = C.pointer(mp)
         if components is not None:
             st, rec = components
             s.do_components = 1
             s.te_eti = st["te_eti"]
             mc = self._met(rec, cell_record, elev, keep)
+            keep.append(mc)
             s.met_components = C.pointer(mc)
-        _chk(self.L.tribs_gpu_et_step(self.h, C.byref(s)))
+        return s
 
     def snow_init(self, basin: dict):
         b, keep = basin, []

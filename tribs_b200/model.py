@@ -215,6 +215,7 @@ class Simulator:
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
         self.step_no = 0
+        self.et_in_batch = True      # False: cut the batches at the ET sweeps and run kernel (1) between them
 
     def UpdatePrecipitationInput(self):
         if self.rain_schedule is None:
@@ -294,7 +295,16 @@ class Simulator:
             # steps in between or uploads made by other entry points (a static gauge map + K gauge values per
             # step is the cheap form of spatially varying rain, see tribs_gpu_set_rain_gauges)
             step_rain = rain
-            if et_on:
+            et_arg = None
+            if et_on and self.evapotrans.getSnowOpt() == 0 and self.et_in_batch:
+                # kernel (1) rides inside the batch as one more phase of every tile (tribs_gpu_run_et)
+                met_due, eti_due = self.met_clock.due(now)
+                if met_due or eti_due:
+                    host = self.evapotrans.host
+                    pot = host.potential_call(t.hour, now) if met_due else None
+                    comp = host.components_call(now) if eti_due else None
+                    et_arg = (pot, comp, host.cell_record, host.elev)
+            elif et_on:
                 met_due, eti_due = self.met_clock.due(now)
                 if met_due or eti_due:
                     flush()
@@ -313,7 +323,7 @@ class Simulator:
             steps.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
                               hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
                               sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())),
-                              rain=step_rain))
+                              rain=step_rain, et=et_arg))
         flush()
         self.batch_qeff = np.concatenate(qeff) if qeff else None
         return out
