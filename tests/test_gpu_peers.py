@@ -92,3 +92,90 @@ def test_peer_ranks_are_bitwise_equal_to_one_gpu(world, nx, ny, stream_every, bu
         assert np.array_equal(ref["q"], np.concatenate([qq[r] for qq in q])), r
     assert np.abs(ref["res"]["mhydro"]).max() > 0 and np.abs(ref["q"]).max() > 0
     lp.close()
+
+
+def _gauge_map(basin, k=3):
+    x, y = np.asarray(basin["x"]), np.asarray(basin["y"])
+    gx = np.minimum((k * (x - x.min()) / max(np.ptp(x), 1e-9)).astype(np.int32), k - 1)
+    gy = np.minimum((k * (y - y.min()) / max(np.ptp(y), 1e-9)).astype(np.int32), k - 1)
+    return (gy * k + gx).astype(np.int32)
+
+
+def _gauge_values(t, n=9):
+    base = 18.0 if 5.0 < t <= 8.0 else 0.0       # a morning storm: the canopy fills, then evaporates in daylight
+    return base * (0.5 + np.arange(n) / n)
+
+
+ET_CHECK = ["PotEvap", "ActEvap", "SurfTemp", "SoilTemp", "CanStorage", "CumIntercept", "EvapWetCanopy", "EvapoTrans",
+            "CumTotEvap", "CanopyStorVol", "NetRad", "LFlux"]
+
+
+def test_config3_forcing_on_peer_ranks_is_bitwise_equal_to_one_gpu(built):
+    """configs[2] in small: gauge rain (per-gauge values + the static Thiessen map on the device), a weather
+    station, Penman-Monteith + Rutter interception as phases of the batch (tribs_gpu_run_et), three ranks."""
+    from tribs_b200 import gpu
+    from tribs_b200.model import Simulator
+    from tribs_b200.partition import cell_owner
+    from tribs_b200.peers import LocalPeers
+    from tribs_b200.synthbasin import add_met_forcing
+    basin = add_met_forcing(_basin(36, 108), hours=48)
+    owner = cell_owner(basin, 3)
+    cg = _gauge_map(basin)
+    rain = lambda t: gpu.GaugeRain(_gauge_values(t))
+    n_steps, batch = 192, 48     # midnight to noon; hourly ET: three ET phases inside every batch
+    ref = Simulator(basin, part=dict(rank=0, nranks=1, cell_owner=owner))
+    ref.dev.set_rain_gauges(cg)
+    for _ in range(n_steps // batch):
+        ref.run_batch(batch, rain_of_time=rain)
+    lp = LocalPeers(basin, 3, owner=owner, max_batch_steps=batch, cell_gauge=cg)
+    for _ in range(n_steps // batch):
+        lp.run_batch(batch, rain_of_time=rain)
+    want = ref.dev.sync(STATE + ["Rain", "NetPrecipitation", "EvapSoil"])
+    want.update(ref.dev.et_sync(ET_CHECK))
+    got = lp.gather(STATE + ["Rain", "NetPrecipitation", "EvapSoil"] + ET_CHECK)
+    for f in want:
+        assert np.array_equal(want[f], got[f]), f
+    assert np.abs(want["PotEvap"]).max() > 0 and np.abs(want["CumTotEvap"]).max() > 0 and np.abs(want["cumsrf"]).max() >= 0
+    lim = int(basin["res_limit"][0])
+    for nm in RESULTS:
+        assert np.array_equal(ref.dev.results(nm, lim), lp.devs[1].results(nm, lim)), nm
+    # and the per-gauge forcing equals the same rain handed over cell by cell
+    pc = Simulator(basin, part=dict(rank=0, nranks=1, cell_owner=owner))
+    for _ in range(n_steps // batch):
+        pc.run_batch(batch, rain_of_time=lambda t: _gauge_values(t)[cg])
+    other = pc.dev.sync(STATE)
+    for f in STATE:
+        assert np.array_equal(want[f], other[f]), f
+    lp.close(); ref.dev.close(); pc.dev.close()
+
+
+def test_snapshot_rollback_and_checkpoint_file(built, tmp_path):
+    """tribs_gpu_snapshot / rollback, and the binary checkpoint loaded into a handle with ANOTHER partition layout
+    (per-cell arrays travel in sweep order): the continued runs agree bit for bit on every cell value."""
+    from tribs_b200.model import Simulator
+    from tribs_b200.partition import cell_owner
+    basin = _basin(30, 60)
+    a = Simulator(basin)
+    a.run_batch(40, rain_of_time=_rain)
+    a.dev.snapshot()
+    t40 = a.timer.currentTime
+    a.dev.save_state(str(tmp_path / "ck.bin"))
+    a.run_batch(56, rain_of_time=_rain)
+    first = a.dev.sync(STATE)
+    res_first = a.dev.results("mhydro", int(basin["res_limit"][0]))
+    a.dev.rollback()
+    a.timer.currentTime = t40
+    a.run_batch(56, rain_of_time=_rain)
+    again = a.dev.sync(STATE)
+    for f in STATE:
+        assert np.array_equal(first[f], again[f]), f
+    assert np.array_equal(res_first, a.dev.results("mhydro", int(basin["res_limit"][0])))
+    b = Simulator(basin, part=dict(rank=0, nranks=1, cell_owner=cell_owner(basin, 2)))
+    b.dev.load_state(str(tmp_path / "ck.bin"))
+    b.timer.currentTime = t40
+    b.run_batch(56, rain_of_time=_rain)
+    other = b.dev.sync(STATE)
+    for f in STATE:
+        assert np.array_equal(first[f], other[f]), f
+    assert np.allclose(res_first, b.dev.results("mhydro", int(basin["res_limit"][0])), rtol=1e-12, atol=1e-300)
+    a.dev.close(); b.dev.close()

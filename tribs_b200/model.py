@@ -215,6 +215,7 @@ class Simulator:
         self.rain_schedule = rain_schedule
         self.gw_on = bool(int(b["GW_model_label"][0])) if gw_on is None else gw_on
         self.step_no = 0
+        self._record_sent = [False, False]
         self.et_in_batch = True      # False: cut the batches at the ET sweeps and run kernel (1) between them
 
     def UpdatePrecipitationInput(self):
@@ -303,7 +304,11 @@ class Simulator:
                     host = self.evapotrans.host
                     pot = host.potential_call(t.hour, now) if met_due else None
                     comp = host.components_call(now) if eti_due else None
-                    et_arg = (pot, comp, host.cell_record, host.elev)
+                    # the cell -> station map is static: it travels once per sweep kind (the library keeps it)
+                    need = (pot is not None and not self._record_sent[0]) or (comp is not None and not self._record_sent[1])
+                    et_arg = (pot, comp, host.cell_record if need else None, host.elev)
+                    if need:
+                        self._record_sent = [self._record_sent[0] or pot is not None, self._record_sent[1] or comp is not None]
             elif et_on:
                 met_due, eti_due = self.met_clock.due(now)
                 if met_due or eti_due:
