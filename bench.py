@@ -161,25 +161,29 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    side = args.side
+    cfg = args.config
+    side = args.side if args.side > 0 else (3163 if cfg == 3 else 1000)
     B = max(1, min(args.batch, args.steps))
     runtime_h = 24.0 + (args.warmup + 2 * args.steps + 64) * 0.0625
     check = None
     partitioned = world > 1 and args.mgpu == "partition"
+    strong = cfg == 3       # configs[2]: ONE 10M-cell basin on 1/2/4/8 GPUs; configs[1] grows with the GPUs
+    if partitioned and not args.no_self_check:
+        check = self_check(rank, world)
+    ny = side if (strong or not partitioned) else side * world
+    # configs[1] on N GPUs: a valley N times as long (side x side*N cells, side^2 per GPU). Either way the basin is
+    # cut into reach partitions along the river and boundary values travel through peer memory inside the batch kernel.
+    basin = build_basin(side, ny, seed=1 if partitioned else 1 + rank, runtime_h=runtime_h, stream_every=args.stream_every)
+    if cfg == 3:
+        from tribs_b200.synthbasin import add_met_forcing
+        add_met_forcing(basin, hours=int(runtime_h) + 24)     # weather station, land class, Penman-Monteith + Rutter
     if partitioned:
-        # ONE basin over all GPUs: a valley `world` times as long (side x side*world cells, side^2 per GPU), cut
-        # into reach partitions along the river; boundary values travel through peer memory inside the batch kernel
         from tribs_b200.partition import cell_owner
         from tribs_b200.peers import PeerSimulator
-        if not args.no_self_check:
-            check = self_check(rank, world)
-        basin = build_basin(side, side * world, seed=1, runtime_h=runtime_h, stream_every=args.stream_every)
         owner = cell_owner(basin, world)
         sim = PeerSimulator(basin, rank, world, owner=owner, max_batch_steps=B)
         n = int((owner == rank).sum())
-        sim.advance = lambda: sim.timer.Advance(sim.timer.getTimeStep())
     else:
-        basin = build_basin(side, side, seed=1 + rank, runtime_h=runtime_h, stream_every=args.stream_every)
         n = int(basin["n_active"][0])
         sim = Simulator(basin, rain_schedule=None)
     dev = sim.dev
@@ -203,30 +207,27 @@ def run_gpu(args):
     gy = np.minimum((4 * (by - by.min()) / max(np.ptp(by), 1e-9)).astype(np.int32), 3)
     dev.set_rain_gauges((gy * 4 + gx).astype(np.int32), n_gauges)
     pinned_rows = torch.empty((B, n_gauges), dtype=torch.float64).pin_memory()
+    gauge_shape = 0.5 + np.arange(n_gauges) / n_gauges if cfg == 3 else np.ones(n_gauges)     # spatially varying (cfg 3)
+    row_of = {"k": 0}
 
-    def host_steps(k, rows=None):
-        t = sim.timer
-        out = []
-        for q in range(k):
-            sim.advance()
-            now = t.getCurrentTime()
-            r = storm_rain(now)
-            if rows is not None:
-                rows[q].fill_(r)
-                r = gpu.GaugeRain(rows[q].numpy())
-            out.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
-                            hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
-                            sat=bool(sim.gw_on and not math.fmod(now, t.getGWTimeStep())), rain=r))
-        return out
+    def rain_resident(now):
+        r = storm_rain(now)
+        return gpu.GaugeRain(r * gauge_shape) if cfg == 3 else r          # cfg 2: tRainfall::NewRain(double)
+
+    def rain_pinned(now):
+        row = pinned_rows[row_of["k"] % B]
+        row_of["k"] += 1
+        row.copy_(torch.from_numpy(storm_rain(now) * gauge_shape))
+        return gpu.GaugeRain(row.numpy())
 
     def resident_batch(k):
-        dev.run(host_steps(k))
+        sim.run_batch(k, rain_of_time=rain_resident)      # with ET on, kernel (1) rides inside the batch (tribs_gpu_run_et)
 
     def e2e_batch(k):
-        dev.run(host_steps(k, pinned_rows))      # H2D: k x n_gauges rain values
-        q = dev.retrieve_qeff_steps(k)           # D2H: per-step lateral inflow for the channel router
-        g = dev.globals()                         # D2H: basin accumulators
-        return q, g
+        row_of["k"] = 0
+        sim.run_batch(k, rain_of_time=rain_pinned, collect_qeff=True)   # H2D: k x n_gauges rain values (+ station records)
+        g = dev.globals()                                               # D2H: per-step lateral inflows, basin accumulators
+        return sim.batch_qeff, g
 
     def loop(fn_batch, k):
         done = 0
@@ -257,7 +258,7 @@ def run_gpu(args):
     loop(resident_batch, args.warmup)
     dev.wait()
     dev.snapshot()
-    t_mark = sim.timer.currentTime
+    sim.host_snapshot()
     dev.set_timing(True)
     dev.phase_ms(reset=True)
     sampler = ClockSampler(local)
@@ -273,11 +274,11 @@ def run_gpu(args):
     n_launch = math.ceil(args.steps / B)
     unsat_ms = phases["unsat"] / max(n_launch, 1)
     steps_per_launch = args.steps / n_launch
-    bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every
+    bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every + (ET_BYTES_PER_CELL / 16.0 if cfg == 3 else 0.0)
     bytes_per_launch = n * steps_per_launch * bytes_per_cell_step
 
     dev.rollback()
-    sim.timer.currentTime = t_mark
+    sim.host_restore()
     ems, ewall = timed(lambda k: loop(e2e_batch, k), args.steps)
     v0 = args.warmup + 1
     windows = {"value": [v0, v0 + args.steps - 1], "e2e": [v0, v0 + args.steps - 1], "storm_ends_at_step": 96}
@@ -306,15 +307,15 @@ def run_gpu(args):
         pass
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong" if strong else "weak", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD[2],
+        "config": {"workload": WORKLOAD[cfg], "baseline_config": f"configs[{cfg - 1}]",
                    "cells_per_gpu": n, "total_cells": total_cells, "stream_cells": n_stream, "sweep_levels": dev.levels(),
                    "l2": "state arrays (54 x 8 B x cells) exceed the 126 MB L2; no explicit flush",
                    "batch_steps": B, "timed_steps": windows,
                    "parallelism": "1 GPU" if world == 1 else (
                        f"one basin of {total_cells} cells, {world} reach partitions along the river (one per GPU, "
-                       f"{n} cells each), pipelined batches of {B} steps; river inflow, water-table and downslope-state "
+                       f"{n} cells on rank 0), pipelined batches of {B} steps; river inflow, water-table and downslope-state "
                        "halos stored into peer memory by the batch kernel, dependent work released with system-scope "
                        "atomics over NVLink (no host exchange, no NCCL on the data path)" if partitioned
                        else f"{world} independent basin replicas, no exchange")},
@@ -333,10 +334,10 @@ def run_gpu(args):
     }
     if check is not None:
         line["self_check"] = check
-    if world == 1 and not args.no_et_kernel:
+    if world == 1 and not args.no_et_kernel and cfg == 2:
         line["kernels"] = {"et_cells_kernel": time_et_kernel(dev, basin, n, stream, peak)}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline_sample(side)
+        line["cpu_baseline"] = cpu_baseline_sample(min(side, 1000), cfg)
     if rank == 0:
         print(json.dumps(line))
     dev.close()
@@ -434,7 +435,7 @@ def _run_reference_sample(n_side: int, hours: float, procs: int = 1):
     return rate, cells, steps, wall
 
 
-def _reference_on_bench_basin(side: int, steps: int):
+def _reference_on_bench_basin(side: int, steps: int, cfg: int = 2):
     """The unmodified serial reference on the GPU arm's own basin: build_basin(side, side, seed=1) is
     written as OPTMESHINPUT 9 files (tribs_b200/meshb.py), which the reference reads without its
     super-linear mesh / flow-network set-up, and runs the first `steps` steps of the storm."""
@@ -444,7 +445,7 @@ def _reference_on_bench_basin(side: int, steps: int):
     d = tempfile.mkdtemp(prefix="tribsbench_")
     t0 = time.perf_counter()
     try:
-        write_meshb_deck(side, d, seed=1, runtime_h=24.0)
+        write_meshb_deck(side, d, seed=1, runtime_h=24.0, scenario="met" if cfg == 3 else "deep")
         r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", "--max-steps", str(steps)], cwd=d,
                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
         for ln in r.stdout.splitlines():
@@ -458,14 +459,15 @@ def _reference_on_bench_basin(side: int, steps: int):
     return None
 
 
-def cpu_baseline_sample(side: int = 1000):
+def cpu_baseline_sample(side: int = 1000, cfg: int = 2):
     if _harness():
-        got = _reference_on_bench_basin(side, 8)
+        got = _reference_on_bench_basin(side, 20 if cfg == 3 else 8, cfg)
         if got:
             rate, cells, steps, setup_s, wall = got
             return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
-                    "sample": f"unmodified serial reference (g++ -O2) on the GPU arm's own basin ({cells} cells, read as "
-                              f"OPTMESHINPUT 9 files), the first {steps} steps of the storm, simulation_loop only; "
+                    "sample": f"unmodified serial reference (g++ -O2) on a basin of the GPU arm's generator ({cells} cells, read as "
+                              f"OPTMESHINPUT 9 files" + (", rain gauges + weather station + ET + Rutter" if cfg == 3 else "") +
+                              f"), the first {steps} steps, simulation_loop only; "
                               f"{wall:.0f} s wall incl. writing the deck and {setup_s:.0f} s of reference set-up"}
         rate, cells, steps, wall = _run_reference_sample(120, 12.0, 1)
         return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
@@ -503,12 +505,13 @@ def run_reference_arm(args):
             avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
         except (ValueError, OSError):
             avail_gb = 64.0
-        side = int(min(args.side, math.sqrt(150.0 * 0.3e6 / total), math.sqrt(0.5 * avail_gb / procs / 6e-6)))
+        want = args.side if args.side > 0 else (3163 if args.config == 3 else 1000)
+        side = int(min(want, math.sqrt(150.0 * 0.3e6 / total), math.sqrt(0.5 * avail_gb / procs / 6e-6)))
         side = max(side, 64)
         base = tempfile.mkdtemp(prefix="tribsbench_ref_")
         src = os.path.join(base, "deck")
         os.makedirs(src)
-        write_meshb_deck(side, src, seed=1, runtime_h=24.0)
+        write_meshb_deck(side, src, seed=1, runtime_h=24.0, scenario="met" if args.config == 3 else "deep")
         dirs = []
         for k in range(procs):
             d = os.path.join(base, f"p{k}")
@@ -552,8 +555,9 @@ def run_reference_arm(args):
         sample = "C oracle port, 9.2k-cell synthetic V-valley, 32 steps per sample"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD[2], "sample": "bounded CPU sample of the GPU arm's workload, see cpu_baseline"},
+            "scaling": "strong" if args.config == 3 else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD[args.config], "baseline_config": f"configs[{args.config - 1}]",
+                       "sample": "bounded CPU sample of the GPU arm's workload, see cpu_baseline"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": procs, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
@@ -565,7 +569,10 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="tribs_b200", choices=["tribs_b200", "reference"])
-    ap.add_argument("--side", type=int, default=1000, help="cells per side of the synthetic basin (per GPU)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3],
+                    help="BASELINE.json configs[1] (1M-cell valley per GPU, uniform storm, ET off; grows with the GPUs) or "
+                         "configs[2] (one 10M-cell valley on all GPUs, gauge rain + weather station + ET + Rutter)")
+    ap.add_argument("--side", type=int, default=0, help="cells per side of the synthetic basin (default: 1000 / 3163)")
     ap.add_argument("--batch", type=int, default=256, help="steps per pipelined launch (tribs_gpu_run), at most --steps")
     ap.add_argument("--mgpu", default="partition", choices=["partition", "replicas"],
                     help="N>1: one reach-partitioned basin with halo exchange (default) or independent replicas")

@@ -77,9 +77,11 @@ __device__ __forceinline__ void export_f64(const PeerView &pv, int i, double *mi
   for (int k = pv.xp_rp[i]; k < pv.xp_rp[i + 1]; k++) st_relaxed_f64(peer_ptr(pv, pv.xp_rank[k], mine), v);
 }
 
-// two ready queues: "hi" for the tiles on the critical cycle of the batch (river cells and the
-// cells next to the river, whose chain through all phases bounds the run time), "lo" for the bulk.
-// ctl = {head_hi, tail_hi, head_lo, tail_lo}; queue_lo starts at queue + n_tasks.
+// Ready queues. Class 0 "hi": the tiles on the critical cycle of the batch (river cells and the cells next to the
+// river, whose chain through all phases bounds the run time); classes 1-3 "lo": the bulk, one queue per kind of
+// phase (sweep, saturated zone, ET) so that the warps of a block can start 16 tasks of the SAME kind together.
+// ctl[2q] = head (consumer cursor), ctl[2q+1] = tail (producer cursor) of class q; class q's slots start at
+// queue + q * n_tasks. Statistics live behind them (ctl + 16).
 struct ReadyQueues { int32_t *ctl; int32_t *queue; const int32_t *tile_hi; int n_tasks; unsigned long long *trace; unsigned cap_hi_ns, cap_lo_ns; };
 
 struct PipeArgs {
@@ -97,7 +99,7 @@ struct PipeArgs {
   const double *evapotrans;
   double gwstep_h;
   int32_t n_pad, n_tiles, tile0, n_own_tiles, own_begin, n_own, K, rec_stride, last_sweep_dev;
-  int32_t n_hi_tasks, n_lo_tasks, n_hi_warps;
+  int32_t n_hi_tasks, n_lo_kind[3], n_hi_warps;
   int32_t *abort_flag, *flags;
   const struct EtPack *et;         // kernel (1)'s constants, static arrays and fields (batches with ET phases)
   const EtStepDev *et_steps;       // one per ET phase of the batch
@@ -115,19 +117,19 @@ __device__ __forceinline__ void fence_tasks(bool sys) {
 }
 __device__ __forceinline__ void release_task(const PipeArgs &a, int p, int tile) {
   const int task = p * a.n_tiles + tile;
-  const int hi = a.rq.tile_hi[tile];
+  const int q = a.rq.tile_hi[tile] ? 0 : 1 + a.phases[p].kind;
   const int r = a.pv.n_ranks > 1 ? a.pv.tile_owner[tile] : a.pv.me;
   if (r == a.pv.me) {
     if (atomicSub(a.cnt + task, 1) == 1) {
       fence_tasks(a.pv.n_ranks > 1);   // acquire the other producers' data before handing the task on
-      const int slot = atomicAdd(a.rq.ctl + (hi ? 1 : 3), 1);
-      st_relaxed_i32(a.rq.queue + (hi ? 0 : a.rq.n_tasks) + slot, task);
+      const int slot = atomicAdd(a.rq.ctl + 2 * q + 1, 1);
+      st_relaxed_i32(a.rq.queue + (size_t)q * a.rq.n_tasks + slot, task);
     }
   } else {   // the dependent lives on another rank: its counter and its ready queue, over NVLink
     if (atomicSub_system(peer_ptr(a.pv, r, a.cnt) + task, 1) == 1) {
       __threadfence_system();
-      const int slot = atomicAdd_system(peer_ptr(a.pv, r, a.rq.ctl) + (hi ? 1 : 3), 1);
-      st_relaxed_i32(peer_ptr(a.pv, r, a.rq.queue) + (hi ? 0 : a.rq.n_tasks) + slot, task);
+      const int slot = atomicAdd_system(peer_ptr(a.pv, r, a.rq.ctl) + 2 * q + 1, 1);
+      st_relaxed_i32(peer_ptr(a.pv, r, a.rq.queue) + (size_t)q * a.rq.n_tasks + slot, task);
     }
   }
 }
@@ -149,8 +151,8 @@ pipeline_init_kernel(TileGraph g, const PhaseInfo *__restrict__ phases, int n_ph
   const int task = p * n_tiles + t;
   cnt[task] = c;
   if (c == 0) {
-    const int hi = rq.tile_hi[t];
-    rq.queue[(hi ? 0 : rq.n_tasks) + atomicAdd(rq.ctl + (hi ? 1 : 3), 1)] = task;
+    const int q = rq.tile_hi[t] ? 0 : 1 + ph.kind;
+    rq.queue[(size_t)q * rq.n_tasks + atomicAdd(rq.ctl + 2 * q + 1, 1)] = task;
   }
 }
 
@@ -188,72 +190,93 @@ constexpr int kPipeThreads = TRIBS_PIPE_THREADS, kPipeWarps = kPipeThreads / 32;
 template <int MAXC>
 __global__ void __launch_bounds__(kPipeThreads, TRIBS_PIPE_MIN_BLOCKS)
 pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, RouteConst rc, PipeArgs a) {
-  const int lane = threadIdx.x & 31;
-  // Two ticket queues. `n_hi_warps` warps, spread over the SMs (warp 0 of every block first), serve the "hi" queue
-  // (river cells and the cells next to the river: their chain through all phases is the critical
-  // path and must never sit behind a backlog of bulk work); every other warp serves "lo". A warp
-  // takes a ticket (atomicAdd on the head) and waits for exactly that slot to be filled, so a
-  // newly released task is picked up at once by the warp that holds its ticket.
-#ifdef TRIBS_BLOCK_TICKETS
-  // The four warps of a "lo" block take four consecutive tickets together. Tiles of one bucket and phase are
-  // released together and sit next to each other in the queue, so the warps of a block run the same part of
-  // the (large, branchy) column code at about the same time and share its lines in the SM's instruction
-  // cache (32 KB against ~80 KB of hot code) instead of 24 warps streaming 24 different parts of it.
-  const bool hi_warp = (int)blockIdx.x * kPipeWarps < a.n_hi_warps;     // whole blocks serve the "hi" queue
-  __shared__ int sh_ticket;
-#else
-  const bool hi_warp = (int)((threadIdx.x >> 5) * gridDim.x + blockIdx.x) < a.n_hi_warps;
-#endif
-  const int my_total = hi_warp ? a.n_hi_tasks : a.n_lo_tasks;
-  int32_t *my_head = a.rq.ctl + (hi_warp ? 0 : 2);
-  const int32_t *my_queue = a.rq.queue + (hi_warp ? 0 : a.rq.n_tasks);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  // Whole blocks serve either the "hi" queue or the three "lo" queues.
+  //  hi: every warp on its own takes a ticket (atomicAdd on the head) and waits for exactly that slot to be
+  //      filled, so a newly released river task is picked up at once by the warp that holds its ticket; the
+  //      chain along the river through all phases is the critical path and never sits behind bulk work.
+  //  lo: the 16 warps of a block start their tasks TOGETHER, and all of one kind of phase: thread 0 claims up to
+  //      16 READY tasks of one class (compare-and-swap on the head, never past the tail, so a block never commits
+  //      to work that does not exist yet), preferring a class that has 16 and the class of its last round. Tasks of
+  //      one bucket and phase are released together and are neighbours in their queue, so the warps walk the same
+  //      part of the (large, branchy) column code at about the same time and share its lines in the SM's 32 KB
+  //      instruction cache, instead of each streaming its own part of ~80 KB of hot code (profiles/r02_block_tickets.md).
+  const bool hi_warp = (int)blockIdx.x * kPipeWarps < a.n_hi_warps;
+  __shared__ int sh_q, sh_base, sh_cnt;
+  int last_q = 1;
   const unsigned ns_cap = hi_warp ? a.rq.cap_hi_ns : a.rq.cap_lo_ns;   // back-off ceiling of the queue poll
   const bool multi = a.pv.n_ranks > 1;
   long long t_wait = 0, t_busy = 0, n_done = 0, t_bar = 0;
+  long long t_kind[3] = {0, 0, 0}, n_kind[3] = {0, 0, 0};
   long long t_mark = clock64();
   for (;;) {
     int task = -1;
-#ifdef TRIBS_BLOCK_TICKETS
-    int blk_idx = 0;
-    if (!hi_warp) {
+    const int32_t *slot = nullptr;
+    if (hi_warp) {
+      if (lane == 0) {
+        const int idx = atomicAdd(a.rq.ctl + 0, 1);
+        if (idx < a.n_hi_tasks) slot = a.rq.queue + idx; else task = -2;
+      }
+    } else {
       const long long tb0 = clock64();
-      __syncthreads();
-      if (threadIdx.x == 0) sh_ticket = *(volatile int32_t *)a.abort_flag ? 0x7fffffff : atomicAdd(my_head, kPipeWarps);
-      __syncthreads();
-      t_bar += clock64() - tb0;
-      blk_idx = sh_ticket;
-      if (blk_idx >= my_total) break;      // uniform over the block
-    }
-#endif
-    if (lane == 0) {
-#ifdef TRIBS_BLOCK_TICKETS
-      const int idx = hi_warp ? atomicAdd(my_head, 1) : blk_idx + (int)(threadIdx.x >> 5);
-#else
-      const int idx = atomicAdd(my_head, 1);
-#endif
-      if (idx < my_total) {
-        unsigned spins = 0, ns = 32;
+      __syncthreads();     // everybody is done with the previous round (and with sh_*)
+      if (threadIdx.x == 0) {
+        unsigned spins = 0, ns = 64;
         unsigned long long t_first = 0;
-        while ((task = ld_relaxed_i32(my_queue + idx)) < 0) {   // nothing of my class is ready yet
+        int cnt = -1;
+        for (;;) {
+          bool all_done = true;
+          int best = -1, best_n = 0;
+          for (int k = 0; k < 3; k++) {
+            const int q = 1 + ((last_q - 1 + k) % 3);      // the class of the last round first
+            const int h = ld_relaxed_i32(a.rq.ctl + 2 * q), t = ld_relaxed_i32(a.rq.ctl + 2 * q + 1);
+            if (h < a.n_lo_kind[q - 1]) all_done = false;
+            const int n = min(t - h, kPipeWarps);
+            if (n > best_n) { best = q; best_n = n; }      // strict: ties go to the class tried first
+          }
+          if (best >= 0) {
+            const int h = ld_relaxed_i32(a.rq.ctl + 2 * best);
+            const int n = min(ld_relaxed_i32(a.rq.ctl + 2 * best + 1) - h, kPipeWarps);
+            if (n > 0 && atomicCAS(a.rq.ctl + 2 * best, h, h + n) == h) { sh_q = best; sh_base = h; cnt = n; break; }
+            continue;                                       // another block was faster: look again
+          }
+          if (all_done) break;
           __nanosleep(ns);
           if (ns < ns_cap) ns += ns;
-          if (((++spins) & 255u) == 0u) {
-            if (*(volatile int32_t *)a.abort_flag) { task = -2; break; }
+          if (((++spins) & 63u) == 0u) {
+            if (*(volatile int32_t *)a.abort_flag) break;
             const unsigned long long t_now = global_ns();
             if (!t_first) t_first = t_now;
-            else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(a.abort_flag, 1); task = -2; break; }
+            else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(a.abort_flag, 1); break; }
           }
         }
-      } else
-        task = -2;
+        sh_cnt = cnt;
+      }
+      __syncthreads();
+      t_bar += clock64() - tb0;
+      const int cnt = sh_cnt;
+      if (cnt < 0) break;                                   // uniform over the block: nothing is left (or abort)
+      last_q = sh_q;
+      if (warp < cnt) { if (lane == 0) slot = a.rq.queue + (size_t)sh_q * a.rq.n_tasks + sh_base + warp; }
+      else task = -3;                                       // fewer ready tasks than warps: this warp sits the round out
+    }
+    if (lane == 0 && slot) {
+      unsigned spins = 0, ns = 32;
+      unsigned long long t_first = 0;
+      while ((task = ld_relaxed_i32(slot)) < 0) {   // hi: not released yet; lo: the tail is ahead of the slot's store by a moment
+        __nanosleep(ns);
+        if (ns < ns_cap) ns += ns;
+        if (((++spins) & 255u) == 0u) {
+          if (*(volatile int32_t *)a.abort_flag) { task = -2; break; }
+          const unsigned long long t_now = global_ns();
+          if (!t_first) t_first = t_now;
+          else if (t_now - t_first > kSpinTimeoutNs) { atomicExch(a.abort_flag, 1); task = -2; break; }
+        }
+      }
     }
     task = __shfl_sync(0xffffffffu, task, 0);
     { const long long now_c = clock64(); t_wait += now_c - t_mark; t_mark = now_c; }
-#ifdef TRIBS_BLOCK_TICKETS
-    if (task < 0) { if (hi_warp) break; else continue; }   // a lo warp past the end leaves with its block
-#else
-    if (task < 0) break;
-#endif
+    if (task < 0) { if (hi_warp) break; else continue; }   // a lo warp without a task goes to the block's next round
     const int p = task / a.n_tiles, tile = task - p * a.n_tiles;
     if (a.rq.trace && lane == 0) a.rq.trace[2 * (size_t)task] = global_ns();   // TRIBS_TRACE: task timeline
     fence_tasks(multi);   // acquire side of the producers' fence -> counter -> queue hand-off
@@ -349,14 +372,18 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
       if (lane == 0) release_task(a, p + 1, tile);
     }
     if (a.rq.trace && lane == 0) a.rq.trace[2 * (size_t)task + 1] = global_ns();
-    { const long long now_c = clock64(); t_busy += now_c - t_mark; t_mark = now_c; n_done++; }
+    { const long long now_c = clock64(); t_busy += now_c - t_mark; t_kind[kind] += now_c - t_mark; n_kind[kind]++; t_mark = now_c; n_done++; }
   }
   if (lane == 0) {   // scheduler statistics: [0..2] lo warps, [3..5] hi warps
-    unsigned long long *st = (unsigned long long *)(a.rq.ctl + 8) + (hi_warp ? 3 : 0);
+    unsigned long long *st = (unsigned long long *)(a.rq.ctl + 16) + (hi_warp ? 3 : 0);
     atomicAdd(st + 0, (unsigned long long)t_wait);
     atomicAdd(st + 1, (unsigned long long)t_busy);
     atomicAdd(st + 2, (unsigned long long)n_done);
-    if (!hi_warp) atomicAdd((unsigned long long *)(a.rq.ctl + 8) + 6, (unsigned long long)t_bar);
+    if (!hi_warp) {
+      unsigned long long *sk = (unsigned long long *)(a.rq.ctl + 16) + 6;
+      atomicAdd(sk, (unsigned long long)t_bar);
+      for (int q = 0; q < 3; q++) { atomicAdd(sk + 1 + 2 * q, (unsigned long long)t_kind[q]); atomicAdd(sk + 2 + 2 * q, (unsigned long long)n_kind[q]); }
+    }
   }
 }
 
@@ -598,7 +625,7 @@ static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
     ps->d_met_batch = nullptr; ps->met_batch_cap = 0;
     if (!c->slab.base) { drop(ps->d_qeff_steps); drop(ps->d_part_vec); drop(ps->d_sums_part); drop(ps->d_cnt); drop(ps->d_queue); }
     const size_t S = (size_t)n_steps, slots = (size_t)c->n_stream + 1;
-    if (shared_alloc(c, &ps->d_cnt, 3 * S * c->n_tiles) || shared_alloc(c, &ps->d_queue, 6 * S * c->n_tiles) ||
+    if (shared_alloc(c, &ps->d_cnt, 3 * S * c->n_tiles) || shared_alloc(c, &ps->d_queue, (size_t)kQueueClasses * 3 * S * c->n_tiles) ||
         shared_alloc(c, &ps->d_part_vec, (size_t)c->n_parts * S * stride) || shared_alloc(c, &ps->d_sums_part, (size_t)c->n_parts * 3 * S * 4) ||
         shared_alloc(c, &ps->d_qeff_steps, S * slots))
       return 1;
@@ -698,6 +725,12 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
                      const tribs_et_step_t *const *et_steps) {
   if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
   CK(cudaSetDevice(c->device));
+  const bool dbg_t = getenv("TRIBS_DEBUG") != nullptr;
+  const auto t_run0 = std::chrono::steady_clock::now();
+  auto lap = [&](const char *what) {
+    if (dbg_t) fprintf(stderr, "[tribs] run host %-22s %8.3f ms\n", what,
+                       1e3 * std::chrono::duration<double>(std::chrono::steady_clock::now() - t_run0).count());
+  };
   if (c->partitioned) return fail("tribs_gpu_run: this handle was partitioned with tribs_gpu_set_partition (host-exchanged single steps); "
                                   "pipelined batches over partitions need tribs_part_t at tribs_gpu_init");
   if (c->n_late > 0) return fail("tribs_gpu_run: the sweep order is not topological (late contributors); use tribs_gpu_step");
@@ -790,20 +823,20 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     CK(cudaMemcpyAsync(ps->d_et_steps, ps->h_et_steps.data(), (size_t)n_et * sizeof(EtStepDev), cudaMemcpyHostToDevice, st));
     c->et->gen += n_et;
   }
+  lap("forcing staged");
   CK(cudaMemcpyAsync(ps->d_phases, pl->phases.data(), (size_t)P * sizeof(PhaseInfo), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ps->d_bins, pl->bins.data(), (size_t)n_steps * sizeof(StepBins), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(ps->d_is_sat, pl->is_sat.data(), (size_t)P * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   const int n_tasks = P * c->n_tiles;
   CK(cudaMemsetAsync(ps->d_headtail, 0, 64 * sizeof(int32_t), st));
-  CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)2 * n_tasks * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)kQueueClasses * n_tasks * sizeof(int32_t), st));
   PeerView pv{};
   pv.me = c->rank; pv.n_ranks = c->n_ranks;
   for (int r = 0; r < c->n_ranks; r++) pv.base[r] = ps->peer_base[r];
   pv.tile_owner = ps->d_tile_owner; pv.xp_rp = ps->d_xp_rp; pv.xp_rank = ps->d_xp_rank; pv.tile_xp = ps->d_tile_xp;
   {
     PhaseTimer pt(c, 0);
-    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr, 128u, 16384u};   // lo ceiling: idle pollers cost the working warps instruction-fetch
-    // bandwidth; measured on the 1M-cell batch 2 us: 373, 16 us: 423, 32 us: 426, 64 us: 397, 128 us: 351 M cell-timesteps/s
+    ReadyQueues rq{ps->d_headtail, ps->d_queue, c->d_tile_hi, n_tasks, nullptr, 128u, 2048u};   // poll ceilings: a hi warp on its slot, thread 0 of an idle lo block
     if (const char *e = getenv("TRIBS_POLL_CAP_NS")) rq.cap_lo_ns = (unsigned)std::max(32, atoi(e));
     if (const char *e = getenv("TRIBS_POLL_CAP_HI_NS")) rq.cap_hi_ns = (unsigned)std::max(32, atoi(e));
     const char *trace_path = c->n_ranks == 1 ? getenv("TRIBS_TRACE") : nullptr;   // debugging aid: start/end time of every task of this launch
@@ -815,22 +848,16 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     }
     // blocks of the persistent grid: all an SM holds, or this handle's share of them when several handles
     // of one process run on the same device (tribs_gpu_attach_local)
-    const int blocks = std::max(1, ps->blocks / std::max(1, ps->share));
+    const int blocks = std::max(2, ps->blocks / std::max(1, ps->share));    // at least one hi and one lo block
     // warps serving the "hi" queue: one per SM for a single river; on a dendritic network the stream
     // tiles are a sizeable share of all tasks and get that share of the warps
     const int total_warps = blocks * kPipeWarps;
-#ifdef TRIBS_BLOCK_TICKETS
     // whole blocks: the hi tasks are about as long as the others but lie on the chain every hillslope waits for;
     // measured on the 1M-cell valley (5 % hi tiles, 2368 warps): 160 warps 697 M, 256: 768 M, 400: 747 M, 600: 692 M
     int n_hi_warps = std::max(std::min(total_warps / 2, ps->n_sms),
                               (int)std::lround(2.2 * total_warps * (double)ps->my_hi_tiles / std::max(1, own_tiles)));
     n_hi_warps = ((n_hi_warps + kPipeWarps - 1) / kPipeWarps) * kPipeWarps;
     n_hi_warps = std::max(kPipeWarps, std::min(n_hi_warps, total_warps - kPipeWarps));
-#else
-    int n_hi_warps = std::max(std::min(blocks, ps->n_sms),
-                              (int)std::lround(1.25 * total_warps * (double)ps->my_hi_tiles / std::max(1, own_tiles)));
-    n_hi_warps = std::min(n_hi_warps, total_warps - std::min(blocks, ps->n_sms));
-#endif
     if (const char *e = getenv("TRIBS_HI_WARPS")) n_hi_warps = std::max(1, std::min(total_warps - 1, atoi(e)));
     const long long n_init = (long long)P * own_tiles;
     pipeline_init_kernel<<<(unsigned)((n_init + 255) / 256), 256, 0, st>>>(ps->graph, ps->d_phases, P, c->n_tiles, tile0, own_tiles,
@@ -847,7 +874,13 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     a.gwstep_h = c->gwstep_h;
     a.n_pad = n_pad; a.n_tiles = c->n_tiles; a.tile0 = tile0; a.n_own_tiles = own_tiles; a.own_begin = c->own_begin; a.n_own = n_own;
     a.K = c->tile_bins; a.rec_stride = c->rec_stride; a.last_sweep_dev = c->last_sweep_dev;
-    a.n_hi_tasks = P * ps->my_hi_tiles; a.n_lo_tasks = P * (own_tiles - ps->my_hi_tiles); a.n_hi_warps = n_hi_warps;
+    {
+      int n_kind[3] = {0, 0, 0};
+      for (int q = 0; q < P; q++) n_kind[pl->phases[q].kind]++;
+      a.n_hi_tasks = P * ps->my_hi_tiles;
+      for (int q = 0; q < 3; q++) a.n_lo_kind[q] = n_kind[q] * (own_tiles - ps->my_hi_tiles);
+      a.n_hi_warps = n_hi_warps;
+    }
     a.abort_flag = c->d_abort; a.flags = c->d_flags; a.pv = pv;
     a.et = ps->d_etpack; a.et_steps = ps->d_et_steps;
     void *args[] = {&c->sv, &d_even, &d_odd, &c->mc, &c->rc, &a};
@@ -855,6 +888,7 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
                      : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
     CK(cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(kPipeThreads), args, 0, st));
     c->launches++;
+    lap("batch kernel launched");
     if (d_trace) {   // file: int32 n_phases, n_tiles; per tile int32 hi flag, int32 first cell (sweep index); 2 x u64 per task
       std::vector<unsigned long long> h((size_t)2 * n_tasks);
       CK(cudaMemcpyAsync(h.data(), d_trace, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st));
@@ -878,12 +912,15 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     if (reduce_sums_local(c, ps->d_tile_sums, (size_t)own_tiles * 4, tile0, P, ps->d_sums_part) ) return 1;
   }
   if (getenv("TRIBS_DEBUG") && c->n_ranks == 1) {
-    unsigned long long h[7];
-    CK(cudaMemcpyAsync(h, ps->d_headtail + 8, sizeof(h), cudaMemcpyDeviceToHost, st));
+    unsigned long long h[13];
+    CK(cudaMemcpyAsync(h, ps->d_headtail + 16, sizeof(h), cudaMemcpyDeviceToHost, st));
     CK(cudaStreamSynchronize(st));
     fprintf(stderr, "[tribs] rank %d batch: phases=%d tiles=%d hi_tiles=%d | lo warps: wait %.1f%% busy/task %.1f us tasks %llu (block barrier %.1f%%) | hi warps: wait %.1f%% busy/task %.1f us tasks %llu\n",
             c->rank, P, own_tiles, ps->my_hi_tiles, 100.0 * h[0] / std::max(1.0, (double)(h[0] + h[1])), h[1] / std::max(1.0, (double)h[2]) / 1.9e3, h[2], 100.0 * h[6] / std::max(1.0, (double)(h[0] + h[1])),
             100.0 * h[3] / std::max(1.0, (double)(h[3] + h[4])), h[4] / std::max(1.0, (double)h[5]) / 1.9e3, h[5]);
+    fprintf(stderr, "[tribs]   lo tasks by kind: sweep %.1f us x %llu | saturated zone %.1f us x %llu | ET %.1f us x %llu\n",
+            h[7] / std::max(1.0, (double)h[8]) / 1.9e3, h[8], h[9] / std::max(1.0, (double)h[10]) / 1.9e3, h[10],
+            h[11] / std::max(1.0, (double)h[12]) / 1.9e3, h[12]);
   }
   ps->g += n_state;
   // the handle's views after the batch: New = what the last phase wrote
@@ -962,6 +999,7 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     c->at_boundary = true;
   }
   CK(cudaGetLastError());
+  lap("all launched");
   return 0;
 }
 

@@ -67,6 +67,7 @@ struct RouteConst {
 };
 
 constexpr int kMaxParts = 16;
+constexpr int kQueueClasses = 4;   // ready queues of a batch: hi, and lo by kind of phase (pipeline.cuh)
 // Memory other ranks map (cudaIpc) or address directly (several handles in one process): one allocation per
 // handle, carved by a bump allocator in the same order on every rank, so an address on a peer is
 // peer_base + (my_address - my_base).
@@ -1258,10 +1259,12 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
 
   // ---- memory the peers address (nranks > 1): one allocation, carved identically on every rank
   if (c->n_ranks > 1) {
-    const size_t S = (size_t)part->max_batch_steps, P2 = 2 * S, nt = (size_t)c->n_tiles;
+    // (sizes as in ensure_pipe: up to 3 phases per step - ET, sweep, saturated zone)
+    const size_t S = (size_t)part->max_batch_steps, P3 = 3 * S, nt = (size_t)c->n_tiles;
     const size_t stride = 5 * (size_t)c->route_window + kMeans;
     size_t bytes = ((size_t)TRIBS_N_FIELDS + 4) * ((size_t)n_pad * 8 + 256)      // fields, qpub x2, wt_elev, transm
-                   + 3 * P2 * nt * 4 + (size_t)c->n_parts * (S * stride + P2 * 4) * 8 + S * (size_t)(c->n_stream + 1) * 8 + (1u << 20);
+                   + (1 + kQueueClasses) * P3 * nt * 4 + 1024                      // task counters + the ready queues
+                   + (size_t)c->n_parts * (S * stride + P3 * 4) * 8 + S * (size_t)(c->n_stream + 1) * 8 + (4u << 20);
     void *q = nullptr;
     CK(cudaMalloc(&q, bytes));
     CK(cudaMemset(q, 0, bytes));

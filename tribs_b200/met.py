@@ -182,9 +182,14 @@ class EvapoTransHost:
         if self.skycover_flag:
             sky_from = 0
         else:
-            bad = np.abs(rec["skyCover"][self.cell_record] - NODATA) < 1.0e-3
-            sky_from = int(np.argmax(bad)) if bad.any() else self.n
-            if bad.any():
+            # per station, not per cell: the first cell (sweep order) of every station is known once and for all
+            if not hasattr(self, "_first_cell_of_record"):
+                first_cell = np.full(len(self.elev), self.n, np.int64)
+                np.minimum.at(first_cell, self.cell_record, np.arange(self.n))
+                self._first_cell_of_record = first_cell
+            bad = np.abs(rec["skyCover"] - NODATA) < 1.0e-3
+            sky_from = int(self._first_cell_of_record[bad].min()) if bad.any() else self.n
+            if sky_from < self.n:
                 self.skycover_flag = 1
         step = dict(alphaD=self.sun[0], sinAlpha=self.sun[1], sunaz=self.sun[2], Io=self.sun[3], hour=self.hour,
                     first_call=int(first), dew_hum_flag=self.dewHumFlag, ts_option=self.ts_option,

@@ -218,6 +218,19 @@ class Simulator:
         self._record_sent = [False, False]
         self.et_in_batch = True      # False: cut the batches at the ET sweeps and run kernel (1) between them
 
+    def host_snapshot(self):
+        """Host-side counterpart of GpuBasin.snapshot(): the timer, the met clock and tEvapoTrans' per-call members."""
+        import copy
+        self._host_snap = copy.deepcopy((self.timer.currentTime, self.timer.calendar, self.met_clock,
+                                         getattr(self.evapotrans.host, "__dict__", None), self.step_no, list(self._record_sent)))
+
+    def host_restore(self):
+        import copy
+        now, cal, clock, host, step_no, sent = copy.deepcopy(self._host_snap)
+        self.timer.currentTime, self.timer.calendar, self.met_clock, self.step_no, self._record_sent = now, cal, clock, step_no, sent
+        if host is not None:
+            self.evapotrans.host.__dict__.update(host)
+
     def UpdatePrecipitationInput(self):
         if self.rain_schedule is None:
             return
