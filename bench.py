@@ -161,6 +161,12 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
+    t_start = time.perf_counter()
+
+    def say(what):
+        if os.environ.get("TRIBS_BENCH_VERBOSE"):
+            print(f"bench.py[rank {rank}] {time.perf_counter() - t_start:7.1f} s  {what}", file=sys.stderr, flush=True)
+
     cfg = args.config
     side = args.side if args.side > 0 else (3163 if cfg == 3 else 1000)
     B = max(1, min(args.batch, args.steps))
@@ -187,6 +193,7 @@ def run_gpu(args):
         n = int(basin["n_active"][0])
         sim = Simulator(basin, rain_schedule=None)
     dev = sim.dev
+    say(f"basin of {int(basin['n_active'][0])} cells on the device")
     gw_every = int(round(dev.gwstep / dev.tstep))
     stream = torch.cuda.ExternalStream(dev.stream_handle())
     n_stream = dev.n_stream
@@ -257,6 +264,7 @@ def run_gpu(args):
     # arm times too): the state after the warm-up is kept on the device and restored between the two legs
     loop(resident_batch, args.warmup)
     dev.wait()
+    say("warm-up done")
     dev.snapshot()
     sim.host_snapshot()
     dev.set_timing(True)
@@ -277,6 +285,7 @@ def run_gpu(args):
     bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every + (ET_BYTES_PER_CELL / 16.0 if cfg == 3 else 0.0)
     bytes_per_launch = n * steps_per_launch * bytes_per_cell_step
 
+    say("resident leg timed")
     dev.rollback()
     sim.host_restore()
     ems, ewall = timed(lambda k: loop(e2e_batch, k), args.steps)
@@ -332,6 +341,7 @@ def run_gpu(args):
                              "see DESIGN.md 4.2"},
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
+    say("end-to-end leg timed")
     if check is not None:
         line["self_check"] = check
     if world == 1 and not args.no_et_kernel and cfg == 2:

@@ -1,0 +1,62 @@
+"""Full-size parity for BASELINE.json configs[2]: the 10M-cell basin under rain gauges + a weather station with
+Penman-Monteith ET and Rutter interception, the configuration bench.py times by default.
+
+tests/golden/fullsize_met_10m.npz holds what the UNMODIFIED REFERENCE leaves after 16 and 32 steps (two ET sweeps,
+four groundwater steps; tests/golden/make_fullsize_met.py; the C oracle reproduced the reference's full arrays bit for
+bit before the fixture was written). The device runs the same 32 steps the way bench.py does: pipelined batches with
+kernel (1) as a phase of the batch, the rain as per-gauge values + the static Thiessen map on the device.
+
+Bar (north_star): per-cell Nwt, Nf, Mu ... and the hydrograph within 1e-6 relative."""
+import os
+
+import numpy as np
+import pytest
+
+from refrun import ROOT
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6
+FIXTURE = os.path.join(ROOT, "tests", "golden", "fullsize_met_10m.npz")
+
+
+@pytest.mark.skipif(not os.path.exists(FIXTURE), reason="tests/golden/fullsize_met_10m.npz not generated")
+def test_gpu_config3_full_size_matches_reference_fixture(built):
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    from make_fullsize_met import BLOCK, RESULTS, RUNTIME_H, STATE, apply_patches, block_sums
+    from tribs_b200 import gpu, met
+    from tribs_b200.model import Simulator
+    from tribs_b200.synthbasin import build_basin
+    z = np.load(FIXTURE)
+    side, seed = int(z["side"][0]), int(z["seed"][0])
+    basin = apply_patches(build_basin(side, side, seed=seed, runtime_h=RUNTIME_H), z)
+    for k in z.files:
+        if k.startswith("extra/"):
+            basin[k[6:]] = np.array(z[k])
+    assert int(basin["n_active"][0]) == int(z["n_active"][0]) and int(z["oracle_bitexact"][0]) == 1
+    idx = z["cells"]
+    rain = met.GaugeRain(basin)
+    sim = Simulator(basin)
+    sim.dev.set_rain_gauges(rain.cell_gauge.astype(np.int32), len(rain.elev))
+    done, worst = 0, {}
+    for st in [int(s) for s in z["snap_steps"]]:
+        sim.run_batch(st - done, rain_of_time=lambda t: gpu.GaugeRain(rain.gauge_values(t).copy()))
+        done = st
+        got = sim.dev.sync(list(STATE))
+        for f in STATE:
+            ref = z[f"s{st}/{f}"]
+            err = np.abs(ref - got[f][idx]) / np.maximum(np.abs(ref), 1e-6)
+            worst[(st, f)] = float(err.max())
+            ref_b, got_b = z[f"s{st}/blk/{f}"], block_sums(got[f])
+            scale = np.maximum(np.abs(ref_b), 1e-6 * BLOCK)
+            worst[(st, "blk", f)] = float((np.abs(ref_b - got_b) / scale).max())
+        for r in RESULTS:
+            ref = z[f"s{st}/res/{r}"]
+            dev = np.asarray(sim.dev.results(r, ref.size))[: ref.size]
+            worst[(st, "res", r)] = float(np.abs(ref - dev).max() / max(np.abs(ref).max(), 1e-6))
+    rows = sorted(worst.items(), key=lambda kv: -kv[1])
+    print("\n[config 3, full size] worst relative differences:\n" + "\n".join(f"  {k}: {v:.3e}" for k, v in rows[:10]))
+    assert rows[0][1] <= REL_TOL, rows[:10]
+    # the sample must have seen the physics: rain through the canopy, wetting fronts, lateral outflow
+    assert np.abs(z["s32/NetPrecipitation"]).max() > 0 and np.abs(z["s32/Qpout"]).max() > 0 and np.abs(z["s32/NfOld"]).max() > 0

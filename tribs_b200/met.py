@@ -240,11 +240,25 @@ class GaugeRain:
         self.z = g("z").astype(np.float64)
         self.hourlyTimeStep = 0
         self.current = np.zeros(self.n)
+        self.current_gauges = np.zeros(ng)
 
     def is_gauge_time(self, current_time):
         """tRunTimer::isGaugeTime (tRunTimer.cpp:270-276)."""
         q = (current_time - self.tstep) / self.dt
         return q == math.floor(q)
+
+    def gauge_values(self, current_time):
+        """The same forcing per GAUGE (for tribs_gpu_set_rain_gauges(self.cell_gauge) + rain_mode GAUGES): what the
+        cells of each gauge's Thiessen polygon receive. Only without a precipitation lapse rate, which makes the
+        value depend on the cell's elevation."""
+        if self.lapse != 0.0:
+            raise ValueError("PRECLAPSE != 0: rain differs from cell to cell inside a Thiessen polygon; use the per-cell form")
+        if self.is_gauge_time(current_time):
+            t = min(self.hourlyTimeStep, self.nt - 1)
+            r = self.series[:, t]
+            self.current_gauges = np.where(r >= 1e-5, r, 0.0)
+            self.hourlyTimeStep += 1
+        return self.current_gauges
 
     def __call__(self, current_time):
         """Per-cell rain (mm/h) valid at *current_time*."""
