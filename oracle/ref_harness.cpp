@@ -50,6 +50,7 @@
 #include "src/Headers/TemplDefinitions.h"
 #include "src/tHydro/tSnowPack.h"
 #include "src/tFlowNet/tFlowResults.h"
+#include "src/tGraph/tGraph.h"
 // the reference-side binding of the C ABI (what INTEGRATION.md tells a maintainer to add);
 // inside tHydroModel it would have member access, here it gets it through the macro above
 #include "tribs_ref_binding.h"
@@ -90,6 +91,7 @@ struct TrbWriter {
 
 // ---------------------------------------------------------------------------------
 struct Harness {
+    SimulationControl *graph_sim = nullptr;   // set: dump tGraph's reach partitions with the basin
     tMesh<tCNode> *mesh;
     tKinemat *flow;
     tHydroModel *hydro;
@@ -263,6 +265,25 @@ struct Harness {
             w.i32("reach_head", heads);
             w.i32("reach_outlet", outs);
             w.i32("reach_nnodes", nn);
+        }
+        // the reference's own reach partition for 2..8 partitions: tGraph::connectivity (tGraph.cpp:297-343) counts
+        // the reaches of tKinemat's lists, tGraph::createDefaultPartition (588-608) assigns them; every cell then
+        // belongs to reach2partition[tCNode::getReach()]. Pins tribs_b200/partition.py (tests/test_partition.py).
+        if (graph_sim) {
+            tGraph::sim = graph_sim; tGraph::mesh = mesh; tGraph::flow = flow;
+            tGraph::connectivity();
+            const int nr = tGraph::numGlobalReach;
+            w.i32s("graph_n_reach", nr);
+            for (int np = 2; np <= 8; np++) {
+                if (nr < np) break;
+                tGraph::reach2partition.assign(nr, 0);
+                tGraph::createDefaultPartition(np);
+                vector<int32_t> r2p(tGraph::reach2partition.begin(), tGraph::reach2partition.end());
+                w.i32("graph_r2p_np" + std::to_string(np), r2p);
+            }
+            tGraph::conn.clear(); tGraph::reach2partition.clear(); tGraph::pointsPerReach.clear();
+            delete[] tGraph::hid; delete[] tGraph::oid; tGraph::hid = tGraph::oid = nullptr;
+            tGraph::numGlobalReach = 0;
         }
         // hydro model scalars / options
         w.f64s("BasArea", hydro->BasArea);
@@ -793,6 +814,7 @@ int main(int argc, char **argv) {
     H.mesh = &BasinMesh; H.flow = &Flow; H.hydro = &Moisture; H.timer = &Timer;
     H.et = &EvapoTrans; H.icp = &Intercept; H.rainfall = &Rainfall; H.snow = &SnowPack;
     H.index();
+    H.graph_sim = &SimCtrl;
     if (do_basin) H.dump_basin(outdir + "/basin.trb", InputFile);
     if (do_kat) H.dump_kat(outdir + "/kat.trb");
 

@@ -127,3 +127,25 @@ def test_single_river_basin_is_cut_into_reaches():
     b, _, _ = load_golden("deep")
     r = cell_reaches(b, 2)
     assert np.unique(r).size >= 2
+
+
+def test_partition_equals_the_references_tgraph_on_a_multi_reach_basin():
+    """CSR / partition indices bit-exact (north_star): the reference itself (tGraph::connectivity +
+    tGraph::createDefaultPartition, src/tGraph/tGraph.cpp:297-343, 588-608, called by the harness on its own
+    tKinemat reach lists) partitions a basin with 13 reaches into 2..8 parts; partition.py must give the same
+    reach -> partition table and, through tCNode::getReach(), the same owner for every cell."""
+    from refrun import have_harness, run_reference, spec_for
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    spec = spec_for("deep", 40, runtime_h=1.0, seed=3, tributary_every=8)
+    basin, _, _, _ = run_reference(spec, snap_from=1, snap_to=0)
+    n_reach = int(basin["graph_n_reach"][0])
+    assert n_reach == len(basin["reach_head"]) == np.unique(basin["reach"]).size >= 8
+    for world in range(2, 9):
+        ref_r2p = np.asarray(basin[f"graph_r2p_np{world}"])
+        assert np.array_equal(default_partition(n_reach, world), ref_r2p), world
+        assert np.array_equal(cell_owner(basin, world), ref_r2p[np.asarray(basin["reach"])]), world
+    # and a partition never separates a hillslope cell from its stream node
+    own = cell_owner(basin, 4)
+    hill = np.flatnonzero((basin["boundary"] == 0) & (basin["stream_node"] >= 0))
+    assert np.array_equal(own[hill], own[basin["stream_node"][hill]])

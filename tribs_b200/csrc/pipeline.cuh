@@ -100,6 +100,8 @@ struct PipeArgs {
   double gwstep_h;
   int32_t n_pad, n_tiles, tile0, n_own_tiles, own_begin, n_own, K, rec_stride, last_sweep_dev;
   int32_t n_hi_tasks, n_lo_kind[3], n_hi_warps;
+  int32_t mid_barrier;
+  int32_t waves;         // a lo block claims up to 16 * waves ready tasks per round (the later waves start without a barrier)
   int32_t *abort_flag, *flags;
   const struct EtPack *et;         // kernel (1)'s constants, static arrays and fields (batches with ET phases)
   const EtStepDev *et_steps;       // one per ET phase of the batch
@@ -204,6 +206,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
   const bool hi_warp = (int)blockIdx.x * kPipeWarps < a.n_hi_warps;
   __shared__ int sh_q, sh_base, sh_cnt;
   int last_q = 1;
+  int my_q = 1, my_base = 0, my_next = 0, my_end = 0;      // this warp's remaining slots of the block's current round
   const unsigned ns_cap = hi_warp ? a.rq.cap_hi_ns : a.rq.cap_lo_ns;   // back-off ceiling of the queue poll
   const bool multi = a.pv.n_ranks > 1;
   long long t_wait = 0, t_busy = 0, n_done = 0, t_bar = 0;
@@ -217,6 +220,9 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
         const int idx = atomicAdd(a.rq.ctl + 0, 1);
         if (idx < a.n_hi_tasks) slot = a.rq.queue + idx; else task = -2;
       }
+    } else if (my_next < my_end) {   // a later wave of this block's round: no barrier, straight to the next slot
+      if (lane == 0) slot = a.rq.queue + (size_t)my_q * a.rq.n_tasks + my_base + my_next;
+      my_next += kPipeWarps;
     } else {
       const long long tb0 = clock64();
       __syncthreads();     // everybody is done with the previous round (and with sh_*)
@@ -231,12 +237,12 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
             const int q = 1 + ((last_q - 1 + k) % 3);      // the class of the last round first
             const int h = ld_relaxed_i32(a.rq.ctl + 2 * q), t = ld_relaxed_i32(a.rq.ctl + 2 * q + 1);
             if (h < a.n_lo_kind[q - 1]) all_done = false;
-            const int n = min(t - h, kPipeWarps);
+            const int n = min(t - h, kPipeWarps * a.waves);
             if (n > best_n) { best = q; best_n = n; }      // strict: ties go to the class tried first
           }
           if (best >= 0) {
             const int h = ld_relaxed_i32(a.rq.ctl + 2 * best);
-            const int n = min(ld_relaxed_i32(a.rq.ctl + 2 * best + 1) - h, kPipeWarps);
+            const int n = min(ld_relaxed_i32(a.rq.ctl + 2 * best + 1) - h, kPipeWarps * a.waves);
             if (n > 0 && atomicCAS(a.rq.ctl + 2 * best, h, h + n) == h) { sh_q = best; sh_base = h; cnt = n; break; }
             continue;                                       // another block was faster: look again
           }
@@ -257,7 +263,8 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
       const int cnt = sh_cnt;
       if (cnt < 0) break;                                   // uniform over the block: nothing is left (or abort)
       last_q = sh_q;
-      if (warp < cnt) { if (lane == 0) slot = a.rq.queue + (size_t)sh_q * a.rq.n_tasks + sh_base + warp; }
+      my_q = sh_q; my_base = sh_base; my_end = cnt; my_next = warp + kPipeWarps;
+      if (warp < cnt) { if (lane == 0) slot = a.rq.queue + (size_t)my_q * a.rq.n_tasks + my_base + warp; }
       else task = -3;                                       // fewer ready tasks than warps: this warp sits the round out
     }
     if (lane == 0 && slot) {
@@ -308,6 +315,9 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
       __syncwarp();
       const int r0 = a.g.down_rp[tile], r1 = a.g.down_rp[tile + 1];
       for (int k = r0 + lane; k < r1; k += 32) release_task(a, p, a.g.down[k]);
+      // experiment (TRIBS_MID_BARRIER): re-align the round's warps before the write-back / diagnostics half
+      if (a.mid_barrier && !hi_warp && my_end > 1 && my_end <= kPipeWarps)
+        asm volatile("bar.sync 1, %0;" ::"r"(my_end * 32) : "memory");
     }
     if (kind == 2) {
       if (act) {
@@ -880,6 +890,9 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
       a.n_hi_tasks = P * ps->my_hi_tiles;
       for (int q = 0; q < 3; q++) a.n_lo_kind[q] = n_kind[q] * (own_tiles - ps->my_hi_tiles);
       a.n_hi_warps = n_hi_warps;
+      a.waves = 1;
+      a.mid_barrier = getenv("TRIBS_MID_BARRIER") != nullptr;
+      if (const char *e = getenv("TRIBS_ROUND_WAVES")) a.waves = std::max(1, std::min(8, atoi(e)));
     }
     a.abort_flag = c->d_abort; a.flags = c->d_flags; a.pv = pv;
     a.et = ps->d_etpack; a.et_steps = ps->d_et_steps;
