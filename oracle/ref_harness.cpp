@@ -760,6 +760,7 @@ int main(int argc, char **argv) {
     int time_from = 0;   // --time-from W: the first W steps are warm-up, left out of the timing line
     string meshb_dir; // --dump-meshb <dir>: write the OPTMESHINPUT 9 files of the mesh / flow network just built
     string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
+    int gpu_ranks = 1, gpu_batch = 16;
     double inject_evap = 0.0;   // --inject-evap R: soil evaporation R mm/h on dry steps (see below)
     vector<char*> rargs;
     for (int i = 0; i < argc; i++) {
@@ -771,6 +772,8 @@ int main(int argc, char **argv) {
         else if (a == "--phases" && i + 1 < argc) phases = argv[++i];
         else if (a == "--kat") do_kat = true;
         else if (a == "--gpu" && i + 1 < argc) gpu_lib = argv[++i];
+        else if (a == "--gpu-ranks" && i + 1 < argc) gpu_ranks = atoi(argv[++i]);     // reach partitions, one handle each
+        else if (a == "--gpu-batch" && i + 1 < argc) gpu_batch = atoi(argv[++i]);     // steps per tribs_gpu_run
         else if (a == "--inject-evap" && i + 1 < argc) inject_evap = atof(argv[++i]);
         else if (a == "--no-basin") do_basin = false;
         else if (a == "--dump-meshb" && i + 1 < argc) meshb_dir = argv[++i];
@@ -820,7 +823,19 @@ int main(int argc, char **argv) {
 
     TribsGpuBinding gpu;
     const bool use_gpu = !gpu_lib.empty();
-    if (use_gpu) gpu.attach(&BasinMesh, &Flow, &Moisture, &Timer, gpu_lib.c_str());
+    vector<int32_t> gpu_owner;
+    if (use_gpu && gpu_ranks > 1) {
+        // the reference's own partition: tGraph::connectivity + createDefaultPartition on tKinemat's reach lists,
+        // every cell with reach2partition[tCNode::getReach()] (what tGraph::update / inLocalPartition use)
+        tGraph::sim = &SimCtrl; tGraph::mesh = &BasinMesh; tGraph::flow = &Flow;
+        tGraph::connectivity();
+        const int nr = tGraph::numGlobalReach;
+        if (nr < gpu_ranks) { cout << "\nError: " << nr << " reaches cannot be split over " << gpu_ranks << " partitions" << endl; exit(2); }
+        tGraph::reach2partition.assign(nr, 0);
+        tGraph::createDefaultPartition(gpu_ranks);
+        for (tCNode *cn : H.cells) gpu_owner.push_back(tGraph::reach2partition[cn->getReach()]);
+    }
+    if (use_gpu) gpu.attach(&BasinMesh, &Flow, &Moisture, &Timer, gpu_lib.c_str(), gpu_ranks, &gpu_owner, gpu_batch);
     const bool gpu_et = use_gpu && EvapoTrans.getEToption() != 0 && SnowPack.getSnowOpt() == 0;
     if (gpu_et) gpu.attachET(&EvapoTrans, &Intercept, &Moisture);
     const bool gpu_snow = use_gpu && EvapoTrans.getEToption() != 0 && SnowPack.getSnowOpt() != 0;
@@ -829,6 +844,44 @@ int main(int argc, char **argv) {
 
     std::unique_ptr<TrbWriter> sw;
     if (snap_to >= snap_from) sw.reset(new TrbWriter(outdir + "/steps.trb"));
+
+    // Partitioned hybrid run: the reference's timer and rainfall objects advance k steps ahead, the device runs them as
+    // ONE pipelined batch on every rank (tribs_gpu_run, peer-memory halos), the owned cells of every rank go back to
+    // the tCNodes. Channel routing on the host is not part of this mode (snapshots are taken after Reset()).
+    if (use_gpu && gpu_ranks > 1) {
+        int step = 0;
+        vector<int32_t> snap_steps;
+        while (!Timer.IsFinished() && !(max_steps > 0 && step >= max_steps)) {
+            const int k_max = max_steps > 0 ? std::min(gpu_batch, max_steps - step) : gpu_batch;
+            vector<tribs_step_t> st;
+            vector<uint32_t> masks;
+            vector<vector<double>> rains;
+            for (int k = 0; k < k_max && !Timer.IsFinished(); k++) {
+                Timer.Advance(Timer.getTimeStep());
+                Sim.UpdatePrecipitationInput(Rainfall.getoptStorm());
+                tribs_step_t s = gpu.flags();
+                rains.emplace_back(H.cells.size());
+                for (size_t i = 0; i < H.cells.size(); i++) rains.back()[i] = H.cells[i]->getRain();
+                s.rain_mode = TRIBS_RAIN_PER_CELL;
+                st.push_back(s);
+                const bool gw = SimCtrl.GW_model_label && !fmod(Timer.getCurrentTime(), Timer.getGWTimeStep());
+                masks.push_back(TRIBS_PHASE_UNSAT | TRIBS_PHASE_ROUTE | TRIBS_PHASE_RESET | (gw ? TRIBS_PHASE_SAT : 0));
+            }
+            for (size_t k = 0; k < st.size(); k++) st[k].rain = rains[k].data();
+            gpu.runBatch(st, masks);
+            step += (int)st.size();
+            if (sw && step >= snap_from && step <= snap_to) {
+                gpu.syncToNodes();
+                char pre[64];
+                snprintf(pre, sizeof pre, "s%d_e_", step);
+                H.dump_state(*sw, pre, true);
+                snap_steps.push_back(step);
+            }
+        }
+        if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
+        printf("\nref_timing {\"cells\": %ld, \"steps\": %d, \"ranks\": %d}\n", (long)H.cells.size(), step, gpu_ranks);
+        return 0;
+    }
 
     // The reference's simulation_loop body (tSimul.cpp:248-293), one call at a time.
     int step = 0;

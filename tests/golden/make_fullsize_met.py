@@ -5,12 +5,13 @@ interception (scenario "met" of tests/refrun.py: the reference's own .sdf/.mdf f
 Like make_fullsize.py: the basin travels to the reference as OPTMESHINPUT 9 files, the unmodified reference
 (oracle/_ref/tribs_ref_harness) runs it (32 GB, ~4 min set-up, ~20 s per step on one core), and the C oracle
 (unsaturated / saturated zone, routing, ET + interception) has to reproduce the reference's FULL arrays bit for
-bit at both snapshots before the fixture is written. The fixture keeps, per snapshot (steps 16 and 32: two ET
-sweeps, four groundwater steps inside): a sample of cells, 1000-cell block sums of every field, the hydrograph
+bit at both snapshots before the fixture is written. The fixture keeps, per snapshot (steps 64 and 96: the gauges' storm
+begins at hour 3 = step 48, so the window has dry ET, the canopy filling under rain, wetting fronts; six ET sweeps, twelve
+groundwater steps): a sample of cells, 1000-cell block sums of every field, the hydrograph
 arrays; plus what turns build_basin()'s dict into the reference's exact inputs (sparse patches, and the
 forcing / land / ET keys whole: they are tiny or compress to nothing).
 
-    python tests/golden/make_fullsize_met.py [side]     # side 3163: ~45 min, 40 GB; writes tests/golden/fullsize_met_10m.npz"""
+    python tests/golden/make_fullsize_met.py [side]     # side 3163: ~75 min, 40 GB; writes tests/golden/fullsize_met_10m.npz"""
 import os
 import sys
 import tempfile
@@ -26,7 +27,7 @@ for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
 
 from make_fullsize import BLOCK, apply_patches, block_sums, make_patches  # noqa: E402,F401
 
-SIDE, SEED, SNAP_STEPS, RUNTIME_H = 3163, 1, (16, 32), 24.0
+SIDE, SEED, SNAP_STEPS, RUNTIME_H = 3163, 1, (64, 96), 24.0
 STATE = {"NwtOld": "NwtNew", "MuOld": "MuNew", "MiOld": "MiNew", "NtOld": "NtNew", "NfOld": "NfNew", "RuOld": "RuNew",
          "RiOld": "RiNew", "Qpout": "Qpout", "cumsrf": "cumsrf", "intstorm": "intstorm", "NetPrecipitation": "NetPrecipitation",
          "EvapSoil": "EvapSoil", "EvapDryCanopy": "EvapDryCanopy", "Rain": "Rain"}
@@ -67,12 +68,19 @@ def main(side=SIDE, out=None):
     work = tempfile.mkdtemp(prefix="tribs_fullsize_met_")
     basin, ref_basin, snaps, timing = reference_run(side, work, SNAP_STEPS)
     print(f"reference run: {time.time() - t0:.0f} s  {timing}", flush=True)
+    from refrun import SCENARIOS
     z = {"side": np.array([side]), "seed": np.array([SEED]), "snap_steps": np.array(SNAP_STEPS),
+         "gw_depth_mm": np.array([float(SCENARIOS["met"]["gw_depth_mm"])]),       # build_basin argument of the deck
          "n_active": np.array([int(basin["n_active"][0])]), "ref_cell_steps_per_s": np.array([timing.get("cell_steps_per_s", 0.0)]),
          "ref_setup_s": np.array([timing.get("setup_s", 0.0)]), "ref_loop_s": np.array([timing.get("loop_s", 0.0)])}
     z.update(make_patches(basin, ref_basin))
-    for k, a in ref_basin.items():          # forcing, land and ET keys build_basin does not make
-        if k not in basin:
+    # forcing, land and ET keys build_basin does not make; mesh bookkeeping the device path never reads (edge ids,
+    # complementary-edge ids ...) and the initial storages of tWaterBalance (not compared here) stay out: they are the
+    # only large ones
+    skip = {"spoke_compl_id", "spoke_edge_id", "edge_id", "edge_dest", "edge_org", "flow_edge_id", "init_TTime",
+            "init_UnSaturatedStorage", "init_SaturatedStorage"}
+    for k, a in ref_basin.items():
+        if k not in basin and k not in skip:
             z[f"extra/{k}"] = np.asarray(a)
     idx = sample_cells(ref_basin)
     z["cells"] = idx

@@ -41,3 +41,36 @@ def test_reference_simulator_drives_gpu_path(name, n, hours, built):
         for f, floor in (("PotEvap", 1e-6), ("SurfTemp", 1.0), ("CanStorage", 1e-6), ("CumTotEvap", 1e-6), ("CumIntercept", 1e-6)):
             err = np.abs(ref[f] - got[f]) / np.maximum(np.abs(ref[f]), floor)
             assert err.max() <= 1e-6, (f, err.max())
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+@pytest.mark.parametrize("ranks", [2, 3])
+def test_reference_host_runs_partitioned_through_the_binding(ranks, built):
+    """The reference's C++ objects drive a PARTITIONED run (what its MPI build does with tGraph + tParallel): the
+    harness partitions its own reach lists with tGraph::createDefaultPartition, the binding creates one handle per
+    partition (tribs_part_t) and runs 16-step pipelined batches on all of them (tribs_gpu_run, peer-memory halos);
+    the tCNodes, refilled from the ranks that own them, must match the pure serial reference (its serial == MPI
+    contract, test_big_spring.py:5-22) within 1e-6."""
+    d = tempfile.mkdtemp(prefix="tribshybp_")
+    write_basin(spec_for("deep", 40, runtime_h=8.0, seed=4, tributary_every=8, pmean=30.0), d)
+    lib = os.path.join(ROOT, "tribs_b200", "libtribs_gpu.so")
+    common = [HARNESS, "basin.in", "-K", "--no-basin", "--snap-from", "16", "--snap-to", "96", "--snap-every", "16",
+              "--phases", "e", "--max-steps", "96"]
+    outs = []
+    for tag, extra in (("ref", []), ("gpu", ["--gpu", lib, "--gpu-ranks", str(ranks), "--gpu-batch", "16"])):
+        out = os.path.join(d, tag)
+        os.makedirs(out)
+        r = subprocess.run([*common, "--out", out, *extra], cwd=d, capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        outs.append(read_trb(os.path.join(out, "steps.trb")))
+    ref, got = outs
+    fields = ["NwtNew", "MuNew", "MiNew", "NtNew", "NfNew", "RuNew", "RiNew", "Qpout", "intstorm", "srf_hr",
+              "SoilMoisture", "RootMoisture"]
+    worst = 0.0
+    for st in (16, 48, 96):
+        for f in fields:
+            a, b = ref[f"s{st}_e_{f}"], got[f"s{st}_e_{f}"]
+            worst = max(worst, float((np.abs(a - b) / np.maximum(np.abs(a), 1e-6)).max()))
+    assert worst <= 1e-6, worst
+    moved = {f: float(np.abs(ref[f"s96_e_{f}"] - ref[f"s16_e_{f}"]).max()) for f in ("NwtNew", "MuNew", "NfNew", "srf_hr")}
+    assert moved["MuNew"] > 0 and moved["NfNew"] > 0, moved

@@ -645,7 +645,8 @@ static int ensure_pipe(tribs_ctx *c, PipeState *ps, int n_steps) {
         dev_alloc(c, &ps->d_phases, 3 * S) || dev_alloc(c, &ps->d_bins, S) || dev_alloc(c, &ps->d_is_sat, 3 * S) ||
         dev_alloc(c, &ps->d_et_steps, S) || (!ps->d_etpack && dev_alloc(c, &ps->d_etpack, 1)))
       return 1;
-    ps->d_rain = nullptr;      // allocated when a step brings per-cell rain
+    ps->d_rain = nullptr;      // allocated when a step brings per-cell rain ...
+    if (c->n_ranks > 1 && dev_alloc(c, &ps->d_rain, S * n_own)) return 1;   // ... but never inside a batch other ranks wait for
     ps->max_steps = n_steps;
   }
   return 0;
@@ -1046,14 +1047,45 @@ static int preload_batch_kernels() {
 #undef TRIBS_PRELOAD
   return 0;
 }
-// the driver's own memset / copy kernels are loaded by using them once
+// the driver's own memset / copy kernels are loaded by using them once, with the sizes and patterns a batch uses
+// (the handle is on a step boundary: the arrays zeroed here are zero there anyway)
 static int warm_driver_kernels(tribs_ctx *c, PipeState *ps) {
-  CK(cudaMemsetAsync(ps->d_headtail, 0, 64 * sizeof(int32_t), c->stream));
-  CK(cudaMemsetAsync(ps->d_queue, 0xFF, 64, c->stream));
-  CK(cudaMemcpyAsync(ps->d_qeff_out, ps->d_qeff_steps, sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
-  double one = 1.0;
-  CK(cudaMemcpyAsync(ps->d_qeff_out, &one, sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  CK(cudaStreamSynchronize(c->stream));
+  cudaStream_t st = c->stream;
+  const size_t slots = (size_t)c->n_stream + 1;
+  CK(cudaMemsetAsync(ps->d_headtail, 0, 64 * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ps->d_queue, 0xFF, (size_t)kQueueClasses * 3 * ps->max_steps * c->n_tiles * sizeof(int32_t), st));
+  CK(cudaMemsetAsync(ps->d_queue, 0xFF, 64, st));
+  if (c->at_boundary) {
+    const int zero7[7] = {TRIBS_F_Qpin, TRIBS_F_srf, TRIBS_F_sbsrf, TRIBS_F_hsrf, TRIBS_F_psrf, TRIBS_F_satsrf, TRIBS_F_gwchange};
+    for (int k = 0; k < 7; k++) CK(cudaMemsetAsync(c->dv.f[zero7[k]], 0, (size_t)c->n_pad * sizeof(double), st));
+  }
+  CK(cudaMemcpyAsync(ps->d_qeff_out, ps->d_qeff_steps, (size_t)ps->max_steps * slots * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  CK(cudaMemcpyAsync(c->d_qeff_now, ps->d_qeff_out, slots * sizeof(double), cudaMemcpyDeviceToDevice, st));
+  std::vector<double> host((size_t)std::max(c->n, 4096), 0.0);      // pageable uploads, small and large
+  CK(cudaMemcpyAsync(c->d_stage, host.data(), (size_t)c->n * sizeof(double), cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_stage, host.data(), 4096, cudaMemcpyHostToDevice, st));
+  CK(cudaMemcpyAsync(c->d_stage, host.data(), sizeof(double), cudaMemcpyHostToDevice, st));
+  if (ps->d_rain) scatter_rain_kernel<<<1, 32, 0, st>>>(c->d_stage, c->d_dev_of_sweep, ps->d_rain, 0, 0, 0);
+  // The first launch of a kernel with a larger stack frame than any before makes the driver grow the context's
+  // local-memory arena, which waits for every running kernel: the batch kernel is therefore launched once here with
+  // nothing to do (every ticket counter is already at its total), not for the first time behind a barrier kernel
+  // that waits for a peer.
+  {
+    PipeArgs a{};
+    a.rq = ReadyQueues{ps->d_headtail, ps->d_queue, c->d_tile_hi, 1, nullptr, 128u, 2048u};
+    a.n_hi_warps = kPipeWarps; a.waves = 1;
+    a.abort_flag = c->d_abort; a.flags = c->d_flags;
+    a.pv.me = c->rank; a.pv.n_ranks = 1;
+    DynView dv = c->dv;
+    void *args[] = {&c->sv, &dv, &dv, &c->mc, &c->rc, &a};
+    const void *fn = c->max_degree <= 16 ? (const void *)pipeline_kernel<16>
+                     : (c->max_degree <= 32 ? (const void *)pipeline_kernel<32> : (const void *)pipeline_kernel<64>);
+    CK(cudaLaunchCooperativeKernel(fn, dim3(2), dim3(kPipeThreads), args, 0, st));
+    peer_barrier_kernel<<<1, 32, 0, st>>>(PeerView{c->rank, 0, {}, nullptr, nullptr, nullptr, nullptr}, ps->d_bar, 0, c->d_abort);
+  }
+  CK(cudaStreamSynchronize(st));
+  CK(cudaMemset(c->d_qeff_now, 0, slots * sizeof(double)));
+  CK(cudaMemset(ps->d_headtail, 0, 64 * sizeof(int32_t)));
   return 0;
 }
 

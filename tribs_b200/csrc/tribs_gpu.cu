@@ -851,6 +851,11 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
                               const tribs_part_t *part, tribs_handle_t *out) {
   if (!mesh || !prm || !out) return fail("tribs_gpu_init: null argument");
   if (part && part->nranks > 1 && !part->cell_owner) return fail("tribs_gpu_init: a partitioned init needs cell_owner");
+  // Kernels are loaded when the library is, not at their first launch: a load in the middle of a batch can wait for
+  // running kernels, and with several ranks in one process the running kernel may be a barrier waiting for the very
+  // rank whose host thread is stuck loading (no effect if the process initialised CUDA before; see also
+  // preload_batch_kernels).
+  setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail("tribs_gpu_init: no CUDA device (this library has no CPU path)");

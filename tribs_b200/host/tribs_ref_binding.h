@@ -51,7 +51,21 @@ struct TribsGpuBinding {
   }
   int idx(tNode *n) const { auto k = pos.find(n); return k == pos.end() ? -1 : k->second; }
 
-  void attach(tMesh<tCNode> *m, tKinemat *flow, tHydroModel *hydro, tRunTimer *t, const char *libpath) {
+  // ---- reach partitions (what tGraph / tParallel do in the MPI build). `rank_h` holds this process's ranks:
+  // one handle per MPI rank in a tRIBSpar-style host (it passes its own rank to attach(), gathers the 64-byte
+  // handles of tribs_gpu_ipc_export with MPI_Allgather where tParallel::initialize sets up MPI, and hands them
+  // to tribs_gpu_attach_peers), or all ranks of the run when one process drives several GPUs (attach() with
+  // nranks > 1 below: tribs_gpu_attach_local). `owner[i]` = reach2partition[tCNode::getReach()] of sweep cell i.
+  std::vector<tribs_handle_t> rank_h;
+  std::vector<int32_t> owner;
+  decltype(&tribs_gpu_run) p_run = nullptr;
+  decltype(&tribs_gpu_wait) p_wait = nullptr;
+  decltype(&tribs_gpu_attach_local) p_attach_local = nullptr;
+  decltype(&tribs_gpu_ipc_export) p_ipc_export = nullptr;
+  decltype(&tribs_gpu_attach_peers) p_attach_peers = nullptr;
+
+  void attach(tMesh<tCNode> *m, tKinemat *flow, tHydroModel *hydro, tRunTimer *t, const char *libpath,
+              int nranks = 1, const std::vector<int32_t> *cell_owner = nullptr, int max_batch_steps = 64) {
     mesh = m; timer = t;
     lib = dlopen(libpath, RTLD_NOW | RTLD_LOCAL);
     if (!lib) die("dlopen");
@@ -146,9 +160,42 @@ struct TribsGpuBinding {
     put(TRIBS_F_RootMoistureSC, col([](tCNode *c) { return c->getRootMoistureSC(); }));
     put(TRIBS_F_AvSoilMoisture, col([](tCNode *c) { return c->getAvSoilMoisture(); }));
     put(TRIBS_F_TTime, ttime);
-    if (p_init(&M, &P, &S, nullptr, &h)) die("tribs_gpu_init");
+    if (nranks <= 1) {
+      if (p_init(&M, &P, &S, nullptr, &h)) die("tribs_gpu_init");
+      rank_h.assign(1, h);
+      owner.assign(n, 0);
+    } else {
+      p_run = (decltype(p_run))dlsym(lib, "tribs_gpu_run");
+      p_wait = (decltype(p_wait))dlsym(lib, "tribs_gpu_wait");
+      p_attach_local = (decltype(p_attach_local))dlsym(lib, "tribs_gpu_attach_local");
+      p_ipc_export = (decltype(p_ipc_export))dlsym(lib, "tribs_gpu_ipc_export");
+      p_attach_peers = (decltype(p_attach_peers))dlsym(lib, "tribs_gpu_attach_peers");
+      if (!p_run || !p_wait || !p_attach_local || !p_ipc_export || !p_attach_peers || !cell_owner) die("dlsym (partitions)");
+      owner = *cell_owner;
+      for (int r = 0; r < nranks; r++) {
+        tribs_part_t pt{};
+        pt.rank = r; pt.nranks = nranks; pt.n_parts = nranks; pt.max_batch_steps = max_batch_steps; pt.cell_owner = owner.data();
+        tribs_handle_t hr = nullptr;
+        if (p_init(&M, &P, &S, &pt, &hr)) die("tribs_gpu_init (partition)");
+        rank_h.push_back(hr);
+      }
+      if (p_attach_local(rank_h.data(), nranks)) die("tribs_gpu_attach_local");
+      h = rank_h[0];
+    }
     for (auto &v : stage) v.assign(n, 0.0);
     rain.assign(n, 0.0);
+  }
+
+  // k whole time steps on every rank of this process in one pipelined batch (tribs_gpu_run): the calls return
+  // at once, the ranks meet on the device; the host waits once at the end. steps[i] as flags() would fill it
+  // for step i (the host advances tRunTimer and tRainfall for the k steps first).
+  void runBatch(const std::vector<tribs_step_t> &steps, const std::vector<uint32_t> &masks) {
+    if (!p_run) { p_run = (decltype(p_run))dlsym(lib, "tribs_gpu_run"); p_wait = (decltype(p_wait))dlsym(lib, "tribs_gpu_wait"); }
+    if (!p_run || !p_wait) die("dlsym (tribs_gpu_run)");
+    for (tribs_handle_t hr : rank_h)
+      if (p_run(hr, (int)steps.size(), steps.data(), masks.data())) die("tribs_gpu_run");
+    for (tribs_handle_t hr : rank_h)
+      if (p_wait(hr)) die("tribs_gpu_wait");
   }
 
   tribs_step_t flags() {
@@ -182,8 +229,10 @@ struct TribsGpuBinding {
     tribs_state_t S{};
     uint64_t mask = 0;
     for (int f : fields) { S.f[f] = stage[f].data(); mask |= TRIBS_MASK(f); }
-    if (p_sync(h, mask, &S)) die("tribs_gpu_sync");
+   for (size_t r = 0; r < rank_h.size(); r++) {       // every rank of this process hands back the cells it owns
+    if (p_sync(rank_h[r], mask, &S)) die("tribs_gpu_sync");
     for (size_t i = 0; i < cells.size(); i++) {
+      if (owner[i] != (int32_t)r) continue;
       tCNode *c = cells[i];
       c->setNwtNew(stage[TRIBS_F_NwtNew][i]); c->setMuNew(stage[TRIBS_F_MuNew][i]); c->setMiNew(stage[TRIBS_F_MiNew][i]);
       c->setNtNew(stage[TRIBS_F_NtNew][i]); c->setNfNew(stage[TRIBS_F_NfNew][i]); c->setRuNew(stage[TRIBS_F_RuNew][i]);
@@ -195,6 +244,7 @@ struct TribsGpuBinding {
       c->setSoilMoistureUNSC(stage[TRIBS_F_SoilMoistureUNSC][i]); c->setRootMoisture(stage[TRIBS_F_RootMoisture][i]);
       c->setRootMoistureSC(stage[TRIBS_F_RootMoistureSC][i]); c->setRecharge(stage[TRIBS_F_Recharge][i]);
     }
+   }
   }
   // ------------------------------------------------------------------ kernel (1): ET + interception
   // These bodies replace the cell loops of tEvapoTrans::callEvapoPotential (tEvapoTrans.cpp:603-795)
