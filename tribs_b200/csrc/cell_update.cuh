@@ -219,7 +219,12 @@ TRIBS_HD void sat_prepare_cell(const StaticView &s, const double *nwt_old, int i
 template <int MAXC>
 TRIBS_HD double sat_gather(const StaticView &s, const DynView &d, int i, const double *wt_elev,
                            const double *transm, int *overflow) {
+  // The reference sorts a cell's edge fluxes, then sums them (tCNode::getGwaterChng). The sorted list lives in
+  // registers: every slot is addressed statically (a bubble pass of min / max per new flux keeps it ascending, unused
+  // slots hold +inf), so nothing is indexed dynamically and nothing goes to local memory.
   double q[MAXC];
+#pragma unroll
+  for (int k = 0; k < MAXC; k++) q[k] = 1.0e308 * 10.0;   // +inf
   int nq = 0;
   const double elev_i = wt_elev[i], nwt_i = d.f[TRIBS_F_NwtOld][i], dbr_i = s.bedrock[i];
   const double t_i = transm[i], area_i = s.varea[i];
@@ -256,10 +261,14 @@ TRIBS_HD double sat_gather(const StaticView &s, const DynView &d, int i, const d
     }
     if (flux > 0.0 || flux < 0.0) {
       if (nq < MAXC) {
-        // insertion keeps q ascending: the reference sorts the contributions, then sums
-        int p = nq++;
-        while (p > 0 && q[p - 1] > flux) { q[p] = q[p - 1]; p--; }
-        q[p] = flux;
+        nq++;
+        double x = flux;
+#pragma unroll
+        for (int k = 0; k < MAXC; k++) {     // ascending: the smaller of (slot, carried) stays, the larger moves on
+          const double lo = fmin(q[k], x);
+          x = fmax(q[k], x);
+          q[k] = lo;
+        }
       } else
         *overflow = 1;
     }
@@ -267,7 +276,9 @@ TRIBS_HD double sat_gather(const StaticView &s, const DynView &d, int i, const d
     if (lp > best) { best = lp; best_pos = out_pos; }
   }
   double gw = 0.0;
-  for (int k = 0; k < nq; k++) gw += q[k];
+#pragma unroll
+  for (int k = 0; k < MAXC; k++)
+    if (k < nq) gw += q[k];
   if (best >= 0) {
     // the last edge of the cell in edge-list order decides which transmissivity is kept (2807, 2821)
     d.f[TRIBS_F_Transmissivity][i] = best_pos ? t_i : s.ar[i] * s.ks[i] * m_exp(-s.f[i] * nwt_i) / s.f[i];

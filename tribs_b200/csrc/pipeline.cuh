@@ -101,6 +101,7 @@ struct PipeArgs {
   int32_t n_pad, n_tiles, tile0, n_own_tiles, own_begin, n_own, K, rec_stride, last_sweep_dev;
   int32_t n_hi_tasks, n_lo_kind[3], n_hi_warps;
   int32_t mid_barrier;
+  uint32_t patience_ns;  // how long thread 0 of a lo block waits for a partial chunk of ready tasks to fill up
   int32_t waves;         // a lo block claims up to 16 * waves ready tasks per round (the later waves start without a barrier)
   int32_t *abort_flag, *flags;
   const struct EtPack *et;         // kernel (1)'s constants, static arrays and fields (batches with ET phases)
@@ -228,7 +229,7 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
       __syncthreads();     // everybody is done with the previous round (and with sh_*)
       if (threadIdx.x == 0) {
         unsigned spins = 0, ns = 64;
-        unsigned long long t_first = 0;
+        unsigned long long t_first = 0, t_seen = 0;
         int cnt = -1;
         for (;;) {
           bool all_done = true;
@@ -239,6 +240,13 @@ pipeline_kernel(StaticView s, DynView d_even, DynView d_odd, ModelConst m, Route
             if (h < a.n_lo_kind[q - 1]) all_done = false;
             const int n = min(t - h, kPipeWarps * a.waves);
             if (n > best_n) { best = q; best_n = n; }      // strict: ties go to the class tried first
+          }
+          if (best >= 0 && best_n < kPipeWarps && a.patience_ns) {
+            // fewer ready tasks than warps: give the rest of their bucket a moment to arrive, so that they start
+            // together on ONE block (and share its instruction cache) instead of one by one on sixteen
+            const unsigned long long t_now = global_ns();
+            if (!t_seen) t_seen = t_now;
+            if (t_now - t_seen < a.patience_ns) { __nanosleep(64); continue; }
           }
           if (best >= 0) {
             const int h = ld_relaxed_i32(a.rq.ctl + 2 * best);
@@ -893,6 +901,8 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
       a.n_hi_warps = n_hi_warps;
       a.waves = 1;
       a.mid_barrier = getenv("TRIBS_MID_BARRIER") != nullptr;
+      a.patience_ns = 0;
+      if (const char *e = getenv("TRIBS_PATIENCE_NS")) a.patience_ns = (uint32_t)std::max(0, atoi(e));
       if (const char *e = getenv("TRIBS_ROUND_WAVES")) a.waves = std::max(1, std::min(8, atoi(e)));
     }
     a.abort_flag = c->d_abort; a.flags = c->d_flags; a.pv = pv;

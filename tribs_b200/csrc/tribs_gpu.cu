@@ -1585,6 +1585,7 @@ struct MaxKey {
 };
 
 struct EtState {
+  bool ready = false;          // tribs_gpu_et_init completed
   EtConst k{};
   EtStatic st{};
   EtView ev{};
@@ -1651,7 +1652,13 @@ static std::vector<T> to_device_order(tribs_ctx *c, const T *sweep, T pad) {
   return v;
 }
 
+static int et_init_impl(tribs_handle_t c, const tribs_et_params_t *p);
 extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
+  const int rc = et_init_impl(c, p);
+  if (rc && c && c->et && !c->et->ready) tribs_free_et(c);   // a failed upload must not block a retry with "already initialised"
+  return rc;
+}
+static int et_init_impl(tribs_handle_t c, const tribs_et_params_t *p) {
   if (!c || !p) return fail("tribs_gpu_et_init: null argument");
   if (c->et) return fail("tribs_gpu_et_init: already initialised");
   if (!p->flow_slope || !p->aspect || !p->vol_heat_cond || !p->soil_heat_cap || !p->soil_cutoff || !p->root_cutoff ||
@@ -1721,6 +1728,7 @@ extern "C" int tribs_gpu_et_init(tribs_handle_t c, const tribs_et_params_t *p) {
     e->ev.f[f] = d;
   }
   for (int sl = 0; sl < 2; sl++) if (dev_alloc(c, &e->d_record[sl], (size_t)c->n_pad)) return 1;
+  e->ready = true;
   return 0;
 }
 
