@@ -30,6 +30,16 @@ def test_gpu_matches_reference_golden(name, built):
     assert w.max() <= REL_TOL, w.report()
 
 
+def test_gpu_two_level_segment_reduce_matches_reference_stacks(built, monkeypatch):
+    """Large partitions stitch the block-boundary runs of the hillslope routing in two levels
+    (route_seg_level2_kernel); forced on here, so that the reference's (TimeInd, Qeff) stacks check that path too."""
+    monkeypatch.setenv("TRIBS_SEG_LEVEL2_MIN", "0")
+    basin, snaps, _ = load_golden("deep")
+    n_steps = int(snaps["n_steps"][0])
+    w = run_and_compare(GpuStepper(basin, _sched(basin)), snaps, n_steps, floor=ABS_FLOOR)
+    assert ("r", "QeffBins") in w.w and w.max() <= REL_TOL, w.report()
+
+
 @pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
 @pytest.mark.parametrize("name,n,hours", [("deep", 40, 30.0), ("shallow", 32, 30.0), ("redistribute", 32, 40.0), ("evap", 32, 40.0), ("met", 32, 40.0)])
 def test_gpu_matches_live_reference(name, n, hours, built):

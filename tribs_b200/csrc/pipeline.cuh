@@ -1049,7 +1049,7 @@ static int preload_batch_kernels() {
   TRIBS_PRELOAD(pipeline_init_kernel); TRIBS_PRELOAD(peer_barrier_kernel);
   TRIBS_PRELOAD(pipeline_kernel<16>); TRIBS_PRELOAD(pipeline_kernel<32>); TRIBS_PRELOAD(pipeline_kernel<64>);
   TRIBS_PRELOAD(sums_reduce_kernel); TRIBS_PRELOAD(combine_sums_kernel); TRIBS_PRELOAD(route_seg_kernel);
-  TRIBS_PRELOAD(route_seg_fixup_kernel); TRIBS_PRELOAD(route_latch_kernel); TRIBS_PRELOAD(tile_reduce_kernel);
+  TRIBS_PRELOAD(route_seg_fixup_kernel); TRIBS_PRELOAD(route_seg_level2_kernel); TRIBS_PRELOAD(route_latch_kernel); TRIBS_PRELOAD(tile_reduce_kernel);
   TRIBS_PRELOAD(part_reduce_kernel); TRIBS_PRELOAD(combine_results_kernel); TRIBS_PRELOAD(qeff_combine_kernel);
   TRIBS_PRELOAD(set_global_kernel); TRIBS_PRELOAD(esrf_fixup_kernel); TRIBS_PRELOAD(scatter_rain_kernel);
   TRIBS_PRELOAD(fill_kernel); TRIBS_PRELOAD(gauge_fill_kernel); TRIBS_PRELOAD(gather_to_sweep_kernel);

@@ -76,8 +76,8 @@ struct Slab { char *base = nullptr; size_t cap = 0, used = 0; };
 struct SegPart {
   int32_t *cell = nullptr, *slot = nullptr;
   double *path = nullptr, *area = nullptr;
-  struct SegBoundary *bnd = nullptr;
-  int n_seg = 0, blocks = 0;
+  struct SegBoundary *bnd = nullptr, *bnd2 = nullptr;   // boundary records of the first / second reduce level
+  int n_seg = 0, blocks = 0, blocks2 = 0;
 };
 struct PipeState;
 struct tribs_ctx {
@@ -90,6 +90,7 @@ struct tribs_ctx {
   std::vector<int32_t> sweep_owner;          // partition of every sweep cell (empty: one partition)
   Slab slab{};
   std::vector<SegPart> seg_parts;
+  int seg_level2_min = 64;                   // partitions with more 1024-entry blocks reduce their boundary runs in two levels
   int tile_bins = 1, rec_stride = 15;        // per-tile routing record: 14 + 5 * tile_bins doubles
   double *d_tile_rec = nullptr;              // [n_own_tiles][rec_stride] single-step routing records
   double *d_part_vec = nullptr, *d_block_part = nullptr, *d_sums_part = nullptr;
@@ -335,34 +336,16 @@ __device__ __forceinline__ double slot_velocity(const StaticView &s, const DynVi
   return hill_velocity(s, d, rc, node, qstrm_outlet);
 }
 
-__global__ void __launch_bounds__(kSegBlock)
-route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restrict__ seg_cell,
-                 const int32_t *__restrict__ seg_slot, const double *__restrict__ seg_path,
-                 const double *__restrict__ seg_area, const int32_t *__restrict__ slot_dev, int n_seg, double now,
-                 double qstrm_outlet, const double *__restrict__ srf_of_cell, double *ring, SegBoundary *bnd) {
+// One 1024-entry block of a streaming reduce-by-key: keys are non-decreasing along the entries, every key is ONE
+// contiguous run. Warp-shuffle segmented scan, carries across warps; the runs that lie strictly inside the block go
+// straight into the slot's ring of bins (unique owner, no atomics), the first and the last (possibly cut) run are handed
+// to the next level as the block's boundary record.
+constexpr long long kSegPadKey = 0x7fffffffffffffffLL;   // padding entries sort last and carry nothing
+__device__ __forceinline__ void seg_block_reduce(long long key, double v, const RouteConst &rc, double *ring, SegBoundary *bnd) {
   __shared__ long long sh_key_last[32], sh_key_first[32];
   __shared__ double sh_acc_last[32], sh_carry[32];
   __shared__ int sh_single[32];
-  const int e = blockIdx.x * kSegBlock + threadIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const double dtreff = rc.dt_reff;
-  const int cur = (int)ceil(now / dtreff);
-  const bool at_end = ((int)ceil(now / dtreff) == (int)floor(now / dtreff));
-  const double same_box_div = at_end ? (rc.tstep * 3600.) : ((cur * dtreff - now + rc.tstep) * 3600.);
-  long long key = 0x7fffffffffffffffLL;   // padding entries sort last and carry nothing
-  double v = 0.0;
-  if (e < n_seg) {
-    const int slot = seg_slot[e];
-    const double hv = slot_velocity(s, d, rc, slot_dev[slot], qstrm_outlet);
-    const double tt = seg_path[e] / hv / 3600.;
-    const int bin = (int)ceil((now + tt) / dtreff);
-    key = ((long long)slot << 32) | (unsigned)bin;
-    const double srf = srf_of_cell[seg_cell[e]];   // the live array, or a per-step snapshot of it (batches)
-    if (srf > 0.0 && !(srf > 999999) && s.owned[seg_cell[e]]) {
-      double vr = srf * seg_area[e] / 1000.;
-      v = (bin == cur) ? vr / same_box_div : vr / (dtreff * 3600.);
-    }
-  }
   // warp-level segmented inclusive scan
   long long prev_key = __shfl_up_sync(0xffffffffu, key, 1);
   const bool head = (lane == 0) || (prev_key != key);
@@ -397,7 +380,7 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
   const bool tail = (next_key != key);
   const long long block_first_key = sh_key_first[0];
   const long long block_last_key = sh_key_last[31];
-  if (tail && key != 0x7fffffffffffffffLL) {
+  if (tail && key != kSegPadKey) {
     const bool is_first_run = (key == block_first_key);
     const bool is_last_run = (key == block_last_key);
     if (is_first_run) { bnd[blockIdx.x].first_key = key; bnd[blockIdx.x].first_val = acc; }
@@ -407,6 +390,55 @@ route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restri
       ring[(size_t)slot * rc.ring + (bin % rc.ring)] += acc;
     }
   }
+}
+
+
+__global__ void __launch_bounds__(kSegBlock)
+route_seg_kernel(StaticView s, DynView d, RouteConst rc, const int32_t *__restrict__ seg_cell,
+                 const int32_t *__restrict__ seg_slot, const double *__restrict__ seg_path,
+                 const double *__restrict__ seg_area, const int32_t *__restrict__ slot_dev, int n_seg, double now,
+                 double qstrm_outlet, const double *__restrict__ srf_of_cell, double *ring, SegBoundary *bnd) {
+  const int e = blockIdx.x * kSegBlock + threadIdx.x;
+  const double dtreff = rc.dt_reff;
+  const int cur = (int)ceil(now / dtreff);
+  const bool at_end = ((int)ceil(now / dtreff) == (int)floor(now / dtreff));
+  const double same_box_div = at_end ? (rc.tstep * 3600.) : ((cur * dtreff - now + rc.tstep) * 3600.);
+  long long key = kSegPadKey;
+  double v = 0.0;
+  if (e < n_seg) {
+    const int slot = seg_slot[e];
+    const double hv = slot_velocity(s, d, rc, slot_dev[slot], qstrm_outlet);
+    const double tt = seg_path[e] / hv / 3600.;
+    const int bin = (int)ceil((now + tt) / dtreff);
+    key = ((long long)slot << 32) | (unsigned)bin;
+    const double srf = srf_of_cell[seg_cell[e]];   // the live array, or a per-step snapshot of it (batches)
+    if (srf > 0.0 && !(srf > 999999) && s.owned[seg_cell[e]]) {
+      double vr = srf * seg_area[e] / 1000.;
+      v = (bin == cur) ? vr / same_box_div : vr / (dtreff * 3600.);
+    }
+  }
+  seg_block_reduce(key, v, rc, ring, bnd);
+}
+
+// second level: the boundary records of the first (two items per block: its first and its last run) are themselves a
+// non-decreasing key sequence; reduce them the same way, so that the sequential stitch only sees a few dozen records
+__global__ void __launch_bounds__(kSegBlock)
+route_seg_level2_kernel(RouteConst rc, const SegBoundary *__restrict__ bnd1, int n_blocks1, double *ring, SegBoundary *bnd2) {
+  const int e = blockIdx.x * kSegBlock + threadIdx.x;
+  long long key = kSegPadKey;
+  double v = 0.0;
+  if (e < 2 * n_blocks1) {
+    const SegBoundary x = bnd1[e >> 1];
+    if (e & 1) {       // a block that is one single run has no "last" record: continue its key with nothing
+      key = x.last_key >= 0 ? x.last_key : x.first_key;
+      v = x.last_key >= 0 ? x.last_val : 0.0;
+    } else {
+      key = x.first_key;
+      v = x.first_val;
+    }
+    if (key < 0) { key = kSegPadKey; v = 0.0; }
+  }
+  seg_block_reduce(key, v, rc, ring, bnd2);
 }
 
 // sequential stitch of the block-boundary runs (block order = entry order) of one partition; the
@@ -1174,6 +1206,7 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
     double max_path = 0.0;
     for (int i = 0; i < n; i++) if (mesh->boundary[i] == 0) max_path = std::max(max_path, mesh->hillpath[i]);
     c->seg_parts.assign(c->n_parts, SegPart{});
+    if (const char *e = getenv("TRIBS_SEG_LEVEL2_MIN")) c->seg_level2_min = atoi(e);   // tests: 0 forces the two-level path on small basins
     for (int r : c->my_parts) {
       std::vector<int32_t> seg_cell, seg_slot;
       std::vector<double> seg_path, seg_area;
@@ -1193,8 +1226,9 @@ extern "C" int tribs_gpu_init(const tribs_mesh_t *mesh, const tribs_params_t *pr
       SegPart &sp = c->seg_parts[r];
       sp.n_seg = (int)seg_cell.size();
       sp.blocks = std::max(1, (sp.n_seg + kSegBlock - 1) / kSegBlock);
+      sp.blocks2 = std::max(1, (2 * sp.blocks + kSegBlock - 1) / kSegBlock);
       if (dev_upload(c, &sp.cell, seg_cell) || dev_upload(c, &sp.slot, seg_slot) || dev_upload(c, &sp.path, seg_path) ||
-          dev_upload(c, &sp.area, seg_area) || dev_alloc(c, &sp.bnd, (size_t)sp.blocks))
+          dev_upload(c, &sp.area, seg_area) || dev_alloc(c, &sp.bnd, (size_t)sp.blocks) || dev_alloc(c, &sp.bnd2, (size_t)sp.blocks2))
         return 1;
     }
     if (dev_upload(c, &c->d_sn_dev, sdev)) return 1;
@@ -1380,7 +1414,12 @@ static int route_segments(tribs_ctx *c, const DynView &dv, const double *srf_of_
     if (sp.n_seg == 0) continue;
     route_seg_kernel<<<sp.blocks, kSegBlock, 0, st>>>(c->sv, dv, c->rc, sp.cell, sp.slot, sp.path, sp.area, c->d_sn_dev, sp.n_seg,
                                                       now, qstrm_outlet, srf_of_cell, c->d_ring, sp.bnd);
-    route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, sp.bnd, sp.blocks, c->d_ring);
+    if (sp.blocks > c->seg_level2_min) {    // many blocks: their boundary runs are reduced once more before the sequential stitch
+      route_seg_level2_kernel<<<sp.blocks2, kSegBlock, 0, st>>>(c->rc, sp.bnd, sp.blocks, c->d_ring, sp.bnd2);
+      route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, sp.bnd2, sp.blocks2, c->d_ring);
+      c->launches++;
+    } else
+      route_seg_fixup_kernel<<<1, 1024, 0, st>>>(c->rc, sp.bnd, sp.blocks, c->d_ring);
     c->launches += 2;
   }
   const int slots = c->n_stream + 1;
