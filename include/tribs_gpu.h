@@ -383,6 +383,10 @@ typedef struct {
   const double *const *init;    /* NULL, or TRIBS_N_SNOW_FIELDS pointers (NULL entries = 0) */
 } tribs_snow_params_t;
 
+/* tribs_gpu_run with the snow pack inside the batch (OPTSNOW 1, OPTINTERCEPT 0): snow_steps[k] (or NULL) and
+ * hourly_time_step[k] are what tribs_gpu_snow_step would be called with before the sweep of step k. */
+int tribs_gpu_run_snow(tribs_handle_t h, int n_steps, const tribs_step_t *steps, const uint32_t *phase_masks,
+                       const tribs_et_step_t *const *snow_steps, const int32_t *hourly_time_step);
 /* after tribs_gpu_et_init (with snow_option = 1 in its parameters) */
 int tribs_gpu_snow_init(tribs_handle_t h, const tribs_snow_params_t *prm);
 /* one callSnowPack: `s` as for tribs_gpu_et_step (do_potential set, met_potential = the record of

@@ -87,6 +87,40 @@ def test_gpu_snow_pack_matches_live_reference(extra, built):
     assert max(np.abs(snaps[k]).max() for k in snaps if k.endswith("_m_CumMelt")) > 0.0
 
 
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+def test_gpu_snow_pack_inside_batches_is_bitwise_identical_to_single_steps(built):
+    """OPTSNOW 1 without a canopy: the snow pack is a phase of the pipelined batch (tribs_gpu_run_snow) and must give
+    exactly what tribs_gpu_snow_step between single steps gives - every water-balance, ET and snow field."""
+    from tribs_b200.gpu import ET_FIELDS, SNOW_FIELDS
+    spec = spec_for("snow", 20, runtime_h=60.0, seed=9, pmean=8.0, extra={"OPTINTERCEPT": 0})
+    basin, _, _, _ = run_reference(spec, snap_from=1, snap_to=0)
+    n_steps = 40 * 16
+    a = GpuStepper(basin, _sched(basin))
+    for _ in range(n_steps):
+        a.advance(); a.unsat()
+        if a.gw_due():
+            a.sat()
+        a.route(); a.reset()
+    b = GpuStepper(basin, _sched(basin))
+    done = 0
+    while done < n_steps:
+        k = min(48, n_steps - done)       # three snow phases inside every batch
+        b.sim.run_batch(k)
+        done += k
+    fa, fb = a.get(ALL_CHECK + ["LiqWE", "IceWE", "LiqRouted"]), b.get(ALL_CHECK + ["LiqWE", "IceWE", "LiqRouted"])
+    for f in fa:
+        assert np.array_equal(fa[f], fb[f]), f
+    ea, eb = a.get(ET_FIELDS), b.get(ET_FIELDS)
+    for f in ET_FIELDS:
+        assert np.array_equal(ea[f], eb[f]), f
+    sa, sb = a.get(SNOW_FIELDS), b.get(SNOW_FIELDS)
+    for f in SNOW_FIELDS:
+        assert np.array_equal(sa[f], sb[f]), f
+    assert np.abs(fa["IceWE"]).max() > 0 and np.abs(sa["CumMelt"]).max() > 0
+    for nm in ["mhydro", "crr", "msm", "mgw"]:
+        assert np.array_equal(a.result(nm), b.result(nm)), nm
+
+
 def test_gpu_et_per_cell_met_records_equal_station_records(built):
     """Gridded meteorology (METDATAOPTION 2) reaches kernel (1) as one record per cell: the same
     values expanded per cell must give bit-identical results to the station form."""

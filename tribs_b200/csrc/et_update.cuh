@@ -82,6 +82,8 @@ struct EtStepDev {
   int32_t hour, first_call, dew_hum_flag, ts_option, sky_flag_from;
   double te_met, te_eti, rs_ratio;                 // rs_ratio = rsRatio[hour] of stomResist()
   MetDev pot, cmp;
+  int32_t snow_hourly;                             // batches with OPTSNOW 1: tEvapoTrans::hourlyTimeStep of this callSnowPack
+  int32_t pad_;
 };
 
 struct EtView { double *f[TRIBS_N_ET_FIELDS]; };

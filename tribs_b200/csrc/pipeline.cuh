@@ -108,11 +108,18 @@ struct PipeArgs {
   const EtStepDev *et_steps;       // one per ET phase of the batch
   PeerView pv;
 };
-struct EtPack { EtConst k; EtStatic st; EtView ev; };
+struct EtPack { EtConst k; EtStatic st; EtView ev; SnowConst sc; SnowView sv; int32_t snow; int32_t pad_; };
 // kernel (1) for one cell inside a batch: out of line, so that its 168 registers' worth of temporaries
-// live in this call's frame instead of raising the register count of every sweep task
+// live in this call's frame instead of raising the register count of every sweep task. With OPTSNOW 1 (no canopy:
+// tSnowPack::callSnowPack then needs nothing but the cell itself) the snow pack takes the place of both ET sweeps.
 __device__ __noinline__ void et_phase_cell(const EtPack *et, const EtStepDev *s, const DynView *d, int i) {
-  et_cell(et->k, et->st, *s, et->ev, *d, i);
+  if (et->snow) {
+    SnowConst sc = et->sc;
+    sc.hourly = s->snow_hourly;
+    SnowProbe pr;
+    snow_cell_step(et->k, et->st, *s, sc, et->ev, et->sv, *d, i, 0.88, 0.0, pr);   // no canopy: nothing reads the carried members
+  } else
+    et_cell(et->k, et->st, *s, et->ev, *d, i);
 }
 
 __device__ __forceinline__ void fence_tasks(bool sys) {
@@ -675,8 +682,9 @@ static const T *peer_host_ptr(tribs_ctx *c, PipeState *ps, int r, const T *mine)
 
 // host-side part of tribs_gpu_et_step for one ET phase of a batch: the device form of the step and its station
 // records, staged into this phase's slice of the batch's record buffer
-static int stage_et_phase(tribs_ctx *c, PipeState *ps, int index, const tribs_et_step_t *s, EtStepDev *out) {
+static int stage_et_phase(tribs_ctx *c, PipeState *ps, int index, const tribs_et_step_t *s, int snow_hourly, EtStepDev *out) {
   EtState *e = c->et;
+  const bool snow = e->snow_option != 0;
   if (s->hour < 0 || s->hour > 23) return fail("tribs_gpu_run_et: hour out of range");
   static const double rsRatio[24] = {3.837, 3.589, 3.21, 2.43, 1.617, 1.196, 1.067, 1.014,   // stomResist, tEvapoTrans.cpp:1494-1496
                                      0.995, 0.976, 0.976, 1.0, 1.053, 1.167, 1.354, 1.637,
@@ -684,13 +692,16 @@ static int stage_et_phase(tribs_ctx *c, PipeState *ps, int index, const tribs_et
   EtStepDev d{};
   d.do_potential = s->do_potential && e->k.et_option; d.do_components = s->do_components; d.intercept_flag = s->intercept_flag;
   d.met_time = s->do_potential;
+  if (snow) {   // as tribs_gpu_snow_step: callSnowPack runs at met_hour only and holds both sweeps
+    d.do_potential = 1; d.do_components = 1; d.met_time = 1; d.intercept_flag = 0; d.snow_hourly = snow_hourly;
+  }
   d.alphaD = s->alphaD; d.sinAlpha = s->sinAlpha; d.sunaz = s->sunaz; d.Io = s->Io;
   d.cos_alpha = cos(asin(s->sinAlpha));
   d.hour = s->hour; d.first_call = s->first_call; d.dew_hum_flag = s->dew_hum_flag; d.ts_option = s->ts_option;
   d.sky_flag_from = s->sky_flag_from; d.te_met = s->te_met; d.te_eti = s->te_eti;
   d.rs_ratio = rsRatio[s->hour];
   const tribs_met_t *mets[2] = {d.do_potential ? s->met_potential : nullptr,
-                                (d.do_components && e->k.et_option) ? s->met_components : nullptr};
+                                (!snow && d.do_components && e->k.et_option) ? s->met_components : nullptr};
   for (int sl = 0; sl < 2; sl++) {
     const tribs_met_t *m = mets[sl];
     if (!m) continue;
@@ -722,14 +733,15 @@ static int stage_et_phase(tribs_ctx *c, PipeState *ps, int index, const tribs_et
     o.atm_press = b + 4 * (size_t)nr; o.wind_speed = b + 5 * (size_t)nr; o.sky_cover = b + 6 * (size_t)nr;
     o.rad_global = b + 7 * (size_t)nr; o.elev = b + 8 * (size_t)nr;
   }
+  if (snow) d.cmp = d.pot;        // ComputeETComponents runs inside the same cell loop, before the met clock advances
   *out = d;
   return 0;
 }
 
 static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
-                     const tribs_et_step_t *const *et_steps);
+                     const tribs_et_step_t *const *et_steps, const int32_t *snow_hourly);
 extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks) {
-  return run_batch(c, n_steps, steps, masks, nullptr);
+  return run_batch(c, n_steps, steps, masks, nullptr, nullptr);
 }
 // The same with kernel (1) inside the batch: et_steps[k] (or NULL) is what tribs_gpu_et_step would be called with
 // before the sweep of step k (Simulator::SurfaceHydroProcesses, tSimul.cpp:419-461). The ET / interception update
@@ -737,11 +749,19 @@ extern "C" int tribs_gpu_run(tribs_handle_t c, int n_steps, const tribs_step_t *
 // basin-wide wait at every METSTEP.
 extern "C" int tribs_gpu_run_et(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
                                 const tribs_et_step_t *const *et_steps) {
-  return run_batch(c, n_steps, steps, masks, et_steps);
+  return run_batch(c, n_steps, steps, masks, et_steps, nullptr);
+}
+// The same with OPTSNOW 1 and no canopy (OPTINTERCEPT 0): snow_steps[k] (or NULL) and hourly_time_step[k] are what
+// tribs_gpu_snow_step would be called with before the sweep of step k (tSimul.cpp:464-492). With a canopy the snow pack
+// carries two members from cell to cell in sweep order and stays a call between batches.
+extern "C" int tribs_gpu_run_snow(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
+                                  const tribs_et_step_t *const *snow_steps, const int32_t *hourly_time_step) {
+  if (!hourly_time_step) return fail("tribs_gpu_run_snow: hourly_time_step missing");
+  return run_batch(c, n_steps, steps, masks, snow_steps, hourly_time_step);
 }
 
 static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, const uint32_t *masks,
-                     const tribs_et_step_t *const *et_steps) {
+                     const tribs_et_step_t *const *et_steps, const int32_t *snow_hourly) {
   if (!c || !steps || !masks || n_steps <= 0) return fail("tribs_gpu_run: bad argument");
   CK(cudaSetDevice(c->device));
   const bool dbg_t = getenv("TRIBS_DEBUG") != nullptr;
@@ -761,7 +781,9 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     pattern[k] = (masks[k] & TRIBS_PHASE_SAT) ? 1 : 0;
     if (et_steps && et_steps[k] && (et_steps[k]->do_potential || et_steps[k]->do_components)) {
       if (!c->et) return fail("tribs_gpu_run_et: call tribs_gpu_et_init first");
-      if (c->et->snow_option) return fail("tribs_gpu_run_et: with OPTSNOW 1 the snow pack runs between batches (tribs_gpu_snow_step)");
+      if (c->et->snow_option && (!c->et->snow_ready || c->et->k.i_option != 0 || !snow_hourly))
+        return fail("tribs_gpu_run_et: with OPTSNOW 1 use tribs_gpu_run_snow (no canopy), or tribs_gpu_snow_step between batches (canopy)");
+      if (!c->et->snow_option && snow_hourly) return fail("tribs_gpu_run_snow: the handle has no snow pack");
       pattern[k] |= 2;
     }
   }
@@ -823,7 +845,7 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
     if (ph.kind != 2) n_state++;
     else {
       EtStepDev d{};
-      if (stage_et_phase(c, ps, n_et, et_steps[ph.step], &d)) return 1;
+      if (stage_et_phase(c, ps, n_et, et_steps[ph.step], snow_hourly ? snow_hourly[ph.step] : 0, &d)) return 1;
       ps->h_et_steps.push_back(d);
       n_et++;
     }
@@ -838,6 +860,8 @@ static int run_batch(tribs_handle_t c, int n_steps, const tribs_step_t *steps, c
   }
   if (n_et > 0) {
     ps->h_etpack.k = c->et->k; ps->h_etpack.st = c->et->st; ps->h_etpack.ev = c->et->ev;
+    ps->h_etpack.snow = c->et->snow_option != 0;
+    if (ps->h_etpack.snow) { ps->h_etpack.sc = c->et->sc; ps->h_etpack.sv = c->et->snv; }
     CK(cudaMemcpyAsync(ps->d_etpack, &ps->h_etpack, sizeof(EtPack), cudaMemcpyHostToDevice, st));
     CK(cudaMemcpyAsync(ps->d_et_steps, ps->h_et_steps.data(), (size_t)n_et * sizeof(EtStepDev), cudaMemcpyHostToDevice, st));
     c->et->gen += n_et;

@@ -136,7 +136,7 @@ class SnowParams(C.Structure):
                 ("reserved", C.c_int32), ("init", C.POINTER(PD))]
 
 
-EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_run_et", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
+EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_run_et", "tribs_gpu_run_snow", "tribs_gpu_retrieve_qeff_steps", "tribs_gpu_sync", "tribs_gpu_push", "tribs_gpu_retrieve_qeff",
            "tribs_gpu_pending_qeff",
            "tribs_gpu_n_stream", "tribs_gpu_stream_cells", "tribs_gpu_get_results", "tribs_gpu_get_globals",
            "tribs_gpu_sweep_levels", "tribs_gpu_device_index", "tribs_gpu_launch_count", "tribs_gpu_set_timing",
@@ -170,6 +170,7 @@ def load():
     L.tribs_gpu_step.argtypes = [H, C.c_uint32, C.POINTER(Step)]
     L.tribs_gpu_run.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32)]
     L.tribs_gpu_run_et.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(EtStep))]
+    L.tribs_gpu_run_snow.argtypes = [H, C.c_int, C.POINTER(Step), C.POINTER(C.c_uint32), C.POINTER(C.POINTER(EtStep)), PI]
     L.tribs_gpu_retrieve_qeff_steps.argtypes = [H, C.c_int, PD]
     L.tribs_gpu_sync.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
     L.tribs_gpu_push.argtypes = [H, C.c_uint64, C.POINTER(StateT)]
@@ -359,7 +360,18 @@ class GpuBasin:
                 s.rain = _d(a)
             s.qstrm_outlet = sd.get("qstrm_outlet", 0.0)
             masks[q] = PHASE_UNSAT | PHASE_ROUTE | PHASE_RESET | (PHASE_SAT if sd.get("sat") else 0)
-        if any(sd.get("et") is not None for sd in steps):
+        if any(sd.get("snow") is not None for sd in steps):      # (step, rec, hourly, cell_record, elev) as for snow_step
+            ets = (C.POINTER(EtStep) * k)()
+            hourly = (C.c_int32 * k)()
+            for q, sd in enumerate(steps):
+                if sd.get("snow") is not None:
+                    step, rec, hr, cell_record, elev = sd["snow"]
+                    es = self._snow_step_struct(step, rec, cell_record, elev, keep)
+                    keep.append(es)
+                    ets[q] = C.pointer(es)
+                    hourly[q] = int(hr)
+            _chk(self.L.tribs_gpu_run_snow(self.h, k, arr, masks, ets, hourly))
+        elif any(sd.get("et") is not None for sd in steps):
             ets = (C.POINTER(EtStep) * k)()
             for q, sd in enumerate(steps):
                 if sd.get("et") is not None:
@@ -533,14 +545,19 @@ class GpuBasin:
     def snow_step(self, step: dict, rec: dict, hourly: int, cell_record=None, elev=None):
         """One tSnowPack::callSnowPack; *step*/*rec* as produced by met.EvapoTransHost.potential_call."""
         keep = []
+        s = self._snow_step_struct(step, rec, cell_record, elev, keep)
+        _chk(self.L.tribs_gpu_snow_step(self.h, C.byref(s), int(hourly)))
+
+    def _snow_step_struct(self, step, rec, cell_record, elev, keep):
         s = EtStep()
         for k in ("alphaD", "sinAlpha", "sunaz", "Io", "hour", "dew_hum_flag", "ts_option", "first_call", "te_met",
                   "te_eti", "sky_flag_from"):
             setattr(s, k, step[k])
         s.do_potential = 1
         m = self._met(rec, cell_record, elev, keep)
+        keep.append(m)
         s.met_potential = C.pointer(m)
-        _chk(self.L.tribs_gpu_snow_step(self.h, C.byref(s), int(hourly)))
+        return s
 
     def snow_members(self):
         """(albedo, snCanWE) as the last swept cell left them, and the probe rounds of the last call."""

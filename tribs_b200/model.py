@@ -309,8 +309,18 @@ class Simulator:
             # steps in between or uploads made by other entry points (a static gauge map + K gauge values per
             # step is the cheap form of spatially varying rain, see tribs_gpu_set_rain_gauges)
             step_rain = rain
-            et_arg = None
-            if et_on and self.evapotrans.getSnowOpt() == 0 and self.et_in_batch:
+            et_arg = snow_arg = None
+            if et_on and self.evapotrans.getSnowOpt() != 0 and self.intercept.getIoption() == 0 and self.et_in_batch:
+                # OPTSNOW 1 without a canopy: callSnowPack needs nothing but the cell itself and rides inside the batch
+                met_due, _ = self.met_clock.due(now)
+                if met_due:
+                    host = self.evapotrans.host
+                    hourly = host.hourlyTimeStep
+                    step, rec = host.potential_call(t.hour, now)
+                    step["te_eti"] = float(t.getElapsedETISteps(now))
+                    snow_arg = (step, rec, hourly, None if self._record_sent[0] else host.cell_record, host.elev)
+                    self._record_sent[0] = True
+            elif et_on and self.evapotrans.getSnowOpt() == 0 and self.et_in_batch:
                 # kernel (1) rides inside the batch as one more phase of every tile (tribs_gpu_run_et)
                 met_due, eti_due = self.met_clock.due(now)
                 if met_due or eti_due:
@@ -341,7 +351,7 @@ class Simulator:
             steps.append(dict(current_time=now, elapsed_steps=t.getElapsedSteps(now),
                               hourly_reset=int(not math.fmod(now - t.getTimeStep(), t.etistep)),
                               sat=bool(self.gw_on and not math.fmod(now, t.getGWTimeStep())),
-                              rain=step_rain, et=et_arg))
+                              rain=step_rain, et=et_arg, snow=snow_arg))
         flush()
         self.batch_qeff = np.concatenate(qeff) if qeff else None
         return out
