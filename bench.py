@@ -32,6 +32,7 @@ METRIC = "voronoi_cell_timesteps_per_sec"
 UNIT = "cell-timesteps/s"
 # compulsory bytes per cell and invocation of the dominant kernel (unsat sweep)
 ET_BYTES_PER_CELL = 548.0      # 236 B read + 312 B written per cell per fused ET call
+SNOW_BYTES_PER_CELL = 920.0    # snow pack per call
 UNSAT_BYTES_PER_CELL = 520.0
 SAT_BYTES_PER_CELL = 710.0
 STEP_BYTES_PER_CELL = 677.0      # whole step, storm-only configuration
@@ -83,6 +84,8 @@ WORKLOAD = {
     2: "synthetic V-valley TIN, uniform storm 20 mm/h, TIMESTEP 3.75 min, GWSTEP 30 min, ET/snow off",
     3: "synthetic V-valley TIN, rain gauges + weather station, Penman-Monteith ET + Rutter interception every "
        "METSTEP 60 min, TIMESTEP 3.75 min, GWSTEP 30 min",
+    5: "synthetic V-valley TIN, winter weather station + gauges, snow pack (OPTSNOW 1, no canopy) every METSTEP 60 min, "
+       "perched zone over a shallow water table, TIMESTEP 3.75 min, GWSTEP 30 min",
 }
 
 
@@ -168,7 +171,7 @@ def run_gpu(args):
             print(f"bench.py[rank {rank}] {time.perf_counter() - t_start:7.1f} s  {what}", file=sys.stderr, flush=True)
 
     cfg = args.config
-    side = args.side if args.side > 0 else (3163 if cfg == 3 else 1000)
+    side = args.side if args.side > 0 else {2: 1000, 3: 3163, 5: 2500}[cfg]       # cfg 5: 6.25M cells per GPU (50M on 8)
     B = max(1, min(args.batch, args.steps))
     runtime_h = 24.0 + (args.warmup + 2 * args.steps + 64) * 0.0625
     check = None
@@ -179,10 +182,14 @@ def run_gpu(args):
     ny = side if (strong or not partitioned) else side * world
     # configs[1] on N GPUs: a valley N times as long (side x side*N cells, side^2 per GPU). Either way the basin is
     # cut into reach partitions along the river and boundary values travel through peer memory inside the batch kernel.
-    basin = build_basin(side, ny, seed=1 if partitioned else 1 + rank, runtime_h=runtime_h, stream_every=args.stream_every)
+    basin = build_basin(side, ny, seed=1 if partitioned else 1 + rank, runtime_h=runtime_h, stream_every=args.stream_every,
+                        **({"gw_depth_mm": 600.0} if cfg == 5 else {}))
     if cfg == 3:
         from tribs_b200.synthbasin import add_met_forcing
         add_met_forcing(basin, hours=int(runtime_h) + 24)     # weather station, land class, Penman-Monteith + Rutter
+    elif cfg == 5:
+        from tribs_b200.synthbasin import add_met_forcing
+        add_met_forcing(basin, hours=int(runtime_h) + 24, i_option=0, winter=True, snow=True)
     if partitioned:
         from tribs_b200.partition import cell_owner
         from tribs_b200.peers import PeerSimulator
@@ -214,12 +221,12 @@ def run_gpu(args):
     gy = np.minimum((4 * (by - by.min()) / max(np.ptp(by), 1e-9)).astype(np.int32), 3)
     dev.set_rain_gauges((gy * 4 + gx).astype(np.int32), n_gauges)
     pinned_rows = torch.empty((B, n_gauges), dtype=torch.float64).pin_memory()
-    gauge_shape = 0.5 + np.arange(n_gauges) / n_gauges if cfg == 3 else np.ones(n_gauges)     # spatially varying (cfg 3)
+    gauge_shape = 0.5 + np.arange(n_gauges) / n_gauges if cfg != 2 else np.ones(n_gauges)     # spatially varying (cfg 3, 5)
     row_of = {"k": 0}
 
     def rain_resident(now):
         r = storm_rain(now)
-        return gpu.GaugeRain(r * gauge_shape) if cfg == 3 else r          # cfg 2: tRainfall::NewRain(double)
+        return gpu.GaugeRain(r * gauge_shape) if cfg != 2 else r          # cfg 2: tRainfall::NewRain(double)
 
     def rain_pinned(now):
         row = pinned_rows[row_of["k"] % B]
@@ -282,7 +289,7 @@ def run_gpu(args):
     n_launch = math.ceil(args.steps / B)
     unsat_ms = phases["unsat"] / max(n_launch, 1)
     steps_per_launch = args.steps / n_launch
-    bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every + (ET_BYTES_PER_CELL / 16.0 if cfg == 3 else 0.0)
+    bytes_per_cell_step = UNSAT_BYTES_PER_CELL + SAT_BYTES_PER_CELL / gw_every + ({3: ET_BYTES_PER_CELL, 5: SNOW_BYTES_PER_CELL}.get(cfg, 0.0) / 16.0)
     bytes_per_launch = n * steps_per_launch * bytes_per_cell_step
 
     say("resident leg timed")
@@ -455,7 +462,8 @@ def _reference_on_bench_basin(side: int, steps: int, cfg: int = 2):
     d = tempfile.mkdtemp(prefix="tribsbench_")
     t0 = time.perf_counter()
     try:
-        write_meshb_deck(side, d, seed=1, runtime_h=24.0, scenario="met" if cfg == 3 else "deep")
+        write_meshb_deck(side, d, seed=1, runtime_h=24.0, scenario={3: "met", 5: "snow"}.get(cfg, "deep"),
+                         **({"extra": {"OPTINTERCEPT": 0}} if cfg == 5 else {}))
         r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--no-basin", "--max-steps", str(steps)], cwd=d,
                            stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=900)
         for ln in r.stdout.splitlines():
@@ -471,12 +479,12 @@ def _reference_on_bench_basin(side: int, steps: int, cfg: int = 2):
 
 def cpu_baseline_sample(side: int = 1000, cfg: int = 2):
     if _harness():
-        got = _reference_on_bench_basin(side, 20 if cfg == 3 else 8, cfg)
+        got = _reference_on_bench_basin(side, 20 if cfg != 2 else 8, cfg)
         if got:
             rate, cells, steps, setup_s, wall = got
             return {"value": rate, "unit": UNIT, "cores": 1, "kind": "reference",
                     "sample": f"unmodified serial reference (g++ -O2) on a basin of the GPU arm's generator ({cells} cells, read as "
-                              f"OPTMESHINPUT 9 files" + (", rain gauges + weather station + ET + Rutter" if cfg == 3 else "") +
+                              f"OPTMESHINPUT 9 files" + ({3: ", rain gauges + weather station + ET + Rutter", 5: ", winter station + snow pack"}.get(cfg, "")) +
                               f"), the first {steps} steps, simulation_loop only; "
                               f"{wall:.0f} s wall incl. writing the deck and {setup_s:.0f} s of reference set-up"}
         rate, cells, steps, wall = _run_reference_sample(120, 12.0, 1)
@@ -515,13 +523,14 @@ def run_reference_arm(args):
             avail_gb = os.sysconf("SC_AVPHYS_PAGES") * os.sysconf("SC_PAGE_SIZE") / 2 ** 30
         except (ValueError, OSError):
             avail_gb = 64.0
-        want = args.side if args.side > 0 else (3163 if args.config == 3 else 1000)
+        want = args.side if args.side > 0 else {2: 1000, 3: 3163, 5: 2500}[args.config]
         side = int(min(want, math.sqrt(150.0 * 0.3e6 / total), math.sqrt(0.5 * avail_gb / procs / 6e-6)))
         side = max(side, 64)
         base = tempfile.mkdtemp(prefix="tribsbench_ref_")
         src = os.path.join(base, "deck")
         os.makedirs(src)
-        write_meshb_deck(side, src, seed=1, runtime_h=24.0, scenario="met" if args.config == 3 else "deep")
+        write_meshb_deck(side, src, seed=1, runtime_h=24.0, scenario={3: "met", 5: "snow"}.get(args.config, "deep"),
+                         **({"extra": {"OPTINTERCEPT": 0}} if args.config == 5 else {}))
         dirs = []
         for k in range(procs):
             d = os.path.join(base, f"p{k}")
@@ -579,9 +588,10 @@ def main():
     ap.add_argument("--steps", type=int, default=256)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="tribs_b200", choices=["tribs_b200", "reference"])
-    ap.add_argument("--config", type=int, default=3, choices=[2, 3],
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 5],
                     help="BASELINE.json configs[1] (1M-cell valley per GPU, uniform storm, ET off; grows with the GPUs) or "
-                         "configs[2] (one 10M-cell valley on all GPUs, gauge rain + weather station + ET + Rutter)")
+                         "configs[2] (one 10M-cell valley on all GPUs, gauge rain + weather station + ET + Rutter) or "
+                         "configs[4] (6.25M cells per GPU, snow pack + shallow water table, weak scaling)")
     ap.add_argument("--side", type=int, default=0, help="cells per side of the synthetic basin (default: 1000 / 3163)")
     ap.add_argument("--batch", type=int, default=256, help="steps per pipelined launch (tribs_gpu_run), at most --steps")
     ap.add_argument("--mgpu", default="partition", choices=["partition", "replicas"],

@@ -359,13 +359,14 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     return basin
 
 
-def add_met_forcing(basin: dict, hours: int = 48, et_option: int = 1, i_option: int = 2) -> dict:
+def add_met_forcing(basin: dict, hours: int = 48, et_option: int = 1, i_option: int = 2, winter: bool = False,
+                    snow: bool = False) -> dict:
     """Adds what kernel (1) needs to a synthetic basin: one land class, per-cell thermal soil
     properties and aspect, one weather station with the hourly series of synth.met_series.
     Keys follow the reference-harness dump so GpuBasin.et_init / met.EvapoTransHost read them."""
     from .synth import BasinSpec, met_series
     n = int(basin["n_active"][0])
-    spec = BasinSpec(runtime_h=float(hours), forcing="met", pmean=12.0, stdur=5.0)
+    spec = BasinSpec(runtime_h=float(hours), forcing="met", pmean=12.0, stdur=5.0, winter=winter)
     _, met = met_series(spec)
     nt = len(met)
     cols = np.array(met)                      # PA RH XC US TA IS
@@ -380,7 +381,9 @@ def add_met_forcing(basin: dict, hours: int = 48, et_option: int = 1, i_option: 
         "land_class": np.ones(n, np.int32), "land_table": land.ravel(),
         "et_option": np.array([et_option], np.int32), "et_Ioption": np.array([i_option], np.int32),
         "et_metdataOption": np.array([1], np.int32), "et_gFluxOption": np.array([2], np.int32),
-        "et_luOption": np.array([0], np.int32), "et_snowOption": np.array([0], np.int32),
+        "et_luOption": np.array([0], np.int32), "et_snowOption": np.array([int(snow)], np.int32),
+        "sn_minSnTemp": np.array([-20.0]), "sn_snliqfrac": np.array([0.06]), "sn_hillAlbedoOption": np.array([0], np.int32),
+        "SnOpt": np.array([int(snow)], np.int32),
         "et_shelterOption": np.array([0], np.int32), "et_timeStep": np.array([60.0]),
         "et_Tlinke": np.array([2.5]), "et_tempLapseRate": np.array([-0.0065]),
         "icp_maxInterStormPeriod": np.array([5000.0]), "icp_option": np.array([i_option], np.int32),
