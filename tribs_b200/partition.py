@@ -46,10 +46,17 @@ def cell_reaches(basin: dict, min_reaches: int = 1) -> np.ndarray:
     reach = np.asarray(basin.get("reach", np.zeros(n, np.int32))).astype(np.int64)
     stream = np.flatnonzero(bnd == 3)
     if np.unique(reach[stream]).size < min_reaches:
+        # Fewer reaches than partitions (a single-river synthetic basin is ONE reach in the reference, which then cannot
+        # be partitioned at all): cut the river, in sweep order, into 4 * min_reaches stretches that drain about the same
+        # number of cells each, so that blocks of stretches are balanced partitions.
         k = max(min_reaches * 4, 1)
-        per = max(1, int(np.ceil(stream.size / k)))
+        slot = np.full(n, -1, np.int64)
+        slot[stream] = np.arange(stream.size)
+        drains_to = np.where(bnd == 3, slot, np.where(sn >= 0, slot[np.maximum(sn, 0)], stream.size - 1))
+        cells_of = np.bincount(drains_to[drains_to >= 0], minlength=stream.size)
+        upto = np.cumsum(cells_of)
         reach = np.zeros(n, np.int64)
-        reach[stream] = np.arange(stream.size) // per
+        reach[stream] = np.minimum((upto - cells_of) * k // max(int(upto[-1]), 1), k - 1)
     else:   # compact the ids in order of first appearance along the sweep (upstream first)
         _, first = np.unique(reach[stream], return_index=True)
         order = reach[stream][np.sort(first)]

@@ -11,6 +11,8 @@ Both give results bit-identical to one GPU running the same partition layout (Si
 Each rank is a model.Simulator on its own handle: same timer arithmetic, same forcing and ET scheduling."""
 from __future__ import annotations
 
+import copy
+
 import numpy as np
 
 from . import gpu
@@ -66,8 +68,9 @@ class LocalPeers:
             if devices is not None:
                 import torch
                 torch.cuda.set_device(devices[r])
-            s = Simulator(basin, rain_schedule, part=dict(rank=r, nranks=world, cell_owner=self.owner,
-                                                          max_batch_steps=max_batch_steps))
+            # a schedule may carry state (met.GaugeRain's position in its series): every rank steps its own copy
+            s = Simulator(basin, copy.deepcopy(rain_schedule), part=dict(rank=r, nranks=world, cell_owner=self.owner,
+                                                                         max_batch_steps=max_batch_steps))
             if cell_gauge is not None:
                 s.dev.set_rain_gauges(cell_gauge)
             self.sims.append(s)
