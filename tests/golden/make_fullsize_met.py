@@ -27,10 +27,15 @@ for p in (ROOT, os.path.join(ROOT, "tests"), HERE):
 
 from make_fullsize import BLOCK, apply_patches, block_sums, make_patches  # noqa: E402,F401
 
-SIDE, SEED, SNAP_STEPS, RUNTIME_H = 3163, 1, (64, 96), 24.0
+SIDE, SEED, RUNTIME_H = 3163, 1, 24.0
+SCENARIO = os.environ.get("TRIBS_FULLSIZE_SCENARIO", "metday")     # tests/refrun.py SCENARIOS: "met" or "metday"
+SNAP_STEPS = (40, 96) if SCENARIO == "metday" else (64, 96)
 STATE = {"NwtOld": "NwtNew", "MuOld": "MuNew", "MiOld": "MiNew", "NtOld": "NtNew", "NfOld": "NfNew", "RuOld": "RuNew",
          "RiOld": "RiNew", "Qpout": "Qpout", "cumsrf": "cumsrf", "intstorm": "intstorm", "NetPrecipitation": "NetPrecipitation",
          "EvapSoil": "EvapSoil", "EvapDryCanopy": "EvapDryCanopy", "Rain": "Rain"}
+# outputs of kernel (1) kept beside the water-balance state (device: the ET field block, tribs_gpu_et_sync)
+ET_STATE = ["PotEvap", "ActEvap", "EvapoTrans", "EvapWetCanopy", "CanStorage", "CumIntercept", "SurfTemp", "NetRad", "LFlux", "HFlux",
+            "GFlux"]
 RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "SatsrfRout"]
 
 
@@ -48,7 +53,7 @@ def reference_run(side, workdir, snap_steps):
     import subprocess
     from refrun import HARNESS, write_meshb_deck
     from tribs_b200.trb import read_trb
-    basin = write_meshb_deck(side, workdir, seed=SEED, runtime_h=RUNTIME_H, scenario="met")
+    basin = write_meshb_deck(side, workdir, seed=SEED, runtime_h=RUNTIME_H, scenario=SCENARIO)
     steps = sorted(snap_steps)
     every = steps[1] - steps[0]
     cmd = [HARNESS, "basin.in", "-K", "--out", workdir, "--snap-from", str(steps[0]), "--snap-to", str(steps[-1]),
@@ -70,7 +75,7 @@ def main(side=SIDE, out=None):
     print(f"reference run: {time.time() - t0:.0f} s  {timing}", flush=True)
     from refrun import SCENARIOS
     z = {"side": np.array([side]), "seed": np.array([SEED]), "snap_steps": np.array(SNAP_STEPS),
-         "gw_depth_mm": np.array([float(SCENARIOS["met"]["gw_depth_mm"])]),       # build_basin argument of the deck
+         "gw_depth_mm": np.array([float(SCENARIOS[SCENARIO]["gw_depth_mm"])]),       # build_basin argument of the deck
          "n_active": np.array([int(basin["n_active"][0])]), "ref_cell_steps_per_s": np.array([timing.get("cell_steps_per_s", 0.0)]),
          "ref_setup_s": np.array([timing.get("setup_s", 0.0)]), "ref_loop_s": np.array([timing.get("loop_s", 0.0)])}
     z.update(make_patches(basin, ref_basin))
@@ -84,11 +89,14 @@ def main(side=SIDE, out=None):
             z[f"extra/{k}"] = np.asarray(a)
     idx = sample_cells(ref_basin)
     z["cells"] = idx
+    z["et_fields"] = np.array(ET_STATE)
     for st in SNAP_STEPS:
         for f, src in STATE.items():
             a = snaps[f"s{st}_r_{src}"]
             z[f"s{st}/{f}"] = a[idx].copy()
             z[f"s{st}/blk/{f}"] = block_sums(a)
+        for f in ET_STATE:
+            z[f"s{st}/{f}"] = snaps[f"s{st}_r_{f}"][idx].copy()
         for r in RESULTS:
             z[f"s{st}/res/{r}"] = np.array(snaps[f"s{st}_r_{r}"]).copy()
     del basin
@@ -100,8 +108,8 @@ def main(side=SIDE, out=None):
             o.sat()
         o.route(); o.balance()
         if st in SNAP_STEPS:
-            got = o.get(list(STATE.values()))
-            for f, src in STATE.items():
+            got = o.get(list(STATE.values()) + ET_STATE)
+            for f, src in list(STATE.items()) + [(f, f) for f in ET_STATE]:
                 same = np.array_equal(got[src], snaps[f"s{st}_r_{src}"])
                 bitexact &= int(same)
                 if not same:

@@ -52,6 +52,8 @@ class BasinSpec:
                                   # one weather station (Penman-Monteith ET, Rutter interception)
     n_gauges: int = 2
     winter: bool = False          # met deck: sub-zero air temperatures and OPTSNOW 1
+    start_hour: int = 0           # met deck: hour of day the run (STARTDATE) and the forcing files begin at
+    rain_hour: int = 3            # met deck: hour of day the daily wet spell begins
     sky_nodata: bool = False      # met deck: write 9999.99 as sky cover (the model then derives it from RH / rain)
     dem_ridge: float = 0.0        # OPTRADSHELT 1-3: height of a wall on the east margin of the DEM (m), to cast shade
     inject_evap: float = 0.0      # test forcing, not a deck keyword: soil evaporation on dry steps (mm/h)
@@ -105,12 +107,13 @@ def met_series(spec: BasinSpec):
     rain = [[0.0] * nh for _ in range(spec.n_gauges)]
     for g in range(spec.n_gauges):
         for h in range(nh):
-            ph = h % 24
-            if 3 <= ph < 3 + int(spec.stdur):
-                rain[g][h] = round(spec.pmean * (0.6 + 0.4 * g) * (0.5 + 0.5 * math.sin(math.pi * (ph - 3 + 0.5) / spec.stdur)), 3)
+            ph = (h + spec.start_hour) % 24
+            if spec.rain_hour <= ph < spec.rain_hour + int(spec.stdur):
+                rain[g][h] = round(spec.pmean * (0.6 + 0.4 * g)
+                                   * (0.5 + 0.5 * math.sin(math.pi * (ph - spec.rain_hour + 0.5) / spec.stdur)), 3)
     met = []
     for h in range(nh):
-        ph = h % 24
+        ph = (h + spec.start_hour) % 24
         day = math.sin(math.pi * (ph - 6) / 12.0) if 6 <= ph <= 18 else 0.0
         wet = any(rain[g][h] > 0 for g in range(spec.n_gauges))
         ta = round((-4.0 if spec.winter else 16.0) + (7.0 if spec.winter else 9.0) * math.sin(2 * math.pi * (ph - 9) / 24.0)
@@ -131,6 +134,7 @@ def write_met_forcing(spec: BasinSpec, outdir: str) -> dict:
     ext = (spec.n - 1) * spec.spacing
 
     def stamp(h):
+        h += spec.start_hour
         return f"2000 6 {1 + h // 24} {h % 24}"
 
     with open(os.path.join(outdir, "gauges.sdf"), "w") as f:
@@ -178,7 +182,7 @@ def write_basin(spec: BasinSpec, outdir: str) -> str:
     with open(os.path.join(outdir, "nodes.pix"), "w") as f:
         f.write("0\n")
     kv = [
-        ("STARTDATE", "06/01/2000/00/00"), ("RUNTIME", spec.runtime_h),
+        ("STARTDATE", f"06/01/2000/{spec.start_hour:02d}/00"), ("RUNTIME", spec.runtime_h),
         ("TIMESTEP", spec.timestep_min), ("GWSTEP", spec.gwstep_min),
         ("METSTEP", spec.metstep_min), ("RAININTRVL", 1), ("OPINTRVL", 1),
         ("SPOPINTRVL", 100000), ("INTSTORMMAX", spec.intstormmax), ("RAINSEARCH", 24),
