@@ -398,3 +398,73 @@ def stochastic_storm_schedule(pmean: float, stdur: float, istdur: float):
         return state["rate"]
 
     return rain
+
+
+# ------------------------------------------------------------------ channel router (tribs_oracle_channel.c)
+class _Channel(C.Structure):
+    _fields_ = [("n_cells", C.c_int), ("n_reach", C.c_int), ("off", PI), ("node", PI), ("width", PD), ("length", PD),
+                ("slope", PD), ("roughness", C.c_double), ("uniform_width", C.c_double)]
+
+
+class _ChannelState(C.Structure):
+    _fields_ = [("hlevel", PD), ("qstrm", PD), ("velocity", PD), ("outlet_hlev", PD)]
+
+
+def channel_network(basin: dict) -> dict:
+    """tKinemat's reach lists as flat arrays: per reach the chain of cell indices from its head along the flow edges to its
+    outlet (index n_cells = the basin outlet node, which is not an active cell), with each entry's channel width and
+    the length / slope of its flow edge. Keys of the reference-harness dump (reach_head, reach_nnodes, flow_dest,
+    chan_width ...)."""
+    n = int(basin["n_active"][0])
+    dest = np.asarray(basin["flow_dest"])
+    heads, nn = np.asarray(basin["reach_head"]), np.asarray(basin["reach_nnodes"])
+    off, node = [0], []
+    for h, k in zip(heads, nn):
+        c = int(h)
+        for _ in range(int(k)):
+            node.append(c if 0 <= c < n else n)
+            c = int(dest[c]) if 0 <= c < n else n
+        off.append(len(node))
+    node = np.array(node, np.int32)
+    inside = node < n
+    safe = np.where(inside, node, 0)
+    width = np.where(inside, np.asarray(basin["chan_width"], float)[safe], float(basin["outlet_chan_width"][0]))
+    return {"n_cells": n, "off": np.array(off, np.int32), "node": node, "width": np.ascontiguousarray(width),
+            "length": np.ascontiguousarray(np.where(inside, np.asarray(basin["flow_len"], float)[safe], 0.0)),
+            "slope": np.ascontiguousarray(np.where(inside, np.asarray(basin["flow_slope"], float)[safe], 0.0)),
+            "roughness": float(basin["chan_roughness"][0]), "uniform_width": float(basin["chan_width_uniform"][0])}
+
+
+class OracleChannel:
+    """One tKinemat::RunRoutingModel call per step (without its hillslope half, which OracleModel.route is)."""
+
+    def __init__(self, basin: dict):
+        self.L = lib()
+        self.L.orc_channel_step.argtypes = [C.POINTER(_Channel), C.POINTER(_ChannelState), PD, C.c_double, PD,
+                                            C.POINTER(C.c_int)]
+        self.L.orc_channel_step.restype = C.c_int
+        assert int(basin["chan_percolation"][0]) == 0 and int(basin["chan_optres"][0]) == 0
+        self.net = net = channel_network(basin)
+        n = net["n_cells"]
+        self.n_reach = len(net["off"]) - 1
+        self.hlevel, self.qstrm, self.velocity = np.zeros(n + 1), np.zeros(n + 1), np.zeros(n + 1)
+        self.outlet_hlev = np.zeros(self.n_reach)
+        for nm, key in (("hlevel", "init_Hlevel"), ("qstrm", "init_Qstrm"), ("velocity", "init_FlowVelocity")):
+            if key in basin:
+                getattr(self, nm)[:n] = np.asarray(basin[key], float)[:n]
+        self.C = _Channel(n, self.n_reach, _pi(net["off"]), _pi(net["node"]), _pd(net["width"]), _pd(net["length"]),
+                          _pd(net["slope"]), net["roughness"], net["uniform_width"])
+        self.S = _ChannelState(_pd(self.hlevel), _pd(self.qstrm), _pd(self.velocity), _pd(self.outlet_hlev))
+        self.dt = float(basin["tstep"][0]) * 3600.0
+        self.iters = 0
+
+    def step(self, qeff) -> float:
+        """qeff: what RetrieveQeff returned for this step, per cell index (+ the basin outlet slot)."""
+        qeff = np.ascontiguousarray(qeff, float)
+        assert qeff.size == self.net["n_cells"] + 1
+        qout, it = C.c_double(0.0), C.c_int(0)
+        rc = self.L.orc_channel_step(C.byref(self.C), C.byref(self.S), _pd(qeff), self.dt, C.byref(qout), C.byref(it))
+        if rc:
+            raise RuntimeError(f"orc_channel_step: reach solver failed ({rc})")
+        self.iters += it.value
+        return qout.value

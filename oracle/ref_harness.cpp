@@ -266,6 +266,13 @@ struct Harness {
             w.i32("reach_outlet", outs);
             w.i32("reach_nnodes", nn);
         }
+        // channel geometry and options of the kinematic-wave router (tKinemat.cpp:1136-1252 reads them per step)
+        w.f64("chan_width", col([](tCNode *c) { return c->getChannelWidth(); }));
+        w.f64s("outlet_chan_width", flow->OutletNode->getChannelWidth());
+        w.f64s("chan_roughness", flow->Roughness);
+        w.f64s("chan_width_uniform", flow->Width);
+        w.i32s("chan_percolation", flow->percolationOption);
+        w.i32s("chan_optres", flow->optres);
         // the reference's own reach partition for 2..8 partitions: tGraph::connectivity (tGraph.cpp:297-343) counts
         // the reaches of tKinemat's lists, tGraph::createDefaultPartition (588-608) assigns them; every cell then
         // belongs to reach2partition[tCNode::getReach()]. Pins tribs_b200/partition.py (tests/test_partition.py).
@@ -544,6 +551,12 @@ struct Harness {
     }
 
     void dump_routing(TrbWriter &w, const string &pre) {
+        {   // channel router state that is not a per-cell field: tKinemat::OutletHlev and the basin outlet node
+            vector<double> oh(flow->OutletHlev, flow->OutletHlev + flow->NodesLstO.getSize());
+            w.f64(pre + "OutletHlev", oh);
+            w.f64s(pre + "outlet_Hlevel", flow->OutletNode->getHlevel());
+            w.f64s(pre + "outlet_Qstrm", flow->OutletNode->getQstrm());
+        }
         // (TimeInd, Qeff) stacks of the stream cells (reference: tKinemat.cpp:1023-1067)
         vector<int32_t> off(1, 0), node, tind;
         vector<double> q;

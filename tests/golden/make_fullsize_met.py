@@ -57,7 +57,7 @@ def reference_run(side, workdir, snap_steps):
     steps = sorted(snap_steps)
     every = steps[1] - steps[0]
     cmd = [HARNESS, "basin.in", "-K", "--out", workdir, "--snap-from", str(steps[0]), "--snap-to", str(steps[-1]),
-           "--snap-every", str(every), "--phases", "r", "--max-steps", str(steps[-1])]
+           "--snap-every", str(every), "--phases", "rm", "--max-steps", str(steps[-1])]
     r = subprocess.run(cmd, cwd=workdir, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("reference harness failed:\n" + r.stdout[-2000:] + r.stderr[-2000:])
@@ -96,7 +96,7 @@ def main(side=SIDE, out=None):
             z[f"s{st}/{f}"] = a[idx].copy()
             z[f"s{st}/blk/{f}"] = block_sums(a)
         for f in ET_STATE:
-            z[f"s{st}/{f}"] = snaps[f"s{st}_r_{f}"][idx].copy()
+            z[f"s{st}/{f}"] = snaps[f"s{st}_m_{f}"][idx].copy()       # kernel (1) runs first in a step; nothing later writes these
         for r in RESULTS:
             z[f"s{st}/res/{r}"] = np.array(snaps[f"s{st}_r_{r}"]).copy()
     del basin
@@ -110,10 +110,11 @@ def main(side=SIDE, out=None):
         if st in SNAP_STEPS:
             got = o.get(list(STATE.values()) + ET_STATE)
             for f, src in list(STATE.items()) + [(f, f) for f in ET_STATE]:
-                same = np.array_equal(got[src], snaps[f"s{st}_r_{src}"])
+                ref_a = snaps[f"s{st}_r_{src}" if f in STATE else f"s{st}_m_{src}"]
+                same = np.array_equal(got[src], ref_a)
                 bitexact &= int(same)
                 if not same:
-                    e = np.abs(got[src] - snaps[f"s{st}_r_{src}"])
+                    e = np.abs(got[src] - ref_a)
                     print(f"  step {st} {src}: oracle differs from the reference in {int((e > 0).sum())} cells, max {e.max():.3e}")
             for r in RESULTS:
                 bitexact &= int(np.array_equal(np.asarray(o.result(r)), snaps[f"s{st}_r_{r}"]))
