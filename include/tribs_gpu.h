@@ -254,6 +254,38 @@ int tribs_gpu_save_state(tribs_handle_t h, const char *path);
 int tribs_gpu_load_state(tribs_handle_t h, const char *path);
 int tribs_gpu_reserve_batch(tribs_handle_t h, int n_steps);
 
+/* ---- channel routing: the kinematic-wave half of tKinemat::RunRoutingModel
+ * (src/tFlowNet/tKinemat.cpp:803-897: InitializeStreamReach 1136, AssignLateralInflux 1296, AssignQin 1561,
+ * KinematWave 1788 / SolveForTwoNodeReach 1736, ComputeQout 1582, UpdateStreamVars 1617) on the device, fed by the
+ * lateral inflows the hillslope routing of the same handle produced (what RetrieveQeff 1504 hands the router).
+ * The network is tKinemat's own lists: reaches in the order of NodesLstH / NodesLstO / NNodes, each the chain of cells
+ * from its head to its outlet (cell index n_cells = the basin outlet node); per entry the node's tCNode::getChannelWidth(),
+ * and getFlowEdg()->getLength() / getSlope() of its flow edge (ignored for the last entry of a reach).
+ * OPTPERCOLATION and OPTRESERVOIR other than 0 are refused. On a partitioned handle every rank routes the whole
+ * network from the combined inflows (a few thousand nodes), so all ranks hold the same channel state. */
+typedef struct {
+  int32_t n_reach;
+  int32_t percolation_option;   /* OPTPERCOLATION, must be 0 */
+  int32_t reservoir_option;     /* OPTRESERVOIR, must be 0 */
+  int32_t pad_;
+  const int32_t *reach_off;     /* [n_reach + 1] */
+  const int32_t *reach_node;    /* [reach_off[n_reach]] */
+  const double *width, *length, *slope;   /* per entry of reach_node */
+  double roughness;             /* CHANNELROUGHNESS (tKinemat::Roughness) */
+  double uniform_width;         /* tKinemat::Width: > 0 overrides the per-node widths */
+  double dt_s;                  /* tRunTimer::getTimeStep() * 3600 */
+  const double *hlevel0, *qstrm0;   /* [n_cells + 1] tCNode::getHlevel / getQstrm at the start, or NULL for zeros */
+  const double *outlet_hlev0;       /* [n_reach] tKinemat::OutletHlev, or NULL */
+} tribs_channel_t;
+int tribs_gpu_channel_init(tribs_handle_t h, const tribs_channel_t *net);
+/* n_steps >= 1: the steps of the last tribs_gpu_run / _run_et / _run_snow batch; n_steps == 0: the single step whose
+ * TRIBS_PHASE_ROUTE ran last. qout[k] = tKinemat::Qout after step k (the value SurfaceFlow 740-757 writes to <base>_Outlet.qout). */
+int tribs_gpu_channel_route(tribs_handle_t h, int32_t n_steps, double *qout);
+/* Hlevel / Qstrm / FlowVelocity per stream slot (tribs_gpu_stream_cells order) + the basin outlet, OutletHlev per reach,
+ * counters[3] = Newton iterations, line-search backtracks, reaches that exceeded MAXITS since init. Pointers may be NULL. */
+int tribs_gpu_channel_sync(tribs_handle_t h, double *hlevel, double *qstrm, double *velocity, double *outlet_hlev,
+                           int64_t *counters);
+
 /* Introspection used by tests and the bench. */
 int tribs_gpu_sweep_levels(tribs_handle_t h);            /* depth of the Qpin dependency DAG */
 int tribs_gpu_device_index(tribs_handle_t h, int32_t *dev_index_of_sweep /* [n_cells] */);

@@ -410,29 +410,7 @@ class _ChannelState(C.Structure):
     _fields_ = [("hlevel", PD), ("qstrm", PD), ("velocity", PD), ("outlet_hlev", PD)]
 
 
-def channel_network(basin: dict) -> dict:
-    """tKinemat's reach lists as flat arrays: per reach the chain of cell indices from its head along the flow edges to its
-    outlet (index n_cells = the basin outlet node, which is not an active cell), with each entry's channel width and
-    the length / slope of its flow edge. Keys of the reference-harness dump (reach_head, reach_nnodes, flow_dest,
-    chan_width ...)."""
-    n = int(basin["n_active"][0])
-    dest = np.asarray(basin["flow_dest"])
-    heads, nn = np.asarray(basin["reach_head"]), np.asarray(basin["reach_nnodes"])
-    off, node = [0], []
-    for h, k in zip(heads, nn):
-        c = int(h)
-        for _ in range(int(k)):
-            node.append(c if 0 <= c < n else n)
-            c = int(dest[c]) if 0 <= c < n else n
-        off.append(len(node))
-    node = np.array(node, np.int32)
-    inside = node < n
-    safe = np.where(inside, node, 0)
-    width = np.where(inside, np.asarray(basin["chan_width"], float)[safe], float(basin["outlet_chan_width"][0]))
-    return {"n_cells": n, "off": np.array(off, np.int32), "node": node, "width": np.ascontiguousarray(width),
-            "length": np.ascontiguousarray(np.where(inside, np.asarray(basin["flow_len"], float)[safe], 0.0)),
-            "slope": np.ascontiguousarray(np.where(inside, np.asarray(basin["flow_slope"], float)[safe], 0.0)),
-            "roughness": float(basin["chan_roughness"][0]), "uniform_width": float(basin["chan_width_uniform"][0])}
+from tribs_b200.channel import channel_network  # noqa: E402  (host-side flattening of tKinemat's reach lists)
 
 
 class OracleChannel:

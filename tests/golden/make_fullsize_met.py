@@ -73,9 +73,9 @@ def main(side=SIDE, out=None):
     work = tempfile.mkdtemp(prefix="tribs_fullsize_met_")
     basin, ref_basin, snaps, timing = reference_run(side, work, SNAP_STEPS)
     print(f"reference run: {time.time() - t0:.0f} s  {timing}", flush=True)
-    from refrun import SCENARIOS
+    from refrun import EXTRA_SCENARIOS, SCENARIOS
     z = {"side": np.array([side]), "seed": np.array([SEED]), "snap_steps": np.array(SNAP_STEPS),
-         "gw_depth_mm": np.array([float(SCENARIOS[SCENARIO]["gw_depth_mm"])]),       # build_basin argument of the deck
+         "gw_depth_mm": np.array([float({**SCENARIOS, **EXTRA_SCENARIOS}[SCENARIO]["gw_depth_mm"])]),       # build_basin argument of the deck
          "n_active": np.array([int(basin["n_active"][0])]), "ref_cell_steps_per_s": np.array([timing.get("cell_steps_per_s", 0.0)]),
          "ref_setup_s": np.array([timing.get("setup_s", 0.0)]), "ref_loop_s": np.array([timing.get("loop_s", 0.0)])}
     z.update(make_patches(basin, ref_basin))

@@ -36,10 +36,15 @@ SCENARIOS = {
     "met": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0),
     # the same with sub-zero temperatures and OPTSNOW 1: snow pack energy balance, canopy snow
     # interception, melt routed to the unsaturated zone (oracle only so far: no device kernel yet)
-    # the same beginning at 09:00 with the wet spell at noon: daytime ET on dry ground, then evaporation from a wet canopy
-    "metday": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0, start_hour=9, rain_hour=12),
     "snow": dict(runtime_h=72.0, forcing="met", winter=True, gw_depth_mm=1500.0, pmean=6.0, stdur=5.0),
     "evap": dict(runtime_h=72.0, gw_depth_mm=350.0, pmean=25.0, stdur=4.0, istdur=20.0, inject_evap=0.6),
+}
+
+
+# decks without a small golden fixture of their own (tests/golden/make_fullsize_met.py): "met" beginning at 09:00 with the
+# wet spell at noon - daytime ET on dry ground, then evaporation from a wet canopy
+EXTRA_SCENARIOS = {
+    "metday": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0, start_hour=9, rain_hour=12),
 }
 
 
@@ -48,7 +53,7 @@ def have_harness() -> bool:
 
 
 def spec_for(name: str, n: int, **over) -> BasinSpec:
-    kw = dict(SCENARIOS[name])
+    kw = dict(SCENARIOS[name] if name in SCENARIOS else EXTRA_SCENARIOS[name])
     kw.update(over)
     return BasinSpec(n=n, **kw)
 

@@ -1,0 +1,113 @@
+"""Device channel router (tribs_gpu_channel_route) against the unmodified reference:
+tests/golden/channel_*.npz hold what tKinemat::RunRoutingModel left after EVERY step (outlet discharge, level / discharge /
+velocity of every stream node, OutletHlev per reach). The hillslope inflows come from the device's own routing, so the
+comparison covers the whole chain rain -> soil column -> hillslope routing -> channels.
+
+Bar: 1e-6 relative (north_star); levels and discharges that are still at zero compare with an absolute floor."""
+import numpy as np
+import pytest
+
+from common import GpuStepper
+from refrun import schedule_for
+from test_channel import channel_golden
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-6
+FLOOR = {"qout": 1e-6, "Hlevel": 1e-6, "Qstrm": 1e-6, "FlowVelocity": 1e-6, "OutletHlev": 1e-6}
+
+
+def worst_of(ref, got, floor):
+    ref, got = np.ravel(np.asarray(ref, float)), np.ravel(np.asarray(got, float))
+    return float((np.abs(ref - got) / np.maximum(np.abs(ref), floor)).max())
+
+
+def compare_state(dev, ref, s, slot_of_stream, worst):
+    got = dev.channel_sync()
+    for f in ("Hlevel", "Qstrm", "FlowVelocity"):
+        worst[f] = max(worst.get(f, 0.0), worst_of(ref[f][s], got[f][slot_of_stream], FLOOR[f]))
+    worst["OutletHlev"] = max(worst.get("OutletHlev", 0.0), worst_of(ref["OutletHlev"][s], got["OutletHlev"], FLOOR["OutletHlev"]))
+    worst["outlet"] = max(worst.get("outlet", 0.0), worst_of([ref["outlet_Hlevel"][s], ref["outlet_Qstrm"][s]],
+                                                             [got["Hlevel"][-1], got["Qstrm"][-1]], 1e-6))
+    return got
+
+
+def slots_of(dev, ref):
+    """fixture order of the stream cells (ascending cell index) -> the device's stream slots"""
+    pos = {int(c): k for k, c in enumerate(dev.stream_cells())}
+    return np.array([pos[int(c)] for c in ref["stream_cells"]])
+
+
+@pytest.mark.parametrize("name", ["channel_single", "channel_dendritic"])
+def test_channel_router_single_steps_match_reference(built, name):
+    basin, ref = channel_golden(name)
+    g = GpuStepper(basin, schedule_for(basin))
+    g.sim.flow.route_channels(basin)
+    sl = slots_of(g.sim.dev, ref)
+    worst = {}
+    for s in range(int(ref["n_steps"][0])):
+        g.advance(); g.unsat()
+        if g.gw_due():
+            g.sat()
+        g.route()
+        worst["qout"] = max(worst.get("qout", 0.0), worst_of(ref["qout"][s], g.sim.flow.Qout, FLOOR["qout"]))
+        if s % 7 == 0 or s == int(ref["n_steps"][0]) - 1:
+            got = compare_state(g.sim.dev, ref, s, sl, worst)
+        g.reset()
+    print(f"\n[{name}] worst relative differences: {worst}; Newton iterations {got['newton_iterations']}, "
+          f"backtracks {got['backtracks']}")
+    assert max(worst.values()) <= REL_TOL, worst
+    assert got["newton_iterations"] > 0 and got["maxits_exceeded"] == 0
+    g.sim.dev.close()
+
+
+@pytest.mark.parametrize("name,ranks", [("channel_single", 1), ("channel_dendritic", 1), ("channel_dendritic", 2)])
+def test_channel_router_after_batches_matches_reference(built, name, ranks):
+    """One launch routes all steps of a batch from the per-step inflows the batch left on the device; with two reach
+    partitions every rank routes the whole net from the combined inflows."""
+    from tribs_b200.model import Simulator
+    from tribs_b200.peers import LocalPeers
+    basin, ref = channel_golden(name)
+    n_steps, batch = int(ref["n_steps"][0]), 40
+    if ranks == 1:
+        sims = [Simulator(basin, rain_schedule=schedule_for(basin))]
+        run = lambda k: sims[0].run_batch(k)
+    else:
+        lp = LocalPeers(basin, ranks, rain_schedule=schedule_for(basin), max_batch_steps=batch)
+        sims = lp.sims
+        run = lp.run_batch
+    for sim in sims:
+        sim.flow.route_channels(basin)
+    sl = slots_of(sims[0].dev, ref)
+    worst, done = {}, 0
+    while done < n_steps:
+        k = min(batch, n_steps - done)
+        run(k)
+        done += k
+        for sim in sims:
+            compare_state(sim.dev, ref, done - 1, sl, worst)
+    for sim in sims:
+        q = np.array(sim.flow.qout_series)
+        assert q.size == n_steps
+        worst["qout"] = max(worst.get("qout", 0.0), worst_of(ref["qout"], q, FLOOR["qout"]))
+    if ranks > 1:
+        assert np.array_equal(np.array(sims[0].flow.qout_series), np.array(sims[1].flow.qout_series))
+    print(f"\n[{name}, {ranks} rank(s)] worst relative differences: {worst}")
+    assert max(worst.values()) <= REL_TOL, worst
+    (lp.close() if ranks > 1 else sims[0].dev.close())
+
+
+def test_channel_init_refuses_what_is_not_built(built):
+    from tribs_b200.channel import channel_network
+    from tribs_b200.model import Simulator
+    basin, _ = channel_golden("channel_single")
+    sim = Simulator(basin, rain_schedule=schedule_for(basin))
+    with pytest.raises(RuntimeError, match="OPTPERCOLATION"):
+        sim.dev.channel_init(channel_network(basin), 225.0, percolation_option=1)
+    with pytest.raises(RuntimeError, match="channel_init has not been called"):
+        sim.dev.channel_route(0)
+    net = channel_network(basin)
+    net["node"] = net["node"].copy(); net["node"][1] = 0          # a hillslope cell inside a reach
+    with pytest.raises(RuntimeError, match="not a stream cell"):
+        sim.dev.channel_init(net, 225.0)
+    sim.dev.close()

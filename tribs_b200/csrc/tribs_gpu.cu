@@ -33,6 +33,7 @@
 #include <chrono>
 #include <numeric>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "cell_update.cuh"
@@ -80,6 +81,7 @@ struct SegPart {
   int n_seg = 0, blocks = 0, blocks2 = 0;
 };
 struct PipeState;
+struct ChannelState;
 struct tribs_ctx {
   int device = 0;
   // partitions (tribs_part_t): cells are laid out partition by partition; sums are formed per partition
@@ -100,6 +102,7 @@ struct tribs_ctx {
   double *d_gauge_vals = nullptr;
   int n_gauges = 0;
   PipeState *pipe = nullptr;   // pipelined-batch state (tribs_gpu_run), created on first use
+  ChannelState *chan = nullptr;   // channel network and state (tribs_gpu_channel_init)
   struct StateSnapshot *snap = nullptr;   // tribs_gpu_snapshot
   struct EtState *et = nullptr; // kernel (1) state (tribs_gpu_et_init)
   int n = 0, n_pad = 0, n_edges = 0, n_levels = 0, n_tiles = 0, n_stream = 0, n_late = 0;
@@ -2287,6 +2290,7 @@ extern "C" int tribs_gpu_wait(tribs_handle_t c) {
 extern "C" void *tribs_gpu_stream(tribs_handle_t c) { return c ? (void *)c->stream : nullptr; }
 static void tribs_free_pipe(tribs_ctx *c);
 static void tribs_free_snapshot(tribs_ctx *c);
+static void tribs_free_channel(tribs_ctx *c);
 extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   if (!c) return 0;
   cudaSetDevice(c->device);
@@ -2298,9 +2302,11 @@ extern "C" int tribs_gpu_destroy(tribs_handle_t c) {
   tribs_free_pipe(c);
   tribs_free_et(c);
   tribs_free_snapshot(c);
+  tribs_free_channel(c);
   delete c;
   return 0;
 }
 
 #include "pipeline.cuh"
 #include "checkpoint.cuh"
+#include "channel.cuh"

@@ -100,6 +100,13 @@ class Part(C.Structure):
                 ("cell_owner", PI)]
 
 
+class Channel(C.Structure):
+    _fields_ = [("n_reach", C.c_int32), ("percolation_option", C.c_int32), ("reservoir_option", C.c_int32), ("pad_", C.c_int32),
+                ("reach_off", PI), ("reach_node", PI), ("width", PD), ("length", PD), ("slope", PD),
+                ("roughness", C.c_double), ("uniform_width", C.c_double), ("dt_s", C.c_double),
+                ("hlevel0", PD), ("qstrm0", PD), ("outlet_hlev0", PD)]
+
+
 class Step(C.Structure):
     _fields_ = [("current_time", C.c_double), ("dt", C.c_double), ("dt_gw", C.c_double),
                 ("elapsed_steps", C.c_int32), ("hourly_reset", C.c_int32), ("rain_mode", C.c_int32),
@@ -147,6 +154,7 @@ EXPORTS = ["tribs_gpu_init", "tribs_gpu_step", "tribs_gpu_run", "tribs_gpu_run_e
            "tribs_gpu_padded_cells", "tribs_gpu_et_init", "tribs_gpu_et_step", "tribs_gpu_et_sync", "tribs_gpu_et_push",
            "tribs_gpu_snow_init", "tribs_gpu_snow_step", "tribs_gpu_snow_sync", "tribs_gpu_snow_members",
            "tribs_gpu_snow_push", "tribs_gpu_snow_set_members",
+           "tribs_gpu_channel_init", "tribs_gpu_channel_route", "tribs_gpu_channel_sync",
            "tribs_gpu_last_error", "tribs_gpu_abi_version"]
 
 _lib = None
@@ -210,6 +218,9 @@ def load():
     L.tribs_gpu_save_state.argtypes = [H, C.c_char_p]
     L.tribs_gpu_load_state.argtypes = [H, C.c_char_p]
     L.tribs_gpu_reserve_batch.argtypes = [H, C.c_int]
+    L.tribs_gpu_channel_init.argtypes = [H, C.POINTER(Channel)]
+    L.tribs_gpu_channel_route.argtypes = [H, C.c_int32, PD]
+    L.tribs_gpu_channel_sync.argtypes = [H, PD, PD, PD, PD, C.POINTER(C.c_int64)]
     L.tribs_gpu_last_error.restype = C.c_char_p
     _lib = L
     return L
@@ -417,6 +428,42 @@ class GpuBasin:
 
     def reserve_batch(self, n_steps: int):
         _chk(self.L.tribs_gpu_reserve_batch(self.h, int(n_steps)))
+
+    # ---- channel routing (tKinemat::RunRoutingModel's kinematic-wave half, tKinemat.cpp:803-897)
+    def channel_init(self, net: dict, dt_s: float, hlevel0=None, qstrm0=None, outlet_hlev0=None,
+                     percolation_option: int = 0, reservoir_option: int = 0):
+        """net: tKinemat's reach lists as flat arrays (tribs_b200.channel.channel_network)."""
+        keep = {k: np.ascontiguousarray(net[k], np.int32) for k in ("off", "node")}
+        keep.update({k: np.ascontiguousarray(net[k], float) for k in ("width", "length", "slope")})
+        opt = {nm: (None if a is None else np.ascontiguousarray(a, float))
+               for nm, a in (("hlevel0", hlevel0), ("qstrm0", qstrm0), ("outlet_hlev0", outlet_hlev0))}
+        for nm in ("hlevel0", "qstrm0"):
+            if opt[nm] is not None and opt[nm].size != self.n + 1:
+                raise ValueError(f"{nm} must hold n_cells + 1 values (the last one the basin outlet)")
+        ch = Channel(len(keep["off"]) - 1, int(percolation_option), int(reservoir_option), 0, _i(keep["off"]), _i(keep["node"]),
+                     _d(keep["width"]), _d(keep["length"]), _d(keep["slope"]), float(net["roughness"]),
+                     float(net["uniform_width"]), float(dt_s),
+                     *[(_d(opt[nm]) if opt[nm] is not None else None) for nm in ("hlevel0", "qstrm0", "outlet_hlev0")])
+        _chk(self.L.tribs_gpu_channel_init(self.h, C.byref(ch)))
+        self.n_reach = len(keep["off"]) - 1
+
+    def channel_route(self, n_steps: int) -> np.ndarray:
+        """Outlet discharge (tKinemat::Qout) after each step of the last batch (n_steps >= 1) or of the last single
+        step (n_steps == 0)."""
+        out = np.empty(max(int(n_steps), 1))
+        _chk(self.L.tribs_gpu_channel_route(self.h, int(n_steps), _d(out)))
+        return out
+
+    def channel_sync(self) -> dict:
+        """Hlevel / Qstrm / FlowVelocity per stream slot (+ the basin outlet), OutletHlev per reach, solver counters."""
+        slots = self.n_stream + 1
+        out = {"Hlevel": np.empty(slots), "Qstrm": np.empty(slots), "FlowVelocity": np.empty(slots),
+               "OutletHlev": np.empty(self.n_reach)}
+        cnt = (C.c_int64 * 3)()
+        _chk(self.L.tribs_gpu_channel_sync(self.h, _d(out["Hlevel"]), _d(out["Qstrm"]), _d(out["FlowVelocity"]),
+                                           _d(out["OutletHlev"]), cnt))
+        out["newton_iterations"], out["backtracks"], out["maxits_exceeded"] = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        return out
 
     def owned_range(self):
         a, b = C.c_int32(0), C.c_int32(0)

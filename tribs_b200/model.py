@@ -158,18 +158,55 @@ class tEvapoTrans:
 
 
 class tKinemat:
-    """SurfaceFlow(): hillslope routing + basin accumulations on the GPU; the kinematic-wave
-    channel solver stays with the host model and consumes `lateral_inflow`."""
+    """SurfaceFlow(): hillslope routing + basin accumulations on the GPU. The kinematic-wave channel solver either
+    stays with the host model and consumes `lateral_inflow`, or - after route_channels() - runs on the device too
+    (tribs_gpu_channel_route) and leaves the outlet discharge of every step in `Qout` / `qout_series`."""
 
     def __init__(self, dev: gpu.GpuBasin, timer: tRunTimer):
         self.dev, self.timer = dev, timer
         self.lateral_inflow = None
+        self.on_device = False
+        self.defer = False           # True: the caller routes the channels itself once every in-process rank has launched
+        self.pending_steps: list[int] = []
+        self.Qout = 0.0
+        self.qout_series: list[float] = []
+
+    def route_channels(self, basin: dict):
+        """Hands tKinemat's reach lists, channel geometry and initial levels to the device (tKinemat.cpp:826-830,
+        1136-1252). From here on SurfaceFlow() / Simulator.run_batch() route the channels as well."""
+        from .channel import channel_network
+        n = int(basin["n_active"][0])
+
+        def init(key):
+            if key not in basin:
+                return None
+            a = np.zeros(n + 1)
+            a[:n] = np.asarray(basin[key], float)[:n]
+            return a
+        self.dev.channel_init(channel_network(basin), self.timer.getTimeStep() * 3600.0, init("init_Hlevel"), init("init_Qstrm"),
+                              percolation_option=int(basin["chan_percolation"][0]) if "chan_percolation" in basin else 0,
+                              reservoir_option=int(basin["chan_optres"][0]) if "chan_optres" in basin else 0)
+        self.on_device = True
+
+    def channels_after_batch(self, n_steps: int, deferred: bool = False):
+        """tribs_gpu_channel_route waits for the batch; ranks that live in one process (peers.LocalPeers) must all have
+        launched theirs before any of them waits, so there the call is deferred to the end of LocalPeers.run_batch."""
+        if self.on_device and n_steps:
+            if self.defer and not deferred:
+                self.pending_steps.append(n_steps)
+                return
+            q = self.dev.channel_route(n_steps)
+            self.qout_series.extend(q.tolist())
+            self.Qout = float(q[-1])
 
     def SurfaceFlow(self, fetch_qeff: bool = True):
         now = self.timer.getCurrentTime()
         self.dev.step(gpu.PHASE_ROUTE, now, self.timer.getElapsedSteps(now), 0)
         if fetch_qeff:
             self.lateral_inflow = self.dev.retrieve_qeff(now)
+        if self.on_device:
+            self.Qout = float(self.dev.channel_route(0)[0])
+            self.qout_series.append(self.Qout)
 
 
 class tCOutput:
@@ -292,8 +329,9 @@ class Simulator:
         def flush():
             if steps:
                 self.dev.run(steps)
-                if collect_qeff:      # per-step lateral inflows for the channel router
+                if collect_qeff:      # per-step lateral inflows for a channel router on the host
                     qeff.append(self.dev.retrieve_qeff_steps(len(steps)))
+                self.flow.channels_after_batch(len(steps))
                 out.extend(steps)
                 steps.clear()
 

@@ -73,6 +73,7 @@ class LocalPeers:
                                                                          max_batch_steps=max_batch_steps))
             if cell_gauge is not None:
                 s.dev.set_rain_gauges(cell_gauge)
+            s.flow.defer = True       # channel routing waits until every rank of this process has launched its batch
             self.sims.append(s)
         self.devs = [s.dev for s in self.sims]
         gpu.GpuBasin.attach_local(self.devs)
@@ -82,6 +83,12 @@ class LocalPeers:
             s.run_batch(k, rain_of_time=rain_of_time)
         for d in self.devs:
             d.wait()
+        for s in self.sims:      # channel routing (if on): every rank routes the whole net from the combined inflows
+            pending, s.flow.pending_steps = s.flow.pending_steps, []
+            if len(pending) > 1:
+                raise RuntimeError("LocalPeers: a batch that was cut into several launches cannot route its channels afterwards")
+            for k in pending:
+                s.flow.channels_after_batch(k, deferred=True)
 
     def gather(self, names):
         out = {nm: np.zeros(self.devs[0].n) for nm in names}
