@@ -386,16 +386,10 @@ def stochastic_storm_schedule(pmean: float, stdur: float, istdur: float):
     (tSimul.cpp:398-399) and, because tStorm::GenerateStorm leaves `p` untouched in mode 1
     (tStorm.cpp:228-242), every later "storm" rains 0 — the reference's actual behaviour.
     (reference: src/tSimulator/tSimul.cpp:386-406, tRunTimer::UpdateStorm tRunTimer.cpp:559)"""
-    state = {"storm_time": stdur + istdur, "rate": pmean}
-
+    # stateless (several in-process ranks evaluate the same schedule, each over its own batch of times): the rate is
+    # PMEAN up to the end of the first storm and 0 from the first step inside the interstorm on
     def rain(t):
-        if t <= state["storm_time"] - istdur:
-            return state["rate"]
-        if t <= state["storm_time"]:
-            state["rate"] = 0.0
-            return 0.0
-        state["storm_time"] += stdur + istdur
-        return state["rate"]
+        return pmean if (t <= stdur or istdur <= 0.0) else 0.0
 
     return rain
 
