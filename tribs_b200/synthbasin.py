@@ -16,6 +16,8 @@ meshElements.cpp:858-867).
 """
 from __future__ import annotations
 
+import math
+
 import numpy as np
 
 # neighbour offsets (di, dj) counter-clockwise, consistent-diagonal triangulation
@@ -295,6 +297,21 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         "init_NwtOld": nwt0, "init_NwtNew": nwt0.copy(), "init_MuOld": mi0, "init_MuNew": mi0.copy(),
         "init_MiOld": mi0.copy(), "init_MiNew": mi0.copy(),
     }
+    # the channel network as tKinemat sets it up for this deck: one reach from the head of the river to the basin outlet,
+    # widths from the geomorphic relation CHANNELWIDTHCOEFF * (contributing area in km2) ** CHANNELWIDTHEXPNT
+    # (tKinemat::AssignChannelWidths, tKinemat.cpp:404-446; synth.py writes 1.0 and 0.3), CHANNELROUGHNESS 0.15
+    stream_mask = basin["boundary"] == 3
+    river = np.flatnonzero(stream_mask)
+    river_head = river[~np.isin(river, fdest[river])]
+    chan_width = np.zeros(n)
+    chan_width[river] = [1.0 * math.pow(a * 1.0E-6, 0.3) for a in contr[river].tolist()]     # libm's pow, as the reference
+    basin.update({
+        "reach_head": river_head[:1].astype(np.int32), "reach_outlet": np.array([-1], np.int32),
+        "reach_nnodes": np.array([river.size + 1], np.int32),
+        "chan_width": chan_width, "outlet_chan_width": np.array([1.0 * math.pow(bas_area * 1.0E-6, 0.3)]),
+        "chan_roughness": np.array([0.15]), "chan_width_uniform": np.array([-999.0]),
+        "chan_percolation": np.array([0], np.int32), "chan_optres": np.array([0], np.int32),
+    })
     if mesh_dir is not None:
         from .meshb import EDGE_DTYPE, NODE_DTYPE, write_meshb
         G = NX * NY
