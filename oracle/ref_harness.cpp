@@ -495,6 +495,8 @@ struct Harness {
         w.f64(pre + "RuNew", col([](tCNode *c) { return c->getRuNew(); }));
         w.f64(pre + "RiNew", col([](tCNode *c) { return c->getRiNew(); }));
         if (with_old) {
+            w.f64(pre + "Hlevel", col([](tCNode *c) { return c->getHlevel(); }));      // channel router (tKinemat)
+            w.f64(pre + "Qstrm", col([](tCNode *c) { return c->getQstrm(); }));
             w.f64(pre + "NwtOld", col([](tCNode *c) { return c->getNwtOld(); }));
             w.f64(pre + "MuOld", col([](tCNode *c) { return c->getMuOld(); }));
             w.f64(pre + "MiOld", col([](tCNode *c) { return c->getMiOld(); }));
@@ -774,6 +776,7 @@ int main(int argc, char **argv) {
     string meshb_dir; // --dump-meshb <dir>: write the OPTMESHINPUT 9 files of the mesh / flow network just built
     string gpu_lib;   // --gpu <libtribs_gpu.so>: the reference's loop drives the B200 path
     int gpu_ranks = 1, gpu_batch = 16;
+    bool gpu_channels = false;
     double inject_evap = 0.0;   // --inject-evap R: soil evaporation R mm/h on dry steps (see below)
     vector<char*> rargs;
     for (int i = 0; i < argc; i++) {
@@ -787,6 +790,7 @@ int main(int argc, char **argv) {
         else if (a == "--gpu" && i + 1 < argc) gpu_lib = argv[++i];
         else if (a == "--gpu-ranks" && i + 1 < argc) gpu_ranks = atoi(argv[++i]);     // reach partitions, one handle each
         else if (a == "--gpu-batch" && i + 1 < argc) gpu_batch = atoi(argv[++i]);     // steps per tribs_gpu_run
+        else if (a == "--gpu-channels") gpu_channels = true;    // partitioned mode: kinematic-wave reaches on the device too
         else if (a == "--inject-evap" && i + 1 < argc) inject_evap = atof(argv[++i]);
         else if (a == "--no-basin") do_basin = false;
         else if (a == "--dump-meshb" && i + 1 < argc) meshb_dir = argv[++i];
@@ -860,9 +864,11 @@ int main(int argc, char **argv) {
 
     // Partitioned hybrid run: the reference's timer and rainfall objects advance k steps ahead, the device runs them as
     // ONE pipelined batch on every rank (tribs_gpu_run, peer-memory halos), the owned cells of every rank go back to
-    // the tCNodes. Channel routing on the host is not part of this mode (snapshots are taken after Reset()).
+    // the tCNodes. With --gpu-channels the reaches are routed on the device as well (tribs_gpu_channel_route over the
+    // batch) and tKinemat's levels and discharges are refilled from it; snapshots are taken after Reset().
     if (use_gpu && gpu_ranks > 1) {
         int step = 0;
+        if (gpu_channels) gpu.attachChannels(&Flow);
         vector<int32_t> snap_steps;
         while (!Timer.IsFinished() && !(max_steps > 0 && step >= max_steps)) {
             const int k_max = max_steps > 0 ? std::min(gpu_batch, max_steps - step) : gpu_batch;
@@ -882,6 +888,10 @@ int main(int argc, char **argv) {
             }
             for (size_t k = 0; k < st.size(); k++) st[k].rain = rains[k].data();
             gpu.runBatch(st, masks);
+            if (gpu_channels) {
+                vector<double> q = gpu.routeChannels((int)st.size());
+                qout_series.insert(qout_series.end(), q.begin(), q.end());
+            }
             step += (int)st.size();
             if (sw && step >= snap_from && step <= snap_to) {
                 gpu.syncToNodes();
@@ -891,7 +901,7 @@ int main(int argc, char **argv) {
                 snap_steps.push_back(step);
             }
         }
-        if (sw) { sw->i32("snap_steps", snap_steps); sw.reset(); }
+        if (sw) { sw->i32("snap_steps", snap_steps); sw->f64("qout", qout_series); sw.reset(); }
         printf("\nref_timing {\"cells\": %ld, \"steps\": %d, \"ranks\": %d}\n", (long)H.cells.size(), step, gpu_ranks);
         return 0;
     }

@@ -74,3 +74,33 @@ def test_reference_host_runs_partitioned_through_the_binding(ranks, built):
     assert worst <= 1e-6, worst
     moved = {f: float(np.abs(ref[f"s96_e_{f}"] - ref[f"s16_e_{f}"]).max()) for f in ("NwtNew", "MuNew", "NfNew", "srf_hr")}
     assert moved["MuNew"] > 0 and moved["NfNew"] > 0, moved
+
+
+@pytest.mark.skipif(not have_harness(), reason="oracle/_ref/tribs_ref_harness not built")
+def test_reference_host_routes_its_channels_on_the_device(built):
+    """SURVEY §8 row f2 through the boundary: the reference's own tKinemat hands its reach lists, widths, slopes and levels
+    to tribs_gpu_channel_init (TribsGpuBinding::attachChannels), every 16-step batch is followed by ONE
+    tribs_gpu_channel_route call, and Hlevel / Qstrm of the tCNodes and the outlet discharge of every step must match the
+    pure serial reference (its own RunRoutingModel on the host) within 1e-6. Dendritic net, two reach partitions."""
+    d = tempfile.mkdtemp(prefix="tribshybc_")
+    write_basin(spec_for("deep", 40, runtime_h=8.0, seed=4, tributary_every=8, pmean=30.0), d)
+    lib = os.path.join(ROOT, "tribs_b200", "libtribs_gpu.so")
+    common = [HARNESS, "basin.in", "-K", "--no-basin", "--snap-from", "16", "--snap-to", "96", "--snap-every", "16",
+              "--phases", "e", "--max-steps", "96"]
+    outs = {}
+    for tag, extra in (("ref", []), ("gpu", ["--gpu", lib, "--gpu-ranks", "2", "--gpu-batch", "16", "--gpu-channels"])):
+        out = os.path.join(d, tag)
+        os.makedirs(out)
+        r = subprocess.run([*common, "--out", out, *extra], cwd=d, capture_output=True, text=True, timeout=1200)
+        assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+        outs[tag] = read_trb(os.path.join(out, "steps.trb"))
+    q_ref = read_trb(os.path.join(d, "ref", "qout_ref.trb"))["qout"][:96]
+    q_gpu = outs["gpu"]["qout"]
+    assert q_gpu.size == 96 and q_ref.max() > 0.05, (q_gpu.size, q_ref.max())
+    worst = float((np.abs(q_ref - q_gpu) / np.maximum(np.abs(q_ref), 1e-6)).max())
+    for st in (16, 48, 96):
+        for f in ("Hlevel", "Qstrm"):
+            a, b = outs["ref"][f"s{st}_e_{f}"], outs["gpu"][f"s{st}_e_{f}"]
+            worst = max(worst, float((np.abs(a - b) / np.maximum(np.abs(a), 1e-6)).max()))
+    assert worst <= 1e-6, worst
+    assert outs["ref"]["s96_e_Hlevel"].max() > 0.01

@@ -42,17 +42,17 @@ __device__ __forceinline__ double chan_block_max(double v, double *red) {
   return r;
 }
 
-// tKinemat.cpp:1950-1998 for element i; X = levels of nodes 1..m at (t+1), H = levels of nodes 0..m at t
-__device__ __forceinline__ double chan_function(int i, int m, const double *X, const double *H, const double *c, const double *y1,
-                                                const double *y2, const double *y3, const double *reff, double qit, double hupp) {
-  const double fk2 = 5. / 3.;
+// tKinemat.cpp:1950-1998 for element i; X = levels of nodes 1..m at (t+1) and XP = X^(5/3) (the reference's XFK2 array),
+// H = levels of nodes 0..m at t
+__device__ __forceinline__ double chan_function(int i, int m, const double *X, const double *XP, const double *H, const double *c,
+                                                const double *y1, const double *y2, const double *y3, const double *reff,
+                                                double qit, double hupp) {
   const int m1 = m - 1;
   if (i == 0)
-    return 0.5 * c[2] * pow(X[1], fk2) - qit + y3[0] * (hupp - H[0]) + y2[0] * (X[0] - H[1]) + y1[0] * (X[1] - H[2]) - reff[0];
+    return 0.5 * c[2] * XP[1] - qit + y3[0] * (hupp - H[0]) + y2[0] * (X[0] - H[1]) + y1[0] * (X[1] - H[2]) - reff[0];
   if (i == m1)
-    return 0.5 * c[m] * pow(X[m1], fk2) - 0.5 * c[m1] * pow(X[m1 - 1], fk2) + y3[m1] * (X[m1 - 1] - H[m1]) + y2[m1] * (X[m1] - H[m])
-           - reff[m1];
-  return 0.5 * c[i + 2] * pow(X[i + 1], fk2) - 0.5 * c[i] * pow(X[i - 1], fk2) + y3[i] * (X[i - 1] - H[i]) + y2[i] * (X[i] - H[i + 1])
+    return 0.5 * c[m] * XP[m1] - 0.5 * c[m1] * XP[m1 - 1] + y3[m1] * (X[m1 - 1] - H[m1]) + y2[m1] * (X[m1] - H[m]) - reff[m1];
+  return 0.5 * c[i + 2] * XP[i + 1] - 0.5 * c[i] * XP[i - 1] + y3[i] * (X[i - 1] - H[i]) + y2[i] * (X[i] - H[i + 1])
          + y1[i] * (X[i + 1] - H[i + 2]) - reff[i];
 }
 
@@ -87,35 +87,46 @@ __device__ double chan_two_node_root(double c1, double c2, double c3, double x1,
 
 // bandec + banbks for one sub- and one super-diagonal (tKinemat.cpp:2154-2230), rows 1..N in A1..A3 (already in the
 // shifted form bandec makes of row 1), right-hand side B[1..N]; the forward substitution rides on the elimination
-// (same operations in the same order per element). Thread 0.
+// (same operations in the same order per element). Thread 0. The pivot row travels in registers and the next row is
+// loaded before the division it does not depend on, so the chain per row is one IEEE division and one multiply-subtract
+// (elimination) or two multiply-subtracts and one division (back substitution), not a round trip through shared memory.
 __device__ void chan_band_solve(double *A1, double *A2, double *A3, double *B, int N) {
-  for (int k = 1; k <= N; k++) {
-    double dum = A1[k];
-    bool swap = false;
-    if (k < N && fabs(A1[k + 1]) > fabs(dum)) { dum = A1[k + 1]; swap = true; }
-    if (dum == 0.0) A1[k] = 1.0E-20;
-    if (swap) {
+  double r1 = A1[1], r2 = A2[1], r3 = A3[1], rb = B[1];
+  double n1 = A1[2], n2 = A2[2], n3 = A3[2], nb = B[2];          // N >= 2
+  for (int k = 1; k < N; k++) {
+    const int kn = min(k + 2, N);                                  // row after the next (its values are still the original ones)
+    const double m1 = A1[kn], m2 = A2[kn], m3 = A3[kn], mb = B[kn];
+    if (fabs(n1) > fabs(r1)) {                                     // partial pivoting over the two candidate rows
       double t;
-      t = A1[k]; A1[k] = A1[k + 1]; A1[k + 1] = t;
-      t = A2[k]; A2[k] = A2[k + 1]; A2[k + 1] = t;
-      t = A3[k]; A3[k] = A3[k + 1]; A3[k + 1] = t;
-      t = B[k]; B[k] = B[k + 1]; B[k + 1] = t;
-    }
-    if (k < N) {
-      dum = A1[k + 1] / A1[k];
-      A1[k + 1] = A2[k + 1] - dum * A2[k];
-      A2[k + 1] = A3[k + 1] - dum * A3[k];
-      A3[k + 1] = 0.0;
-      B[k + 1] -= dum * B[k];
-    }
+      t = r1; r1 = n1; n1 = t;
+      t = r2; r2 = n2; n2 = t;
+      t = r3; r3 = n3; n3 = t;
+      t = rb; rb = nb; nb = t;
+    } else if (r1 == 0.0)
+      r1 = 1.0E-20;
+    const double dum = n1 / r1;
+    A1[k] = r1; A2[k] = r2; A3[k] = r3; B[k] = rb;
+    r1 = n2 - dum * r2;
+    r2 = n3 - dum * r3;
+    r3 = 0.0;
+    rb = nb - dum * rb;
+    n1 = m1; n2 = m2; n3 = m3; nb = mb;
   }
-  int l = 1;
-  for (int i = N; i >= 1; i--) {
-    double dum = B[i];
-    if (l >= 2) dum -= A2[i] * B[i + 1];
-    if (l >= 3) dum -= A3[i] * B[i + 2];
-    B[i] = dum / A1[i];
-    if (l < 3) l++;
+  if (r1 == 0.0) r1 = 1.0E-20;
+  // back substitution: x[i] = (b[i] - a2[i] x[i+1] - a3[i] x[i+2]) / a1[i]
+  double x1 = rb / r1;                                             // row N
+  B[N] = x1;
+  double x2 = 0.0;
+  double c1 = A1[N - 1], c2 = A2[N - 1], c3 = A3[N - 1], cb = B[N - 1];
+  for (int i = N - 1; i >= 1; i--) {
+    const int ip = max(i - 1, 1);
+    const double p1 = A1[ip], p2 = A2[ip], p3 = A3[ip], pb = B[ip];
+    double dum = cb - c2 * x1;
+    if (i <= N - 2) dum -= c3 * x2;
+    const double x = dum / c1;
+    B[i] = x;
+    x2 = x1; x1 = x;
+    c1 = p1; c2 = p2; c3 = p3; cb = pb;
   }
 }
 
@@ -128,7 +139,7 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
   const size_t stride = (size_t)cn.max_n + 2;
   double *X = cn.ws, *X1 = X + stride, *Fg = X1 + stride, *aa = Fg + stride, *bb = aa + stride, *cc = bb + stride,
          *reis = cc + stride, *his = reis + stride, *gA1 = his + stride, *gA2 = gA1 + stride, *gA3 = gA2 + stride,
-         *gB = gA3 + stride;
+         *gB = gA3 + stride, *XP = gB + stride;     // XP: X^(5/3) for the function, X^(2/3) for the Jacobian
   const bool in_shared = (int)stride <= shared_rows;
   double *A1 = in_shared ? chan_sm : gA1, *A2 = in_shared ? chan_sm + stride : gA2, *A3 = in_shared ? chan_sm + 2 * stride : gA3,
          *B = in_shared ? chan_sm + 3 * stride : gB;
@@ -171,14 +182,14 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
         if (tid == 0) { his[0] = hupp; his[1] = sc[6]; }
         __syncthreads();
       } else {                                                     // KinematWave
-        for (int i = tid; i < m; i += T) X[i] = X1[i] = his[i + 1];
+        for (int i = tid; i < m; i += T) { const double x = his[i + 1]; X[i] = X1[i] = x; A3[i] = x; XP[i] = pow(x, fk2); }
         __syncthreads();
-        for (int i = tid; i < m; i += T) { const double f = chan_function(i, m, X1, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = f; FS[i] = f; }
+        for (int i = tid; i < m; i += T) { const double f = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = f; FS[i] = f; }
         __syncthreads();
         if (tid == 0) {
           double sum = 0.0, test = 0.0, sx = 0.0;
           for (int i = 0; i < m; i++) { const double f = FS[i]; sum += f * f; if (fabs(f) > test) test = fabs(f); }
-          for (int i = 0; i < m; i++) { const double x = his[i + 1]; sx += x * x; }
+          for (int i = 0; i < m; i++) { const double x = A3[i]; sx += x * x; }
           sc[0] = 0.5 * sum; sc[1] = test; sc[2] = STPMX * fmax(sqrt(sx), (double)m);
         }
         __syncthreads();
@@ -190,12 +201,13 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
         for (; !done && iter <= 200; iter++) {
           iters++;
           // Jacobian (global copy for the gradient) and, in the same pass, the band matrix and right-hand side of the solve
+          for (int i = tid; i < m; i += T) XP[i] = pow(X1[i], fk3);
+          __syncthreads();
           for (int i = tid; i < m; i += T) {
-            const double p_i = pow(X1[i], fk3);
             double b_i, c_i = 0.0, a_i = 0.0;
-            if (i < m - 1) { b_i = y2[i]; c_i = fk1 * c[i + 2] * pow(X1[i + 1], fk3) + y1[i]; }
-            else b_i = fk1 * c[m] * p_i + y2[m - 1];
-            if (i >= 1) a_i = -fk1 * c[i] * pow(X1[i - 1], fk3) + y3[i];
+            if (i < m - 1) { b_i = y2[i]; c_i = fk1 * c[i + 2] * XP[i + 1] + y1[i]; }
+            else b_i = fk1 * c[m] * XP[i] + y2[m - 1];
+            if (i >= 1) a_i = -fk1 * c[i] * XP[i - 1] + y3[i];
             aa[i] = a_i; bb[i] = b_i; cc[i] = c_i;
             const int k = i + 1;                                    // 1-based row
             if (k == 1) { A1[1] = b_i; A2[1] = c_i; A3[1] = 0.0; }   // bandec's left shift of row 1
@@ -219,17 +231,28 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
           const double fold = f;
           // lnsrch
           double tloc = 0.0;
+          // the two sums are independent chains: two threads walk them side by side (a scaled step - never seen on the
+          // test basins - redoes the slope after the scaling, as the reference's order of operations requires)
           if (tid == 0) {
             double sum = 0.0;
             for (int i = 0; i < m; i++) sum += p[i] * p[i];
-            sum = sqrt(sum);
-            if (sum > stpmax)
-              for (int i = 0; i < m; i++) B[i + 1] *= stpmax / sum;
+            sc[4] = sqrt(sum);
+          } else if (tid == 32) {
             double slope = 0.0;
             for (int i = 0; i < m; i++) slope += G[i] * p[i];
             sc[3] = slope;
           }
           __syncthreads();
+          if (sc[4] > stpmax) {
+            if (tid == 0) {
+              const double sum = sc[4];
+              for (int i = 0; i < m; i++) B[i + 1] *= stpmax / sum;
+              double slope = 0.0;
+              for (int i = 0; i < m; i++) slope += G[i] * p[i];
+              sc[3] = slope;
+            }
+            __syncthreads();
+          }
           for (int i = tid; i < m; i += T) tloc = fmax(tloc, fabs(p[i]) / fmax(fabs(X[i]), 1.0));
           const double ptest = chan_block_max(tloc, red);
           const double slope = sc[3];
@@ -246,9 +269,10 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
               double x = X[i] + alam * p[i];
               if (x < 0.0) x = 1.0E-6;
               X1[i] = x;
+              XP[i] = pow(x, fk2);
             }
             __syncthreads();
-            for (int i = tid; i < m; i += T) { const double fv = chan_function(i, m, X1, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = fv; FS[i] = fv; }
+            for (int i = tid; i < m; i += T) { const double fv = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = fv; FS[i] = fv; }
             __syncthreads();
             if (tid == 0) {
               double sum = 0.0, test = 0.0;

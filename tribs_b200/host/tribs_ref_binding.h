@@ -246,6 +246,81 @@ struct TribsGpuBinding {
     }
    }
   }
+  // ------------------------------------------------------------------ channel routing
+  // attachChannels hands tKinemat's reach lists, channel geometry and levels to the device (what InitializeStreamReach,
+  // tKinemat.cpp:1136-1252, reads per reach and step); routeChannels(k) replaces the reach loop of
+  // tKinemat::RunRoutingModel (823-891) for the k steps of the last batch (k = 0: the single step whose ROUTE phase
+  // ran last) and writes Hlevel / Qstrm / FlowVelocity back to the stream nodes, OutletHlev and Qout to tKinemat.
+  // Inside the reference this is member code of tKinemat (it uses its protected lists).
+  tKinemat *kin = nullptr;
+  decltype(&tribs_gpu_channel_init) p_ch_init = nullptr;
+  decltype(&tribs_gpu_channel_route) p_ch_route = nullptr;
+  decltype(&tribs_gpu_channel_sync) p_ch_sync = nullptr;
+  std::vector<int32_t> ch_off, ch_node, ch_stream_cells;
+  std::vector<double> ch_width, ch_length, ch_slope;
+
+  void attachChannels(tKinemat *flow) {
+    kin = flow;
+    p_ch_init = (decltype(p_ch_init))dlsym(lib, "tribs_gpu_channel_init");
+    p_ch_route = (decltype(p_ch_route))dlsym(lib, "tribs_gpu_channel_route");
+    p_ch_sync = (decltype(p_ch_sync))dlsym(lib, "tribs_gpu_channel_sync");
+    auto p_n_stream = (decltype(&tribs_gpu_n_stream))dlsym(lib, "tribs_gpu_n_stream");
+    auto p_stream_cells = (decltype(&tribs_gpu_stream_cells))dlsym(lib, "tribs_gpu_stream_cells");
+    if (!p_ch_init || !p_ch_route || !p_ch_sync || !p_n_stream || !p_stream_cells) die("dlsym (tribs_gpu_channel_*)");
+    const int n = (int)cells.size();
+    tPtrListIter<tCNode> hi(flow->NodesLstH);
+    tListIter<int> ni(flow->NNodes);
+    ch_off.assign(1, 0);
+    ni.First();
+    for (tCNode *head = hi.FirstP(); !hi.AtEnd(); head = hi.NextP(), ni.Next()) {
+      tCNode *c = head;
+      const int nn = ni.DatRef();
+      for (int k = 0; k < nn; k++) {
+        const int id = idx((tNode *)c);                       // the basin outlet is not an active cell
+        const bool last = k == nn - 1;
+        ch_node.push_back(id >= 0 ? id : n);
+        ch_width.push_back(c->getChannelWidth());
+        ch_length.push_back(last ? 0.0 : c->getFlowEdg()->getLength());
+        ch_slope.push_back(last ? 0.0 : c->getFlowEdg()->getSlope());
+        if (!last) c = c->getDownstrmNbr();
+      }
+      ch_off.push_back((int32_t)ch_node.size());
+    }
+    std::vector<double> h0(n + 1), q0(n + 1), oh(ch_off.size() - 1);
+    for (int i = 0; i < n; i++) { h0[i] = cells[i]->getHlevel(); q0[i] = cells[i]->getQstrm(); }
+    h0[n] = flow->OutletNode->getHlevel(); q0[n] = flow->OutletNode->getQstrm();
+    for (size_t r = 0; r < oh.size(); r++) oh[r] = flow->OutletHlev[r];
+    tribs_channel_t C{};
+    C.n_reach = (int32_t)oh.size();
+    C.percolation_option = flow->percolationOption; C.reservoir_option = flow->optres;
+    C.reach_off = ch_off.data(); C.reach_node = ch_node.data();
+    C.width = ch_width.data(); C.length = ch_length.data(); C.slope = ch_slope.data();
+    C.roughness = flow->Roughness; C.uniform_width = flow->Width; C.dt_s = timer->getTimeStep() * 3600.;
+    C.hlevel0 = h0.data(); C.qstrm0 = q0.data(); C.outlet_hlev0 = oh.data();
+    for (tribs_handle_t hr : rank_h)
+      if (p_ch_init(hr, &C)) die("tribs_gpu_channel_init");
+    ch_stream_cells.resize(p_n_stream(rank_h[0]));
+    if (p_stream_cells(rank_h[0], ch_stream_cells.data())) die("tribs_gpu_stream_cells");
+  }
+
+  // returns tKinemat::Qout after each of the k steps
+  std::vector<double> routeChannels(int k) {
+    std::vector<double> q((size_t)std::max(k, 1));
+    for (tribs_handle_t hr : rank_h)            // every rank routes the whole net from the combined inflows: same result
+      if (p_ch_route(hr, k, q.data())) die("tribs_gpu_channel_route");
+    const size_t S = ch_stream_cells.size();
+    std::vector<double> hl(S + 1), qs(S + 1), vel(S + 1), oh(ch_off.size() - 1);
+    if (p_ch_sync(rank_h[0], hl.data(), qs.data(), vel.data(), oh.data(), nullptr)) die("tribs_gpu_channel_sync");
+    for (size_t s = 0; s < S; s++) {
+      tCNode *c = cells[ch_stream_cells[s]];
+      c->setHlevel(hl[s]); c->setQstrm(qs[s]); c->setFlowVelocity(vel[s]);
+    }
+    kin->OutletNode->setHlevel(hl[S]); kin->OutletNode->setQstrm(qs[S]);
+    for (size_t r = 0; r < oh.size(); r++) kin->OutletHlev[r] = oh[r];
+    kin->Qout = q.back();
+    return q;
+  }
+
   // ------------------------------------------------------------------ kernel (1): ET + interception
   // These bodies replace the cell loops of tEvapoTrans::callEvapoPotential (tEvapoTrans.cpp:603-795)
   // and tEvapoTrans::callEvapoTrans (1010-1028); inside the reference they are member code of
