@@ -237,11 +237,20 @@ def run_gpu(args):
     def resident_batch(k):
         sim.run_batch(k, rain_of_time=rain_resident)      # with ET on, kernel (1) rides inside the batch (tribs_gpu_run_et)
 
+    # A third leg repeats e2e with the channels routed on the device as well (tKinemat's kinematic-wave reaches, SURVEY
+    # row f2: one launch per batch, the outlet discharge per step comes back instead of the lateral inflows): the
+    # reference's SurfaceFlow, which its arm times, includes them.
+    channels = not args.no_channels and args.stream_every == 0
+    if channels:
+        sim.flow.route_channels(basin)
+        sim.flow.on_device = False        # `value` and `e2e` time the per-cell path, whose boundary is the lateral inflow
+
     def e2e_batch(k):
         row_of["k"] = 0
-        sim.run_batch(k, rain_of_time=rain_pinned, collect_qeff=True)   # H2D: k x n_gauges rain values (+ station records)
-        g = dev.globals()                                               # D2H: per-step lateral inflows, basin accumulators
-        return sim.batch_qeff, g
+        with_channels = sim.flow.on_device
+        sim.run_batch(k, rain_of_time=rain_pinned, collect_qeff=not with_channels)   # H2D: k x n_gauges rain values (+ station records)
+        g = dev.globals()                                               # D2H: lateral inflows (or outlet discharge) per step, accumulators
+        return (sim.flow.qout_series if with_channels else sim.batch_qeff), g
 
     def loop(fn_batch, k):
         done = 0
@@ -296,14 +305,22 @@ def run_gpu(args):
     dev.rollback()
     sim.host_restore()
     ems, ewall = timed(lambda k: loop(e2e_batch, k), args.steps)
+    chan_ms = None
+    if channels:
+        dev.rollback()
+        sim.host_restore()
+        sim.flow.on_device = True
+        cms, cwall = timed(lambda k: loop(e2e_batch, k), args.steps)
+        chan_ms = max(cms, cwall)
+        chan_state = dev.channel_sync()
     v0 = args.warmup + 1
     windows = {"value": [v0, v0 + args.steps - 1], "e2e": [v0, v0 + args.steps - 1], "storm_ends_at_step": 96}
     # host work (numpy fill, ctypes) is part of the user-visible e2e time: use the wall clock
     e2e_ms = max(ems, ewall)
     if world > 1:
-        tt = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([e2e_ms, chan_ms or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        e2e_ms = float(tt.item())
+        e2e_ms, chan_ms = float(tt[0].item()), (float(tt[1].item()) if channels else None)
 
     if world > 1:   # cells advanced by all ranks together
         tt = torch.tensor([float(n)], dtype=torch.float64, device="cuda")
@@ -349,6 +366,14 @@ def run_gpu(args):
         "phase_ms_per_step": {k: v / args.steps for k, v in phases.items()},
     }
     say("end-to-end leg timed")
+    if channels:
+        line["e2e_with_channels"] = {
+            "value": total_cells * args.steps / (chan_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": 8 * n_gauges * world,
+            "d2h_bytes_per_step": (8 + 8 * len(gpu.GLOBALS)) * world,
+            "what": "e2e plus tribs_gpu_channel_route after every batch (kinematic-wave reaches on the device, every rank routes "
+                    "the whole net); the outlet discharge per step replaces the lateral inflows in the D2H copy",
+            "stream_nodes": n_stream + 1, "newton_iterations": chan_state["newton_iterations"],
+            "outlet_discharge_m3s": float(sim.flow.Qout)}
     if check is not None:
         line["self_check"] = check
     if world == 1 and not args.no_et_kernel and cfg == 2:
@@ -596,6 +621,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256, help="steps per pipelined launch (tribs_gpu_run), at most --steps")
     ap.add_argument("--mgpu", default="partition", choices=["partition", "replicas"],
                     help="N>1: one reach-partitioned basin with halo exchange (default) or independent replicas")
+    ap.add_argument("--no-channels", action="store_true", help="e2e leg: leave the channel routing to the host (copy the lateral inflows out)")
     ap.add_argument("--no-self-check", action="store_true", help="N>1: skip the bit-equality check against one GPU")
     ap.add_argument("--stream-every", type=int, default=0, help="tributary stream row every K rows (0: one river, "
                     "hillslopes as long as half the basin width)")

@@ -282,7 +282,8 @@ int tribs_gpu_channel_init(tribs_handle_t h, const tribs_channel_t *net);
  * TRIBS_PHASE_ROUTE ran last. qout[k] = tKinemat::Qout after step k (the value SurfaceFlow 740-757 writes to <base>_Outlet.qout). */
 int tribs_gpu_channel_route(tribs_handle_t h, int32_t n_steps, double *qout);
 /* Hlevel / Qstrm / FlowVelocity per stream slot (tribs_gpu_stream_cells order) + the basin outlet, OutletHlev per reach,
- * counters[3] = Newton iterations, line-search backtracks, reaches that exceeded MAXITS since init. Pointers may be NULL. */
+ * counters[7] = Newton iterations, line-search backtracks, reaches that exceeded MAXITS since init, then the device clock
+ * cycles thread 0 spent in the band solve, the line-search sums, the function sums and the whole kernel. Pointers may be NULL. */
 int tribs_gpu_channel_sync(tribs_handle_t h, double *hlevel, double *qstrm, double *velocity, double *outlet_hlev,
                            int64_t *counters);
 

@@ -37,4 +37,5 @@ for b in range(batches):
           f"({1e3 * (t2 - t1) / max(it - prev, 1):.3f} ms each), backtracks so far {st['backtracks']}, Qout {sim.flow.Qout:.4f} m3/s, "
           f"max level {st['Hlevel'].max():.3f} m")
     prev = it
+print('thread-0 cycles:', st['cycles'])
 sim.dev.close()

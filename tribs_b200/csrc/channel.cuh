@@ -14,7 +14,8 @@
 // banded LU), a few thousand unknowns per reach: everything element-wise (function values with their x^(5/3), the
 // Jacobian, the trial levels of the line search, maxima) is spread over the block, the order-dependent parts - the LU with
 // its forward / backward substitution and the three sums of the line search - run in thread 0 from shared memory in
-// exactly the reference's order. FP64 throughout; differs from the reference only through the library's pow().
+// the reference's order. FP64 throughout; differs from the reference through the library's pow() and through the back
+// substitution, which multiplies by reciprocal pivots (see chan_band_back).
 #pragma once
 
 constexpr int kChanThreads = 1024;
@@ -29,6 +30,7 @@ struct ChanNet {
   double *outlet_hlev;                     // per reach (tKinemat::OutletHlev)
   double *ws;                              // workspace: kChanWsVecs vectors of (max_n + 2)
   int32_t *status;                         // [0] first error, [1] Newton iterations, [2] backtracks, [3] MAXITS exceeded
+  long long *cycles;                       // thread 0's clock64() spent in [0] band solve, [1] line-search sums, [2] function sums, [3] whole kernel
 };
 constexpr int kChanWsVecs = 14;
 
@@ -86,11 +88,12 @@ __device__ double chan_two_node_root(double c1, double c2, double c3, double x1,
 }
 
 // bandec + banbks for one sub- and one super-diagonal (tKinemat.cpp:2154-2230), rows 1..N in A1..A3 (already in the
-// shifted form bandec makes of row 1), right-hand side B[1..N]; the forward substitution rides on the elimination
-// (same operations in the same order per element). Thread 0. The pivot row travels in registers and the next row is
-// loaded before the division it does not depend on, so the chain per row is one IEEE division and one multiply-subtract
-// (elimination) or two multiply-subtracts and one division (back substitution), not a round trip through shared memory.
-__device__ void chan_band_solve(double *A1, double *A2, double *A3, double *B, int N) {
+// shifted form bandec makes of row 1), right-hand side B[1..N].
+// Elimination (thread 0): the reference's operations in the reference's order, with the forward substitution of the
+// right-hand side riding along. The pivot row travels in registers and the next row is loaded before the division it
+// does not depend on, so the chain per row is one IEEE division and one multiply-subtract. A dependent FP64 operation
+// costs ~20 cycles here, the division nine of them: that chain is what the kernel's time is made of.
+__device__ void chan_band_eliminate(double *A1, double *A2, double *A3, double *B, int N) {
   double r1 = A1[1], r2 = A2[1], r3 = A3[1], rb = B[1];
   double n1 = A1[2], n2 = A2[2], n3 = A3[2], nb = B[2];          // N >= 2
   for (int k = 1; k < N; k++) {
@@ -113,17 +116,22 @@ __device__ void chan_band_solve(double *A1, double *A2, double *A3, double *B, i
     n1 = m1; n2 = m2; n3 = m3; nb = mb;
   }
   if (r1 == 0.0) r1 = 1.0E-20;
-  // back substitution: x[i] = (b[i] - a2[i] x[i+1] - a3[i] x[i+2]) / a1[i]
-  double x1 = rb / r1;                                             // row N
+  A1[N] = r1; A2[N] = 0.0; A3[N] = 0.0; B[N] = rb;
+}
+// Back substitution (thread 0): x[i] = (b[i] - a2[i] x[i+1] - a3[i] x[i+2]) / a1[i], with the division replaced by a
+// multiplication with the reciprocal pivot that all threads computed beforehand (R1 = 1 / a1, IEEE division, off the
+// chain): three to five dependent operations per row instead of twelve. This is the one place where the arithmetic is
+// not the reference's: x differs from a correctly rounded quotient by at most one unit in the last place.
+__device__ void chan_band_back(const double *R1, const double *A2, const double *A3, double *B, int N) {
+  double x1 = B[N] * R1[N], x2 = 0.0;
   B[N] = x1;
-  double x2 = 0.0;
-  double c1 = A1[N - 1], c2 = A2[N - 1], c3 = A3[N - 1], cb = B[N - 1];
+  double c1 = R1[N - 1], c2 = A2[N - 1], c3 = A3[N - 1], cb = B[N - 1];
   for (int i = N - 1; i >= 1; i--) {
     const int ip = max(i - 1, 1);
-    const double p1 = A1[ip], p2 = A2[ip], p3 = A3[ip], pb = B[ip];
+    const double p1 = R1[ip], p2 = A2[ip], p3 = A3[ip], pb = B[ip];
     double dum = cb - c2 * x1;
     if (i <= N - 2) dum -= c3 * x2;
-    const double x = dum / c1;
+    const double x = dum * c1;
     B[i] = x;
     x2 = x1; x1 = x;
     c1 = p1; c2 = p2; c3 = p3; cb = pb;
@@ -148,6 +156,8 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
   const double TOLF = 1.0e-4, TOLX = 1.0e-7, STPMX = 100.0, ALF = 1.0e-4;
   const double fk2 = 5. / 3., fk3 = 2. / 3., fk1 = 5. / 6.;
   int iters = 0, backtracks = 0, maxits = 0;
+  long long cy_solve = 0, cy_ls = 0, cy_fs = 0;
+  const long long cy_begin = clock64();
 
   for (int step = 0; step < n_steps; step++) {
     const double *qeff = qeff_steps + (size_t)step * cn.slots;
@@ -216,7 +226,11 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
             B[k] = (fv == 0) ? fv : -fv;
           }
           __syncthreads();
-          if (tid == 0) chan_band_solve(A1, A2, A3, B, m);
+          if (tid == 0) { const long long t0 = clock64(); chan_band_eliminate(A1, A2, A3, B, m); cy_solve += clock64() - t0; }
+          __syncthreads();
+          for (int k = 1 + tid; k <= m; k += T) A1[k] = 1.0 / A1[k];
+          __syncthreads();
+          if (tid == 0) { const long long t0 = clock64(); chan_band_back(A1, A2, A3, B, m); cy_solve += clock64() - t0; }
           __syncthreads();
           const double *p = B + 1;
           for (int i = tid; i < m; i += T) {                        // grad(f) = F*J, and the levels of the preceding iteration
@@ -234,9 +248,11 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
           // the two sums are independent chains: two threads walk them side by side (a scaled step - never seen on the
           // test basins - redoes the slope after the scaling, as the reference's order of operations requires)
           if (tid == 0) {
+            const long long t0 = clock64();
             double sum = 0.0;
             for (int i = 0; i < m; i++) sum += p[i] * p[i];
             sc[4] = sqrt(sum);
+            cy_ls += clock64() - t0;
           } else if (tid == 32) {
             double slope = 0.0;
             for (int i = 0; i < m; i++) slope += G[i] * p[i];
@@ -275,9 +291,11 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
             for (int i = tid; i < m; i += T) { const double fv = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = fv; FS[i] = fv; }
             __syncthreads();
             if (tid == 0) {
+              const long long t0 = clock64();
               double sum = 0.0, test = 0.0;
               for (int i = 0; i < m; i++) { const double fv = FS[i]; sum += fv * fv; if (fabs(fv) > test) test = fabs(fv); }
               sc[0] = 0.5 * sum; sc[1] = test;
+              cy_fs += clock64() - t0;
             }
             __syncthreads();
             f = sc[0];
@@ -348,6 +366,7 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
   }
   if (tid == 0) {
     cn.status[1] += iters; cn.status[2] += backtracks; cn.status[3] += maxits;
+    cn.cycles[0] += cy_solve; cn.cycles[1] += cy_ls; cn.cycles[2] += cy_fs; cn.cycles[3] += clock64() - cy_begin;
   }
 }
 
@@ -450,15 +469,22 @@ extern "C" int tribs_gpu_channel_init(tribs_handle_t c, const tribs_channel_t *c
   };
   if (state(&nt.hlevel, ch->hlevel0, S + 1, true) || state(&nt.qstrm, ch->qstrm0, S + 1, true) || state(&nt.velocity, nullptr, S + 1, true) ||
       state(&nt.outlet_hlev, ch->outlet_hlev0, R, false) || dev_alloc(c, &nt.ws, (size_t)kChanWsVecs * (max_n + 2)) ||
-      dev_alloc(c, &nt.status, 4)) {
+      dev_alloc(c, &nt.status, 4) || dev_alloc(c, &nt.cycles, 4)) {
     delete cs;
     return 1;
   }
   CK(cudaMemset(nt.ws, 0, (size_t)kChanWsVecs * (max_n + 2) * sizeof(double)));
   CK(cudaMemset(nt.status, 0, 4 * sizeof(int32_t)));
+  CK(cudaMemset(nt.cycles, 0, 4 * sizeof(long long)));
   cs->shared_rows = (max_n + 2 <= kChanSharedRows + 2) ? max_n + 2 : 0;
   cs->smem = (size_t)4 * cs->shared_rows * sizeof(double);
   CK(cudaFuncSetAttribute(channel_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * (kChanSharedRows + 2) * sizeof(double))));
+  // nothing is allocated or loaded inside a timed batch: the outlet series buffer exists, the kernel's code is resident
+  cs->qout_cap = 1024;
+  if (dev_alloc(c, &cs->d_qout, (size_t)cs->qout_cap)) { delete cs; return 1; }
+  channel_route_kernel<<<1, kChanThreads, cs->smem, c->stream>>>(cs->net, c->d_qeff_now, 0, cs->d_qout, cs->shared_rows);
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(c->stream));
   channel_of(c) = cs;
   return 0;
 }
@@ -494,7 +520,8 @@ extern "C" int tribs_gpu_channel_route(tribs_handle_t c, int n_steps, double *qo
 }
 
 // hlevel / qstrm / velocity: per stream slot (tribs_gpu_stream_cells order) + the basin outlet; outlet_hlev: per reach;
-// counters: Newton iterations, line-search backtracks, reaches that hit MAXITS since init. Any pointer may be NULL.
+// counters[7]: Newton iterations, line-search backtracks, reaches that hit MAXITS since init, then thread 0's clock
+// cycles in the band solve, the line-search sums, the function sums, and the whole kernel. Any pointer may be NULL.
 extern "C" int tribs_gpu_channel_sync(tribs_handle_t c, double *hlevel, double *qstrm, double *velocity, double *outlet_hlev,
                                       int64_t *counters) {
   if (!c) return fail("tribs_gpu_channel_sync: null handle");
@@ -509,6 +536,11 @@ extern "C" int tribs_gpu_channel_sync(tribs_handle_t c, double *hlevel, double *
   int32_t status[4] = {0, 0, 0, 0};
   if (counters) CK(cudaMemcpyAsync(status, cs->net.status, sizeof status, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
-  if (counters) { counters[0] = status[1]; counters[1] = status[2]; counters[2] = status[3]; }
+  if (counters) {
+    counters[0] = status[1]; counters[1] = status[2]; counters[2] = status[3];
+    long long cy[4];
+    CK(cudaMemcpy(cy, cs->net.cycles, sizeof cy, cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 4; k++) counters[3 + k] = cy[k];
+  }
   return 0;
 }

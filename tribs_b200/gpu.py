@@ -459,10 +459,11 @@ class GpuBasin:
         slots = self.n_stream + 1
         out = {"Hlevel": np.empty(slots), "Qstrm": np.empty(slots), "FlowVelocity": np.empty(slots),
                "OutletHlev": np.empty(self.n_reach)}
-        cnt = (C.c_int64 * 3)()
+        cnt = (C.c_int64 * 7)()
         _chk(self.L.tribs_gpu_channel_sync(self.h, _d(out["Hlevel"]), _d(out["Qstrm"]), _d(out["FlowVelocity"]),
                                            _d(out["OutletHlev"]), cnt))
         out["newton_iterations"], out["backtracks"], out["maxits_exceeded"] = int(cnt[0]), int(cnt[1]), int(cnt[2])
+        out["cycles"] = {"band_solve": int(cnt[3]), "line_search_sums": int(cnt[4]), "function_sums": int(cnt[5]), "kernel": int(cnt[6])}
         return out
 
     def owned_range(self):
