@@ -1,13 +1,15 @@
 """Full-size golden vectors for BASELINE.json configs[2], made by the REFERENCE ITSELF: the 10M-cell V-valley
 (build_basin(3163, 3163, seed=1)) under rain gauges + a weather station with Penman-Monteith ET and Rutter
-interception (scenario "met" of tests/refrun.py: the reference's own .sdf/.mdf forcing files, METSTEP 60 min).
+interception (scenario "metday" of tests/refrun.py: the deck "met" beginning at 09:00 with the wet spell at noon; the
+reference's own .sdf/.mdf forcing files, METSTEP 60 min).
 
 Like make_fullsize.py: the basin travels to the reference as OPTMESHINPUT 9 files, the unmodified reference
 (oracle/_ref/tribs_ref_harness) runs it (32 GB, ~4 min set-up, ~20 s per step on one core), and the C oracle
 (unsaturated / saturated zone, routing, ET + interception) has to reproduce the reference's FULL arrays bit for
-bit at both snapshots before the fixture is written. The fixture keeps, per snapshot (steps 64 and 96: the gauges' storm
-begins at hour 3 = step 48, so the window has dry ET, the canopy filling under rain, wetting fronts; six ET sweeps, twelve
-groundwater steps): a sample of cells, 1000-cell block sums of every field, the hydrograph
+bit at both snapshots before the fixture is written. The fixture keeps, per snapshot (steps 40 and 96: the gauges' storm
+begins at hour 3 = step 48, so the window has daytime ET on dry ground, then the canopy filling under rain, wet-canopy
+evaporation, wetting fronts; six ET sweeps, twelve groundwater steps): a sample of cells with the state and the outputs of
+kernel (1), 1000-cell block sums of every state field, the hydrograph
 arrays; plus what turns build_basin()'s dict into the reference's exact inputs (sparse patches, and the
 forcing / land / ET keys whole: they are tiny or compress to nothing).
 

@@ -1,10 +1,10 @@
 """Full-size parity for BASELINE.json configs[2]: the 10M-cell basin under rain gauges + a weather station with
 Penman-Monteith ET and Rutter interception, the configuration bench.py times by default.
 
-tests/golden/fullsize_met_10m.npz holds what the UNMODIFIED REFERENCE leaves after two step counts inside the first six
-hours (`snap_steps`; the storm of the gauges begins at step 48; six ET sweeps, twelve groundwater steps;
-tests/golden/make_fullsize_met.py; the C oracle reproduced the reference's full arrays bit for bit before the fixture was
-written). The device runs the same 96 steps the way bench.py does: pipelined batches with
+tests/golden/fullsize_met_10m.npz holds what the UNMODIFIED REFERENCE leaves after 40 and 96 steps of a run that begins at
+09:00 (`snap_steps`: dry ground under the late-morning sun, then the gauges' storm from step 48 on: wet-canopy evaporation,
+wetting fronts; six ET sweeps, twelve groundwater steps; tests/golden/make_fullsize_met.py, scenario "metday"; the C oracle
+reproduced the reference's full arrays - state and the outputs of kernel (1) - bit for bit before the fixture was written). The device runs the same 96 steps the way bench.py does: pipelined batches with
 kernel (1) as a phase of the batch, the rain as per-gauge values + the static Thiessen map on the device.
 
 Bar (north_star): per-cell Nwt, Nf, Mu ... and the hydrograph within 1e-6 relative."""
@@ -18,7 +18,7 @@ from refrun import ROOT
 pytestmark = pytest.mark.gpu
 
 REL_TOL = 1e-6
-FIXTURE = os.path.join(ROOT, "tests", "golden", "fullsize_met_10m.npz")
+FIXTURE = os.environ.get("TRIBS_FULLSIZE_FIXTURE") or os.path.join(ROOT, "tests", "golden", "fullsize_met_10m.npz")
 
 
 @pytest.mark.skipif(not os.path.exists(FIXTURE), reason="tests/golden/fullsize_met_10m.npz not generated")

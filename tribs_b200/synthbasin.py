@@ -254,6 +254,13 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
     maxtt = float(ttime.max())
     res_limit = int(np.ceil((runtime_h + maxtt) / out_interval)) + 2
 
+    # aspect of a cell = direction of its flow edge, clockwise from north (tEvapoTrans::DeriveAspect, tEvapoTrans.cpp:2723-2756)
+    xg, yg = x.ravel(), y.ravel()
+    dest_g = ((J + dj[kb]) * NX + (I + di[kb]))[order]
+    fx, fy, fl = xg[dest_g] - xg[cell_g], yg[dest_g] - yg[cell_g], slen[np.arange(n), kbo]
+    aspect = np.arccos((fx * 0.0 + fy * fl) / (fl * fl))
+    aspect = np.where(xg[dest_g] < xg[cell_g], 8.0 * math.atan(1.0) - aspect, aspect)
+
     ks, ths, thr, lam, psib, f, ar, uar = soil
     full = lambda v: np.full(n, float(v))
     if n_soil_classes > 1:
@@ -276,7 +283,7 @@ def build_basin(nx: int, ny: int, spacing: float = 30.0, jitter: float = 3.0, se
         "flow_slope": flow_slope, "flow_len": slen[np.arange(n), kbo], "flow_vedglen": flow_vedglen,
         "flow_dest": fdest, "stream_node": remap(stream_node)[order],
         "hillpath": hp, "streampath": sp, "ttime": ttime, "contr_area": contr,
-        "reach": np.zeros(n, np.int32), "aspect": np.zeros(n),
+        "reach": np.zeros(n, np.int32), "aspect": aspect,
         "Ks": ks_a, "ThetaS": full(ths), "ThetaR": full(thr), "PoreSize": lam_a, "AirEBubPres": full(psib),
         "DecayF": full(f), "SatAnRatio": full(ar), "UnsatAnRatio": full(uar),
         "spoke_rowptr": rowptr, "spoke_nbr": nbr.ravel(), "spoke_edge_listpos": listpos,
@@ -392,7 +399,6 @@ def add_met_forcing(basin: dict, hours: int = 48, et_option: int = 1, i_option: 
     land[1, 1:] = spec.land
     nd = np.full(nt, 9999.99)
     basin.update({
-        "aspect": np.where(basin["x"] < xc, 0.5 * np.pi, 1.5 * np.pi),
         "VolHeatCond": np.full(n, spec.soil[9]), "SoilHeatCap": np.full(n, spec.soil[10]),
         "soil_cutoff": basin["ThetaR"] + 1e-3, "root_cutoff": basin["ThetaR"] + 1e-3,
         "land_class": np.ones(n, np.int32), "land_table": land.ravel(),
