@@ -243,7 +243,8 @@ int tribs_gpu_padded_cells(tribs_handle_t h);
 
 /* ---- state of a handle
  * tribs_gpu_snapshot keeps one device-side copy of everything the path evolves (all dynamic, ET, snow fields,
- * pending hillslope inflow bins, tFlowResults arrays, basin accumulators); tribs_gpu_rollback returns to it.
+ * pending hillslope inflow bins, tFlowResults arrays, basin accumulators, and - after tribs_gpu_channel_init - the channel
+ * router's levels, discharges and OutletHlev); tribs_gpu_rollback returns to it.
  * tribs_gpu_save_state / tribs_gpu_load_state write / read the same content as a binary checkpoint on a step
  * boundary (what tRestart / tCNode::writeRestart do for this path, src/tSimulator/tRestart.cpp; per-cell arrays
  * in sweep order, so the file does not depend on the partition layout).

@@ -379,10 +379,67 @@ struct ChannelState {
   size_t smem = 0;
   int shared_rows = 0;
   int64_t launches = 0;
+  double *snap = nullptr;                  // tribs_gpu_snapshot: 3 x slots + n_reach
 };
 
 static ChannelState *&channel_of(tribs_ctx *c) { return c->chan; }
 static void tribs_free_channel(tribs_ctx *c) { delete c->chan; c->chan = nullptr; }   // device memory is in c->allocs
+
+// ---- the channel state in tribs_gpu_snapshot / rollback and in the checkpoint file (checkpoint.cuh)
+static bool channel_present(tribs_ctx *c) { return c->chan != nullptr; }
+static int channel_copy_state(tribs_ctx *c, bool to_snapshot) {
+  ChannelState *cs = c->chan;
+  const size_t S = (size_t)cs->net.slots, R = (size_t)cs->net.n_reach;
+  double *parts[4] = {cs->net.hlevel, cs->net.qstrm, cs->net.velocity, cs->net.outlet_hlev};
+  const size_t counts[4] = {S, S, S, R};
+  size_t off = 0;
+  for (int k = 0; k < 4; k++) {
+    CK(cudaMemcpyAsync(to_snapshot ? cs->snap + off : parts[k], to_snapshot ? parts[k] : cs->snap + off, counts[k] * sizeof(double),
+                       cudaMemcpyDeviceToDevice, c->stream));
+    off += counts[k];
+  }
+  return 0;
+}
+static int channel_snapshot(tribs_ctx *c) {
+  if (!c->chan) return 0;
+  if (!c->chan->snap && dev_alloc(c, &c->chan->snap, (size_t)3 * c->chan->net.slots + c->chan->net.n_reach)) return 1;
+  return channel_copy_state(c, true);
+}
+static int channel_rollback(tribs_ctx *c) {
+  if (!c->chan) return 0;
+  if (!c->chan->snap) return fail("tribs_gpu_rollback: the channel network was attached after the snapshot");
+  return channel_copy_state(c, false);
+}
+static bool channel_write(tribs_ctx *c, FILE *f) {
+  if (!c->chan) return true;
+  ChannelState *cs = c->chan;
+  const int32_t hdr[2] = {cs->net.n_reach, cs->net.slots};
+  if (fwrite("CHAN", 1, 4, f) != 4 || fwrite(hdr, sizeof(int32_t), 2, f) != 2) return false;
+  const double *parts[4] = {cs->net.hlevel, cs->net.qstrm, cs->net.velocity, cs->net.outlet_hlev};
+  const size_t counts[4] = {(size_t)cs->net.slots, (size_t)cs->net.slots, (size_t)cs->net.slots, (size_t)cs->net.n_reach};
+  for (int k = 0; k < 4; k++) {
+    std::vector<double> b(counts[k]);
+    if (cudaMemcpy(b.data(), parts[k], counts[k] * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess) return false;
+    if (fwrite(b.data(), sizeof(double), counts[k], f) != counts[k]) return false;
+  }
+  return true;
+}
+static int channel_read(tribs_ctx *c, FILE *f) {
+  ChannelState *cs = c->chan;
+  char magic[4];
+  int32_t hdr[2];
+  if (fread(magic, 1, 4, f) != 4 || memcmp(magic, "CHAN", 4) != 0 || fread(hdr, sizeof(int32_t), 2, f) != 2)
+    return fail("tribs_gpu_load_state: the channel section of the checkpoint is unreadable");
+  if (hdr[0] != cs->net.n_reach || hdr[1] != cs->net.slots) return fail("tribs_gpu_load_state: the checkpoint's channel network is another one");
+  double *parts[4] = {cs->net.hlevel, cs->net.qstrm, cs->net.velocity, cs->net.outlet_hlev};
+  const size_t counts[4] = {(size_t)cs->net.slots, (size_t)cs->net.slots, (size_t)cs->net.slots, (size_t)cs->net.n_reach};
+  for (int k = 0; k < 4; k++) {
+    std::vector<double> b(counts[k]);
+    if (fread(b.data(), sizeof(double), counts[k], f) != counts[k]) return fail("tribs_gpu_load_state: the channel section of the checkpoint is truncated");
+    CK(cudaMemcpy(parts[k], b.data(), counts[k] * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  return 0;
+}
 
 template <typename T>
 static int chan_upload(tribs_ctx *c, T **dst, const std::vector<T> &h) {

@@ -15,6 +15,13 @@ struct StateSnapshot {
   bool valid = false;
 };
 
+// channel router state (channel.cuh): levels, discharges, velocities per stream slot and OutletHlev per reach
+static int channel_snapshot(tribs_ctx *c);
+static int channel_rollback(tribs_ctx *c);
+static bool channel_present(tribs_ctx *c);
+static bool channel_write(tribs_ctx *c, FILE *f);
+static int channel_read(tribs_ctx *c, FILE *f);
+
 static void state_arrays(tribs_ctx *c, std::vector<double *> &out) {
   out.clear();
   for (int k = 0; k < TRIBS_N_FIELDS; k++) out.push_back(c->dv.f[k]);
@@ -49,6 +56,7 @@ extern "C" int tribs_gpu_snapshot(tribs_handle_t c) {
   CK(cudaMemcpyAsync(sn.qeff_now, c->d_qeff_now, slots * sizeof(double), cudaMemcpyDeviceToDevice, st));
   sn.new_valid = c->new_valid; sn.at_boundary = c->at_boundary; sn.gw_dirty = c->gw_dirty;
   if (c->et && c->et->snow_ready && tribs_gpu_snow_members(c, sn.members, nullptr)) return 1;
+  if (channel_snapshot(c)) return 1;
   sn.valid = true;
   return 0;
 }
@@ -71,11 +79,12 @@ extern "C" int tribs_gpu_rollback(tribs_handle_t c) {
   CK(cudaMemcpyAsync(c->d_qeff_now, sn.qeff_now, slots * sizeof(double), cudaMemcpyDeviceToDevice, st));
   c->new_valid = sn.new_valid; c->at_boundary = sn.at_boundary; c->gw_dirty = sn.gw_dirty;
   if (c->et && c->et->snow_ready && tribs_gpu_snow_set_members(c, sn.members)) return 1;
-  return 0;
+  return channel_rollback(c);
 }
 
 // ---- checkpoint file: "TRIBSCK1", int32 {n_cells, n_arrays, n_slots, ring, n_results, res_limit, n_globals, flags},
-//      2 doubles (snow members), then n_arrays x n_cells doubles (sweep order), ring, results, globals, qeff_now
+//      2 doubles (snow members), then n_arrays x n_cells doubles (sweep order), ring, results, globals, qeff_now; with
+//      flags bit 2: "CHAN", int32 {n_reach, n_slots}, Hlevel, Qstrm, FlowVelocity per stream slot, OutletHlev per reach
 extern "C" int tribs_gpu_save_state(tribs_handle_t c, const char *path) {
   if (!c || !path) return fail("tribs_gpu_save_state: null argument");
   CK(cudaSetDevice(c->device));
@@ -87,7 +96,7 @@ extern "C" int tribs_gpu_save_state(tribs_handle_t c, const char *path) {
   state_arrays(c, arr);
   const int32_t slots = c->n_stream + 1;
   const int32_t hdr[8] = {c->n, (int32_t)arr.size(), slots, c->rc.ring, TRIBS_N_RESULTS, c->rc.res_limit, TRIBS_N_GLOBALS,
-                          (c->new_valid ? 1 : 0) | (c->gw_dirty ? 2 : 0)};
+                          (c->new_valid ? 1 : 0) | (c->gw_dirty ? 2 : 0) | (channel_present(c) ? 4 : 0)};
   double members[2] = {0.88, 0.0};
   if (c->et && c->et->snow_ready && tribs_gpu_snow_members(c, members, nullptr)) { fclose(f); return 1; }
   bool ok = fwrite("TRIBSCK1", 1, 8, f) == 8 && fwrite(hdr, sizeof(int32_t), 8, f) == 8 && fwrite(members, sizeof(double), 2, f) == 2;
@@ -108,6 +117,7 @@ extern "C" int tribs_gpu_save_state(tribs_handle_t c, const char *path) {
   };
   ok = ok && dump(c->d_ring, (size_t)slots * c->rc.ring) && dump(c->d_results, (size_t)TRIBS_N_RESULTS * c->rc.res_limit) &&
        dump(c->d_globals, TRIBS_N_GLOBALS) && dump(c->d_qeff_now, slots);
+  ok = ok && channel_write(c, f);
   ok = (fclose(f) == 0) && ok;
   return ok ? 0 : fail(std::string("tribs_gpu_save_state: write to ") + path + " failed");
 }
@@ -147,6 +157,10 @@ extern "C" int tribs_gpu_load_state(tribs_handle_t c, const char *path) {
   };
   ok = ok && load(c->d_ring, (size_t)slots * c->rc.ring) && load(c->d_results, (size_t)TRIBS_N_RESULTS * c->rc.res_limit) &&
        load(c->d_globals, TRIBS_N_GLOBALS) && load(c->d_qeff_now, slots);
+  if (ok && channel_present(c)) {
+    if (!(hdr[7] & 4)) { fclose(f); return fail("tribs_gpu_load_state: the handle routes its channels on the device, the checkpoint holds no channel state"); }
+    if (channel_read(c, f)) { fclose(f); return 1; }
+  }
   fclose(f);
   if (!ok) return fail(std::string("tribs_gpu_load_state: ") + path + " is truncated or unreadable");
   c->gw_dirty = (hdr[7] & 2) != 0;
