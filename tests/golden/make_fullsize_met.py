@@ -31,13 +31,16 @@ from make_fullsize import BLOCK, apply_patches, block_sums, make_patches  # noqa
 
 SIDE, SEED, RUNTIME_H = 3163, 1, 24.0
 SCENARIO = os.environ.get("TRIBS_FULLSIZE_SCENARIO", "metday")     # tests/refrun.py SCENARIOS: "met" or "metday"
-SNAP_STEPS = (40, 96) if SCENARIO == "metday" else (64, 96)
+SNAP_STEPS = {"metday": (40, 96), "snowplain": (96, 160)}.get(SCENARIO, (64, 96))
 STATE = {"NwtOld": "NwtNew", "MuOld": "MuNew", "MiOld": "MiNew", "NtOld": "NtNew", "NfOld": "NfNew", "RuOld": "RuNew",
          "RiOld": "RiNew", "Qpout": "Qpout", "cumsrf": "cumsrf", "intstorm": "intstorm", "NetPrecipitation": "NetPrecipitation",
          "EvapSoil": "EvapSoil", "EvapDryCanopy": "EvapDryCanopy", "Rain": "Rain"}
 # outputs of kernel (1) kept beside the water-balance state (device: the ET field block, tribs_gpu_et_sync)
 ET_STATE = ["PotEvap", "ActEvap", "EvapoTrans", "EvapWetCanopy", "CanStorage", "CumIntercept", "SurfTemp", "NetRad", "LFlux", "HFlux",
             "GFlux"]
+if SCENARIO == "snowplain":     # BASELINE configs[4]: the snow pack replaces both ET sweeps (tSnowPack::callSnowPack)
+    ET_STATE = ["LiqWE", "IceWE", "SnTempC", "LiqRouted", "SnSub", "SnEvap", "CumMelt", "PeakSWE", "DU", "Unode", "SnLHF", "SnSHF", "SnGHF",
+                "SnPHF", "SnRLin", "SnRLout", "SnRSin", "CrustAge", "DensityAge", "CumHrsSnow", "AirTemp", "NetRad"]
 RESULTS = ["mhydro", "HsrfRout", "SbsrfRout", "SatsrfRout"]
 
 

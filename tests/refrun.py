@@ -45,6 +45,10 @@ SCENARIOS = {
 # wet spell at noon - daytime ET on dry ground, then evaporation from a wet canopy
 EXTRA_SCENARIOS = {
     "metday": dict(runtime_h=48.0, forcing="met", gw_depth_mm=1500.0, pmean=12.0, stdur=5.0, start_hour=9, rain_hour=12),
+    # BASELINE configs[4] in small: winter station, OPTSNOW 1 without a canopy, shallow water table; begins at 06:00, snow
+    # falls from 08:00 on while the air warms through 0 degC towards noon
+    "snowplain": dict(runtime_h=72.0, forcing="met", winter=True, gw_depth_mm=600.0, pmean=6.0, stdur=5.0, start_hour=6,
+                      rain_hour=8, extra={"OPTINTERCEPT": 0}),
 }
 
 
