@@ -5,6 +5,7 @@
 // in sweep order, which is one valid schedule of the device sweep.
 #include "../../tribs_b200/csrc/cell_update.cuh"
 #include "../../tribs_b200/csrc/snow_update.cuh"
+#include "../../tribs_b200/csrc/channel_solve.cuh"
 #include <vector>
 #include <algorithm>
 #include <cstring>
@@ -196,5 +197,32 @@ void hc_et_step(int n, const int32_t *ci, const double *cd, double **est, const 
   if (last_alb[n] > 0) members[0] = val_alb[buf][last_alb[n] - 1];
   if (last_can[n] > 0) members[1] = val_can[buf][last_can[n] - 1];
   snow[6] = rounds;
+}
+
+// Channel router: the two linear solvers of channel_solve.cuh on one tridiagonal system (0-based sub / dia / sup, rhs f).
+// x_ref: the reference's order (pivoted band elimination, one thread); x_part: the partition form, lanes looped.
+void hc_chan_solve(int N, const double *sub, const double *dia, const double *sup, const double *f, double *x_ref, double *x_part, int *parts) {
+  std::vector<double> A1(N + 2), A2(N + 2), A3(N + 2), B(N + 2), V(N + 2), W(N + 2);
+  for (int i = 0; i < N; i++) {
+    const int k = i + 1;
+    if (k == 1) { A1[1] = dia[0]; A2[1] = sup[0]; A3[1] = 0.0; }
+    else { A1[k] = sub[i]; A2[k] = dia[i]; A3[k] = (k == N) ? 999. : sup[i]; }
+    B[k] = f[i];
+  }
+  chan_band_eliminate(A1.data(), A2.data(), A3.data(), B.data(), N);
+  for (int k = 1; k <= N; k++) A1[k] = 1.0 / A1[k];
+  chan_band_back(A1.data(), A2.data(), A3.data(), B.data(), N);
+  for (int i = 0; i < N; i++) x_ref[i] = B[i + 1];
+  const int P = chan_part_count(N);
+  *parts = P;
+  for (int i = 0; i < N; i++) B[i + 1] = f[i];
+  for (int p = 0; p < P; p++) {
+    int first, last;
+    chan_part_range(N, P, p, &first, &last);
+    chan_part_chunk(sub, dia, sup, A1.data(), A2.data(), A3.data(), B.data(), V.data(), W.data(), first, last, p > 0, p < P - 1);
+  }
+  std::vector<double> M((size_t)(2 * P) * (2 * P + 1)), X(2 * P);
+  chan_part_interface(B.data(), V.data(), W.data(), N, P, M.data(), X.data());
+  for (int i = 0; i < N; i++) x_part[i] = chan_part_assemble(B.data(), V.data(), W.data(), X.data(), N, P, i + 1);
 }
 }

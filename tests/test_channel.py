@@ -45,3 +45,50 @@ def test_oracle_channel_router_is_bit_exact(name):
         assert np.array_equal(ch.outlet_hlev, ref["OutletHlev"][s]), s
         assert ch.hlevel[n] == ref["outlet_Hlevel"][s] and ch.qstrm[n] == ref["outlet_Qstrm"][s], s
     assert ch.iters > 0
+
+
+def test_partition_solver_matches_the_reference_order_solver(built):
+    """channel_solve.cuh compiled with g++: the partition form of the Newton step's linear solve (chunks eliminated side by
+    side, a small interface system, assembly) against the reference-order pivoted band solve and against LAPACK, on
+    Jacobians of the kinematic-wave system (diagonal ~ b/dt, off-diagonals +-K h^(2/3): pivoting in almost every row) and
+    on random tridiagonal systems, sizes from 2 rows to the 10M-cell basin's reach."""
+    import ctypes as C
+    import os
+    from refrun import ROOT
+    L = C.CDLL(os.path.join(ROOT, "tests", "hostcheck", "libhostcheck.so"))
+    PD = C.POINTER(C.c_double)
+    L.hc_chan_solve.argtypes = [C.c_int, PD, PD, PD, PD, PD, PD, C.POINTER(C.c_int)]
+    rng = np.random.default_rng(7)
+    worst = 0.0
+    for n in (2, 3, 11, 12, 23, 24, 25, 100, 383, 384, 385, 1000, 3163):
+        for kind in ("jacobian", "random", "dominant"):
+            if kind == "jacobian":
+                h = rng.uniform(0.0, 3.0, n + 2) ** (2.0 / 3.0)
+                K = rng.uniform(0.5, 30.0)
+                dia = rng.uniform(0.5, 1.5, n)
+                sup = (5.0 / 6.0) * K * h[2:] + 0.2
+                sub = -(5.0 / 6.0) * K * h[:n] + 0.2
+            elif kind == "random":
+                dia, sup, sub = (rng.normal(size=n) for _ in range(3))
+                dia = dia + np.sign(dia) * 0.3
+            else:
+                sup, sub = rng.normal(size=n), rng.normal(size=n)
+                dia = 4.0 + np.abs(sup) + np.abs(sub)
+            f = rng.normal(size=n)
+            from scipy.linalg import solve_banded
+            ab = np.zeros((3, n))
+            ab[0, 1:], ab[1], ab[2, :-1] = sup[:-1], dia, sub[1:]
+            x = solve_banded((1, 1), ab, f)                  # LAPACK dgbsv: partial pivoting
+            resid = np.abs(dia * x + np.r_[sup[:-1] * x[1:], 0.0] + np.r_[0.0, sub[1:] * x[:-1]] - f).max()
+            if resid > 1e-9 * max(1.0, np.abs(x).max()):     # too ill-conditioned to serve as a reference
+                continue
+            xr, xp, parts = np.empty(n), np.empty(n), C.c_int(0)
+            arrs = [np.ascontiguousarray(a, np.float64) for a in (sub, dia, sup, f)]
+            L.hc_chan_solve(n, *[a.ctypes.data_as(PD) for a in arrs], xr.ctypes.data_as(PD), xp.ctypes.data_as(PD), C.byref(parts))
+            scale = np.abs(x).max()
+            e_ref, e_part = np.abs(xr - x).max() / scale, np.abs(xp - x).max() / scale
+            tol = 1e-9 if kind != "random" else 1e-6        # random systems can be badly conditioned
+            assert e_ref <= tol and e_part <= tol, (n, kind, parts.value, e_ref, e_part)
+            assert parts.value == min(32, max(1, n // 12))
+            worst = max(worst, e_part)
+    assert worst > 0.0

@@ -12,14 +12,19 @@
 //
 // Layout: one 1024-thread block. The work is a chain (steps x reaches in list order x Newton iterations x a pivoted
 // banded LU), a few thousand unknowns per reach: everything element-wise (function values with their x^(5/3), the
-// Jacobian, the trial levels of the line search, maxima) is spread over the block, the order-dependent parts - the LU with
-// its forward / backward substitution and the three sums of the line search - run in thread 0 from shared memory in
-// the reference's order. FP64 throughout; differs from the reference through the library's pow() and through the back
-// substitution, which multiplies by reciprocal pivots (see chan_band_back).
+// Jacobian, the trial levels of the line search, maxima) is spread over the block; the pivoted LU of the Newton step is cut
+// into up to 32 chunks eliminated side by side on the lanes of one warp plus a small interface system (channel_solve.cuh:
+// the reference's single chain of N rows costs ~420 cycles per row on this GPU); the three sums of the line search run in
+// thread 0 from shared memory in the reference's order. FP64 throughout; differs from the reference through the library's
+// pow() and through the order of operations of the linear solve (1e-15 relative on the step).
 #pragma once
 
+#include "channel_solve.cuh"
+
 constexpr int kChanThreads = 1024;
-constexpr int kChanSharedRows = 7000;      // 4 vectors of (rows + 2) doubles in shared memory: 224 KB
+constexpr int kChanSharedVecs = 6;         // band rows (3), right-hand sides y / v / w of the partition solve (3)
+constexpr int kChanInterface = 2 * kChanMaxParts * (2 * kChanMaxParts + 1) + 2 * kChanMaxParts;   // interface matrix + unknowns
+constexpr int kChanSharedRows = (226 * 1024 / 8 - kChanInterface - 256) / kChanSharedVecs;       // rows (+2) per vector that fit
 
 struct ChanNet {
   int n_reach, max_n, slots;               // slots = stream slots + the basin outlet
@@ -32,7 +37,7 @@ struct ChanNet {
   int32_t *status;                         // [0] first error, [1] Newton iterations, [2] backtracks, [3] MAXITS exceeded
   long long *cycles;                       // thread 0's clock64() spent in [0] band solve, [1] line-search sums, [2] function sums, [3] whole kernel
 };
-constexpr int kChanWsVecs = 14;
+constexpr int kChanWsVecs = 16;
 
 __device__ __forceinline__ double chan_block_max(double v, double *red) {
   for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
@@ -87,57 +92,6 @@ __device__ double chan_two_node_root(double c1, double c2, double c3, double x1,
   return 0.0;
 }
 
-// bandec + banbks for one sub- and one super-diagonal (tKinemat.cpp:2154-2230), rows 1..N in A1..A3 (already in the
-// shifted form bandec makes of row 1), right-hand side B[1..N].
-// Elimination (thread 0): the reference's operations in the reference's order, with the forward substitution of the
-// right-hand side riding along. The pivot row travels in registers and the next row is loaded before the division it
-// does not depend on, so the chain per row is one IEEE division and one multiply-subtract. A dependent FP64 operation
-// costs ~20 cycles here, the division nine of them: that chain is what the kernel's time is made of.
-__device__ void chan_band_eliminate(double *A1, double *A2, double *A3, double *B, int N) {
-  double r1 = A1[1], r2 = A2[1], r3 = A3[1], rb = B[1];
-  double n1 = A1[2], n2 = A2[2], n3 = A3[2], nb = B[2];          // N >= 2
-  for (int k = 1; k < N; k++) {
-    const int kn = min(k + 2, N);                                  // row after the next (its values are still the original ones)
-    const double m1 = A1[kn], m2 = A2[kn], m3 = A3[kn], mb = B[kn];
-    if (fabs(n1) > fabs(r1)) {                                     // partial pivoting over the two candidate rows
-      double t;
-      t = r1; r1 = n1; n1 = t;
-      t = r2; r2 = n2; n2 = t;
-      t = r3; r3 = n3; n3 = t;
-      t = rb; rb = nb; nb = t;
-    } else if (r1 == 0.0)
-      r1 = 1.0E-20;
-    const double dum = n1 / r1;
-    A1[k] = r1; A2[k] = r2; A3[k] = r3; B[k] = rb;
-    r1 = n2 - dum * r2;
-    r2 = n3 - dum * r3;
-    r3 = 0.0;
-    rb = nb - dum * rb;
-    n1 = m1; n2 = m2; n3 = m3; nb = mb;
-  }
-  if (r1 == 0.0) r1 = 1.0E-20;
-  A1[N] = r1; A2[N] = 0.0; A3[N] = 0.0; B[N] = rb;
-}
-// Back substitution (thread 0): x[i] = (b[i] - a2[i] x[i+1] - a3[i] x[i+2]) / a1[i], with the division replaced by a
-// multiplication with the reciprocal pivot that all threads computed beforehand (R1 = 1 / a1, IEEE division, off the
-// chain): three to five dependent operations per row instead of twelve. This is the one place where the arithmetic is
-// not the reference's: x differs from a correctly rounded quotient by at most one unit in the last place.
-__device__ void chan_band_back(const double *R1, const double *A2, const double *A3, double *B, int N) {
-  double x1 = B[N] * R1[N], x2 = 0.0;
-  B[N] = x1;
-  double c1 = R1[N - 1], c2 = A2[N - 1], c3 = A3[N - 1], cb = B[N - 1];
-  for (int i = N - 1; i >= 1; i--) {
-    const int ip = max(i - 1, 1);
-    const double p1 = R1[ip], p2 = A2[ip], p3 = A3[ip], pb = B[ip];
-    double dum = cb - c2 * x1;
-    if (i <= N - 2) dum -= c3 * x2;
-    const double x = dum * c1;
-    B[i] = x;
-    x2 = x1; x1 = x;
-    c1 = p1; c2 = p2; c3 = p3; cb = pb;
-  }
-}
-
 __global__ void __launch_bounds__(kChanThreads, 1)
 channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *qout, int shared_rows) {
   extern __shared__ double chan_sm[];
@@ -147,10 +101,13 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
   const size_t stride = (size_t)cn.max_n + 2;
   double *X = cn.ws, *X1 = X + stride, *Fg = X1 + stride, *aa = Fg + stride, *bb = aa + stride, *cc = bb + stride,
          *reis = cc + stride, *his = reis + stride, *gA1 = his + stride, *gA2 = gA1 + stride, *gA3 = gA2 + stride,
-         *gB = gA3 + stride, *XP = gB + stride;     // XP: X^(5/3) for the function, X^(2/3) for the Jacobian
+         *gB = gA3 + stride, *XP = gB + stride,     // XP: X^(5/3) for the function, X^(2/3) for the Jacobian
+         *gV = XP + stride, *gW = gV + stride;
   const bool in_shared = (int)stride <= shared_rows;
-  double *A1 = in_shared ? chan_sm : gA1, *A2 = in_shared ? chan_sm + stride : gA2, *A3 = in_shared ? chan_sm + 2 * stride : gA3,
-         *B = in_shared ? chan_sm + 3 * stride : gB;
+  double *IM = chan_sm, *IX = IM + 2 * kChanMaxParts * (2 * kChanMaxParts + 1);       // interface system of the partition solve
+  double *vec = chan_sm + kChanInterface;
+  double *A1 = in_shared ? vec : gA1, *A2 = in_shared ? vec + stride : gA2, *A3 = in_shared ? vec + 2 * stride : gA3,
+         *B = in_shared ? vec + 3 * stride : gB, *V = in_shared ? vec + 4 * stride : gV, *W = in_shared ? vec + 5 * stride : gW;
   double *G = A1, *FS = A2;         // after the solve: gradient and function values where thread 0 sums them
   const double rif = cn.roughness;
   const double TOLF = 1.0e-4, TOLX = 1.0e-7, STPMX = 100.0, ALF = 1.0e-4;
@@ -219,19 +176,27 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
             else b_i = fk1 * c[m] * XP[i] + y2[m - 1];
             if (i >= 1) a_i = -fk1 * c[i] * XP[i - 1] + y3[i];
             aa[i] = a_i; bb[i] = b_i; cc[i] = c_i;
-            const int k = i + 1;                                    // 1-based row
-            if (k == 1) { A1[1] = b_i; A2[1] = c_i; A3[1] = 0.0; }   // bandec's left shift of row 1
-            else { A1[k] = a_i; A2[k] = b_i; A3[k] = (k == m) ? 999. : c_i; }
+            const int k = i + 1;                                    // 1-based row: sub-diagonal, diagonal, super-diagonal
+            A1[k] = a_i; A2[k] = b_i; A3[k] = c_i;
             const double fv = Fg[i];
             B[k] = (fv == 0) ? fv : -fv;
           }
           __syncthreads();
-          if (tid == 0) { const long long t0 = clock64(); chan_band_eliminate(A1, A2, A3, B, m); cy_solve += clock64() - t0; }
+          // partition solve (channel_solve.cuh): chunks side by side on the lanes of warp 0, the interface system on
+          // thread 0, the assembly on everybody
+          const int P = chan_part_count(m);
+          const long long t0 = clock64();
+          if (tid < P) {
+            int first, last;
+            chan_part_range(m, P, tid, &first, &last);
+            chan_part_chunk(A1 + 1, A2 + 1, A3 + 1, A1, A2, A3, B, V, W, first, last, tid > 0, tid < P - 1);
+          }
           __syncthreads();
-          for (int k = 1 + tid; k <= m; k += T) A1[k] = 1.0 / A1[k];
+          if (tid == 0) chan_part_interface(B, V, W, m, P, IM, IX);
           __syncthreads();
-          if (tid == 0) { const long long t0 = clock64(); chan_band_back(A1, A2, A3, B, m); cy_solve += clock64() - t0; }
+          for (int k = 1 + tid; k <= m; k += T) B[k] = chan_part_assemble(B, V, W, IX, m, P, k);
           __syncthreads();
+          if (tid == 0) cy_solve += clock64() - t0;
           const double *p = B + 1;
           for (int i = tid; i < m; i += T) {                        // grad(f) = F*J, and the levels of the preceding iteration
             double g;
@@ -533,9 +498,12 @@ extern "C" int tribs_gpu_channel_init(tribs_handle_t c, const tribs_channel_t *c
   CK(cudaMemset(nt.ws, 0, (size_t)kChanWsVecs * (max_n + 2) * sizeof(double)));
   CK(cudaMemset(nt.status, 0, 4 * sizeof(int32_t)));
   CK(cudaMemset(nt.cycles, 0, 4 * sizeof(long long)));
-  cs->shared_rows = (max_n + 2 <= kChanSharedRows + 2) ? max_n + 2 : 0;
-  cs->smem = (size_t)4 * cs->shared_rows * sizeof(double);
-  CK(cudaFuncSetAttribute(channel_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)4 * (kChanSharedRows + 2) * sizeof(double))));
+  // the six vectors of the linear solve live in shared memory when the longest reach fits (about 4 700 nodes), else in the
+  // workspace in global memory (slower, same results)
+  cs->shared_rows = (max_n + 2 <= kChanSharedRows) ? max_n + 2 : 0;
+  cs->smem = ((size_t)kChanInterface + (size_t)kChanSharedVecs * cs->shared_rows) * sizeof(double);
+  CK(cudaFuncSetAttribute(channel_route_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                          (int)(((size_t)kChanInterface + (size_t)kChanSharedVecs * kChanSharedRows) * sizeof(double))));
   // nothing is allocated or loaded inside a timed batch: the outlet series buffer exists, the kernel's code is resident
   cs->qout_cap = 1024;
   if (dev_alloc(c, &cs->d_qout, (size_t)cs->qout_cap)) { delete cs; return 1; }
