@@ -97,6 +97,24 @@ def test_channel_router_after_batches_matches_reference(built, name, ranks):
     (lp.close() if ranks > 1 else sims[0].dev.close())
 
 
+def test_channel_router_with_its_vectors_in_global_memory(built, monkeypatch):
+    """Reaches longer than about 4 000 nodes do not fit the shared-memory layout of the linear solve; the kernel then works
+    on its global workspace. Same results (forced here on the small basin)."""
+    monkeypatch.setenv("TRIBS_CHAN_GLOBAL_VECTORS", "1")
+    from tribs_b200.model import Simulator
+    basin, ref = channel_golden("channel_single")
+    sim = Simulator(basin, rain_schedule=schedule_for(basin))
+    sim.flow.route_channels(basin)
+    sl = slots_of(sim.dev, ref)
+    worst = {}
+    for done in range(40, 201, 40):
+        sim.run_batch(40)
+        compare_state(sim.dev, ref, done - 1, sl, worst)
+    worst["qout"] = worst_of(ref["qout"][:200], np.array(sim.flow.qout_series), FLOOR["qout"])
+    assert max(worst.values()) <= REL_TOL and ref["qout"][:200].max() > 0.5, worst
+    sim.dev.close()
+
+
 def test_channel_init_refuses_what_is_not_built(built):
     from tribs_b200.channel import channel_network
     from tribs_b200.model import Simulator
