@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define TRIBS_GPU_ABI_VERSION 3   /* 3: tribs_part_t (peer-memory partitions), rain gauges, tribs_gpu_pending_qeff */
+#define TRIBS_GPU_ABI_VERSION 4   /* 3: tribs_part_t (peer-memory partitions), rain gauges, tribs_gpu_pending_qeff; 4: tribs_channel_t, tribs_gpu_channel_* */
 
 typedef struct tribs_ctx *tribs_handle_t;
 

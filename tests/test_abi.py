@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol(built):
     assert sorted(gpu.EXPORTS) == names
     import re as _re
     want = int(_re.search(r"#define\s+TRIBS_GPU_ABI_VERSION\s+(\d+)", open(f"{ROOT}/include/tribs_gpu.h").read()).group(1))
-    assert L.tribs_gpu_abi_version() == want == 3
+    assert L.tribs_gpu_abi_version() == want == 4
 
 
 def test_field_table_matches_between_header_and_binding(built):
@@ -67,7 +67,8 @@ def test_ctypes_structs_have_the_layout_of_the_c_header(tmp_path):
     from tribs_b200 import gpu
     pairs = [("tribs_mesh_t", gpu.Mesh), ("tribs_params_t", gpu.Params), ("tribs_state_t", gpu.StateT),
              ("tribs_part_t", gpu.Part), ("tribs_step_t", gpu.Step), ("tribs_et_params_t", gpu.EtParams),
-             ("tribs_met_t", gpu.MetT), ("tribs_et_step_t", gpu.EtStep), ("tribs_snow_params_t", gpu.SnowParams)]
+             ("tribs_met_t", gpu.MetT), ("tribs_et_step_t", gpu.EtStep), ("tribs_snow_params_t", gpu.SnowParams),
+             ("tribs_channel_t", gpu.Channel)]
     lines = ['#include <stdio.h>', '#include <stddef.h>', f'#include "{ROOT}/include/tribs_gpu.h"', "int main(void) {"]
     for cname, cls in pairs:
         lines.append(f'  printf("{cname} %zu\\n", sizeof({cname}));')
