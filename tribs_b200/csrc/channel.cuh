@@ -14,9 +14,9 @@
 // banded LU), a few thousand unknowns per reach: everything element-wise (function values with their x^(5/3), the
 // Jacobian, the trial levels of the line search, maxima) is spread over the block; the pivoted LU of the Newton step is cut
 // into up to 32 chunks eliminated side by side on the lanes of one warp plus a small interface system (channel_solve.cuh:
-// the reference's single chain of N rows costs ~420 cycles per row on this GPU); the three sums of the line search run in
-// thread 0 from shared memory in the reference's order. FP64 throughout; differs from the reference through the library's
-// pow() and through the order of operations of the linear solve (1e-15 relative on the step).
+// the reference's single chain of N rows costs ~420 cycles per row on this GPU); the sums of the line search (|F|^2, p.p,
+// grad.p) are added up by one warp each in a fixed order (chan_warp_sum). FP64 throughout; differs from the reference through
+// the library's pow() and through the order of operations of the linear solve and of those sums (1e-15 relative).
 #pragma once
 
 #include "channel_solve.cuh"
@@ -47,6 +47,19 @@ __device__ __forceinline__ double chan_block_max(double v, double *red) {
   double r = red[0];
   for (int w = 1; w < (int)(blockDim.x >> 5); w++) r = fmax(r, red[w]);
   return r;
+}
+
+// A sum over 0..m-1 by one warp in a fixed order: every lane adds up its contiguous chunk, the 32 partial sums are then
+// added in lane order. Not the reference's left-to-right order (the sums only feed the step-length decisions of the line
+// search), but the same on every run. Call with all 32 lanes of a warp; every lane receives the total.
+template <typename Term>
+__device__ __forceinline__ double chan_warp_sum(int m, Term term) {
+  const int lane = threadIdx.x & 31, per = (m + 31) / 32, lo = lane * per, hi = min(m, lo + per);
+  double s = 0.0;
+  for (int i = lo; i < hi; i++) s += term(i);
+  double tot = 0.0;
+  for (int l = 0; l < 32; l++) tot += __shfl_sync(0xffffffffu, s, l);
+  return tot;
 }
 
 // tKinemat.cpp:1950-1998 for element i; X = levels of nodes 1..m at (t+1) and XP = X^(5/3) (the reference's XFK2 array),
@@ -151,18 +164,23 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
       } else {                                                     // KinematWave
         for (int i = tid; i < m; i += T) { const double x = his[i + 1]; X[i] = X1[i] = x; A3[i] = x; XP[i] = pow(x, fk2); }
         __syncthreads();
-        for (int i = tid; i < m; i += T) { const double f = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = f; FS[i] = f; }
-        __syncthreads();
-        if (tid == 0) {
-          double sum = 0.0, test = 0.0, sx = 0.0;
-          for (int i = 0; i < m; i++) { const double f = FS[i]; sum += f * f; if (fabs(f) > test) test = fabs(f); }
-          for (int i = 0; i < m; i++) { const double x = A3[i]; sx += x * x; }
-          sc[0] = 0.5 * sum; sc[1] = test; sc[2] = STPMX * fmax(sqrt(sx), (double)m);
+        double fmx = 0.0;
+        for (int i = tid; i < m; i += T) {
+          const double f = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp);
+          Fg[i] = f; FS[i] = f; fmx = fmax(fmx, fabs(f));
+        }
+        const double ftest0 = chan_block_max(fmx, red);          // (barriers inside: FS and A3 are complete behind it)
+        if (tid < 32) {
+          const double sum = chan_warp_sum(m, [&](int i) { const double v = FS[i]; return v * v; });
+          if (tid == 0) sc[0] = 0.5 * sum;
+        } else if (tid < 64) {
+          const double sx = chan_warp_sum(m, [&](int i) { const double v = A3[i]; return v * v; });
+          if (tid == 32) sc[2] = STPMX * fmax(sqrt(sx), (double)m);
         }
         __syncthreads();
         double f = sc[0];
         const double stpmax = sc[2];
-        bool done = sc[1] < 0.01 * TOLF;                           // the old levels already solve the system: nothing is written
+        bool done = ftest0 < 0.01 * TOLF;                          // the old levels already solve the system: nothing is written
         bool converged_levels = false;
         int iter = 1;
         for (; !done && iter <= 200; iter++) {
@@ -212,25 +230,23 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
           double tloc = 0.0;
           // the two sums are independent chains: two threads walk them side by side (a scaled step - never seen on the
           // test basins - redoes the slope after the scaling, as the reference's order of operations requires)
-          if (tid == 0) {
+          if (tid < 32) {
             const long long t0 = clock64();
-            double sum = 0.0;
-            for (int i = 0; i < m; i++) sum += p[i] * p[i];
-            sc[4] = sqrt(sum);
-            cy_ls += clock64() - t0;
-          } else if (tid == 32) {
-            double slope = 0.0;
-            for (int i = 0; i < m; i++) slope += G[i] * p[i];
-            sc[3] = slope;
+            const double sum = chan_warp_sum(m, [&](int i) { const double v = p[i]; return v * v; });
+            if (tid == 0) { sc[4] = sqrt(sum); cy_ls += clock64() - t0; }
+          } else if (tid < 64) {
+            const double slope = chan_warp_sum(m, [&](int i) { return G[i] * p[i]; });
+            if (tid == 32) sc[3] = slope;
           }
           __syncthreads();
-          if (sc[4] > stpmax) {
-            if (tid == 0) {
-              const double sum = sc[4];
-              for (int i = 0; i < m; i++) B[i + 1] *= stpmax / sum;
-              double slope = 0.0;
-              for (int i = 0; i < m; i++) slope += G[i] * p[i];
-              sc[3] = slope;
+          if (sc[4] > stpmax) {                                     // scale the step, then the slope of the scaled step
+            const double scale = stpmax / sc[4];
+            __syncthreads();
+            for (int i = tid; i < m; i += T) B[i + 1] *= scale;
+            __syncthreads();
+            if (tid < 32) {
+              const double slope = chan_warp_sum(m, [&](int i) { return G[i] * p[i]; });
+              if (tid == 0) sc[3] = slope;
             }
             __syncthreads();
           }
@@ -253,14 +269,16 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
               XP[i] = pow(x, fk2);
             }
             __syncthreads();
-            for (int i = tid; i < m; i += T) { const double fv = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp); Fg[i] = fv; FS[i] = fv; }
-            __syncthreads();
-            if (tid == 0) {
+            double tmx = 0.0;
+            for (int i = tid; i < m; i += T) {
+              const double fv = chan_function(i, m, X1, XP, his, c, y1, y2, y3, reis, qit, hupp);
+              Fg[i] = fv; FS[i] = fv; tmx = fmax(tmx, fabs(fv));
+            }
+            const double trial_max = chan_block_max(tmx, red);
+            if (tid < 32) {
               const long long t0 = clock64();
-              double sum = 0.0, test = 0.0;
-              for (int i = 0; i < m; i++) { const double fv = FS[i]; sum += fv * fv; if (fabs(fv) > test) test = fabs(fv); }
-              sc[0] = 0.5 * sum; sc[1] = test;
-              cy_fs += clock64() - t0;
+              const double sum = chan_warp_sum(m, [&](int i) { const double v = FS[i]; return v * v; });
+              if (tid == 0) { sc[0] = 0.5 * sum; sc[1] = trial_max; cy_fs += clock64() - t0; }
             }
             __syncthreads();
             f = sc[0];
