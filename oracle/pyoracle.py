@@ -410,13 +410,13 @@ from tribs_b200.channel import channel_network  # noqa: E402  (host-side flatten
 class OracleChannel:
     """One tKinemat::RunRoutingModel call per step (without its hillslope half, which OracleModel.route is)."""
 
-    def __init__(self, basin: dict):
+    def __init__(self, basin: dict, net: dict | None = None):
         self.L = lib()
         self.L.orc_channel_step.argtypes = [C.POINTER(_Channel), C.POINTER(_ChannelState), PD, C.c_double, PD,
                                             C.POINTER(C.c_int)]
         self.L.orc_channel_step.restype = C.c_int
         assert int(basin["chan_percolation"][0]) == 0 and int(basin["chan_optres"][0]) == 0
-        self.net = net = channel_network(basin)
+        self.net = net = channel_network(basin) if net is None else net
         n = net["n_cells"]
         self.n_reach = len(net["off"]) - 1
         self.hlevel, self.qstrm, self.velocity = np.zeros(n + 1), np.zeros(n + 1), np.zeros(n + 1)

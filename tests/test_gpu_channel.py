@@ -97,6 +97,44 @@ def test_channel_router_after_batches_matches_reference(built, name, ranks):
     (lp.close() if ranks > 1 else sims[0].dev.close())
 
 
+def test_two_node_reaches_and_uniform_width_match_the_oracle(built):
+    """tKinemat::SolveForTwoNodeReach (tKinemat.cpp:1736-1765: a reach of a head and its outlet, solved by rtsafe on one
+    polynomial) and CHANNELWIDTH as a uniform width (1227-1228). The decks of this repo never produce such reaches, so the
+    single reach of the golden basin is cut into a two-node reach, a three-node reach and the rest (confluences are the
+    heads of the next reaches), and the device is compared with the C restatement on the same lists."""
+    from oracle.pyoracle import OracleChannel
+    from common import OracleStepper
+    from tribs_b200.channel import channel_network
+    from tribs_b200.model import Simulator
+    basin, _ = channel_golden("channel_single")
+    net = channel_network(basin)
+    cuts = [(0, 2), (1, 4), (3, len(net["node"]))]             # entry ranges; a cut repeats the confluence node
+    sel = np.concatenate([np.arange(a, b) for a, b in cuts])
+    net2 = dict(net, off=np.cumsum([0] + [b - a for a, b in cuts]).astype(np.int32), node=net["node"][sel].copy(),
+                width=net["width"][sel].copy(), length=net["length"][sel].copy(), slope=net["slope"][sel].copy(),
+                uniform_width=1.5)
+    sim = Simulator(basin, rain_schedule=schedule_for(basin))
+    sim.flow.route_channels(basin, net=net2)
+    o, ch = OracleStepper(basin, schedule_for(basin)), OracleChannel(basin, net=net2)
+    q_ref = []
+    for _ in range(5):
+        sim.run_batch(32)
+        for _ in range(32):
+            o.advance(); o.unsat()
+            if o.gw_due():
+                o.sat()
+            o.m.route()
+            q_ref.append(ch.step(o.m.retrieve_qeff()))
+            o.balance(); o.reset()
+        got, stream = sim.dev.channel_sync(), sim.dev.stream_cells()
+        for f, ref in (("Hlevel", ch.hlevel), ("Qstrm", ch.qstrm), ("FlowVelocity", ch.velocity)):
+            assert worst_of(ref[stream], got[f][:-1], 1e-6) <= REL_TOL, f
+        assert worst_of(ch.outlet_hlev, got["OutletHlev"], 1e-6) <= REL_TOL
+    q_ref = np.array(q_ref)
+    assert q_ref.max() > 0.3 and worst_of(q_ref, np.array(sim.flow.qout_series), 1e-6) <= REL_TOL
+    sim.dev.close()
+
+
 def test_channel_router_with_its_vectors_in_global_memory(built, monkeypatch):
     """Reaches longer than about 4 000 nodes do not fit the shared-memory layout of the linear solve; the kernel then works
     on its global workspace. Same results (forced here on the small basin)."""

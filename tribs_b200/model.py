@@ -171,9 +171,10 @@ class tKinemat:
         self.Qout = 0.0
         self.qout_series: list[float] = []
 
-    def route_channels(self, basin: dict):
+    def route_channels(self, basin: dict, net: dict | None = None):
         """Hands tKinemat's reach lists, channel geometry and initial levels to the device (tKinemat.cpp:826-830,
-        1136-1252). From here on SurfaceFlow() / Simulator.run_batch() route the channels as well."""
+        1136-1252). From here on SurfaceFlow() / Simulator.run_batch() route the channels as well. `net`: reach lists other
+        than the basin's own (channel.channel_network's layout)."""
         from .channel import channel_network
         n = int(basin["n_active"][0])
 
@@ -183,7 +184,7 @@ class tKinemat:
             a = np.zeros(n + 1)
             a[:n] = np.asarray(basin[key], float)[:n]
             return a
-        self.dev.channel_init(channel_network(basin), self.timer.getTimeStep() * 3600.0, init("init_Hlevel"), init("init_Qstrm"),
+        self.dev.channel_init(channel_network(basin) if net is None else net, self.timer.getTimeStep() * 3600.0, init("init_Hlevel"), init("init_Qstrm"),
                               percolation_option=int(basin["chan_percolation"][0]) if "chan_percolation" in basin else 0,
                               reservoir_option=int(basin["chan_optres"][0]) if "chan_optres" in basin else 0)
         self.on_device = True
