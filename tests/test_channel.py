@@ -59,7 +59,7 @@ def test_partition_solver_matches_the_reference_order_solver(built):
     PD = C.POINTER(C.c_double)
     L.hc_chan_solve.argtypes = [C.c_int, PD, PD, PD, PD, PD, PD, C.POINTER(C.c_int)]
     rng = np.random.default_rng(7)
-    worst = 0.0
+    worst, seen_parts = 0.0, set()
     for n in (2, 3, 11, 12, 23, 24, 25, 100, 383, 384, 385, 1000, 3163):
         for kind in ("jacobian", "random", "dominant"):
             if kind == "jacobian":
@@ -89,6 +89,7 @@ def test_partition_solver_matches_the_reference_order_solver(built):
             e_ref, e_part = np.abs(xr - x).max() / scale, np.abs(xp - x).max() / scale
             tol = 1e-9 if kind != "random" else 1e-6        # random systems can be badly conditioned
             assert e_ref <= tol and e_part <= tol, (n, kind, parts.value, e_ref, e_part)
-            assert parts.value == min(32, max(1, n // 12))
+            assert 1 <= parts.value <= 32 and (parts.value == 1 or n // parts.value >= 12)
+            seen_parts.add(parts.value)
             worst = max(worst, e_part)
-    assert worst > 0.0
+    assert worst > 0.0 and max(seen_parts) >= 13 and 1 in seen_parts and 2 in seen_parts

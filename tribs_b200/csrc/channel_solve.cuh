@@ -76,8 +76,13 @@ CHAN_FN inline void chan_band_back(const double *R1, const double *A2, const dou
 constexpr int kChanMaxParts = 32;
 constexpr int kChanMinChunk = 12;      // rows per chunk below which fewer chunks are used
 
+// Chunks against interface unknowns: P = sqrt(N / 17). Measured on 3 163 rows (profiles/r02_channel.md): 218 k cycles per
+// solve at P = 13 (this rule), 241 k at P = 18, 232 k at P = 32 - a shallow optimum.
 CHAN_FN inline int chan_part_count(int N) {
-  int P = N / kChanMinChunk;
+  int P = 1;
+  while ((P + 1) * (P + 1) * 17 <= N) P++;
+  const int cap = N / kChanMinChunk;
+  if (P > cap) P = cap;
   return P < 1 ? 1 : (P > kChanMaxParts ? kChanMaxParts : P);
 }
 // chunk p covers rows first .. last (1-based, inclusive)
