@@ -13,7 +13,7 @@
 // Layout: one 1024-thread block. The work is a chain (steps x reaches in list order x Newton iterations x a pivoted
 // banded LU), a few thousand unknowns per reach: everything element-wise (function values with their x^(5/3), the
 // Jacobian, the trial levels of the line search, maxima) is spread over the block; the pivoted LU of the Newton step is cut
-// into up to 32 chunks eliminated side by side on the lanes of one warp plus a small interface system (channel_solve.cuh:
+// into chunks eliminated side by side on the lanes of one warp plus a small interface system (channel_solve.cuh:
 // the reference's single chain of N rows costs ~420 cycles per row on this GPU); the sums of the line search (|F|^2, p.p,
 // grad.p) are added up by one warp each in a fixed order (chan_warp_sum). FP64 throughout; differs from the reference through
 // the library's pow() and through the order of operations of the linear solve and of those sums (1e-15 relative).
