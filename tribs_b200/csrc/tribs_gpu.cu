@@ -284,8 +284,14 @@ sat_prepare_kernel(StaticView s, DynView d, double *wt_elev, double *transm, int
   sat_prepare_cell(s, d.f[TRIBS_F_NwtOld], i, wt_elev, transm);
 }
 
+// 8 blocks of 128 threads per SM = 64 registers per thread (124 without the bound): the kernel waits for its neighbour
+// gathers, more resident warps hide more of that. 1M-cell valley, per groundwater step (prepare + cells): 1.01 ms unbounded,
+// 0.88 ms at 6 blocks (80 registers), 0.83 ms at 8 (tools/sat_ab.py).
+#ifndef TRIBS_SAT_MIN_BLOCKS
+#define TRIBS_SAT_MIN_BLOCKS 8
+#endif
 template <int MAXC>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, (MAXC <= 16 ? TRIBS_SAT_MIN_BLOCKS : 1))   // the wide-degree variants would spill
 sat_cells_kernel(StaticView s, DynView d, ModelConst m, StepConst t, const double *__restrict__ wt_elev,
                  const double *__restrict__ transm, int n_pad, double *tile_sums, int32_t *flags,
                  const double *__restrict__ globals) {
