@@ -93,3 +93,48 @@ def test_partition_solver_matches_the_reference_order_solver(built):
             seen_parts.add(parts.value)
             worst = max(worst, e_part)
     assert worst > 0.0 and max(seen_parts) >= 13 and 1 in seen_parts and 2 in seen_parts
+
+
+def test_oracle_channel_router_uniform_width_against_a_live_reference_run():
+    """CHANNELWIDTHCOEFF <= 0 makes tKinemat use CHANNELWIDTH for every node (tKinemat.cpp:44-47, 1227-1228): the branch the
+    golden basins (geomorphic widths) do not take. tInputFile::ReadItem matches keywords by prefix
+    (tInputFile.cpp:85), so CHANNELWIDTH has to come first in the deck for the reference to read it at all. Live run of
+    the reference, every step, bit for bit."""
+    import os
+    import re
+    import subprocess
+    import tempfile
+    from refrun import HARNESS, have_harness, spec_for
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    from oracle.pyoracle import OracleChannel
+    from tribs_b200.synth import write_basin
+    from tribs_b200.trb import read_trb
+    steps = 240
+    spec = spec_for("shallow", 14, runtime_h=steps * 0.0625 + 1, tributary_every=5, seed=3,
+                    extra={"CHANNELWIDTHCOEFF": 0.0, "CHANNELWIDTH": 4.0})
+    d = tempfile.mkdtemp(prefix="tribs_chanw_")
+    write_basin(spec, d)
+    inp = os.path.join(d, "basin.in")
+    txt = open(inp).read()
+    blocks = {k: re.search(rf"^{k}:[^\n]*\n[^\n]*\n", txt, re.M).group(0) for k in ("CHANNELWIDTHCOEFF", "CHANNELWIDTH")}
+    txt = txt.replace(blocks["CHANNELWIDTH"], "").replace(blocks["CHANNELWIDTHCOEFF"], blocks["CHANNELWIDTH"] + blocks["CHANNELWIDTHCOEFF"])
+    open(inp, "w").write(txt)
+    r = subprocess.run([HARNESS, "basin.in", "-K", "--out", d, "--snap-from", "1", "--snap-to", str(steps), "--snap-every", "1",
+                        "--phases", "r"], cwd=d, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-1500:] + r.stderr[-1500:]
+    basin, snaps = read_trb(os.path.join(d, "basin.trb")), read_trb(os.path.join(d, "steps.trb"))
+    basin["_spec_pmean"], basin["_spec_stdur"] = np.array([spec.pmean]), np.array([spec.stdur])
+    basin["_spec_istdur"], basin["_spec_evap"] = np.array([spec.istdur]), np.array([spec.inject_evap])
+    assert float(basin["chan_width_uniform"][0]) == 4.0 and len(basin["reach_head"]) > 1
+    o, ch = OracleStepper(basin, schedule_for(basin)), OracleChannel(basin)
+    stream = np.nonzero(np.asarray(basin["boundary"]) == 3)[0]
+    peak = 0.0
+    for s in range(1, steps + 1):
+        qout = oracle_step(o, ch)
+        assert qout == snaps[f"s{s}_r_globals"][6], s
+        assert np.array_equal(ch.hlevel[stream], snaps[f"s{s}_r_Hlevel"][stream]), s
+        assert np.array_equal(ch.qstrm[stream], snaps[f"s{s}_r_Qstrm"][stream]), s
+        assert np.array_equal(ch.outlet_hlev, snaps[f"s{s}_r_OutletHlev"]), s
+        peak = max(peak, qout)
+    assert peak > 0.1
