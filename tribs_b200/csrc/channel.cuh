@@ -516,7 +516,7 @@ extern "C" int tribs_gpu_channel_init(tribs_handle_t c, const tribs_channel_t *c
   CK(cudaMemset(nt.ws, 0, (size_t)kChanWsVecs * (max_n + 2) * sizeof(double)));
   CK(cudaMemset(nt.status, 0, 4 * sizeof(int32_t)));
   CK(cudaMemset(nt.cycles, 0, 4 * sizeof(long long)));
-  // the six vectors of the linear solve live in shared memory when the longest reach fits (about 4 700 nodes), else in the
+  // the six vectors of the linear solve live in shared memory when the longest reach fits (kChanSharedRows - 2 = 4 072 nodes), else in the
   // workspace in global memory (slower, same results)
   cs->shared_rows = (max_n + 2 <= kChanSharedRows && !getenv("TRIBS_CHAN_GLOBAL_VECTORS")) ? max_n + 2 : 0;   // the variable: test hook
   cs->smem = ((size_t)kChanInterface + (size_t)kChanSharedVecs * cs->shared_rows) * sizeof(double);
