@@ -121,7 +121,7 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
   double *vec = chan_sm + kChanInterface;
   double *A1 = in_shared ? vec : gA1, *A2 = in_shared ? vec + stride : gA2, *A3 = in_shared ? vec + 2 * stride : gA3,
          *B = in_shared ? vec + 3 * stride : gB, *V = in_shared ? vec + 4 * stride : gV, *W = in_shared ? vec + 5 * stride : gW;
-  double *G = A1, *FS = A2;         // after the solve: gradient and function values where thread 0 sums them
+  double *G = A1, *FS = A2;         // after the solve: gradient and function values where the warp sums read them
   const double rif = cn.roughness;
   const double TOLF = 1.0e-4, TOLX = 1.0e-7, STPMX = 100.0, ALF = 1.0e-4;
   const double fk2 = 5. / 3., fk3 = 2. / 3., fk1 = 5. / 6.;
@@ -228,8 +228,8 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
           const double fold = f;
           // lnsrch
           double tloc = 0.0;
-          // the two sums are independent chains: two threads walk them side by side (a scaled step - never seen on the
-          // test basins - redoes the slope after the scaling, as the reference's order of operations requires)
+          // the two sums are independent: one warp each, side by side (a scaled step - never seen on the test basins -
+          // redoes the slope after the scaling, as the reference's order of operations requires)
           if (tid < 32) {
             const long long t0 = clock64();
             const double sum = chan_warp_sum(m, [&](int i) { const double v = p[i]; return v * v; });
@@ -332,7 +332,7 @@ channel_route_kernel(ChanNet cn, const double *qeff_steps, int n_steps, double *
         cn.qstrm[sl[i]] = (bis[i] * pow(h, (5. / 3.)) * sqrt(siis[i]) / rif);
         cn.velocity[sl[i]] = (pow(h, (2. / 3.)) * sqrt(siis[i]) / rif);
       }
-      __syncthreads();                                              // a one-reach loop: slot of node 0 may equal no outlet, but keep the order
+      __syncthreads();                                              // the outlet's discharge is added after the nodes' values are set
       if (tid == 0) {
         const double h = his[m];
         if (basin_outlet) cn.hlevel[sl[m]] = h;
