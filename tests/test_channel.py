@@ -138,3 +138,25 @@ def test_oracle_channel_router_uniform_width_against_a_live_reference_run():
         assert np.array_equal(ch.outlet_hlev, snaps[f"s{s}_r_OutletHlev"]), s
         peak = max(peak, qout)
     assert peak > 0.1
+
+
+def test_synthetic_basin_carries_the_reference_channel_network_and_aspect():
+    """synthbasin.build_basin's channel keys (one reach from the head of the river to the outlet, geomorphic widths) and
+    cell aspects against what the reference itself sets up when it reads the same basin (OPTMESHINPUT 9): the inputs of
+    tribs_gpu_channel_init and of kernel (1) on the bench basins."""
+    from refrun import have_harness, run_reference_meshb
+    if not have_harness():
+        pytest.skip("oracle/_ref/tribs_ref_harness not built")
+    from tribs_b200.channel import channel_network
+    from tribs_b200.synthbasin import build_basin
+    ref, _, _ = run_reference_meshb(60, "metday", 1.0)
+    mine = build_basin(60, 60, seed=1, runtime_h=1.0, gw_depth_mm=1500.0)
+    for k in ("reach_head", "reach_outlet", "reach_nnodes", "outlet_chan_width", "chan_roughness", "chan_width_uniform",
+              "chan_percolation", "chan_optres"):
+        assert np.array_equal(np.asarray(mine[k]), np.asarray(ref[k])), k
+    stream = np.asarray(ref["boundary"]) == 3
+    assert np.array_equal(np.asarray(mine["chan_width"])[stream], np.asarray(ref["chan_width"])[stream])
+    a, b = channel_network(mine), channel_network(ref)
+    for k in ("off", "node", "width", "length", "slope"):
+        assert np.array_equal(a[k], b[k]), k
+    assert np.abs(np.asarray(mine["aspect"]) - np.asarray(ref["aspect"])).max() <= 4e-15      # numpy's arccos against libm's
